@@ -1,0 +1,397 @@
+"""ctypes bindings of the CPU oracle (oracle/_build/libsdoracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "libsdoracle.so")
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+    return LIB_PATH
+
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class Cpx(C.Structure):
+    _fields_ = [("re", C.c_float), ("im", C.c_float)]
+
+
+class Ncqo(C.Structure):
+    _fields_ = [("phi", C.c_float), ("omega", C.c_float)]
+
+
+class FftPlan(C.Structure):
+    _fields_ = [("n", C.c_uint), ("log2n", C.c_uint), ("tw_re", c_float_p), ("tw_im", c_float_p),
+                ("rev", C.POINTER(C.c_uint))]
+
+
+class Filt(C.Structure):
+    _fields_ = [("nb", C.c_uint), ("na", C.c_uint), ("b", c_float_p), ("a", c_float_p),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("xp", C.c_uint), ("yp", C.c_uint),
+                ("gain", C.c_float)]
+
+
+class AgcParams(C.Structure):
+    _fields_ = [("threshold", C.c_float), ("slope_factor", C.c_float), ("hang_max", C.c_uint),
+                ("delay_line_size", C.c_uint), ("mag_history_size", C.c_uint),
+                ("fast_rise_t", C.c_float), ("fast_fall_t", C.c_float), ("slow_rise_t", C.c_float),
+                ("slow_fall_t", C.c_float)]
+
+
+class Agc(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("knee", C.c_float), ("gain_slope", C.c_float),
+                ("fixed_gain", C.c_float), ("hang_max", C.c_uint), ("hang_n", C.c_uint),
+                ("fast_alpha_rise", C.c_float), ("fast_alpha_fall", C.c_float),
+                ("slow_alpha_rise", C.c_float), ("slow_alpha_fall", C.c_float),
+                ("fast_level", C.c_float), ("slow_level", C.c_float), ("peak", C.c_float),
+                ("delay_line_size", C.c_uint), ("delay_line_ptr", C.c_uint),
+                ("mag_history_size", C.c_uint), ("mag_history_ptr", C.c_uint),
+                ("delay_line", C.c_void_p), ("mag_history", C.c_void_p)]
+
+
+class Pll(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("ncqo", Ncqo)]
+
+
+class Costas(C.Structure):
+    _fields_ = [("kind", C.c_int), ("a", C.c_float), ("b", C.c_float), ("y_alpha", C.c_float),
+                ("gain", C.c_float), ("lock", C.c_float), ("y", Cpx), ("z", Cpx), ("ncqo", Ncqo),
+                ("af", Filt)]
+
+
+class Clock(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("bnor", C.c_float), ("bmin", C.c_float),
+                ("bmax", C.c_float), ("phi", C.c_float), ("gain", C.c_float), ("e", C.c_float),
+                ("halfcycle", C.c_int), ("x", Cpx * 3), ("prev", Cpx)]
+
+
+class Sampler(C.Structure):
+    _fields_ = [("bnor", C.c_float), ("period", C.c_float), ("phase", C.c_float),
+                ("phase0_rel", C.c_float), ("phase0", C.c_float), ("prev", Cpx)]
+
+
+class Decider(C.Structure):
+    _fields_ = [("mode", C.c_int), ("bps", C.c_uint), ("intervals", C.c_uint), ("min", C.c_float),
+                ("max", C.c_float), ("h", C.c_float)]
+
+
+class InspConfig(C.Structure):
+    _fields_ = [("insp_class", C.c_int), ("fs", C.c_float), ("agc_enabled", C.c_int),
+                ("agc_gain_db", C.c_float), ("costas_order", C.c_uint), ("bits_per_symbol", C.c_uint),
+                ("loop_bw", C.c_float), ("offset", C.c_float), ("fsk_phase", C.c_float),
+                ("fsk_quad_demod", C.c_int), ("ask_use_pll", C.c_int), ("ask_channel", C.c_uint),
+                ("mf_type", C.c_uint), ("mf_rolloff", C.c_float), ("clock_type", C.c_uint),
+                ("baud", C.c_float), ("clock_gain", C.c_float), ("clock_phase", C.c_float),
+                ("clock_running", C.c_int), ("audio_cutoff", C.c_float), ("audio_volume", C.c_float),
+                ("audio_squelch_level", C.c_float), ("agc_ts", C.c_float),
+                ("audio_sample_rate", C.c_uint), ("audio_demod", C.c_uint), ("audio_squelch", C.c_int)]
+
+
+class AnChannel(C.Structure):
+    _fields_ = [("f0", C.c_float), ("bw", C.c_float), ("guard", C.c_float), ("precise", C.c_int),
+                ("insp", InspConfig)]
+
+
+class AnParams(C.Structure):
+    _fields_ = [("psd_size", C.c_uint), ("psd_window", C.c_int), ("st_window_size", C.c_uint),
+                ("n_channels", C.c_uint), ("channels", C.POINTER(AnChannel))]
+
+
+class AnCounts(C.Structure):
+    _fields_ = [("n_frames", C.c_size_t), ("n_chan", C.POINTER(C.c_size_t)),
+                ("n_sym", C.POINTER(C.c_size_t))]
+
+
+class StChannelParams(C.Structure):
+    pass
+
+
+ON_DATA = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Cpx), C.c_size_t)
+StChannelParams._fields_ = [("f0", C.c_float), ("delta_f", C.c_float), ("bw", C.c_float),
+                            ("guard", C.c_float), ("precise", C.c_int), ("privdata", C.c_void_p),
+                            ("on_data", ON_DATA)]
+
+
+class SpectrumView(C.Structure):
+    _fields_ = [("freq_min", C.c_double), ("freq_max", C.c_double), ("freq_range", C.c_double),
+                ("fft_bandwidth", C.c_double), ("fft_rel_bw", C.c_float), ("spectrum_size", C.c_uint),
+                ("psd", c_float_p), ("psd_accum", c_float_p), ("psd_count", c_float_p)]
+
+
+WINDOW = {"none": 0, "hamming": 1, "hann": 2, "flat_top": 3, "blackmann_harris": 4}
+INSP = {"psk": 0, "fsk": 1, "ask": 2, "audio": 3, "raw": 4}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(LIB_PATH)
+        L.sdo_atan2f.restype = C.c_float
+        L.sdo_atan2f.argtypes = [C.c_float, C.c_float]
+        L.sdo_log10f.restype = C.c_float
+        L.sdo_log10f.argtypes = [C.c_float]
+        L.sdo_exp10f.restype = C.c_float
+        L.sdo_exp10f.argtypes = [C.c_float]
+        L.sdo_sincosf.argtypes = [C.c_float, c_float_p, c_float_p]
+        L.sdo_ncqo_read.restype = Cpx
+        L.sdo_agc_feed.restype = Cpx
+        L.sdo_agc_feed.argtypes = [C.c_void_p, Cpx]
+        L.sdo_costas_feed.restype = Cpx
+        L.sdo_costas_feed.argtypes = [C.c_void_p, Cpx]
+        L.sdo_pll_track.restype = Cpx
+        L.sdo_pll_track.argtypes = [C.c_void_p, Cpx]
+        L.sdo_filt_feed.restype = Cpx
+        L.sdo_filt_feed.argtypes = [C.c_void_p, Cpx]
+        L.sdo_clock_feed.argtypes = [C.c_void_p, Cpx, C.c_void_p]
+        L.sdo_sampler_feed.argtypes = [C.c_void_p, Cpx, C.c_void_p]
+        L.sdo_ncqo_init.argtypes = [C.c_void_p, C.c_float]
+        L.sdo_ncqo_set_phase.argtypes = [C.c_void_p, C.c_float]
+        L.sdo_pll_init.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.sdo_costas_init.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint, C.c_float]
+        L.sdo_clock_init.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.sdo_sampler_init.argtypes = [C.c_void_p, C.c_float]
+        L.sdo_sampler_set_phase.argtypes = [C.c_void_p, C.c_float]
+        L.sdo_decider_init.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_float]
+        L.sdo_decider_decide.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.sdo_taps_rrc.argtypes = [c_float_p, C.c_uint, C.c_float, C.c_float]
+        L.sdo_taps_brickwall_lp.argtypes = [c_float_p, C.c_uint, C.c_float]
+        L.sdo_butter_lp.argtypes = [C.c_uint, C.c_float, c_float_p, c_float_p]
+        L.sdo_mf_span.restype = C.c_uint
+        L.sdo_mf_span.argtypes = [C.c_float]
+        L.sdo_agc_params_from_tau.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.sdo_window_fill.argtypes = [c_float_p, C.c_uint, C.c_int]
+        L.sdo_fft_plan_init.argtypes = [C.c_void_p, C.c_uint]
+        L.sdo_fft_exec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sdo_psd_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sdo_psd_shift_db.argtypes = [C.c_void_p, C.c_uint]
+        L.sdo_averager_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_float]
+        L.sdo_quad_demod.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.sdo_carrier_xlate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.sdo_specttuner_new.restype = C.c_void_p
+        L.sdo_specttuner_new.argtypes = [C.c_uint]
+        L.sdo_specttuner_destroy.argtypes = [C.c_void_p]
+        L.sdo_specttuner_open_channel.restype = C.c_void_p
+        L.sdo_specttuner_open_channel.argtypes = [C.c_void_p, C.c_void_p]
+        L.sdo_specttuner_feed_bulk.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.sdo_st_channel_geometry.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float,
+                                              C.POINTER(C.c_uint), C.POINTER(C.c_uint),
+                                              C.POINTER(C.c_uint)]
+        L.sdo_st_filter_response.argtypes = [C.c_uint, C.c_uint, c_float_p]
+        L.sdo_insp_config_default.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.sdo_inspector_new.restype = C.c_void_p
+        L.sdo_inspector_new.argtypes = [C.c_void_p]
+        L.sdo_inspector_destroy.argtypes = [C.c_void_p]
+        L.sdo_inspector_feed.restype = C.c_size_t
+        L.sdo_inspector_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.sdo_inspector_decider.argtypes = [C.c_void_p, C.c_void_p]
+        L.sdo_analyzer_new.restype = C.c_void_p
+        L.sdo_analyzer_new.argtypes = [C.c_void_p]
+        L.sdo_analyzer_destroy.argtypes = [C.c_void_p]
+        L.sdo_analyzer_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]
+        L.sdo_baseline_run.restype = C.c_double
+        L.sdo_baseline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                       C.POINTER(C.c_uint64)]
+        L.sdo_sview_init.argtypes = [C.c_void_p]
+        L.sdo_sview_free.argtypes = [C.c_void_p]
+        L.sdo_sview_set_range.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.sdo_sview_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int]
+        L.sdo_sview_interpolate.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _c64(a):
+    a = np.ascontiguousarray(a, dtype=np.complex64)
+    return a
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------------------------
+# convenient numpy-level wrappers
+# ----------------------------------------------------------------------------------------------
+def sincos(x):
+    L = lib()
+    x = np.asarray(x, np.float32)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    sv, cv = C.c_float(), C.c_float()
+    for i, v in enumerate(x.ravel()):
+        L.sdo_sincosf(C.c_float(float(v)), C.byref(sv), C.byref(cv))
+        s.ravel()[i] = sv.value
+        c.ravel()[i] = cv.value
+    return s, c
+
+
+def vec1(fn, x):
+    x = np.asarray(x, np.float32)
+    out = np.empty_like(x)
+    for i, v in enumerate(x.ravel()):
+        out.ravel()[i] = fn(C.c_float(float(v)))
+    return out
+
+
+def fft(x, sign=-1):
+    L = lib()
+    x = _c64(x)
+    p = FftPlan()
+    assert L.sdo_fft_plan_init(C.byref(p), len(x)) == 0
+    out = np.empty_like(x)
+    L.sdo_fft_exec(C.byref(p), ptr(x), ptr(out), sign)
+    L.sdo_fft_plan_free(C.byref(p))
+    return out
+
+
+def window(n, kind):
+    w = np.empty(n, np.float32)
+    lib().sdo_window_fill(w.ctypes.data_as(c_float_p), n, WINDOW[kind] if isinstance(kind, str) else kind)
+    return w
+
+
+def psd_frames(x, n, kind):
+    """PSD of consecutive non-overlapping n-sample frames of x -> [frames, n] float32."""
+    L = lib()
+    x = _c64(x)
+    p = FftPlan()
+    assert L.sdo_fft_plan_init(C.byref(p), n) == 0
+    w = window(n, kind)
+    nf = len(x) // n
+    out = np.empty((nf, n), np.float32)
+    scratch = np.empty(2 * n, np.complex64)
+    for f in range(nf):
+        L.sdo_psd_frame(C.byref(p), ptr(w), ptr(x[f * n:(f + 1) * n]), ptr(out[f]), ptr(scratch))
+    L.sdo_fft_plan_free(C.byref(p))
+    return out
+
+
+def insp_config(cls, fs, **kw):
+    c = InspConfig()
+    lib().sdo_insp_config_default(C.byref(c), INSP[cls], C.c_float(fs))
+    for k, v in kw.items():
+        assert hasattr(c, k), k
+        setattr(c, k, v)
+    return c
+
+
+def inspector_run(cfg, x, chunk=None):
+    """Run one inspector over channel-rate samples x; returns (soft complex64, hard uint8)."""
+    L = lib()
+    x = _c64(x)
+    h = L.sdo_inspector_new(C.byref(cfg))
+    out = np.empty(len(x) + 16, np.complex64)
+    k = 0
+    step = chunk or len(x)
+    for s in range(0, len(x), step):
+        seg = x[s:s + step]
+        k += L.sdo_inspector_feed(h, ptr(seg), len(seg), ptr(out[k:]), len(out) - k)
+    L.sdo_inspector_destroy(h)
+    soft = out[:k].copy()
+    d = Decider()
+    L.sdo_inspector_decider(C.byref(cfg), C.byref(d))
+    hard = np.empty(k, np.uint8)
+    if k:
+        L.sdo_decider_decide(C.byref(d), ptr(soft), ptr(hard), k)
+    return soft, hard
+
+
+def specttuner_run(x, window_size, channels, chunk=None):
+    """channels: list of dict(f0, bw, guard, precise). Returns list of complex64 arrays."""
+    L = lib()
+    x = _c64(x)
+    st = L.sdo_specttuner_new(window_size)
+    outs = [[] for _ in channels]
+    cbs = []
+    for i, ch in enumerate(channels):
+        def mk(i):
+            def cb(chp, priv, data, n):
+                outs[i].append(np.ctypeslib.as_array(C.cast(data, c_float_p), shape=(2 * n,)).copy()
+                               .view(np.complex64))
+                return 1
+            return ON_DATA(cb)
+        cb = mk(i)
+        cbs.append(cb)
+        p = StChannelParams(f0=ch["f0"], delta_f=0.0, bw=ch["bw"], guard=ch.get("guard", 1.0),
+                            precise=int(ch.get("precise", 0)), privdata=None, on_data=cb)
+        assert L.sdo_specttuner_open_channel(st, C.byref(p)), "open_channel failed"
+    step = chunk or len(x)
+    for s in range(0, len(x), step):
+        seg = x[s:s + step]
+        assert L.sdo_specttuner_feed_bulk(st, ptr(seg), len(seg))
+    L.sdo_specttuner_destroy(st)
+    return [np.concatenate(o) if o else np.zeros(0, np.complex64) for o in outs]
+
+
+def channel_geometry(window_size, f0, bw, guard):
+    c, s, w = C.c_uint(), C.c_uint(), C.c_uint()
+    lib().sdo_st_channel_geometry(window_size, f0, bw, guard, C.byref(c), C.byref(s), C.byref(w))
+    return c.value, s.value, w.value
+
+
+def make_an_params(psd_size, psd_window, channels, st_window_size=0):
+    """channels: list of (f0, bw, guard, precise, InspConfig)."""
+    arr = (AnChannel * max(1, len(channels)))()
+    for i, (f0, bw, guard, precise, ic) in enumerate(channels):
+        arr[i].f0, arr[i].bw, arr[i].guard, arr[i].precise, arr[i].insp = f0, bw, guard, int(precise), ic
+    p = AnParams(psd_size=psd_size, psd_window=WINDOW[psd_window] if isinstance(psd_window, str) else psd_window,
+                 st_window_size=st_window_size, n_channels=len(channels), channels=arr)
+    p._keep = arr
+    return p
+
+
+def analyzer_run(params, x, chunk=None, want_chan=True):
+    """Full oracle pass. Returns dict(psd [F,N], chan [list], soft [list], hard [list])."""
+    L = lib()
+    x = _c64(x)
+    K = params.n_channels
+    N = params.psd_size
+    a = L.sdo_analyzer_new(C.byref(params))
+    assert a
+    step = chunk or len(x)
+    psd_l, chan_l, soft_l, hard_l = [], [[] for _ in range(K)], [[] for _ in range(K)], [[] for _ in range(K)]
+    for s in range(0, len(x), step):
+        seg = x[s:s + step]
+        n = len(seg)
+        nf = n // N + 2
+        psd = np.empty((nf, N), np.float32)
+        chan = [np.empty(n + 16, np.complex64) for _ in range(K)]
+        soft = [np.empty(n + 16, np.complex64) for _ in range(K)]
+        hard = [np.empty(n + 16, np.uint8) for _ in range(K)]
+        pp = lambda lst: (C.c_void_p * max(1, K))(*[ptr(v) for v in lst]) if K else None
+        nch = (C.c_size_t * max(1, K))()
+        nsy = (C.c_size_t * max(1, K))()
+        cnt = AnCounts(0, C.cast(nch, C.POINTER(C.c_size_t)), C.cast(nsy, C.POINTER(C.c_size_t)))
+        rc = L.sdo_analyzer_feed(a, ptr(seg), n, ptr(psd), nf, pp(chan) if want_chan else None, n + 16,
+                                 pp(soft), pp(hard), n + 16, C.byref(cnt))
+        assert rc == 0
+        psd_l.append(psd[:cnt.n_frames].copy())
+        for k in range(K):
+            if want_chan:
+                chan_l[k].append(chan[k][:nch[k]].copy())
+            soft_l[k].append(soft[k][:nsy[k]].copy())
+            hard_l[k].append(hard[k][:nsy[k]].copy())
+    L.sdo_analyzer_destroy(a)
+    cat = lambda l, dt: np.concatenate(l) if l else np.zeros(0, dt)
+    return dict(psd=np.concatenate(psd_l) if psd_l else np.zeros((0, N), np.float32),
+                chan=[cat(c, np.complex64) for c in chan_l],
+                soft=[cat(c, np.complex64) for c in soft_l],
+                hard=[cat(c, np.uint8) for c in hard_l])
