@@ -1,0 +1,185 @@
+/*
+ * sigdigger_b200.h -- C-ABI of libsigdigger_b200.so: the B200-native replacement of the suscan /
+ * sigutils analyzer hot path that BatchDrake/SigDigger drives.
+ *
+ * Plain C, plain pointers and sizes, no CUDA or torch types.  Every entry point names the reference
+ * interface it replaces (file:line under /root/reference).  `const sdb_complex *` has the layout of
+ * SUCOMPLEX (interleaved float32 re, im).  Functions return 0 / a non-negative value on success and -1
+ * on failure (SUBOOL-style callers map that to SU_FALSE; message via sdb_last_error(), which plays
+ * the role of the sigutils log sink, include/Suscan/Logger.h:55).  There is NO CPU fallback: without a
+ * CUDA device sdb_engine_new() fails.
+ */
+#ifndef SIGDIGGER_B200_H
+#define SIGDIGGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float re, im; } sdb_complex;      /* SUCOMPLEX */
+typedef struct sdb_engine sdb_engine_t;             /* one analyzer batch on one GPU */
+
+/* SU_CHANNEL_DETECTOR_WINDOW_* (include/Suscan/AnalyzerParams.h:37-43) */
+enum { SDB_WINDOW_NONE = 0, SDB_WINDOW_HAMMING, SDB_WINDOW_HANN, SDB_WINDOW_FLAT_TOP,
+       SDB_WINDOW_BLACKMANN_HARRIS };
+
+/* inspector classes: "psk" / "fsk" / "ask" (Default/Inspection/InspToolWidget.cpp:932,938,944),
+ * "audio" (Default/Audio/AudioProcessor.cpp:153), "raw" (InspToolWidget.cpp:612) */
+enum { SDB_INSP_PSK = 0, SDB_INSP_FSK = 1, SDB_INSP_ASK = 2, SDB_INSP_AUDIO = 3, SDB_INSP_RAW = 4 };
+
+/* SigDigger's AudioDemod enum + 1 as it goes on the wire (include/SigDiggerHelpers.h:39-45,
+ * Default/Audio/AudioProcessor.cpp:261) */
+enum { SDB_AUDIO_DISABLED = 0, SDB_AUDIO_AM, SDB_AUDIO_FM, SDB_AUDIO_USB, SDB_AUDIO_LSB };
+
+#define SDB_FLAG_PSD_SHIFT_DB 1u  /* fold the GUI's fft-shift + SU_POWER_DB pass
+                                     (Suscan/Messages/PSDMessage.cpp:32-38) into the PSD kernel */
+
+/* Replaces struct suscan_analyzer_params.detector_params.{window_size, window}
+ * (Suscan/AnalyzerParams.cpp:56-66) + the specttuner's sigutils_specttuner_params.window_size
+ * (Tasks/LPFTask.cpp:52). n_streams > 1 batches independent sources through the same plan. */
+typedef struct {
+  uint32_t n_streams;
+  uint32_t psd_size;        /* power of two, 512 .. 2^20 (Default/FFT/FFTWidget.cpp:350-351); 0 = no PSD */
+  int32_t  psd_window;
+  uint32_t st_window_size;  /* channeliser FFT size; 0 = psd_size */
+  uint32_t max_feed;        /* largest per-stream feed, samples */
+  int32_t  device;          /* CUDA ordinal */
+  uint32_t flags;
+} sdb_engine_params;
+
+/* Replaces struct sigutils_specttuner_channel_params {f0, bw, guard, precise}
+ * (Tasks/LPFTask.cpp:63-67); angular units (rad/sample). */
+typedef struct {
+  float   f0, bw, guard;
+  int32_t precise;
+} sdb_channel_params;
+
+typedef struct {
+  uint32_t center, size, width;
+  float    decimation;      /* st_window_size / size */
+} sdb_channel_info;
+
+/* Typed image of the inspector's suscan_config_t key/value bag.  Field <-> key:
+ * agc.enabled, agc.gain (GainControl.cpp:51-60); afc.costas-order, afc.bits-per-symbol, afc.loop-bw,
+ * afc.offset (AfcControl.cpp:54-83); fsk.bits-per-symbol, fsk.phase, fsk.quad-demod
+ * (ToneControl.cpp:59-81); ask.bits-per-symbol, ask.use-pll, ask.loop-bw, ask.offset, ask.channel
+ * (AskControl.cpp:53-77); mf.type, mf.roll-off (MfControl.cpp:56-78); clock.type, clock.baud,
+ * clock.gain, clock.phase, clock.running (ClockRecovery.cpp:59-93); audio.* and agc.ts
+ * (Default/Audio/AudioProcessor.cpp:257-265).  All under Default/GenericInspector/InspectorCtl/. */
+typedef struct {
+  int32_t  insp_class;
+  float    fs;              /* filled by the engine: equivalent channel rate in Hz (= samp_rate / decimation) */
+  int32_t  agc_enabled;
+  float    agc_gain_db;
+  uint32_t costas_order;    /* 0 manual, 1 BPSK, 2 QPSK, 3 8PSK */
+  uint32_t bits_per_symbol;
+  float    loop_bw;         /* Hz */
+  float    offset;          /* Hz */
+  float    fsk_phase;
+  int32_t  fsk_quad_demod;
+  int32_t  ask_use_pll;
+  uint32_t ask_channel;
+  uint32_t mf_type;         /* SUSCAN_INSPECTOR_MATCHED_FILTER_{BYPASS=0, MANUAL=1} */
+  float    mf_rolloff;
+  uint32_t clock_type;      /* SUSCAN_INSPECTOR_BAUDRATE_CONTROL_{MANUAL=0, GARDNER=1} */
+  float    baud, clock_gain, clock_phase;
+  int32_t  clock_running;
+  float    audio_cutoff, audio_volume, audio_squelch_level, agc_ts;
+  uint32_t audio_sample_rate, audio_demod;
+  int32_t  audio_squelch;
+} sdb_inspector_config;
+
+const char *sdb_last_error(void);
+int         sdb_device_count(void);
+
+/* suscan_analyzer_new / suscan_analyzer_destroy (Suscan/Analyzer.cpp:608, :636) */
+sdb_engine_t *sdb_engine_new(const sdb_engine_params *params, double samp_rate);
+void          sdb_engine_destroy(sdb_engine_t *e);
+
+/* su_specttuner_open_channel (Tasks/LPFTask.cpp:69) / suscan_analyzer_open_ex_async
+ * (Suscan/Analyzer.cpp:459-484).  Returns the channel handle (SUHANDLE). */
+int sdb_engine_open_channel(sdb_engine_t *e, const sdb_channel_params *p, sdb_channel_info *info);
+/* suscan_analyzer_set_inspector_config_async (Suscan/Analyzer.cpp:486-495) */
+int sdb_engine_set_inspector(sdb_engine_t *e, int handle, const sdb_inspector_config *cfg);
+/* fills cfg with the class defaults the OPEN message would carry
+ * (Suscan/Messages/InspectorMessage.cpp:28-71 `config`) */
+int sdb_inspector_config_default(sdb_inspector_config *cfg, int insp_class, float fs);
+/* freezes the channel plan and allocates device buffers; required before the first feed */
+int sdb_engine_commit(sdb_engine_t *e);
+
+/* One pass of the hot path over `n` new samples of every stream (the body of suscan's source-worker
+ * loop, SURVEY.md 3.2 HOT LOOP #1 + 3.3 HOT LOOP #2).  n must be a multiple of the PSD size and of
+ * half the channeliser window.  x: stream s starts at x + s * stream_stride.
+ *   _device: x is a device pointer (IQ already resident in HBM); asynchronous.
+ *   _host:   x is host memory (pinned for full speed); copies H2D inside the call; asynchronous. */
+int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *x, size_t stream_stride, size_t n);
+int sdb_engine_feed_host(sdb_engine_t *e, const sdb_complex *x, size_t stream_stride, size_t n);
+int sdb_engine_sync(sdb_engine_t *e);
+
+/* Results of the last feed.  PSD = payload of suscan_analyzer_psd_msg (psd_size, psd_data;
+ * Suscan/Messages/PSDMessage.cpp:26-39): [stream][frame][psd_size] float32, linear power, DC at 0
+ * unless SDB_FLAG_PSD_SHIFT_DB. */
+size_t       sdb_engine_psd_frames(const sdb_engine_t *e);
+const float *sdb_engine_psd_device(const sdb_engine_t *e);
+int          sdb_engine_read_psd(sdb_engine_t *e, float *dst, size_t cap_floats);
+/* channel-rate output of the channeliser (what on_data delivers, Tasks/LPFTask.cpp:28-42) */
+long         sdb_engine_read_channel(sdb_engine_t *e, uint32_t stream, int handle, sdb_complex *dst,
+                                     size_t cap);
+/* inspector output: suscan_analyzer_sample_batch_msg.samples
+ * (include/Suscan/Messages/SamplesMessage.h:33-59) + the GUI's Decider output
+ * (Default/GenericInspector/InspectorUI.cpp:836-846).  Either dst may be NULL. */
+long         sdb_engine_read_symbols(sdb_engine_t *e, uint32_t stream, int handle, sdb_complex *soft,
+                                     uint8_t *hard, size_t cap);
+/* all streams, all channels at once: counts[S*K], soft/hard laid out [S][K][cap] */
+int          sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft,
+                                         uint8_t *hard, size_t cap);
+/* device-side views for zero-copy consumers / benchmarks */
+const uint32_t *sdb_engine_symbol_counts_device(const sdb_engine_t *e);
+size_t          sdb_engine_symbol_capacity(const sdb_engine_t *e);
+
+/* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
+void    *sdb_engine_stream(const sdb_engine_t *e);
+/* kernels launched since engine creation (for bench.py's gpu_launches) */
+uint64_t sdb_engine_launch_count(const sdb_engine_t *e);
+/* average device time (ms) of the named kernel family over the launches since the last reset, measured
+ * with CUDA events on the engine stream; families: "fft_cols", "fft_rows_psd", "fft_rows_chan",
+ * "chan_ifft", "inspector" */
+int      sdb_engine_kernel_time(sdb_engine_t *e, const char *family, double *avg_ms, uint64_t *launches);
+void     sdb_engine_timing(sdb_engine_t *e, int enable);
+
+/* ------------------------------------------------------------------------------------------------
+ * Offline Tasks/ primitives over a whole capture buffer (host pointers; one GPU chain each; the
+ * batched forms take `batch` independent buffers of n samples, contiguous).
+ * ---------------------------------------------------------------------------------------------- */
+/* CarrierXlator: su_ncqo_init(-relFreq), su_ncqo_set_phase(-phase), dst = src * su_ncqo_read()
+ * (Tasks/CarrierXlator.cpp:36-37,57-60) */
+int sdb_task_carrier_xlate(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch,
+                           float rel_freq, float phase);
+/* QuadDemodTask (Tasks/QuadDemodTask.cpp:44-60) */
+int sdb_task_quad_demod(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch);
+/* CostasRecoveryTask: su_costas_init(kind, 0, 1/tau, 3, loopbw) + su_costas_feed loop
+ * (Tasks/CostasRecoveryTask.cpp:36-41,58-61) */
+int sdb_task_costas(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, int kind,
+                    float tau, float loop_bw);
+/* PLLSyncTask: su_pll_init(0, bw) + su_pll_track loop (Tasks/PLLSyncTask.cpp:36,53-56) */
+int sdb_task_pll(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
+/* AGCTask: su_agc_init with tau fractions + su_agc_feed loop (Tasks/AGCTask.cpp:41-53,70-73) */
+int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float tau);
+/* LPFTask: su_specttuner low-pass with guard = 2 pi / bw, output length == input length
+ * (Tasks/LPFTask.cpp:52-69,83-87,104-107) */
+int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
+
+/* Offline inspector over captured channel-rate buffers (the block-wise CPU loops the GUI's TimeWindow
+ * launches, Components/TimeWindow.cpp:1571-2183; sampler + decider of Tasks/WaveSampler.cpp:188-205,
+ * 316-317): `batch` buffers of n samples -> soft [batch][cap], hard [batch][cap], counts [batch].
+ * cfg->fs must be the buffers' sample rate. */
+long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_complex *src, size_t n, size_t batch,
+                        sdb_complex *soft, uint8_t *hard, uint32_t *counts, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

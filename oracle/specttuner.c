@@ -31,7 +31,7 @@ void sdo_st_channel_geometry(unsigned window_size, float f0, float bw, float gua
   double c = 2.0 * floor((double) f0 / (4.0 * SDO_PI) * N + 0.5);
   double m = ceil(krel * N - 1e-3);
   unsigned msz, sz = 1, w;
-  if (m < 2.0) m = 2.0;
+  if (m < 4.0) m = 4.0;
   if (m > N) m = N;
   msz = (unsigned) m;
   while (sz < msz) sz <<= 1;

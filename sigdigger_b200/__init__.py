@@ -1,0 +1,300 @@
+"""sigdigger_b200 -- Python host mirror of the C-ABI in include/sigdigger_b200.h.
+
+The product is libsigdigger_b200.so (hand-written CUDA for sm_100a + a C++ host runtime); this module
+is a thin ctypes binding used by the tests and the benchmark.  It fails loudly when the native library
+is missing or no CUDA device is present: there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsigdigger_b200.so")
+
+WINDOW = {"none": 0, "hamming": 1, "hann": 2, "flat_top": 3, "blackmann_harris": 4}
+INSP = {"psk": 0, "fsk": 1, "ask": 2, "audio": 3, "raw": 4}
+AUDIO = {"disabled": 0, "am": 1, "fm": 2, "usb": 3, "lsb": 4}
+FLAG_PSD_SHIFT_DB = 1
+
+
+class EngineParams(C.Structure):
+    _fields_ = [("n_streams", C.c_uint32), ("psd_size", C.c_uint32), ("psd_window", C.c_int32),
+                ("st_window_size", C.c_uint32), ("max_feed", C.c_uint32), ("device", C.c_int32),
+                ("flags", C.c_uint32)]
+
+
+class ChannelParams(C.Structure):
+    _fields_ = [("f0", C.c_float), ("bw", C.c_float), ("guard", C.c_float), ("precise", C.c_int32)]
+
+
+class ChannelInfo(C.Structure):
+    _fields_ = [("center", C.c_uint32), ("size", C.c_uint32), ("width", C.c_uint32),
+                ("decimation", C.c_float)]
+
+
+class InspectorConfig(C.Structure):
+    _fields_ = [("insp_class", C.c_int32), ("fs", C.c_float), ("agc_enabled", C.c_int32),
+                ("agc_gain_db", C.c_float), ("costas_order", C.c_uint32), ("bits_per_symbol", C.c_uint32),
+                ("loop_bw", C.c_float), ("offset", C.c_float), ("fsk_phase", C.c_float),
+                ("fsk_quad_demod", C.c_int32), ("ask_use_pll", C.c_int32), ("ask_channel", C.c_uint32),
+                ("mf_type", C.c_uint32), ("mf_rolloff", C.c_float), ("clock_type", C.c_uint32),
+                ("baud", C.c_float), ("clock_gain", C.c_float), ("clock_phase", C.c_float),
+                ("clock_running", C.c_int32), ("audio_cutoff", C.c_float), ("audio_volume", C.c_float),
+                ("audio_squelch_level", C.c_float), ("agc_ts", C.c_float),
+                ("audio_sample_rate", C.c_uint32), ("audio_demod", C.c_uint32), ("audio_squelch", C.c_int32)]
+
+
+_lib = None
+
+_PROTOS = {
+    "sdb_last_error": (C.c_char_p, []),
+    "sdb_device_count": (C.c_int, []),
+    "sdb_engine_new": (C.c_void_p, [C.c_void_p, C.c_double]),
+    "sdb_engine_destroy": (None, [C.c_void_p]),
+    "sdb_engine_open_channel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdb_engine_set_inspector": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "sdb_inspector_config_default": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    "sdb_engine_commit": (C.c_int, [C.c_void_p]),
+    "sdb_engine_feed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "sdb_engine_feed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "sdb_engine_sync": (C.c_int, [C.c_void_p]),
+    "sdb_engine_psd_frames": (C.c_size_t, [C.c_void_p]),
+    "sdb_engine_psd_device": (C.c_void_p, [C.c_void_p]),
+    "sdb_engine_read_psd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_read_channel": (C.c_long, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]),
+    "sdb_engine_read_symbols": (C.c_long, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_read_all_symbols": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_symbol_counts_device": (C.c_void_p, [C.c_void_p]),
+    "sdb_engine_symbol_capacity": (C.c_size_t, [C.c_void_p]),
+    "sdb_engine_stream": (C.c_void_p, [C.c_void_p]),
+    "sdb_engine_launch_count": (C.c_uint64, [C.c_void_p]),
+    "sdb_engine_kernel_time": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "sdb_engine_timing": (None, [C.c_void_p, C.c_int]),
+    "sdb_task_carrier_xlate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_float]),
+    "sdb_task_quad_demod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "sdb_task_costas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_float]),
+    "sdb_task_pll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_task_agc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_task_lpf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_task_inspector": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_size_t]),
+}
+
+EXPORTED_SYMBOLS = sorted(_PROTOS)
+
+
+def load_library():
+    """dlopen the native library and bind every symbol the header declares. No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("native library %s missing: run `python __graft_entry__.py` (build())" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)      # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return load_library().sdb_last_error().decode()
+
+
+def device_count():
+    return load_library().sdb_device_count()
+
+
+class SdbError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc is None or rc < 0:
+        raise SdbError(last_error())
+    return rc
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class Engine:
+    """Batch analyzer engine: main PSD + channeliser + inspectors over S streams on one GPU."""
+
+    def __init__(self, n_streams=1, psd_size=65536, psd_window="blackmann_harris", st_window_size=0,
+                 max_feed=0, samp_rate=1.0, device=0, flags=0):
+        L = load_library()
+        p = EngineParams(n_streams, psd_size, WINDOW[psd_window] if isinstance(psd_window, str) else psd_window,
+                         st_window_size, max_feed, device, flags)
+        self._L = L
+        self.n_streams, self.psd_size, self.samp_rate = n_streams, psd_size, samp_rate
+        self.st_window_size = st_window_size or psd_size
+        self.device = device
+        self._h = L.sdb_engine_new(C.byref(p), samp_rate)
+        if not self._h:
+            raise SdbError(last_error())
+        self._info = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def open_channel(self, f0, bw, guard=1.0, precise=False):
+        info = ChannelInfo()
+        p = ChannelParams(f0, bw, guard, int(precise))
+        h = _check(self._L.sdb_engine_open_channel(self._h, C.byref(p), C.byref(info)))
+        self._info.append(info)
+        return h
+
+    def channel_info(self, h):
+        return self._info[h]
+
+    def channel_rate(self, h):
+        return self.samp_rate * self._info[h].size / self.st_window_size
+
+    def set_inspector(self, h, cls, **kw):
+        cfg = InspectorConfig()
+        _check(self._L.sdb_inspector_config_default(C.byref(cfg), INSP[cls], self.channel_rate(h)))
+        for k, v in kw.items():
+            if not hasattr(cfg, k):
+                raise KeyError(k)
+            setattr(cfg, k, v)
+        _check(self._L.sdb_engine_set_inspector(self._h, h, C.byref(cfg)))
+
+    def commit(self):
+        _check(self._L.sdb_engine_commit(self._h))
+
+    def feed(self, x, sync=True):
+        """x: [S, n] complex64 numpy array (host path, copies H2D) or torch cuda tensor (device path)."""
+        if _is_torch(x):
+            assert x.is_cuda and x.dim() == 2 and x.shape[0] == self.n_streams
+            assert x.stride(1) == 1
+            _check(self._L.sdb_engine_feed_device(self._h, x.data_ptr(), x.stride(0), x.shape[1]))
+        else:
+            x = np.ascontiguousarray(x, dtype=np.complex64)
+            assert x.ndim == 2 and x.shape[0] == self.n_streams
+            self._keep = x
+            _check(self._L.sdb_engine_feed_host(self._h, x.ctypes.data, x.shape[1], x.shape[1]))
+        if sync:
+            self.sync()
+
+    def feed_host_ptr(self, ptr, stride, n):
+        _check(self._L.sdb_engine_feed_host(self._h, ptr, stride, n))
+
+    def feed_device_ptr(self, ptr, stride, n):
+        _check(self._L.sdb_engine_feed_device(self._h, ptr, stride, n))
+
+    def sync(self):
+        _check(self._L.sdb_engine_sync(self._h))
+
+    def read_psd(self, out=None):
+        f = self._L.sdb_engine_psd_frames(self._h)
+        if out is None:
+            out = np.empty((self.n_streams, f, self.psd_size), np.float32)
+        _check(self._L.sdb_engine_read_psd(self._h, out.ctypes.data, out.size))
+        return out
+
+    def read_channel(self, stream, h, cap=None):
+        cap = cap or (1 << 24)
+        out = np.empty(cap, np.complex64)
+        n = _check(self._L.sdb_engine_read_channel(self._h, stream, h, out.ctypes.data, cap))
+        return out[:n].copy()
+
+    def read_symbols(self, stream, h):
+        cap = self._L.sdb_engine_symbol_capacity(self._h)
+        soft = np.empty(cap, np.complex64)
+        hard = np.empty(cap, np.uint8)
+        n = _check(self._L.sdb_engine_read_symbols(self._h, stream, h, soft.ctypes.data, hard.ctypes.data, cap))
+        return soft[:n].copy(), hard[:n].copy()
+
+    def read_all_symbols(self, counts, soft, hard, cap):
+        _check(self._L.sdb_engine_read_all_symbols(self._h, counts.ctypes.data,
+                                                   soft.ctypes.data if soft is not None else None,
+                                                   hard.ctypes.data if hard is not None else None, cap))
+
+    @property
+    def symbol_capacity(self):
+        return self._L.sdb_engine_symbol_capacity(self._h)
+
+    @property
+    def stream_ptr(self):
+        return self._L.sdb_engine_stream(self._h)
+
+    @property
+    def launches(self):
+        return self._L.sdb_engine_launch_count(self._h)
+
+    def timing(self, enable=True):
+        self._L.sdb_engine_timing(self._h, int(enable))
+
+    def kernel_time(self, family):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(self._L.sdb_engine_kernel_time(self._h, family.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def _task(fn, x, *args):
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    batch = 1 if x.ndim == 1 else x.shape[0]
+    n = x.shape[-1]
+    out = np.empty_like(x)
+    _check(fn(x.ctypes.data, out.ctypes.data, n, batch, *args))
+    return out
+
+
+def carrier_xlate(x, rel_freq, phase=0.0):
+    """Tasks/CarrierXlator.cpp"""
+    return _task(load_library().sdb_task_carrier_xlate, x, rel_freq, phase)
+
+
+def quad_demod(x):
+    """Tasks/QuadDemodTask.cpp"""
+    return _task(load_library().sdb_task_quad_demod, x)
+
+
+def costas(x, kind, tau, loop_bw):
+    """Tasks/CostasRecoveryTask.cpp"""
+    return _task(load_library().sdb_task_costas, x, kind, tau, loop_bw)
+
+
+def pll(x, bw):
+    """Tasks/PLLSyncTask.cpp"""
+    return _task(load_library().sdb_task_pll, x, bw)
+
+
+def agc(x, tau):
+    """Tasks/AGCTask.cpp"""
+    return _task(load_library().sdb_task_agc, x, tau)
+
+
+def lpf(x, bw):
+    """Tasks/LPFTask.cpp"""
+    return _task(load_library().sdb_task_lpf, x, bw)
+
+
+def inspector_run(cls, fs, x, **kw):
+    """Offline inspector over captured channel-rate buffers x [batch, n] -> list of (soft, hard)."""
+    L = load_library()
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    if x.ndim == 1:
+        x = x[None, :]
+    batch, n = x.shape
+    cfg = InspectorConfig()
+    _check(L.sdb_inspector_config_default(C.byref(cfg), INSP[cls], fs))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    cap = n
+    soft = np.empty((batch, cap), np.complex64)
+    hard = np.empty((batch, cap), np.uint8)
+    counts = np.zeros(batch, np.uint32)
+    _check(L.sdb_task_inspector(C.byref(cfg), x.ctypes.data, n, batch, soft.ctypes.data, hard.ctypes.data,
+                                counts.ctypes.data, cap))
+    return [(soft[b, :counts[b]].copy(), hard[b, :counts[b]].copy()) for b in range(batch)]

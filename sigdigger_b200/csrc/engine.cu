@@ -1,0 +1,856 @@
+// engine.cu -- host runtime + C-ABI (include/sigdigger_b200.h) of the B200 analyzer engine.
+//
+// One engine = one channel plan applied to a batch of S independent IQ streams on one GPU.
+// feed(): main PSD over every psd_size frame (four-step FFT, two kernels), channeliser forward FFT
+// over half-overlapping windows with a compacting bin scatter, per-channel IFFT + cross-fade, and
+// the inspector chains.  Everything is queued on one CUDA stream; results are read back on demand.
+//
+// This file replaces, for the hot path only, suscan's analyzer object as the reference drives it:
+// suscan_analyzer_new/destroy (Suscan/Analyzer.cpp:608,636), open/set_inspector_config
+// (Suscan/Analyzer.cpp:459-495), and the PSD / SAMPLES payloads (Suscan/Messages/PSDMessage.cpp:26-39,
+// include/Suscan/Messages/SamplesMessage.h:33-59).  No CPU fallback exists: without a device the
+// constructor fails with an error string.
+#include "../../include/sigdigger_b200.h"
+#include "sdb_internal.h"
+#include "host_design.h"
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return -1; }
+#define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+  g_err = std::string(#expr) + ": " + cudaGetErrorString(e__); return -1; } } while (0)
+#define CKP(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+  g_err = std::string(#expr) + ": " + cudaGetErrorString(e__); return nullptr; } } while (0)
+
+extern "C" const char *sdb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sdb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static bool is_pow2(unsigned v) { return v && !(v & (v - 1)); }
+static int ilog2u(unsigned v) { int l = 0; while ((1u << l) < v) ++l; return l; }
+
+struct Channel {
+  sdb_channel_params p;
+  unsigned center, size, width, halfw, halfsz;
+  bool has_insp;
+  sdb_inspector_config cfg;
+};
+
+struct TimedSpan { int family; cudaEvent_t a, b; };
+enum { FAM_COLS = 0, FAM_ROWS_PSD, FAM_ROWS_CHAN, FAM_CHAN_IFFT, FAM_INSPECTOR, FAM_COUNT };
+static const char *kFamNames[FAM_COUNT] = { "fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft",
+                                            "inspector" };
+
+struct sdb_engine {
+  sdb_engine_params prm;
+  double samp_rate;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  bool committed = false, first_feed = true, timing = false;
+  std::vector<Channel> channels;
+  std::map<unsigned, float2 *> tw;     // twiddle tables by size
+  std::vector<void *> allocs;
+
+  unsigned Np = 0, W = 0;               // PSD size, channeliser window
+  SdbFourStep fs_psd{}, fs_st{};
+  bool psd_small = false;
+  float *d_window = nullptr;
+  float2 *d_scratch = nullptr; int chunk_windows = 1;
+  float2 *d_xin = nullptr;              // staging for host feeds
+  float2 *d_hist = nullptr;             // [S][W/2]
+  float *d_psd = nullptr; size_t max_frames = 0, last_frames = 0;
+  // channeliser
+  int *d_binmap = nullptr; int n_bins = 0;
+  float2 *d_cspec = nullptr; size_t max_hops = 0;
+  std::vector<SdbChannelDev> h_chans; SdbChannelDev *d_chans = nullptr;
+  struct Group { int size; int len; int *d_ids; };
+  std::vector<Group> groups;
+  float2 *d_tails = nullptr; size_t tail_stride = 0;
+  float *d_lo_phase = nullptr;
+  float2 *d_chan = nullptr; size_t chan_stride = 0;
+  size_t last_hops = 0;
+  // chains
+  SdbChainCfg *d_cfg = nullptr; std::vector<SdbChainCfg> h_cfg;
+  SdbChainState *d_state = nullptr;
+  float *d_pool = nullptr; size_t pool_stride = 0;
+  float *d_taps = nullptr;
+  float2 *d_soft = nullptr; uint8_t *d_hard = nullptr; uint32_t *d_counts = nullptr; size_t sym_cap = 0;
+  // timing
+  std::vector<TimedSpan> spans;
+  double fam_ms[FAM_COUNT] = {0}; uint64_t fam_n[FAM_COUNT] = {0};
+
+  template <typename T> T *dalloc(size_t n)
+  {
+    void *p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    allocs.push_back(p);
+    return (T *) p;
+  }
+  const float2 *twiddle(unsigned n)
+  {
+    auto it = tw.find(n);
+    if (it != tw.end()) return it->second;
+    std::vector<float2> h;
+    sdbh::twiddle_fill(n, h);
+    float2 *d = dalloc<float2>(n);
+    if (!d) return nullptr;
+    cudaMemcpy(d, h.data(), n * sizeof(float2), cudaMemcpyHostToDevice);
+    tw[n] = d;
+    return d;
+  }
+  void span_begin(int fam)
+  {
+    if (!timing) return;
+    TimedSpan s; s.family = fam;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, stream);
+    spans.push_back(s);
+  }
+  void span_end()
+  {
+    if (!timing) return;
+    cudaEventRecord(spans.back().b, stream);
+  }
+  void collect_spans()
+  {
+    for (auto &s : spans) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { fam_ms[s.family] += ms; fam_n[s.family]++; }
+      cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    spans.clear();
+  }
+};
+
+static bool make_four_step(sdb_engine *e, unsigned N, SdbFourStep *fs)
+{
+  int l = ilog2u(N), l1 = l / 2;
+  fs->N = (int) N; fs->N1 = 1 << l1; fs->N2 = (int) N / fs->N1;
+  fs->twN1 = e->twiddle(fs->N1); fs->twN2 = e->twiddle(fs->N2); fs->twN = e->twiddle(N);
+  return fs->twN1 && fs->twN2 && fs->twN;
+}
+
+extern "C" sdb_engine_t *sdb_engine_new(const sdb_engine_params *p, double samp_rate)
+{
+  if (!p) { g_err = "null params"; return nullptr; }
+  if (sdb_device_count() <= 0) { g_err = "no CUDA device: sigdigger_b200 has no CPU fallback"; return nullptr; }
+  if (p->n_streams < 1) { g_err = "n_streams must be >= 1"; return nullptr; }
+  if (p->psd_size && (!is_pow2(p->psd_size) || p->psd_size < 16 || p->psd_size > (1u << 20))) {
+    g_err = "psd_size must be a power of two in [16, 2^20]"; return nullptr;
+  }
+  unsigned W = p->st_window_size ? p->st_window_size : p->psd_size;
+  if (!is_pow2(W) || W < 64 || W > (1u << 20)) { g_err = "st_window_size must be a power of two in [64, 2^20]"; return nullptr; }
+  CKP(cudaSetDevice(p->device));
+  sdb_engine *e = new sdb_engine();
+  e->prm = *p; e->samp_rate = samp_rate; e->Np = p->psd_size; e->W = W;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_err = "cudaStreamCreate failed"; delete e; return nullptr;
+  }
+  return e;
+}
+
+extern "C" void sdb_engine_destroy(sdb_engine_t *e)
+{
+  if (!e) return;
+  cudaSetDevice(e->prm.device);
+  cudaStreamSynchronize(e->stream);
+  e->collect_spans();
+  for (void *p : e->allocs) cudaFree(p);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int sdb_inspector_config_default(sdb_inspector_config *c, int insp_class, float fs)
+{
+  if (!c) return fail("null config");
+  memset(c, 0, sizeof(*c));
+  c->insp_class = insp_class; c->fs = fs;
+  c->agc_enabled = 1; c->agc_gain_db = 0.0f;
+  c->costas_order = insp_class == SDB_INSP_PSK ? 2 : 0;
+  c->bits_per_symbol = insp_class == SDB_INSP_PSK ? 2 : 1;
+  c->loop_bw = fs * 1e-3f; c->offset = 0.0f;
+  c->mf_type = 0; c->mf_rolloff = 0.35f;
+  c->clock_type = 1; c->baud = fs * 0.25f; c->clock_gain = 1.0f; c->clock_phase = 0.0f; c->clock_running = 1;
+  c->audio_cutoff = 5000.0f; c->audio_volume = 1.0f; c->audio_sample_rate = 44100;
+  c->audio_demod = SDB_AUDIO_FM; c->agc_ts = 0.1f;
+  return 0;
+}
+
+extern "C" int sdb_engine_open_channel(sdb_engine_t *e, const sdb_channel_params *p, sdb_channel_info *info)
+{
+  if (!e || !p) return fail("null argument");
+  if (e->committed) return fail("engine already committed");
+  if (!(p->guard >= 1.0f) || !(p->bw > 0.0f) || p->bw > 6.28318530717958647692f * 1.0001f)
+    return fail("invalid channel: guard >= 1 and 0 < bw <= 2 pi required");   // INVALID_CHANNEL
+  if (!(p->f0 >= 0.0f) || p->f0 >= 6.28318530717958647692f) return fail("invalid channel: f0 must be in [0, 2 pi)");
+  Channel c;
+  c.p = *p; c.has_insp = false;
+  sdbh::channel_geometry(e->W, p->f0, p->bw, p->guard, &c.center, &c.size, &c.width);
+  c.halfw = c.width >> 1; c.halfsz = c.size >> 1;
+  if (c.size > 16384) return fail("channel size > 16384 bins not supported by the shared-memory IFFT");
+  memset(&c.cfg, 0, sizeof(c.cfg));
+  e->channels.push_back(c);
+  if (info) { info->center = c.center; info->size = c.size; info->width = c.width;
+              info->decimation = (float) e->W / (float) c.size; }
+  return (int) e->channels.size() - 1;
+}
+
+extern "C" int sdb_engine_set_inspector(sdb_engine_t *e, int handle, const sdb_inspector_config *cfg)
+{
+  if (!e || !cfg) return fail("null argument");
+  if (handle < 0 || handle >= (int) e->channels.size()) return fail("wrong handle");   // WRONG_HANDLE
+  if (e->committed) return fail("engine already committed");
+  if (cfg->insp_class < SDB_INSP_PSK || cfg->insp_class > SDB_INSP_RAW) return fail("wrong kind");
+  Channel &c = e->channels[handle];
+  c.cfg = *cfg; c.has_insp = true;
+  c.cfg.fs = (float) (e->samp_rate * (double) c.size / (double) e->W);
+  return 0;
+}
+
+// sdb_inspector_config -> SdbChainCfg (SPEC X; same derivations as the inspector constructors)
+static bool build_chain_cfg(const Channel &ch, SdbChainCfg &c, std::vector<float> &taps_pool)
+{
+  const sdb_inspector_config &g = ch.cfg;
+  memset(&c, 0, sizeof(c));
+  c.cls = ch.has_insp ? g.insp_class : SDB_INSP_RAW;
+  if (c.cls == SDB_INSP_RAW) return true;
+  const float fs = g.fs;
+  float bnor = g.baud / fs;
+  if (bnor > 1.0f) bnor = 1.0f;
+  if (!(bnor > 0.0f)) bnor = 1e-6f;
+  const float T = 1.0f / bnor;
+  c.bnor = bnor;
+  c.gain2 = 2.0f * d_db_to_mag(g.agc_gain_db);
+  c.dl_size = c.mh_size = 1;
+
+  if (c.cls == SDB_INSP_AUDIO) {
+    float tau = g.agc_ts * fs;
+    if (tau < 2.0f) tau = 2.0f;
+    if (g.agc_enabled) {
+      sdbh::AgcDesign d = sdbh::agc_from_tau(tau, 1.0f);
+      c.have_agc = 1; c.knee = d.knee; c.gain_slope = d.gain_slope; c.fixed_gain = d.fixed_gain;
+      c.hang_max = d.hang_max; c.dl_size = d.dl_size; c.mh_size = d.mh_size;
+      c.far_ = d.far_; c.faf = d.faf; c.sar = d.sar; c.saf = d.saf;
+    }
+    if (sdbh::butter_lp(4, sdbh::clampf(2.0f * g.audio_cutoff / fs, 1e-4f, 0.95f), c.alpf_b, c.alpf_a))
+      c.alpf_n = 5;
+    c.audio_demod = (int) g.audio_demod; c.audio_squelch = g.audio_squelch;
+    c.audio_volume = g.audio_volume;
+    c.dc_alpha = (float) (1.0 - exp(-1.0 / (0.05 * (double) fs)));
+    c.sq_alpha = (float) (1.0 - exp(-1.0 / (0.01 * (double) fs)));
+    c.sq_thr = g.audio_squelch_level;
+    c.rs_step = (double) g.audio_sample_rate / (double) fs;
+    float fo = g.audio_demod == SDB_AUDIO_USB ? g.offset : -g.offset;
+    c.lo_omega = 3.14159265358979323846f * (2.0f * fo / fs);
+    return true;
+  }
+
+  if (g.agc_enabled) {
+    sdbh::AgcDesign d = sdbh::agc_from_tau(T, 1.0f);
+    c.have_agc = 1; c.knee = d.knee; c.gain_slope = d.gain_slope; c.fixed_gain = d.fixed_gain;
+    c.hang_max = d.hang_max; c.dl_size = d.dl_size; c.mh_size = d.mh_size;
+    c.far_ = d.far_; c.faf = d.faf; c.sar = d.sar; c.saf = d.saf;
+  }
+  c.af_n = 1; c.af_b[0] = 1.0f; c.af_a[0] = 1.0f;
+  switch (c.cls) {
+    case SDB_INSP_PSK:
+      if (g.costas_order > 0) {
+        if (g.costas_order > 3) return false;
+        c.have_costas = 1; c.costas_kind = (int) g.costas_order;
+        float loop = 2.0f * g.loop_bw / fs;
+        c.c_a = 3.14159265358979323846f * loop;
+        c.c_b = 0.5f * c.c_a * c.c_a;
+        // arm filter "order 3" = 2-pole Butterworth (Tasks/CostasRecoveryTask.cpp:41)
+        if (!sdbh::butter_lp(2, sdbh::clampf(2.0f * bnor, 1e-3f, 0.95f), c.af_b, c.af_a)) return false;
+        c.af_n = 3;
+      } else {
+        c.have_lo = 1;
+        c.lo_omega = 3.14159265358979323846f * (2.0f * g.offset / fs);
+      }
+      break;
+    case SDB_INSP_FSK: {
+      float s, co;
+      d_sincosf(g.fsk_phase, &s, &co);
+      c.fsk_rot_re = co; c.fsk_rot_im = s;
+      c.fsk_quad_demod = g.fsk_quad_demod;
+      break;
+    }
+    case SDB_INSP_ASK:
+      if (g.ask_use_pll) {
+        float fc = 3.14159265358979323846f * (2.0f * g.loop_bw / fs);
+        float dinv = 1.0f / (1.0f + 2.0f * 0.707f * fc + fc * fc);
+        c.have_pll = 1;
+        c.pll_alpha = 4.0f * fc * fc * dinv;
+        c.pll_beta = 4.0f * 0.707f * fc * dinv;
+      } else {
+        c.have_lo = 1;
+        c.lo_omega = 3.14159265358979323846f * (2.0f * g.offset / fs);
+      }
+      c.ask_channel = (int) g.ask_channel;
+      break;
+    default:
+      return false;
+  }
+  if (g.mf_type == 1) {
+    std::vector<float> h;
+    unsigned n = sdbh::mf_span(T);
+    sdbh::taps_rrc(h, n, T, g.mf_rolloff);
+    c.have_mf = 1; c.mf_n = (int) n; c.mf_off = (int) taps_pool.size();
+    taps_pool.insert(taps_pool.end(), h.begin(), h.end());
+  }
+  c.clock_type = (int) g.clock_type; c.clock_running = g.clock_running;
+  c.clk_gain = g.clock_gain; c.clk_alpha = 2e-1f; c.clk_beta = 6e-4f * c.clk_alpha;
+  c.smp_period = 1.0f / bnor; c.smp_phase0 = g.clock_phase * c.smp_period;
+  if (c.cls == SDB_INSP_ASK) { c.dec_mode = 1; c.dec_min = 0.0f; c.dec_h = 1.0f - 0.0f; }
+  else { c.dec_mode = 0; c.dec_min = -3.14159265358979323846f;
+         c.dec_h = 3.14159265358979323846f - (-3.14159265358979323846f); }
+  c.dec_intervals = 1 << g.bits_per_symbol;
+  return true;
+}
+
+extern "C" int sdb_engine_commit(sdb_engine_t *e)
+{
+  if (!e) return fail("null engine");
+  if (e->committed) return fail("already committed");
+  CK(cudaSetDevice(e->prm.device));
+  const unsigned S = e->prm.n_streams, W = e->W, Np = e->Np;
+  const int K = (int) e->channels.size();
+  size_t max_feed = e->prm.max_feed;
+  if (max_feed == 0) return fail("max_feed must be > 0");
+  if (max_feed % (W / 2)) return fail("max_feed must be a multiple of st_window_size / 2");
+  if (Np && max_feed % Np) return fail("max_feed must be a multiple of psd_size");
+
+  // ---- PSD plan
+  if (Np) {
+    std::vector<float> w;
+    if (e->prm.psd_window != SDB_WINDOW_NONE) {
+      sdbh::window_fill(w, Np, e->prm.psd_window);
+      e->d_window = e->dalloc<float>(Np);
+      if (!e->d_window) return fail("out of device memory");
+      CK(cudaMemcpy(e->d_window, w.data(), Np * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    e->psd_small = Np <= 4096;
+    if (e->psd_small) { if (!e->twiddle(Np)) return fail("out of device memory"); }
+    else if (!make_four_step(e, Np, &e->fs_psd)) return fail("out of device memory");
+    e->max_frames = max_feed / Np;
+    e->d_psd = e->dalloc<float>((size_t) S * e->max_frames * Np);
+    if (!e->d_psd) return fail("out of device memory (psd)");
+  }
+  // ---- scratch sized to stay inside L2 (126 MB): 32 MB
+  {
+    unsigned big = std::max(Np > 4096 ? Np : 0u, K > 0 ? W : 0u);
+    if (big) {
+      size_t cw = (32u << 20) / ((size_t) big * sizeof(float2));
+      if (cw < 1) cw = 1;
+      e->chunk_windows = (int) cw;
+      e->d_scratch = e->dalloc<float2>((size_t) e->chunk_windows * big);
+      if (!e->d_scratch) return fail("out of device memory (scratch)");
+    }
+  }
+  // ---- channeliser plan
+  e->max_hops = max_feed / (W / 2);
+  if (K > 0) {
+    if (!make_four_step(e, W, &e->fs_st)) return fail("out of device memory");
+    std::vector<int> binmap(W, -1);
+    std::vector<char> need(W, 0);
+    for (auto &c : e->channels)
+      for (unsigned i = 0; i < 2 * c.halfw; ++i) need[(c.center + W - c.halfw + i) % W] = 1;
+    int nb = 0;
+    for (unsigned b = 0; b < W; ++b) if (need[b]) binmap[b] = nb++;
+    e->n_bins = nb;
+    e->d_binmap = e->dalloc<int>(W);
+    if (!e->d_binmap) return fail("out of device memory");
+    CK(cudaMemcpy(e->d_binmap, binmap.data(), W * sizeof(int), cudaMemcpyHostToDevice));
+    e->d_cspec = e->dalloc<float2>((size_t) S * e->max_hops * nb);
+    e->d_hist = e->dalloc<float2>((size_t) S * (W / 2));
+    if (!e->d_cspec || !e->d_hist) return fail("out of device memory (cspec)");
+    CK(cudaMemset(e->d_hist, 0, (size_t) S * (W / 2) * sizeof(float2)));
+
+    e->h_chans.resize(K);
+    size_t out_off = 0, tail_off = 0;
+    std::map<int, std::vector<int>> by_size;
+    for (int k = 0; k < K; ++k) {
+      Channel &c = e->channels[k];
+      SdbChannelDev &d = e->h_chans[k];
+      memset(&d, 0, sizeof(d));
+      d.center = (int) c.center; d.size = (int) c.size; d.log2size = ilog2u(c.size);
+      d.halfw = (int) c.halfw; d.halfsz = (int) c.halfsz;
+      unsigned b0 = (c.center + W - c.halfw) % W;
+      d.c1 = binmap[b0];
+      d.L1 = (int) std::min<unsigned>(2 * c.halfw, W - b0);
+      d.precise = c.p.precise;
+      if (c.p.precise) {
+        double resid = (double) c.p.f0 - 2.0 * sdbh::kPi * (double) c.center / (double) W;
+        if (resid > sdbh::kPi) resid -= 2.0 * sdbh::kPi;
+        float dec = (float) W / (float) c.size;
+        float fnor = (float) (resid * (double) dec / sdbh::kPi);
+        d.lo_omega = 3.14159265358979323846f * fnor;
+      }
+      std::vector<float> kh, xf;
+      sdbh::channel_weights(W, c.halfw, kh);
+      sdbh::xfade_fill(c.size, xf);
+      float *dkh = e->dalloc<float>(kh.size()), *dxf = e->dalloc<float>(xf.size());
+      if (!dkh || !dxf) return fail("out of device memory");
+      CK(cudaMemcpy(dkh, kh.data(), kh.size() * sizeof(float), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dxf, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice));
+      d.kh = dkh; d.xfade = dxf; d.tw = e->twiddle(c.size);
+      if (!d.tw) return fail("out of device memory");
+      d.out_off = out_off; d.out_cap = e->max_hops * c.halfsz; out_off += d.out_cap;
+      d.tail_off = tail_off; tail_off += c.halfsz;
+      by_size[(int) c.size].push_back(k);
+    }
+    e->chan_stride = out_off; e->tail_stride = tail_off;
+    e->d_chans = e->dalloc<SdbChannelDev>(K);
+    e->d_chan = e->dalloc<float2>((size_t) S * out_off);
+    e->d_tails = e->dalloc<float2>((size_t) S * tail_off);
+    e->d_lo_phase = e->dalloc<float>((size_t) S * K);
+    if (!e->d_chans || !e->d_chan || !e->d_tails || !e->d_lo_phase) return fail("out of device memory (channels)");
+    CK(cudaMemcpy(e->d_chans, e->h_chans.data(), K * sizeof(SdbChannelDev), cudaMemcpyHostToDevice));
+    CK(cudaMemset(e->d_tails, 0, (size_t) S * tail_off * sizeof(float2)));
+    CK(cudaMemset(e->d_lo_phase, 0, (size_t) S * K * sizeof(float)));
+    for (auto &kv : by_size) {
+      sdb_engine::Group g; g.size = kv.first; g.len = (int) kv.second.size();
+      g.d_ids = e->dalloc<int>(kv.second.size());
+      if (!g.d_ids) return fail("out of device memory");
+      CK(cudaMemcpy(g.d_ids, kv.second.data(), kv.second.size() * sizeof(int), cudaMemcpyHostToDevice));
+      e->groups.push_back(g);
+    }
+    // ---- chains
+    e->h_cfg.resize(K);
+    std::vector<float> taps_pool;
+    size_t pool = 1, cap = 1;
+    for (int k = 0; k < K; ++k) {
+      if (!build_chain_cfg(e->channels[k], e->h_cfg[k], taps_pool)) return fail("invalid inspector configuration");
+      SdbChainCfg &c = e->h_cfg[k];
+      c.st_dl_off = 0; c.st_mh_off = 2 * (int) c.dl_size; c.st_mf_off = c.st_mh_off + (int) c.mh_size;
+      c.st_pool = c.st_mf_off + 2 * c.mf_n;
+      pool = std::max<size_t>(pool, (size_t) c.st_pool);
+      cap = std::max<size_t>(cap, e->max_hops * e->channels[k].halfsz);
+    }
+    e->pool_stride = pool; e->sym_cap = cap;
+    const size_t chains = (size_t) S * K;
+    e->d_cfg = e->dalloc<SdbChainCfg>(K);
+    e->d_state = e->dalloc<SdbChainState>(chains);
+    e->d_pool = e->dalloc<float>(chains * pool);
+    e->d_taps = e->dalloc<float>(taps_pool.size());
+    e->d_soft = e->dalloc<float2>(chains * cap);
+    e->d_hard = e->dalloc<uint8_t>(chains * cap);
+    e->d_counts = e->dalloc<uint32_t>(chains);
+    if (!e->d_cfg || !e->d_state || !e->d_pool || !e->d_taps || !e->d_soft || !e->d_hard || !e->d_counts)
+      return fail("out of device memory (chains)");
+    CK(cudaMemcpy(e->d_cfg, e->h_cfg.data(), K * sizeof(SdbChainCfg), cudaMemcpyHostToDevice));
+    if (!taps_pool.empty())
+      CK(cudaMemcpy(e->d_taps, taps_pool.data(), taps_pool.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<SdbChainState> st(chains);
+    std::vector<float> hp(chains * pool, 0.0f);
+    for (size_t ci = 0; ci < chains; ++ci) {
+      const SdbChainCfg &c = e->h_cfg[ci % K];
+      SdbChainState &s = st[ci];
+      memset(&s, 0, sizeof(s));
+      s.fast_level = s.slow_level = s.peak = -160.0f;
+      s.k_phi = 0.25f; s.k_bnor = c.bnor;
+      for (unsigned i = 0; i < c.mh_size; ++i) hp[ci * pool + c.st_mh_off + i] = -160.0f;
+    }
+    CK(cudaMemcpy(e->d_state, st.data(), chains * sizeof(SdbChainState), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_pool, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemset(e->d_counts, 0, chains * sizeof(uint32_t)));
+  }
+  e->committed = true;
+  return 0;
+}
+
+extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, size_t stride, size_t n)
+{
+  if (!e || !xv) return fail("null argument");
+  if (!e->committed) return fail("engine not committed");
+  const unsigned S = e->prm.n_streams, W = e->W, Np = e->Np;
+  const int K = (int) e->channels.size();
+  if (n == 0 || n > e->prm.max_feed) return fail("feed size out of range");
+  if (Np && n % Np) return fail("feed size must be a multiple of psd_size");
+  if (K && n % (W / 2)) return fail("feed size must be a multiple of st_window_size / 2");
+  CK(cudaSetDevice(e->prm.device));
+  const float2 *x = reinterpret_cast<const float2 *>(xv);
+  SdbLaunchCtx ctx{ e->stream, &e->launches };
+  const int shift_db = (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) ? 1 : 0;
+
+  // ---- main PSD
+  if (Np) {
+    const int frames = (int) (n / Np);
+    e->last_frames = frames;
+    if (e->psd_small) {
+      e->span_begin(FAM_ROWS_PSD);
+      CK(sdb_launch_small_psd(ctx, (int) Np, e->twiddle(Np), x, stride, frames, (int) S, e->d_window,
+                              e->d_psd, shift_db));
+      e->span_end();
+    } else {
+      const int total = frames * (int) S;
+      for (int w0 = 0; w0 < total; w0 += e->chunk_windows) {
+        const int cw = std::min(e->chunk_windows, total - w0);
+        SdbPassAArgs a{};
+        a.x = x; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
+        a.windows_per_stream = frames; a.first_window = 0; a.hop = (int) Np; a.base_off = 0;
+        a.window = e->d_window; a.scratch = e->d_scratch;
+        e->span_begin(FAM_COLS);
+        CK(sdb_launch_pass_a_range(ctx, e->fs_psd, a, w0, cw));
+        e->span_end();
+        SdbPassBArgs b{};
+        b.scratch = e->d_scratch; b.n_windows = cw; b.psd = e->d_psd + (size_t) w0 * Np;
+        b.inv_n = 1.0f / (float) Np; b.shift_db = shift_db;
+        e->span_begin(FAM_ROWS_PSD);
+        CK(sdb_launch_pass_b_psd(ctx, e->fs_psd, b));
+        e->span_end();
+      }
+    }
+  }
+  // ---- channeliser + inspectors
+  if (K) {
+    const int H = (int) (n / (W / 2));
+    const int first = e->first_feed ? 1 : 0;
+    const int wps = H - first;
+    e->last_hops = wps > 0 ? wps : 0;
+    if (wps > 0) {
+      const int total = wps * (int) S;
+      for (int w0 = 0; w0 < total; w0 += e->chunk_windows) {
+        const int cw = std::min(e->chunk_windows, total - w0);
+        SdbPassAArgs a{};
+        a.x = x; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
+        a.windows_per_stream = wps; a.first_window = first; a.hop = (int) (W / 2); a.base_off = 0;
+        a.window = nullptr; a.scratch = e->d_scratch;
+        e->span_begin(FAM_COLS);
+        CK(sdb_launch_pass_a_range(ctx, e->fs_st, a, w0, cw));
+        e->span_end();
+        SdbPassBArgs b{};
+        b.scratch = e->d_scratch; b.n_windows = cw; b.binmap = e->d_binmap;
+        b.cspec = e->d_cspec + (size_t) w0 * e->n_bins; b.n_bins = e->n_bins;
+        e->span_begin(FAM_ROWS_CHAN);
+        CK(sdb_launch_pass_b_chan(ctx, e->fs_st, b));
+        e->span_end();
+      }
+      e->span_begin(FAM_CHAN_IFFT);
+      for (auto &g : e->groups)
+        CK(sdb_launch_chan_ifft_group(ctx, e->d_chans, g.d_ids, g.len, g.size, K, (int) S, e->d_cspec,
+                                      e->n_bins, wps, e->d_tails, e->tail_stride, e->d_lo_phase, e->d_chan,
+                                      e->chan_stride));
+      e->span_end();
+      e->span_begin(FAM_INSPECTOR);
+      CK(sdb_launch_inspectors_n(ctx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
+                                 e->d_chans, e->d_chan, e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
+                                 e->d_counts, e->sym_cap));
+      e->span_end();
+    } else {
+      CK(cudaMemsetAsync(e->d_counts, 0, (size_t) S * K * sizeof(uint32_t), e->stream));
+    }
+    // keep the last half window of every stream as history for the next feed
+    CK(cudaMemcpy2DAsync(e->d_hist, (W / 2) * sizeof(float2), x + (n - W / 2), stride * sizeof(float2),
+                         (W / 2) * sizeof(float2), S, cudaMemcpyDeviceToDevice, e->stream));
+    e->first_feed = false;
+  }
+  return 0;
+}
+
+extern "C" int sdb_engine_feed_host(sdb_engine_t *e, const sdb_complex *x, size_t stride, size_t n)
+{
+  if (!e || !x) return fail("null argument");
+  if (!e->committed) return fail("engine not committed");
+  if (n == 0 || n > e->prm.max_feed) return fail("feed size out of range");
+  CK(cudaSetDevice(e->prm.device));
+  const unsigned S = e->prm.n_streams;
+  if (!e->d_xin) {
+    e->d_xin = e->dalloc<float2>((size_t) S * e->prm.max_feed);
+    if (!e->d_xin) return fail("out of device memory (input staging)");
+  }
+  CK(cudaMemcpy2DAsync(e->d_xin, n * sizeof(float2), x, stride * sizeof(float2), n * sizeof(float2), S,
+                       cudaMemcpyHostToDevice, e->stream));
+  return sdb_engine_feed_device(e, reinterpret_cast<const sdb_complex *>(e->d_xin), n, n);
+}
+
+extern "C" int sdb_engine_sync(sdb_engine_t *e)
+{
+  if (!e) return fail("null engine");
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaStreamSynchronize(e->stream));
+  e->collect_spans();
+  return 0;
+}
+
+extern "C" size_t sdb_engine_psd_frames(const sdb_engine_t *e) { return e ? e->last_frames : 0; }
+extern "C" const float *sdb_engine_psd_device(const sdb_engine_t *e) { return e ? e->d_psd : nullptr; }
+
+extern "C" int sdb_engine_read_psd(sdb_engine_t *e, float *dst, size_t cap)
+{
+  if (!e || !dst) return fail("null argument");
+  const size_t n = (size_t) e->prm.n_streams * e->last_frames * e->Np;
+  if (cap < n) return fail("destination too small");
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaMemcpyAsync(dst, e->d_psd, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" long sdb_engine_read_channel(sdb_engine_t *e, uint32_t stream, int handle, sdb_complex *dst, size_t cap)
+{
+  if (!e || !dst) return fail("null argument");
+  if (handle < 0 || handle >= (int) e->channels.size()) return fail("wrong handle");
+  if (stream >= e->prm.n_streams) return fail("stream out of range");
+  const SdbChannelDev &d = e->h_chans[handle];
+  size_t n = e->last_hops * (size_t) d.halfsz;
+  if (n > cap) n = cap;
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaMemcpyAsync(dst, e->d_chan + (size_t) stream * e->chan_stride + d.out_off, n * sizeof(float2),
+                     cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return (long) n;
+}
+
+extern "C" long sdb_engine_read_symbols(sdb_engine_t *e, uint32_t stream, int handle, sdb_complex *soft,
+                                        uint8_t *hard, size_t cap)
+{
+  if (!e) return fail("null argument");
+  const int K = (int) e->channels.size();
+  if (handle < 0 || handle >= K) return fail("wrong handle");
+  if (stream >= e->prm.n_streams) return fail("stream out of range");
+  const size_t chain = (size_t) stream * K + handle;
+  uint32_t cnt = 0;
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaMemcpyAsync(&cnt, e->d_counts + chain, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  size_t n = cnt;
+  if (n > cap) n = cap;
+  if (soft) CK(cudaMemcpyAsync(soft, e->d_soft + chain * e->sym_cap, n * sizeof(float2), cudaMemcpyDeviceToHost, e->stream));
+  if (hard) CK(cudaMemcpyAsync(hard, e->d_hard + chain * e->sym_cap, n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return (long) n;
+}
+
+extern "C" int sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft, uint8_t *hard,
+                                           size_t cap)
+{
+  if (!e || !counts) return fail("null argument");
+  const size_t chains = (size_t) e->prm.n_streams * e->channels.size();
+  if (chains == 0) return 0;
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaMemcpyAsync(counts, e->d_counts, chains * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  const size_t w = std::min(cap, e->sym_cap);
+  if (soft) CK(cudaMemcpy2DAsync(soft, cap * sizeof(float2), e->d_soft, e->sym_cap * sizeof(float2),
+                                 w * sizeof(float2), chains, cudaMemcpyDeviceToHost, e->stream));
+  if (hard) CK(cudaMemcpy2DAsync(hard, cap, e->d_hard, e->sym_cap, w, chains, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" const uint32_t *sdb_engine_symbol_counts_device(const sdb_engine_t *e) { return e ? e->d_counts : nullptr; }
+extern "C" size_t sdb_engine_symbol_capacity(const sdb_engine_t *e) { return e ? e->sym_cap : 0; }
+extern "C" void *sdb_engine_stream(const sdb_engine_t *e) { return e ? (void *) e->stream : nullptr; }
+extern "C" uint64_t sdb_engine_launch_count(const sdb_engine_t *e) { return e ? e->launches : 0; }
+extern "C" void sdb_engine_timing(sdb_engine_t *e, int enable)
+{
+  if (!e) return;
+  e->timing = enable != 0;
+  for (int i = 0; i < FAM_COUNT; ++i) { e->fam_ms[i] = 0; e->fam_n[i] = 0; }
+}
+extern "C" int sdb_engine_kernel_time(sdb_engine_t *e, const char *family, double *avg_ms, uint64_t *launches)
+{
+  if (!e || !family) return fail("null argument");
+  for (int i = 0; i < FAM_COUNT; ++i)
+    if (!strcmp(family, kFamNames[i])) {
+      if (avg_ms) *avg_ms = e->fam_n[i] ? e->fam_ms[i] / (double) e->fam_n[i] : 0.0;
+      if (launches) *launches = e->fam_n[i];
+      return 0;
+    }
+  return fail("unknown kernel family");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tasks/ primitives on host buffers
+// ---------------------------------------------------------------------------------------------
+struct TaskBufs {
+  float2 *src = nullptr, *dst = nullptr; float *pool = nullptr;
+  ~TaskBufs() { cudaFree(src); cudaFree(dst); cudaFree(pool); }
+};
+
+static int task_io_begin(TaskBufs &b, const sdb_complex *src, size_t n, size_t batch)
+{
+  if (!src || n == 0 || batch == 0) return fail("invalid task buffer");
+  if (sdb_device_count() <= 0) return fail("no CUDA device: sigdigger_b200 has no CPU fallback");
+  CK(cudaMalloc(&b.src, n * batch * sizeof(float2)));
+  CK(cudaMalloc(&b.dst, n * batch * sizeof(float2)));
+  CK(cudaMemcpy(b.src, src, n * batch * sizeof(float2), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int task_io_end(TaskBufs &b, sdb_complex *dst, size_t n, size_t batch)
+{
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, b.dst, n * batch * sizeof(float2), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int sdb_task_carrier_xlate(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch,
+                                      float rel_freq, float phase)
+{
+  TaskBufs b;
+  if (task_io_begin(b, src, n, batch)) return -1;
+  // su_ncqo_init(-relFreq); su_ncqo_set_phase(-phase)   (Tasks/CarrierXlator.cpp:36-37)
+  float omega = 3.14159265358979323846f * (-rel_freq);
+  float phi = -phase;
+  phi = phi - 6.28318530717958647692f * floorf(phi / 6.28318530717958647692f);
+  if (phi >= 6.28318530717958647692f) phi = 0.0f;
+  CK(sdb_launch_task_xlate(0, b.src, b.dst, n, batch, omega, phi));
+  return task_io_end(b, dst, n, batch);
+}
+
+extern "C" int sdb_task_quad_demod(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch)
+{
+  TaskBufs b;
+  if (task_io_begin(b, src, n, batch)) return -1;
+  CK(sdb_launch_task_quad(0, b.src, b.dst, n, batch));
+  return task_io_end(b, dst, n, batch);
+}
+
+extern "C" int sdb_task_costas(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, int kind,
+                               float tau, float loop_bw)
+{
+  if (kind < 1 || kind > 3) return fail("invalid Costas kind");
+  TaskBufs b;
+  if (task_io_begin(b, src, n, batch)) return -1;
+  SdbChainCfg c; memset(&c, 0, sizeof(c));
+  // su_costas_init(&costas, kind, 0, 1/tau, 3, loopbw)   (Tasks/CostasRecoveryTask.cpp:36-41)
+  c.costas_kind = kind;
+  c.c_a = 3.14159265358979323846f * loop_bw;
+  c.c_b = 0.5f * c.c_a * c.c_a;
+  if (!sdbh::butter_lp(2, 1.0f / tau, c.af_b, c.af_a)) return fail("invalid arm bandwidth");
+  c.af_n = 3;
+  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, c, 0, nullptr, 0));
+  return task_io_end(b, dst, n, batch);
+}
+
+extern "C" int sdb_task_pll(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw)
+{
+  TaskBufs b;
+  if (task_io_begin(b, src, n, batch)) return -1;
+  SdbChainCfg c; memset(&c, 0, sizeof(c));
+  float fc = 3.14159265358979323846f * bw;
+  float dinv = 1.0f / (1.0f + 2.0f * 0.707f * fc + fc * fc);
+  c.pll_alpha = 4.0f * fc * fc * dinv;
+  c.pll_beta = 4.0f * 0.707f * fc * dinv;
+  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, c, 1, nullptr, 0));
+  return task_io_end(b, dst, n, batch);
+}
+
+extern "C" int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float tau)
+{
+  TaskBufs b;
+  if (task_io_begin(b, src, n, batch)) return -1;
+  SdbChainCfg c; memset(&c, 0, sizeof(c));
+  // AGCTask sets only the five time constants; delay line / history keep the defaults (20)
+  // (Tasks/AGCTask.cpp:43-47 and the comment in SURVEY.md 8a row a6)
+  sdbh::AgcDesign d = sdbh::agc_from_tau(tau, 2.0f);
+  c.knee = d.knee; c.gain_slope = d.gain_slope; c.fixed_gain = d.fixed_gain;
+  c.hang_max = d.hang_max; c.dl_size = 20; c.mh_size = 20;
+  c.far_ = d.far_; c.faf = d.faf; c.sar = d.sar; c.saf = d.saf;
+  c.st_dl_off = 0; c.st_mh_off = 40; c.st_pool = 60;
+  std::vector<float> hp(batch * 60, 0.0f);
+  for (size_t i = 0; i < batch; ++i) for (int j = 0; j < 20; ++j) hp[i * 60 + 40 + j] = -160.0f;
+  CK(cudaMalloc(&b.pool, hp.size() * sizeof(float)));
+  CK(cudaMemcpy(b.pool, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, c, 2, b.pool, 60));
+  return task_io_end(b, dst, n, batch);
+}
+
+// Offline inspector over `batch` captured channel-rate buffers (what the GUI's TimeWindow / SamplerDialog
+// do block-wise on the CPU, Components/TimeWindow.cpp:1571-2183): one GPU chain per buffer.
+extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_complex *src, size_t n,
+                                   size_t batch, sdb_complex *soft, uint8_t *hard, uint32_t *counts, size_t cap)
+{
+  if (!cfg || !src || !counts || n == 0 || batch == 0) return fail("invalid argument");
+  if (sdb_device_count() <= 0) return fail("no CUDA device: sigdigger_b200 has no CPU fallback");
+  Channel ch; memset(&ch.p, 0, sizeof(ch.p));
+  ch.center = 0; ch.size = 2; ch.width = 2; ch.halfw = 1; ch.halfsz = 1; ch.has_insp = true; ch.cfg = *cfg;
+  SdbChainCfg c; std::vector<float> taps;
+  if (!build_chain_cfg(ch, c, taps)) return fail("invalid inspector configuration");
+  c.st_dl_off = 0; c.st_mh_off = 2 * (int) c.dl_size; c.st_mf_off = c.st_mh_off + (int) c.mh_size;
+  c.st_pool = c.st_mf_off + 2 * c.mf_n;
+  const size_t pool = (size_t) std::max(1, c.st_pool);
+  SdbChannelDev cd; memset(&cd, 0, sizeof(cd)); cd.halfsz = 1; cd.out_off = 0;
+  std::vector<SdbChainState> st(batch);
+  std::vector<float> hp(batch * pool, 0.0f);
+  for (size_t i = 0; i < batch; ++i) {
+    memset(&st[i], 0, sizeof(SdbChainState));
+    st[i].fast_level = st[i].slow_level = st[i].peak = -160.0f;
+    st[i].k_phi = 0.25f; st[i].k_bnor = c.bnor;
+    for (unsigned j = 0; j < c.mh_size; ++j) hp[i * pool + c.st_mh_off + j] = -160.0f;
+  }
+  struct Bufs { void *p[9] = {0}; ~Bufs() { for (auto q : p) cudaFree(q); } } b;
+  float2 *d_src, *d_soft; uint8_t *d_hard; uint32_t *d_cnt; SdbChainCfg *d_cfg; SdbChainState *d_st;
+  float *d_pool, *d_taps; SdbChannelDev *d_cd;
+  CK(cudaMalloc(&b.p[0], n * batch * sizeof(float2))); d_src = (float2 *) b.p[0];
+  CK(cudaMalloc(&b.p[1], cap * batch * sizeof(float2))); d_soft = (float2 *) b.p[1];
+  CK(cudaMalloc(&b.p[2], cap * batch)); d_hard = (uint8_t *) b.p[2];
+  CK(cudaMalloc(&b.p[3], batch * sizeof(uint32_t))); d_cnt = (uint32_t *) b.p[3];
+  CK(cudaMalloc(&b.p[4], sizeof(SdbChainCfg))); d_cfg = (SdbChainCfg *) b.p[4];
+  CK(cudaMalloc(&b.p[5], batch * sizeof(SdbChainState))); d_st = (SdbChainState *) b.p[5];
+  CK(cudaMalloc(&b.p[6], hp.size() * sizeof(float))); d_pool = (float *) b.p[6];
+  CK(cudaMalloc(&b.p[7], std::max<size_t>(1, taps.size()) * sizeof(float))); d_taps = (float *) b.p[7];
+  CK(cudaMalloc(&b.p[8], sizeof(SdbChannelDev))); d_cd = (SdbChannelDev *) b.p[8];
+  CK(cudaMemcpy(d_src, src, n * batch * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_cfg, &c, sizeof(c), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_st, st.data(), batch * sizeof(SdbChainState), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_pool, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (!taps.empty()) CK(cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_cd, &cd, sizeof(cd), cudaMemcpyHostToDevice));
+  SdbLaunchCtx ctx{ 0, nullptr };
+  // every chain is "stream s, channel 0"; chan_stream_stride = n
+  CK(sdb_launch_inspectors_n(ctx, d_cfg, 1, (int) batch, d_st, d_pool, pool, d_taps, d_cd, d_src, n,
+                             (uint32_t) n, d_soft, d_hard, d_cnt, cap));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(counts, d_cnt, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (soft) CK(cudaMemcpy(soft, d_soft, cap * batch * sizeof(float2), cudaMemcpyDeviceToHost));
+  if (hard) CK(cudaMemcpy(hard, d_hard, cap * batch, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw)
+{
+  // LPFTask: specttuner with the default 4096-sample window, one channel at f0 = 0 with
+  // guard = 2 pi / bw (no decimation), input flushed with zeros until n outputs exist
+  // (Tasks/LPFTask.cpp:52-69,104-107).
+  if (!src || !dst || n == 0 || batch == 0) return fail("invalid task buffer");
+  const unsigned W = 4096;   // sigutils_specttuner_params_INITIALIZER default window
+  sdb_engine_params p; memset(&p, 0, sizeof(p));
+  size_t padded = ((n + W / 2 + W / 2 - 1) / (W / 2)) * (W / 2);   // + half-window latency, rounded up
+  p.n_streams = (uint32_t) batch; p.psd_size = 0; p.st_window_size = W; p.max_feed = (uint32_t) padded; p.device = 0;
+  int dev = 0; cudaGetDevice(&dev); p.device = dev;
+  sdb_engine_t *e = sdb_engine_new(&p, 1.0);
+  if (!e) return -1;
+  sdb_channel_params cp; cp.f0 = 0.0f; cp.bw = 3.14159265358979323846f * bw; cp.guard = 6.28318530717958647692f / cp.bw;
+  cp.precise = 0;
+  int rc = -1;
+  std::vector<float2> in(batch * padded, make_float2(0.f, 0.f)), out(padded);
+  for (size_t b = 0; b < batch; ++b) memcpy(&in[b * padded], src + b * n, n * sizeof(float2));
+  do {
+    int h = sdb_engine_open_channel(e, &cp, nullptr);
+    if (h < 0) break;
+    if (sdb_engine_commit(e)) break;
+    if (sdb_engine_feed_host(e, reinterpret_cast<const sdb_complex *>(in.data()), padded, padded)) break;
+    bool ok = true;
+    for (size_t b = 0; b < batch && ok; ++b) {
+      long got = sdb_engine_read_channel(e, (uint32_t) b, h, reinterpret_cast<sdb_complex *>(out.data()), padded);
+      if (got < (long) n) { g_err = "lpf produced too few samples"; ok = false; break; }
+      memcpy(dst + b * n, out.data(), n * sizeof(float2));
+    }
+    if (ok) rc = 0;
+  } while (0);
+  sdb_engine_destroy(e);
+  return rc;
+}

@@ -1,0 +1,413 @@
+// fft_kernels.cu -- cuFFT-free FFT machinery of the analyzer hot path, hand-written for sm_100a.
+//
+//   * block_fft_inplace: Stockham radix-4 (+ one radix-2) transform of M points held in shared
+//     memory, twiddles from a correctly rounded table (W_M^i computed in double on the host).
+//   * four-step N = N1 x N2 transform in two kernels:
+//       pass A (k_pass_a): coalesced float2 tile loads of CW adjacent columns, optional window
+//                          multiply (main PSD), N1-point column FFTs, twiddle W_N^(n2 k1), transposed
+//                          coalesced store to an L2-resident scratch;
+//       pass B (k_pass_b): N2-point row FFTs + fused epilogue: |X|^2/N (+ optional fft-shift and dB)
+//                          for the main PSD, or a compacting scatter of
+//                          only the bins some channel needs (su_specttuner forward side, row a4).
+//   * k_small_psd: one CTA per frame for N <= 4096.
+//   * k_chan_ifft: su_specttuner inverse side: gather + k*h shaping + small IFFT + sin^2
+//     cross-fade with the previous half window, optional per-sample LO ("precise").
+//
+// Reference behaviour being replaced: su_specttuner feed (Tasks/LPFTask.cpp:52-69,83-87) and the PSD
+// message payload (Suscan/Messages/PSDMessage.cpp:26-39).  Compiled WITH fma contraction: results are
+// compared with the oracle to the float tolerance of SPEC.md section T, not bit-exactly.
+#include "sdb_internal.h"
+#include <math_constants.h>
+
+static __device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+static __device__ __forceinline__ float2 cmulc(float2 a, float2 b)  // a * conj(b)
+{
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+static __device__ __forceinline__ float2 ldtw(const float2 *__restrict__ tw, int i)
+{
+  return __ldg(tw + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-place shared-memory FFT of M = 2^logM points.  `nthr` threads (lane = 0..nthr-1) cooperate,
+// nthr * BPT >= M / 4.  Every thread of the CTA must call this with the same M (CTA-wide barriers).
+// DIR = -1 forward, +1 inverse (unnormalised).
+// ---------------------------------------------------------------------------------------------
+template <int DIR, int BPT>
+static __device__ __forceinline__ void block_fft_inplace(float2 *s, const int M, const int logM,
+                                                         const int lane, const int nthr,
+                                                         const float2 *__restrict__ tw)
+{
+  const int q = M >> 2;
+  int logNs = 0;
+  for (; logNs + 2 <= logM; logNs += 2) {
+    const int Ns = 1 << logNs;
+    float2 v[BPT][4];
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      const int j = lane + b * nthr;
+      if (j < q) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[b][t] = s[j + t * q];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      const int j = lane + b * nthr;
+      if (j < q) {
+        const int k = j & (Ns - 1);
+        if (logNs > 0) {
+          const int step = M >> (logNs + 2);
+          float2 w1 = ldtw(tw, k * step), w2 = ldtw(tw, 2 * k * step), w3 = ldtw(tw, 3 * k * step);
+          if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+          v[b][1] = cmul(v[b][1], w1);
+          v[b][2] = cmul(v[b][2], w2);
+          v[b][3] = cmul(v[b][3], w3);
+        }
+        const float2 a = make_float2(v[b][0].x + v[b][2].x, v[b][0].y + v[b][2].y);
+        const float2 bb = make_float2(v[b][0].x - v[b][2].x, v[b][0].y - v[b][2].y);
+        const float2 c = make_float2(v[b][1].x + v[b][3].x, v[b][1].y + v[b][3].y);
+        const float2 dd = make_float2(v[b][1].x - v[b][3].x, v[b][1].y - v[b][3].y);
+        // forward: d = -i * dd ; inverse: d = +i * dd
+        const float2 d = DIR < 0 ? make_float2(dd.y, -dd.x) : make_float2(-dd.y, dd.x);
+        const int j0 = ((j - k) << 2) + k;
+        s[j0]          = make_float2(a.x + c.x, a.y + c.y);
+        s[j0 + Ns]     = make_float2(bb.x + d.x, bb.y + d.y);
+        s[j0 + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
+        s[j0 + 3 * Ns] = make_float2(bb.x - d.x, bb.y - d.y);
+      }
+    }
+    __syncthreads();
+  }
+  if (logNs < logM) {  // one radix-2 stage with Ns = M/2: in place, butterfly j touches s[j], s[j+h]
+    const int h = M >> 1;
+#pragma unroll
+    for (int b = 0; b < 2 * BPT; ++b) {
+      const int j = lane + b * nthr;
+      if (j < h) {
+        float2 w = ldtw(tw, j);
+        if (DIR > 0) w.y = -w.y;
+        const float2 a = s[j], t = cmul(s[j + h], w);
+        s[j]     = make_float2(a.x + t.x, a.y + t.y);
+        s[j + h] = make_float2(a.x - t.x, a.y - t.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// ---------------------------------------------------------------------------------------------
+// pass A: column FFTs
+// ---------------------------------------------------------------------------------------------
+struct PassAK {
+  SdbFourStep fs;
+  SdbPassAArgs a;
+  int CW, logN1, win_base;
+};
+
+__global__ void __launch_bounds__(1024) k_pass_a(const PassAK p)
+{
+  extern __shared__ float2 sm[];
+  const int N1 = p.fs.N1, N2 = p.fs.N2, LD = N1 + 1, CW = p.CW;
+  const int w = p.win_base + blockIdx.y;
+  const int stream = w / p.a.windows_per_stream;
+  const int j = p.a.first_window + (w - stream * p.a.windows_per_stream);
+  const int col0 = blockIdx.x * CW;
+  const long v0 = (long) p.a.base_off + (long) j * p.a.hop;
+  const float2 *__restrict__ xs = p.a.x + (size_t) stream * p.a.stream_stride;
+  const float2 *__restrict__ hs = p.a.hist ? p.a.hist + (size_t) stream * p.a.hist_len : nullptr;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int total = N1 * CW;
+
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int r = idx / CW, c = idx - r * CW;
+    const long vi = v0 + (long) r * N2 + col0 + c;
+    float2 val = vi < p.a.hist_len ? __ldg(hs + vi) : __ldg(xs + (vi - p.a.hist_len));
+    if (p.a.window) {
+      const float wv = __ldg(p.a.window + r * N2 + col0 + c);
+      val.x *= wv; val.y *= wv;
+    }
+    sm[c * LD + r] = val;
+  }
+  __syncthreads();
+  {
+    const int per = nthreads / CW;
+    const int t = tid / per, lane = tid - t * per;
+    block_fft_inplace<-1, 1>(sm + t * LD, N1, p.logN1, lane, per, p.fs.twN1);
+  }
+  float2 *__restrict__ out = p.a.scratch + (size_t) blockIdx.y * p.fs.N;
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int k1 = idx / CW, c = idx - k1 * CW;
+    const float2 v = sm[c * LD + k1];
+    const float2 tw = ldtw(p.fs.twN, (col0 + c) * k1);
+    out[(size_t) k1 * N2 + col0 + c] = cmul(v, tw);
+  }
+}
+
+cudaError_t sdb_launch_pass_a_range(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
+                                    int win_base, int n_win)
+{
+  PassAK p;
+  p.fs = fs; p.a = a; p.win_base = win_base;
+  p.logN1 = ilog2(fs.N1);
+  int cw = 4096 / fs.N1; if (cw > 16) cw = 16; if (cw > fs.N2) cw = fs.N2; if (cw < 1) cw = 1;
+  p.CW = cw;
+  const int threads = cw * (fs.N1 / 4);
+  const size_t smem = (size_t) cw * (fs.N1 + 1) * sizeof(float2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_done = true;
+  }
+  dim3 grid(fs.N2 / cw, n_win);
+  k_pass_a<<<grid, threads, smem, c.stream>>>(p);
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass B: row FFTs + epilogue
+// ---------------------------------------------------------------------------------------------
+struct PassBK {
+  SdbFourStep fs;
+  SdbPassBArgs a;
+  int RW, logN2;
+};
+
+template <int MODE>  // 0 = PSD, 1 = channeliser scatter
+__global__ void __launch_bounds__(1024) k_pass_b(const PassBK p)
+{
+  extern __shared__ float2 sm[];
+  const int N1 = p.fs.N1, N2 = p.fs.N2, N = p.fs.N, LD = N2 + 1, RW = p.RW;
+  const int win = blockIdx.y;
+  const int k1_0 = blockIdx.x * RW;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int total = RW * N2;
+  const float2 *__restrict__ in = p.a.scratch + (size_t) win * N + (size_t) k1_0 * N2;
+
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int r = idx / N2, n2 = idx - r * N2;
+    sm[r * LD + n2] = in[idx];
+  }
+  __syncthreads();
+  {
+    const int per = nthreads / RW;
+    const int t = tid / per, lane = tid - t * per;
+    block_fft_inplace<-1, 1>(sm + t * LD, N2, p.logN2, lane, per, p.fs.twN2);
+  }
+  if (MODE == 0) {
+    float *__restrict__ psd = p.a.psd + (size_t) win * N;
+    const int half = N >> 1;
+    for (int idx = tid; idx < total; idx += nthreads) {
+      const int k2 = idx / RW, r = idx - k2 * RW;
+      const float2 X = sm[r * LD + k2];
+      const int k = k1_0 + r + N1 * k2;
+      float pw = (X.x * X.x + X.y * X.y) * p.a.inv_n;
+      if (p.a.shift_db) {
+        // Suscan/Messages/PSDMessage.cpp:32-38: swap halves, SU_POWER_DB
+        pw = 10.0f * log10f(pw + 1e-8f);
+        psd[(k + half) & (N - 1)] = pw;
+      } else {
+        psd[k] = pw;
+      }
+    }
+  } else {
+    float2 *__restrict__ cs = p.a.cspec + (size_t) win * p.a.n_bins;
+    for (int idx = tid; idx < total; idx += nthreads) {
+      const int k2 = idx / RW, r = idx - k2 * RW;
+      const int k = k1_0 + r + N1 * k2;
+      const int m = __ldg(p.a.binmap + k);
+      if (m >= 0) cs[m] = sm[r * LD + k2];
+    }
+  }
+}
+
+static cudaError_t launch_pass_b(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a,
+                                 int mode)
+{
+  PassBK p;
+  p.fs = fs; p.a = a;
+  p.logN2 = ilog2(fs.N2);
+  int rw = 4096 / fs.N2; if (rw > 16) rw = 16; if (rw > fs.N1) rw = fs.N1; if (rw < 1) rw = 1;
+  p.RW = rw;
+  const int threads = rw * (fs.N2 / 4);
+  const size_t smem = (size_t) rw * (fs.N2 + 1) * sizeof(float2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_pass_b<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_done = true;
+  }
+  dim3 grid(fs.N1 / rw, a.n_windows);
+  if (mode == 0) k_pass_b<0><<<grid, threads, smem, c.stream>>>(p);
+  else           k_pass_b<1><<<grid, threads, smem, c.stream>>>(p);
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_pass_b_psd(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a)
+{
+  return launch_pass_b(c, fs, a, 0);
+}
+cudaError_t sdb_launch_pass_b_chan(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a)
+{
+  return launch_pass_b(c, fs, a, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small PSD: one CTA per frame, N <= 4096
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_small_psd(int N, int logN, const float2 *__restrict__ tw,
+                                                     const float2 *__restrict__ x, size_t stream_stride,
+                                                     int frames_per_stream, const float *__restrict__ window,
+                                                     float *__restrict__ psd, int shift_db)
+{
+  extern __shared__ float2 sm[];
+  const int f = blockIdx.x;
+  const int stream = f / frames_per_stream, fr = f - stream * frames_per_stream;
+  const float2 *__restrict__ in = x + (size_t) stream * stream_stride + (size_t) fr * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float2 v = __ldg(in + i);
+    if (window) { const float w = __ldg(window + i); v.x *= w; v.y *= w; }
+    sm[i] = v;
+  }
+  __syncthreads();
+  block_fft_inplace<-1, 1>(sm, N, logN, threadIdx.x, blockDim.x, tw);
+  const float inv_n = 1.0f / (float) N;
+  float *__restrict__ out = psd + (size_t) f * N;
+  const int half = N >> 1;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const float2 X = sm[k];
+    float pw = (X.x * X.x + X.y * X.y) * inv_n;
+    if (shift_db) { pw = 10.0f * log10f(pw + 1e-8f); out[(k + half) & (N - 1)] = pw; }
+    else out[k] = pw;
+  }
+}
+
+cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const float2 *x,
+                                 size_t stream_stride, int frames_per_stream, int n_streams,
+                                 const float *window, float *psd, int shift_db)
+{
+  int threads = N / 4; if (threads < 32) threads = 32;
+  k_small_psd<<<frames_per_stream * n_streams, threads, (size_t) N * sizeof(float2), c.stream>>>(
+      N, ilog2(N), tw, x, stream_stride, frames_per_stream, window, psd, shift_db);
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// channeliser inverse side.  One CTA per (channel, stream); hops are processed in order because the
+// cross-fade needs the second half of the previous hop's IFFT (kept in shared memory, carried
+// between feeds in `tails`).
+// ---------------------------------------------------------------------------------------------
+template <int BPT>
+__global__ void __launch_bounds__(1024) k_chan_ifft(const SdbChannelDev *__restrict__ chans,
+                                                     const int *__restrict__ group, int n_channels,
+                                                     const float2 *__restrict__ cspec, int n_bins,
+                                                     int wps, float2 *__restrict__ tails,
+                                                     size_t tail_stream_stride, float *__restrict__ lo_phase,
+                                                     float2 *__restrict__ chan_out, size_t chan_stream_stride)
+{
+  extern __shared__ float2 sm[];
+  const int ci = group[blockIdx.x];
+  const SdbChannelDev ch = chans[ci];
+  const int s = blockIdx.y;
+  const int size = ch.size, hs = ch.halfsz, hw = ch.halfw;
+  float2 *buf = sm, *prev = sm + size;
+  float *phase = reinterpret_cast<float *>(prev + hs);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  float2 *__restrict__ tail = tails + (size_t) s * tail_stream_stride + ch.tail_off;
+  float2 *__restrict__ out = chan_out + (size_t) s * chan_stream_stride + ch.out_off;
+
+  for (int i = tid; i < hs; i += nthr) prev[i] = tail[i];
+  float lo_phi = ch.precise ? lo_phase[(size_t) s * n_channels + ci] : 0.0f;
+  __syncthreads();
+
+  for (int j = 0; j < wps; ++j) {
+    const float2 *__restrict__ cs = cspec + ((size_t) s * wps + j) * n_bins;
+    for (int i = tid; i < size; i += nthr) buf[i] = make_float2(0.0f, 0.0f);
+    __syncthreads();
+    for (int i = tid; i < 2 * hw; i += nthr) {
+      const int cidx = i < ch.L1 ? ch.c1 + i : i - ch.L1;
+      float2 X = __ldg(cs + cidx);
+      const float w = __ldg(ch.kh + i);
+      const int r = i - hw;
+      X.x *= w; X.y *= w;
+      buf[r >= 0 ? r : size + r] = X;
+    }
+    if (ch.precise && tid == 0) {
+      // sequential phase accumulation, exactly as the per-sample NCQO would do it
+      float phi = lo_phi;
+      for (int i = 0; i < hs; ++i) {
+        phase[i] = phi;
+        phi += ch.lo_omega;
+        if (phi >= 6.28318530717958647692f) phi -= 6.28318530717958647692f;
+        else if (phi < 0.0f) phi += 6.28318530717958647692f;
+      }
+      lo_phi = phi;
+    }
+    __syncthreads();
+    block_fft_inplace<+1, BPT>(buf, size, ch.log2size, tid, nthr, ch.tw);
+    for (int i = tid; i < hs; i += nthr) {
+      const float al = __ldg(ch.xfade + i), be = __ldg(ch.xfade + i + hs);
+      const float2 cu = buf[i], pv = prev[i];
+      float2 o = make_float2(al * cu.x + be * pv.x, al * cu.y + be * pv.y);
+      if (ch.precise) {
+        float sn, cs_;
+        sincosf(phase[i], &sn, &cs_);
+        o = cmulc(o, make_float2(cs_, sn));
+      }
+      out[(size_t) j * hs + i] = o;
+      prev[i] = buf[i + hs];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < hs; i += nthr) tail[i] = prev[i];
+  if (ch.precise && tid == 0) lo_phase[(size_t) s * n_channels + ci] = lo_phi;
+}
+
+// host side: channels grouped by size so that every CTA of a launch has the right block size
+cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDev *chans_dev,
+                                       const int *group_dev, int group_len, int size, int n_channels,
+                                       int n_streams, const float2 *cspec, int n_bins, int wps,
+                                       float2 *tails, size_t tail_stream_stride, float *lo_phase,
+                                       float2 *chan_out, size_t chan_stream_stride)
+{
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_chan_ifft<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_chan_ifft<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_chan_ifft<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const size_t smem = (size_t) size * sizeof(float2) + (size_t) (size / 2) * sizeof(float2)
+                      + (size_t) (size / 2) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  int bpt = 1, threads = size / 4;
+  while (threads > 1024) { threads >>= 1; bpt <<= 1; }
+  if (threads < 32) threads = 32;
+  dim3 grid(group_len, n_streams);
+  if (bpt == 1)
+    k_chan_ifft<1><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+                                                      tails, tail_stream_stride, lo_phase, chan_out,
+                                                      chan_stream_stride);
+  else if (bpt == 2)
+    k_chan_ifft<2><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+                                                      tails, tail_stream_stride, lo_phase, chan_out,
+                                                      chan_stream_stride);
+  else if (bpt == 4)
+    k_chan_ifft<4><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+                                                      tails, tail_stream_stride, lo_phase, chan_out,
+                                                      chan_stream_stride);
+  else
+    return cudaErrorInvalidValue;
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}

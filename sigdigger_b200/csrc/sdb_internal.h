@@ -1,0 +1,163 @@
+// sdb_internal.h -- structures shared by the host runtime (engine.cu) and the kernels.
+// Product code: nothing here includes or links oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define SDB_MAX_FIR      1024
+#define SDB_MAX_IIR      5        // coefficients (order <= 4)
+#define SDB_MAX_AGC_HIST 4096
+
+// ---------------------------------------------------------------------------------------------
+// FFT plan pieces (fft_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+struct SdbFourStep {
+  int N, N1, N2;            // N = N1 * N2; pass A does N1-point column FFTs, pass B N2-point row FFTs
+  const float2 *twN1;       // W_N1^i, i < N1 (forward sign)
+  const float2 *twN2;
+  const float2 *twN;        // W_N^i, i < N
+};
+
+struct SdbPassAArgs {
+  const float2 *x;          // new samples, stream 0
+  size_t        stream_stride;
+  const float2 *hist;       // [S][hist_len] samples preceding x (may be null when hist_len == 0)
+  int           hist_len;
+  int           windows_per_stream; // windows handled per stream in this launch
+  int           first_window;       // index of the first window (per stream) in this launch
+  int           hop;                // samples between consecutive windows
+  int           base_off;           // offset of window 0 in the virtual buffer hist ++ x
+  const float  *window;             // N taps or null
+  float2       *scratch;            // [launch windows][N1][N2] as [k1][n2]
+};
+
+struct SdbPassBArgs {
+  const float2 *scratch;
+  int           n_windows;          // windows in this launch (flattened stream-major)
+  // PSD epilogue
+  float        *psd;                // [n_windows][N]
+  float         inv_n;
+  int           shift_db;
+  // channeliser epilogue
+  const int    *binmap;             // N entries, compact index or -1
+  float2       *cspec;              // [n_windows][n_bins]
+  int           n_bins;
+};
+
+// ---------------------------------------------------------------------------------------------
+// channel plan (channeliser inverse side)
+// ---------------------------------------------------------------------------------------------
+struct SdbChannelDev {
+  int    center, size, log2size, halfw, halfsz;
+  // the channel's bins are the circular range [center-halfw, center+halfw) of the N-bin spectrum;
+  // in the compacted spectrum they form one run (c1, L1 entries) plus, when the range wraps past
+  // bin N-1, a second run starting at compact index 0.
+  int    c1, L1;
+  int    precise;
+  float  lo_omega;          // rad / channel sample
+  const float  *kh;         // 2*halfw weights k*h, ordered from bin center-halfw upwards
+  const float  *xfade;      // size cross-fade weights sin^2(pi i / size)
+  const float2 *tw;         // W_size^i (forward sign; conjugated for the inverse)
+  size_t out_off;           // offset (complex samples) of this channel inside one stream's channel block
+  size_t out_cap;           // capacity per feed
+  size_t tail_off;          // offset of this channel's halfsz-sample tail inside one stream's tail block
+};
+
+// ---------------------------------------------------------------------------------------------
+// inspector chains (chain_kernels.cu). Layout mirrors SPEC.md sections A, C, G, X.
+// ---------------------------------------------------------------------------------------------
+struct SdbChainCfg {
+  int   cls;                // SDB_INSP_*
+  int   have_agc, have_costas, have_pll, have_lo, have_mf;
+  int   clock_type, clock_running;
+  float gain2;
+  // agc
+  float knee, gain_slope, fixed_gain;
+  unsigned hang_max, dl_size, mh_size;
+  float far_, faf, sar, saf;
+  // costas / pll / lo
+  int   costas_kind;
+  float c_a, c_b;
+  int   af_n;               // arm filter coefficient count (1 = pass-through)
+  float af_b[SDB_MAX_IIR], af_a[SDB_MAX_IIR];
+  float pll_alpha, pll_beta;
+  float lo_omega;
+  // fsk / ask
+  int   fsk_quad_demod;
+  float fsk_rot_re, fsk_rot_im;
+  int   ask_channel;
+  // matched filter
+  int   mf_n;
+  int   mf_off;             // offset into the taps pool
+  // clock
+  float clk_gain, clk_alpha, clk_beta, bnor;
+  float smp_period, smp_phase0;
+  // decider
+  int   dec_mode, dec_intervals;
+  float dec_min, dec_h;
+  // audio
+  int   audio_demod, audio_squelch;
+  float audio_volume, dc_alpha, sq_alpha, sq_thr;
+  int   alpf_n;
+  float alpf_b[SDB_MAX_IIR], alpf_a[SDB_MAX_IIR];
+  double rs_step;
+  // per-chain state pool sizes (in floats) so the kernel can index the pools
+  int   st_dl_off, st_mh_off, st_mf_off;  // offsets inside one chain's float pool
+  int   st_pool;                           // floats per chain
+};
+
+struct SdbChainState {
+  // agc
+  float fast_level, slow_level, peak;
+  unsigned hang_n, dl_ptr, mh_ptr;
+  // costas
+  float c_phi, c_omega, c_lock, c_yre, c_yim;
+  float afx_re[SDB_MAX_IIR], afx_im[SDB_MAX_IIR], afy_re[SDB_MAX_IIR], afy_im[SDB_MAX_IIR];
+  unsigned afxp, afyp;
+  // pll / lo
+  float p_phi, p_omega, lo_phi;
+  // fsk / fm
+  float prev_re, prev_im;
+  // mf
+  unsigned mf_ptr;
+  // clock
+  float k_phi, k_bnor, k_x0r, k_x0i, k_x1r, k_x1i, k_x2r, k_x2i, k_pr, k_pi;
+  int   k_half;
+  float s_phase, s_pr, s_pi;
+  // audio
+  float dc, sq_level, rs_prev;
+  float al_x[SDB_MAX_IIR], al_y[SDB_MAX_IIR];
+  unsigned al_xp, al_yp;
+  double rs_phase;
+  int   fm_primed;
+};
+
+// host-callable launchers ----------------------------------------------------------------------
+struct SdbLaunchCtx {
+  cudaStream_t stream;
+  uint64_t    *launch_counter;
+};
+
+cudaError_t sdb_launch_pass_a_range(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
+                                    int win_base, int n_win);
+cudaError_t sdb_launch_pass_b_psd(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a);
+cudaError_t sdb_launch_pass_b_chan(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a);
+cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const float2 *x,
+                                 size_t stream_stride, int frames_per_stream, int n_streams,
+                                 const float *window, float *psd, int shift_db);
+cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDev *chans_dev,
+                                       const int *group_dev, int group_len, int size, int n_channels,
+                                       int n_streams, const float2 *cspec, int n_bins, int wps,
+                                       float2 *tails, size_t tail_stream_stride, float *lo_phase,
+                                       float2 *chan_out, size_t chan_stream_stride);
+cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cfg_dev, int n_channels,
+                                    int n_streams, SdbChainState *state, float *pool, size_t pool_stride,
+                                    const float *taps_pool, const SdbChannelDev *chans_dev,
+                                    const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
+                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap);
+cudaError_t sdb_launch_task_xlate(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
+                                  float omega, float phi0);
+cudaError_t sdb_launch_task_quad(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch);
+cudaError_t sdb_launch_task_chain(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
+                                  const SdbChainCfg &c, int mode, float *pool, size_t pool_stride);
