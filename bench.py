@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the analyzer hot path (main PSD + FFT channeliser + inspectors).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement on the host cores
+
+Workload (BASELINE.json configs[1], "cfg2"): complex64 IQ at a nominal 100 MS/s, 65536-point
+Blackman-Harris main spectrum over every frame + one QPSK inspector (1 MBd, RRC 0.35, Costas + Gardner,
+3 MHz channel at +12.5 MHz -> 2048-point IFFT, decimation 32).  `--workload cfg3` selects the 64-inspector
+mix of configs[2].  One "step" = one pass over a batch of `streams` independent IQ streams of
+`hops * 32768` samples each (the serial carrier/clock loops bound a single stream, so the engine batches
+independent sources; config.streams says how many).  Metric: complex MSamples/s ingested, whole job.
+
+Prints ONE JSON line (see README / DESIGN.md section "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FFT = 65536
+FS = 100e6
+B_ALG = {"cfg2": 12.09, "cfg3": 14.41}     # BASELINE.md section 3, bytes per input sample
+
+
+# --------------------------------------------------------------------------------------------------
+# workload definition (shared by both arms)
+# --------------------------------------------------------------------------------------------------
+def workload_channels(name):
+    """-> list of (kind, f_hz, baud, bw_hz, inspector class, config kwargs builder(fs_ch))."""
+    if name == "cfg2":
+        return [("qpsk", 12.5e6 + 300.0, 1e6, 3e6)]
+    if name == "cfg3":
+        out = []
+        for k in range(64):
+            f = (k - 31.5) * 3e6
+            kind = ("fsk", "qpsk", "ask")[k % 3]
+            baud = 0.5e6 if kind == "ask" else 1e6
+            out.append((kind, f + 300.0, baud, 2.5e6))
+        return out
+    raise ValueError(name)
+
+
+def insp_kwargs(kind, baud, fs_ch):
+    if kind == "qpsk":
+        return "psk", dict(baud=baud, costas_order=2, bits_per_symbol=2, loop_bw=fs_ch * 2e-3, mf_type=1,
+                           mf_rolloff=0.35, clock_type=1, clock_gain=0.1)
+    if kind == "fsk":
+        return "fsk", dict(baud=baud, bits_per_symbol=1, mf_type=1, mf_rolloff=0.35, clock_type=1, clock_gain=0.2)
+    if kind == "ask":
+        return "ask", dict(baud=baud, bits_per_symbol=1, ask_use_pll=1, ask_channel=0, loop_bw=fs_ch * 5e-3,
+                           mf_type=1, mf_rolloff=0.35, clock_type=1, clock_gain=0.2)
+    raise ValueError(kind)
+
+
+def chan_angular(f_hz, bw_hz):
+    f0 = 2 * np.pi * ((f_hz - 300.0) / FS % 1.0)
+    return float(np.float32(f0)), float(np.float32(2 * np.pi * bw_hz / FS))
+
+
+def make_base_signal(name, n, seed):
+    from sigdigger_b200 import synth
+    carriers = []
+    for kind, f, baud, _ in workload_channels(name):
+        kw = {"levels": 2} if kind == "ask" else {}
+        carriers.append((kind, f, baud, -20.0 if name == "cfg3" else -12.0, kw))
+    x, _ = synth.multi_carrier(n, FS, carriers, noise_db=-80.0, seed=seed)
+    return x
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if o.returncode == 0 and o.stdout.strip():
+                    self.rows.append([c.strip() for c in o.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle restatement on the host cores
+# --------------------------------------------------------------------------------------------------
+def oracle_params(name):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    chans = []
+    for kind, f, baud, bw in workload_channels(name):
+        f0, bwa = chan_angular(f, bw)
+        _, size, _ = O.channel_geometry(N_FFT, f0, bwa, 1.0)
+        fs_ch = FS * size / N_FFT
+        cls, kw = insp_kwargs(kind, baud, fs_ch)
+        chans.append((f0, bwa, 1.0, 0, O.insp_config(cls, fs_ch, **kw)))
+    return O, O.make_an_params(N_FFT, "blackmann_harris", chans)
+
+
+def cpu_run(name, n_streams, n, threads, reps=1, warm=0):
+    import ctypes as C
+    O, p = oracle_params(name)
+    base = make_base_signal(name, n, seed=1)
+    x = np.ascontiguousarray(np.tile(base, (n_streams, 1)))
+    rng = np.random.default_rng(0)
+    x += (1e-3 * (rng.standard_normal(x.shape) + 1j * rng.standard_normal(x.shape))).astype(np.complex64)
+    chk = C.c_uint64()
+    times = []
+    for i in range(warm + reps):
+        t = O.lib().sdo_baseline_run(C.byref(p), O.ptr(x), n_streams, n, threads, C.byref(chk))
+        if i >= warm:
+            times.append(t)
+    return times, n_streams * n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = N_FFT // 2 * 32                      # 2^20 samples per stream
+    streams = min(cores, 16)
+    times, samples = cpu_run(args.workload, streams, n, cores, reps=args.steps, warm=args.warmup)
+    total = sum(times)
+    v = samples * len(times) / total / 1e6
+    sample = "%d streams x %d samples per step, %d OpenMP threads" % (streams, n, cores)
+    out = {"impl": "reference", "metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)",
+           "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args, streams=streams, hops=32),
+           "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload_config(args, streams, hops):
+    k = len(workload_channels(args.workload))
+    return {"workload": "%s: fs 100 MS/s nominal, 65536-pt Blackman-Harris PSD every frame + 65536-pt "
+                        "50%%-overlap FFT channeliser + %d inspector(s) (%s), Costas + RRC + Gardner + decision"
+                        % (args.workload, k, "QPSK 1 MBd" if args.workload == "cfg2" else "2-FSK / QPSK / ASK mix"),
+            "streams_per_gpu": streams, "samples_per_stream_per_step": hops * N_FFT // 2,
+            "inputs": "larger than L2 (no flush needed)", "parallelism": "independent streams per GPU"}
+
+
+# --------------------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------------------
+def build_engine(sdb, name, streams, n, device):
+    e = sdb.Engine(n_streams=streams, psd_size=N_FFT, psd_window="blackmann_harris", max_feed=n,
+                   samp_rate=FS, device=device)
+    hs = []
+    for kind, f, baud, bw in workload_channels(name):
+        f0, bwa = chan_angular(f, bw)
+        h = e.open_channel(f0, bwa, 1.0)
+        cls, kw = insp_kwargs(kind, baud, e.channel_rate(h))
+        e.set_inspector(h, cls, **kw)
+        hs.append(h)
+    e.commit()
+    return e, hs
+
+
+def run_cuda(args):
+    import torch
+    import sigdigger_b200 as sdb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if sdb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    name = args.workload
+    S, H = args.streams, args.hops
+    n = H * N_FFT // 2
+    e, hs = build_engine(sdb, name, S, n, local)
+    K = len(hs)
+
+    # synthetic IQ, device resident: one modulated base signal per rank + independent noise per stream
+    base = torch.from_numpy(make_base_signal(name, n, seed=1 + rank)).cuda()
+    x = base.unsqueeze(0).repeat(S, 1).contiguous()
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x += torch.view_as_complex(1e-3 * torch.randn((S, n, 2), generator=g, device="cuda"))
+    xh = torch.empty((S, n), dtype=torch.complex64, pin_memory=True)
+    xh.copy_(x)
+    torch.cuda.synchronize()
+
+    es = torch.cuda.ExternalStream(e.stream_ptr)
+    samples_step = S * n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(es)
+        for _ in range(steps):
+            fn()
+        b.record(es)
+        e.sync()
+        ms = a.elapsed_time(b)
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident arm
+    step_dev = lambda: e.feed_device_ptr(x.data_ptr(), x.stride(0), n)
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    e.sync()
+    l0 = e.launches
+    with Clocks(local) as clk:
+        ms = timed(step_dev, args.steps)
+    launches = e.launches - l0
+    value = samples_step * world * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel device times (separate, untimed-for-value pass with event spans)
+    e.timing(True)
+    for _ in range(2):
+        step_dev()
+    e.sync()
+    fam = {f: e.kernel_time(f) for f in ("fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft", "inspector")}
+    e.timing(False)
+    wps, frames = H, H // 2
+    chunk = max(1, (32 << 20) // (N_FFT * 8))
+    nb = sum(2 * (e.channel_info(h).width // 2) for h in hs)
+    alg = {"fft_cols": min(chunk, S * wps) * N_FFT * 8.0,
+           "fft_rows_psd": min(chunk, S * frames) * N_FFT * 4.0,
+           "fft_rows_chan": min(chunk, S * wps) * nb * 8.0,
+           "chan_ifft": S * wps * nb * 8.0 + sum(S * wps * e.channel_info(h).size // 2 * 8.0 for h in hs),
+           "inspector": sum(S * wps * e.channel_info(h).size // 2 * 8.0 for h in hs) * 1.5}
+    tot = {f: fam[f][0] * fam[f][1] for f in fam}
+    dom = max(tot, key=tot.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg[dom] / (fam[dom][0] * 1e-3) / 1e9 if fam[dom][0] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "kernel_share_of_step": tot[dom] / max(1e-9, sum(tot.values())),
+                "kernel_ms": {f: round(fam[f][0], 4) for f in fam},
+                "path": {"b_alg_bytes_per_sample": B_ALG[name],
+                         "achieved": B_ALG[name] * value * 1e6 / world / 1e9,
+                         "frac": B_ALG[name] * value * 1e6 / world / 1e9 / peak}}
+
+    # ---- end to end: pinned host IQ -> H2D -> path -> D2H of PSD frames and symbols, every step
+    cap = e.symbol_capacity
+    psd_h = torch.empty((S, frames, N_FFT), dtype=torch.float32, pin_memory=True).numpy()
+    cnt_h = np.zeros(S * K, np.uint32)
+    soft_h = torch.empty((S * K, cap), dtype=torch.complex64, pin_memory=True).numpy()
+    hard_h = torch.empty((S * K, cap), dtype=torch.uint8, pin_memory=True).numpy()
+
+    def step_e2e():
+        e.feed_host_ptr(xh.data_ptr(), xh.stride(0), n)
+        e.read_psd(psd_h)
+        e.read_all_symbols(cnt_h, soft_h, hard_h, cap)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e.sync()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_v = samples_step * world * args.steps / dt / 1e6
+    h2d = samples_step * 8
+    d2h = psd_h.nbytes + cnt_h.nbytes + soft_h.nbytes + hard_h.nbytes
+
+    # ---- single-stream number (what one continuous source gets)
+    single = None
+    if rank == 0 and not args.no_single:
+        e1, _ = build_engine(sdb, name, 1, n, local)
+        x1 = x[:1].contiguous()
+        for _ in range(3):
+            e1.feed_device_ptr(x1.data_ptr(), x1.stride(0), n)
+        e1.sync()
+        es1 = torch.cuda.ExternalStream(e1.stream_ptr)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(es1)
+        for _ in range(5):
+            e1.feed_device_ptr(x1.data_ptr(), x1.stride(0), n)
+        b.record(es1)
+        e1.sync()
+        single = n * 5 / (a.elapsed_time(b) * 1e-3) / 1e6
+        e1.close()
+
+    # ---- bounded CPU baseline on rank 0, N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        times, samples = cpu_run(name, min(cores, 16), N_FFT // 2 * 32, cores, reps=2, warm=0)
+        cpu = {"value": samples * len(times) / sum(times) / 1e6, "unit": "MS/s", "cores": cores, "kind": "port",
+               "sample": "%d streams x %d samples x %d reps of the same workload (oracle restatement, OpenMP)"
+                         % (min(cores, 16), N_FFT // 2 * 32, len(times))}
+
+    if rank == 0:
+        out = {"metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)", "value": value,
+               "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args, S, H),
+               "clocks": clk.summary(), "gpu_launches": int(launches),
+               "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+               "roofline": roofline, "cpu_baseline": cpu, "single_stream_msps": single}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--hops", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
+    args = ap.parse_args()
+    if args.streams == 0:
+        args.streams = 256 if args.workload == "cfg2" else 64
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,362 +36,547 @@ static __device__ __forceinline__ float2 ncqo_read(float &phi, float omega)
   return make_float2(c, s);
 }
 
-// Small direct-form filter with circular lines of length n (SPEC I): used for the Costas arm filter
-// and the audio low-pass.  Lines live in the state struct (registers / local memory).
-static __device__ __forceinline__ float2 iir_feed(const float *b, const float *a, int n,
-                                                  float *xre, float *xim, float *yre, float *yim,
-                                                  unsigned &xp, unsigned &yp, float2 x)
+// ------------------------------------------------------------------ small IIR/FIR, shift registers --
+// y[n] = sum_{i<N} b[i] x[n-i] - sum_{1<=i<N} a[i] y[n-i], single accumulator, ascending i (SPEC I.1).
+// Lines are shift registers ([0] newest) so every index is a compile-time constant -> registers.
+template <int N>
+static __device__ __forceinline__ float2 iir_step(const float (&b)[SDB_MAX_IIR], const float (&a)[SDB_MAX_IIR],
+                                                  float (&xr)[SDB_MAX_IIR], float (&xi)[SDB_MAX_IIR],
+                                                  float (&yr)[SDB_MAX_IIR], float (&yi)[SDB_MAX_IIR], float2 in)
 {
-  float accr = 0.0f, acci = 0.0f;
-  xre[xp] = x.x; xim[xp] = x.y;
-  unsigned p = xp;
-  for (int i = 0; i < n; ++i) {
-    accr = accr + b[i] * xre[p];
-    acci = acci + b[i] * xim[p];
-    p = p == 0 ? n - 1 : p - 1;
+#pragma unroll
+  for (int i = N - 1; i > 0; --i) { xr[i] = xr[i - 1]; xi[i] = xi[i - 1]; }
+  xr[0] = in.x; xi[0] = in.y;
+  float ar = 0.0f, ai = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { ar = ar + b[i] * xr[i]; ai = ai + b[i] * xi[i]; }
+  if (N > 1) {
+#pragma unroll
+    for (int i = 1; i < N; ++i) { ar = ar - a[i] * yr[i - 1]; ai = ai - a[i] * yi[i - 1]; }
+#pragma unroll
+    for (int i = N - 1; i > 0; --i) { yr[i] = yr[i - 1]; yi[i] = yi[i - 1]; }
+    yr[0] = ar; yi[0] = ai;
   }
-  xp = xp + 1 == (unsigned) n ? 0 : xp + 1;
-  if (n > 1) {
-    p = yp;
-    for (int i = 1; i < n; ++i) {
-      accr = accr - a[i] * yre[p];
-      acci = acci - a[i] * yim[p];
-      p = p == 0 ? n - 1 : p - 1;
-    }
-    yp = yp + 1 == (unsigned) n ? 0 : yp + 1;
-    yre[yp] = accr; yim[yp] = acci;
-  }
-  return make_float2(accr, acci);
+  return make_float2(ar, ai);
 }
 
-// ------------------------------------------------------------------ chain blocks ----------------
-struct AgcView {
-  float *dl_re, *dl_im, *mh;     // strided pools in global memory
-  int stride;
-};
-
-static __device__ __forceinline__ float2 agc_feed(const SdbChainCfg &c, SdbChainState &st, float *dl,
-                                                  float *mh, float2 x)
+static __device__ __forceinline__ float2 iir_any(int n, const float (&b)[SDB_MAX_IIR], const float (&a)[SDB_MAX_IIR],
+                                                 float (&xr)[SDB_MAX_IIR], float (&xi)[SDB_MAX_IIR],
+                                                 float (&yr)[SDB_MAX_IIR], float (&yi)[SDB_MAX_IIR], float2 in)
 {
-  // delay line stores interleaved re, im
-  float2 xd = make_float2(dl[2 * st.dl_ptr], dl[2 * st.dl_ptr + 1]);
-  dl[2 * st.dl_ptr] = x.x; dl[2 * st.dl_ptr + 1] = x.y;
-  if (++st.dl_ptr >= c.dl_size) st.dl_ptr = 0;
-
-  float m = 10.0f * d_log10f(x.x * x.x + x.y * x.y + 1e-16f);
-  float m_old = mh[st.mh_ptr];
-  mh[st.mh_ptr] = m;
-  if (++st.mh_ptr >= c.mh_size) st.mh_ptr = 0;
-
-  if (m > st.peak) {
-    st.peak = m;
-  } else if (st.peak == m_old) {
-    float pk = -160.0f;
-    for (unsigned i = 0; i < c.mh_size; ++i) {
-      float v = mh[i];
-      if (pk < v) pk = v;
-    }
-    st.peak = pk;
+  switch (n) {
+    case 1:  return iir_step<1>(b, a, xr, xi, yr, yi, in);
+    case 2:  return iir_step<2>(b, a, xr, xi, yr, yi, in);
+    case 3:  return iir_step<3>(b, a, xr, xi, yr, yi, in);
+    case 4:  return iir_step<4>(b, a, xr, xi, yr, yi, in);
+    default: return iir_step<5>(b, a, xr, xi, yr, yi, in);
   }
-  float d = st.peak - st.fast_level;
-  if (d > 0.0f) st.fast_level = st.fast_level + c.far_ * d;
-  else          st.fast_level = st.fast_level + c.faf * d;
-  d = st.peak - st.slow_level;
-  if (d > 0.0f) {
-    st.slow_level = st.slow_level + c.sar * d;
-    st.hang_n = 0;
-  } else if (st.hang_n >= c.hang_max) {
-    st.slow_level = st.slow_level + c.saf * d;
-  } else {
-    ++st.hang_n;
-  }
-  float lvl = st.fast_level > st.slow_level ? st.fast_level : st.slow_level;
-  float g = lvl < c.knee ? c.fixed_gain : d_db_to_mag(lvl * (c.gain_slope - 1.0f));
-  g = g * 0.7f;
-  xd.x = xd.x * g;
-  xd.y = xd.y * g;
-  return xd;
 }
 
 static __device__ __forceinline__ float sgnf(float v) { return v < 0.0f ? -1.0f : (v > 0.0f ? 1.0f : 0.0f); }
 
-static __device__ __forceinline__ float2 costas_feed(const SdbChainCfg &c, SdbChainState &st, float2 x)
+// ------------------------------------------------------------------ per-block state, all in registers --
+// AGC (SPEC A).  dl / mh are strided arrays (stride 32 floats: one column per lane).
+struct AgcK {
+  float knee, slope_m1, fixed_gain, far_, faf, sar, saf;
+  unsigned hang_max, dl_size, mh_size;
+};
+struct AgcS { float fast, slow, peak; unsigned hang_n, dl_ptr, mh_ptr; };
+
+static __device__ __forceinline__ float2 agc_step(const AgcK &k, AgcS &s, float *dl, float *mh, float2 x)
 {
-  float2 s = ncqo_read(st.c_phi, st.c_omega);
-  float2 mixed = make_float2(x.x * s.x + x.y * s.y, x.y * s.x - x.x * s.y);
-  float2 z = iir_feed(c.af_b, c.af_a, c.af_n, st.afx_re, st.afx_im, st.afy_re, st.afy_im, st.afxp,
-                      st.afyp, mixed);
-  float e = 0.0f, lr, li;
-  switch (c.costas_kind) {
-    case 1:
-      e = -(z.x * z.y);
-      break;
-    case 2:
-      lr = sgnf(z.x); li = sgnf(z.y);
-      e = lr * z.y - li * z.x;
-      break;
-    case 3:
-      lr = sgnf(z.x); li = sgnf(z.y);
-      if (fabsf(z.x) >= fabsf(z.y)) e = lr * z.y - li * z.x * 0.41421356237309504f;
-      else                          e = lr * z.y * 0.41421356237309504f - li * z.x;
-      break;
-    default:
-      break;
+  float2 xd = make_float2(dl[(2 * s.dl_ptr) * 32], dl[(2 * s.dl_ptr + 1) * 32]);
+  dl[(2 * s.dl_ptr) * 32] = x.x; dl[(2 * s.dl_ptr + 1) * 32] = x.y;
+  if (++s.dl_ptr >= k.dl_size) s.dl_ptr = 0;
+  float m = 10.0f * d_log10f(x.x * x.x + x.y * x.y + 1e-16f);
+  float m_old = mh[s.mh_ptr * 32];
+  mh[s.mh_ptr * 32] = m;
+  if (++s.mh_ptr >= k.mh_size) s.mh_ptr = 0;
+  if (m > s.peak) {
+    s.peak = m;
+  } else if (s.peak == m_old) {
+    float pk = -160.0f;
+    for (unsigned i = 0; i < k.mh_size; ++i) { float v = mh[i * 32]; if (pk < v) pk = v; }
+    s.peak = pk;
   }
-  st.c_lock = st.c_lock + c.c_a * (1.0f - e - st.c_lock);
-  st.c_yre = st.c_yre + 1.0f * (z.x - st.c_yre);
-  st.c_yim = st.c_yim + 1.0f * (z.y - st.c_yim);
-  st.c_omega = st.c_omega + c.c_b * e;
-  st.c_phi = wrap_once(st.c_phi + c.c_a * e);
-  return make_float2(st.c_yre, st.c_yim);
+  float d = s.peak - s.fast;
+  if (d > 0.0f) s.fast = s.fast + k.far_ * d;
+  else          s.fast = s.fast + k.faf * d;
+  d = s.peak - s.slow;
+  if (d > 0.0f) { s.slow = s.slow + k.sar * d; s.hang_n = 0; }
+  else if (s.hang_n >= k.hang_max) s.slow = s.slow + k.saf * d;
+  else ++s.hang_n;
+  float lvl = s.fast > s.slow ? s.fast : s.slow;
+  float g = lvl < k.knee ? k.fixed_gain : d_db_to_mag(lvl * k.slope_m1);
+  g = g * 0.7f;
+  xd.x = xd.x * g; xd.y = xd.y * g;
+  return xd;
 }
 
-static __device__ __forceinline__ float2 pll_track(const SdbChainCfg &c, SdbChainState &st, float2 x)
+struct CostasK { int kind, af_n; float a, b; float af_b[SDB_MAX_IIR], af_a[SDB_MAX_IIR]; };
+struct CostasS { float phi, omega, lock, yre, yim; float xr[SDB_MAX_IIR], xi[SDB_MAX_IIR], yr[SDB_MAX_IIR], yi[SDB_MAX_IIR]; };
+
+static __device__ __forceinline__ float2 costas_step(const CostasK &k, CostasS &s, float2 x)
 {
-  float2 ref = ncqo_read(st.p_phi, st.p_omega);
+  float2 n = ncqo_read(s.phi, s.omega);
+  float2 mixed = make_float2(x.x * n.x + x.y * n.y, x.y * n.x - x.x * n.y);
+  float2 z = iir_any(k.af_n, k.af_b, k.af_a, s.xr, s.xi, s.yr, s.yi, mixed);
+  float e = 0.0f, lr, li;
+  if (k.kind == 1) {
+    e = -(z.x * z.y);
+  } else if (k.kind == 2) {
+    lr = sgnf(z.x); li = sgnf(z.y);
+    e = lr * z.y - li * z.x;
+  } else if (k.kind == 3) {
+    lr = sgnf(z.x); li = sgnf(z.y);
+    if (fabsf(z.x) >= fabsf(z.y)) e = lr * z.y - li * z.x * 0.41421356237309504f;
+    else                          e = lr * z.y * 0.41421356237309504f - li * z.x;
+  }
+  s.lock = s.lock + k.a * (1.0f - e - s.lock);
+  s.yre = s.yre + 1.0f * (z.x - s.yre);
+  s.yim = s.yim + 1.0f * (z.y - s.yim);
+  s.omega = s.omega + k.b * e;
+  s.phi = wrap_once(s.phi + k.a * e);
+  return make_float2(s.yre, s.yim);
+}
+
+static __device__ __forceinline__ float2 pll_step(float alpha, float beta, float &phi, float &omega, float2 x)
+{
+  float2 ref = ncqo_read(phi, omega);
   float2 mix = make_float2(x.x * ref.x + x.y * ref.y, x.y * ref.x - x.x * ref.y);
-  float err = d_atan2f(x.y, x.x) - st.p_phi;
+  float err = d_atan2f(x.y, x.x) - phi;
   if (err > PI_F) err = err - TWOPI_F;
   else if (err < -PI_F) err = err + TWOPI_F;
-  st.p_omega = st.p_omega + c.pll_alpha * err;
-  st.p_phi = wrap_once(st.p_phi + c.pll_beta * err);
+  omega = omega + alpha * err;
+  phi = wrap_once(phi + beta * err);
   return mix;
 }
 
-static __device__ __forceinline__ bool clock_feed(const SdbChainCfg &c, SdbChainState &st, float2 v,
-                                                  float2 &out)
+struct ClockS { float phi, bnor, x0r, x0i, x1r, x1i, x2r, x2i, pr, pi; int half; };
+
+static __device__ __forceinline__ bool clock_step(float gain, float alpha, float beta, ClockS &s, float2 v, float2 &out)
 {
   bool produced = false;
-  st.k_phi = st.k_phi + st.k_bnor;
-  if (st.k_phi >= 0.5f) {
-    float al = st.k_bnor * (st.k_phi - 0.5f);
+  s.phi = s.phi + s.bnor;
+  if (s.phi >= 0.5f) {
+    float al = s.bnor * (s.phi - 0.5f);
     float om = 1.0f - al;
-    float pr = om * v.x + al * st.k_pr;
-    float pi = om * v.y + al * st.k_pi;
-    st.k_half = !st.k_half;
-    st.k_phi = st.k_phi - 0.5f;
-    if (!st.k_half) {
-      st.k_x2r = st.k_x0r; st.k_x2i = st.k_x0i;
-      st.k_x0r = pr; st.k_x0i = pi;
-      float dr = st.k_x0r - st.k_x2r;
-      float di = st.k_x0i - st.k_x2i;
-      float e = c.clk_gain * (st.k_x1r * dr + st.k_x1i * di);
-      st.k_phi = st.k_phi + c.clk_alpha * e;
-      float bn = st.k_bnor + c.clk_beta * e;
+    float pr = om * v.x + al * s.pr;
+    float pi = om * v.y + al * s.pi;
+    s.half = !s.half;
+    s.phi = s.phi - 0.5f;
+    if (!s.half) {
+      s.x2r = s.x0r; s.x2i = s.x0i;
+      s.x0r = pr; s.x0i = pi;
+      float dr = s.x0r - s.x2r;
+      float di = s.x0i - s.x2i;
+      float e = gain * (s.x1r * dr + s.x1i * di);
+      s.phi = s.phi + alpha * e;
+      float bn = s.bnor + beta * e;
       if (bn > 1.0f) bn = 1.0f;
       if (bn < 0.0f) bn = 0.0f;
-      st.k_bnor = bn;
+      s.bnor = bn;
       out = make_float2(pr, pi);
       produced = true;
     } else {
-      st.k_x1r = pr; st.k_x1i = pi;
+      s.x1r = pr; s.x1i = pi;
     }
   }
-  st.k_pr = v.x; st.k_pi = v.y;
+  s.pr = v.x; s.pi = v.y;
   return produced;
 }
 
-static __device__ __forceinline__ bool sampler_feed(const SdbChainCfg &c, SdbChainState &st, float2 v,
-                                                    float2 &out)
+static __device__ __forceinline__ bool sampler_step(float period, float phase0, float &phase, float &pr, float &pi,
+                                                    float2 v, float2 &out)
 {
   bool sampled = false;
-  if (c.smp_period >= 1.0f) {
-    st.s_phase = st.s_phase + 1.0f;
-    if (st.s_phase >= c.smp_period) st.s_phase = st.s_phase - c.smp_period;
-    float ph = st.s_phase - c.smp_phase0;
-    if (ph < 0.0f) ph = ph + c.smp_period;
+  if (period >= 1.0f) {
+    phase = phase + 1.0f;
+    if (phase >= period) phase = phase - period;
+    float ph = phase - phase0;
+    if (ph < 0.0f) ph = ph + period;
     float fl = floorf(ph);
     if (fl == 0.0f) {
       float al = ph - fl, om = 1.0f - al;
-      out = make_float2(om * st.s_pr + al * v.x, om * st.s_pi + al * v.y);
+      out = make_float2(om * pr + al * v.x, om * pi + al * v.y);
       sampled = true;
     }
   }
-  st.s_pr = v.x; st.s_pi = v.y;
+  pr = v.x; pi = v.y;
   return sampled;
 }
 
-static __device__ __forceinline__ unsigned char decide(const SdbChainCfg &c, float2 x)
+static __device__ __forceinline__ unsigned char decide(int mode, float dmin, float dh, int intervals, float2 x)
 {
-  float v = c.dec_mode == 0 ? d_atan2f(x.y, x.x) : d_cabsf(x.x, x.y);
-  float s = floorf((v - c.dec_min) / c.dec_h * (float) c.dec_intervals);
+  float v = mode == 0 ? d_atan2f(x.y, x.x) : d_cabsf(x.x, x.y);
+  float s = floorf((v - dmin) / dh * (float) intervals);
   int k = (int) s;
   if (!(s >= 0.0f)) k = 0;
-  if (k > c.dec_intervals - 1) k = c.dec_intervals - 1;
+  if (k > intervals - 1) k = intervals - 1;
   return (unsigned char) k;
 }
 
 // ------------------------------------------------------------------ the chain kernel ------------
-// grid: ceil(S*K / block). thread -> chain (s, k).  Per-chain float pool layout:
-//   [st_dl_off .. +2*dl_size) AGC delay line, [st_mh_off .. +mh_size) magnitude history,
-//   [st_mf_off .. +2*mf_n) matched-filter delay line.
-__global__ void __launch_bounds__(64) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
-                                                    int n_streams, SdbChainState *__restrict__ states,
-                                                    float *__restrict__ pool, size_t pool_stride,
-                                                    const float *__restrict__ taps_pool,
-                                                    const SdbChannelDev *__restrict__ chans,
-                                                    const float2 *__restrict__ chan_in,
-                                                    size_t chan_stream_stride, uint32_t n_in,
-                                                    float2 *__restrict__ soft, unsigned char *__restrict__ hard,
-                                                    uint32_t *__restrict__ sym_counts, size_t sym_cap)
+// One CTA = 32 chains x 4 stage-warps.  Warp w runs stage w of every chain of the CTA (lane = chain):
+//   warp 0  gain      : manual offset LO, AGC / fixed gain                     -> ring A
+//   warp 1  carrier   : Costas | PLL + component select | FSK discriminator | audio demodulators -> ring B
+//   warp 2  filter    : RRC matched filter (FIR) | audio low-pass            -> ring C
+//   warp 3  clock     : Gardner | manual sampler | audio resampler, x0.75, decision, output
+// Stage w works on chunk (it - w) of CHUNK samples while stage w+1 works on the previous one, so the
+// serial latency per sample is that of the slowest stage (the carrier loop), not the sum; loop state
+// lives in registers for the whole feed.  Chains are ordered channel-major so a warp normally holds 32
+// streams of the SAME channel (uniform configuration, no divergence).
+#define CHUNK 32
+#define MF_RING 64
+struct ChainSmem {
+  float2 tile[32][33];
+  float2 ring[3][2][CHUNK][32];
+  float2 mfh[MF_RING][32];
+  float  agc[48][32];
+};
+
+__global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
+                                                     int n_streams, SdbChainState *__restrict__ states,
+                                                     float *__restrict__ pool, size_t pool_stride,
+                                                     const float *__restrict__ taps_pool,
+                                                     const SdbChannelDev *__restrict__ chans,
+                                                     const float2 *__restrict__ chan_in,
+                                                     size_t chan_stream_stride, uint32_t n_hops,
+                                                     float2 *__restrict__ soft, unsigned char *__restrict__ hard,
+                                                     uint32_t *__restrict__ sym_counts, size_t sym_cap, int fresh)
 {
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= n_channels * n_streams) return;
-  const int s = chain / n_channels, k = chain - s * n_channels;
-  const SdbChainCfg c = cfgs[k];
-  SdbChainState st = states[chain];
-  float *mypool = pool + (size_t) chain * pool_stride;
-  float *dl = mypool + c.st_dl_off, *mh = mypool + c.st_mh_off, *mfl = mypool + c.st_mf_off;
-  const float *taps = taps_pool + c.mf_off;
-  const SdbChannelDev ch = chans[k];
-  // number of channel samples this feed: n_in hops worth
-  const uint32_t n = n_in * (uint32_t) ch.halfsz;
-  const float2 *__restrict__ in = chan_in + (size_t) s * chan_stream_stride + ch.out_off;
-  float2 *__restrict__ so = soft + (size_t) chain * sym_cap;
-  unsigned char *__restrict__ ho = hard + (size_t) chain * sym_cap;
+  extern __shared__ unsigned char smem_raw[];
+  ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chains = n_channels * n_streams;
+  const int g = blockIdx.x * 32 + lane;                // channel-major chain index
+  const bool valid = g < chains;
+  const int k = valid ? g / n_streams : 0, s = valid ? g - k * n_streams : 0;
+  const int chain = s * n_channels + k;                // index into states / outputs (stream-major)
+  const SdbChainCfg *__restrict__ cp = cfgs + k;
+  const int cls = valid ? cp->cls : -1;
+  const uint32_t n = valid ? n_hops * (uint32_t) chans[k].halfsz : 0;
+  // per-CTA pool, interleaved [slot][lane]
+  float *bpool = pool + (size_t) blockIdx.x * 32 * pool_stride + lane;
+  // number of chunks: CTA-wide maximum
+  __shared__ uint32_t s_nmax;
+  if (threadIdx.x == 0) s_nmax = 0;
+  __syncthreads();
+  if (warp == 0) atomicMax(&s_nmax, n);
+  __syncthreads();
+  const uint32_t nchunks = (s_nmax + CHUNK - 1) / CHUNK;
+  SdbChainState *__restrict__ stp = states + chain;
+
+  // ------------------------------------------------------------------ stage set-up (registers)
+  // stage 0
+  AgcK ak; AgcS as; float lo_phi = 0.0f, lo_omega = 0.0f, gain2 = 1.0f;
+  int have_agc = 0, have_lo = 0;
+  float *dl = nullptr, *mh = nullptr;
+  // stage 1
+  CostasK ck; CostasS cs; float p_phi = 0, p_omega = 0, pll_a = 0, pll_b = 0, prev_re = 0, prev_im = 0;
+  float rot_re = 1, rot_im = 0, dc = 0, sq_level = 0, dc_alpha = 0, sq_alpha = 0, sq_thr = 0;
+  int have_costas = 0, have_pll = 0, quad = 0, ask_ch = 0, ademod = 0, asquelch = 0;
+  // stage 2
+  int mf_n = 0, have_mf = 0, alpf_n = 0; unsigned mf_ptr = 0; const float *taps = nullptr; float *mfl = nullptr;
+  float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
+  // stage 3
+  ClockS ks; float clk_gain = 0, clk_alpha = 0, clk_beta = 0, smp_period = 0, smp_phase0 = 0, s_phase = 0, s_pr = 0, s_pi = 0;
+  int clock_type = 1, clock_running = 1, dec_mode = 0, dec_int = 1; float dec_min = 0, dec_h = 1;
+  float avol = 1, rs_prev = 0; double rs_step = 0, rs_phase = 0;
   uint32_t nout = 0;
 
-  if (c.cls == SDB_INSP_RAW) {
-    for (uint32_t i = 0; i < n && i < sym_cap; ++i) { so[i] = in[i]; ho[i] = 0; }
-    sym_counts[chain] = n < sym_cap ? n : (uint32_t) sym_cap;
-    return;
-  }
-
-  if (c.cls == SDB_INSP_AUDIO) {
-    for (uint32_t i = 0; i < n; ++i) {
-      float2 y = in[i];
-      float v = 0.0f;
-      if (c.have_agc) y = agc_feed(c, st, dl, mh, y);
-      float p = y.x * y.x + y.y * y.y;
-      st.sq_level = st.sq_level + c.sq_alpha * (p - st.sq_level);
-      switch (c.audio_demod) {
-        case SDB_AUDIO_AM:
-          v = d_cabsf(y.x, y.y);
-          st.dc = st.dc + c.dc_alpha * (v - st.dc);
-          v = v - st.dc;
-          break;
-        case SDB_AUDIO_FM: {
-          float dr = y.x * st.prev_re + y.y * st.prev_im;
-          float di = y.y * st.prev_re - y.x * st.prev_im;
-          v = d_atan2f(di, dr) * 0.318309886183790671538f;
-          st.prev_re = y.x; st.prev_im = y.y;
-          break;
-        }
-        case SDB_AUDIO_USB:
-        case SDB_AUDIO_LSB: {
-          float2 ph = ncqo_read(st.lo_phi, c.lo_omega);
-          v = y.x * ph.x - y.y * ph.y;
-          break;
-        }
-        default:
-          break;
-      }
-      if (c.audio_squelch && !(st.sq_level > c.sq_thr)) v = 0.0f;
-      float2 o = make_float2(v, 0.0f);
-      if (c.alpf_n > 0) {
-        // real-valued low-pass: reuse the complex helper with a zero imaginary line
-        float xi[SDB_MAX_IIR] = {0, 0, 0, 0, 0}, yi[SDB_MAX_IIR] = {0, 0, 0, 0, 0};
-        o = iir_feed(c.alpf_b, c.alpf_a, c.alpf_n, st.al_x, xi, st.al_y, yi, st.al_xp, st.al_yp, o);
-      }
-      st.rs_phase += c.rs_step;
-      if (st.rs_phase >= 1.0) {
-        st.rs_phase -= 1.0;
-        float al = (float) (st.rs_phase / c.rs_step);
-        if (al > 1.0f) al = 1.0f;
-        if (nout < sym_cap) {
-          so[nout] = make_float2(c.audio_volume * ((1.0f - al) * o.x + al * st.rs_prev), 0.0f);
-          ho[nout] = 0;
-          ++nout;
-        }
-      }
-      st.rs_prev = o.x;
-    }
-    states[chain] = st;
-    sym_counts[chain] = nout;
-    return;
-  }
-
-  for (uint32_t i = 0; i < n; ++i) {
-    float2 y = in[i], o;
-    bool produced;
-
-    if (c.have_lo) {
-      float2 ph = ncqo_read(st.lo_phi, c.lo_omega);
-      y = make_float2(y.x * ph.x + y.y * ph.y, y.y * ph.x - y.x * ph.y);
-    }
-    if (c.have_agc) {
-      y = agc_feed(c, st, dl, mh, y);
-      y.x = 2.0f * y.x; y.y = 2.0f * y.y;
-    } else {
-      y.x = c.gain2 * y.x; y.y = c.gain2 * y.y;
-    }
-    if (c.cls == SDB_INSP_PSK) {
-      if (c.have_costas) y = costas_feed(c, st, y);
-    } else if (c.cls == SDB_INSP_FSK) {
-      float dr = y.x * st.prev_re + y.y * st.prev_im;
-      float di = y.y * st.prev_re - y.x * st.prev_im;
-      st.prev_re = y.x; st.prev_im = y.y;
-      if (c.fsk_quad_demod) {
-        y.x = d_atan2f(di, dr) * 0.318309886183790671538f;
-        y.y = 0.0f;
+  if (valid) {
+    if (warp == 0) {
+      have_agc = cp->have_agc; have_lo = cls != SDB_INSP_AUDIO ? cp->have_lo : 0;
+      gain2 = cls == SDB_INSP_AUDIO ? 1.0f : cp->gain2;
+      lo_omega = cp->lo_omega; lo_phi = stp->lo_phi;
+      ak.knee = cp->knee; ak.slope_m1 = cp->gain_slope - 1.0f; ak.fixed_gain = cp->fixed_gain;
+      ak.far_ = cp->far_; ak.faf = cp->faf; ak.sar = cp->sar; ak.saf = cp->saf;
+      ak.hang_max = cp->hang_max; ak.dl_size = cp->dl_size; ak.mh_size = cp->mh_size;
+      as.fast = stp->fast_level; as.slow = stp->slow_level; as.peak = stp->peak;
+      as.hang_n = stp->hang_n; as.dl_ptr = stp->dl_ptr; as.mh_ptr = stp->mh_ptr;
+      const bool in_smem = 2 * ak.dl_size + ak.mh_size <= 48;
+      float *gdl = bpool + (size_t) cp->st_dl_off * 32, *gmh = bpool + (size_t) cp->st_mh_off * 32;
+      if (in_smem && have_agc) {
+        dl = &sm.agc[0][lane]; mh = &sm.agc[2 * ak.dl_size][lane];
+        for (unsigned i = 0; i < 2 * ak.dl_size; ++i) dl[i * 32] = fresh ? 0.0f : gdl[i * 32];
+        for (unsigned i = 0; i < ak.mh_size; ++i) mh[i * 32] = fresh ? -160.0f : gmh[i * 32];
       } else {
-        y.x = dr * c.fsk_rot_re - di * c.fsk_rot_im;
-        y.y = dr * c.fsk_rot_im + di * c.fsk_rot_re;
+        dl = gdl; mh = gmh;
+        if (fresh && have_agc) {
+          for (unsigned i = 0; i < 2 * ak.dl_size; ++i) dl[i * 32] = 0.0f;
+          for (unsigned i = 0; i < ak.mh_size; ++i) mh[i * 32] = -160.0f;
+        }
       }
-    } else if (c.cls == SDB_INSP_ASK) {
-      if (c.have_pll) y = pll_track(c, st, y);
-      if (c.ask_channel == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
-      else if (c.ask_channel == 1) { y.y = 0.0f; }
-      else                         { y.x = y.y; y.y = 0.0f; }
-    }
-
-    if (c.have_mf) {
-      // FIR, single accumulator, ascending tap index (SPEC I.1)
-      mfl[2 * st.mf_ptr] = y.x; mfl[2 * st.mf_ptr + 1] = y.y;
-      float accr = 0.0f, acci = 0.0f;
-      unsigned p = st.mf_ptr;
-      for (int t = 0; t < c.mf_n; ++t) {
-        const float b = taps[t];
-        accr = accr + b * mfl[2 * p];
-        acci = acci + b * mfl[2 * p + 1];
-        p = p == 0 ? c.mf_n - 1 : p - 1;
+    } else if (warp == 1) {
+      have_costas = cp->have_costas; have_pll = cp->have_pll;
+      ck.kind = cp->costas_kind; ck.af_n = cp->af_n; ck.a = cp->c_a; ck.b = cp->c_b;
+#pragma unroll
+      for (int i = 0; i < SDB_MAX_IIR; ++i) {
+        ck.af_b[i] = cp->af_b[i]; ck.af_a[i] = cp->af_a[i];
+        cs.xr[i] = stp->afx_re[i]; cs.xi[i] = stp->afx_im[i]; cs.yr[i] = stp->afy_re[i]; cs.yi[i] = stp->afy_im[i];
       }
-      st.mf_ptr = st.mf_ptr + 1 == (unsigned) c.mf_n ? 0 : st.mf_ptr + 1;
-      y = make_float2(accr, acci);
-    }
-
-    if (c.clock_type == 1) produced = clock_feed(c, st, y, o);
-    else                   produced = sampler_feed(c, st, y, o);
-
-    if (produced && c.clock_running && nout < sym_cap) {
-      o.x = 0.75f * o.x; o.y = 0.75f * o.y;
-      so[nout] = o;
-      ho[nout] = decide(c, o);
-      ++nout;
+      cs.phi = stp->c_phi; cs.omega = stp->c_omega; cs.lock = stp->c_lock; cs.yre = stp->c_yre; cs.yim = stp->c_yim;
+      p_phi = stp->p_phi; p_omega = stp->p_omega; pll_a = cp->pll_alpha; pll_b = cp->pll_beta;
+      prev_re = stp->prev_re; prev_im = stp->prev_im;
+      rot_re = cp->fsk_rot_re; rot_im = cp->fsk_rot_im; quad = cp->fsk_quad_demod; ask_ch = cp->ask_channel;
+      ademod = cp->audio_demod; asquelch = cp->audio_squelch; dc = stp->dc; sq_level = stp->sq_level;
+      dc_alpha = cp->dc_alpha; sq_alpha = cp->sq_alpha; sq_thr = cp->sq_thr;
+      if (cls == SDB_INSP_AUDIO) { lo_phi = stp->lo_phi; lo_omega = cp->lo_omega; }
+    } else if (warp == 2) {
+      have_mf = cp->have_mf; mf_n = cp->mf_n; mf_ptr = stp->mf_ptr; taps = taps_pool + cp->mf_off;
+      alpf_n = cls == SDB_INSP_AUDIO ? cp->alpf_n : 0;
+#pragma unroll
+      for (int i = 0; i < SDB_MAX_IIR; ++i) {
+        al_b[i] = cp->alpf_b[i]; al_a[i] = cp->alpf_a[i]; al_x[i] = stp->al_x[i]; al_y[i] = stp->al_y[i];
+        al_xi[i] = 0.0f; al_yi[i] = 0.0f;
+      }
+      float *gmf = bpool + (size_t) cp->st_mf_off * 32;
+      if (have_mf && mf_n <= MF_RING) {
+        mfl = reinterpret_cast<float *>(&sm.mfh[0][lane]);   // float2 ring, stride 32 float2 = 64 floats
+        for (int i = 0; i < mf_n; ++i) {
+          float2 v = fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * i) * 32], gmf[(2 * i + 1) * 32]);
+          sm.mfh[i][lane] = v;
+        }
+      } else {
+        mfl = gmf;
+        if (fresh && have_mf) for (int i = 0; i < 2 * mf_n; ++i) gmf[i * 32] = 0.0f;
+      }
+    } else {
+      ks.phi = stp->k_phi; ks.bnor = stp->k_bnor; ks.x0r = stp->k_x0r; ks.x0i = stp->k_x0i; ks.x1r = stp->k_x1r;
+      ks.x1i = stp->k_x1i; ks.x2r = stp->k_x2r; ks.x2i = stp->k_x2i; ks.pr = stp->k_pr; ks.pi = stp->k_pi;
+      ks.half = stp->k_half;
+      clk_gain = cp->clk_gain; clk_alpha = cp->clk_alpha; clk_beta = cp->clk_beta;
+      smp_period = cp->smp_period; smp_phase0 = cp->smp_phase0; s_phase = stp->s_phase; s_pr = stp->s_pr; s_pi = stp->s_pi;
+      clock_type = cp->clock_type; clock_running = cp->clock_running;
+      dec_mode = cp->dec_mode; dec_int = cp->dec_intervals; dec_min = cp->dec_min; dec_h = cp->dec_h;
+      avol = cp->audio_volume; rs_prev = stp->rs_prev; rs_step = cp->rs_step; rs_phase = stp->rs_phase;
     }
   }
-  states[chain] = st;
-  sym_counts[chain] = nout;
+  float2 *__restrict__ so = soft + (size_t) chain * sym_cap;
+  unsigned char *__restrict__ ho = hard + (size_t) chain * sym_cap;
+  __syncthreads();
+
+  for (uint32_t it = 0; it < nchunks + 3; ++it) {
+    if (warp == 0) {
+      if (it < nchunks) {
+        const uint32_t base = it * CHUNK;
+        // cooperative, coalesced load of CHUNK samples of each of the CTA's 32 chains
+        for (int r = 0; r < 32; ++r) {
+          const int gr = blockIdx.x * 32 + r;
+          if (gr < chains) {
+            const int kr = gr / n_streams, sr = gr - kr * n_streams;
+            const uint32_t nr = n_hops * (uint32_t) chans[kr].halfsz;
+            if (base + lane < nr)
+              sm.tile[r][lane] = __ldg(chan_in + (size_t) sr * chan_stream_stride + chans[kr].out_off + base + lane);
+          }
+        }
+        __syncwarp();
+        float2 (*out)[32] = sm.ring[0][it & 1];
+        for (int i = 0; i < CHUNK; ++i) {
+          if (base + i < n) {
+            float2 y = sm.tile[lane][i];
+            if (have_lo) {
+              float2 ph = ncqo_read(lo_phi, lo_omega);
+              y = make_float2(y.x * ph.x + y.y * ph.y, y.y * ph.x - y.x * ph.y);
+            }
+            if (cls != SDB_INSP_RAW) {
+              if (have_agc) {
+                y = agc_step(ak, as, dl, mh, y);
+                if (cls != SDB_INSP_AUDIO) { y.x = 2.0f * y.x; y.y = 2.0f * y.y; }
+              } else if (cls != SDB_INSP_AUDIO) {
+                y.x = gain2 * y.x; y.y = gain2 * y.y;
+              }
+            }
+            out[i][lane] = y;
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      if (it >= 1 && it < nchunks + 1) {
+        const uint32_t c = it - 1, base = c * CHUNK;
+        float2 (*in)[32] = sm.ring[0][c & 1];
+        float2 (*out)[32] = sm.ring[1][c & 1];
+        for (int i = 0; i < CHUNK; ++i) {
+          if (base + i < n) {
+            float2 y = in[i][lane];
+            if (cls == SDB_INSP_PSK) {
+              if (have_costas) y = costas_step(ck, cs, y);
+            } else if (cls == SDB_INSP_FSK) {
+              float dr = y.x * prev_re + y.y * prev_im;
+              float di = y.y * prev_re - y.x * prev_im;
+              prev_re = y.x; prev_im = y.y;
+              if (quad) { y.x = d_atan2f(di, dr) * 0.318309886183790671538f; y.y = 0.0f; }
+              else { y.x = dr * rot_re - di * rot_im; y.y = dr * rot_im + di * rot_re; }
+            } else if (cls == SDB_INSP_ASK) {
+              if (have_pll) y = pll_step(pll_a, pll_b, p_phi, p_omega, y);
+              if (ask_ch == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
+              else if (ask_ch == 1) { y.y = 0.0f; }
+              else                  { y.x = y.y; y.y = 0.0f; }
+            } else if (cls == SDB_INSP_AUDIO) {
+              float v = 0.0f;
+              float p = y.x * y.x + y.y * y.y;
+              sq_level = sq_level + sq_alpha * (p - sq_level);
+              if (ademod == SDB_AUDIO_AM) {
+                v = d_cabsf(y.x, y.y);
+                dc = dc + dc_alpha * (v - dc);
+                v = v - dc;
+              } else if (ademod == SDB_AUDIO_FM) {
+                float dr = y.x * prev_re + y.y * prev_im;
+                float di = y.y * prev_re - y.x * prev_im;
+                v = d_atan2f(di, dr) * 0.318309886183790671538f;
+                prev_re = y.x; prev_im = y.y;
+              } else if (ademod == SDB_AUDIO_USB || ademod == SDB_AUDIO_LSB) {
+                float2 ph = ncqo_read(lo_phi, lo_omega);
+                v = y.x * ph.x - y.y * ph.y;
+              }
+              if (asquelch && !(sq_level > sq_thr)) v = 0.0f;
+              y = make_float2(v, 0.0f);
+            }
+            out[i][lane] = y;
+          }
+        }
+      }
+    } else if (warp == 2) {
+      if (it >= 2 && it < nchunks + 2) {
+        const uint32_t c = it - 2, base = c * CHUNK;
+        float2 (*in)[32] = sm.ring[1][c & 1];
+        float2 (*out)[32] = sm.ring[2][c & 1];
+        for (int i = 0; i < CHUNK; ++i) {
+          if (base + i < n) {
+            float2 y = in[i][lane];
+            if (have_mf) {
+              float accr = 0.0f, acci = 0.0f;
+              if (mf_n <= MF_RING) {
+                sm.mfh[mf_ptr][lane] = y;
+                unsigned p = mf_ptr;
+                for (int t = 0; t < mf_n; ++t) {
+                  const float b = __ldg(taps + t);
+                  const float2 v = sm.mfh[p][lane];
+                  accr = accr + b * v.x;
+                  acci = acci + b * v.y;
+                  p = p == 0 ? mf_n - 1 : p - 1;
+                }
+              } else {
+                mfl[(2 * mf_ptr) * 32] = y.x; mfl[(2 * mf_ptr + 1) * 32] = y.y;
+                unsigned p = mf_ptr;
+                for (int t = 0; t < mf_n; ++t) {
+                  const float b = __ldg(taps + t);
+                  accr = accr + b * mfl[(2 * p) * 32];
+                  acci = acci + b * mfl[(2 * p + 1) * 32];
+                  p = p == 0 ? mf_n - 1 : p - 1;
+                }
+              }
+              mf_ptr = mf_ptr + 1 == (unsigned) mf_n ? 0 : mf_ptr + 1;
+              y = make_float2(accr, acci);
+            } else if (alpf_n > 0) {
+              y = iir_any(alpf_n, al_b, al_a, al_x, al_xi, al_y, al_yi, y);
+            }
+            out[i][lane] = y;
+          }
+        }
+      }
+    } else {
+      if (it >= 3) {
+        const uint32_t c = it - 3, base = c * CHUNK;
+        float2 (*in)[32] = sm.ring[2][c & 1];
+        for (int i = 0; i < CHUNK; ++i) {
+          if (base + i < n) {
+            float2 y = in[i][lane], o;
+            if (cls == SDB_INSP_RAW) {
+              if (nout < sym_cap) { so[nout] = y; ho[nout] = 0; ++nout; }
+            } else if (cls == SDB_INSP_AUDIO) {
+              rs_phase += rs_step;
+              if (rs_phase >= 1.0) {
+                rs_phase -= 1.0;
+                float al = (float) (rs_phase / rs_step);
+                if (al > 1.0f) al = 1.0f;
+                if (nout < sym_cap) {
+                  so[nout] = make_float2(avol * ((1.0f - al) * y.x + al * rs_prev), 0.0f);
+                  ho[nout] = 0;
+                  ++nout;
+                }
+              }
+              rs_prev = y.x;
+            } else {
+              bool produced;
+              if (clock_type == 1) produced = clock_step(clk_gain, clk_alpha, clk_beta, ks, y, o);
+              else                 produced = sampler_step(smp_period, smp_phase0, s_phase, s_pr, s_pi, y, o);
+              if (produced && clock_running && nout < sym_cap) {
+                o.x = 0.75f * o.x; o.y = 0.75f * o.y;
+                so[nout] = o;
+                ho[nout] = decide(dec_mode, dec_min, dec_h, dec_int, o);
+                ++nout;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ write state back
+  if (valid) {
+    if (warp == 0) {
+      stp->fast_level = as.fast; stp->slow_level = as.slow; stp->peak = as.peak;
+      stp->hang_n = as.hang_n; stp->dl_ptr = as.dl_ptr; stp->mh_ptr = as.mh_ptr;
+      if (cls != SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
+      if (have_agc && 2 * ak.dl_size + ak.mh_size <= 48) {
+        float *gdl = bpool + (size_t) cp->st_dl_off * 32, *gmh = bpool + (size_t) cp->st_mh_off * 32;
+        for (unsigned i = 0; i < 2 * ak.dl_size; ++i) gdl[i * 32] = dl[i * 32];
+        for (unsigned i = 0; i < ak.mh_size; ++i) gmh[i * 32] = mh[i * 32];
+      }
+    } else if (warp == 1) {
+#pragma unroll
+      for (int i = 0; i < SDB_MAX_IIR; ++i) {
+        stp->afx_re[i] = cs.xr[i]; stp->afx_im[i] = cs.xi[i]; stp->afy_re[i] = cs.yr[i]; stp->afy_im[i] = cs.yi[i];
+      }
+      stp->c_phi = cs.phi; stp->c_omega = cs.omega; stp->c_lock = cs.lock; stp->c_yre = cs.yre; stp->c_yim = cs.yim;
+      stp->p_phi = p_phi; stp->p_omega = p_omega; stp->prev_re = prev_re; stp->prev_im = prev_im;
+      stp->dc = dc; stp->sq_level = sq_level;
+      if (cls == SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
+    } else if (warp == 2) {
+      stp->mf_ptr = mf_ptr;
+#pragma unroll
+      for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
+      if (have_mf && mf_n <= MF_RING) {
+        float *gmf = bpool + (size_t) cp->st_mf_off * 32;
+        for (int i = 0; i < mf_n; ++i) { float2 v = sm.mfh[i][lane]; gmf[(2 * i) * 32] = v.x; gmf[(2 * i + 1) * 32] = v.y; }
+      }
+    } else {
+      stp->k_phi = ks.phi; stp->k_bnor = ks.bnor; stp->k_x0r = ks.x0r; stp->k_x0i = ks.x0i; stp->k_x1r = ks.x1r;
+      stp->k_x1i = ks.x1i; stp->k_x2r = ks.x2r; stp->k_x2i = ks.x2i; stp->k_pr = ks.pr; stp->k_pi = ks.pi;
+      stp->k_half = ks.half; stp->s_phase = s_phase; stp->s_pr = s_pr; stp->s_pi = s_pi;
+      stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
+      sym_counts[chain] = nout;
+    }
+  }
 }
 
 cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cfg_dev, int n_channels,
                                     int n_streams, SdbChainState *state, float *pool, size_t pool_stride,
                                     const float *taps_pool, const SdbChannelDev *chans_dev,
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
-                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap)
+                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap, int fresh)
 {
   const int chains = n_channels * n_streams;
   if (chains == 0) return cudaSuccess;
-  const int block = 32;
-  k_inspectors<<<(chains + block - 1) / block, block, 0, c.stream>>>(
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_inspectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ChainSmem));
+    attr_done = true;
+  }
+  k_inspectors<<<(chains + 31) / 32, 128, sizeof(ChainSmem), c.stream>>>(
       cfg_dev, n_channels, n_streams, state, pool, pool_stride, taps_pool, chans_dev, chan_in,
-      chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap);
+      chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap, fresh);
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ Tasks/ primitives -----------
-// One thread per buffer of the batch; same recurrences as above.
+// One thread per buffer of the batch; same recurrences, state in registers.
 __global__ void k_task_xlate(const float2 *__restrict__ src, float2 *__restrict__ dst, size_t n, size_t batch,
                              float omega, float phi0)
 {
@@ -420,24 +605,39 @@ __global__ void k_task_quad(const float2 *__restrict__ src, float2 *__restrict__
   dst[i] = make_float2(0.0f, 0.318309886183790671538f * d_atan2f(di, dr));
 }
 
+// mode 0 Costas, 1 PLL, 2 AGC.  pool: per-buffer AGC arrays, interleaved by 32 buffers ([slot][lane]).
 __global__ void k_task_chain(const float2 *__restrict__ src, float2 *__restrict__ dst, size_t n, size_t batch,
-                             SdbChainCfg c, int mode, float *pool, size_t pool_stride)
+                             const SdbChainCfg *__restrict__ cp, int mode, float *pool, size_t pool_stride)
 {
   size_t b = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  SdbChainState st;
-  memset(&st, 0, sizeof(st));
-  st.fast_level = st.slow_level = st.peak = -160.0f;
-  float *mypool = pool ? pool + b * pool_stride : nullptr;
-  float *dl = mypool ? mypool + c.st_dl_off : nullptr, *mh = mypool ? mypool + c.st_mh_off : nullptr;
   const float2 *x = src + b * n;
   float2 *y = dst + b * n;
-  for (size_t i = 0; i < n; ++i) {
-    float2 v = x[i];
-    if (mode == 0)      v = costas_feed(c, st, v);
-    else if (mode == 1) v = pll_track(c, st, v);
-    else                v = agc_feed(c, st, dl, mh, v);
-    y[i] = v;
+  if (mode == 0) {
+    CostasK ck; CostasS cs;
+    ck.kind = cp->costas_kind; ck.af_n = cp->af_n; ck.a = cp->c_a; ck.b = cp->c_b;
+#pragma unroll
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      ck.af_b[i] = cp->af_b[i]; ck.af_a[i] = cp->af_a[i];
+      cs.xr[i] = cs.xi[i] = cs.yr[i] = cs.yi[i] = 0.0f;
+    }
+    cs.phi = cs.omega = cs.lock = cs.yre = cs.yim = 0.0f;
+    for (size_t i = 0; i < n; ++i) y[i] = costas_step(ck, cs, x[i]);
+  } else if (mode == 1) {
+    float phi = 0.0f, omega = 0.0f;
+    const float a = cp->pll_alpha, be = cp->pll_beta;
+    for (size_t i = 0; i < n; ++i) y[i] = pll_step(a, be, phi, omega, x[i]);
+  } else {
+    AgcK ak; AgcS as;
+    ak.knee = cp->knee; ak.slope_m1 = cp->gain_slope - 1.0f; ak.fixed_gain = cp->fixed_gain;
+    ak.far_ = cp->far_; ak.faf = cp->faf; ak.sar = cp->sar; ak.saf = cp->saf;
+    ak.hang_max = cp->hang_max; ak.dl_size = cp->dl_size; ak.mh_size = cp->mh_size;
+    as.fast = as.slow = as.peak = -160.0f; as.hang_n = as.dl_ptr = as.mh_ptr = 0;
+    float *bp = pool + (b / 32) * 32 * pool_stride + (b % 32);
+    float *dl = bp + (size_t) cp->st_dl_off * 32, *mh = bp + (size_t) cp->st_mh_off * 32;
+    for (unsigned i = 0; i < 2 * ak.dl_size; ++i) dl[i * 32] = 0.0f;
+    for (unsigned i = 0; i < ak.mh_size; ++i) mh[i * 32] = -160.0f;
+    for (size_t i = 0; i < n; ++i) y[i] = agc_step(ak, as, dl, mh, x[i]);
   }
 }
 
@@ -454,8 +654,8 @@ cudaError_t sdb_launch_task_quad(cudaStream_t s, const float2 *src, float2 *dst,
   return cudaGetLastError();
 }
 cudaError_t sdb_launch_task_chain(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
-                                  const SdbChainCfg &c, int mode, float *pool, size_t pool_stride)
+                                  const SdbChainCfg *cfg_dev, int mode, float *pool, size_t pool_stride)
 {
-  k_task_chain<<<(unsigned) ((batch + 31) / 32), 32, 0, s>>>(src, dst, n, batch, c, mode, pool, pool_stride);
+  k_task_chain<<<(unsigned) ((batch + 31) / 32), 32, 0, s>>>(src, dst, n, batch, cfg_dev, mode, pool, pool_stride);
   return cudaGetLastError();
 }

@@ -57,7 +57,7 @@ struct sdb_engine {
   double samp_rate;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
-  bool committed = false, first_feed = true, timing = false;
+  bool committed = false, first_feed = true, timing = false, chains_fresh = true;
   std::vector<Channel> channels;
   std::map<unsigned, float2 *> tw;     // twiddle tables by size
   std::vector<void *> allocs;
@@ -443,7 +443,8 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     const size_t chains = (size_t) S * K;
     e->d_cfg = e->dalloc<SdbChainCfg>(K);
     e->d_state = e->dalloc<SdbChainState>(chains);
-    e->d_pool = e->dalloc<float>(chains * pool);
+    const size_t pool_floats = ((chains + 31) / 32) * 32 * pool;   // per-CTA interleaved [slot][lane]
+    e->d_pool = e->dalloc<float>(pool_floats);
     e->d_taps = e->dalloc<float>(taps_pool.size());
     e->d_soft = e->dalloc<float2>(chains * cap);
     e->d_hard = e->dalloc<uint8_t>(chains * cap);
@@ -454,17 +455,15 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     if (!taps_pool.empty())
       CK(cudaMemcpy(e->d_taps, taps_pool.data(), taps_pool.size() * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<SdbChainState> st(chains);
-    std::vector<float> hp(chains * pool, 0.0f);
     for (size_t ci = 0; ci < chains; ++ci) {
       const SdbChainCfg &c = e->h_cfg[ci % K];
       SdbChainState &s = st[ci];
       memset(&s, 0, sizeof(s));
       s.fast_level = s.slow_level = s.peak = -160.0f;
       s.k_phi = 0.25f; s.k_bnor = c.bnor;
-      for (unsigned i = 0; i < c.mh_size; ++i) hp[ci * pool + c.st_mh_off + i] = -160.0f;
     }
     CK(cudaMemcpy(e->d_state, st.data(), chains * sizeof(SdbChainState), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_pool, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemset(e->d_pool, 0, pool_floats * sizeof(float)));   // the kernel initialises its lines when `fresh`
     CK(cudaMemset(e->d_counts, 0, chains * sizeof(uint32_t)));
   }
   e->committed = true;
@@ -502,14 +501,17 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
         a.x = x; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
         a.windows_per_stream = frames; a.first_window = 0; a.hop = (int) Np; a.base_off = 0;
         a.window = e->d_window; a.scratch = e->d_scratch;
+        const bool fast = e->fs_psd.N1 == 256 && e->fs_psd.N2 == 256;
         e->span_begin(FAM_COLS);
-        CK(sdb_launch_pass_a_range(ctx, e->fs_psd, a, w0, cw));
+        if (fast) CK(sdb_launch_cols256(ctx, e->fs_psd, a, e->fs_psd.twN, w0, cw));
+        else      CK(sdb_launch_pass_a_range(ctx, e->fs_psd, a, w0, cw));
         e->span_end();
         SdbPassBArgs b{};
         b.scratch = e->d_scratch; b.n_windows = cw; b.psd = e->d_psd + (size_t) w0 * Np;
         b.inv_n = 1.0f / (float) Np; b.shift_db = shift_db;
         e->span_begin(FAM_ROWS_PSD);
-        CK(sdb_launch_pass_b_psd(ctx, e->fs_psd, b));
+        if (fast) CK(sdb_launch_rows256(ctx, e->fs_psd, b, 0));
+        else      CK(sdb_launch_pass_b_psd(ctx, e->fs_psd, b));
         e->span_end();
       }
     }
@@ -528,14 +530,17 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
         a.x = x; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
         a.windows_per_stream = wps; a.first_window = first; a.hop = (int) (W / 2); a.base_off = 0;
         a.window = nullptr; a.scratch = e->d_scratch;
+        const bool fast = e->fs_st.N1 == 256 && e->fs_st.N2 == 256;
         e->span_begin(FAM_COLS);
-        CK(sdb_launch_pass_a_range(ctx, e->fs_st, a, w0, cw));
+        if (fast) CK(sdb_launch_cols256(ctx, e->fs_st, a, e->fs_st.twN, w0, cw));
+        else      CK(sdb_launch_pass_a_range(ctx, e->fs_st, a, w0, cw));
         e->span_end();
         SdbPassBArgs b{};
         b.scratch = e->d_scratch; b.n_windows = cw; b.binmap = e->d_binmap;
         b.cspec = e->d_cspec + (size_t) w0 * e->n_bins; b.n_bins = e->n_bins;
         e->span_begin(FAM_ROWS_CHAN);
-        CK(sdb_launch_pass_b_chan(ctx, e->fs_st, b));
+        if (fast) CK(sdb_launch_rows256(ctx, e->fs_st, b, 1));
+        else      CK(sdb_launch_pass_b_chan(ctx, e->fs_st, b));
         e->span_end();
       }
       e->span_begin(FAM_CHAN_IFFT);
@@ -547,7 +552,8 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       e->span_begin(FAM_INSPECTOR);
       CK(sdb_launch_inspectors_n(ctx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
                                  e->d_chans, e->d_chan, e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
-                                 e->d_counts, e->sym_cap));
+                                 e->d_counts, e->sym_cap, e->chains_fresh ? 1 : 0));
+      e->chains_fresh = false;
       e->span_end();
     } else {
       CK(cudaMemsetAsync(e->d_counts, 0, (size_t) S * K * sizeof(uint32_t), e->stream));
@@ -676,8 +682,14 @@ extern "C" int sdb_engine_kernel_time(sdb_engine_t *e, const char *family, doubl
 // Tasks/ primitives on host buffers
 // ---------------------------------------------------------------------------------------------
 struct TaskBufs {
-  float2 *src = nullptr, *dst = nullptr; float *pool = nullptr;
-  ~TaskBufs() { cudaFree(src); cudaFree(dst); cudaFree(pool); }
+  float2 *src = nullptr, *dst = nullptr; float *pool = nullptr; SdbChainCfg *cfg = nullptr;
+  ~TaskBufs() { cudaFree(src); cudaFree(dst); cudaFree(pool); cudaFree(cfg); }
+  int put_cfg(const SdbChainCfg &c)
+  {
+    CK(cudaMalloc(&cfg, sizeof(c)));
+    CK(cudaMemcpy(cfg, &c, sizeof(c), cudaMemcpyHostToDevice));
+    return 0;
+  }
 };
 
 static int task_io_begin(TaskBufs &b, const sdb_complex *src, size_t n, size_t batch)
@@ -731,7 +743,8 @@ extern "C" int sdb_task_costas(const sdb_complex *src, sdb_complex *dst, size_t 
   c.c_b = 0.5f * c.c_a * c.c_a;
   if (!sdbh::butter_lp(2, 1.0f / tau, c.af_b, c.af_a)) return fail("invalid arm bandwidth");
   c.af_n = 3;
-  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, c, 0, nullptr, 0));
+  if (b.put_cfg(c)) return -1;
+  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, b.cfg, 0, nullptr, 0));
   return task_io_end(b, dst, n, batch);
 }
 
@@ -744,7 +757,8 @@ extern "C" int sdb_task_pll(const sdb_complex *src, sdb_complex *dst, size_t n, 
   float dinv = 1.0f / (1.0f + 2.0f * 0.707f * fc + fc * fc);
   c.pll_alpha = 4.0f * fc * fc * dinv;
   c.pll_beta = 4.0f * 0.707f * fc * dinv;
-  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, c, 1, nullptr, 0));
+  if (b.put_cfg(c)) return -1;
+  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, b.cfg, 1, nullptr, 0));
   return task_io_end(b, dst, n, batch);
 }
 
@@ -760,11 +774,9 @@ extern "C" int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, 
   c.hang_max = d.hang_max; c.dl_size = 20; c.mh_size = 20;
   c.far_ = d.far_; c.faf = d.faf; c.sar = d.sar; c.saf = d.saf;
   c.st_dl_off = 0; c.st_mh_off = 40; c.st_pool = 60;
-  std::vector<float> hp(batch * 60, 0.0f);
-  for (size_t i = 0; i < batch; ++i) for (int j = 0; j < 20; ++j) hp[i * 60 + 40 + j] = -160.0f;
-  CK(cudaMalloc(&b.pool, hp.size() * sizeof(float)));
-  CK(cudaMemcpy(b.pool, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
-  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, c, 2, b.pool, 60));
+  CK(cudaMalloc(&b.pool, ((batch + 31) / 32) * 32 * 60 * sizeof(float)));
+  if (b.put_cfg(c)) return -1;
+  CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, b.cfg, 2, b.pool, 60));
   return task_io_end(b, dst, n, batch);
 }
 
@@ -784,12 +796,11 @@ extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_co
   const size_t pool = (size_t) std::max(1, c.st_pool);
   SdbChannelDev cd; memset(&cd, 0, sizeof(cd)); cd.halfsz = 1; cd.out_off = 0;
   std::vector<SdbChainState> st(batch);
-  std::vector<float> hp(batch * pool, 0.0f);
+  const size_t pool_floats = ((batch + 31) / 32) * 32 * pool;
   for (size_t i = 0; i < batch; ++i) {
     memset(&st[i], 0, sizeof(SdbChainState));
     st[i].fast_level = st[i].slow_level = st[i].peak = -160.0f;
     st[i].k_phi = 0.25f; st[i].k_bnor = c.bnor;
-    for (unsigned j = 0; j < c.mh_size; ++j) hp[i * pool + c.st_mh_off + j] = -160.0f;
   }
   struct Bufs { void *p[9] = {0}; ~Bufs() { for (auto q : p) cudaFree(q); } } b;
   float2 *d_src, *d_soft; uint8_t *d_hard; uint32_t *d_cnt; SdbChainCfg *d_cfg; SdbChainState *d_st;
@@ -800,19 +811,19 @@ extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_co
   CK(cudaMalloc(&b.p[3], batch * sizeof(uint32_t))); d_cnt = (uint32_t *) b.p[3];
   CK(cudaMalloc(&b.p[4], sizeof(SdbChainCfg))); d_cfg = (SdbChainCfg *) b.p[4];
   CK(cudaMalloc(&b.p[5], batch * sizeof(SdbChainState))); d_st = (SdbChainState *) b.p[5];
-  CK(cudaMalloc(&b.p[6], hp.size() * sizeof(float))); d_pool = (float *) b.p[6];
+  CK(cudaMalloc(&b.p[6], pool_floats * sizeof(float))); d_pool = (float *) b.p[6];
   CK(cudaMalloc(&b.p[7], std::max<size_t>(1, taps.size()) * sizeof(float))); d_taps = (float *) b.p[7];
   CK(cudaMalloc(&b.p[8], sizeof(SdbChannelDev))); d_cd = (SdbChannelDev *) b.p[8];
   CK(cudaMemcpy(d_src, src, n * batch * sizeof(float2), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_cfg, &c, sizeof(c), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_st, st.data(), batch * sizeof(SdbChainState), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_pool, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_pool, 0, pool_floats * sizeof(float)));
   if (!taps.empty()) CK(cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_cd, &cd, sizeof(cd), cudaMemcpyHostToDevice));
   SdbLaunchCtx ctx{ 0, nullptr };
   // every chain is "stream s, channel 0"; chan_stream_stride = n
   CK(sdb_launch_inspectors_n(ctx, d_cfg, 1, (int) batch, d_st, d_pool, pool, d_taps, d_cd, d_src, n,
-                             (uint32_t) n, d_soft, d_hard, d_cnt, cap));
+                             (uint32_t) n, d_soft, d_hard, d_cnt, cap, 1));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(counts, d_cnt, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   if (soft) CK(cudaMemcpy(soft, d_soft, cap * batch * sizeof(float2), cudaMemcpyDeviceToHost));

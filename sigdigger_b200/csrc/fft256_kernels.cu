@@ -1,0 +1,213 @@
+// fft256_kernels.cu -- the 65536-point transform of BASELINE.json's headline configs, specialised:
+// 65536 = 256 x 256, each 256-point transform = 16 x 16 with BOTH radix-16 butterflies held in
+// registers (16 complex values per thread) and ONE shared-memory exchange between them.
+//
+//   pass A (k_cols256): a CTA owns 16 adjacent columns of a window: every thread issues 16 independent
+//       coalesced float2 loads (128 B per thread in flight), optional window multiply, radix-16 over the
+//       high row digit, twiddle W_256^(t ka), exchange, radix-16 over the low row digit, inter-pass twiddle
+//       W_65536^(n2 k1) from two 256-entry tables (coarse x fine), transposed coalesced store.
+//   pass B (k_rows256): a CTA owns 32 rows of the scratch; same two butterflies; the second one is mapped
+//       so that a warp holds 32 consecutive output bins -> 128-byte PSD / compacted-spectrum stores.
+//
+// Same mathematics as the generic path in fft_kernels.cu (which remains for every other size); results
+// agree with the oracle to SPEC.md section T.  Replaces the forward FFTs of su_specttuner
+// (Tasks/LPFTask.cpp:83-87) and of the PSD (Suscan/Messages/PSDMessage.cpp:26-39).
+#include "sdb_internal.h"
+
+#define C1 0.92387953251128675613f   // cos(pi/8)
+#define S1 0.38268343236508977173f   // sin(pi/8)
+#define R2 0.70710678118654752440f
+
+static __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+static __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+static __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// forward 4-point DFT in place: (a, b, c, d) <- DFT4
+static __device__ __forceinline__ void fft4(float2 &a, float2 &b, float2 &c, float2 &d)
+{
+  const float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = mul_mi(csub(b, d));
+  a = cadd(s0, s1); b = cadd(d0, d1); c = csub(s0, s1); d = csub(d0, d1);
+}
+
+// forward 16-point DFT of v[0..15] (natural order in).  Result X[m + 4 q] is left in v[4 m + q].
+static __device__ __forceinline__ void fft16(float2 (&v)[16])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i) fft4(v[i], v[i + 4], v[i + 8], v[i + 12]);
+  // twiddles W16^(i m) on v[i + 4 m]
+  v[5]  = cmulf(v[5],  make_float2(C1, -S1));      // i=1 m=1 : W^1
+  v[9]  = cmulf(v[9],  make_float2(R2, -R2));      // i=1 m=2 : W^2
+  v[13] = cmulf(v[13], make_float2(S1, -C1));      // i=1 m=3 : W^3
+  v[6]  = cmulf(v[6],  make_float2(R2, -R2));      // i=2 m=1 : W^2
+  v[10] = mul_mi(v[10]);                           // i=2 m=2 : W^4 = -i
+  v[14] = cmulf(v[14], make_float2(-R2, -R2));     // i=2 m=3 : W^6
+  v[7]  = cmulf(v[7],  make_float2(S1, -C1));      // i=3 m=1 : W^3
+  v[11] = cmulf(v[11], make_float2(-R2, -R2));     // i=3 m=2 : W^6
+  v[15] = cmulf(v[15], make_float2(-C1, S1));      // i=3 m=3 : W^9
+#pragma unroll
+  for (int m = 0; m < 4; ++m) fft4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
+}
+// position p = 4 m + q of fft16's output holds X[m + 4 q]
+#define REV16(p) ((((p) >> 2)) | (((p) & 3) << 2))
+
+struct Cols256K {
+  const float2 *x; size_t stream_stride;
+  const float2 *hist; int hist_len;
+  int windows_per_stream, first_window, hop, base_off, win_base;
+  const float *window;
+  float2 *scratch;
+  const float2 *tw256;     // W_256^i
+  const float2 *twfine;    // W_65536^i, i < 256
+};
+
+#define LDC 273    // pitch of one column's [ka][17] block (odd: conflict-free across columns)
+
+__global__ void __launch_bounds__(256, 3) k_cols256(const Cols256K p)
+{
+  __shared__ float2 sm[16 * LDC];
+  __shared__ float2 s_tw[256], s_fine[256];
+  const int tid = threadIdx.x;
+  s_tw[tid] = __ldg(p.tw256 + tid);
+  s_fine[tid] = __ldg(p.twfine + tid);
+  const int c = tid & 15, t = tid >> 4;
+  const int w = p.win_base + blockIdx.y;
+  const int stream = w / p.windows_per_stream;
+  const int j0 = p.first_window + (w - stream * p.windows_per_stream);
+  const int col = blockIdx.x * 16 + c;
+  const long v0 = (long) p.base_off + (long) j0 * p.hop;
+  const float2 *__restrict__ xs = p.x + (size_t) stream * p.stream_stride;
+  const float2 *__restrict__ hs = p.hist ? p.hist + (size_t) stream * p.hist_len : nullptr;
+
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int r = t + 16 * j;                       // row n1
+    const long vi = v0 + (long) r * 256 + col;
+    v[j] = vi < p.hist_len ? __ldg(hs + vi) : __ldg(xs + (vi - p.hist_len));
+  }
+  if (p.window) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float wv = __ldg(p.window + (t + 16 * j) * 256 + col);
+      v[j].x *= wv; v[j].y *= wv;
+    }
+  }
+  fft16(v);                                         // over j: Y[t][ka], ka = REV16(position)
+  __syncthreads();                                  // tables loaded
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int ka = REV16(q);
+    float2 y = v[q];
+    if (ka) y = cmulf(y, s_tw[t * ka]);             // W_256^(t ka)
+    sm[c * LDC + ka * 17 + t] = y;
+  }
+  __syncthreads();
+  const int ka = t;                                 // second butterfly: thread (c, ka) gathers all t
+#pragma unroll
+  for (int tt = 0; tt < 16; ++tt) v[tt] = sm[c * LDC + ka * 17 + tt];
+  fft16(v);                                         // over t: X[ka + 16 kb], kb = REV16(position)
+  float2 *__restrict__ out = p.scratch + (size_t) blockIdx.y * 65536;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int kb = REV16(q);
+    const int k1 = ka + 16 * kb;
+    const int pw = col * k1;                        // < 65536
+    const float2 tw = cmulf(s_tw[pw >> 8], s_fine[pw & 255]);
+    out[(size_t) k1 * 256 + col] = cmulf(v[q], tw);
+  }
+}
+
+cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
+                               const float2 *twfine, int win_base, int n_win)
+{
+  Cols256K p;
+  p.x = a.x; p.stream_stride = a.stream_stride; p.hist = a.hist; p.hist_len = a.hist_len;
+  p.windows_per_stream = a.windows_per_stream; p.first_window = a.first_window; p.hop = a.hop;
+  p.base_off = a.base_off; p.win_base = win_base; p.window = a.window; p.scratch = a.scratch;
+  p.tw256 = fs.twN1; p.twfine = twfine;
+  dim3 grid(16, n_win);
+  k_cols256<<<grid, 256, 0, c.stream>>>(p);
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Rows256K {
+  const float2 *scratch;
+  float *psd; float inv_n; int shift_db;
+  const int *binmap; float2 *cspec; int n_bins;
+  const float2 *tw256;
+};
+
+#define LDR 273
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
+{
+  extern __shared__ float2 smr[];                   // 32 rows x LDR
+  __shared__ float2 s_tw[256];
+  const int tid = threadIdx.x;
+  if (tid < 256) s_tw[tid] = __ldg(p.tw256 + tid);
+  const int win = blockIdx.y, k1_0 = blockIdx.x * 32;
+  const float2 *__restrict__ in = p.scratch + (size_t) win * 65536 + (size_t) k1_0 * 256;
+  {
+    const int t = tid & 15, r = tid >> 4;           // 32 rows x 16 t
+    float2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = in[(size_t) r * 256 + t + 16 * j];
+    fft16(v);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int ka = REV16(q);
+      float2 y = v[q];
+      if (ka) y = cmulf(y, s_tw[t * ka]);
+      smr[r * LDR + ka * 17 + t] = y;
+    }
+  }
+  __syncthreads();
+  {
+    const int r = tid & 31, ka = tid >> 5;          // a warp = 32 consecutive rows = 32 consecutive bins
+    float2 v[16];
+#pragma unroll
+    for (int tt = 0; tt < 16; ++tt) v[tt] = smr[r * LDR + ka * 17 + tt];
+    fft16(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int kb = REV16(q);
+      const int k = k1_0 + r + 256 * (ka + 16 * kb);
+      if (MODE == 0) {
+        float pw = (v[q].x * v[q].x + v[q].y * v[q].y) * p.inv_n;
+        float *__restrict__ psd = p.psd + (size_t) win * 65536;
+        if (p.shift_db) { pw = 10.0f * log10f(pw + 1e-8f); psd[(k + 32768) & 65535] = pw; }
+        else psd[k] = pw;
+      } else {
+        const int m = __ldg(p.binmap + k);
+        if (m >= 0) p.cspec[(size_t) win * p.n_bins + m] = v[q];
+      }
+    }
+  }
+}
+
+cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a, int mode)
+{
+  Rows256K p;
+  p.scratch = a.scratch; p.psd = a.psd; p.inv_n = a.inv_n; p.shift_db = a.shift_db;
+  p.binmap = a.binmap; p.cspec = a.cspec; p.n_bins = a.n_bins; p.tw256 = fs.twN2;
+  const size_t smem = (size_t) 32 * LDR * sizeof(float2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_rows256<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    attr_done = true;
+  }
+  dim3 grid(8, a.n_windows);
+  if (mode == 0) k_rows256<0><<<grid, 512, smem, c.stream>>>(p);
+  else           k_rows256<1><<<grid, 512, smem, c.stream>>>(p);
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}

@@ -141,6 +141,10 @@ struct SdbLaunchCtx {
 
 cudaError_t sdb_launch_pass_a_range(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
                                     int win_base, int n_win);
+// 65536 = 256 x 256 specialisation (fft256_kernels.cu)
+cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
+                               const float2 *twfine, int win_base, int n_win);
+cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a, int mode);
 cudaError_t sdb_launch_pass_b_psd(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a);
 cudaError_t sdb_launch_pass_b_chan(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a);
 cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const float2 *x,
@@ -155,9 +159,10 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
                                     int n_streams, SdbChainState *state, float *pool, size_t pool_stride,
                                     const float *taps_pool, const SdbChannelDev *chans_dev,
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
-                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap);
+                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap,
+                                    int fresh);
 cudaError_t sdb_launch_task_xlate(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
                                   float omega, float phi0);
 cudaError_t sdb_launch_task_quad(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch);
 cudaError_t sdb_launch_task_chain(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
-                                  const SdbChainCfg &c, int mode, float *pool, size_t pool_stride);
+                                  const SdbChainCfg *cfg_dev, int mode, float *pool, size_t pool_stride);
