@@ -264,9 +264,11 @@ def run_cuda(args):
 
     # ---- per-kernel device times (separate, untimed-for-value pass with event spans)
     e.timing(True)
+    sdb.stage_cycles(reset=True)
     for _ in range(2):
         step_dev()
     e.sync()
+    stage_bal = sdb.stage_cycles(reset=True)
     fam = {f: e.kernel_time(f) for f in ("fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft", "inspector")}
     e.timing(False)
     wps, frames = H, H // 2
@@ -291,6 +293,7 @@ def run_cuda(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "kernel_share_of_step": tot[dom] / max(1e-9, sum(tot.values())),
                 "kernel_ms": {f: round(fam[f][0], 4) for f in fam},
+                "inspector_stage_cycles_per_sample": {k_: round(v_, 1) for k_, v_ in stage_bal.items()},
                 "path": {"b_alg_bytes_per_sample": B_ALG[name],
                          "achieved": B_ALG[name] * value * 1e6 / world / 1e9,
                          "frac": B_ALG[name] * value * 1e6 / world / 1e9 / peak}}

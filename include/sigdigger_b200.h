@@ -149,6 +149,9 @@ uint64_t sdb_engine_launch_count(const sdb_engine_t *e);
  * "chan_ifft", "inspector" */
 int      sdb_engine_kernel_time(sdb_engine_t *e, const char *family, double *avg_ms, uint64_t *launches);
 void     sdb_engine_timing(sdb_engine_t *e, int enable);
+/* inspector-kernel stage balance since the last reset: out[0..3] = busy SM cycles of the gain / carrier /
+ * filter / clock stage warps summed over CTAs, out[4] = chunk-samples processed (profiling aid) */
+int      sdb_debug_stage_cycles(uint64_t out[8], int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * Offline Tasks/ primitives over a whole capture buffer (host pointers; one GPU chain each; the
@@ -171,6 +174,32 @@ int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batc
 /* LPFTask: su_specttuner low-pass with guard = 2 pi / bw, output length == input length
  * (Tasks/LPFTask.cpp:52-69,83-87,104-107) */
 int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
+
+/* ------------------------------------------------------------------------------------------------
+ * Panoramic scanner: SpectrumView (Panoramic/Scanner.cpp:36-293, constants include/Scanner.h:26-32).
+ * The reference does view.feed(psd, nullptr, fftSize, fc) per PSD message on the GUI thread
+ * (Panoramic/Scanner.cpp:503-523).  Here the per-hop projection (the O(psd_size) part) is separate from
+ * the order-dependent per-bin accumulation so that hops can be spread over GPUs: project on every rank,
+ * gather the small contribution lists (NCCL), accumulate on rank 0.  project + accumulate of the same
+ * hops in the same order == the reference's feed() sequence, value by value.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sdb_sview sdb_sview_t;
+sdb_sview_t *sdb_sview_new(int device);
+void         sdb_sview_destroy(sdb_sview_t *v);
+/* SpectrumView::setRange + fftBandwidth / fftRelBw members; resets the view */
+int      sdb_sview_set_range(sdb_sview_t *v, double freq_min, double freq_max, double fft_bandwidth, float rel_bw);
+int      sdb_sview_reset(sdb_sview_t *v);                         /* SpectrumView::reset */
+uint32_t sdb_sview_size(const sdb_sview_t *v);                    /* spectrumSize */
+uint32_t sdb_sview_max_bins(const sdb_sview_t *v);                /* row pitch of the contribution lists */
+/* psd_dev: device pointer [n_hops][psd_size], PSDMessage layout (shifted, dB); centers: host doubles */
+int      sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t psd_size, const double *centers,
+                           size_t n_hops, int adjust_sides);
+/* device pointers of the last projection: j0[n_hops], nb[n_hops], va/vc[n_hops][max_bins] */
+int      sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc);
+/* apply contribution lists (device pointers; own or gathered from peers) in hop order, then fill gaps */
+int      sdb_sview_accumulate(sdb_sview_t *v, const int32_t *j0, const int32_t *nb, const float *va,
+                              const float *vc, size_t n_hops);
+int      sdb_sview_read(sdb_sview_t *v, float *psd, float *accum, float *count, size_t cap);
 
 /* Offline inspector over captured channel-rate buffers (the block-wise CPU loops the GUI's TimeWindow
  * launches, Components/TimeWindow.cpp:1571-2183; sampler + decider of Tasks/WaveSampler.cpp:188-205,

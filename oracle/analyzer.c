@@ -31,8 +31,9 @@ typedef struct {
 struct sdo_analyzer {
   sdo_an_params   p;
   sdo_an_channel *chdefs;
-  sdo_fft_plan    psd_plan;
+  sdo_spec_plan   psd_plan;
   float          *window;
+  int             psd_window_none;
   sdo_cpx        *frame, *scratch;
   unsigned        frame_fill;
   sdo_specttuner *st;
@@ -72,9 +73,10 @@ sdo_analyzer *sdo_analyzer_new(const sdo_an_params *p)
   a->chdefs = (sdo_an_channel *) malloc(sizeof(sdo_an_channel) * (p->n_channels ? p->n_channels : 1));
   memcpy(a->chdefs, p->channels, sizeof(sdo_an_channel) * p->n_channels);
   a->p.channels = a->chdefs;
-  if (sdo_fft_plan_init(&a->psd_plan, p->psd_size) != 0) { free(a->chdefs); free(a); return NULL; }
+  if (sdo_spec_plan_init(&a->psd_plan, p->psd_size, 0) != 0) { free(a->chdefs); free(a); return NULL; }
   a->window = (float *) malloc(sizeof(float) * p->psd_size);
   sdo_window_fill(a->window, p->psd_size, p->psd_window);
+  a->psd_window_none = p->psd_window == SDO_WINDOW_NONE;
   a->frame = (sdo_cpx *) malloc(sizeof(sdo_cpx) * p->psd_size);
   a->scratch = (sdo_cpx *) malloc(sizeof(sdo_cpx) * 2 * p->psd_size);
   ws = p->st_window_size ? p->st_window_size : p->psd_size;
@@ -105,7 +107,7 @@ void sdo_analyzer_destroy(sdo_analyzer *a)
     free(a->chans[k].tmp);
   }
   sdo_specttuner_destroy(a->st);
-  sdo_fft_plan_free(&a->psd_plan);
+  sdo_spec_plan_free(&a->psd_plan);
   free(a->window); free(a->frame); free(a->scratch); free(a->chans); free(a->chdefs); free(a);
 }
 
@@ -132,7 +134,8 @@ int sdo_analyzer_feed(sdo_analyzer *a, const sdo_cpx *x, size_t n,
     a->frame_fill += (unsigned) take; off += take;
     if (a->frame_fill == N) {
       if (psd_out && frames < n_frames_cap)
-        sdo_psd_frame(&a->psd_plan, a->window, a->frame, psd_out + frames * N, a->scratch);
+        sdo_psd_frame_spec(&a->psd_plan, a->psd_window_none ? NULL : a->window, a->frame, psd_out + frames * N,
+                           a->scratch);
       ++frames;
       a->frame_fill = 0;
     }

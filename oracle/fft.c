@@ -110,6 +110,18 @@ void sdo_psd_frame(const sdo_fft_plan *p, const float *window, const sdo_cpx *x,
     psd[i] = (X[i].re * X[i].re + X[i].im * X[i].im) * inv_n;
 }
 
+/* same, with the SPEC transform (bit-identical to the CUDA path) */
+void sdo_psd_frame_spec(const sdo_spec_plan *p, const float *window, const sdo_cpx *x, float *psd,
+                        sdo_cpx *scratch)
+{
+  const unsigned n = p->N;
+  const float inv_n = 1.0f / (float) n;
+  unsigned i;
+  sdo_spec_forward(p, x, window, scratch);
+  for (i = 0; i < n; ++i)
+    psd[i] = (scratch[i].re * scratch[i].re + scratch[i].im * scratch[i].im) * inv_n;
+}
+
 /* Suscan/Messages/PSDMessage.cpp:32-38 -- swap halves and convert to dB in one pass. */
 void sdo_psd_shift_db(float *psd, unsigned n)
 {

@@ -60,6 +60,23 @@ int  sdo_fft_plan_init(sdo_fft_plan *p, unsigned n);
 void sdo_fft_plan_free(sdo_fft_plan *p);
 void sdo_fft_exec(const sdo_fft_plan *p, const sdo_cpx *in, sdo_cpx *out, int sign);
 
+/* SPEC FFT (SPEC.md F.2-F.4, fft_spec.c): the fixed dataflows the CUDA kernels also follow, so that
+ * transforms are bit-identical on both sides.  sdo_fft_exec above is the independent cross-check. */
+typedef struct {
+  unsigned N, N1, N2;
+  int      four, kind;       /* kind 0: single Stockham, 1: four-step, 2: 65536 = 256 x 256 fft16 form */
+  sdo_cpx *tw_a, *tw_b, *tw_n, *scr, *buf, *tmp;
+} sdo_spec_plan;
+sdo_cpx *sdo_spec_twiddles(unsigned n);
+void sdo_spec_fft_stockham(sdo_cpx *s, unsigned M, const sdo_cpx *tw, int sign, sdo_cpx *tmp);
+int  sdo_spec_plan_init(sdo_spec_plan *p, unsigned N, int four);
+void sdo_spec_plan_free(sdo_spec_plan *p);
+void sdo_spec_forward(const sdo_spec_plan *p, const sdo_cpx *x, const float *window, sdo_cpx *X);
+void sdo_spec_inverse_stockham(const sdo_spec_plan *p, sdo_cpx *s);
+/* main PSD with the SPEC transform: psd[k] = (re^2 + im^2) * (1/N) */
+void sdo_psd_frame_spec(const sdo_spec_plan *p, const float *window, const sdo_cpx *x, float *psd,
+                        sdo_cpx *scratch /* N */);
+
 /* ------------------------------------------------------------------------------------------------
  * Windows (SPEC.md section W; su_taps_apply_*_complex seen at Tasks/CarrierDetector.cpp:87-89,
  * enum order at include/Suscan/AnalyzerParams.h:37-43).
@@ -221,7 +238,7 @@ struct sdo_st_channel {
   sdo_cpx *ifft[2];  /* size each */
   sdo_cpx *out;      /* halfsz */
   int      state;
-  sdo_fft_plan plan;
+  sdo_cpx *tw, *tmp; /* W_size table and scratch of the inverse transform */
   struct sdo_st_channel *next;
 };
 

@@ -17,7 +17,7 @@ struct sdo_specttuner {
   unsigned     window_size, half_size, p;
   sdo_cpx     *window;   /* window_size input samples */
   sdo_cpx     *fft;      /* window_size spectrum */
-  sdo_fft_plan plan;
+  sdo_spec_plan plan;      /* forward transform: SPEC F.3 / F.4, always the four-step form */
   sdo_st_channel *channels;
   unsigned long hops;
 };
@@ -72,7 +72,7 @@ sdo_specttuner *sdo_specttuner_new(unsigned window_size)
 {
   sdo_specttuner *st = (sdo_specttuner *) calloc(1, sizeof(*st));
   if (!st) return NULL;
-  if (sdo_fft_plan_init(&st->plan, window_size) != 0) { free(st); return NULL; }
+  if (sdo_spec_plan_init(&st->plan, window_size, 1) != 0) { free(st); return NULL; }
   st->window_size = window_size;
   st->half_size = window_size / 2;
   st->window = (sdo_cpx *) calloc(window_size, sizeof(sdo_cpx));
@@ -83,7 +83,7 @@ sdo_specttuner *sdo_specttuner_new(unsigned window_size)
 static void channel_free(sdo_st_channel *ch)
 {
   free(ch->h); free(ch->window); free(ch->fft); free(ch->ifft[0]); free(ch->ifft[1]); free(ch->out);
-  sdo_fft_plan_free(&ch->plan);
+  free(ch->tw); free(ch->tmp);
   free(ch);
 }
 
@@ -92,7 +92,7 @@ void sdo_specttuner_destroy(sdo_specttuner *st)
   sdo_st_channel *ch, *nx;
   if (!st) return;
   for (ch = st->channels; ch; ch = nx) { nx = ch->next; channel_free(ch); }
-  sdo_fft_plan_free(&st->plan);
+  sdo_spec_plan_free(&st->plan);
   free(st->window); free(st->fft); free(st);
 }
 
@@ -119,7 +119,8 @@ sdo_st_channel *sdo_specttuner_open_channel(sdo_specttuner *st, const sdo_st_cha
   ch->ifft[0] = (sdo_cpx *) calloc(ch->size, sizeof(sdo_cpx));
   ch->ifft[1] = (sdo_cpx *) calloc(ch->size, sizeof(sdo_cpx));
   ch->out = (sdo_cpx *) calloc(ch->halfsz, sizeof(sdo_cpx));
-  if (sdo_fft_plan_init(&ch->plan, ch->size) != 0) { channel_free(ch); return NULL; }
+  ch->tw = sdo_spec_twiddles(ch->size);
+  ch->tmp = (sdo_cpx *) malloc(sizeof(sdo_cpx) * ch->size);
   sdo_st_filter_response(st->window_size, ch->halfw, ch->h);
   for (i = 0; i < st->window_size; ++i) ch->h[i] = ch->k * ch->h[i];
   for (i = 0; i < ch->size; ++i) {
@@ -156,7 +157,8 @@ static int feed_channel(sdo_specttuner *st, sdo_st_channel *ch)
   }
   curr = ch->ifft[ch->state];
   prev = ch->ifft[!ch->state] + hs;
-  sdo_fft_exec(&ch->plan, ch->fft, curr, +1);
+  memcpy(curr, ch->fft, sizeof(sdo_cpx) * sz);
+  sdo_spec_fft_stockham(curr, sz, ch->tw, +1, ch->tmp);   /* SPEC S.4: inverse F.2 */
   for (i = 0; i < hs; ++i) {
     float al = ch->window[i], be = ch->window[i + hs];
     sdo_cpx o;
@@ -186,7 +188,7 @@ int sdo_specttuner_feed_bulk(sdo_specttuner *st, const sdo_cpx *x, size_t n)
     memcpy(st->window + st->p, x, take * sizeof(sdo_cpx));
     st->p += (unsigned) take; x += take; n -= take;
     if (st->p == st->window_size) {
-      sdo_fft_exec(&st->plan, st->window, st->fft, -1);
+      sdo_spec_forward(&st->plan, st->window, NULL, st->fft);
       ++st->hops;
       for (ch = st->channels; ch; ch = ch->next)
         if (!feed_channel(st, ch)) return 0;

@@ -71,12 +71,24 @@ _PROTOS = {
     "sdb_engine_launch_count": (C.c_uint64, [C.c_void_p]),
     "sdb_engine_kernel_time": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "sdb_engine_timing": (None, [C.c_void_p, C.c_int]),
+    "sdb_debug_stage_cycles": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "sdb_task_carrier_xlate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_float]),
     "sdb_task_quad_demod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sdb_task_costas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_float]),
     "sdb_task_pll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_agc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_lpf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_sview_new": (C.c_void_p, [C.c_int]),
+    "sdb_sview_destroy": (None, [C.c_void_p]),
+    "sdb_sview_set_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_float]),
+    "sdb_sview_reset": (C.c_int, [C.c_void_p]),
+    "sdb_sview_size": (C.c_uint32, [C.c_void_p]),
+    "sdb_sview_max_bins": (C.c_uint32, [C.c_void_p]),
+    "sdb_sview_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "sdb_sview_contrib": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "sdb_sview_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_sview_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_task_inspector": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t]),
 }
@@ -109,6 +121,15 @@ def device_count():
 
 class SdbError(RuntimeError):
     pass
+
+
+def stage_cycles(reset=False):
+    """Inspector-kernel stage balance: dict of busy cycles per stage per processed chunk-sample."""
+    buf = (C.c_uint64 * 8)()
+    _check(load_library().sdb_debug_stage_cycles(buf, int(reset)))
+    n = max(1, buf[4])
+    return {"gain": buf[0] / n, "carrier": buf[1] / n, "filter": buf[2] / n, "clock": buf[3] / n,
+            "chunk_samples": int(buf[4])}
 
 
 def _check(rc):
@@ -223,6 +244,10 @@ class Engine:
         return self._L.sdb_engine_symbol_capacity(self._h)
 
     @property
+    def psd_device_ptr(self):
+        return self._L.sdb_engine_psd_device(self._h)
+
+    @property
     def stream_ptr(self):
         return self._L.sdb_engine_stream(self._h)
 
@@ -298,3 +323,56 @@ def inspector_run(cls, fs, x, **kw):
     _check(L.sdb_task_inspector(C.byref(cfg), x.ctypes.data, n, batch, soft.ctypes.data, hard.ctypes.data,
                                 counts.ctypes.data, cap))
     return [(soft[b, :counts[b]].copy(), hard[b, :counts[b]].copy()) for b in range(batch)]
+
+
+class SpectrumView:
+    """Panoramic stitcher (Panoramic/Scanner.cpp:36-293). project() per rank, accumulate() on the owner."""
+
+    def __init__(self, freq_min, freq_max, fft_bandwidth, rel_bw=0.5, device=0):
+        self._L = load_library()
+        self._h = self._L.sdb_sview_new(device)
+        if not self._h:
+            raise SdbError(last_error())
+        _check(self._L.sdb_sview_set_range(self._h, freq_min, freq_max, fft_bandwidth, rel_bw))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_sview_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def size(self):
+        return self._L.sdb_sview_size(self._h)
+
+    @property
+    def max_bins(self):
+        return self._L.sdb_sview_max_bins(self._h)
+
+    def reset(self):
+        _check(self._L.sdb_sview_reset(self._h))
+
+    def project(self, psd_dev_ptr, psd_size, centers, adjust_sides=True):
+        centers = np.ascontiguousarray(centers, dtype=np.float64)
+        self._centers = centers
+        _check(self._L.sdb_sview_project(self._h, psd_dev_ptr, psd_size, centers.ctypes.data, len(centers),
+                                         int(adjust_sides)))
+        self._n_hops = len(centers)
+
+    def contrib_ptrs(self):
+        p = [C.c_void_p() for _ in range(4)]
+        _check(self._L.sdb_sview_contrib(self._h, *[C.byref(q) for q in p]))
+        return [q.value for q in p]
+
+    def accumulate(self, j0_ptr=None, nb_ptr=None, va_ptr=None, vc_ptr=None, n_hops=None):
+        if j0_ptr is None:
+            j0_ptr, nb_ptr, va_ptr, vc_ptr = self.contrib_ptrs()
+            n_hops = self._n_hops
+        _check(self._L.sdb_sview_accumulate(self._h, j0_ptr, nb_ptr, va_ptr, vc_ptr, n_hops))
+
+    def read(self):
+        n = self.size
+        psd, acc, cnt = (np.empty(n, np.float32) for _ in range(3))
+        _check(self._L.sdb_sview_read(self._h, psd.ctypes.data, acc.ctypes.data, cnt.ctypes.data, n))
+        return psd, acc, cnt

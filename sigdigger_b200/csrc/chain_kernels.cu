@@ -227,13 +227,56 @@ static __device__ __forceinline__ unsigned char decide(int mode, float dmin, flo
 // lives in registers for the whole feed.  Chains are ordered channel-major so a warp normally holds 32
 // streams of the SAME channel (uniform configuration, no divergence).
 #define CHUNK 32
-#define MF_RING 64
+#define MF_RING 64      // longest matched filter kept in shared memory
+#define MF_SLOTS 80     // 8 margin + 2 * 32 (duplicated short line) or 64 (single long line), + slack
+__device__ unsigned long long g_stage_cycles[8];
+
+cudaError_t sdb_stage_cycles(unsigned long long out[8], int reset)
+{
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_stage_cycles, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[8] = { 0 };
+    e = cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z));
+  }
+  return e;
+}
+static __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+  const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 struct ChainSmem {
-  float2 tile[32][33];
+  float2 tile[2][32][33];
   float2 ring[3][2][CHUNK][32];
-  float2 mfh[MF_RING][32];
+  float2 mfh[MF_SLOTS][32];
   float  agc[48][32];
+  float  lvl[CHUNK][32];
 };
+
+// Matched filter for mf_n <= 32 taps, NT = mf_n rounded up to a multiple of 8.  The line is kept twice
+// (slot p and p + mf_n, after a margin of 8 slots) so that x[n-t] is always at slot base - t: every
+// load has a compile-time offset from one base address and none depends on another.  Taps t >= mf_n
+// are zero: adding +-0 to a +0-initialised accumulator never changes its bits, so the result is exactly
+// the SPEC I.1 sum over mf_n taps.
+template <int NT>
+static __device__ __forceinline__ float2 mf_fir(const float2 (*mfh)[32], int lane, unsigned ptr, int mf_n,
+                                                const float (&tp)[32])
+{
+  const float2 *base = &mfh[8 + ptr + mf_n][lane];
+  float accr = 0.0f, acci = 0.0f;
+  float2 v[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) v[t] = base[-t * 32];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    accr = accr + tp[t] * v[t].x;
+    acci = acci + tp[t] * v[t].y;
+  }
+  return make_float2(accr, acci);
+}
 
 __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
                                                      int n_streams, SdbChainState *__restrict__ states,
@@ -279,6 +322,7 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
   // stage 2
   int mf_n = 0, have_mf = 0, alpf_n = 0; unsigned mf_ptr = 0; const float *taps = nullptr; float *mfl = nullptr;
   float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
+  float tp[32];     // matched-filter taps in registers when mf_n <= 32
   // stage 3
   ClockS ks; float clk_gain = 0, clk_alpha = 0, clk_beta = 0, smp_period = 0, smp_phase0 = 0, s_phase = 0, s_pr = 0, s_pi = 0;
   int clock_type = 1, clock_running = 1, dec_mode = 0, dec_int = 1; float dec_min = 0, dec_h = 1;
@@ -331,12 +375,16 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
         al_b[i] = cp->alpf_b[i]; al_a[i] = cp->alpf_a[i]; al_x[i] = stp->al_x[i]; al_y[i] = stp->al_y[i];
         al_xi[i] = 0.0f; al_yi[i] = 0.0f;
       }
+#pragma unroll
+      for (int t = 0; t < 32; ++t) tp[t] = (have_mf && t < mf_n) ? __ldg(taps + t) : 0.0f;
       float *gmf = bpool + (size_t) cp->st_mf_off * 32;
+      for (int i = 0; i < MF_SLOTS; ++i) sm.mfh[i][lane] = make_float2(0.f, 0.f);
       if (have_mf && mf_n <= MF_RING) {
         mfl = reinterpret_cast<float *>(&sm.mfh[0][lane]);   // float2 ring, stride 32 float2 = 64 floats
         for (int i = 0; i < mf_n; ++i) {
           float2 v = fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * i) * 32], gmf[(2 * i + 1) * 32]);
-          sm.mfh[i][lane] = v;
+          if (mf_n <= 32) { sm.mfh[8 + i][lane] = v; sm.mfh[8 + i + mf_n][lane] = v; }   // duplicated line
+          else sm.mfh[i][lane] = v;
         }
       } else {
         mfl = gmf;
@@ -355,39 +403,106 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
   }
   float2 *__restrict__ so = soft + (size_t) chain * sym_cap;
   unsigned char *__restrict__ ho = hard + (size_t) chain * sym_cap;
+  // coalesced, asynchronous tile load: row r of the tile = CHUNK consecutive samples of the CTA's chain r
+  // (= lane r's own chain); lane L copies column L of every row.  Double-buffered one chunk ahead.
+  const unsigned long long rowp =
+      valid ? (unsigned long long) (chan_in + (size_t) s * chan_stream_stride + chans[k].out_off) : 0ull;
+  auto issue_tile = [&](uint32_t c) {
+    const uint32_t b0 = c * CHUNK;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const unsigned long long pr = __shfl_sync(0xffffffffu, rowp, r);
+      const uint32_t nr = __shfl_sync(0xffffffffu, n, r);
+      if (b0 + lane < nr) cp_async8(&sm.tile[c & 1][r][lane], (const float2 *) pr + b0 + lane);
+    }
+    cp_async_commit();
+  };
+  if (warp == 0 && nchunks > 0) issue_tile(0);
   __syncthreads();
 
+  long long busy = 0;
   for (uint32_t it = 0; it < nchunks + 3; ++it) {
+    const long long t_begin = clock64();
     if (warp == 0) {
       if (it < nchunks) {
         const uint32_t base = it * CHUNK;
-        // cooperative, coalesced load of CHUNK samples of each of the CTA's 32 chains
-        for (int r = 0; r < 32; ++r) {
-          const int gr = blockIdx.x * 32 + r;
-          if (gr < chains) {
-            const int kr = gr / n_streams, sr = gr - kr * n_streams;
-            const uint32_t nr = n_hops * (uint32_t) chans[kr].halfsz;
-            if (base + lane < nr)
-              sm.tile[r][lane] = __ldg(chan_in + (size_t) sr * chan_stream_stride + chans[kr].out_off + base + lane);
-          }
+        // chunk `it` was prefetched (cp.async) one iteration ago; start the copy of chunk it+1 now
+        if (it + 1 < nchunks) {
+          issue_tile(it + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
         }
         __syncwarp();
         float2 (*out)[32] = sm.ring[0][it & 1];
-        for (int i = 0; i < CHUNK; ++i) {
-          if (base + i < n) {
-            float2 y = sm.tile[lane][i];
+        float2 (*tl)[33] = sm.tile[it & 1];
+        const int cnt = base >= n ? 0 : (n - base < CHUNK ? (int) (n - base) : CHUNK);
+        if (have_agc && cls != SDB_INSP_RAW) {
+          // Same arithmetic as agc_step() per sample, regrouped so that the long independent parts
+          // (log10 of the magnitudes, 10^x of the gains) of different samples overlap; only the
+          // peak / level tracker in the middle is a true recurrence.
+          // pass 1: LO, delay-line swap, magnitude [dB]
+          unsigned dlp = as.dl_ptr;
+#pragma unroll 4
+          for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+              float2 y = tl[lane][i];
+              if (have_lo) {
+                float2 ph = ncqo_read(lo_phi, lo_omega);
+                y = make_float2(y.x * ph.x + y.y * ph.y, y.y * ph.x - y.x * ph.y);
+              }
+              const unsigned dp = dlp;
+              dlp = dlp + 1 >= ak.dl_size ? 0 : dlp + 1;
+              const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
+              dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
+              out[i][lane] = xd;
+              sm.lvl[i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
+            }
+          }
+          as.dl_ptr = dlp;
+          // pass 2: magnitude history, running peak, fast / slow levels (serial)
+          for (int i = 0; i < cnt; ++i) {
+            const float m = sm.lvl[i][lane];
+            const float m_old = mh[as.mh_ptr * 32];
+            mh[as.mh_ptr * 32] = m;
+            if (++as.mh_ptr >= ak.mh_size) as.mh_ptr = 0;
+            if (m > as.peak) {
+              as.peak = m;
+            } else if (as.peak == m_old) {
+              float pk = -160.0f;
+              for (unsigned q = 0; q < ak.mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
+              as.peak = pk;
+            }
+            float d = as.peak - as.fast;
+            if (d > 0.0f) as.fast = as.fast + ak.far_ * d;
+            else          as.fast = as.fast + ak.faf * d;
+            d = as.peak - as.slow;
+            if (d > 0.0f) { as.slow = as.slow + ak.sar * d; as.hang_n = 0; }
+            else if (as.hang_n >= ak.hang_max) as.slow = as.slow + ak.saf * d;
+            else ++as.hang_n;
+            sm.lvl[i][lane] = as.fast > as.slow ? as.fast : as.slow;
+          }
+          // pass 3: gain and scaling of the delayed sample
+#pragma unroll 4
+          for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+              const float lvl = sm.lvl[i][lane];
+              float g = lvl < ak.knee ? ak.fixed_gain : d_db_to_mag(lvl * ak.slope_m1);
+              g = g * 0.7f;
+              float2 y = out[i][lane];
+              y.x = y.x * g; y.y = y.y * g;
+              if (cls != SDB_INSP_AUDIO) { y.x = 2.0f * y.x; y.y = 2.0f * y.y; }
+              out[i][lane] = y;
+            }
+          }
+        } else {
+          for (int i = 0; i < cnt; ++i) {
+            float2 y = tl[lane][i];
             if (have_lo) {
               float2 ph = ncqo_read(lo_phi, lo_omega);
               y = make_float2(y.x * ph.x + y.y * ph.y, y.y * ph.x - y.x * ph.y);
             }
-            if (cls != SDB_INSP_RAW) {
-              if (have_agc) {
-                y = agc_step(ak, as, dl, mh, y);
-                if (cls != SDB_INSP_AUDIO) { y.x = 2.0f * y.x; y.y = 2.0f * y.y; }
-              } else if (cls != SDB_INSP_AUDIO) {
-                y.x = gain2 * y.x; y.y = gain2 * y.y;
-              }
-            }
+            if (cls != SDB_INSP_RAW && cls != SDB_INSP_AUDIO) { y.x = gain2 * y.x; y.y = gain2 * y.y; }
             out[i][lane] = y;
           }
         }
@@ -448,7 +563,17 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
             float2 y = in[i][lane];
             if (have_mf) {
               float accr = 0.0f, acci = 0.0f;
-              if (mf_n <= MF_RING) {
+              if (mf_n <= 32) {
+                // taps in registers, duplicated line, branch-free unrolled sum (see mf_fir)
+                sm.mfh[8 + mf_ptr][lane] = y;
+                sm.mfh[8 + mf_ptr + mf_n][lane] = y;
+                float2 r;
+                if (mf_n <= 8)       r = mf_fir<8>(sm.mfh, lane, mf_ptr, mf_n, tp);
+                else if (mf_n <= 16) r = mf_fir<16>(sm.mfh, lane, mf_ptr, mf_n, tp);
+                else if (mf_n <= 24) r = mf_fir<24>(sm.mfh, lane, mf_ptr, mf_n, tp);
+                else                 r = mf_fir<32>(sm.mfh, lane, mf_ptr, mf_n, tp);
+                accr = r.x; acci = r.y;
+              } else if (mf_n <= MF_RING) {
                 sm.mfh[mf_ptr][lane] = y;
                 unsigned p = mf_ptr;
                 for (int t = 0; t < mf_n; ++t) {
@@ -514,7 +639,12 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
         }
       }
     }
+    busy += clock64() - t_begin;
     __syncthreads();
+  }
+  if (lane == 0) {   // stage balance bookkeeping (profiles/): busy cycles per stage, samples processed
+    atomicAdd(&g_stage_cycles[warp], (unsigned long long) busy);
+    if (warp == 0) atomicAdd(&g_stage_cycles[4], (unsigned long long) nchunks * CHUNK);
   }
 
   // ------------------------------------------------------------------ write state back
@@ -543,7 +673,10 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
       if (have_mf && mf_n <= MF_RING) {
         float *gmf = bpool + (size_t) cp->st_mf_off * 32;
-        for (int i = 0; i < mf_n; ++i) { float2 v = sm.mfh[i][lane]; gmf[(2 * i) * 32] = v.x; gmf[(2 * i + 1) * 32] = v.y; }
+        for (int i = 0; i < mf_n; ++i) {
+          float2 v = mf_n <= 32 ? sm.mfh[8 + i][lane] : sm.mfh[i][lane];
+          gmf[(2 * i) * 32] = v.x; gmf[(2 * i + 1) * 32] = v.y;
+        }
       }
     } else {
       stp->k_phi = ks.phi; stp->k_bnor = ks.bnor; stp->k_x0r = ks.x0r; stp->k_x0i = ks.x0i; stp->k_x1r = ks.x1r;

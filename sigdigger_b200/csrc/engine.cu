@@ -666,6 +666,16 @@ extern "C" void sdb_engine_timing(sdb_engine_t *e, int enable)
   e->timing = enable != 0;
   for (int i = 0; i < FAM_COUNT; ++i) { e->fam_ms[i] = 0; e->fam_n[i] = 0; }
 }
+cudaError_t sdb_stage_cycles(unsigned long long out[8], int reset);
+extern "C" int sdb_debug_stage_cycles(uint64_t out[8], int reset)
+{
+  unsigned long long tmp[8];
+  CK(cudaDeviceSynchronize());
+  CK(sdb_stage_cycles(tmp, reset));
+  for (int i = 0; i < 8; ++i) out[i] = tmp[i];
+  return 0;
+}
+
 extern "C" int sdb_engine_kernel_time(sdb_engine_t *e, const char *family, double *avg_ms, uint64_t *launches)
 {
   if (!e || !family) return fail("null argument");
@@ -864,4 +874,135 @@ extern "C" int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, 
   } while (0);
   sdb_engine_destroy(e);
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpectrumView (Panoramic/Scanner.cpp:36-293): panoramic stitcher
+// ---------------------------------------------------------------------------------------------
+cudaError_t sdb_launch_sview_project(cudaStream_t s, double freq_min, double freq_range, double fft_bandwidth,
+                                     float rel_bw, unsigned spectrum_size, const float *psd, size_t psd_size,
+                                     const double *centers_dev, int n_hops, int adjust_sides, int *j0, int *nb,
+                                     float *va, float *vc, int max_bins);
+cudaError_t sdb_launch_sview_accumulate(cudaStream_t s, unsigned spectrum_size, const int *j0, const int *nb,
+                                        const float *va, const float *vc, int n_hops, int max_bins, float *psd,
+                                        float *accum, float *count);
+
+struct sdb_sview {
+  int device = 0;
+  double freq_min = 0, freq_max = 0, freq_range = 0, fft_bandwidth = 0;
+  float rel_bw = 0.5f;                     // include/Scanner.h:70
+  unsigned spectrum_size = 65536;          // SIGDIGGER_SCANNER_SPECTRUM_SIZE
+  int max_bins = 0;
+  float *d_psd = nullptr, *d_accum = nullptr, *d_count = nullptr;
+  size_t hop_cap = 0;
+  double *d_centers = nullptr; int *d_j0 = nullptr, *d_nb = nullptr; float *d_va = nullptr, *d_vc = nullptr;
+};
+
+extern "C" sdb_sview_t *sdb_sview_new(int device)
+{
+  if (sdb_device_count() <= 0) { g_err = "no CUDA device: sigdigger_b200 has no CPU fallback"; return nullptr; }
+  CKP(cudaSetDevice(device));
+  sdb_sview *v = new sdb_sview();
+  v->device = device;
+  const size_t n = 65536 * sizeof(float);
+  if (cudaMalloc(&v->d_psd, n) != cudaSuccess || cudaMalloc(&v->d_accum, n) != cudaSuccess ||
+      cudaMalloc(&v->d_count, n) != cudaSuccess) { g_err = "out of device memory"; delete v; return nullptr; }
+  cudaMemset(v->d_psd, 0, n); cudaMemset(v->d_accum, 0, n); cudaMemset(v->d_count, 0, n);
+  return v;
+}
+
+extern "C" void sdb_sview_destroy(sdb_sview_t *v)
+{
+  if (!v) return;
+  cudaSetDevice(v->device);
+  cudaFree(v->d_psd); cudaFree(v->d_accum); cudaFree(v->d_count); cudaFree(v->d_centers);
+  cudaFree(v->d_j0); cudaFree(v->d_nb); cudaFree(v->d_va); cudaFree(v->d_vc);
+  delete v;
+}
+
+extern "C" int sdb_sview_reset(sdb_sview_t *v)
+{
+  if (!v) return fail("null view");
+  CK(cudaSetDevice(v->device));
+  const size_t n = 65536 * sizeof(float);          // SpectrumView::reset, Scanner.cpp:287-293
+  CK(cudaMemset(v->d_psd, 0, n)); CK(cudaMemset(v->d_accum, 0, n)); CK(cudaMemset(v->d_count, 0, n));
+  return 0;
+}
+
+extern "C" int sdb_sview_set_range(sdb_sview_t *v, double fmin, double fmax, double fft_bandwidth, float rel_bw)
+{
+  if (!v) return fail("null view");
+  if (!(fmax > fmin) || !(fft_bandwidth > 0)) return fail("invalid frequency range");
+  v->freq_min = fmin; v->freq_max = fmax; v->freq_range = fmax - fmin;   // setRange, Scanner.cpp:41-54
+  unsigned n = (unsigned) (v->freq_range / 1000.0), sz = 1;               // SIGDIGGER_SCANNER_FREQ_RESOLUTION
+  while (sz < n) sz <<= 1;
+  if (sz > 65536) sz = 65536;
+  v->spectrum_size = sz;
+  v->fft_bandwidth = fft_bandwidth; v->rel_bw = rel_bw;
+  double mb = (double) sz * fft_bandwidth / v->freq_range + 4.0;
+  v->max_bins = mb > (double) sz ? (int) sz : (int) mb;
+  if (v->max_bins < 2) v->max_bins = 2;
+  v->hop_cap = 0;   // contribution buffers depend on max_bins: reallocate lazily
+  return sdb_sview_reset(v);
+}
+
+extern "C" uint32_t sdb_sview_size(const sdb_sview_t *v) { return v ? v->spectrum_size : 0; }
+extern "C" uint32_t sdb_sview_max_bins(const sdb_sview_t *v) { return v ? (uint32_t) v->max_bins : 0; }
+
+extern "C" int sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t psd_size, const double *centers,
+                                 size_t n_hops, int adjust_sides)
+{
+  if (!v || !psd_dev || !centers) return fail("null argument");
+  if (v->max_bins <= 0) return fail("set_range first");
+  CK(cudaSetDevice(v->device));
+  if (n_hops > v->hop_cap) {
+    cudaFree(v->d_centers); cudaFree(v->d_j0); cudaFree(v->d_nb); cudaFree(v->d_va); cudaFree(v->d_vc);
+    v->d_centers = nullptr; v->d_j0 = v->d_nb = nullptr; v->d_va = v->d_vc = nullptr;
+    CK(cudaMalloc(&v->d_centers, n_hops * sizeof(double)));
+    CK(cudaMalloc(&v->d_j0, n_hops * sizeof(int)));
+    CK(cudaMalloc(&v->d_nb, n_hops * sizeof(int)));
+    CK(cudaMalloc(&v->d_va, n_hops * (size_t) v->max_bins * sizeof(float)));
+    CK(cudaMalloc(&v->d_vc, n_hops * (size_t) v->max_bins * sizeof(float)));
+    v->hop_cap = n_hops;
+  }
+  CK(cudaMemcpy(v->d_centers, centers, n_hops * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemset(v->d_va, 0, n_hops * (size_t) v->max_bins * sizeof(float)));
+  CK(cudaMemset(v->d_vc, 0, n_hops * (size_t) v->max_bins * sizeof(float)));
+  CK(sdb_launch_sview_project(0, v->freq_min, v->freq_range, v->fft_bandwidth, v->rel_bw, v->spectrum_size, psd_dev,
+                              psd_size, v->d_centers, (int) n_hops, adjust_sides, v->d_j0, v->d_nb, v->d_va, v->d_vc,
+                              v->max_bins));
+  return 0;
+}
+
+extern "C" int sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc)
+{
+  if (!v) return fail("null view");
+  if (j0) *j0 = v->d_j0;
+  if (nb) *nb = v->d_nb;
+  if (va) *va = v->d_va;
+  if (vc) *vc = v->d_vc;
+  return 0;
+}
+
+extern "C" int sdb_sview_accumulate(sdb_sview_t *v, const int32_t *j0, const int32_t *nb, const float *va,
+                                    const float *vc, size_t n_hops)
+{
+  if (!v) return fail("null view");
+  CK(cudaSetDevice(v->device));
+  CK(sdb_launch_sview_accumulate(0, v->spectrum_size, j0, nb, va, vc, (int) n_hops, v->max_bins, v->d_psd, v->d_accum,
+                                 v->d_count));
+  return 0;
+}
+
+extern "C" int sdb_sview_read(sdb_sview_t *v, float *psd, float *accum, float *count, size_t cap)
+{
+  if (!v) return fail("null view");
+  if (cap < v->spectrum_size) return fail("destination too small");
+  CK(cudaSetDevice(v->device));
+  CK(cudaDeviceSynchronize());
+  const size_t n = v->spectrum_size * sizeof(float);
+  if (psd) CK(cudaMemcpy(psd, v->d_psd, n, cudaMemcpyDeviceToHost));
+  if (accum) CK(cudaMemcpy(accum, v->d_accum, n, cudaMemcpyDeviceToHost));
+  if (count) CK(cudaMemcpy(count, v->d_count, n, cudaMemcpyDeviceToHost));
+  return 0;
 }

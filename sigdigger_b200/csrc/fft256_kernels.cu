@@ -13,6 +13,7 @@
 // agree with the oracle to SPEC.md section T.  Replaces the forward FFTs of su_specttuner
 // (Tasks/LPFTask.cpp:83-87) and of the PSD (Suscan/Messages/PSDMessage.cpp:26-39).
 #include "sdb_internal.h"
+#include "sdb_math.h"
 
 #define C1 0.92387953251128675613f   // cos(pi/8)
 #define S1 0.38268343236508977173f   // sin(pi/8)
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
       if (MODE == 0) {
         float pw = (v[q].x * v[q].x + v[q].y * v[q].y) * p.inv_n;
         float *__restrict__ psd = p.psd + (size_t) win * 65536;
-        if (p.shift_db) { pw = 10.0f * log10f(pw + 1e-8f); psd[(k + 32768) & 65535] = pw; }
+        if (p.shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); psd[(k + 32768) & 65535] = pw; }
         else psd[k] = pw;
       } else {
         const int m = __ldg(p.binmap + k);

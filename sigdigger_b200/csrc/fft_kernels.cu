@@ -17,6 +17,7 @@
 // message payload (Suscan/Messages/PSDMessage.cpp:26-39).  Compiled WITH fma contraction: results are
 // compared with the oracle to the float tolerance of SPEC.md section T, not bit-exactly.
 #include "sdb_internal.h"
+#include "sdb_math.h"
 #include <math_constants.h>
 
 static __device__ __forceinline__ float2 cmul(float2 a, float2 b)
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(1024) k_pass_b(const PassBK p)
       float pw = (X.x * X.x + X.y * X.y) * p.a.inv_n;
       if (p.a.shift_db) {
         // Suscan/Messages/PSDMessage.cpp:32-38: swap halves, SU_POWER_DB
-        pw = 10.0f * log10f(pw + 1e-8f);
+        pw = 10.0f * d_log10f(pw + 1e-8f);
         psd[(k + half) & (N - 1)] = pw;
       } else {
         psd[k] = pw;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(1024) k_small_psd(int N, int logN, const float
   for (int k = threadIdx.x; k < N; k += blockDim.x) {
     const float2 X = sm[k];
     float pw = (X.x * X.x + X.y * X.y) * inv_n;
-    if (shift_db) { pw = 10.0f * log10f(pw + 1e-8f); out[(k + half) & (N - 1)] = pw; }
+    if (shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); out[(k + half) & (N - 1)] = pw; }
     else out[k] = pw;
   }
 }
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(1024) k_chan_ifft(const SdbChannelDev *__restr
       float2 o = make_float2(al * cu.x + be * pv.x, al * cu.y + be * pv.y);
       if (ch.precise) {
         float sn, cs_;
-        sincosf(phase[i], &sn, &cs_);
+        d_sincosf(phase[i], &sn, &cs_);            // SPEC M.1, as the per-sample NCQO read does
         o = cmulc(o, make_float2(cs_, sn));
       }
       out[(size_t) j * hs + i] = o;

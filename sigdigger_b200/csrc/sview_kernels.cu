@@ -1,0 +1,183 @@
+// sview_kernels.cu -- panoramic-scanner PSD stitcher (SpectrumView) on the GPU.
+//
+// Reference arithmetic (fully present in the reference, so followed value by value):
+//   SpectrumView::feedLinearMode     Panoramic/Scanner.cpp:118-185
+//   SpectrumView::feedHistogramMode  Panoramic/Scanner.cpp:187-237
+//   SpectrumView::interpolate        Panoramic/Scanner.cpp:56-116   (count > 5 -> reset to 1, gap filling)
+//   constants                        include/Scanner.h:26-32
+//
+// The reference feeds one hop at a time and calls interpolate() after each.  The per-bin state
+// (psdAccum, psdCount) only depends on that bin's own contributions in hop order, so the work splits in:
+//   project    : per hop, the box average of the source bins that fall in each destination bin (the
+//                O(psd_size) part; hops are independent -> shards over GPUs);
+//   accumulate : per destination bin, apply the contributions in hop order with the forgetting rule;
+//   fill       : the final gap interpolation.
+// Between project and accumulate the (tiny) contribution lists are what crosses NVLink (NCCL gather).
+// Compiled with -fmad=false; double arithmetic for frequencies / positions exactly as in the C++.
+#include "sdb_internal.h"
+
+struct SviewGeom {
+  double freq_min, freq_range, fft_bandwidth;
+  float  rel_bw;
+  unsigned spectrum_size;
+};
+
+// one CTA per hop; thread t handles destination bins j0 + t, j0 + t + blockDim, ...
+__global__ void k_sview_project(SviewGeom g, const float *__restrict__ psd, size_t psd_size,
+                                const double *__restrict__ centers, int n_hops, int adjust_sides,
+                                int *__restrict__ j0_out, int *__restrict__ nb_out,
+                                float *__restrict__ va, float *__restrict__ vc, int max_bins)
+{
+  const int h = blockIdx.x;
+  if (h >= n_hops) return;
+  const double center = centers[h];
+  const double fmin = center - g.fft_bandwidth / 2, fmax = center + g.fft_bandwidth / 2;
+  const float *__restrict__ src = psd + (size_t) h * psd_size;
+  float *__restrict__ oa = va + (size_t) h * max_bins, *__restrict__ oc = vc + (size_t) h * max_bins;
+  const double fft_count_rel = (fmax - fmin) / g.freq_range;
+
+  if (fft_count_rel * g.spectrum_size >= 2) {
+    // ---- linear mode (Scanner.cpp:118-185)
+    const double inp_bw = fmax - fmin;
+    const int skip = adjust_sides ? (int) (.5f * (1 - g.rel_bw) * psd_size) : 0;
+    const double freq_skip = (double) skip / psd_size * inp_bw;
+    const double bw = inp_bw - 2 * freq_skip;
+    const double fft_count = g.freq_range / bw;
+    const double bins = g.spectrum_size / fft_count;
+    const double src_bin_w = inp_bw / psd_size;
+    const double dst_bin_w = g.freq_range / g.spectrum_size;
+    const double delta = dst_bin_w / src_bin_w;
+    double pos = (freq_skip + fmin - g.freq_min) / g.freq_range;
+    pos *= g.spectrum_size;
+    const int j0 = pos > 0 ? (int) pos : 0;
+    const int k = pos + bins < g.spectrum_size ? (int) (pos + bins) : (int) g.spectrum_size;
+    int nb = k - j0;
+    if (nb < 0) nb = 0;
+    if (nb > max_bins) nb = max_bins;
+    if (threadIdx.x == 0) { j0_out[h] = j0; nb_out[h] = nb; }
+    for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+      const int j = j0 + t;
+      const double freq_j = g.freq_min + dst_bin_w * j;
+      const double src_bin = (freq_j - fmin) / src_bin_w;
+      int start_bin = (int) src_bin;
+      int end_bin = (int) (src_bin + delta);
+      start_bin = start_bin < 0 ? 0 : (start_bin > (int) psd_size - 1 ? (int) psd_size - 1 : start_bin);
+      end_bin = end_bin < start_bin + 1 ? start_bin + 1 : (end_bin > (int) psd_size ? (int) psd_size : end_bin);
+      float acc = 0, cnt = 0;
+      for (int i = start_bin; i < end_bin; ++i) { acc += src[i]; cnt += 1; }
+      oa[t] = acc / cnt;      // cnt > 0 always (end_bin > start_bin)
+      oc[t] = 1.0f;
+    }
+  } else {
+    // ---- histogram mode (Scanner.cpp:187-237): the hop is narrower than two destination bins
+    double rel_bw = (fmax - fmin) / g.freq_range;
+    double f_start = (fmin - g.freq_min) / g.freq_range;
+    double f_end = (fmax - g.freq_min) / g.freq_range;
+    f_start *= g.spectrum_size; f_end *= g.spectrum_size; rel_bw *= g.spectrum_size;
+    if (threadIdx.x == 0) {
+      unsigned j = f_start < 0 ? 0u : (unsigned) f_start;
+      if (j > g.spectrum_size - 1) j = g.spectrum_size - 1;
+      const float inv = (float) (1. / psd_size);
+      float accum = 0;
+      for (size_t i = 0; i < psd_size; ++i) accum += src[i];
+      accum *= inv;
+      j0_out[h] = (int) j;
+      if (floor(f_start) != floor(f_end)) {
+        const float t = (float) ((f_start - floor(f_start)) / rel_bw);
+        oc[0] = 1 - t; oa[0] = (1 - t) * accum;
+        if (j + 1 < g.spectrum_size) { oc[1] = t; oa[1] = t * accum; nb_out[h] = 2; }
+        else nb_out[h] = 1;
+      } else {
+        oc[0] = 1; oa[0] = accum; nb_out[h] = 1;
+      }
+    }
+  }
+}
+
+// one thread per destination bin: contributions in hop order + the count > 5 forgetting rule that
+// interpolate() applies after every feed (Scanner.cpp:77-81).
+__global__ void k_sview_accumulate(unsigned spectrum_size, const int *__restrict__ j0, const int *__restrict__ nb,
+                                   const float *__restrict__ va, const float *__restrict__ vc, int n_hops,
+                                   int max_bins, float *__restrict__ psd, float *__restrict__ accum,
+                                   float *__restrict__ count)
+{
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= spectrum_size) return;
+  float a = accum[j], c = count[j], p = psd[j];
+  float cl = j > 0 ? count[j - 1] : 1.0f;     // left neighbour's count: only its emptiness matters
+  for (int h = 0; h < n_hops; ++h) {
+    const int t = (int) j - j0[h], n = nb[h];
+    if (t >= 0 && t < n) {
+      a += va[(size_t) h * max_bins + t];
+      c += vc[(size_t) h * max_bins + t];
+    }
+    if (t - 1 >= 0 && t - 1 < n) cl += vc[(size_t) h * max_bins + t - 1];
+    // interpolate() runs after every feed: a non-empty bin gets psd = accum / count; the count > 5
+    // forgetting rule is applied only when the bin does not close a gap (Scanner.cpp:70-90: the branch
+    // that ends a run of empty bins computes `right` without the reset).
+    if (c > .5f) {
+      p = a / c;
+      const bool closes_gap = j > 0 && cl <= .5f;
+      if (!closes_gap && c > 5.0f) { c = 1.0f; a = p * 1.0f; }
+    }
+  }
+  accum[j] = a; count[j] = c; psd[j] = p;
+}
+
+// final gap filling: exactly interpolate()'s treatment of runs of empty bins (Scanner.cpp:56-116).
+// A single thread walks the array (65536 bins, once per sweep): the loop carries `left` from the
+// possibly just-filled previous bin, as the reference does.
+__global__ void k_sview_fill(unsigned spectrum_size, float *__restrict__ psd, const float *__restrict__ count)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned i, j, cnt = 1, zero_pos = 0;
+  bool first = true, in_gap = false;
+  float left = -200.0f, right, t;
+  for (i = 0; i < spectrum_size; ++i) {
+    const bool empty = count[i] <= .5f;
+    if (!in_gap) {
+      if (empty) {
+        in_gap = true; zero_pos = i; cnt = 1;
+        first = i == 0;
+        if (!first) left = psd[i - 1];
+      }
+    } else if (empty) {
+      ++cnt;
+    } else {
+      in_gap = false;
+      right = psd[i];
+      if (first) {
+        for (j = 0; j < cnt; ++j) psd[j + zero_pos] = right;
+      } else {
+        for (j = 0; j < cnt; ++j) {
+          t = (float) (j + .5f) / cnt;
+          psd[j + zero_pos] = (1 - t) * left + t * right;
+        }
+      }
+    }
+  }
+  if (in_gap)
+    for (j = 0; j < cnt; ++j) psd[j + zero_pos] = left;
+}
+
+cudaError_t sdb_launch_sview_project(cudaStream_t s, double freq_min, double freq_range, double fft_bandwidth,
+                                     float rel_bw, unsigned spectrum_size, const float *psd, size_t psd_size,
+                                     const double *centers_dev, int n_hops, int adjust_sides, int *j0, int *nb,
+                                     float *va, float *vc, int max_bins)
+{
+  SviewGeom g{ freq_min, freq_range, fft_bandwidth, rel_bw, spectrum_size };
+  if (n_hops <= 0) return cudaSuccess;
+  k_sview_project<<<n_hops, 256, 0, s>>>(g, psd, psd_size, centers_dev, n_hops, adjust_sides, j0, nb, va, vc, max_bins);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_sview_accumulate(cudaStream_t s, unsigned spectrum_size, const int *j0, const int *nb,
+                                        const float *va, const float *vc, int n_hops, int max_bins, float *psd,
+                                        float *accum, float *count)
+{
+  if (n_hops > 0)
+    k_sview_accumulate<<<(spectrum_size + 255) / 256, 256, 0, s>>>(spectrum_size, j0, nb, va, vc, n_hops, max_bins,
+                                                                   psd, accum, count);
+  k_sview_fill<<<1, 32, 0, s>>>(spectrum_size, psd, count);
+  return cudaGetLastError();
+}

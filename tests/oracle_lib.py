@@ -178,6 +178,10 @@ def lib():
         L.sdo_window_fill.argtypes = [c_float_p, C.c_uint, C.c_int]
         L.sdo_fft_plan_init.argtypes = [C.c_void_p, C.c_uint]
         L.sdo_fft_exec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sdo_spec_plan_init.argtypes = [C.c_void_p, C.c_uint, C.c_int]
+        L.sdo_spec_plan_free.argtypes = [C.c_void_p]
+        L.sdo_spec_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sdo_psd_frame_spec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sdo_psd_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sdo_psd_shift_db.argtypes = [C.c_void_p, C.c_uint]
         L.sdo_averager_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_float]
@@ -268,10 +272,42 @@ def window(n, kind):
     return w
 
 
-def psd_frames(x, n, kind):
-    """PSD of consecutive non-overlapping n-sample frames of x -> [frames, n] float32."""
+class SpecPlan(C.Structure):
+    _fields_ = [("N", C.c_uint), ("N1", C.c_uint), ("N2", C.c_uint), ("four", C.c_int), ("kind", C.c_int),
+                ("tw_a", C.c_void_p), ("tw_b", C.c_void_p), ("tw_n", C.c_void_p), ("scr", C.c_void_p),
+                ("buf", C.c_void_p), ("tmp", C.c_void_p)]
+
+
+def spec_fft(x, four=False):
+    """Forward SPEC transform (F.2 / F.3 / F.4 by size) of complex64 x."""
     L = lib()
     x = _c64(x)
+    p = SpecPlan()
+    assert L.sdo_spec_plan_init(C.byref(p), len(x), int(four)) == 0
+    out = np.empty_like(x)
+    L.sdo_spec_forward(C.byref(p), ptr(x), None, ptr(out))
+    L.sdo_spec_plan_free(C.byref(p))
+    return out
+
+
+def psd_frames(x, n, kind, spec=True):
+    """PSD of consecutive non-overlapping n-sample frames of x -> [frames, n] float32.
+    spec=True uses the SPEC transform (bit-identical to the CUDA path); False the radix-2 cross-check."""
+    L = lib()
+    x = _c64(x)
+    if spec:
+        p = SpecPlan()
+        assert L.sdo_spec_plan_init(C.byref(p), n, 0) == 0
+        w = window(n, kind)
+        none = (kind == "none" or kind == 0)
+        nf = len(x) // n
+        out = np.empty((nf, n), np.float32)
+        scratch = np.empty(n, np.complex64)
+        for f in range(nf):
+            L.sdo_psd_frame_spec(C.byref(p), None if none else ptr(w), ptr(x[f * n:(f + 1) * n]), ptr(out[f]),
+                                 ptr(scratch))
+        L.sdo_spec_plan_free(C.byref(p))
+        return out
     p = FftPlan()
     assert L.sdo_fft_plan_init(C.byref(p), n) == 0
     w = window(n, kind)

@@ -1,0 +1,108 @@
+"""-m gpu: panoramic scanner path (BASELINE.json configs[4]): per-hop 65536-pt PSD in the PSDMessage layout
+(fft-shift + dB) -> SpectrumView stitch.  The CUDA project + accumulate must reproduce the reference's
+feed() / interpolate() sequence (Panoramic/Scanner.cpp:239-256) value by value."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _hops(n_hops, N, fs, seed):
+    rng = np.random.default_rng(seed)
+    x = (0.02 * (rng.standard_normal((n_hops, N)) + 1j * rng.standard_normal((n_hops, N)))).astype(np.complex64)
+    t = np.arange(N)
+    for h in range(n_hops):
+        for k in range(3):
+            f = rng.uniform(-0.2, 0.2)
+            x[h] += (rng.uniform(0.05, 0.4) * np.exp(2j * np.pi * f * t)).astype(np.complex64)
+    return x
+
+
+def _oracle_view(oracle, psd_db, centers, fmin, fmax, fftbw, rel_bw):
+    L = oracle.lib()
+    v = oracle.SpectrumView()
+    assert L.sdo_sview_init(C.byref(v)) == 0
+    L.sdo_sview_set_range(C.byref(v), fmin, fmax)
+    v.fft_bandwidth = fftbw
+    v.fft_rel_bw = rel_bw
+    for h, c in enumerate(centers):
+        L.sdo_sview_feed(C.byref(v), oracle.ptr(psd_db[h]), None, psd_db.shape[1], float(c), 1)
+    n = v.spectrum_size
+    out = tuple(np.ctypeslib.as_array(p, shape=(65536,))[:n].copy() for p in (v.psd, v.psd_accum, v.psd_count))
+    L.sdo_sview_free(C.byref(v))
+    return out
+
+
+@pytest.mark.parametrize("N,n_hops,revisit", [(65536, 24, True), (8192, 40, True), (4096, 16, False)])
+def test_panoramic_sweep_matches_reference_sequence(sdb, oracle, N, n_hops, revisit):
+    import torch
+    fs = 100e6
+    fftbw = fs
+    rel_bw = 0.5
+    fmin, fmax = 1.0e9, 1.0e9 + n_hops * fs * rel_bw * 0.9
+    centers = fmin + fs * rel_bw * (0.4 + 0.9 * np.arange(n_hops))
+    order = list(range(n_hops))
+    if revisit:                       # exercise the count > 5 forgetting rule and out-of-order hops
+        order += order[3:9] * 6 + order[::-1][:5]
+    x = _hops(n_hops, N, fs, seed=N % 13)
+    xs = np.stack([x[h] for h in order])
+    cs = centers[order]
+    # oracle: SPEC PSD + GUI shift/dB, then the literal feed sequence
+    psd_db = np.stack([oracle.psd_frames(xs[h], N, "blackmann_harris")[0] for h in range(len(order))])
+    for h in range(len(order)):
+        oracle.lib().sdo_psd_shift_db(oracle.ptr(psd_db[h]), N)
+    ref = _oracle_view(oracle, psd_db, cs, fmin, fmax, fftbw, rel_bw)
+    # CUDA: hop PSDs with the fused shift/dB epilogue, then project + accumulate
+    e = sdb.Engine(n_streams=len(order), psd_size=N, psd_window="blackmann_harris", max_feed=N,
+                   flags=sdb.FLAG_PSD_SHIFT_DB)
+    e.commit()
+    e.feed(xs)
+    got_db = e.read_psd()[:, 0, :]
+    assert np.array_equal(got_db.view(np.uint32), psd_db.view(np.uint32)), "hop PSDs (dB) not bit-identical"
+    v = sdb.SpectrumView(fmin, fmax, fftbw, rel_bw)
+    v.project(e.psd_device_ptr, N, cs)
+    v.accumulate()
+    psd, acc, cnt = v.read()
+    assert len(psd) == len(ref[0])
+    assert np.array_equal(cnt, ref[2])
+    assert np.array_equal(acc.view(np.uint32), ref[1].view(np.uint32))
+    assert np.array_equal(psd.view(np.uint32), ref[0].view(np.uint32))
+    # split in two accumulate() calls == one (what the multi-GPU gather does)
+    v2 = sdb.SpectrumView(fmin, fmax, fftbw, rel_bw)
+    v2.project(e.psd_device_ptr, N, cs)
+    j0, nb, va, vc = v2.contrib_ptrs()
+    half = len(order) // 2
+    mb = v2.max_bins
+    v2.accumulate(j0, nb, va, vc, half)
+    v2.accumulate(j0 + 4 * half, nb + 4 * half, va + 4 * half * mb, vc + 4 * half * mb, len(order) - half)
+    psd2, acc2, cnt2 = v2.read()
+    assert np.array_equal(acc2.view(np.uint32), acc.view(np.uint32)) and np.array_equal(cnt2, cnt)
+    assert np.array_equal(psd2.view(np.uint32), psd.view(np.uint32))
+    del torch
+
+
+def test_panoramic_histogram_mode(sdb, oracle):
+    """hop narrower than two destination bins -> feedHistogramMode (Scanner.cpp:187-237)"""
+    N, n_hops = 4096, 30
+    fftbw = 1e6
+    fmin, fmax = 100e6, 100e6 + 65536 * 1000.0 * 4          # 4 kHz bins, hops of 1 MHz * ... wide range
+    fmax = fmin + 65536 * 1.2e6                               # destination bin 1.2 MHz > hop width
+    rng = np.random.default_rng(3)
+    cs = fmin + rng.uniform(0.01, 0.99, n_hops) * (fmax - fmin)
+    x = _hops(n_hops, N, fftbw, seed=5)
+    psd_db = np.stack([oracle.psd_frames(x[h], N, "hann")[0] for h in range(n_hops)])
+    for h in range(n_hops):
+        oracle.lib().sdo_psd_shift_db(oracle.ptr(psd_db[h]), N)
+    ref = _oracle_view(oracle, psd_db, cs, fmin, fmax, fftbw, 0.5)
+    e = sdb.Engine(n_streams=n_hops, psd_size=N, psd_window="hann", max_feed=N, flags=sdb.FLAG_PSD_SHIFT_DB)
+    e.commit()
+    e.feed(x)
+    v = sdb.SpectrumView(fmin, fmax, fftbw, 0.5)
+    v.project(e.psd_device_ptr, N, cs)
+    v.accumulate()
+    psd, acc, cnt = v.read()
+    assert np.array_equal(cnt.view(np.uint32), ref[2].view(np.uint32))
+    assert np.array_equal(acc.view(np.uint32), ref[1].view(np.uint32))
+    assert np.array_equal(psd.view(np.uint32), ref[0].view(np.uint32))

@@ -50,6 +50,22 @@ def test_fft_vs_numpy(oracle, n):
     assert np.abs(back - z).max() < 5e-6
 
 
+@pytest.mark.parametrize("n,four", [(16, False), (64, True), (256, False), (2048, False), (4096, True),
+                                    (8192, False), (32768, False), (65536, False), (1 << 17, False)])
+def test_spec_fft_vs_radix2_and_float64(oracle, n, four):
+    """The SPEC dataflows (F.2 Stockham, F.3 four-step, F.4 256x256 fft16) against the independent
+    radix-2 transform and numpy float64: same transform to float32 accuracy."""
+    rng = np.random.default_rng(n + four)
+    z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    S = oracle.spec_fft(z, four=four)
+    R2 = oracle.fft(z)
+    T = np.fft.fft(z.astype(np.complex128))
+    rms = np.sqrt(np.mean(np.abs(T) ** 2))
+    assert np.abs(S - T).max() <= 3e-6 * rms
+    assert np.abs(S - R2).max() <= 4e-6 * rms
+    assert np.sqrt(np.mean(np.abs(S - T) ** 2)) <= 3e-7 * rms
+
+
 def test_windows_vs_scipy(oracle):
     for k, nm in [("hamming", "hamming"), ("hann", "hann"), ("blackmann_harris", "blackmanharris")]:
         assert np.abs(oracle.window(1024, k) - signal.get_window(nm, 1024, fftbins=False)).max() < 1e-7
