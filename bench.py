@@ -241,6 +241,7 @@ def run_cuda(args):
         a.record(es)
         for _ in range(steps):
             fn()
+        e.join()                 # the end event must also cover the inspector stream
         b.record(es)
         e.sync()
         ms = a.elapsed_time(b)
@@ -272,7 +273,7 @@ def run_cuda(args):
     fam = {f: e.kernel_time(f) for f in ("fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft", "inspector")}
     e.timing(False)
     wps, frames = H, H // 2
-    chunk = max(1, (32 << 20) // (N_FFT * 8))
+    chunk = max(1, (int(os.environ.get("SDB_SCRATCH_MB", "64")) << 20) // (N_FFT * 8))
     nb = sum(2 * (e.channel_info(h).width // 2) for h in hs)
     alg = {"fft_cols": min(chunk, S * wps) * N_FFT * 8.0,
            "fft_rows_psd": min(chunk, S * frames) * N_FFT * 4.0,
@@ -339,6 +340,7 @@ def run_cuda(args):
         a.record(es1)
         for _ in range(5):
             e1.feed_device_ptr(x1.data_ptr(), x1.stride(0), n)
+        e1.join()
         b.record(es1)
         e1.sync()
         single = n * 5 / (a.elapsed_time(b) * 1e-3) / 1e6
@@ -375,12 +377,12 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
     ap.add_argument("--streams", type=int, default=0)
-    ap.add_argument("--hops", type=int, default=32)
+    ap.add_argument("--hops", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
     args = ap.parse_args()
     if args.streams == 0:
-        args.streams = 256 if args.workload == "cfg2" else 64
+        args.streams = 1024 if args.workload == "cfg2" else 128
     if args.impl == "reference":
         run_reference(args)
     else:

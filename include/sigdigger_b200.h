@@ -118,6 +118,10 @@ int sdb_engine_commit(sdb_engine_t *e);
 int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *x, size_t stream_stride, size_t n);
 int sdb_engine_feed_host(sdb_engine_t *e, const sdb_complex *x, size_t stream_stride, size_t n);
 int sdb_engine_sync(sdb_engine_t *e);
+/* The inspector kernels run on a second CUDA stream so that the next feed's FFT kernels overlap them.
+ * sdb_engine_join() makes work queued afterwards on the engine stream wait for all of them (call it
+ * before recording a CUDA event that must cover whole feeds); sdb_engine_sync() joins and blocks. */
+int sdb_engine_join(sdb_engine_t *e);
 
 /* Results of the last feed.  PSD = payload of suscan_analyzer_psd_msg (psd_size, psd_data;
  * Suscan/Messages/PSDMessage.cpp:26-39): [stream][frame][psd_size] float32, linear power, DC at 0

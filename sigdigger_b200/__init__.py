@@ -59,6 +59,7 @@ _PROTOS = {
     "sdb_engine_feed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sdb_engine_feed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sdb_engine_sync": (C.c_int, [C.c_void_p]),
+    "sdb_engine_join": (C.c_int, [C.c_void_p]),
     "sdb_engine_psd_frames": (C.c_size_t, [C.c_void_p]),
     "sdb_engine_psd_device": (C.c_void_p, [C.c_void_p]),
     "sdb_engine_read_psd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -213,6 +214,9 @@ class Engine:
 
     def sync(self):
         _check(self._L.sdb_engine_sync(self._h))
+
+    def join(self):
+        _check(self._L.sdb_engine_join(self._h))
 
     def read_psd(self, out=None):
         f = self._L.sdb_engine_psd_frames(self._h)

@@ -78,7 +78,13 @@ struct sdb_engine {
   std::vector<Group> groups;
   float2 *d_tails = nullptr; size_t tail_stride = 0;
   float *d_lo_phase = nullptr;
-  float2 *d_chan = nullptr; size_t chan_stride = 0;
+  // channel streams are double-buffered: the (latency-bound, 1-CTA-per-32-chains) inspector kernel of feed i
+  // runs on its own stream while the FFT kernels of feed i+1 fill the other buffer
+  float2 *d_chanb[2] = { nullptr, nullptr }; size_t chan_stride = 0;
+  cudaStream_t insp_stream = nullptr;
+  cudaEvent_t ev_chan[2] = { nullptr, nullptr }, ev_insp[2] = { nullptr, nullptr };
+  bool ev_insp_valid[2] = { false, false };
+  unsigned feed_index = 0; int last_buf = 0;
   size_t last_hops = 0;
   // chains
   SdbChainCfg *d_cfg = nullptr; std::vector<SdbChainCfg> h_cfg;
@@ -110,18 +116,26 @@ struct sdb_engine {
     tw[n] = d;
     return d;
   }
-  void span_begin(int fam)
+  void span_begin(int fam, cudaStream_t on = nullptr)
   {
     if (!timing) return;
     TimedSpan s; s.family = fam;
     cudaEventCreate(&s.a); cudaEventCreate(&s.b);
-    cudaEventRecord(s.a, stream);
+    cudaEventRecord(s.a, on ? on : stream);
     spans.push_back(s);
   }
-  void span_end()
+  void span_end(cudaStream_t on = nullptr)
   {
     if (!timing) return;
-    cudaEventRecord(spans.back().b, stream);
+    cudaEventRecord(spans.back().b, on ? on : stream);
+  }
+  // make the main stream wait for everything queued on the inspector stream
+  cudaError_t join()
+  {
+    if (!insp_stream) return cudaSuccess;
+    const int b = last_buf;
+    if (ev_insp_valid[b]) return cudaStreamWaitEvent(stream, ev_insp[b], 0);
+    return cudaSuccess;
   }
   void collect_spans()
   {
@@ -166,8 +180,14 @@ extern "C" void sdb_engine_destroy(sdb_engine_t *e)
   if (!e) return;
   cudaSetDevice(e->prm.device);
   cudaStreamSynchronize(e->stream);
+  if (e->insp_stream) cudaStreamSynchronize(e->insp_stream);
   e->collect_spans();
   for (void *p : e->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_chan[i]) cudaEventDestroy(e->ev_chan[i]);
+    if (e->ev_insp[i]) cudaEventDestroy(e->ev_insp[i]);
+  }
+  if (e->insp_stream) cudaStreamDestroy(e->insp_stream);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -352,7 +372,9 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
   {
     unsigned big = std::max(Np > 4096 ? Np : 0u, K > 0 ? W : 0u);
     if (big) {
-      size_t cw = (32u << 20) / ((size_t) big * sizeof(float2));
+      size_t scratch_mb = 64;   // measured: 32 MB 39.5, 64 MB 41.7, 96 MB 43.2 GS/s (cfg2); stays inside the 126 MB L2
+      if (const char *env = getenv("SDB_SCRATCH_MB")) { long v = atol(env); if (v >= 1 && v <= 4096) scratch_mb = (size_t) v; }
+      size_t cw = (scratch_mb << 20) / ((size_t) big * sizeof(float2));
       if (cw < 1) cw = 1;
       e->chunk_windows = (int) cw;
       e->d_scratch = e->dalloc<float2>((size_t) e->chunk_windows * big);
@@ -413,10 +435,17 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     }
     e->chan_stride = out_off; e->tail_stride = tail_off;
     e->d_chans = e->dalloc<SdbChannelDev>(K);
-    e->d_chan = e->dalloc<float2>((size_t) S * out_off);
+    e->d_chanb[0] = e->dalloc<float2>((size_t) S * out_off);
+    e->d_chanb[1] = e->dalloc<float2>((size_t) S * out_off);
     e->d_tails = e->dalloc<float2>((size_t) S * tail_off);
     e->d_lo_phase = e->dalloc<float>((size_t) S * K);
-    if (!e->d_chans || !e->d_chan || !e->d_tails || !e->d_lo_phase) return fail("out of device memory (channels)");
+    if (!e->d_chans || !e->d_chanb[0] || !e->d_chanb[1] || !e->d_tails || !e->d_lo_phase)
+      return fail("out of device memory (channels)");
+    CK(cudaStreamCreateWithFlags(&e->insp_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&e->ev_chan[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_insp[i], cudaEventDisableTiming));
+    }
     CK(cudaMemcpy(e->d_chans, e->h_chans.data(), K * sizeof(SdbChannelDev), cudaMemcpyHostToDevice));
     CK(cudaMemset(e->d_tails, 0, (size_t) S * tail_off * sizeof(float2)));
     CK(cudaMemset(e->d_lo_phase, 0, (size_t) S * K * sizeof(float)));
@@ -543,21 +572,31 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
         else      CK(sdb_launch_pass_b_chan(ctx, e->fs_st, b));
         e->span_end();
       }
+      const int b = (int) (e->feed_index & 1u);
+      e->last_buf = b;
+      // buffer b was last read by the inspector launch of feed i-2
+      if (e->ev_insp_valid[b]) CK(cudaStreamWaitEvent(e->stream, e->ev_insp[b], 0));
       e->span_begin(FAM_CHAN_IFFT);
       for (auto &g : e->groups)
         CK(sdb_launch_chan_ifft_group(ctx, e->d_chans, g.d_ids, g.len, g.size, K, (int) S, e->d_cspec,
-                                      e->n_bins, wps, e->d_tails, e->tail_stride, e->d_lo_phase, e->d_chan,
+                                      e->n_bins, wps, e->d_tails, e->tail_stride, e->d_lo_phase, e->d_chanb[b],
                                       e->chan_stride));
       e->span_end();
-      e->span_begin(FAM_INSPECTOR);
-      CK(sdb_launch_inspectors_n(ctx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
-                                 e->d_chans, e->d_chan, e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
+      CK(cudaEventRecord(e->ev_chan[b], e->stream));
+      CK(cudaStreamWaitEvent(e->insp_stream, e->ev_chan[b], 0));
+      SdbLaunchCtx ictx{ e->insp_stream, &e->launches };
+      e->span_begin(FAM_INSPECTOR, e->insp_stream);
+      CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
+                                 e->d_chans, e->d_chanb[b], e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
                                  e->d_counts, e->sym_cap, e->chains_fresh ? 1 : 0));
       e->chains_fresh = false;
-      e->span_end();
+      e->span_end(e->insp_stream);
+      CK(cudaEventRecord(e->ev_insp[b], e->insp_stream));
+      e->ev_insp_valid[b] = true;
     } else {
-      CK(cudaMemsetAsync(e->d_counts, 0, (size_t) S * K * sizeof(uint32_t), e->stream));
+      CK(cudaMemsetAsync(e->d_counts, 0, (size_t) S * K * sizeof(uint32_t), e->insp_stream));
     }
+    ++e->feed_index;
     // keep the last half window of every stream as history for the next feed
     CK(cudaMemcpy2DAsync(e->d_hist, (W / 2) * sizeof(float2), x + (n - W / 2), stride * sizeof(float2),
                          (W / 2) * sizeof(float2), S, cudaMemcpyDeviceToDevice, e->stream));
@@ -586,8 +625,20 @@ extern "C" int sdb_engine_sync(sdb_engine_t *e)
 {
   if (!e) return fail("null engine");
   CK(cudaSetDevice(e->prm.device));
+  CK(e->join());
   CK(cudaStreamSynchronize(e->stream));
   e->collect_spans();
+  return 0;
+}
+
+// Queue a dependency: work submitted to the engine stream after this call starts only once the
+// inspector kernels of all previous feeds have finished (they run on a second stream so that the
+// next feed's FFT kernels overlap them).  Use before recording an event that should cover a feed.
+extern "C" int sdb_engine_join(sdb_engine_t *e)
+{
+  if (!e) return fail("null engine");
+  CK(cudaSetDevice(e->prm.device));
+  CK(e->join());
   return 0;
 }
 
@@ -614,7 +665,7 @@ extern "C" long sdb_engine_read_channel(sdb_engine_t *e, uint32_t stream, int ha
   size_t n = e->last_hops * (size_t) d.halfsz;
   if (n > cap) n = cap;
   CK(cudaSetDevice(e->prm.device));
-  CK(cudaMemcpyAsync(dst, e->d_chan + (size_t) stream * e->chan_stride + d.out_off, n * sizeof(float2),
+  CK(cudaMemcpyAsync(dst, e->d_chanb[e->last_buf] + (size_t) stream * e->chan_stride + d.out_off, n * sizeof(float2),
                      cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return (long) n;
@@ -630,6 +681,7 @@ extern "C" long sdb_engine_read_symbols(sdb_engine_t *e, uint32_t stream, int ha
   const size_t chain = (size_t) stream * K + handle;
   uint32_t cnt = 0;
   CK(cudaSetDevice(e->prm.device));
+  CK(e->join());
   CK(cudaMemcpyAsync(&cnt, e->d_counts + chain, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   size_t n = cnt;
@@ -647,6 +699,7 @@ extern "C" int sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sd
   const size_t chains = (size_t) e->prm.n_streams * e->channels.size();
   if (chains == 0) return 0;
   CK(cudaSetDevice(e->prm.device));
+  CK(e->join());
   CK(cudaMemcpyAsync(counts, e->d_counts, chains * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
   const size_t w = std::min(cap, e->sym_cap);
   if (soft) CK(cudaMemcpy2DAsync(soft, cap * sizeof(float2), e->d_soft, e->sym_cap * sizeof(float2),
