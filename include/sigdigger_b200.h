@@ -140,6 +140,13 @@ long         sdb_engine_read_symbols(sdb_engine_t *e, uint32_t stream, int handl
 /* all streams, all channels at once: counts[S*K], soft/hard laid out [S][K][cap] */
 int          sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft,
                                          uint8_t *hard, size_t cap);
+/* Asynchronous reads: queued on the engine's D2H stream behind the kernels that produce the data, so the
+ * next feed can be submitted at once (H2D of feed i+1, kernels of feed i and D2H of feed i-1 overlap;
+ * results are double-buffered by feed parity).  Destinations should be pinned host memory and stay valid
+ * until sdb_engine_sync(). */
+int          sdb_engine_read_psd_async(sdb_engine_t *e, float *dst, size_t cap_floats);
+int          sdb_engine_read_all_symbols_async(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft,
+                                               uint8_t *hard, size_t cap);
 /* device-side views for zero-copy consumers / benchmarks */
 const uint32_t *sdb_engine_symbol_counts_device(const sdb_engine_t *e);
 size_t          sdb_engine_symbol_capacity(const sdb_engine_t *e);
@@ -180,6 +187,87 @@ int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batc
 int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
 
 /* ------------------------------------------------------------------------------------------------
+ * suscan-style asynchronous analyzer: a worker thread reads the source, runs the
+ * engine block by block and posts messages; requests are answered in order with messages carrying req_id.
+ * Field names follow the structs the reference dereferences (Suscan/Messages/PSDMessage.cpp:30-112,
+ * include/Suscan/Messages/SamplesMessage.h:33-59, Suscan/Messages/InspectorMessage.cpp:28-252,
+ * Suscan/Messages/StatusMessage.cpp:33-45, include/Suscan/Analyzer.h:113-254).
+ * ---------------------------------------------------------------------------------------------- */
+#include <sys/time.h>
+
+enum {   /* SUSCAN_ANALYZER_MESSAGE_TYPE_* as dispatched at Suscan/Analyzer.cpp:75-98 */
+  SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INFO = 0, SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_MESSAGE_TYPE_CHANNEL,
+  SDB_ANALYZER_MESSAGE_TYPE_EOS, SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR, SDB_ANALYZER_MESSAGE_TYPE_INTERNAL,
+  SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR, SDB_ANALYZER_MESSAGE_TYPE_PSD,
+  SDB_ANALYZER_MESSAGE_TYPE_PARAMS
+};
+#define SDB_WORKER_MSG_TYPE_HALT   0xffffffffu      /* SUSCAN_WORKER_MSG_TYPE_HALT */
+#define SDB_ANALYZER_INIT_FAILURE  (-1)             /* SUSCAN_ANALYZER_INIT_FAILURE, App/Application.cpp:529 */
+enum {   /* SUSCAN_ANALYZER_INSPECTOR_MSGKIND_* (Suscan/AnalyzerRequestTracker.cpp:138-177) */
+  SDB_INSPECTOR_MSGKIND_OPEN = 0, SDB_INSPECTOR_MSGKIND_SET_ID, SDB_INSPECTOR_MSGKIND_GET_CONFIG,
+  SDB_INSPECTOR_MSGKIND_SET_CONFIG, SDB_INSPECTOR_MSGKIND_ESTIMATOR, SDB_INSPECTOR_MSGKIND_SPECTRUM,
+  SDB_INSPECTOR_MSGKIND_CLOSE, SDB_INSPECTOR_MSGKIND_INVALID_CHANNEL, SDB_INSPECTOR_MSGKIND_WRONG_HANDLE,
+  SDB_INSPECTOR_MSGKIND_WRONG_OBJECT, SDB_INSPECTOR_MSGKIND_WRONG_KIND
+};
+enum { SDB_ANALYZER_MODE_CHANNEL = 0, SDB_ANALYZER_MODE_WIDE_SPECTRUM = 1 };
+
+/* struct sigutils_channel {fc, ft, f_lo, f_hi, bw} (Suscan/Analyzer.cpp:417-424); Hz, fc relative to the tuner */
+typedef struct { double fc, ft, f_lo, f_hi; float bw; } sdb_sigutils_channel;
+
+/* struct suscan_analyzer_params (Suscan/AnalyzerParams.cpp:27-68) */
+typedef struct {
+  int32_t mode;
+  struct { uint64_t window_size; int32_t window; float alpha, beta, gamma, snr; } detector_params;
+  float   channel_update_int, psd_update_int;       /* seconds */
+  double  min_freq, max_freq;
+} sdb_analyzer_params;
+
+/* the part of suscan_source_config_t this path needs: a callback source (role of file / stdin / SoapySDR
+ * back-ends) or an in-memory capture */
+typedef long (*sdb_source_read_fn)(void *priv, sdb_complex *dst, size_t max_samples);   /* 0 = EOS, < 0 = error */
+typedef struct {
+  double  samp_rate, freq;
+  size_t  read_size;              /* samples per block (rounded to a multiple of window_size; 0 = 8 windows) */
+  sdb_source_read_fn read; void *priv;
+  const sdb_complex *data; size_t length; int32_t loop;
+  int32_t device;
+} sdb_source_config;
+
+typedef struct {                  /* suscan_analyzer_psd_msg */
+  int64_t fc; uint32_t inspector_id; struct timeval timestamp, rt_time; int32_t looped; uint64_t history_size;
+  float samp_rate, measured_samp_rate; uint64_t psd_size; float *psd_data;
+} sdb_analyzer_psd_msg;
+typedef struct {                  /* suscan_analyzer_sample_batch_msg (+ the GUI Decider's output) */
+  uint32_t inspector_id; sdb_complex *samples; uint64_t sample_count; uint8_t *symbols;
+} sdb_analyzer_sample_batch_msg;
+typedef struct {                  /* suscan_analyzer_inspector_msg, fields this path fills */
+  int32_t kind; uint32_t inspector_id, req_id; int32_t handle; char *class_name; sdb_sigutils_channel channel;
+  sdb_inspector_config config; float fs, equiv_fs, bandwidth, lo;
+} sdb_analyzer_inspector_msg;
+typedef struct { int32_t code; char *err_msg; } sdb_analyzer_status_msg;   /* suscan_analyzer_status_msg */
+typedef struct {                  /* suscan_source_info, fields this path fills */
+  uint64_t permissions, source_samp_rate, effective_samp_rate; float measured_samp_rate; double frequency;
+  int32_t seekable;
+} sdb_source_info;
+
+typedef struct sdb_analyzer sdb_analyzer_t;
+sdb_analyzer_t *sdb_analyzer_new(const sdb_analyzer_params *params, const sdb_source_config *src);  /* Analyzer.cpp:608 */
+void  *sdb_analyzer_read(sdb_analyzer_t *a, uint32_t *type);                 /* blocking; Analyzer.cpp:111-115 */
+void  *sdb_analyzer_read_timeout(sdb_analyzer_t *a, uint32_t *type, unsigned timeout_ms);
+void   sdb_analyzer_dispose_message(uint32_t type, void *ptr);               /* Suscan/Message.cpp:43-48 */
+void   sdb_analyzer_req_halt(sdb_analyzer_t *a);                             /* Analyzer.cpp:321 */
+void   sdb_analyzer_destroy(sdb_analyzer_t *a);                              /* Analyzer.cpp:625-638 */
+int    sdb_analyzer_open_ex_async(sdb_analyzer_t *a, const char *class_name, const sdb_sigutils_channel *ch,
+                                  int precise, int32_t parent, uint32_t req_id);        /* Analyzer.cpp:459-484 */
+int    sdb_analyzer_set_inspector_id_async(sdb_analyzer_t *a, int32_t handle, uint32_t inspector_id, uint32_t req_id);
+int    sdb_analyzer_set_inspector_config_async(sdb_analyzer_t *a, int32_t handle, const sdb_inspector_config *cfg,
+                                               uint32_t req_id);
+int    sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint32_t req_id);
+int    sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyzer_params *p, uint32_t req_id);
+uint64_t sdb_analyzer_get_samp_rate(const sdb_analyzer_t *a);
+float    sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a);
+
+/* ------------------------------------------------------------------------------------------------
  * Panoramic scanner: SpectrumView (Panoramic/Scanner.cpp:36-293, constants include/Scanner.h:26-32).
  * The reference does view.feed(psd, nullptr, fftSize, fc) per PSD message on the GUI thread
  * (Panoramic/Scanner.cpp:503-523).  Here the per-hop projection (the O(psd_size) part) is separate from
@@ -200,6 +288,8 @@ int      sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t psd_size
                            size_t n_hops, int adjust_sides);
 /* device pointers of the last projection: j0[n_hops], nb[n_hops], va/vc[n_hops][max_bins] */
 int      sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc);
+/* copy them into caller-owned device buffers (e.g. the send buffers of the NCCL gather) */
+int      sdb_sview_contrib_copy(sdb_sview_t *v, int32_t *j0, int32_t *nb, float *va, float *vc, size_t n_hops);
 /* apply contribution lists (device pointers; own or gathered from peers) in hop order, then fill gaps */
 int      sdb_sview_accumulate(sdb_sview_t *v, const int32_t *j0, const int32_t *nb, const float *va,
                               const float *vc, size_t n_hops);

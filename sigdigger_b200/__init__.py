@@ -66,6 +66,8 @@ _PROTOS = {
     "sdb_engine_read_channel": (C.c_long, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]),
     "sdb_engine_read_symbols": (C.c_long, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_read_all_symbols": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_read_psd_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_read_all_symbols_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_symbol_counts_device": (C.c_void_p, [C.c_void_p]),
     "sdb_engine_symbol_capacity": (C.c_size_t, [C.c_void_p]),
     "sdb_engine_stream": (C.c_void_p, [C.c_void_p]),
@@ -79,6 +81,19 @@ _PROTOS = {
     "sdb_task_pll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_agc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_lpf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_analyzer_new": (C.c_void_p, [C.c_void_p, C.c_void_p]),
+    "sdb_analyzer_read": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "sdb_analyzer_read_timeout": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint]),
+    "sdb_analyzer_dispose_message": (None, [C.c_uint32, C.c_void_p]),
+    "sdb_analyzer_req_halt": (None, [C.c_void_p]),
+    "sdb_analyzer_destroy": (None, [C.c_void_p]),
+    "sdb_analyzer_open_ex_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int32, C.c_uint32]),
+    "sdb_analyzer_set_inspector_id_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32]),
+    "sdb_analyzer_set_inspector_config_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32]),
+    "sdb_analyzer_close_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
+    "sdb_analyzer_set_params_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sdb_analyzer_get_samp_rate": (C.c_uint64, [C.c_void_p]),
+    "sdb_analyzer_get_measured_samp_rate": (C.c_float, [C.c_void_p]),
     "sdb_sview_new": (C.c_void_p, [C.c_int]),
     "sdb_sview_destroy": (None, [C.c_void_p]),
     "sdb_sview_set_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_float]),
@@ -88,6 +103,7 @@ _PROTOS = {
     "sdb_sview_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "sdb_sview_contrib": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "sdb_sview_contrib_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_sview_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_sview_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_task_inspector": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
@@ -238,6 +254,14 @@ class Engine:
         n = _check(self._L.sdb_engine_read_symbols(self._h, stream, h, soft.ctypes.data, hard.ctypes.data, cap))
         return soft[:n].copy(), hard[:n].copy()
 
+    def read_psd_async(self, out):
+        _check(self._L.sdb_engine_read_psd_async(self._h, out.ctypes.data, out.size))
+
+    def read_all_symbols_async(self, counts, soft, hard, cap):
+        _check(self._L.sdb_engine_read_all_symbols_async(self._h, counts.ctypes.data,
+                                                         soft.ctypes.data if soft is not None else None,
+                                                         hard.ctypes.data if hard is not None else None, cap))
+
     def read_all_symbols(self, counts, soft, hard, cap):
         _check(self._L.sdb_engine_read_all_symbols(self._h, counts.ctypes.data,
                                                    soft.ctypes.data if soft is not None else None,
@@ -368,6 +392,9 @@ class SpectrumView:
         p = [C.c_void_p() for _ in range(4)]
         _check(self._L.sdb_sview_contrib(self._h, *[C.byref(q) for q in p]))
         return [q.value for q in p]
+
+    def contrib_copy(self, j0_ptr, nb_ptr, va_ptr, vc_ptr, n_hops):
+        _check(self._L.sdb_sview_contrib_copy(self._h, j0_ptr, nb_ptr, va_ptr, vc_ptr, n_hops))
 
     def accumulate(self, j0_ptr=None, nb_ptr=None, va_ptr=None, vc_ptr=None, n_hops=None):
         if j0_ptr is None:

@@ -1,0 +1,149 @@
+"""ctypes mirror of the suscan-style asynchronous analyzer (include/sigdigger_b200.h, sdb_analyzer_*).
+
+Plays the role of `Suscan::Analyzer` + `Analyzer::AsyncThread` (Suscan/Analyzer.cpp:63-115, 601-638): construct,
+queue requests, drain messages.  Message payloads are copied into Python objects and disposed at once."""
+import ctypes as C
+
+import numpy as np
+
+from . import INSP, WINDOW, InspectorConfig, SdbError, last_error, load_library
+
+MSG = {"SOURCE_INFO": 0, "SOURCE_INIT": 1, "CHANNEL": 2, "EOS": 3, "READ_ERROR": 4, "INTERNAL": 5, "SAMPLES": 6,
+       "INSPECTOR": 7, "PSD": 8, "PARAMS": 9, "HALT": 0xffffffff, "TIMEOUT": 0xfffffffe}
+MSG_NAME = {v: k for k, v in MSG.items()}
+KIND = {0: "OPEN", 1: "SET_ID", 2: "GET_CONFIG", 3: "SET_CONFIG", 4: "ESTIMATOR", 5: "SPECTRUM", 6: "CLOSE",
+        7: "INVALID_CHANNEL", 8: "WRONG_HANDLE", 9: "WRONG_OBJECT", 10: "WRONG_KIND"}
+
+
+class Timeval(C.Structure):
+    _fields_ = [("tv_sec", C.c_long), ("tv_usec", C.c_long)]
+
+
+class SigutilsChannel(C.Structure):
+    _fields_ = [("fc", C.c_double), ("ft", C.c_double), ("f_lo", C.c_double), ("f_hi", C.c_double), ("bw", C.c_float)]
+
+
+class DetectorParams(C.Structure):
+    _fields_ = [("window_size", C.c_uint64), ("window", C.c_int32), ("alpha", C.c_float), ("beta", C.c_float),
+                ("gamma", C.c_float), ("snr", C.c_float)]
+
+
+class AnalyzerParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("detector_params", DetectorParams), ("channel_update_int", C.c_float),
+                ("psd_update_int", C.c_float), ("min_freq", C.c_double), ("max_freq", C.c_double)]
+
+
+READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class SourceConfig(C.Structure):
+    _fields_ = [("samp_rate", C.c_double), ("freq", C.c_double), ("read_size", C.c_size_t), ("read", READ_FN),
+                ("priv", C.c_void_p), ("data", C.c_void_p), ("length", C.c_size_t), ("loop", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class PsdMsg(C.Structure):
+    _fields_ = [("fc", C.c_int64), ("inspector_id", C.c_uint32), ("timestamp", Timeval), ("rt_time", Timeval),
+                ("looped", C.c_int32), ("history_size", C.c_uint64), ("samp_rate", C.c_float),
+                ("measured_samp_rate", C.c_float), ("psd_size", C.c_uint64), ("psd_data", C.POINTER(C.c_float))]
+
+
+class SampleBatchMsg(C.Structure):
+    _fields_ = [("inspector_id", C.c_uint32), ("samples", C.POINTER(C.c_float)), ("sample_count", C.c_uint64),
+                ("symbols", C.POINTER(C.c_uint8))]
+
+
+class InspectorMsg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("inspector_id", C.c_uint32), ("req_id", C.c_uint32), ("handle", C.c_int32),
+                ("class_name", C.c_char_p), ("channel", SigutilsChannel), ("config", InspectorConfig),
+                ("fs", C.c_float), ("equiv_fs", C.c_float), ("bandwidth", C.c_float), ("lo", C.c_float)]
+
+
+class StatusMsg(C.Structure):
+    _fields_ = [("code", C.c_int32), ("err_msg", C.c_char_p)]
+
+
+class Analyzer:
+    def __init__(self, samp_rate, window_size=8192, window="hann", psd_update_int=0.04, data=None, read=None,
+                 read_size=0, loop=False, freq=0.0, device=0):
+        self._L = load_library()
+        p = AnalyzerParams()
+        p.mode = 0
+        p.detector_params.window_size = window_size
+        p.detector_params.window = WINDOW[window] if isinstance(window, str) else window
+        p.psd_update_int = psd_update_int
+        self.params = p
+        s = SourceConfig()
+        s.samp_rate, s.freq, s.read_size, s.loop, s.device = samp_rate, freq, read_size, int(loop), device
+        if data is not None:
+            self._data = np.ascontiguousarray(data, dtype=np.complex64)
+            s.data, s.length = self._data.ctypes.data, len(self._data)
+            s.read = READ_FN(0)
+        else:
+            self._cb = READ_FN(read)
+            s.read = self._cb
+        self._h = self._L.sdb_analyzer_new(C.byref(p), C.byref(s))
+        if not self._h:
+            raise SdbError(last_error() or "sdb_analyzer_new failed (no CUDA device or invalid parameters)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_analyzer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def halt(self):
+        self._L.sdb_analyzer_req_halt(self._h)
+
+    def open(self, cls, fc, bw, precise=False, req_id=0):
+        ch = SigutilsChannel(fc, 0.0, fc - bw / 2 - fc, fc + bw / 2 - fc, bw)
+        ch.f_lo, ch.f_hi = -bw / 2, bw / 2          # as InspToolWidget.cpp:688-693 fills it
+        if self._L.sdb_analyzer_open_ex_async(self._h, cls.encode(), C.byref(ch), int(precise), -1, req_id):
+            raise SdbError("open_ex_async rejected")
+
+    def set_inspector_id(self, handle, inspector_id, req_id=0):
+        self._L.sdb_analyzer_set_inspector_id_async(self._h, handle, inspector_id, req_id)
+
+    def set_inspector_config(self, handle, cfg, req_id=0):
+        self._L.sdb_analyzer_set_inspector_config_async(self._h, handle, C.byref(cfg), req_id)
+
+    def close_inspector(self, handle, req_id=0):
+        self._L.sdb_analyzer_close_async(self._h, handle, req_id)
+
+    def read(self, timeout_ms=None):
+        """-> (type name, payload dict); payload memory is disposed before returning."""
+        t = C.c_uint32()
+        if timeout_ms is None:
+            ptr = self._L.sdb_analyzer_read(self._h, C.byref(t))
+        else:
+            ptr = self._L.sdb_analyzer_read_timeout(self._h, C.byref(t), timeout_ms)
+        name = MSG_NAME.get(t.value, str(t.value))
+        out = {}
+        if ptr:
+            if name == "PSD":
+                m = C.cast(ptr, C.POINTER(PsdMsg)).contents
+                out = dict(psd=np.ctypeslib.as_array(m.psd_data, shape=(m.psd_size,)).copy(), samp_rate=m.samp_rate,
+                           measured_samp_rate=m.measured_samp_rate, fc=m.fc,
+                           timestamp=m.timestamp.tv_sec + 1e-6 * m.timestamp.tv_usec)
+            elif name == "SAMPLES":
+                m = C.cast(ptr, C.POINTER(SampleBatchMsg)).contents
+                n = m.sample_count
+                out = dict(inspector_id=m.inspector_id,
+                           samples=np.ctypeslib.as_array(m.samples, shape=(2 * n,)).copy().view(np.complex64),
+                           symbols=np.ctypeslib.as_array(m.symbols, shape=(n,)).copy())
+            elif name == "INSPECTOR":
+                m = C.cast(ptr, C.POINTER(InspectorMsg)).contents
+                cfg = InspectorConfig()
+                C.memmove(C.byref(cfg), C.byref(m.config), C.sizeof(cfg))
+                out = dict(kind=KIND.get(m.kind, m.kind), req_id=m.req_id, handle=m.handle,
+                           inspector_id=m.inspector_id, class_name=(m.class_name or b"").decode(), config=cfg,
+                           fs=m.fs, equiv_fs=m.equiv_fs, bandwidth=m.bandwidth, lo=m.lo)
+            elif name in ("EOS", "READ_ERROR", "HALT", "SOURCE_INIT"):
+                m = C.cast(ptr, C.POINTER(StatusMsg)).contents
+                out = dict(code=m.code, err_msg=(m.err_msg or b"").decode())
+            self._L.sdb_analyzer_dispose_message(t.value, ptr)
+        return name, out
+
+
+__all__ = ["Analyzer", "MSG", "INSP"]

@@ -1,0 +1,444 @@
+// analyzer.cu -- suscan-style asynchronous analyzer on top of the engine: a worker thread pulls IQ from a
+// source, runs the engine block by block and posts heap-allocated messages on a FIFO that the caller
+// drains with sdb_analyzer_read(); requests (open / set id / set config / close / set params) are queued
+// and answered in order with messages carrying the caller's req_id.
+//
+// This is SURVEY.md section 8(a) row a18 + the command half of section 8(b), i.e. what the reference's
+// Suscan::Analyzer wrapper drives:
+//   suscan_analyzer_new / read / dispose_message / req_halt / destroy   Suscan/Analyzer.cpp:608, :111-115, :63-103, :321, :625-638
+//   suscan_analyzer_open_ex_async                                      Suscan/Analyzer.cpp:459-484
+//   suscan_analyzer_set_inspector_id_async / _config_async / close     Suscan/Analyzer.cpp:486-537
+//   suscan_analyzer_set_params_async                                   Suscan/Analyzer.cpp:219-227
+//   open handshake OPEN -> SET_ID                                      Suscan/AnalyzerRequestTracker.cpp:138-157
+//   message payload fields                                             Suscan/Messages/PSDMessage.cpp:30-112,
+//                                                                      include/Suscan/Messages/SamplesMessage.h:33-59,
+//                                                                      Suscan/Messages/InspectorMessage.cpp:28-71
+// Differences stated openly: the channel plan is rebuilt at a block boundary whenever an inspector is
+// opened, closed or reconfigured, which restarts the loops of the inspectors that stay open (suscan keeps
+// them running); one source per analyzer; no estimators / spectrum sources (section 8(f)).
+#include "../../include/sigdigger_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <sys/time.h>
+
+namespace {
+
+struct Cmd {
+  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS } kind;
+  uint32_t req_id = 0;
+  int32_t handle = -1;
+  uint32_t inspector_id = 0;
+  std::string cls;
+  sdb_sigutils_channel channel{};
+  int precise = 0;
+  sdb_inspector_config cfg{};
+  sdb_analyzer_params params{};
+};
+
+struct Insp {
+  int32_t handle;
+  bool open;
+  bool has_id;
+  uint32_t inspector_id;
+  int cls;
+  sdb_sigutils_channel channel;
+  int precise;
+  sdb_inspector_config cfg;
+  int engine_handle;      // handle inside the current engine, -1 if not mapped
+  float fs, bandwidth, lo;
+};
+
+int class_id(const std::string &c)
+{
+  if (c == "psk") return SDB_INSP_PSK;
+  if (c == "fsk") return SDB_INSP_FSK;
+  if (c == "ask") return SDB_INSP_ASK;
+  if (c == "audio") return SDB_INSP_AUDIO;
+  if (c == "raw") return SDB_INSP_RAW;
+  return -1;
+}
+
+char *dupstr(const char *s)
+{
+  size_t n = strlen(s) + 1;
+  char *p = (char *) malloc(n);
+  memcpy(p, s, n);
+  return p;
+}
+
+}  // namespace
+
+struct sdb_analyzer {
+  sdb_analyzer_params params;
+  sdb_source_config src;
+  size_t src_pos = 0;
+  // output queue (suscan_mq): MPSC FIFO of (type, payload)
+  std::mutex mq_m;
+  std::condition_variable mq_cv;
+  std::deque<std::pair<uint32_t, void *>> mq;
+  // command queue
+  std::mutex cmd_m;
+  std::deque<Cmd> cmds;
+  bool halt_req = false;
+  std::thread worker;
+  std::vector<Insp> insps;
+  sdb_engine_t *eng = nullptr;
+  bool plan_dirty = true;
+  size_t block = 0;
+  double measured_rate = 0;
+  uint64_t total_samples = 0;
+  double psd_credit = 0;
+
+  void post(uint32_t type, void *payload)
+  {
+    std::lock_guard<std::mutex> l(mq_m);
+    mq.emplace_back(type, payload);
+    mq_cv.notify_one();
+  }
+  void post_status(uint32_t type, int code, const char *msg)
+  {
+    sdb_analyzer_status_msg *m = (sdb_analyzer_status_msg *) calloc(1, sizeof(*m));
+    m->code = code;
+    m->err_msg = msg ? dupstr(msg) : nullptr;
+    post(type, m);
+  }
+  void post_inspector(int kind, const Cmd &c, const Insp *i)
+  {
+    sdb_analyzer_inspector_msg *m = (sdb_analyzer_inspector_msg *) calloc(1, sizeof(*m));
+    m->kind = kind; m->req_id = c.req_id; m->handle = i ? i->handle : c.handle;
+    m->inspector_id = i ? i->inspector_id : c.inspector_id;
+    m->class_name = dupstr(i ? (const char *[]){ "psk", "fsk", "ask", "audio", "raw" }[i->cls] : c.cls.c_str());
+    if (i) { m->channel = i->channel; m->config = i->cfg; m->fs = (float) src.samp_rate; m->equiv_fs = i->fs;
+             m->bandwidth = i->bandwidth; m->lo = i->lo; }
+    else m->channel = c.channel;
+    post(SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR, m);
+  }
+
+  // (re)build the engine from the open inspectors; returns false on failure (status message posted)
+  bool rebuild()
+  {
+    if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
+    sdb_engine_params ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.n_streams = 1;
+    ep.psd_size = (uint32_t) params.detector_params.window_size;
+    ep.psd_window = params.detector_params.window;
+    ep.st_window_size = 0;
+    ep.max_feed = (uint32_t) block;
+    ep.device = src.device;
+    ep.flags = 0;
+    eng = sdb_engine_new(&ep, src.samp_rate);
+    if (!eng) { post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error()); return false; }
+    for (auto &i : insps) {
+      i.engine_handle = -1;
+      if (!i.open) continue;
+      sdb_channel_params cp;
+      double f = fmod(i.channel.fc / src.samp_rate + 1.0, 1.0);
+      cp.f0 = (float) (2.0 * 3.14159265358979323846 * f);
+      cp.bw = (float) (2.0 * 3.14159265358979323846 * (i.channel.f_hi - i.channel.f_lo) / src.samp_rate);
+      cp.guard = 1.0f; cp.precise = i.precise;
+      sdb_channel_info info;
+      int h = sdb_engine_open_channel(eng, &cp, &info);
+      if (h < 0) continue;
+      i.engine_handle = h;
+      i.fs = (float) (src.samp_rate / info.decimation);
+      i.bandwidth = (float) (i.channel.f_hi - i.channel.f_lo);
+      i.lo = (float) i.channel.fc;
+      i.cfg.insp_class = i.cls;
+      sdb_engine_set_inspector(eng, h, &i.cfg);
+    }
+    if (sdb_engine_commit(eng)) {
+      post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error());
+      return false;
+    }
+    plan_dirty = false;
+    return true;
+  }
+
+  void handle_cmds()
+  {
+    std::deque<Cmd> todo;
+    { std::lock_guard<std::mutex> l(cmd_m); todo.swap(cmds); }
+    for (auto &c : todo) {
+      switch (c.kind) {
+        case Cmd::OPEN: {
+          int cls = class_id(c.cls);
+          double bw = c.channel.f_hi - c.channel.f_lo;
+          if (cls < 0) { post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_KIND, c, nullptr); break; }
+          if (!(bw > 0) || bw > src.samp_rate || fabs(c.channel.fc) > src.samp_rate / 2) {
+            post_inspector(SDB_INSPECTOR_MSGKIND_INVALID_CHANNEL, c, nullptr); break;
+          }
+          Insp i;
+          memset(&i, 0, sizeof(i));
+          i.handle = (int32_t) insps.size(); i.open = true; i.has_id = false; i.cls = cls; i.channel = c.channel;
+          i.precise = c.precise; i.engine_handle = -1;
+          // geometry -> equivalent rate, needed for the default config the OPEN reply carries
+          {
+            sdb_engine_params ep; memset(&ep, 0, sizeof(ep));
+            ep.n_streams = 1; ep.psd_size = (uint32_t) params.detector_params.window_size; ep.max_feed = (uint32_t) block;
+            ep.device = src.device;
+            sdb_engine_t *probe = sdb_engine_new(&ep, src.samp_rate);
+            sdb_channel_params cp;
+            cp.f0 = (float) (2.0 * 3.14159265358979323846 * fmod(c.channel.fc / src.samp_rate + 1.0, 1.0));
+            cp.bw = (float) (2.0 * 3.14159265358979323846 * bw / src.samp_rate); cp.guard = 1.0f; cp.precise = c.precise;
+            sdb_channel_info info; memset(&info, 0, sizeof(info));
+            int h = probe ? sdb_engine_open_channel(probe, &cp, &info) : -1;
+            if (probe) sdb_engine_destroy(probe);
+            if (h < 0) { post_inspector(SDB_INSPECTOR_MSGKIND_INVALID_CHANNEL, c, nullptr); break; }
+            i.fs = (float) (src.samp_rate / info.decimation);
+          }
+          i.bandwidth = (float) bw; i.lo = (float) c.channel.fc;
+          sdb_inspector_config_default(&i.cfg, cls, i.fs);
+          i.cfg.clock_running = 0;       // "by default ... no samples are being delivered" (manual p.62)
+          insps.push_back(i);
+          plan_dirty = true;
+          post_inspector(SDB_INSPECTOR_MSGKIND_OPEN, c, &insps.back());
+          break;
+        }
+        case Cmd::SET_ID:
+        case Cmd::SET_CONFIG:
+        case Cmd::CLOSE: {
+          if (c.handle < 0 || c.handle >= (int32_t) insps.size() || !insps[c.handle].open) {
+            post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_HANDLE, c, nullptr); break;
+          }
+          Insp &i = insps[c.handle];
+          if (c.kind == Cmd::SET_ID) {
+            i.inspector_id = c.inspector_id; i.has_id = true;
+            post_inspector(SDB_INSPECTOR_MSGKIND_SET_ID, c, &i);
+          } else if (c.kind == Cmd::SET_CONFIG) {
+            if (c.cfg.insp_class != i.cls) { post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_KIND, c, nullptr); break; }
+            i.cfg = c.cfg; plan_dirty = true;
+            post_inspector(SDB_INSPECTOR_MSGKIND_SET_CONFIG, c, &i);
+          } else {
+            i.open = false; plan_dirty = true;
+            post_inspector(SDB_INSPECTOR_MSGKIND_CLOSE, c, &i);
+          }
+          break;
+        }
+        case Cmd::SET_PARAMS: {
+          params = c.params; plan_dirty = true;
+          sdb_analyzer_params *m = (sdb_analyzer_params *) malloc(sizeof(*m));
+          *m = params;
+          post(SDB_ANALYZER_MESSAGE_TYPE_PARAMS, m);
+          break;
+        }
+      }
+    }
+  }
+
+  long source_read(sdb_complex *dst, size_t n)
+  {
+    if (src.read) return src.read(src.priv, dst, n);
+    if (!src.data) return -1;
+    size_t got = 0;
+    while (got < n) {
+      if (src_pos >= src.length) { if (!src.loop) break; src_pos = 0; }
+      size_t take = std::min(n - got, src.length - src_pos);
+      memcpy(dst + got, src.data + src_pos, take * sizeof(sdb_complex));
+      got += take; src_pos += take;
+    }
+    return (long) got;
+  }
+
+  void run()
+  {
+    std::vector<sdb_complex> buf(block);
+    std::vector<float> psd;
+    std::vector<sdb_complex> soft;
+    std::vector<uint8_t> hard;
+    {
+      sdb_source_info *si = (sdb_source_info *) calloc(1, sizeof(*si));
+      si->source_samp_rate = (uint64_t) src.samp_rate; si->effective_samp_rate = (uint64_t) src.samp_rate;
+      si->measured_samp_rate = 0; si->frequency = src.freq; si->seekable = src.read ? 0 : 1;
+      post(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INFO, si);
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    uint32_t exit_type = SDB_WORKER_MSG_TYPE_HALT;
+    for (;;) {
+      { std::lock_guard<std::mutex> l(cmd_m); if (halt_req) break; }
+      handle_cmds();
+      const size_t N = (size_t) params.detector_params.window_size;
+      if (block % N) block = std::max<size_t>(N, (block / N) * N);     // after a PARAMS change
+      if (buf.size() != block) buf.resize(block);
+      if (plan_dirty && !rebuild()) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
+      long got = source_read(buf.data(), block);
+      if (got < 0) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
+      if ((size_t) got < block) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_EOS; break; }   // partial tail blocks are dropped
+      if (sdb_engine_feed_host(eng, buf.data(), block, block) || sdb_engine_sync(eng)) {
+        exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break;
+      }
+      total_samples += block;
+      double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      measured_rate = el > 0 ? (double) total_samples / el : 0;
+      // PSD messages at psd_update_int cadence of SIGNAL time (coverage = N / (fs * interval))
+      const size_t frames = block / N;
+      psd.resize(frames * N);
+      if (sdb_engine_read_psd(eng, psd.data(), psd.size()) == 0) {
+        const double per_frame = (double) N / src.samp_rate;
+        for (size_t f = 0; f < frames; ++f) {
+          psd_credit += per_frame;
+          if (psd_credit + 1e-12 >= params.psd_update_int) {
+            psd_credit = params.psd_update_int > 0 ? fmod(psd_credit, params.psd_update_int) : 0;
+            sdb_analyzer_psd_msg *m = (sdb_analyzer_psd_msg *) calloc(1, sizeof(*m));
+            m->fc = (int64_t) src.freq; m->samp_rate = (float) src.samp_rate; m->measured_samp_rate = (float) measured_rate;
+            gettimeofday(&m->rt_time, nullptr);
+            double ts = (double) (total_samples - block + f * N) / src.samp_rate;
+            m->timestamp.tv_sec = (time_t) ts; m->timestamp.tv_usec = (suseconds_t) ((ts - floor(ts)) * 1e6);
+            m->psd_size = N;
+            m->psd_data = (float *) malloc(N * sizeof(float));
+            memcpy(m->psd_data, &psd[f * N], N * sizeof(float));
+            post(SDB_ANALYZER_MESSAGE_TYPE_PSD, m);
+          }
+        }
+      }
+      // sample batches, keyed by the caller-chosen inspector_id
+      for (auto &i : insps) {
+        if (!i.open || !i.has_id || i.engine_handle < 0) continue;
+        size_t cap = block;
+        soft.resize(cap); hard.resize(cap);
+        long n = sdb_engine_read_symbols(eng, 0, i.engine_handle, soft.data(), hard.data(), cap);
+        if (n <= 0) continue;
+        sdb_analyzer_sample_batch_msg *m = (sdb_analyzer_sample_batch_msg *) calloc(1, sizeof(*m));
+        m->inspector_id = i.inspector_id; m->sample_count = (uint64_t) n;
+        m->samples = (sdb_complex *) malloc((size_t) n * sizeof(sdb_complex));
+        m->symbols = (uint8_t *) malloc((size_t) n);
+        memcpy(m->samples, soft.data(), (size_t) n * sizeof(sdb_complex));
+        memcpy(m->symbols, hard.data(), (size_t) n);
+        post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
+      }
+    }
+    if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
+    post_status(exit_type, 0, exit_type == SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR ? sdb_last_error() : nullptr);
+  }
+};
+
+extern "C" sdb_analyzer_t *sdb_analyzer_new(const sdb_analyzer_params *params, const sdb_source_config *src)
+{
+  if (!params || !src) return nullptr;
+  if (sdb_device_count() <= 0) return nullptr;   // sdb_last_error() is set by the engine on first use; no CPU fallback
+  const uint64_t N = params->detector_params.window_size;
+  if (N < 16 || (N & (N - 1)) || !(src->samp_rate > 0) || (!src->read && !src->data)) return nullptr;
+  sdb_analyzer *a = new sdb_analyzer();
+  a->params = *params;
+  a->src = *src;
+  size_t blk = src->read_size ? src->read_size : (size_t) N * 8;
+  blk = std::max<size_t>(N, (blk / N) * N);
+  a->block = blk;
+  a->worker = std::thread([a] { a->run(); });
+  return a;
+}
+
+extern "C" void *sdb_analyzer_read(sdb_analyzer_t *a, uint32_t *type)
+{
+  if (!a) return nullptr;
+  std::unique_lock<std::mutex> l(a->mq_m);
+  a->mq_cv.wait(l, [a] { return !a->mq.empty(); });
+  auto m = a->mq.front();
+  a->mq.pop_front();
+  if (type) *type = m.first;
+  return m.second;
+}
+
+extern "C" void *sdb_analyzer_read_timeout(sdb_analyzer_t *a, uint32_t *type, unsigned timeout_ms)
+{
+  if (!a) return nullptr;
+  std::unique_lock<std::mutex> l(a->mq_m);
+  if (!a->mq_cv.wait_for(l, std::chrono::milliseconds(timeout_ms), [a] { return !a->mq.empty(); })) {
+    if (type) *type = 0xfffffffeu;
+    return nullptr;
+  }
+  auto m = a->mq.front();
+  a->mq.pop_front();
+  if (type) *type = m.first;
+  return m.second;
+}
+
+extern "C" void sdb_analyzer_dispose_message(uint32_t type, void *ptr)
+{
+  if (!ptr) return;
+  switch (type) {
+    case SDB_ANALYZER_MESSAGE_TYPE_PSD:
+      free(((sdb_analyzer_psd_msg *) ptr)->psd_data); break;
+    case SDB_ANALYZER_MESSAGE_TYPE_SAMPLES:
+      free(((sdb_analyzer_sample_batch_msg *) ptr)->samples);
+      free(((sdb_analyzer_sample_batch_msg *) ptr)->symbols); break;
+    case SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR:
+      free(((sdb_analyzer_inspector_msg *) ptr)->class_name); break;
+    case SDB_ANALYZER_MESSAGE_TYPE_EOS:
+    case SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR:
+    case SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT:
+    case SDB_WORKER_MSG_TYPE_HALT:
+      free(((sdb_analyzer_status_msg *) ptr)->err_msg); break;
+    default: break;
+  }
+  free(ptr);
+}
+
+extern "C" void sdb_analyzer_req_halt(sdb_analyzer_t *a)
+{
+  if (!a) return;
+  std::lock_guard<std::mutex> l(a->cmd_m);
+  a->halt_req = true;
+}
+
+extern "C" void sdb_analyzer_destroy(sdb_analyzer_t *a)
+{
+  if (!a) return;
+  sdb_analyzer_req_halt(a);
+  if (a->worker.joinable()) a->worker.join();
+  for (auto &m : a->mq) sdb_analyzer_dispose_message(m.first, m.second);
+  delete a;
+}
+
+static int push_cmd(sdb_analyzer_t *a, Cmd &&c)
+{
+  if (!a) return -1;
+  std::lock_guard<std::mutex> l(a->cmd_m);
+  a->cmds.push_back(std::move(c));
+  return 0;
+}
+
+extern "C" int sdb_analyzer_open_ex_async(sdb_analyzer_t *a, const char *class_name, const sdb_sigutils_channel *ch,
+                                          int precise, int32_t parent, uint32_t req_id)
+{
+  if (!class_name || !ch) return -1;
+  if (parent != -1) return -1;        // sub-carrier inspection (parent handles) is section 8(f), not built
+  Cmd c; c.kind = Cmd::OPEN; c.req_id = req_id; c.cls = class_name; c.channel = *ch; c.precise = precise;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_inspector_id_async(sdb_analyzer_t *a, int32_t handle, uint32_t inspector_id, uint32_t req_id)
+{
+  Cmd c; c.kind = Cmd::SET_ID; c.req_id = req_id; c.handle = handle; c.inspector_id = inspector_id;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_inspector_config_async(sdb_analyzer_t *a, int32_t handle, const sdb_inspector_config *cfg,
+                                                       uint32_t req_id)
+{
+  if (!cfg) return -1;
+  Cmd c; c.kind = Cmd::SET_CONFIG; c.req_id = req_id; c.handle = handle; c.cfg = *cfg;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint32_t req_id)
+{
+  Cmd c; c.kind = Cmd::CLOSE; c.req_id = req_id; c.handle = handle;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyzer_params *p, uint32_t req_id)
+{
+  if (!p) return -1;
+  const uint64_t N = p->detector_params.window_size;
+  if (N < 16 || (N & (N - 1))) return -1;
+  Cmd c; c.kind = Cmd::SET_PARAMS; c.req_id = req_id; c.params = *p;
+  return push_cmd(a, std::move(c));
+}
+extern "C" uint64_t sdb_analyzer_get_samp_rate(const sdb_analyzer_t *a) { return a ? (uint64_t) a->src.samp_rate : 0; }
+extern "C" float sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a) { return a ? (float) a->measured_rate : 0; }

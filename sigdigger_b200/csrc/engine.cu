@@ -85,6 +85,18 @@ struct sdb_engine {
   cudaEvent_t ev_chan[2] = { nullptr, nullptr }, ev_insp[2] = { nullptr, nullptr };
   bool ev_insp_valid[2] = { false, false };
   unsigned feed_index = 0; int last_buf = 0;
+  // Host-buffer pipeline: results and input staging are double-buffered by feed parity so that the H2D
+  // copy of feed i+1 and the D2H reads of feed i-1 overlap the kernels of feed i (three copy/compute
+  // streams).  d_psd / d_soft / d_hard / d_counts always point at the buffers of the latest feed.
+  float *d_psdb[2] = { nullptr, nullptr };
+  float2 *d_softb[2] = { nullptr, nullptr }; uint8_t *d_hardb[2] = { nullptr, nullptr };
+  uint32_t *d_countsb[2] = { nullptr, nullptr };
+  float2 *d_xinb[2] = { nullptr, nullptr };
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_psd_ready[2] = { nullptr, nullptr }, ev_psd_read[2] = { nullptr, nullptr },
+              ev_sym_read[2] = { nullptr, nullptr }, ev_h2d[2] = { nullptr, nullptr }, ev_xfree[2] = { nullptr, nullptr };
+  bool psd_read_valid[2] = { false, false }, sym_read_valid[2] = { false, false }, xfree_valid[2] = { false, false };
+  unsigned host_feeds = 0;
   size_t last_hops = 0;
   // chains
   SdbChainCfg *d_cfg = nullptr; std::vector<SdbChainCfg> h_cfg;
@@ -188,6 +200,11 @@ extern "C" void sdb_engine_destroy(sdb_engine_t *e)
     if (e->ev_insp[i]) cudaEventDestroy(e->ev_insp[i]);
   }
   if (e->insp_stream) cudaStreamDestroy(e->insp_stream);
+  if (e->h2d_stream) { cudaStreamSynchronize(e->h2d_stream); cudaStreamDestroy(e->h2d_stream); }
+  if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
+  for (int i = 0; i < 2; ++i)
+    for (cudaEvent_t ev : { e->ev_psd_ready[i], e->ev_psd_read[i], e->ev_sym_read[i], e->ev_h2d[i], e->ev_xfree[i] })
+      if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -365,8 +382,11 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     if (e->psd_small) { if (!e->twiddle(Np)) return fail("out of device memory"); }
     else if (!make_four_step(e, Np, &e->fs_psd)) return fail("out of device memory");
     e->max_frames = max_feed / Np;
-    e->d_psd = e->dalloc<float>((size_t) S * e->max_frames * Np);
-    if (!e->d_psd) return fail("out of device memory (psd)");
+    for (int i = 0; i < 2; ++i) {
+      e->d_psdb[i] = e->dalloc<float>((size_t) S * e->max_frames * Np);
+      if (!e->d_psdb[i]) return fail("out of device memory (psd)");
+    }
+    e->d_psd = e->d_psdb[0];
   }
   // ---- scratch sized to stay inside L2 (126 MB): 32 MB
   {
@@ -475,9 +495,14 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     const size_t pool_floats = ((chains + 31) / 32) * 32 * pool;   // per-CTA interleaved [slot][lane]
     e->d_pool = e->dalloc<float>(pool_floats);
     e->d_taps = e->dalloc<float>(taps_pool.size());
-    e->d_soft = e->dalloc<float2>(chains * cap);
-    e->d_hard = e->dalloc<uint8_t>(chains * cap);
-    e->d_counts = e->dalloc<uint32_t>(chains);
+    for (int i = 0; i < 2; ++i) {
+      e->d_softb[i] = e->dalloc<float2>(chains * cap);
+      e->d_hardb[i] = e->dalloc<uint8_t>(chains * cap);
+      e->d_countsb[i] = e->dalloc<uint32_t>(chains);
+      if (!e->d_softb[i] || !e->d_hardb[i] || !e->d_countsb[i]) return fail("out of device memory (symbols)");
+      CK(cudaMemset(e->d_countsb[i], 0, chains * sizeof(uint32_t)));
+    }
+    e->d_soft = e->d_softb[0]; e->d_hard = e->d_hardb[0]; e->d_counts = e->d_countsb[0];
     if (!e->d_cfg || !e->d_state || !e->d_pool || !e->d_taps || !e->d_soft || !e->d_hard || !e->d_counts)
       return fail("out of device memory (chains)");
     CK(cudaMemcpy(e->d_cfg, e->h_cfg.data(), K * sizeof(SdbChainCfg), cudaMemcpyHostToDevice));
@@ -494,6 +519,15 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     CK(cudaMemcpy(e->d_state, st.data(), chains * sizeof(SdbChainState), cudaMemcpyHostToDevice));
     CK(cudaMemset(e->d_pool, 0, pool_floats * sizeof(float)));   // the kernel initialises its lines when `fresh`
     CK(cudaMemset(e->d_counts, 0, chains * sizeof(uint32_t)));
+  }
+  CK(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&e->ev_psd_ready[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_psd_read[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_sym_read[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_xfree[i], cudaEventDisableTiming));
   }
   e->committed = true;
   return 0;
@@ -512,11 +546,14 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
   const float2 *x = reinterpret_cast<const float2 *>(xv);
   SdbLaunchCtx ctx{ e->stream, &e->launches };
   const int shift_db = (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) ? 1 : 0;
+  const int ob = (int) (e->feed_index & 1u);     // result buffers of this feed
 
   // ---- main PSD
   if (Np) {
     const int frames = (int) (n / Np);
     e->last_frames = frames;
+    e->d_psd = e->d_psdb[ob];
+    if (e->psd_read_valid[ob]) CK(cudaStreamWaitEvent(e->stream, e->ev_psd_read[ob], 0));   // async read of feed i-2
     if (e->psd_small) {
       e->span_begin(FAM_ROWS_PSD);
       CK(sdb_launch_small_psd(ctx, (int) Np, e->twiddle(Np), x, stride, frames, (int) S, e->d_window,
@@ -544,6 +581,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
         e->span_end();
       }
     }
+    CK(cudaEventRecord(e->ev_psd_ready[ob], e->stream));
   }
   // ---- channeliser + inspectors
   if (K) {
@@ -584,6 +622,8 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       e->span_end();
       CK(cudaEventRecord(e->ev_chan[b], e->stream));
       CK(cudaStreamWaitEvent(e->insp_stream, e->ev_chan[b], 0));
+      e->d_soft = e->d_softb[b]; e->d_hard = e->d_hardb[b]; e->d_counts = e->d_countsb[b];
+      if (e->sym_read_valid[b]) CK(cudaStreamWaitEvent(e->insp_stream, e->ev_sym_read[b], 0));
       SdbLaunchCtx ictx{ e->insp_stream, &e->launches };
       e->span_begin(FAM_INSPECTOR, e->insp_stream);
       CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
@@ -594,14 +634,19 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       CK(cudaEventRecord(e->ev_insp[b], e->insp_stream));
       e->ev_insp_valid[b] = true;
     } else {
+      e->d_counts = e->d_countsb[ob];
+      e->last_buf = ob;
+      if (e->sym_read_valid[ob]) CK(cudaStreamWaitEvent(e->insp_stream, e->ev_sym_read[ob], 0));
       CK(cudaMemsetAsync(e->d_counts, 0, (size_t) S * K * sizeof(uint32_t), e->insp_stream));
+      CK(cudaEventRecord(e->ev_insp[ob], e->insp_stream));
+      e->ev_insp_valid[ob] = true;
     }
-    ++e->feed_index;
     // keep the last half window of every stream as history for the next feed
     CK(cudaMemcpy2DAsync(e->d_hist, (W / 2) * sizeof(float2), x + (n - W / 2), stride * sizeof(float2),
                          (W / 2) * sizeof(float2), S, cudaMemcpyDeviceToDevice, e->stream));
     e->first_feed = false;
   }
+  ++e->feed_index;
   return 0;
 }
 
@@ -612,13 +657,27 @@ extern "C" int sdb_engine_feed_host(sdb_engine_t *e, const sdb_complex *x, size_
   if (n == 0 || n > e->prm.max_feed) return fail("feed size out of range");
   CK(cudaSetDevice(e->prm.device));
   const unsigned S = e->prm.n_streams;
-  if (!e->d_xin) {
-    e->d_xin = e->dalloc<float2>((size_t) S * e->prm.max_feed);
-    if (!e->d_xin) return fail("out of device memory (input staging)");
+  const int hb = (int) (e->host_feeds & 1u);
+  if (!e->d_xinb[hb]) {
+    e->d_xinb[hb] = e->dalloc<float2>((size_t) S * e->prm.max_feed);
+    if (!e->d_xinb[hb]) return fail("out of device memory (input staging)");
   }
-  CK(cudaMemcpy2DAsync(e->d_xin, n * sizeof(float2), x, stride * sizeof(float2), n * sizeof(float2), S,
-                       cudaMemcpyHostToDevice, e->stream));
-  return sdb_engine_feed_device(e, reinterpret_cast<const sdb_complex *>(e->d_xin), n, n);
+  // H2D on its own stream into staging buffer hb, as soon as the kernels of feed i-2 are done with it;
+  // the kernels of this feed wait for the copy.  Copies of consecutive feeds overlap compute.
+  if (e->xfree_valid[hb]) CK(cudaStreamWaitEvent(e->h2d_stream, e->ev_xfree[hb], 0));
+  if (stride == n)
+    CK(cudaMemcpyAsync(e->d_xinb[hb], x, (size_t) S * n * sizeof(float2), cudaMemcpyHostToDevice, e->h2d_stream));
+  else
+    CK(cudaMemcpy2DAsync(e->d_xinb[hb], n * sizeof(float2), x, stride * sizeof(float2), n * sizeof(float2), S,
+                         cudaMemcpyHostToDevice, e->h2d_stream));
+  CK(cudaEventRecord(e->ev_h2d[hb], e->h2d_stream));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_h2d[hb], 0));
+  int rc = sdb_engine_feed_device(e, reinterpret_cast<const sdb_complex *>(e->d_xinb[hb]), n, n);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_xfree[hb], e->stream));
+  e->xfree_valid[hb] = true;
+  ++e->host_feeds;
+  return 0;
 }
 
 extern "C" int sdb_engine_sync(sdb_engine_t *e)
@@ -627,6 +686,8 @@ extern "C" int sdb_engine_sync(sdb_engine_t *e)
   CK(cudaSetDevice(e->prm.device));
   CK(e->join());
   CK(cudaStreamSynchronize(e->stream));
+  if (e->d2h_stream) CK(cudaStreamSynchronize(e->d2h_stream));
+  if (e->h2d_stream) CK(cudaStreamSynchronize(e->h2d_stream));
   e->collect_spans();
   return 0;
 }
@@ -650,9 +711,27 @@ extern "C" int sdb_engine_read_psd(sdb_engine_t *e, float *dst, size_t cap)
   if (!e || !dst) return fail("null argument");
   const size_t n = (size_t) e->prm.n_streams * e->last_frames * e->Np;
   if (cap < n) return fail("destination too small");
+  if (sdb_engine_read_psd_async(e, dst, cap)) return -1;
+  CK(cudaStreamSynchronize(e->d2h_stream));
+  return 0;
+}
+
+// Asynchronous variants: the copy is queued on the engine's D2H stream behind the kernels that produce
+// the data; the next feed may be submitted immediately (results are double-buffered by feed parity, a
+// buffer is reused two feeds later and its writer waits for this copy).  dst should be pinned memory and
+// must stay valid until sdb_engine_sync().
+extern "C" int sdb_engine_read_psd_async(sdb_engine_t *e, float *dst, size_t cap)
+{
+  if (!e || !dst) return fail("null argument");
+  if (!e->committed || !e->Np || e->feed_index == 0) return fail("no PSD available");
+  const size_t n = (size_t) e->prm.n_streams * e->last_frames * e->Np;
+  if (cap < n) return fail("destination too small");
+  const int ob = (int) ((e->feed_index - 1) & 1u);
   CK(cudaSetDevice(e->prm.device));
-  CK(cudaMemcpyAsync(dst, e->d_psd, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamWaitEvent(e->d2h_stream, e->ev_psd_ready[ob], 0));
+  CK(cudaMemcpyAsync(dst, e->d_psdb[ob], n * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+  CK(cudaEventRecord(e->ev_psd_read[ob], e->d2h_stream));
+  e->psd_read_valid[ob] = true;
   return 0;
 }
 
@@ -698,14 +777,29 @@ extern "C" int sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sd
   if (!e || !counts) return fail("null argument");
   const size_t chains = (size_t) e->prm.n_streams * e->channels.size();
   if (chains == 0) return 0;
+  if (sdb_engine_read_all_symbols_async(e, counts, soft, hard, cap)) return -1;
+  CK(cudaStreamSynchronize(e->d2h_stream));
+  return 0;
+}
+
+extern "C" int sdb_engine_read_all_symbols_async(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft,
+                                                 uint8_t *hard, size_t cap)
+{
+  if (!e || !counts) return fail("null argument");
+  const size_t chains = (size_t) e->prm.n_streams * e->channels.size();
+  if (chains == 0) return 0;
+  if (e->feed_index == 0) return fail("no symbols available");
+  const int ob = (int) ((e->feed_index - 1) & 1u);
   CK(cudaSetDevice(e->prm.device));
-  CK(e->join());
-  CK(cudaMemcpyAsync(counts, e->d_counts, chains * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  // everything queued so far on the inspector stream (including this feed's launch or its count reset)
+  if (e->ev_insp_valid[ob]) CK(cudaStreamWaitEvent(e->d2h_stream, e->ev_insp[ob], 0));
+  CK(cudaMemcpyAsync(counts, e->d_countsb[ob], chains * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->d2h_stream));
   const size_t w = std::min(cap, e->sym_cap);
-  if (soft) CK(cudaMemcpy2DAsync(soft, cap * sizeof(float2), e->d_soft, e->sym_cap * sizeof(float2),
-                                 w * sizeof(float2), chains, cudaMemcpyDeviceToHost, e->stream));
-  if (hard) CK(cudaMemcpy2DAsync(hard, cap, e->d_hard, e->sym_cap, w, chains, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  if (soft) CK(cudaMemcpy2DAsync(soft, cap * sizeof(float2), e->d_softb[ob], e->sym_cap * sizeof(float2),
+                                 w * sizeof(float2), chains, cudaMemcpyDeviceToHost, e->d2h_stream));
+  if (hard) CK(cudaMemcpy2DAsync(hard, cap, e->d_hardb[ob], e->sym_cap, w, chains, cudaMemcpyDeviceToHost, e->d2h_stream));
+  CK(cudaEventRecord(e->ev_sym_read[ob], e->d2h_stream));
+  e->sym_read_valid[ob] = true;
   return 0;
 }
 
@@ -1034,6 +1128,21 @@ extern "C" int sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, flo
   if (nb) *nb = v->d_nb;
   if (va) *va = v->d_va;
   if (vc) *vc = v->d_vc;
+  return 0;
+}
+
+// copy the last projection's contribution lists into caller-owned DEVICE buffers (the send buffers of the
+// NCCL gather): j0/nb [n_hops] int32, va/vc [n_hops][max_bins] float32
+extern "C" int sdb_sview_contrib_copy(sdb_sview_t *v, int32_t *j0, int32_t *nb, float *va, float *vc, size_t n_hops)
+{
+  if (!v || !j0 || !nb || !va || !vc) return fail("null argument");
+  if (n_hops > v->hop_cap) return fail("more hops than the last projection held");
+  CK(cudaSetDevice(v->device));
+  const size_t row = (size_t) v->max_bins * sizeof(float);
+  CK(cudaMemcpy(j0, v->d_j0, n_hops * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(nb, v->d_nb, n_hops * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(va, v->d_va, n_hops * row, cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(vc, v->d_vc, n_hops * row, cudaMemcpyDeviceToDevice));
   return 0;
 }
 

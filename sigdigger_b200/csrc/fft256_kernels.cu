@@ -67,7 +67,7 @@ struct Cols256K {
 
 #define LDC 273    // pitch of one column's [ka][17] block (odd: conflict-free across columns)
 
-__global__ void __launch_bounds__(256, 3) k_cols256(const Cols256K p)
+__global__ void __launch_bounds__(256, 4) k_cols256(const Cols256K p)   // 64 regs, 39 KB smem -> 4 CTAs / SM
 {
   __shared__ float2 sm[16 * LDC];
   __shared__ float2 s_tw[256], s_fine[256];

@@ -58,14 +58,8 @@ def sweep(sdb, torch, dist, x_local, centers_all, psd_size, window, view_range, 
     if hi > lo:
         eng.feed(x_local)
         view.project(eng.psd_device_ptr, psd_size, centers_all[lo:hi])
-        pj0, pnb, pva, pvc = view.contrib_ptrs()
-        n = hi - lo
-        # device-to-device copies of the contribution lists into the (padded) send buffers
-        import ctypes as C
-        cudart = torch.cuda.cudart()
-        for dst, src, nbytes in ((j0, pj0, 4 * n), (nb, pnb, 4 * n), (va, pva, 4 * n * mb), (vc, pvc, 4 * n * mb)):
-            cudart.cudaMemcpy(dst.data_ptr(), src, nbytes, 3)
-        del C
+        # device-to-device copy of the contribution lists into the (padded) send buffers
+        view.contrib_copy(j0.data_ptr(), nb.data_ptr(), va.data_ptr(), vc.data_ptr(), hi - lo)
     torch.cuda.synchronize()
     if world > 1:
         outs = []

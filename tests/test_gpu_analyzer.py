@@ -1,0 +1,105 @@
+"""-m gpu: the suscan-style asynchronous analyzer (message queue + requests), SURVEY.md 8(a) a18 / 8(b).
+Message flow follows the reference's handshake (Suscan/AnalyzerRequestTracker.cpp:138-157): OPEN reply ->
+SET_ID -> SET_CONFIG -> SAMPLES keyed by the caller's inspector id; PSD messages; EOS terminates."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+import parity
+from sigdigger_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_analyzer_message_flow_and_parity(sdb, oracle):
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 8192, 1.0e6
+    baud = fs / 100.0
+    blocks, per_block = 6, N * 8
+    n = blocks * per_block
+    x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs + 3.0, baud, -10.0, {})], noise_db=-50.0, seed=31)
+    go = threading.Event()
+    pos = [0]
+
+    def read(priv, dst, maxn):                    # plays the role of a file / SDR source back-end
+        go.wait(30)
+        take = min(maxn, n - pos[0])
+        if take > 0:
+            C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+            pos[0] += take
+        return take
+
+    a = Analyzer(fs, window_size=N, window="blackmann_harris", psd_update_int=N / fs, read=read, read_size=per_block)
+    name, info = a.read(5000)
+    assert name == "SOURCE_INFO"
+    # the worker is now blocked in the first read; queue the handshake, then let the source run
+    a.open("psk", 0.125 * fs, 3 * baud, req_id=11)
+    a.open("nope", 0.0, 1000.0, req_id=12)                       # unknown class -> WRONG_KIND
+    a.set_inspector_id(0, 0xBEEF, req_id=13)
+    cfg = sdb.InspectorConfig()
+    fs_ch = fs * 256 / N
+    sdb._check(sdb.load_library().sdb_inspector_config_default(C.byref(cfg), sdb.INSP["psk"], fs_ch))
+    kw = dict(baud=baud, costas_order=2, bits_per_symbol=2, loop_bw=fs_ch * 2e-3, mf_type=1, mf_rolloff=0.35,
+              clock_type=1, clock_gain=0.1, clock_running=1)
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    a.set_inspector_config(0, cfg, req_id=14)
+    a.set_inspector_id(7, 1, req_id=15)                          # bad handle -> WRONG_HANDLE
+    go.set()
+    psd, soft, hard, replies = [], [], [], []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "PSD":
+            psd.append(m["psd"])
+            assert m["samp_rate"] == fs
+        elif name == "SAMPLES":
+            assert m["inspector_id"] == 0xBEEF
+            soft.append(m["samples"])
+            hard.append(m["symbols"])
+        elif name == "INSPECTOR":
+            replies.append((m["kind"], m["req_id"], m["handle"]))
+            if m["kind"] == "OPEN":
+                assert m["class_name"] == "psk" and abs(m["equiv_fs"] - fs_ch) < 1e-3 and m["config"].clock_running == 0
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    assert name == "EOS"
+    a.close()
+    assert replies == [("OPEN", 11, 0), ("WRONG_KIND", 12, -1), ("SET_ID", 13, 0), ("SET_CONFIG", 14, 0),
+                       ("WRONG_HANDLE", 15, 7)]
+    # every PSD frame of every block, bit-identical to the oracle
+    ref_psd = oracle.psd_frames(x, N, "blackmann_harris")
+    assert len(psd) == n // N
+    assert np.array_equal(np.stack(psd).view(np.uint32), ref_psd.view(np.uint32))
+    # the inspector became active at the second block (requests are applied at block boundaries)
+    ic = oracle.insp_config("psk", fs_ch, **kw)
+    f0, bw = float(np.float32(2.0 * np.pi * 0.125)), float(np.float32(2.0 * np.pi * (3 * baud) / fs))
+    ref = oracle.analyzer_run(oracle.make_an_params(N, "blackmann_harris", [(f0, bw, 1.0, 0, ic)]), x[per_block:])
+    parity.assert_symbols_match(np.concatenate(soft), np.concatenate(hard), ref["soft"][0], ref["hard"][0],
+                                exact_soft=True)
+
+
+def test_analyzer_memory_source_halt(sdb):
+    from sigdigger_b200.analyzer import Analyzer
+    N = 4096
+    x = (0.1 * np.exp(2j * np.pi * 0.1 * np.arange(N * 16))).astype(np.complex64)
+    a = Analyzer(1e6, window_size=N, window="hann", psd_update_int=0.0, data=x, loop=True, read_size=N * 4)
+    seen = 0
+    for _ in range(50):
+        name, m = a.read(10000)
+        if name == "PSD":
+            seen += 1
+            k = int(np.argmax(m["psd"]))
+            assert abs(k - 0.1 * N) <= 1
+        if seen >= 12:
+            break
+    assert seen >= 12
+    a.halt()
+    for _ in range(1000):
+        name, m = a.read(10000)
+        if name == "HALT":
+            break
+    assert name == "HALT"
+    a.close()

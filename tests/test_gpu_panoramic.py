@@ -83,6 +83,24 @@ def test_panoramic_sweep_matches_reference_sequence(sdb, oracle, N, n_hops, revi
     del torch
 
 
+def test_panoramic_sweep_driver_single_rank(sdb, oracle):
+    """sigdigger_b200.panoramic.sweep() with world = 1 (the multi-GPU form is tests/test_gpu_multi.py)."""
+    import torch
+    from sigdigger_b200 import panoramic
+    N, n_hops, fs, rel_bw = 16384, 21, 100e6, 0.5
+    fmin, fmax = 3.0e9, 3.0e9 + n_hops * fs * rel_bw
+    centers = fmin + fs * rel_bw * (0.5 + np.arange(n_hops))
+    x = _hops(n_hops, N, fs, seed=2)
+    psd, acc, cnt = panoramic.sweep(sdb, torch, None, torch.from_numpy(x).cuda(), centers, N, "hann", (fmin, fmax),
+                                    fs, rel_bw)
+    psd_db = np.stack([oracle.psd_frames(x[h], N, "hann")[0] for h in range(n_hops)])
+    for h in range(n_hops):
+        oracle.lib().sdo_psd_shift_db(oracle.ptr(psd_db[h]), N)
+    ref = _oracle_view(oracle, psd_db, centers, fmin, fmax, fs, rel_bw)
+    assert np.array_equal(cnt, ref[2]) and np.array_equal(acc.view(np.uint32), ref[1].view(np.uint32))
+    assert np.array_equal(psd.view(np.uint32), ref[0].view(np.uint32))
+
+
 def test_panoramic_histogram_mode(sdb, oracle):
     """hop narrower than two destination bins -> feedHistogramMode (Scanner.cpp:187-237)"""
     N, n_hops = 4096, 30

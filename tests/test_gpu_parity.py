@@ -429,6 +429,58 @@ def test_pipeline_mixed_inspectors_streams_and_chunks(sdb, oracle):
     assert not failures, "\n".join(failures)
 
 
+def test_async_pipeline_matches_sync(sdb):
+    """feed_host + read_*_async queued back to back (H2D / kernels / D2H of neighbouring feeds overlap,
+    results double-buffered) must give exactly what feed + blocking reads give."""
+    N, S, feeds = 16384, 4, 5
+    n = N * 4
+    specs = [("qpsk", 0.10, 1 / 128., -14.0, {}), ("fsk", 0.30, 1 / 160., -14.0, {})]
+    x, _ = _pipeline_case(N, 8 * feeds, 70, specs, S=S)
+
+    def make():
+        e = sdb.Engine(n_streams=S, psd_size=N, psd_window="hann", max_feed=n)
+        hs = []
+        for kind, f, baud, _, _ in specs:
+            h = e.open_channel(2 * np.pi * f, 2 * np.pi * 3 * baud, 1.0)
+            if kind == "qpsk":
+                e.set_inspector(h, "psk", baud=baud, costas_order=2, bits_per_symbol=2,
+                                loop_bw=e.channel_rate(h) * 2e-3, mf_type=1, clock_type=1, clock_gain=0.1)
+            else:
+                e.set_inspector(h, "fsk", baud=baud, bits_per_symbol=1, mf_type=1, clock_type=1, clock_gain=0.2)
+            hs.append(h)
+        e.commit()
+        return e, hs
+
+    e1, hs = make()
+    cap = e1.symbol_capacity
+    K = len(hs)
+    ref = []
+    for i in range(feeds):
+        e1.feed(x[:, i * n:(i + 1) * n])
+        cnt = np.zeros(S * K, np.uint32)
+        soft = np.zeros((S * K, cap), np.complex64)
+        hard = np.zeros((S * K, cap), np.uint8)
+        e1.read_all_symbols(cnt, soft, hard, cap)
+        ref.append((e1.read_psd().copy(), cnt, soft, hard))
+    e2, _ = make()
+    outs = []
+    for i in range(feeds):
+        seg = np.ascontiguousarray(x[:, i * n:(i + 1) * n])
+        outs.append((seg, np.zeros((S, n // N, N), np.float32), np.zeros(S * K, np.uint32),
+                     np.zeros((S * K, cap), np.complex64), np.zeros((S * K, cap), np.uint8)))
+        e2.feed_host_ptr(seg.ctypes.data, n, n)
+        e2.read_psd_async(outs[-1][1])
+        e2.read_all_symbols_async(outs[-1][2], outs[-1][3], outs[-1][4], cap)
+    e2.sync()
+    for i in range(feeds):
+        assert np.array_equal(outs[i][1].view(np.uint32), ref[i][0].view(np.uint32)), "psd of feed %d" % i
+        assert np.array_equal(outs[i][2], ref[i][1])
+        for c in range(S * K):
+            m = ref[i][1][c]
+            assert np.array_equal(outs[i][3][c, :m].view(np.uint32), ref[i][2][c, :m].view(np.uint32))
+            assert np.array_equal(outs[i][4][c, :m], ref[i][3][c, :m])
+
+
 def test_error_paths(sdb):
     e = sdb.Engine(n_streams=1, psd_size=8192, max_feed=8192)
     with pytest.raises(sdb.SdbError):
