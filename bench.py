@@ -273,7 +273,10 @@ def run_cuda(args):
     fam = {f: e.kernel_time(f) for f in ("fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft", "inspector")}
     e.timing(False)
     wps, frames = H, H // 2
-    chunk = max(1, (int(os.environ.get("SDB_SCRATCH_MB", "64")) << 20) // (N_FFT * 8))
+    if "SDB_SCRATCH_MB" in os.environ:
+        chunk = max(1, (int(os.environ["SDB_SCRATCH_MB"]) << 20) // (N_FFT * 8))
+    else:
+        chunk = torch.cuda.get_device_properties(local).multi_processor_count   # one window per SM (engine.cu)
     nb = sum(2 * (e.channel_info(h).width // 2) for h in hs)
     alg = {"fft_cols": min(chunk, S * wps) * N_FFT * 8.0,
            "fft_rows_psd": min(chunk, S * frames) * N_FFT * 4.0,
@@ -314,31 +317,59 @@ def run_cuda(args):
     soft_h = [pin((S * K, cap), torch.complex64) for _ in range(2)]
     hard_h = [pin((S * K, cap), torch.uint8) for _ in range(2)]
     e.sync()
-    step_no = [0]
 
-    def step_e2e():
-        b = step_no[0] & 1
-        step_no[0] += 1
-        e.feed_host_ptr(xh.data_ptr(), xh.stride(0), n)
-        e.read_psd_async(psd_h[b])
-        e.read_all_symbols_async(cnt_h[b], soft_h[b], hard_h[b], cap)
+    def run_e2e(eng, host_ptr, stride):
+        step_no = [0]
 
-    for _ in range(3):
-        step_e2e()
-    e.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    e.sync()
-    dt = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([dt], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_v = samples_step * world * args.steps / dt / 1e6
+        def step_e2e():
+            b = step_no[0] & 1
+            step_no[0] += 1
+            eng.feed_host_ptr(host_ptr, stride, n)
+            eng.read_psd_async(psd_h[b])
+            eng.read_all_symbols_async(cnt_h[b], soft_h[b], hard_h[b], cap)
+
+        for _ in range(3):
+            step_e2e()
+        eng.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        eng.sync()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return samples_step * world * args.steps / dt / 1e6
+
+    e2e_v = run_e2e(e, xh.data_ptr(), xh.stride(0))
     h2d = samples_step * 8
     d2h = psd_h[0].nbytes + cnt_h[0].nbytes + soft_h[0].nbytes + hard_h[0].nbytes
+
+    # ---- the same end-to-end loop with the IQ in native SDR sample formats (converted inside the first load):
+    # 4 and 2 bytes per complex sample over PCIe instead of 8.  Extra information; `e2e` above is float32.
+    e2e_fmt = {}
+    if not args.no_formats:
+        xr = torch.view_as_real(x)
+        for fmt, tdt, scale, off in (("s16", torch.int16, 32768.0, 0.0), ("u8", torch.uint8, 128.0, 128.0)):
+            lo, hi = (-32768, 32767) if fmt == "s16" else (0, 255)
+            q = torch.clamp(torch.round(xr * scale + off), lo, hi).to(tdt)
+            qh = torch.empty(q.shape, dtype=tdt, pin_memory=True)
+            qh.copy_(q)
+            del q
+            ef = sdb.Engine(n_streams=S, psd_size=N_FFT, psd_window="blackmann_harris", max_feed=n, samp_rate=FS,
+                            device=local, input_format=fmt)
+            for kind, f, baud, bw in workload_channels(name):
+                f0, bwa = chan_angular(f, bw)
+                hh = ef.open_channel(f0, bwa, 1.0)
+                cls, kw = insp_kwargs(kind, baud, ef.channel_rate(hh))
+                ef.set_inspector(hh, cls, **kw)
+            ef.commit()
+            e2e_fmt[fmt] = {"value": run_e2e(ef, qh.data_ptr(), n), "unit": "MS/s",
+                            "h2d_bytes_per_step": int(samples_step * (4 if fmt == "s16" else 2))}
+            ef.close()
+            del qh
 
     # ---- single-stream number (what one continuous source gets)
     single = None
@@ -375,7 +406,8 @@ def run_cuda(args):
                "dtype": "f32", "data": "synthetic", "config": workload_config(args, S, H),
                "clocks": clk.summary(), "gpu_launches": int(launches),
                "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-               "roofline": roofline, "cpu_baseline": cpu, "single_stream_msps": single}
+               "roofline": roofline, "cpu_baseline": cpu, "single_stream_msps": single,
+               "e2e_native_formats": e2e_fmt}
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -393,6 +425,7 @@ def main():
     ap.add_argument("--hops", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--no-formats", action="store_true")
     args = ap.parse_args()
     if args.streams == 0:
         args.streams = 1024 if args.workload == "cfg2" else 128

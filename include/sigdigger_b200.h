@@ -48,7 +48,13 @@ typedef struct {
   uint32_t max_feed;        /* largest per-stream feed, samples */
   int32_t  device;          /* CUDA ordinal */
   uint32_t flags;
+  int32_t  input_format;    /* SDB_FORMAT_*: layout of the IQ the feed calls receive */
 } sdb_engine_params;
+
+/* SUSCAN_SOURCE_FORMAT_RAW_{FLOAT32, UNSIGNED8, SIGNED8, SIGNED16} (Default/SourceConfig/FileSourcePage.cpp:80-104):
+ * interleaved I,Q pairs; 8/16-bit samples are converted inside the first load of the path (u8: (v-128)/128,
+ * s8: v/128, s16: v/32768), so an 8-bit source moves 4x fewer bytes over PCIe and HBM than float32. */
+enum { SDB_FORMAT_FLOAT32 = 0, SDB_FORMAT_UNSIGNED8 = 1, SDB_FORMAT_SIGNED8 = 2, SDB_FORMAT_SIGNED16 = 3 };
 
 /* Replaces struct sigutils_specttuner_channel_params {f0, bw, guard, precise}
  * (Tasks/LPFTask.cpp:63-67); angular units (rad/sample). */

@@ -119,7 +119,7 @@ void sdo_psd_frame_spec(const sdo_spec_plan *p, const float *window, const sdo_c
   unsigned i;
   sdo_spec_forward(p, x, window, scratch);
   for (i = 0; i < n; ++i)
-    psd[i] = (scratch[i].re * scratch[i].re + scratch[i].im * scratch[i].im) * inv_n;
+    psd[i] = fmaf(scratch[i].re, scratch[i].re, scratch[i].im * scratch[i].im) * inv_n;
 }
 
 /* Suscan/Messages/PSDMessage.cpp:32-38 -- swap halves and convert to dB in one pass. */

@@ -21,7 +21,11 @@ FLAG_PSD_SHIFT_DB = 1
 class EngineParams(C.Structure):
     _fields_ = [("n_streams", C.c_uint32), ("psd_size", C.c_uint32), ("psd_window", C.c_int32),
                 ("st_window_size", C.c_uint32), ("max_feed", C.c_uint32), ("device", C.c_int32),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32), ("input_format", C.c_int32)]
+
+
+FORMAT = {"f32": 0, "u8": 1, "s8": 2, "s16": 3}
+FORMAT_DTYPE = {0: np.complex64, 1: np.uint8, 2: np.int8, 3: np.int16}
 
 
 class ChannelParams(C.Structure):
@@ -163,10 +167,11 @@ class Engine:
     """Batch analyzer engine: main PSD + channeliser + inspectors over S streams on one GPU."""
 
     def __init__(self, n_streams=1, psd_size=65536, psd_window="blackmann_harris", st_window_size=0,
-                 max_feed=0, samp_rate=1.0, device=0, flags=0):
+                 max_feed=0, samp_rate=1.0, device=0, flags=0, input_format="f32"):
         L = load_library()
+        self.input_format = FORMAT[input_format] if isinstance(input_format, str) else int(input_format)
         p = EngineParams(n_streams, psd_size, WINDOW[psd_window] if isinstance(psd_window, str) else psd_window,
-                         st_window_size, max_feed, device, flags)
+                         st_window_size, max_feed, device, flags, self.input_format)
         self._L = L
         self.n_streams, self.psd_size, self.samp_rate = n_streams, psd_size, samp_rate
         self.st_window_size = st_window_size or psd_size
@@ -214,9 +219,15 @@ class Engine:
             assert x.is_cuda and x.dim() == 2 and x.shape[0] == self.n_streams
             assert x.stride(1) == 1
             _check(self._L.sdb_engine_feed_device(self._h, x.data_ptr(), x.stride(0), x.shape[1]))
-        else:
+        elif self.input_format == 0:
             x = np.ascontiguousarray(x, dtype=np.complex64)
             assert x.ndim == 2 and x.shape[0] == self.n_streams
+            self._keep = x
+            _check(self._L.sdb_engine_feed_host(self._h, x.ctypes.data, x.shape[1], x.shape[1]))
+        else:
+            # native SDR format: [S, n, 2] interleaved I, Q of dtype uint8 / int8 / int16
+            x = np.ascontiguousarray(x, dtype=FORMAT_DTYPE[self.input_format])
+            assert x.ndim == 3 and x.shape[0] == self.n_streams and x.shape[2] == 2
             self._keep = x
             _check(self._L.sdb_engine_feed_host(self._h, x.ctypes.data, x.shape[1], x.shape[1]))
         if sync:

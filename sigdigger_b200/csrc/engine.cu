@@ -71,7 +71,7 @@ struct sdb_engine {
   float2 *d_hist = nullptr;             // [S][W/2]
   float *d_psd = nullptr; size_t max_frames = 0, last_frames = 0;
   // channeliser
-  int *d_binmap = nullptr; int n_bins = 0;
+  int *d_binmap = nullptr; int n_bins = 0; unsigned ka_mask = 0;
   float2 *d_cspec = nullptr; size_t max_hops = 0;
   std::vector<SdbChannelDev> h_chans; SdbChannelDev *d_chans = nullptr;
   struct Group { int size; int len; int *d_ids; };
@@ -178,6 +178,9 @@ extern "C" sdb_engine_t *sdb_engine_new(const sdb_engine_params *p, double samp_
   }
   unsigned W = p->st_window_size ? p->st_window_size : p->psd_size;
   if (!is_pow2(W) || W < 64 || W > (1u << 20)) { g_err = "st_window_size must be a power of two in [64, 2^20]"; return nullptr; }
+  if (p->input_format < SDB_FORMAT_FLOAT32 || p->input_format > SDB_FORMAT_SIGNED16) {
+    g_err = "unknown input_format"; return nullptr;
+  }
   CKP(cudaSetDevice(p->device));
   sdb_engine *e = new sdb_engine();
   e->prm = *p; e->samp_rate = samp_rate; e->Np = p->psd_size; e->W = W;
@@ -396,6 +399,15 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       if (const char *env = getenv("SDB_SCRATCH_MB")) { long v = atol(env); if (v >= 1 && v <= 4096) scratch_mb = (size_t) v; }
       size_t cw = (scratch_mb << 20) / ((size_t) big * sizeof(float2));
       if (cw < 1) cw = 1;
+      if (big == 65536 && !getenv("SDB_SCRATCH_MB")) {
+        // 65536 path: 16 (pass A, 4 CTAs/SM) and 8 (pass B, 2 CTAs/SM) CTAs per window, all of equal duration:
+        // a chunk of one window per SM fills both kernels with exactly 4 waves (no partial last wave).
+        // 148 SMs -> 148 windows -> 74 MB of scratch, still inside the 126 MB L2.
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->prm.device) == cudaSuccess && sms > 0 &&
+            (size_t) sms * big * sizeof(float2) <= (100u << 20))
+          cw = (size_t) sms;
+      }
       e->chunk_windows = (int) cw;
       e->d_scratch = e->dalloc<float2>((size_t) e->chunk_windows * big);
       if (!e->d_scratch) return fail("out of device memory (scratch)");
@@ -410,7 +422,8 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     for (auto &c : e->channels)
       for (unsigned i = 0; i < 2 * c.halfw; ++i) need[(c.center + W - c.halfw + i) % W] = 1;
     int nb = 0;
-    for (unsigned b = 0; b < W; ++b) if (need[b]) binmap[b] = nb++;
+    e->ka_mask = 0;
+    for (unsigned b = 0; b < W; ++b) if (need[b]) { binmap[b] = nb++; e->ka_mask |= 1u << ((b >> 8) & 15u); }
     e->n_bins = nb;
     e->d_binmap = e->dalloc<int>(W);
     if (!e->d_binmap) return fail("out of device memory");
@@ -543,7 +556,9 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
   if (Np && n % Np) return fail("feed size must be a multiple of psd_size");
   if (K && n % (W / 2)) return fail("feed size must be a multiple of st_window_size / 2");
   CK(cudaSetDevice(e->prm.device));
-  const float2 *x = reinterpret_cast<const float2 *>(xv);
+  const void *x = reinterpret_cast<const void *>(xv);
+  const int fmt = e->prm.input_format;
+  const size_t bps = sdb_fmt_bytes(fmt);
   SdbLaunchCtx ctx{ e->stream, &e->launches };
   const int shift_db = (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) ? 1 : 0;
   const int ob = (int) (e->feed_index & 1u);     // result buffers of this feed
@@ -556,7 +571,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
     if (e->psd_read_valid[ob]) CK(cudaStreamWaitEvent(e->stream, e->ev_psd_read[ob], 0));   // async read of feed i-2
     if (e->psd_small) {
       e->span_begin(FAM_ROWS_PSD);
-      CK(sdb_launch_small_psd(ctx, (int) Np, e->twiddle(Np), x, stride, frames, (int) S, e->d_window,
+      CK(sdb_launch_small_psd(ctx, (int) Np, e->twiddle(Np), x, fmt, stride, frames, (int) S, e->d_window,
                               e->d_psd, shift_db));
       e->span_end();
     } else {
@@ -564,7 +579,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       for (int w0 = 0; w0 < total; w0 += e->chunk_windows) {
         const int cw = std::min(e->chunk_windows, total - w0);
         SdbPassAArgs a{};
-        a.x = x; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
+        a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
         a.windows_per_stream = frames; a.first_window = 0; a.hop = (int) Np; a.base_off = 0;
         a.window = e->d_window; a.scratch = e->d_scratch;
         const bool fast = e->fs_psd.N1 == 256 && e->fs_psd.N2 == 256;
@@ -594,7 +609,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       for (int w0 = 0; w0 < total; w0 += e->chunk_windows) {
         const int cw = std::min(e->chunk_windows, total - w0);
         SdbPassAArgs a{};
-        a.x = x; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
+        a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
         a.windows_per_stream = wps; a.first_window = first; a.hop = (int) (W / 2); a.base_off = 0;
         a.window = nullptr; a.scratch = e->d_scratch;
         const bool fast = e->fs_st.N1 == 256 && e->fs_st.N2 == 256;
@@ -604,7 +619,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
         e->span_end();
         SdbPassBArgs b{};
         b.scratch = e->d_scratch; b.n_windows = cw; b.binmap = e->d_binmap;
-        b.cspec = e->d_cspec + (size_t) w0 * e->n_bins; b.n_bins = e->n_bins;
+        b.cspec = e->d_cspec + (size_t) w0 * e->n_bins; b.n_bins = e->n_bins; b.ka_mask = e->ka_mask;
         e->span_begin(FAM_ROWS_CHAN);
         if (fast) CK(sdb_launch_rows256(ctx, e->fs_st, b, 1));
         else      CK(sdb_launch_pass_b_chan(ctx, e->fs_st, b));
@@ -642,8 +657,11 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       e->ev_insp_valid[ob] = true;
     }
     // keep the last half window of every stream as history for the next feed
-    CK(cudaMemcpy2DAsync(e->d_hist, (W / 2) * sizeof(float2), x + (n - W / 2), stride * sizeof(float2),
-                         (W / 2) * sizeof(float2), S, cudaMemcpyDeviceToDevice, e->stream));
+    if (fmt == SDB_FMT_F32)
+      CK(cudaMemcpy2DAsync(e->d_hist, (W / 2) * sizeof(float2), reinterpret_cast<const float2 *>(x) + (n - W / 2),
+                           stride * sizeof(float2), (W / 2) * sizeof(float2), S, cudaMemcpyDeviceToDevice, e->stream));
+    else
+      CK(sdb_launch_hist_convert(e->stream, x, fmt, stride, n - W / 2, e->d_hist, (int) (W / 2), (int) S));
     e->first_feed = false;
   }
   ++e->feed_index;
@@ -658,6 +676,7 @@ extern "C" int sdb_engine_feed_host(sdb_engine_t *e, const sdb_complex *x, size_
   CK(cudaSetDevice(e->prm.device));
   const unsigned S = e->prm.n_streams;
   const int hb = (int) (e->host_feeds & 1u);
+  const size_t bps = sdb_fmt_bytes(e->prm.input_format);
   if (!e->d_xinb[hb]) {
     e->d_xinb[hb] = e->dalloc<float2>((size_t) S * e->prm.max_feed);
     if (!e->d_xinb[hb]) return fail("out of device memory (input staging)");
@@ -666,9 +685,9 @@ extern "C" int sdb_engine_feed_host(sdb_engine_t *e, const sdb_complex *x, size_
   // the kernels of this feed wait for the copy.  Copies of consecutive feeds overlap compute.
   if (e->xfree_valid[hb]) CK(cudaStreamWaitEvent(e->h2d_stream, e->ev_xfree[hb], 0));
   if (stride == n)
-    CK(cudaMemcpyAsync(e->d_xinb[hb], x, (size_t) S * n * sizeof(float2), cudaMemcpyHostToDevice, e->h2d_stream));
+    CK(cudaMemcpyAsync(e->d_xinb[hb], x, (size_t) S * n * bps, cudaMemcpyHostToDevice, e->h2d_stream));
   else
-    CK(cudaMemcpy2DAsync(e->d_xinb[hb], n * sizeof(float2), x, stride * sizeof(float2), n * sizeof(float2), S,
+    CK(cudaMemcpy2DAsync(e->d_xinb[hb], n * bps, x, stride * bps, n * bps, S,
                          cudaMemcpyHostToDevice, e->h2d_stream));
   CK(cudaEventRecord(e->ev_h2d[hb], e->h2d_stream));
   CK(cudaStreamWaitEvent(e->stream, e->ev_h2d[hb], 0));

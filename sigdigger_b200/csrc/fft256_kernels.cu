@@ -19,9 +19,11 @@
 #define S1 0.38268343236508977173f   // sin(pi/8)
 #define R2 0.70710678118654752440f
 
+// SPEC F.1 twiddle product: one rounded product + one fused multiply-add per component (explicit, the
+// unit is compiled with -fmad=false so nothing else is contracted)
 static __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
 {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
 }
 static __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 static __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -56,7 +58,7 @@ static __device__ __forceinline__ void fft16(float2 (&v)[16])
 #define REV16(p) ((((p) >> 2)) | (((p) & 3) << 2))
 
 struct Cols256K {
-  const float2 *x; size_t stream_stride;
+  const void *x; int fmt; size_t stream_stride;
   const float2 *hist; int hist_len;
   int windows_per_stream, first_window, hop, base_off, win_base;
   const float *window;
@@ -80,15 +82,26 @@ __global__ void __launch_bounds__(256, 4) k_cols256(const Cols256K p)   // 64 re
   const int j0 = p.first_window + (w - stream * p.windows_per_stream);
   const int col = blockIdx.x * 16 + c;
   const long v0 = (long) p.base_off + (long) j0 * p.hop;
-  const float2 *__restrict__ xs = p.x + (size_t) stream * p.stream_stride;
+  const int fmt = p.fmt;
+  const char *__restrict__ xs = reinterpret_cast<const char *>(p.x) + (size_t) stream * p.stream_stride * sdb_fmt_bytes(fmt);
   const float2 *__restrict__ hs = p.hist ? p.hist + (size_t) stream * p.hist_len : nullptr;
 
   float2 v[16];
+  if (fmt == SDB_FMT_F32) {
+    const float2 *__restrict__ xf = reinterpret_cast<const float2 *>(xs);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int r = t + 16 * j;                       // row n1
-    const long vi = v0 + (long) r * 256 + col;
-    v[j] = vi < p.hist_len ? __ldg(hs + vi) : __ldg(xs + (vi - p.hist_len));
+    for (int j = 0; j < 16; ++j) {
+      const int r = t + 16 * j;                     // row n1
+      const long vi = v0 + (long) r * 256 + col;
+      v[j] = vi < p.hist_len ? __ldg(hs + vi) : __ldg(xf + (vi - p.hist_len));
+    }
+  } else {                                          // 8 / 16-bit SDR samples: converted in the load
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = t + 16 * j;
+      const long vi = v0 + (long) r * 256 + col;
+      v[j] = vi < p.hist_len ? __ldg(hs + vi) : sdb_ld_iq(xs, vi - p.hist_len, fmt);
+    }
   }
   if (p.window) {
 #pragma unroll
@@ -126,7 +139,7 @@ cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
                                const float2 *twfine, int win_base, int n_win)
 {
   Cols256K p;
-  p.x = a.x; p.stream_stride = a.stream_stride; p.hist = a.hist; p.hist_len = a.hist_len;
+  p.x = a.x; p.fmt = a.fmt; p.stream_stride = a.stream_stride; p.hist = a.hist; p.hist_len = a.hist_len;
   p.windows_per_stream = a.windows_per_stream; p.first_window = a.first_window; p.hop = a.hop;
   p.base_off = a.base_off; p.win_base = win_base; p.window = a.window; p.scratch = a.scratch;
   p.tw256 = fs.twN1; p.twfine = twfine;
@@ -142,6 +155,7 @@ struct Rows256K {
   float *psd; float inv_n; int shift_db;
   const int *binmap; float2 *cspec; int n_bins;
   const float2 *tw256;
+  unsigned ka_mask;
 };
 
 #define LDR 273
@@ -165,6 +179,8 @@ __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int ka = REV16(q);
+      // channeliser: output bin k = k1 + 256 (ka + 16 kb); digits ka no channel touches are never formed
+      if (MODE == 1 && !((p.ka_mask >> ka) & 1)) continue;
       float2 y = v[q];
       if (ka) y = cmulf(y, s_tw[t * ka]);
       smr[r * LDR + ka * 17 + t] = y;
@@ -173,6 +189,7 @@ __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
   __syncthreads();
   {
     const int r = tid & 31, ka = tid >> 5;          // a warp = 32 consecutive rows = 32 consecutive bins
+    if (MODE == 1 && !((p.ka_mask >> ka) & 1)) return;     // warp-uniform: this warp's 512 bins are unused
     float2 v[16];
 #pragma unroll
     for (int tt = 0; tt < 16; ++tt) v[tt] = smr[r * LDR + ka * 17 + tt];
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
       const int kb = REV16(q);
       const int k = k1_0 + r + 256 * (ka + 16 * kb);
       if (MODE == 0) {
-        float pw = (v[q].x * v[q].x + v[q].y * v[q].y) * p.inv_n;
+        float pw = __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y) * p.inv_n;
         float *__restrict__ psd = p.psd + (size_t) win * 65536;
         if (p.shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); psd[(k + 32768) & 65535] = pw; }
         else psd[k] = pw;
@@ -199,6 +216,7 @@ cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
   Rows256K p;
   p.scratch = a.scratch; p.psd = a.psd; p.inv_n = a.inv_n; p.shift_db = a.shift_db;
   p.binmap = a.binmap; p.cspec = a.cspec; p.n_bins = a.n_bins; p.tw256 = fs.twN2;
+  p.ka_mask = a.ka_mask ? a.ka_mask : 0xffffu;
   const size_t smem = (size_t) 32 * LDR * sizeof(float2);
   static bool attr_done = false;
   if (!attr_done) {

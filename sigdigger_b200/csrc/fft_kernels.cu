@@ -20,9 +20,10 @@
 #include "sdb_math.h"
 #include <math_constants.h>
 
+// SPEC F.1 twiddle product: one rounded product + one fused multiply-add per component
 static __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
 }
 static __device__ __forceinline__ float2 cmulc(float2 a, float2 b)  // a * conj(b)
 {
@@ -122,7 +123,8 @@ __global__ void __launch_bounds__(1024) k_pass_a(const PassAK p)
   const int j = p.a.first_window + (w - stream * p.a.windows_per_stream);
   const int col0 = blockIdx.x * CW;
   const long v0 = (long) p.a.base_off + (long) j * p.a.hop;
-  const float2 *__restrict__ xs = p.a.x + (size_t) stream * p.a.stream_stride;
+  const int fmt = p.a.fmt;
+  const char *__restrict__ xs = reinterpret_cast<const char *>(p.a.x) + (size_t) stream * p.a.stream_stride * sdb_fmt_bytes(fmt);
   const float2 *__restrict__ hs = p.a.hist ? p.a.hist + (size_t) stream * p.a.hist_len : nullptr;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int total = N1 * CW;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(1024) k_pass_a(const PassAK p)
   for (int idx = tid; idx < total; idx += nthreads) {
     const int r = idx / CW, c = idx - r * CW;
     const long vi = v0 + (long) r * N2 + col0 + c;
-    float2 val = vi < p.a.hist_len ? __ldg(hs + vi) : __ldg(xs + (vi - p.a.hist_len));
+    float2 val = vi < p.a.hist_len ? __ldg(hs + vi) : sdb_ld_iq(xs, vi - p.a.hist_len, fmt);
     if (p.a.window) {
       const float wv = __ldg(p.a.window + r * N2 + col0 + c);
       val.x *= wv; val.y *= wv;
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(1024) k_pass_b(const PassBK p)
       const int k2 = idx / RW, r = idx - k2 * RW;
       const float2 X = sm[r * LD + k2];
       const int k = k1_0 + r + N1 * k2;
-      float pw = (X.x * X.x + X.y * X.y) * p.a.inv_n;
+      float pw = __fmaf_rn(X.x, X.x, X.y * X.y) * p.a.inv_n;
       if (p.a.shift_db) {
         // Suscan/Messages/PSDMessage.cpp:32-38: swap halves, SU_POWER_DB
         pw = 10.0f * d_log10f(pw + 1e-8f);
@@ -266,16 +268,17 @@ cudaError_t sdb_launch_pass_b_chan(const SdbLaunchCtx &c, const SdbFourStep &fs,
 // small PSD: one CTA per frame, N <= 4096
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_small_psd(int N, int logN, const float2 *__restrict__ tw,
-                                                     const float2 *__restrict__ x, size_t stream_stride,
+                                                     const void *__restrict__ x, int fmt, size_t stream_stride,
                                                      int frames_per_stream, const float *__restrict__ window,
                                                      float *__restrict__ psd, int shift_db)
 {
   extern __shared__ float2 sm[];
   const int f = blockIdx.x;
   const int stream = f / frames_per_stream, fr = f - stream * frames_per_stream;
-  const float2 *__restrict__ in = x + (size_t) stream * stream_stride + (size_t) fr * N;
+  const char *__restrict__ in = reinterpret_cast<const char *>(x)
+                                + ((size_t) stream * stream_stride + (size_t) fr * N) * sdb_fmt_bytes(fmt);
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float2 v = __ldg(in + i);
+    float2 v = sdb_ld_iq(in, i, fmt);
     if (window) { const float w = __ldg(window + i); v.x *= w; v.y *= w; }
     sm[i] = v;
   }
@@ -286,20 +289,39 @@ __global__ void __launch_bounds__(1024) k_small_psd(int N, int logN, const float
   const int half = N >> 1;
   for (int k = threadIdx.x; k < N; k += blockDim.x) {
     const float2 X = sm[k];
-    float pw = (X.x * X.x + X.y * X.y) * inv_n;
+    float pw = __fmaf_rn(X.x, X.x, X.y * X.y) * inv_n;
     if (shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); out[(k + half) & (N - 1)] = pw; }
     else out[k] = pw;
   }
 }
 
-cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const float2 *x,
+cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const void *x, int fmt,
                                  size_t stream_stride, int frames_per_stream, int n_streams,
                                  const float *window, float *psd, int shift_db)
 {
   int threads = N / 4; if (threads < 32) threads = 32;
   k_small_psd<<<frames_per_stream * n_streams, threads, (size_t) N * sizeof(float2), c.stream>>>(
-      N, ilog2(N), tw, x, stream_stride, frames_per_stream, window, psd, shift_db);
+      N, ilog2(N), tw, x, fmt, stream_stride, frames_per_stream, window, psd, shift_db);
   if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}
+
+// last `hist_len` samples of every stream (starting at sample `offset`) -> complex float32 history
+__global__ void k_hist_convert(const void *__restrict__ x, int fmt, size_t stream_stride, size_t offset,
+                               float2 *__restrict__ hist, int hist_len)
+{
+  const int s = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hist_len) return;
+  const char *xs = reinterpret_cast<const char *>(x) + ((size_t) s * stream_stride + offset) * sdb_fmt_bytes(fmt);
+  hist[(size_t) s * hist_len + i] = sdb_ld_iq(xs, i, fmt);
+}
+
+cudaError_t sdb_launch_hist_convert(cudaStream_t s, const void *x, int fmt, size_t stream_stride, size_t offset,
+                                    float2 *hist, int hist_len, int n_streams)
+{
+  dim3 grid((hist_len + 255) / 256, n_streams);
+  k_hist_convert<<<grid, 256, 0, s>>>(x, fmt, stream_stride, offset, hist, hist_len);
   return cudaGetLastError();
 }
 

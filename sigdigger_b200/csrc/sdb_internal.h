@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include "sdb_iq.h"
 
 #define SDB_MAX_FIR      1024
 #define SDB_MAX_IIR      5        // coefficients (order <= 4)
@@ -20,8 +21,9 @@ struct SdbFourStep {
 };
 
 struct SdbPassAArgs {
-  const float2 *x;          // new samples, stream 0
-  size_t        stream_stride;
+  const void   *x;          // new samples, stream 0, in format `fmt` (sdb_iq.h)
+  int           fmt;
+  size_t        stream_stride;      // in samples
   const float2 *hist;       // [S][hist_len] samples preceding x (may be null when hist_len == 0)
   int           hist_len;
   int           windows_per_stream; // windows handled per stream in this launch
@@ -43,6 +45,7 @@ struct SdbPassBArgs {
   const int    *binmap;             // N entries, compact index or -1
   float2       *cspec;              // [n_windows][n_bins]
   int           n_bins;
+  unsigned      ka_mask;            // 65536 path: bit (k >> 8) & 15 set for every needed bin k (0 = all)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -147,7 +150,9 @@ cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
 cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a, int mode);
 cudaError_t sdb_launch_pass_b_psd(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a);
 cudaError_t sdb_launch_pass_b_chan(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a);
-cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const float2 *x,
+cudaError_t sdb_launch_hist_convert(cudaStream_t s, const void *x, int fmt, size_t stream_stride, size_t offset,
+                                    float2 *hist, int hist_len, int n_streams);
+cudaError_t sdb_launch_small_psd(const SdbLaunchCtx &c, int N, const float2 *tw, const void *x, int fmt,
                                  size_t stream_stride, int frames_per_stream, int n_streams,
                                  const float *window, float *psd, int shift_db);
 cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDev *chans_dev,

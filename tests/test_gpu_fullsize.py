@@ -70,6 +70,54 @@ def test_cfg2_full_size_batch(sdb, oracle):
         assert best[0] == 0, "stream %d: PRBS not recovered: %r" % (s, best)
 
 
+def test_cfg4_audio_path(sdb, oracle):
+    """configs[3]: 50 MS/s, 32768-pt spectrum + 8 audio channels (3 AM, 3 FM, 2 USB), 200 kHz wide
+    (Default/Audio/AudioProcessor.cpp:118-121) -> 256-pt IFFT, decimation 128, resampled to 44.1 kS/s."""
+    fs, Np, hops = 50e6, 32768, 40
+    n = hops * Np // 2
+    t = np.arange(n) / fs
+    tone = np.cos(2 * np.pi * 1000 * t)
+    x = synth.awgn(n, 10 ** (-60 / 20), np.random.default_rng(4))
+    demods, f_off = ["am"] * 3 + ["fm"] * 3 + ["usb"] * 2, []
+    for k, d in enumerate(demods):
+        f = (k - 3.5) * 2.0e6
+        f_off.append(f)
+        if d == "am":
+            s = (1 + 0.5 * tone) * 0.2
+        elif d == "fm":
+            s = 0.2 * np.exp(1j * 2 * np.pi * 5000 * np.cumsum(tone) / fs)
+        else:
+            s = 0.1 * (np.exp(2j * np.pi * 700 * t) + 0.5 * np.exp(2j * np.pi * 1900 * t))
+        x = x + s * np.exp(2j * np.pi * f * t)
+    x = x.astype(np.complex64)
+    e = sdb.Engine(n_streams=1, psd_size=Np, psd_window="blackmann_harris", max_feed=n, samp_rate=fs)
+    hs, ochans = [], []
+    for d, f in zip(demods, f_off):
+        f0 = float(np.float32(2 * np.pi * ((f / fs) % 1.0)))
+        bw = float(np.float32(2 * np.pi * 200e3 / fs))
+        h = e.open_channel(f0, bw, 1.0)
+        assert e.channel_info(h).size == 256 and e.channel_info(h).decimation == 128.0
+        kw = dict(audio_demod=sdb.AUDIO[d], audio_cutoff=5000.0, audio_sample_rate=44100, agc_enabled=1, agc_ts=0.0005,
+                  offset=1300.0, audio_squelch=0, audio_volume=1.0)
+        e.set_inspector(h, "audio", **kw)
+        hs.append(h)
+        ochans.append((f0, bw, 1.0, 0, oracle.insp_config("audio", e.channel_rate(h), **kw)))
+    e.commit()
+    e.feed(x[None, :])
+    ref = oracle.analyzer_run(oracle.make_an_params(Np, "blackmann_harris", ochans), x, want_chan=False)
+    assert np.array_equal(e.read_psd()[0].view(np.uint32), ref["psd"].view(np.uint32))
+    for i, h in enumerate(hs):
+        soft, _ = e.read_symbols(0, h)
+        assert abs(len(soft) - (n - Np // 2) / 128 * 44100 / 390625.0) <= 2
+        assert np.array_equal(soft.view(np.uint32), ref["soft"][i].view(np.uint32)), demods[i]
+        # the 1 kHz tone comes out of the AM and FM channels
+        if demods[i] in ("am", "fm"):
+            a = soft.real[200:]
+            spec = np.abs(np.fft.rfft((a - a.mean()) * np.hanning(len(a))))
+            fpk = np.argmax(spec[2:]) + 2
+            assert abs(fpk * 44100.0 / len(a) - 1000.0) < 150.0, (demods[i], fpk * 44100.0 / len(a))
+
+
 def test_cfg3_full_size_64_inspectors(sdb, oracle):
     """configs[2]: 200 MS/s, 65536-pt spectrum + 64 inspectors (2-FSK / QPSK / ASK mix) on a 3 MHz raster."""
     fs = 200e6

@@ -429,6 +429,54 @@ def test_pipeline_mixed_inspectors_streams_and_chunks(sdb, oracle):
     assert not failures, "\n".join(failures)
 
 
+@pytest.mark.parametrize("fmt", ["u8", "s8", "s16"])
+def test_native_sample_formats(sdb, oracle, fmt):
+    """8 / 16-bit SDR sample formats (Default/SourceConfig/FileSourcePage.cpp:80-104) converted inside the first
+    load (SPEC Q): identical to feeding the converted float32 samples, for PSD (small and four-step paths),
+    channeliser history across feeds, and symbols."""
+    N, hops, S = 65536 if fmt == "s16" else 8192, 10, 2
+    n = N // 2 * hops
+    baud = 1 / 100.
+    xs = []
+    for s in range(S):
+        xf, _ = synth.multi_carrier(n, 1.0, [("qpsk", 0.125 + 3e-6, baud, -8.0, {})], noise_db=-45.0, seed=60 + s)
+        xs.append(xf)
+    xf = np.stack(xs)
+    iq = np.stack([xf.real, xf.imag], axis=-1)
+    if fmt == "u8":
+        q = np.clip(np.rint(iq * 128.0 + 128.0), 0, 255).astype(np.uint8)
+        back = (q.astype(np.float32) - 128.0) / 128.0
+    elif fmt == "s8":
+        q = np.clip(np.rint(iq * 128.0), -128, 127).astype(np.int8)
+        back = q.astype(np.float32) / 128.0
+    else:
+        q = np.clip(np.rint(iq * 32768.0), -32768, 32767).astype(np.int16)
+        back = q.astype(np.float32) / 32768.0
+    xc = (back[..., 0] + 1j * back[..., 1]).astype(np.complex64)      # exactly what the kernels must see
+    f0, bw = 2 * np.pi * 0.125, 2 * np.pi * 3 * baud
+    e = sdb.Engine(n_streams=S, psd_size=N, psd_window="hann", max_feed=n, input_format=fmt)
+    h = e.open_channel(f0, bw, 1.0)
+    kw = dict(baud=baud, costas_order=2, bits_per_symbol=2, loop_bw=e.channel_rate(h) * 2e-3, mf_type=1,
+              clock_type=1, clock_gain=0.1)
+    e.set_inspector(h, "psk", **kw)
+    e.commit()
+    ic = oracle.insp_config("psk", e.channel_rate(h), **kw)
+    psd, soft, hard = [], [[] for _ in range(S)], [[] for _ in range(S)]
+    half = n // 2 // N * N
+    for seg in (slice(0, half), slice(half, n)):
+        e.feed(q[:, seg])
+        psd.append(e.read_psd().copy())
+        for s in range(S):
+            a, b = e.read_symbols(s, h)
+            soft[s].append(a)
+            hard[s].append(b)
+    for s in range(S):
+        ref = oracle.analyzer_run(oracle.make_an_params(N, "hann", [(f0, bw, 1.0, 0, ic)]), xc[s], want_chan=False)
+        assert np.array_equal(np.concatenate([p[s] for p in psd]).view(np.uint32), ref["psd"].view(np.uint32))
+        parity.assert_symbols_match(np.concatenate(soft[s]), np.concatenate(hard[s]), ref["soft"][0], ref["hard"][0],
+                                    exact_soft=True)
+
+
 def test_async_pipeline_matches_sync(sdb):
     """feed_host + read_*_async queued back to back (H2D / kernels / D2H of neighbouring feeds overlap,
     results double-buffered) must give exactly what feed + blocking reads give."""
