@@ -73,7 +73,8 @@ typedef struct {
  * afc.offset (AfcControl.cpp:54-83); fsk.bits-per-symbol, fsk.phase, fsk.quad-demod
  * (ToneControl.cpp:59-81); ask.bits-per-symbol, ask.use-pll, ask.loop-bw, ask.offset, ask.channel
  * (AskControl.cpp:53-77); mf.type, mf.roll-off (MfControl.cpp:56-78); clock.type, clock.baud,
- * clock.gain, clock.phase, clock.running (ClockRecovery.cpp:59-93); audio.* and agc.ts
+ * clock.gain, clock.phase, clock.running (ClockRecovery.cpp:59-93); equalizer.type, equalizer.rate,
+ * equalizer.locked (EqualizerControl.cpp:47-75); audio.* and agc.ts
  * (Default/Audio/AudioProcessor.cpp:257-265).  All under Default/GenericInspector/InspectorCtl/. */
 typedef struct {
   int32_t  insp_class;
@@ -96,6 +97,9 @@ typedef struct {
   float    audio_cutoff, audio_volume, audio_squelch_level, agc_ts;
   uint32_t audio_sample_rate, audio_demod;
   int32_t  audio_squelch;
+  uint32_t eq_type;         /* equalizer.type: SUSCAN_INSPECTOR_EQUALIZER_{BYPASS=0, CMA=1} (EqualizerControl.cpp:56-75) */
+  float    eq_rate;         /* equalizer.rate */
+  int32_t  eq_locked;       /* equalizer.locked */
 } sdb_inspector_config;
 
 const char *sdb_last_error(void);

@@ -476,6 +476,40 @@ int sdo_sampler_feed(sdo_sampler *s, sdo_cpx v, sdo_cpx *out)
   return sampled;
 }
 
+/* ------------------------------------------------------------------ E: CMA equaliser -------------
+ * equalizer.type / equalizer.rate / equalizer.locked (Default/GenericInspector/InspectorCtl/
+ * EqualizerControl.cpp:56-75); constant-modulus update on the symbol-rate stream, 10 complex weights. */
+void sdo_equalizer_init(sdo_equalizer *e, float mu, int locked)
+{
+  memset(e, 0, sizeof(*e));
+  e->mu = mu; e->locked = locked;
+  e->w[0].re = 1.0f;
+}
+
+sdo_cpx sdo_equalizer_feed(sdo_equalizer *e, sdo_cpx x)
+{
+  int i;
+  sdo_cpx y = { 0.0f, 0.0f };
+  for (i = SDO_EQ_LEN - 1; i > 0; --i) e->x[i] = e->x[i - 1];
+  e->x[0] = x;
+  for (i = 0; i < SDO_EQ_LEN; ++i) {
+    y.re = y.re + (e->w[i].re * e->x[i].re - e->w[i].im * e->x[i].im);
+    y.im = y.im + (e->w[i].re * e->x[i].im + e->w[i].im * e->x[i].re);
+  }
+  if (!e->locked) {
+    float y2 = y.re * y.re + y.im * y.im;
+    float er = y.re * (y2 - 1.0f), ei = y.im * (y2 - 1.0f);
+    for (i = 0; i < SDO_EQ_LEN; ++i) {
+      /* w -= mu * conj(x) * err */
+      float gr = e->x[i].re * er + e->x[i].im * ei;
+      float gi = e->x[i].re * ei - e->x[i].im * er;
+      e->w[i].re = e->w[i].re - e->mu * gr;
+      e->w[i].im = e->w[i].im - e->mu * gi;
+    }
+  }
+  return y;
+}
+
 /* ------------------------------------------------------------------ D: decider -------------------
  * ARGUMENT on [-pi, pi] for psk ("afc" prefix) and fsk, MODULUS on [0,1] for ask
  * (Default/GenericInspector/InspectorUI.cpp:228-253). */

@@ -32,6 +32,7 @@ struct sdo_inspector {
   sdo_filt   mf;
   sdo_clock  cd;
   sdo_sampler sampler;
+  sdo_equalizer eq;
   sdo_cpx    prev;        /* fsk / fm discriminator memory */
   sdo_cpx    fsk_rot;
   /* audio */
@@ -71,6 +72,9 @@ void sdo_insp_config_default(sdo_insp_config *c, int insp_class, float fs)
   c->audio_squelch = 0;
   c->audio_squelch_level = 0.0f;
   c->agc_ts = 0.1f;
+  c->eq_type = 0;
+  c->eq_rate = 1e-3f;
+  c->eq_locked = 0;
 }
 
 static float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -153,6 +157,7 @@ sdo_inspector *sdo_inspector_new(const sdo_insp_config *c)
     s->have_mf = 1;
   }
 
+  sdo_equalizer_init(&s->eq, c->eq_rate, c->eq_locked);
   sdo_clock_init(&s->cd, c->clock_gain, s->bnor);
   sdo_sampler_init(&s->sampler, s->bnor);
   sdo_sampler_set_phase(&s->sampler, c->clock_phase);
@@ -297,6 +302,9 @@ size_t sdo_inspector_feed(sdo_inspector *s, const sdo_cpx *x, size_t n, sdo_cpx 
 
     if (c->clock_type == 1) produced = sdo_clock_feed(&s->cd, y, &o);
     else                    produced = sdo_sampler_feed(&s->sampler, y, &o);
+
+    /* CMA equaliser on the symbol stream (manual p.50: "... sampler / CR -> CMA (opt) -> -2.5 dB") */
+    if (produced && c->eq_type == 1) o = sdo_equalizer_feed(&s->eq, o);
 
     if (produced && c->clock_running && k < cap) {
       out[k].re = 0.75f * o.re;

@@ -290,7 +290,17 @@ typedef struct {
   float    audio_cutoff, audio_volume, audio_squelch_level, agc_ts;
   unsigned audio_sample_rate, audio_demod;
   int      audio_squelch;
+  /* equalizer (Default/GenericInspector/InspectorCtl/EqualizerControl.cpp:56-75) */
+  unsigned eq_type;            /* equalizer.type: 0 bypass, 1 CMA */
+  float    eq_rate;            /* equalizer.rate (mu) */
+  int      eq_locked;          /* equalizer.locked: weights frozen */
 } sdo_insp_config;
+
+/* CMA equaliser (SPEC section E) */
+#define SDO_EQ_LEN 10
+typedef struct { float mu; int locked; sdo_cpx w[SDO_EQ_LEN], x[SDO_EQ_LEN]; } sdo_equalizer;
+void    sdo_equalizer_init(sdo_equalizer *e, float mu, int locked);
+sdo_cpx sdo_equalizer_feed(sdo_equalizer *e, sdo_cpx x);
 
 void sdo_insp_config_default(sdo_insp_config *c, int insp_class, float fs);
 

@@ -46,7 +46,8 @@ class InspectorConfig(C.Structure):
                 ("baud", C.c_float), ("clock_gain", C.c_float), ("clock_phase", C.c_float),
                 ("clock_running", C.c_int32), ("audio_cutoff", C.c_float), ("audio_volume", C.c_float),
                 ("audio_squelch_level", C.c_float), ("agc_ts", C.c_float),
-                ("audio_sample_rate", C.c_uint32), ("audio_demod", C.c_uint32), ("audio_squelch", C.c_int32)]
+                ("audio_sample_rate", C.c_uint32), ("audio_demod", C.c_uint32), ("audio_squelch", C.c_int32),
+                ("eq_type", C.c_uint32), ("eq_rate", C.c_float), ("eq_locked", C.c_int32)]
 
 
 _lib = None

@@ -254,7 +254,40 @@ struct ChainSmem {
   float2 mfh[MF_SLOTS][32];
   float  agc[48][32];
   float  lvl[CHUNK][32];
+  float2 eqw[SDB_EQ_LEN][32];     // CMA weights and line (SPEC E), one column per chain
+  float2 eqx[SDB_EQ_LEN][32];
 };
+
+// SPEC E: constant-modulus equaliser on the symbol stream.  Sums and updates run in index order.
+static __device__ __forceinline__ float2 cma_step(float2 (*w)[32], float2 (*x)[32], int lane, float mu,
+                                                  int locked, float2 in)
+{
+#pragma unroll
+  for (int i = SDB_EQ_LEN - 1; i > 0; --i) x[i][lane] = x[i - 1][lane];
+  x[0][lane] = in;
+  float yr = 0.0f, yi = 0.0f;
+#pragma unroll
+  for (int i = 0; i < SDB_EQ_LEN; ++i) {
+    const float2 wi = w[i][lane], xi = x[i][lane];
+    yr = yr + (wi.x * xi.x - wi.y * xi.y);
+    yi = yi + (wi.x * xi.y + wi.y * xi.x);
+  }
+  if (!locked) {
+    const float y2 = yr * yr + yi * yi;
+    const float er = yr * (y2 - 1.0f), ei = yi * (y2 - 1.0f);
+#pragma unroll
+    for (int i = 0; i < SDB_EQ_LEN; ++i) {
+      const float2 xi = x[i][lane];
+      float2 wi = w[i][lane];
+      const float gr = xi.x * er + xi.y * ei;
+      const float gi = xi.x * ei - xi.y * er;
+      wi.x = wi.x - mu * gr;
+      wi.y = wi.y - mu * gi;
+      w[i][lane] = wi;
+    }
+  }
+  return make_float2(yr, yi);
+}
 
 // Matched filter for mf_n <= 32 taps, NT = mf_n rounded up to a multiple of 8.  The line is kept twice
 // (slot p and p + mf_n, after a margin of 8 slots) so that x[n-t] is always at slot base - t: every
@@ -327,6 +360,7 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
   ClockS ks; float clk_gain = 0, clk_alpha = 0, clk_beta = 0, smp_period = 0, smp_phase0 = 0, s_phase = 0, s_pr = 0, s_pi = 0;
   int clock_type = 1, clock_running = 1, dec_mode = 0, dec_int = 1; float dec_min = 0, dec_h = 1;
   float avol = 1, rs_prev = 0; double rs_step = 0, rs_phase = 0;
+  int eq_type = 0, eq_locked = 0; float eq_mu = 0;
   uint32_t nout = 0;
 
   if (valid) {
@@ -399,6 +433,13 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       clock_type = cp->clock_type; clock_running = cp->clock_running;
       dec_mode = cp->dec_mode; dec_int = cp->dec_intervals; dec_min = cp->dec_min; dec_h = cp->dec_h;
       avol = cp->audio_volume; rs_prev = stp->rs_prev; rs_step = cp->rs_step; rs_phase = stp->rs_phase;
+      eq_type = cp->eq_type; eq_locked = cp->eq_locked; eq_mu = cp->eq_mu;
+      if (eq_type == 1) {
+        for (int i = 0; i < SDB_EQ_LEN; ++i) {
+          sm.eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
+          sm.eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
+        }
+      }
     }
   }
   float2 *__restrict__ so = soft + (size_t) chain * sym_cap;
@@ -628,6 +669,7 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
               bool produced;
               if (clock_type == 1) produced = clock_step(clk_gain, clk_alpha, clk_beta, ks, y, o);
               else                 produced = sampler_step(smp_period, smp_phase0, s_phase, s_pr, s_pi, y, o);
+              if (produced && eq_type == 1) o = cma_step(sm.eqw, sm.eqx, lane, eq_mu, eq_locked, o);
               if (produced && clock_running && nout < sym_cap) {
                 o.x = 0.75f * o.x; o.y = 0.75f * o.y;
                 so[nout] = o;
@@ -683,6 +725,12 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       stp->k_x1i = ks.x1i; stp->k_x2r = ks.x2r; stp->k_x2i = ks.x2i; stp->k_pr = ks.pr; stp->k_pi = ks.pi;
       stp->k_half = ks.half; stp->s_phase = s_phase; stp->s_pr = s_pr; stp->s_pi = s_pi;
       stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
+      if (eq_type == 1) {
+        for (int i = 0; i < SDB_EQ_LEN; ++i) {
+          stp->eq_wr[i] = sm.eqw[i][lane].x; stp->eq_wi[i] = sm.eqw[i][lane].y;
+          stp->eq_xr[i] = sm.eqx[i][lane].x; stp->eq_xi[i] = sm.eqx[i][lane].y;
+        }
+      }
       sym_counts[chain] = nout;
     }
   }

@@ -225,6 +225,7 @@ extern "C" int sdb_inspector_config_default(sdb_inspector_config *c, int insp_cl
   c->clock_type = 1; c->baud = fs * 0.25f; c->clock_gain = 1.0f; c->clock_phase = 0.0f; c->clock_running = 1;
   c->audio_cutoff = 5000.0f; c->audio_volume = 1.0f; c->audio_sample_rate = 44100;
   c->audio_demod = SDB_AUDIO_FM; c->agc_ts = 0.1f;
+  c->eq_type = 0; c->eq_rate = 1e-3f; c->eq_locked = 0;
   return 0;
 }
 
@@ -357,6 +358,8 @@ static bool build_chain_cfg(const Channel &ch, SdbChainCfg &c, std::vector<float
   else { c.dec_mode = 0; c.dec_min = -3.14159265358979323846f;
          c.dec_h = 3.14159265358979323846f - (-3.14159265358979323846f); }
   c.dec_intervals = 1 << g.bits_per_symbol;
+  c.eq_type = (int) g.eq_type; c.eq_locked = g.eq_locked; c.eq_mu = g.eq_rate;
+  if (g.eq_type > 1) return false;
   return true;
 }
 
@@ -527,7 +530,7 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       SdbChainState &s = st[ci];
       memset(&s, 0, sizeof(s));
       s.fast_level = s.slow_level = s.peak = -160.0f;
-      s.k_phi = 0.25f; s.k_bnor = c.bnor;
+      s.k_phi = 0.25f; s.k_bnor = c.bnor; s.eq_wr[0] = 1.0f;
     }
     CK(cudaMemcpy(e->d_state, st.data(), chains * sizeof(SdbChainState), cudaMemcpyHostToDevice));
     CK(cudaMemset(e->d_pool, 0, pool_floats * sizeof(float)));   // the kernel initialises its lines when `fresh`
@@ -976,7 +979,7 @@ extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_co
   for (size_t i = 0; i < batch; ++i) {
     memset(&st[i], 0, sizeof(SdbChainState));
     st[i].fast_level = st[i].slow_level = st[i].peak = -160.0f;
-    st[i].k_phi = 0.25f; st[i].k_bnor = c.bnor;
+    st[i].k_phi = 0.25f; st[i].k_bnor = c.bnor; st[i].eq_wr[0] = 1.0f;
   }
   struct Bufs { void *p[9] = {0}; ~Bufs() { for (auto q : p) cudaFree(q); } } b;
   float2 *d_src, *d_soft; uint8_t *d_hard; uint32_t *d_cnt; SdbChainCfg *d_cfg; SdbChainState *d_st;

@@ -9,6 +9,7 @@
 #define SDB_MAX_FIR      1024
 #define SDB_MAX_IIR      5        // coefficients (order <= 4)
 #define SDB_MAX_AGC_HIST 4096
+#define SDB_EQ_LEN       10
 
 // ---------------------------------------------------------------------------------------------
 // FFT plan pieces (fft_kernels.cu)
@@ -105,6 +106,9 @@ struct SdbChainCfg {
   int   alpf_n;
   float alpf_b[SDB_MAX_IIR], alpf_a[SDB_MAX_IIR];
   double rs_step;
+  // CMA equaliser (SPEC E)
+  int   eq_type, eq_locked;
+  float eq_mu;
   // per-chain state pool sizes (in floats) so the kernel can index the pools
   int   st_dl_off, st_mh_off, st_mf_off;  // offsets inside one chain's float pool
   int   st_pool;                           // floats per chain
@@ -134,6 +138,7 @@ struct SdbChainState {
   unsigned al_xp, al_yp;
   double rs_phase;
   int   fm_primed;
+  float eq_wr[SDB_EQ_LEN], eq_wi[SDB_EQ_LEN], eq_xr[SDB_EQ_LEN], eq_xi[SDB_EQ_LEN];
 };
 
 // host-callable launchers ----------------------------------------------------------------------

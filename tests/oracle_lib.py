@@ -97,7 +97,8 @@ class InspConfig(C.Structure):
                 ("baud", C.c_float), ("clock_gain", C.c_float), ("clock_phase", C.c_float),
                 ("clock_running", C.c_int), ("audio_cutoff", C.c_float), ("audio_volume", C.c_float),
                 ("audio_squelch_level", C.c_float), ("agc_ts", C.c_float),
-                ("audio_sample_rate", C.c_uint), ("audio_demod", C.c_uint), ("audio_squelch", C.c_int)]
+                ("audio_sample_rate", C.c_uint), ("audio_demod", C.c_uint), ("audio_squelch", C.c_int),
+                ("eq_type", C.c_uint), ("eq_rate", C.c_float), ("eq_locked", C.c_int)]
 
 
 class AnChannel(C.Structure):

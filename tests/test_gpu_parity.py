@@ -181,6 +181,24 @@ def test_psk_chain_variants_bit_exact(sdb, oracle, kw):
     parity.assert_symbols_match(soft, hard, rs, rh, exact_soft=True)
 
 
+@pytest.mark.parametrize("locked,rate", [(0, 1e-3), (0, 2e-2), (1, 1e-3)])
+def test_psk_chain_cma_bit_exact(sdb, oracle, locked, rate):
+    """SPEC E: CMA equaliser after the clock recovery, multipath capture, across two feeds (state kept)."""
+    fs, sps, n = 1.0, 4.0, 24000
+    x = _psk_capture(n, sps, 4, seed=21)
+    x = (x + 0.35 * np.exp(0.7j) * np.roll(x, 3) - 0.2j * np.roll(x, 9)).astype(np.complex64)
+    kw = dict(baud=fs / sps, costas_order=2, bits_per_symbol=2, loop_bw=fs * 1e-3, mf_type=1, clock_type=1,
+              clock_gain=0.1, eq_type=1, eq_rate=rate, eq_locked=locked)
+    (soft, hard), = sdb.inspector_run("psk", fs, x, **kw)
+    rs, rh = oracle.inspector_run(oracle.insp_config("psk", fs, **kw), x)
+    assert len(rs) > n / sps * 0.9
+    parity.assert_symbols_match(soft, hard, rs, rh, exact_soft=True)
+    if not locked:   # the equaliser does something: the output differs from the unequalised chain
+        kw0 = dict(kw, eq_type=0)
+        (soft0, _), = sdb.inspector_run("psk", fs, x, **kw0)
+        assert not np.array_equal(soft0.view(np.uint32), soft.view(np.uint32))
+
+
 @pytest.mark.parametrize("quad", [0, 1])
 def test_fsk_chain_bit_exact(sdb, oracle, quad):
     fs, sps, n = 1.0, 5.0, 30000

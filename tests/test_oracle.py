@@ -230,6 +230,29 @@ def test_gardner_recovers_prbs_exactly(oracle):
     assert np.array_equal(soft.view(np.uint32), soft2.view(np.uint32)) and np.array_equal(hard, hard2)
 
 
+def test_cma_equalizer_restores_constant_modulus(oracle):
+    """SPEC E: two-ray multipath QPSK; CMA shrinks the modulus spread and settles on |y| = 1 (0.75 after
+    the -2.5 dB output gain); eq_locked freezes the identity weights, i.e. passes the symbols through."""
+    fs, sps, n = 1.0, 4.0, 160000
+    s, _ = synth.psk_signal(n, sps, order=4, seed=8)
+    rng = np.random.default_rng(8)
+    x = 0.25 * (s + 0.3 * np.exp(0.9j) * np.roll(s, 4)) + synth.awgn(n, 10 ** (-50 / 20), rng)
+    x = x.astype(np.complex64)
+    kw = dict(baud=fs / sps, costas_order=2, bits_per_symbol=2, loop_bw=fs * 1e-3, mf_type=1, clock_type=1,
+              clock_gain=0.05)
+    off, _ = oracle.inspector_run(oracle.insp_config("psk", fs, **kw), x)
+    on, _ = oracle.inspector_run(oracle.insp_config("psk", fs, eq_type=1, eq_rate=5e-3, **kw), x)
+    lock, _ = oracle.inspector_run(oracle.insp_config("psk", fs, eq_type=1, eq_rate=5e-3, eq_locked=1, **kw), x)
+    assert len(on) == len(off) == len(lock)
+    assert np.array_equal(lock.view(np.uint32), off.view(np.uint32))
+    t = len(on) * 2 // 3
+    spread_off, spread_on = np.std(np.abs(off[t:])), np.std(np.abs(on[t:]))
+    assert spread_on < 0.6 * spread_off, (spread_on, spread_off)
+    # CMA's fixed point has E|y|^4 = E|y|^2, i.e. |y| ~ 1 before the 0.75 gain
+    m2, m4 = np.mean(np.abs(on[t:] / 0.75) ** 2), np.mean(np.abs(on[t:] / 0.75) ** 4)
+    assert abs(m4 / m2 - 1.0) < 0.05
+
+
 def test_decider_intervals(oracle):
     L = oracle.lib()
     d = oracle.Decider()
