@@ -66,7 +66,11 @@ struct sdb_engine {
   SdbFourStep fs_psd{}, fs_st{};
   bool psd_small = false;
   float *d_window = nullptr;
-  float2 *d_scratch = nullptr; int chunk_windows = 1;
+  float2 *d_scratch = nullptr; int chunk_windows = 1; size_t l2_pinned_bytes = 0;
+  // The PSD transforms run on their own stream, concurrently with the channeliser transforms of the same
+  // group of streams (feed_device): the two kernel chains fill each other's launch gaps and partial waves,
+  // and both read the same input region while it is still in L2.
+  cudaStream_t psd_stream = nullptr; cudaEvent_t ev_feed = nullptr;
   float2 *d_xin = nullptr;              // staging for host feeds
   float2 *d_hist = nullptr;             // [S][W/2]
   float *d_psd = nullptr; size_t max_frames = 0, last_frames = 0;
@@ -165,7 +169,29 @@ static bool make_four_step(sdb_engine *e, unsigned N, SdbFourStep *fs)
   int l = ilog2u(N), l1 = l / 2;
   fs->N = (int) N; fs->N1 = 1 << l1; fs->N2 = (int) N / fs->N1;
   fs->twN1 = e->twiddle(fs->N1); fs->twN2 = e->twiddle(fs->N2); fs->twN = e->twiddle(N);
-  return fs->twN1 && fs->twN2 && fs->twN;
+  fs->twPQ = nullptr;
+  if (!(fs->twN1 && fs->twN2 && fs->twN)) return false;
+  if (N == 65536) {
+    // the product the kernels used to form per output (two table look-ups + one complex multiply), tabulated
+    // once with the same arithmetic (SPEC F.1: one rounded product + one fused multiply-add per component)
+    auto it = e->tw.find(0x10000u | 1u);
+    if (it != e->tw.end()) { fs->twPQ = it->second; return true; }
+    std::vector<float2> c, f, pq((size_t) 65536);
+    sdbh::twiddle_fill(256, c); sdbh::twiddle_fill(65536, f);
+    for (unsigned k1 = 0; k1 < 256; ++k1)
+      for (unsigned n2 = 0; n2 < 256; ++n2) {
+        const unsigned p = n2 * k1;
+        const float2 a = c[p >> 8], b = f[p & 255];
+        pq[(size_t) k1 * 256 + n2].x = fmaf(a.x, b.x, -(a.y * b.y));
+        pq[(size_t) k1 * 256 + n2].y = fmaf(a.x, b.y, a.y * b.x);
+      }
+    float2 *d = e->dalloc<float2>(65536);
+    if (!d) return false;
+    cudaMemcpy(d, pq.data(), 65536 * sizeof(float2), cudaMemcpyHostToDevice);
+    e->tw[0x10000u | 1u] = d;
+    fs->twPQ = d;
+  }
+  return true;
 }
 
 extern "C" sdb_engine_t *sdb_engine_new(const sdb_engine_params *p, double samp_rate)
@@ -197,12 +223,15 @@ extern "C" void sdb_engine_destroy(sdb_engine_t *e)
   cudaStreamSynchronize(e->stream);
   if (e->insp_stream) cudaStreamSynchronize(e->insp_stream);
   e->collect_spans();
+  if (e->l2_pinned_bytes) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
   for (void *p : e->allocs) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (e->ev_chan[i]) cudaEventDestroy(e->ev_chan[i]);
     if (e->ev_insp[i]) cudaEventDestroy(e->ev_insp[i]);
   }
   if (e->insp_stream) cudaStreamDestroy(e->insp_stream);
+  if (e->psd_stream) { cudaStreamSynchronize(e->psd_stream); cudaStreamDestroy(e->psd_stream); }
+  if (e->ev_feed) cudaEventDestroy(e->ev_feed);
   if (e->h2d_stream) { cudaStreamSynchronize(e->h2d_stream); cudaStreamDestroy(e->h2d_stream); }
   if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
   for (int i = 0; i < 2; ++i)
@@ -394,26 +423,57 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     }
     e->d_psd = e->d_psdb[0];
   }
-  // ---- scratch sized to stay inside L2 (126 MB): 32 MB
+  // ---- four-step scratch: one window per SM, pinned in L2
   {
     unsigned big = std::max(Np > 4096 ? Np : 0u, K > 0 ? W : 0u);
     if (big) {
-      size_t scratch_mb = 64;   // measured: 32 MB 39.5, 64 MB 41.7, 96 MB 43.2 GS/s (cfg2); stays inside the 126 MB L2
+      size_t scratch_mb = 64;
       if (const char *env = getenv("SDB_SCRATCH_MB")) { long v = atol(env); if (v >= 1 && v <= 4096) scratch_mb = (size_t) v; }
       size_t cw = (scratch_mb << 20) / ((size_t) big * sizeof(float2));
       if (cw < 1) cw = 1;
       if (big == 65536 && !getenv("SDB_SCRATCH_MB")) {
         // 65536 path: 16 (pass A, 4 CTAs/SM) and 8 (pass B, 2 CTAs/SM) CTAs per window, all of equal duration:
-        // a chunk of one window per SM fills both kernels with exactly 4 waves (no partial last wave).
-        // 148 SMs -> 148 windows -> 74 MB of scratch, still inside the 126 MB L2.
+        // one window per SM is exactly 4 waves of either kernel.  148 SMs -> 148 windows -> 77.6 MB, inside
+        // the 82.9 MB of L2 that can be set aside for persisting lines on B200.
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->prm.device) == cudaSuccess && sms > 0 &&
             (size_t) sms * big * sizeof(float2) <= (100u << 20))
           cw = (size_t) sms;
       }
+      if (const char *env = getenv("SDB_CHUNK_WINDOWS")) { long v = atol(env); if (v >= 1 && v <= 65536) cw = (size_t) v; }
       e->chunk_windows = (int) cw;
       e->d_scratch = e->dalloc<float2>((size_t) e->chunk_windows * big);
       if (!e->d_scratch) return fail("out of device memory (scratch)");
+      if (Np > 4096 && K > 0 && Np == W && !getenv("SDB_NO_PSD_STREAM")) {
+        CK(cudaStreamCreateWithFlags(&e->psd_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_feed, cudaEventDisableTiming));
+      }
+      // Pin the scratch in L2.  Without this the streamed input and output evict it between the two passes
+      // and every window costs two extra HBM round trips (ncu: 266 MB of DRAM traffic per 148-window chunk
+      // against 116 MB algorithmic, profiles/r02_l2.md).  Accesses of the transform streams inside the window
+      // are "persisting" (a set-aside part of L2 that normal traffic cannot evict); the kernels additionally
+      // mark their one-shot outputs as streaming (st.global.cs).
+      if (!getenv("SDB_NO_L2_PIN")) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->prm.device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->prm.device);
+        const size_t bytes = (size_t) e->chunk_windows * big * sizeof(float2);
+        if (max_persist > 0 && max_window > 0) {
+          const size_t set_aside = std::min(bytes, (size_t) max_persist);
+          if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = e->d_scratch;
+            av.accessPolicyWindow.num_bytes = std::min(bytes, (size_t) max_window);
+            av.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) set_aside / (double) av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess)
+              e->l2_pinned_bytes = set_aside;
+            if (e->psd_stream) cudaStreamSetAttribute(e->psd_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+          }
+          cudaGetLastError();   // the pin is an optimisation: never fail the commit because of it
+        }
+      }
     }
   }
   // ---- channeliser plan
@@ -566,68 +626,100 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
   const int shift_db = (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) ? 1 : 0;
   const int ob = (int) (e->feed_index & 1u);     // result buffers of this feed
 
-  // ---- main PSD
+  // transform launchers: windows [w0, w0 + cw) of the flattened [stream][window] order, scratch region `scr`
+  auto psd_chunk = [&](const SdbLaunchCtx &lc, int frames, int w0, int cw, float2 *scr) -> int {
+    SdbPassAArgs a{};
+    a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
+    a.windows_per_stream = frames; a.first_window = 0; a.hop = (int) Np; a.base_off = 0;
+    a.window = e->d_window; a.scratch = scr;
+    const bool fast = e->fs_psd.N1 == 256 && e->fs_psd.N2 == 256;
+    e->span_begin(FAM_COLS, lc.stream);
+    if (fast) CK(sdb_launch_cols256(lc, e->fs_psd, a, e->fs_psd.twN, w0, cw));
+    else      CK(sdb_launch_pass_a_range(lc, e->fs_psd, a, w0, cw));
+    e->span_end(lc.stream);
+    SdbPassBArgs b{};
+    b.scratch = scr; b.n_windows = cw; b.psd = e->d_psd + (size_t) w0 * Np;
+    b.inv_n = 1.0f / (float) Np; b.shift_db = shift_db;
+    e->span_begin(FAM_ROWS_PSD, lc.stream);
+    if (fast) CK(sdb_launch_rows256(lc, e->fs_psd, b, 0));
+    else      CK(sdb_launch_pass_b_psd(lc, e->fs_psd, b));
+    e->span_end(lc.stream);
+    return 0;
+  };
+  auto chan_chunk = [&](const SdbLaunchCtx &lc, int wps, int first, int w0, int cw, float2 *scr) -> int {
+    SdbPassAArgs a{};
+    a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
+    a.windows_per_stream = wps; a.first_window = first; a.hop = (int) (W / 2); a.base_off = 0;
+    a.window = nullptr; a.scratch = scr;
+    const bool fast = e->fs_st.N1 == 256 && e->fs_st.N2 == 256;
+    e->span_begin(FAM_COLS, lc.stream);
+    if (fast) CK(sdb_launch_cols256(lc, e->fs_st, a, e->fs_st.twN, w0, cw));
+    else      CK(sdb_launch_pass_a_range(lc, e->fs_st, a, w0, cw));
+    e->span_end(lc.stream);
+    SdbPassBArgs b{};
+    b.scratch = scr; b.n_windows = cw; b.binmap = e->d_binmap;
+    b.cspec = e->d_cspec + (size_t) w0 * e->n_bins; b.n_bins = e->n_bins; b.ka_mask = e->ka_mask;
+    e->span_begin(FAM_ROWS_CHAN, lc.stream);
+    if (fast) CK(sdb_launch_rows256(lc, e->fs_st, b, 1));
+    else      CK(sdb_launch_pass_b_chan(lc, e->fs_st, b));
+    e->span_end(lc.stream);
+    return 0;
+  };
+
+  const int frames = Np ? (int) (n / Np) : 0;
+  const int H = K ? (int) (n / (W / 2)) : 0;
+  const int first = (K && e->first_feed) ? 1 : 0;
+  const int wps = K ? H - first : 0;
+  // Stream groups: G whole streams per step, PSD frames on psd_stream and channeliser windows on the main stream,
+  // each with its own part of the pinned scratch (G * (frames + wps) windows <= chunk_windows).
+  int G = 0;
+  if (e->psd_stream && Np && !e->psd_small && wps > 0) G = e->chunk_windows / (frames + wps);
+  if (G > (int) S) G = (int) S;
+
   if (Np) {
-    const int frames = (int) (n / Np);
     e->last_frames = frames;
     e->d_psd = e->d_psdb[ob];
-    if (e->psd_read_valid[ob]) CK(cudaStreamWaitEvent(e->stream, e->ev_psd_read[ob], 0));   // async read of feed i-2
-    if (e->psd_small) {
-      e->span_begin(FAM_ROWS_PSD);
-      CK(sdb_launch_small_psd(ctx, (int) Np, e->twiddle(Np), x, fmt, stride, frames, (int) S, e->d_window,
-                              e->d_psd, shift_db));
-      e->span_end();
-    } else {
-      const int total = frames * (int) S;
-      for (int w0 = 0; w0 < total; w0 += e->chunk_windows) {
-        const int cw = std::min(e->chunk_windows, total - w0);
-        SdbPassAArgs a{};
-        a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
-        a.windows_per_stream = frames; a.first_window = 0; a.hop = (int) Np; a.base_off = 0;
-        a.window = e->d_window; a.scratch = e->d_scratch;
-        const bool fast = e->fs_psd.N1 == 256 && e->fs_psd.N2 == 256;
-        e->span_begin(FAM_COLS);
-        if (fast) CK(sdb_launch_cols256(ctx, e->fs_psd, a, e->fs_psd.twN, w0, cw));
-        else      CK(sdb_launch_pass_a_range(ctx, e->fs_psd, a, w0, cw));
-        e->span_end();
-        SdbPassBArgs b{};
-        b.scratch = e->d_scratch; b.n_windows = cw; b.psd = e->d_psd + (size_t) w0 * Np;
-        b.inv_n = 1.0f / (float) Np; b.shift_db = shift_db;
-        e->span_begin(FAM_ROWS_PSD);
-        if (fast) CK(sdb_launch_rows256(ctx, e->fs_psd, b, 0));
-        else      CK(sdb_launch_pass_b_psd(ctx, e->fs_psd, b));
-        e->span_end();
-      }
-    }
-    CK(cudaEventRecord(e->ev_psd_ready[ob], e->stream));
   }
-  // ---- channeliser + inspectors
+  if (G >= 1) {
+    SdbLaunchCtx pctx{ e->psd_stream, &e->launches };
+    CK(cudaEventRecord(e->ev_feed, e->stream));              // the input is valid from here on
+    CK(cudaStreamWaitEvent(e->psd_stream, e->ev_feed, 0));
+    if (e->psd_read_valid[ob]) CK(cudaStreamWaitEvent(e->psd_stream, e->ev_psd_read[ob], 0));   // async read of feed i-2
+    float2 *scr_psd = e->d_scratch, *scr_ch = e->d_scratch + (size_t) G * frames * Np;
+    for (int s0 = 0; s0 < (int) S; s0 += G) {
+      const int g = std::min(G, (int) S - s0);
+      if (psd_chunk(pctx, frames, s0 * frames, g * frames, scr_psd)) return -1;
+      if (chan_chunk(ctx, wps, first, s0 * wps, g * wps, scr_ch)) return -1;
+    }
+    CK(cudaEventRecord(e->ev_psd_ready[ob], e->psd_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_psd_ready[ob], 0));   // the main stream stays the engine's timeline
+  } else {
+    // ---- main PSD
+    if (Np) {
+      if (e->psd_read_valid[ob]) CK(cudaStreamWaitEvent(e->stream, e->ev_psd_read[ob], 0));   // async read of feed i-2
+      if (e->psd_small) {
+        e->span_begin(FAM_ROWS_PSD);
+        CK(sdb_launch_small_psd(ctx, (int) Np, e->twiddle(Np), x, fmt, stride, frames, (int) S, e->d_window,
+                                e->d_psd, shift_db));
+        e->span_end();
+      } else {
+        const int total = frames * (int) S;
+        for (int w0 = 0; w0 < total; w0 += e->chunk_windows)
+          if (psd_chunk(ctx, frames, w0, std::min(e->chunk_windows, total - w0), e->d_scratch)) return -1;
+      }
+      CK(cudaEventRecord(e->ev_psd_ready[ob], e->stream));
+    }
+    // ---- channeliser forward transforms
+    if (K && wps > 0) {
+      const int total = wps * (int) S;
+      for (int w0 = 0; w0 < total; w0 += e->chunk_windows)
+        if (chan_chunk(ctx, wps, first, w0, std::min(e->chunk_windows, total - w0), e->d_scratch)) return -1;
+    }
+  }
+  // ---- per-channel inverse transforms + inspectors
   if (K) {
-    const int H = (int) (n / (W / 2));
-    const int first = e->first_feed ? 1 : 0;
-    const int wps = H - first;
     e->last_hops = wps > 0 ? wps : 0;
     if (wps > 0) {
-      const int total = wps * (int) S;
-      for (int w0 = 0; w0 < total; w0 += e->chunk_windows) {
-        const int cw = std::min(e->chunk_windows, total - w0);
-        SdbPassAArgs a{};
-        a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
-        a.windows_per_stream = wps; a.first_window = first; a.hop = (int) (W / 2); a.base_off = 0;
-        a.window = nullptr; a.scratch = e->d_scratch;
-        const bool fast = e->fs_st.N1 == 256 && e->fs_st.N2 == 256;
-        e->span_begin(FAM_COLS);
-        if (fast) CK(sdb_launch_cols256(ctx, e->fs_st, a, e->fs_st.twN, w0, cw));
-        else      CK(sdb_launch_pass_a_range(ctx, e->fs_st, a, w0, cw));
-        e->span_end();
-        SdbPassBArgs b{};
-        b.scratch = e->d_scratch; b.n_windows = cw; b.binmap = e->d_binmap;
-        b.cspec = e->d_cspec + (size_t) w0 * e->n_bins; b.n_bins = e->n_bins; b.ka_mask = e->ka_mask;
-        e->span_begin(FAM_ROWS_CHAN);
-        if (fast) CK(sdb_launch_rows256(ctx, e->fs_st, b, 1));
-        else      CK(sdb_launch_pass_b_chan(ctx, e->fs_st, b));
-        e->span_end();
-      }
       const int b = (int) (e->feed_index & 1u);
       e->last_buf = b;
       // buffer b was last read by the inspector launch of feed i-2

@@ -14,27 +14,14 @@
 // (Tasks/LPFTask.cpp:83-87) and of the PSD (Suscan/Messages/PSDMessage.cpp:26-39).
 #include "sdb_internal.h"
 #include "sdb_math.h"
+#include "sdb_cpx.h"
 
 #define C1 0.92387953251128675613f   // cos(pi/8)
 #define S1 0.38268343236508977173f   // sin(pi/8)
 #define R2 0.70710678118654752440f
 
-// SPEC F.1 twiddle product: one rounded product + one fused multiply-add per component (explicit, the
-// unit is compiled with -fmad=false so nothing else is contracted)
-static __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
-{
-  return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
-}
-static __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-static __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-static __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
-
-// forward 4-point DFT in place: (a, b, c, d) <- DFT4
-static __device__ __forceinline__ void fft4(float2 &a, float2 &b, float2 &c, float2 &d)
-{
-  const float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = mul_mi(csub(b, d));
-  a = cadd(s0, s1); b = cadd(d0, d1); c = csub(s0, s1); d = csub(d0, d1);
-}
+// complex arithmetic (cadd, csub, cmulf = SPEC F.1 twiddle product, fft4) on the packed FP32x2 pipe:
+// sdb_cpx.h.  The unit is compiled with -fmad=false so nothing else is contracted.
 
 // forward 16-point DFT of v[0..15] (natural order in).  Result X[m + 4 q] is left in v[4 m + q].
 static __device__ __forceinline__ void fft16(float2 (&v)[16])
@@ -65,6 +52,7 @@ struct Cols256K {
   float2 *scratch;
   const float2 *tw256;     // W_256^i
   const float2 *twfine;    // W_65536^i, i < 256
+  const float2 *twpq;      // tabulated inter-pass twiddle [k1][n2]
 };
 
 #define LDC 273    // pitch of one column's [ka][17] block (odd: conflict-free across columns)
@@ -72,10 +60,9 @@ struct Cols256K {
 __global__ void __launch_bounds__(256, 4) k_cols256(const Cols256K p)   // 64 regs, 39 KB smem -> 4 CTAs / SM
 {
   __shared__ float2 sm[16 * LDC];
-  __shared__ float2 s_tw[256], s_fine[256];
+  __shared__ float2 s_tw[256];
   const int tid = threadIdx.x;
   s_tw[tid] = __ldg(p.tw256 + tid);
-  s_fine[tid] = __ldg(p.twfine + tid);
   const int c = tid & 15, t = tid >> 4;
   const int w = p.win_base + blockIdx.y;
   const int stream = w / p.windows_per_stream;
@@ -89,11 +76,17 @@ __global__ void __launch_bounds__(256, 4) k_cols256(const Cols256K p)   // 64 re
   float2 v[16];
   if (fmt == SDB_FMT_F32) {
     const float2 *__restrict__ xf = reinterpret_cast<const float2 *>(xs);
+    if (v0 >= p.hist_len) {                         // CTA-uniform: the window lies wholly in the new samples
+      const float2 *__restrict__ src = xf + (v0 - p.hist_len) + t * 256 + col;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int r = t + 16 * j;                     // row n1
-      const long vi = v0 + (long) r * 256 + col;
-      v[j] = vi < p.hist_len ? __ldg(hs + vi) : __ldg(xf + (vi - p.hist_len));
+      for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j * 4096);    // row n1 = t + 16 j
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = t + 16 * j;
+        const long vi = v0 + (long) r * 256 + col;
+        v[j] = vi < p.hist_len ? __ldg(hs + vi) : __ldg(xf + (vi - p.hist_len));
+      }
     }
   } else {                                          // 8 / 16-bit SDR samples: converted in the load
 #pragma unroll
@@ -107,7 +100,7 @@ __global__ void __launch_bounds__(256, 4) k_cols256(const Cols256K p)   // 64 re
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float wv = __ldg(p.window + (t + 16 * j) * 256 + col);
-      v[j].x *= wv; v[j].y *= wv;
+      v[j] = sdb_mul2(v[j], make_float2(wv, wv));
     }
   }
   fft16(v);                                         // over j: Y[t][ka], ka = REV16(position)
@@ -129,9 +122,7 @@ __global__ void __launch_bounds__(256, 4) k_cols256(const Cols256K p)   // 64 re
   for (int q = 0; q < 16; ++q) {
     const int kb = REV16(q);
     const int k1 = ka + 16 * kb;
-    const int pw = col * k1;                        // < 65536
-    const float2 tw = cmulf(s_tw[pw >> 8], s_fine[pw & 255]);
-    out[(size_t) k1 * 256 + col] = cmulf(v[q], tw);
+    out[(size_t) k1 * 256 + col] = cmulf(v[q], __ldg(p.twpq + k1 * 256 + col));   // SPEC F.4 inter-pass twiddle
   }
 }
 
@@ -142,7 +133,7 @@ cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
   p.x = a.x; p.fmt = a.fmt; p.stream_stride = a.stream_stride; p.hist = a.hist; p.hist_len = a.hist_len;
   p.windows_per_stream = a.windows_per_stream; p.first_window = a.first_window; p.hop = a.hop;
   p.base_off = a.base_off; p.win_base = win_base; p.window = a.window; p.scratch = a.scratch;
-  p.tw256 = fs.twN1; p.twfine = twfine;
+  p.tw256 = fs.twN1; p.twfine = twfine; p.twpq = fs.twPQ;
   dim3 grid(16, n_win);
   k_cols256<<<grid, 256, 0, c.stream>>>(p);
   if (c.launch_counter) ++*c.launch_counter;
@@ -201,11 +192,12 @@ __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
       if (MODE == 0) {
         float pw = __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y) * p.inv_n;
         float *__restrict__ psd = p.psd + (size_t) win * 65536;
-        if (p.shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); psd[(k + 32768) & 65535] = pw; }
-        else psd[k] = pw;
+        // one-shot outputs: streaming stores, so that they do not displace the scratch / input in L2
+        if (p.shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); __stcs(psd + ((k + 32768) & 65535), pw); }
+        else __stcs(psd + k, pw);
       } else {
         const int m = __ldg(p.binmap + k);
-        if (m >= 0) p.cspec[(size_t) win * p.n_bins + m] = v[q];
+        if (m >= 0) __stcs(p.cspec + (size_t) win * p.n_bins + m, v[q]);
       }
     }
   }

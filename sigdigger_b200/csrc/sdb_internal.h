@@ -19,6 +19,7 @@ struct SdbFourStep {
   const float2 *twN1;       // W_N1^i, i < N1 (forward sign)
   const float2 *twN2;
   const float2 *twN;        // W_N^i, i < N
+  const float2 *twPQ;       // N = 65536 only: SPEC F.4 inter-pass twiddle [k1][n2] = W_256^(p>>8) x W_65536^(p&255), p = n2 k1
 };
 
 struct SdbPassAArgs {
