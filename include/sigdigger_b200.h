@@ -157,6 +157,57 @@ int          sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sdb_
 int          sdb_engine_read_psd_async(sdb_engine_t *e, float *dst, size_t cap_floats);
 int          sdb_engine_read_all_symbols_async(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft,
                                                uint8_t *hard, size_t cap);
+/* ---- inspector spectrum sources and parameter estimators (SPEC.md section U) ----
+ * suscan_analyzer_inspector_set_spectrum_async(analyzer, handle, spectsrc_id, req_id) (Suscan/Analyzer.cpp:539-548)
+ * and suscan_analyzer_inspector_estimator_cmd_async(analyzer, handle, estimator_id, enabled, req_id)
+ * (Suscan/Analyzer.cpp:550-565).  Index 0 of the GUI's source combo is "none"; the OPEN message lists the
+ * sources / estimators below in this order (Suscan/Messages/InspectorMessage.cpp:40-61).  Every feed that
+ * produced more than `size` channel-rate samples emits one spectrum of the last `size` samples (linear power,
+ * DC at index 0: the GUI converts to dB and swaps halves itself, GenericInspector.cpp:232-250) and one value
+ * per enabled estimator.  Both calls must precede sdb_engine_commit(). */
+enum { SDB_SPECTSRC_NONE = 0, SDB_SPECTSRC_PSD, SDB_SPECTSRC_CYCLO, SDB_SPECTSRC_FMSPECT, SDB_SPECTSRC_TIMEDIFF,
+       SDB_SPECTSRC_ABSTIMEDIFF, SDB_SPECTSRC_EXP_2, SDB_SPECTSRC_EXP_4, SDB_SPECTSRC_EXP_8, SDB_SPECTSRC_FAC,
+       SDB_SPECTSRC_COUNT };
+enum { SDB_ESTIMATOR_BAUD_FAC = 0, SDB_ESTIMATOR_BAUD_NONLINEAR = 1, SDB_ESTIMATOR_COUNT };
+/* name / description strings of the registries (suscan_spectsrc_class_lookup, suscan_estimator_class_lookup) */
+const char *sdb_spectsrc_name(int spectsrc_id);
+const char *sdb_estimator_name(int estimator_id);
+int sdb_engine_set_spectrum_source(sdb_engine_t *e, int handle, int spectsrc_id, uint32_t size /* 64..4096, 2^k */);
+int sdb_engine_set_estimator(sdb_engine_t *e, int handle, int estimator_id, int enabled);
+/* latest spectra of one channel, all streams: out[n_streams][size] (FAC fills size/2), sizes[n_streams] = floats
+ * emitted per stream (0 = nothing this feed).  Waits for the feed's kernels. */
+int sdb_engine_read_spectrum(sdb_engine_t *e, int handle, float *out, uint32_t *sizes);
+/* latest estimates of one channel, all streams: values[n_streams], valid[n_streams] */
+int sdb_engine_read_estimate(sdb_engine_t *e, int handle, int estimator_id, float *values, int32_t *valid);
+
+/* ---- channel detector on the main PSD (SPEC.md section K) ----
+ * struct suscan_analyzer_params.detector_params.{alpha, beta, gamma, snr} + channel_update_int
+ * (Suscan/AnalyzerParams.cpp:27-66) -> SUSCAN_ANALYZER_MESSAGE_TYPE_CHANNEL lists of struct sigutils_channel
+ * (Suscan/Messages/ChannelMessage.cpp:25-70; include/Suscan/Channel.h:26-32).  alpha = spectrum averaging,
+ * gamma = noise-floor averaging, snr = linear power ratio over the floor; beta (signal-level averaging) is accepted
+ * for ABI compatibility and unused: levels are reported per update.  One update per feed. */
+typedef struct {
+  double   fc, f_lo, f_hi, bw;      /* Hz (sigutils_channel.fc / f_lo / f_hi / bw) */
+  float    snr, S0, N0;             /* linear power: peak averaged level, noise floor, S0 / N0 */
+  uint32_t bin_lo, bin_hi;          /* [lo, hi) in ascending-frequency bin order */
+} sdb_detected_channel;
+/* engine-integrated: enable before sdb_engine_commit(); needs a linear PSD (no SDB_FLAG_PSD_SHIFT_DB) */
+int  sdb_engine_set_channel_detector(sdb_engine_t *e, float alpha, float beta, float gamma, float snr,
+                                     uint32_t min_bins);
+/* channels of one stream after the latest feed (ascending frequency); *total = channels found before the
+ * 256-entry cap.  center_freq shifts the reported frequencies (source tuner frequency, sigutils_channel.ft). */
+long sdb_engine_read_channels(sdb_engine_t *e, uint32_t stream, double center_freq, sdb_detected_channel *out,
+                              size_t cap, uint32_t *total);
+/* stand-alone detector on any device-resident linear PSD (e.g. the stitched SpectrumView of the panoramic
+ * scanner, BASELINE config 5 "per-GPU channel detector"): psd_dev[stream][frame][n_bins], DC at index 0 */
+typedef struct sdb_chdet sdb_chdet_t;
+sdb_chdet_t *sdb_chdet_new(int device, uint32_t n_bins, uint32_t n_streams, float alpha, float gamma, float snr,
+                           uint32_t min_bins);
+void sdb_chdet_destroy(sdb_chdet_t *d);
+int  sdb_chdet_feed_device(sdb_chdet_t *d, const float *psd_dev, uint32_t frames, size_t stream_stride);
+long sdb_chdet_read(sdb_chdet_t *d, uint32_t stream, double samp_rate, double center_freq,
+                    sdb_detected_channel *out, size_t cap, uint32_t *total);
+
 /* device-side views for zero-copy consumers / benchmarks */
 const uint32_t *sdb_engine_symbol_counts_device(const sdb_engine_t *e);
 size_t          sdb_engine_symbol_capacity(const sdb_engine_t *e);

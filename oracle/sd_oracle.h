@@ -374,6 +374,32 @@ int sdo_analyzer_feed(sdo_analyzer *a, const sdo_cpx *x, size_t n,
                       sdo_cpx **sym_out, uint8_t **hard_out, size_t sym_cap,
                       sdo_an_counts *counts);
 
+/* ---- K: channel detector on the main PSD (chdetect.c, SPEC.md section K) ---- */
+typedef struct {
+  unsigned bin_lo, bin_hi;     /* [lo, hi) in ascending-frequency (fft-shifted) bin order */
+  float    s0, n0, snr;        /* peak averaged level, noise floor, s0 / n0 (linear power) */
+} sdo_channel;
+typedef struct {
+  unsigned n, min_bins, last_total;
+  float    alpha, gamma, snr, n0;
+  int      primed, n0_primed;
+  float   *avg, *tmp;
+} sdo_chdet;
+#define SDO_CHDET_MAXRAW 8192u
+int      sdo_chdet_init(sdo_chdet *d, unsigned n, float alpha, float gamma, float snr, unsigned min_bins);
+void     sdo_chdet_free(sdo_chdet *d);
+unsigned sdo_chdet_feed(sdo_chdet *d, const float *psd, unsigned frames, sdo_channel *out, unsigned cap);
+
+/* ---- U: inspector spectrum sources + baud estimators (spectsrc.c, SPEC.md section U) ---- */
+enum sdo_spectsrc { SDO_SPECTSRC_NONE = 0, SDO_SPECTSRC_PSD, SDO_SPECTSRC_CYCLO, SDO_SPECTSRC_FMSPECT,
+                    SDO_SPECTSRC_TIMEDIFF, SDO_SPECTSRC_ABSTIMEDIFF, SDO_SPECTSRC_EXP_2, SDO_SPECTSRC_EXP_4,
+                    SDO_SPECTSRC_EXP_8, SDO_SPECTSRC_FAC, SDO_SPECTSRC_COUNT };
+enum sdo_estimator { SDO_ESTIMATOR_BAUD_FAC = 0, SDO_ESTIMATOR_BAUD_NONLINEAR = 1, SDO_ESTIMATOR_COUNT };
+#define SDO_U5_KMIN 8u
+unsigned sdo_spectsrc_out_size(int kind, unsigned ns);
+unsigned sdo_spectsrc_frame(int kind, unsigned ns, const sdo_cpx *c, size_t n_ch, float *out);
+int      sdo_estimate_baud(int estimator, unsigned ns, float fs_ch, const sdo_cpx *c, size_t n_ch, float *baud);
+
 /* multi-threaded CPU baseline: S independent streams, each n samples, same params (OpenMP). */
 double sdo_baseline_run(const sdo_an_params *p, const sdo_cpx *x, size_t n_streams, size_t n,
                         int n_threads, uint64_t *checksum);

@@ -16,6 +16,9 @@ WINDOW = {"none": 0, "hamming": 1, "hann": 2, "flat_top": 3, "blackmann_harris":
 INSP = {"psk": 0, "fsk": 1, "ask": 2, "audio": 3, "raw": 4}
 AUDIO = {"disabled": 0, "am": 1, "fm": 2, "usb": 3, "lsb": 4}
 FLAG_PSD_SHIFT_DB = 1
+SPECTSRC = {"none": 0, "psd": 1, "cyclo": 2, "fmspect": 3, "timediff": 4, "abstimediff": 5, "exp_2": 6,
+            "exp_4": 7, "exp_8": 8, "fac": 9}
+ESTIMATOR = {"baud-fac": 0, "baud-nonlinear": 1}
 
 
 class EngineParams(C.Structure):
@@ -26,6 +29,43 @@ class EngineParams(C.Structure):
 
 FORMAT = {"f32": 0, "u8": 1, "s8": 2, "s16": 3}
 FORMAT_DTYPE = {0: np.complex64, 1: np.uint8, 2: np.int8, 3: np.int16}
+
+
+class DetectedChannel(C.Structure):
+    """sdb_detected_channel (struct sigutils_channel)."""
+    _fields_ = [("fc", C.c_double), ("f_lo", C.c_double), ("f_hi", C.c_double), ("bw", C.c_double),
+                ("snr", C.c_float), ("S0", C.c_float), ("N0", C.c_float), ("bin_lo", C.c_uint32),
+                ("bin_hi", C.c_uint32)]
+
+
+class ChannelDetector:
+    """Stand-alone SPEC K detector on device-resident linear PSDs (e.g. a stitched SpectrumView)."""
+
+    def __init__(self, n_bins, n_streams=1, alpha=0.01, gamma=0.5, snr=4.0, min_bins=2, device=0):
+        self._L = load_library()
+        self._h = self._L.sdb_chdet_new(device, n_bins, n_streams, alpha, gamma, snr, min_bins)
+        if not self._h:
+            raise RuntimeError("sdb_chdet_new failed (no CUDA device or bad parameters)")
+        self.n_bins, self.n_streams = n_bins, n_streams
+
+    def close(self):
+        if self._h:
+            self._L.sdb_chdet_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def feed(self, psd):
+        """psd: CUDA float32 tensor [n_streams, frames, n_bins] (linear power, DC at index 0)."""
+        assert psd.is_cuda and psd.dim() == 3 and psd.shape[0] == self.n_streams and psd.shape[2] == self.n_bins
+        psd = psd.contiguous()
+        _check(self._L.sdb_chdet_feed_device(self._h, psd.data_ptr(), psd.shape[1], psd.shape[1] * psd.shape[2]))
+
+    def read(self, stream=0, samp_rate=1.0, center_freq=0.0, cap=256):
+        out = (DetectedChannel * cap)()
+        tot = C.c_uint32()
+        n = _check(self._L.sdb_chdet_read(self._h, stream, samp_rate, center_freq, out, cap, C.byref(tot)))
+        return [out[i] for i in range(n)], tot.value
 
 
 class ChannelParams(C.Structure):
@@ -75,6 +115,18 @@ _PROTOS = {
     "sdb_engine_read_all_symbols_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_symbol_counts_device": (C.c_void_p, [C.c_void_p]),
     "sdb_engine_symbol_capacity": (C.c_size_t, [C.c_void_p]),
+    "sdb_spectsrc_name": (C.c_char_p, [C.c_int]),
+    "sdb_estimator_name": (C.c_char_p, [C.c_int]),
+    "sdb_engine_set_spectrum_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32]),
+    "sdb_engine_set_estimator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "sdb_engine_read_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sdb_engine_read_estimate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "sdb_engine_set_channel_detector": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]),
+    "sdb_engine_read_channels": (C.c_long, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sdb_chdet_new": (C.c_void_p, [C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32]),
+    "sdb_chdet_destroy": (None, [C.c_void_p]),
+    "sdb_chdet_feed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "sdb_chdet_read": (C.c_long, [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sdb_engine_stream": (C.c_void_p, [C.c_void_p]),
     "sdb_engine_launch_count": (C.c_uint64, [C.c_void_p]),
     "sdb_engine_kernel_time": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -252,6 +304,43 @@ class Engine:
             out = np.empty((self.n_streams, f, self.psd_size), np.float32)
         _check(self._L.sdb_engine_read_psd(self._h, out.ctypes.data, out.size))
         return out
+
+    # ---- channel detector (SPEC K; detector_params of Suscan/AnalyzerParams.cpp:27-66)
+    def set_channel_detector(self, alpha=0.01, beta=0.01, gamma=0.5, snr=4.0, min_bins=2):
+        _check(self._L.sdb_engine_set_channel_detector(self._h, alpha, beta, gamma, snr, min_bins))
+
+    def read_channels(self, stream, center_freq=0.0, cap=256):
+        """-> (structured array of DetectedChannel fields, total found before the cap)"""
+        out = (DetectedChannel * cap)()
+        tot = C.c_uint32()
+        n = _check(self._L.sdb_engine_read_channels(self._h, stream, center_freq, out, cap, C.byref(tot)))
+        return [out[i] for i in range(n)], tot.value
+
+    # ---- inspector spectrum sources / estimators (SPEC U; Suscan/Analyzer.cpp:539-565)
+    def set_spectrum_source(self, h, kind, size=1024):
+        k = SPECTSRC[kind] if isinstance(kind, str) else int(kind)
+        _check(self._L.sdb_engine_set_spectrum_source(self._h, h, k, size))
+        self._spect_size = getattr(self, "_spect_size", {})
+        self._spect_size[h] = size
+
+    def set_estimator(self, h, estimator, enabled=True):
+        e = ESTIMATOR[estimator] if isinstance(estimator, str) else int(estimator)
+        _check(self._L.sdb_engine_set_estimator(self._h, h, e, int(enabled)))
+
+    def read_spectrum(self, h):
+        """-> (spectra [n_streams, size] float32, sizes [n_streams] uint32: floats emitted per stream)"""
+        size = self._spect_size[h]
+        out = np.zeros((self.n_streams, size), np.float32)
+        sizes = np.zeros(self.n_streams, np.uint32)
+        _check(self._L.sdb_engine_read_spectrum(self._h, h, out.ctypes.data, sizes.ctypes.data))
+        return out, sizes
+
+    def read_estimate(self, h, estimator):
+        e = ESTIMATOR[estimator] if isinstance(estimator, str) else int(estimator)
+        vals = np.zeros(self.n_streams, np.float32)
+        valid = np.zeros(self.n_streams, np.int32)
+        _check(self._L.sdb_engine_read_estimate(self._h, h, e, vals.ctypes.data, valid.ctypes.data))
+        return vals, valid
 
     def read_channel(self, stream, h, cap=None):
         cap = cap or (1 << 24)

@@ -45,6 +45,7 @@ struct Channel {
   unsigned center, size, width, halfw, halfsz;
   bool has_insp;
   sdb_inspector_config cfg;
+  int spect_kind = 0; unsigned spect_size = 0, est_mask = 0;   // SPEC U
 };
 
 struct TimedSpan { int family; cudaEvent_t a, b; };
@@ -108,6 +109,14 @@ struct sdb_engine {
   float *d_pool = nullptr; size_t pool_stride = 0;
   float *d_taps = nullptr;
   float2 *d_soft = nullptr; uint8_t *d_hard = nullptr; uint32_t *d_counts = nullptr; size_t sym_cap = 0;
+  // channel detector on the main PSD (SPEC K; chdet_kernels.cu)
+  struct sdb_chdet *chdet = nullptr; bool cd_enabled = false;
+  float cd_alpha = 0, cd_gamma = 0, cd_snr = 0; unsigned cd_min_bins = 1;
+  // inspector spectrum sources / estimators (SPEC U)
+  std::map<unsigned, float *> bh_windows;
+  std::vector<SdbSpectCfg> h_spect; SdbSpectCfg *d_spectcfg = nullptr;
+  float *d_spect = nullptr; size_t spect_stride = 0; int spect_max_ns = 0;
+  uint32_t *d_spect_size = nullptr; float *d_est = nullptr; int *d_est_valid = nullptr;
   // timing
   std::vector<TimedSpan> spans;
   double fam_ms[FAM_COUNT] = {0}; uint64_t fam_n[FAM_COUNT] = {0};
@@ -224,6 +233,7 @@ extern "C" void sdb_engine_destroy(sdb_engine_t *e)
   if (e->insp_stream) cudaStreamSynchronize(e->insp_stream);
   e->collect_spans();
   if (e->l2_pinned_bytes) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
+  if (e->chdet) sdb_chdet_destroy(e->chdet);
   for (void *p : e->allocs) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (e->ev_chan[i]) cudaEventDestroy(e->ev_chan[i]);
@@ -286,6 +296,101 @@ extern "C" int sdb_engine_set_inspector(sdb_engine_t *e, int handle, const sdb_i
   Channel &c = e->channels[handle];
   c.cfg = *cfg; c.has_insp = true;
   c.cfg.fs = (float) (e->samp_rate * (double) c.size / (double) e->W);
+  return 0;
+}
+
+struct sdb_chdet;
+cudaError_t sdb_chdet_feed_stream(sdb_chdet *d, const float *psd_dev, uint32_t frames, size_t stream_stride,
+                                  cudaStream_t stream, uint64_t *launch_counter);
+
+extern "C" int sdb_engine_set_channel_detector(sdb_engine_t *e, float alpha, float beta, float gamma, float snr,
+                                               uint32_t min_bins)
+{
+  (void) beta;
+  if (!e) return fail("null argument");
+  if (e->committed) return fail("engine already committed");
+  if (!e->prm.psd_size) return fail("the channel detector needs the main PSD");
+  if (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) return fail("the channel detector needs a linear PSD");
+  if (!(snr > 0.0f) || !(alpha >= 0.0f && alpha <= 1.0f) || !(gamma >= 0.0f && gamma <= 1.0f))
+    return fail("detector parameters out of range");
+  e->cd_enabled = true; e->cd_alpha = alpha; e->cd_gamma = gamma; e->cd_snr = snr; e->cd_min_bins = min_bins ? min_bins : 1;
+  return 0;
+}
+
+extern "C" long sdb_engine_read_channels(sdb_engine_t *e, uint32_t stream, double center_freq,
+                                         sdb_detected_channel *out, size_t cap, uint32_t *total)
+{
+  if (!e) return fail("null argument");
+  if (!e->committed || !e->chdet) return fail("channel detector not enabled");
+  if (stream >= e->prm.n_streams) return fail("stream out of range");
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaStreamSynchronize(e->psd_stream ? e->psd_stream : e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const long n = sdb_chdet_read(e->chdet, stream, e->samp_rate, center_freq, out, cap, total);
+  if (n < 0) return fail("channel read failed");
+  return n;
+}
+
+static const char *kSpectNames[SDB_SPECTSRC_COUNT] = { "none", "psd", "cyclo", "fmspect", "timediff", "abstimediff",
+                                                      "exp_2", "exp_4", "exp_8", "fac" };
+static const char *kEstNames[SDB_ESTIMATOR_COUNT] = { "baud-fac", "baud-nonlinear" };
+extern "C" const char *sdb_spectsrc_name(int id) { return id >= 0 && id < SDB_SPECTSRC_COUNT ? kSpectNames[id] : nullptr; }
+extern "C" const char *sdb_estimator_name(int id) { return id >= 0 && id < SDB_ESTIMATOR_COUNT ? kEstNames[id] : nullptr; }
+
+extern "C" int sdb_engine_set_spectrum_source(sdb_engine_t *e, int handle, int spectsrc_id, uint32_t size)
+{
+  if (!e) return fail("null argument");
+  if (handle < 0 || handle >= (int) e->channels.size()) return fail("wrong handle");
+  if (e->committed) return fail("engine already committed");
+  if (spectsrc_id < 0 || spectsrc_id >= SDB_SPECTSRC_COUNT) return fail("unknown spectrum source");
+  if (!is_pow2(size) || size < 64 || size > 4096) return fail("spectrum size must be a power of two in [64, 4096]");
+  Channel &c = e->channels[handle];
+  if (c.spect_size && c.spect_size != size && c.est_mask) return fail("spectrum size already fixed by an estimator");
+  c.spect_kind = spectsrc_id; c.spect_size = size;
+  return 0;
+}
+
+extern "C" int sdb_engine_set_estimator(sdb_engine_t *e, int handle, int estimator_id, int enabled)
+{
+  if (!e) return fail("null argument");
+  if (handle < 0 || handle >= (int) e->channels.size()) return fail("wrong handle");
+  if (e->committed) return fail("engine already committed");
+  if (estimator_id < 0 || estimator_id >= SDB_ESTIMATOR_COUNT) return fail("unknown estimator");
+  Channel &c = e->channels[handle];
+  if (enabled) c.est_mask |= 1u << estimator_id; else c.est_mask &= ~(1u << estimator_id);
+  return 0;
+}
+
+extern "C" int sdb_engine_read_spectrum(sdb_engine_t *e, int handle, float *out, uint32_t *sizes)
+{
+  if (!e || !out || !sizes) return fail("null argument");
+  if (!e->committed) return fail("engine not committed");
+  if (handle < 0 || handle >= (int) e->channels.size()) return fail("wrong handle");
+  if (!e->d_spect || e->h_spect[handle].kind == 0) return fail("no spectrum source on this channel");
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaStreamSynchronize(e->insp_stream));
+  const unsigned S = e->prm.n_streams; const int K = (int) e->channels.size();
+  const SdbSpectCfg &q = e->h_spect[handle];
+  CK(cudaMemcpy2D(out, (size_t) q.ns * sizeof(float), e->d_spect + q.out_off, e->spect_stride * sizeof(float),
+                  (size_t) q.ns * sizeof(float), S, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(sizes, sizeof(uint32_t), e->d_spect_size + handle, (size_t) K * sizeof(uint32_t), sizeof(uint32_t), S,
+                  cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int sdb_engine_read_estimate(sdb_engine_t *e, int handle, int estimator_id, float *values, int32_t *valid)
+{
+  if (!e || !values || !valid) return fail("null argument");
+  if (!e->committed) return fail("engine not committed");
+  if (handle < 0 || handle >= (int) e->channels.size()) return fail("wrong handle");
+  if (estimator_id < 0 || estimator_id >= SDB_ESTIMATOR_COUNT) return fail("unknown estimator");
+  if (!e->d_est || !(e->h_spect[handle].est_mask & (1u << estimator_id))) return fail("estimator not enabled on this channel");
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaStreamSynchronize(e->insp_stream));
+  const unsigned S = e->prm.n_streams; const int K = (int) e->channels.size();
+  const size_t pitch = (size_t) K * 2 * sizeof(float), off = (size_t) handle * 2 + estimator_id;
+  CK(cudaMemcpy2D(values, sizeof(float), e->d_est + off, pitch, sizeof(float), S, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(valid, sizeof(int32_t), e->d_est_valid + off, pitch, sizeof(int32_t), S, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -422,6 +527,10 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       if (!e->d_psdb[i]) return fail("out of device memory (psd)");
     }
     e->d_psd = e->d_psdb[0];
+    if (e->cd_enabled) {
+      e->chdet = sdb_chdet_new(e->prm.device, Np, S, e->cd_alpha, e->cd_gamma, e->cd_snr, e->cd_min_bins);
+      if (!e->chdet) return fail("out of device memory (channel detector)");
+    }
   }
   // ---- four-step scratch: one window per SM, pinned in L2
   {
@@ -551,6 +660,48 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       if (!g.d_ids) return fail("out of device memory");
       CK(cudaMemcpy(g.d_ids, kv.second.data(), kv.second.size() * sizeof(int), cudaMemcpyHostToDevice));
       e->groups.push_back(g);
+    }
+    // ---- inspector spectrum sources / estimators (SPEC U)
+    {
+      std::vector<SdbSpectCfg> sc(K);
+      size_t off = 0; int max_ns = 0; bool any = false;
+      for (int k = 0; k < K; ++k) {
+        const Channel &c = e->channels[k];
+        SdbSpectCfg &q = sc[k];
+        memset(&q, 0, sizeof(q));
+        if (c.spect_kind == 0 && c.est_mask == 0) continue;
+        any = true;
+        const unsigned ns = c.spect_size ? c.spect_size : 1024u;
+        q.kind = c.spect_kind; q.ns = (int) ns; q.logns = ilog2u(ns); q.est_mask = c.est_mask;
+        q.fs_ch = (float) (e->samp_rate * (double) c.size / (double) W);
+        q.tw = e->twiddle(ns);
+        if (!q.tw) return fail("out of device memory");
+        auto it = e->bh_windows.find(ns);
+        if (it == e->bh_windows.end()) {
+          std::vector<float> w;
+          sdbh::window_fill(w, ns, SDB_WINDOW_BLACKMANN_HARRIS);
+          float *d = e->dalloc<float>(ns);
+          if (!d) return fail("out of device memory");
+          CK(cudaMemcpy(d, w.data(), ns * sizeof(float), cudaMemcpyHostToDevice));
+          it = e->bh_windows.emplace(ns, d).first;
+        }
+        q.window = it->second;
+        q.out_off = off; off += ns;
+        max_ns = std::max(max_ns, (int) ns);
+      }
+      if (any) {
+        e->spect_stride = off; e->spect_max_ns = max_ns; e->h_spect = sc;
+        e->d_spectcfg = e->dalloc<SdbSpectCfg>(K);
+        e->d_spect = e->dalloc<float>((size_t) S * off);
+        e->d_spect_size = e->dalloc<uint32_t>((size_t) S * K);
+        e->d_est = e->dalloc<float>((size_t) S * K * 2);
+        e->d_est_valid = e->dalloc<int>((size_t) S * K * 2);
+        if (!e->d_spectcfg || !e->d_spect || !e->d_spect_size || !e->d_est || !e->d_est_valid)
+          return fail("out of device memory (spectrum sources)");
+        CK(cudaMemcpy(e->d_spectcfg, sc.data(), K * sizeof(SdbSpectCfg), cudaMemcpyHostToDevice));
+        CK(cudaMemset(e->d_spect_size, 0, (size_t) S * K * sizeof(uint32_t)));
+        CK(cudaMemset(e->d_est_valid, 0, (size_t) S * K * 2 * sizeof(int)));
+      }
     }
     // ---- chains
     e->h_cfg.resize(K);
@@ -691,6 +842,8 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       if (psd_chunk(pctx, frames, s0 * frames, g * frames, scr_psd)) return -1;
       if (chan_chunk(ctx, wps, first, s0 * wps, g * wps, scr_ch)) return -1;
     }
+    if (e->chdet) CK(sdb_chdet_feed_stream(e->chdet, e->d_psd, (uint32_t) frames, (size_t) frames * Np, e->psd_stream,
+                                           &e->launches));
     CK(cudaEventRecord(e->ev_psd_ready[ob], e->psd_stream));
     CK(cudaStreamWaitEvent(e->stream, e->ev_psd_ready[ob], 0));   // the main stream stays the engine's timeline
   } else {
@@ -707,6 +860,8 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
         for (int w0 = 0; w0 < total; w0 += e->chunk_windows)
           if (psd_chunk(ctx, frames, w0, std::min(e->chunk_windows, total - w0), e->d_scratch)) return -1;
       }
+      if (e->chdet) CK(sdb_chdet_feed_stream(e->chdet, e->d_psd, (uint32_t) frames, (size_t) frames * Np, e->stream,
+                                             &e->launches));
       CK(cudaEventRecord(e->ev_psd_ready[ob], e->stream));
     }
     // ---- channeliser forward transforms
@@ -735,6 +890,10 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       e->d_soft = e->d_softb[b]; e->d_hard = e->d_hardb[b]; e->d_counts = e->d_countsb[b];
       if (e->sym_read_valid[b]) CK(cudaStreamWaitEvent(e->insp_stream, e->ev_sym_read[b], 0));
       SdbLaunchCtx ictx{ e->insp_stream, &e->launches };
+      if (e->d_spectcfg)
+        CK(sdb_launch_spectsrc(ictx, e->d_spectcfg, e->d_chans, K, (int) S, e->spect_max_ns, e->d_chanb[b],
+                               e->chan_stride, (uint32_t) wps, e->d_spect, e->spect_stride, e->d_spect_size,
+                               e->d_est, e->d_est_valid));
       e->span_begin(FAM_INSPECTOR, e->insp_stream);
       CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
                                  e->d_chans, e->d_chanb[b], e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,

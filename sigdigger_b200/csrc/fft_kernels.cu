@@ -17,6 +17,7 @@
 // message payload (Suscan/Messages/PSDMessage.cpp:26-39).  Compiled WITH fma contraction: results are
 // compared with the oracle to the float tolerance of SPEC.md section T, not bit-exactly.
 #include "sdb_internal.h"
+#include "../../include/sigdigger_b200.h"
 #include "sdb_math.h"
 #include <math_constants.h>
 
@@ -322,6 +323,174 @@ cudaError_t sdb_launch_hist_convert(cudaStream_t s, const void *x, int fmt, size
 {
   dim3 grid((hist_len + 255) / 256, n_streams);
   k_hist_convert<<<grid, 256, 0, s>>>(x, fmt, stream_stride, offset, hist, hist_len);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inspector spectrum sources and baud estimators (SPEC U): one CTA per (channel, stream) works on the last
+// ns channel-rate samples of the feed.  Replaces what suscan's spectsrc / estimator workers would send as
+// kind=SPECTRUM / kind=ESTIMATOR inspector messages (consumers: Default/GenericInspector/GenericInspector.cpp:232-264);
+// the fast autocorrelation follows Default/GenericInspector/FACTab.cpp:209-221.
+// ---------------------------------------------------------------------------------------------
+static __device__ __forceinline__ float2 csq(float2 a)
+{
+  const float m = a.x * a.y;
+  return make_float2(a.x * a.x - a.y * a.y, m + m);
+}
+static __device__ __forceinline__ float2 spect_pre(int kind, float2 x, float2 p)
+{
+  switch (kind) {
+    case SDB_SPECTSRC_CYCLO: return make_float2(x.x * p.x + x.y * p.y, x.y * p.x - x.x * p.y);
+    case SDB_SPECTSRC_FMSPECT: {
+      const float dr = x.x * p.x + x.y * p.y, di = x.y * p.x - x.x * p.y;
+      return make_float2(d_atan2f(di, dr) * 0.318309886f, 0.0f);
+    }
+    case SDB_SPECTSRC_TIMEDIFF: return make_float2(x.x - p.x, x.y - p.y);
+    case SDB_SPECTSRC_ABSTIMEDIFF: return make_float2(d_cabsf(x.x - p.x, x.y - p.y), 0.0f);
+    case SDB_SPECTSRC_EXP_2: return csq(x);
+    case SDB_SPECTSRC_EXP_4: return csq(csq(x));
+    case SDB_SPECTSRC_EXP_8: return csq(csq(csq(x)));
+    default: return x;       // PSD, FAC
+  }
+}
+
+// (value, index) arg-max over the CTA, lowest index on ties; every thread gets the result
+static __device__ void block_argmax(float &v, int &i, float *sv, int *si)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_down_sync(0xffffffffu, v, o);
+    const int oi = __shfl_down_sync(0xffffffffu, i, o);
+    if (oi >= 0 && (i < 0 || ov > v || (ov == v && oi < i))) { v = ov; i = oi; }
+  }
+  const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { sv[warp] = v; si[warp] = i; }
+  __syncthreads();
+  v = sv[0]; i = si[0];
+  for (int w = 1; w < nw; ++w)
+    if (si[w] >= 0 && (i < 0 || sv[w] > v || (sv[w] == v && si[w] < i))) { v = sv[w]; i = si[w]; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_spectsrc(const SdbSpectCfg *__restrict__ cfgs,
+                                                    const SdbChannelDev *__restrict__ chans, int n_channels,
+                                                    const float2 *__restrict__ chan_in, size_t chan_stream_stride,
+                                                    uint32_t n_hops, float *__restrict__ spect,
+                                                    size_t spect_stream_stride, uint32_t *__restrict__ spect_size,
+                                                    float *__restrict__ est, int *__restrict__ est_valid)
+{
+  extern __shared__ float2 sm[];
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  const int k = blockIdx.x, st = blockIdx.y;
+  const SdbSpectCfg c = cfgs[k];
+  if (c.kind == 0 && c.est_mask == 0) return;
+  const int ns = c.ns, half = ns >> 1, chain = st * n_channels + k;
+  const uint32_t n_ch = n_hops * (uint32_t) chans[k].halfsz;
+  if (n_ch < (uint32_t) ns + 1u) {             // SPEC U.1: nothing is emitted for this feed
+    if (threadIdx.x == 0) {
+      spect_size[chain] = 0;
+      est_valid[2 * chain] = 0; est_valid[2 * chain + 1] = 0;
+    }
+    return;
+  }
+  const float2 *__restrict__ x = chan_in + (size_t) st * chan_stream_stride + chans[k].out_off + (n_ch - ns);
+  const float inv_n = 1.0f / (float) ns;
+  if (c.kind) {
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+      float2 v = spect_pre(c.kind, x[i], x[i - 1]);
+      if (c.kind != SDB_SPECTSRC_FAC) { const float w = __ldg(c.window + i); v.x *= w; v.y *= w; }
+      sm[i] = v;
+    }
+    __syncthreads();
+    block_fft_inplace<-1, 1>(sm, ns, c.logns, threadIdx.x, blockDim.x, c.tw);
+    float *__restrict__ out = spect + (size_t) st * spect_stream_stride + c.out_off;
+    if (c.kind != SDB_SPECTSRC_FAC) {
+      for (int i = threadIdx.x; i < ns; i += blockDim.x)
+        out[i] = __fmaf_rn(sm[i].x, sm[i].x, sm[i].y * sm[i].y) * inv_n;
+      if (threadIdx.x == 0) spect_size[chain] = (uint32_t) ns;
+    } else {
+      for (int i = threadIdx.x; i < ns; i += blockDim.x)
+        sm[i] = make_float2(__fmaf_rn(sm[i].x, sm[i].x, sm[i].y * sm[i].y), 0.0f);
+      __syncthreads();
+      block_fft_inplace<+1, 1>(sm, ns, c.logns, threadIdx.x, blockDim.x, c.tw);
+      for (int i = threadIdx.x; i < half; i += blockDim.x) out[i] = d_cabsf(sm[i].x, sm[i].y) * inv_n;
+      if (threadIdx.x == 0) spect_size[chain] = (uint32_t) half;
+    }
+    __syncthreads();
+  }
+  if (c.est_mask & 2u) {      // baud-nonlinear: line of |x[n] - x[n-1]| at the symbol rate
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+      float2 v = spect_pre(SDB_SPECTSRC_ABSTIMEDIFF, x[i], x[i - 1]);
+      const float w = __ldg(c.window + i);
+      v.x *= w; v.y *= w;
+      sm[i] = v;
+    }
+    __syncthreads();
+    block_fft_inplace<-1, 1>(sm, ns, c.logns, threadIdx.x, blockDim.x, c.tw);
+    float bv = 0.0f; int bi = -1;
+    for (int i = SDB_U5_KMIN + threadIdx.x; i < half; i += blockDim.x) {
+      const float v = __fmaf_rn(sm[i].x, sm[i].x, sm[i].y * sm[i].y) * inv_n;
+      if (bi < 0 || v > bv) { bv = v; bi = i; }
+    }
+    block_argmax(bv, bi, s_v, s_i);
+    if (threadIdx.x == 0) {
+      const bool ok = bi >= 0 && bv > 0.0f;
+      est_valid[2 * chain + 1] = ok ? 1 : 0;
+      est[2 * chain + 1] = ok ? (float) bi * c.fs_ch / (float) ns : 0.0f;
+    }
+    __syncthreads();
+  } else if (threadIdx.x == 0) est_valid[2 * chain + 1] = 0;
+  if (c.est_mask & 1u) {      // baud-fac: autocorrelation of the mean-removed |x[n] - x[n-1]|
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) sm[i] = spect_pre(SDB_SPECTSRC_ABSTIMEDIFF, x[i], x[i - 1]);
+    __syncthreads();
+    block_fft_inplace<-1, 1>(sm, ns, c.logns, threadIdx.x, blockDim.x, c.tw);
+    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+      sm[i] = make_float2(i == 0 ? 0.0f : __fmaf_rn(sm[i].x, sm[i].x, sm[i].y * sm[i].y), 0.0f);
+    __syncthreads();
+    block_fft_inplace<+1, 1>(sm, ns, c.logns, threadIdx.x, blockDim.x, c.tw);
+    // first lag >= 1 with a negative value: arg-max of (-index) among the negative ones
+    float fv = 0.0f; int fi = -1;
+    for (int i = 1 + threadIdx.x; i < half; i += blockDim.x)
+      if (sm[i].x < 0.0f) { fv = (float) -i; fi = i; break; }
+    block_argmax(fv, fi, s_v, s_i);
+    const int from = fi;
+    float bv = 0.0f; int bi = -1;
+    if (from >= 1) {
+      for (int i = from + threadIdx.x; i < half; i += blockDim.x) {
+        const float v = sm[i].x;
+        if (bi < 0 || v > bv) { bv = v; bi = i; }
+      }
+    }
+    block_argmax(bv, bi, s_v, s_i);
+    // first local maximum reaching half of the largest one (every multiple of the period peaks alike)
+    float pv = 0.0f; int pi = -1;
+    if (from >= 1 && bi >= 0 && bv > 0.0f) {
+      const float thr = 0.5f * bv;
+      for (int i = from + threadIdx.x; i + 1 < half; i += blockDim.x)
+        if (sm[i].x >= thr && sm[i].x >= sm[i - 1].x && sm[i].x >= sm[i + 1].x) { pv = (float) -i; pi = i; break; }
+    }
+    block_argmax(pv, pi, s_v, s_i);
+    if (threadIdx.x == 0) {
+      const bool ok = pi >= 1;
+      est_valid[2 * chain] = ok ? 1 : 0;
+      est[2 * chain] = ok ? c.fs_ch / (float) pi : 0.0f;
+    }
+  } else if (threadIdx.x == 0) est_valid[2 * chain] = 0;
+}
+
+cudaError_t sdb_launch_spectsrc(const SdbLaunchCtx &c, const SdbSpectCfg *cfg_dev, const SdbChannelDev *chans_dev,
+                                int n_channels, int n_streams, int max_ns, const float2 *chan_in,
+                                size_t chan_stream_stride, uint32_t n_hops, float *spect, size_t spect_stream_stride,
+                                uint32_t *spect_size, float *est, int *est_valid)
+{
+  int threads = max_ns / 4; if (threads < 32) threads = 32;
+  dim3 grid(n_channels, n_streams);
+  k_spectsrc<<<grid, threads, (size_t) max_ns * sizeof(float2), c.stream>>>(
+      cfg_dev, chans_dev, n_channels, chan_in, chan_stream_stride, n_hops, spect, spect_stream_stride, spect_size,
+      est, est_valid);
+  if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }
 

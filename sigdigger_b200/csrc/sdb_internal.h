@@ -142,6 +142,20 @@ struct SdbChainState {
   float eq_wr[SDB_EQ_LEN], eq_wi[SDB_EQ_LEN], eq_xr[SDB_EQ_LEN], eq_xi[SDB_EQ_LEN];
 };
 
+// ---------------------------------------------------------------------------------------------
+// inspector spectrum sources + baud estimators (SPEC U; kernel in fft_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+#define SDB_U5_KMIN 8
+struct SdbSpectCfg {
+  int   kind;               // SDB_SPECTSRC_* (0 = none)
+  int   ns, logns;          // frame size
+  unsigned est_mask;        // bit i = estimator i enabled
+  float fs_ch;              // channel sample rate (Hz)
+  const float2 *tw;         // W_ns^i
+  const float  *window;     // Blackman-Harris(ns)
+  size_t out_off;           // offset (floats) of this channel's spectrum inside one stream's block
+};
+
 // host-callable launchers ----------------------------------------------------------------------
 struct SdbLaunchCtx {
   cudaStream_t stream;
@@ -172,6 +186,10 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
                                     float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap,
                                     int fresh);
+cudaError_t sdb_launch_spectsrc(const SdbLaunchCtx &c, const SdbSpectCfg *cfg_dev, const SdbChannelDev *chans_dev,
+                                int n_channels, int n_streams, int max_ns, const float2 *chan_in,
+                                size_t chan_stream_stride, uint32_t n_hops, float *spect, size_t spect_stream_stride,
+                                uint32_t *spect_size, float *est, int *est_valid);
 cudaError_t sdb_launch_task_xlate(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
                                   float omega, float phi0);
 cudaError_t sdb_launch_task_quad(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch);

@@ -432,3 +432,66 @@ def analyzer_run(params, x, chunk=None, want_chan=True):
                 chan=[cat(c, np.complex64) for c in chan_l],
                 soft=[cat(c, np.complex64) for c in soft_l],
                 hard=[cat(c, np.uint8) for c in hard_l])
+
+
+# ----------------------------------------------------------------------------------------------
+# U: inspector spectrum sources and baud estimators
+# ----------------------------------------------------------------------------------------------
+SPECTSRC = {"none": 0, "psd": 1, "cyclo": 2, "fmspect": 3, "timediff": 4, "abstimediff": 5, "exp_2": 6,
+            "exp_4": 7, "exp_8": 8, "fac": 9}
+ESTIMATOR = {"baud-fac": 0, "baud-nonlinear": 1}
+
+
+def spectsrc_frame(kind, ns, chan):
+    """chan = the channel samples of one feed.  Returns the emitted spectrum or None."""
+    L = lib()
+    L.sdo_spectsrc_frame.restype = C.c_uint
+    L.sdo_spectsrc_frame.argtypes = [C.c_int, C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p]
+    chan = _c64(chan)
+    out = np.zeros(ns, np.float32)
+    k = SPECTSRC[kind] if isinstance(kind, str) else kind
+    n = L.sdo_spectsrc_frame(k, ns, ptr(chan), len(chan), ptr(out))
+    return out[:n].copy() if n else None
+
+
+def estimate_baud(estimator, ns, fs_ch, chan):
+    L = lib()
+    L.sdo_estimate_baud.restype = C.c_int
+    L.sdo_estimate_baud.argtypes = [C.c_int, C.c_uint, C.c_float, C.c_void_p, C.c_size_t, c_float_p]
+    chan = _c64(chan)
+    v = C.c_float()
+    e = ESTIMATOR[estimator] if isinstance(estimator, str) else estimator
+    ok = L.sdo_estimate_baud(e, ns, C.c_float(fs_ch), ptr(chan), len(chan), C.byref(v))
+    return v.value if ok else None
+
+
+# ----------------------------------------------------------------------------------------------
+# K: channel detector
+# ----------------------------------------------------------------------------------------------
+class OChannel(C.Structure):
+    _fields_ = [("bin_lo", C.c_uint), ("bin_hi", C.c_uint), ("s0", C.c_float), ("n0", C.c_float), ("snr", C.c_float)]
+
+
+class ChDet(C.Structure):
+    _fields_ = [("n", C.c_uint), ("min_bins", C.c_uint), ("last_total", C.c_uint), ("alpha", C.c_float),
+                ("gamma", C.c_float), ("snr", C.c_float), ("n0", C.c_float), ("primed", C.c_int),
+                ("n0_primed", C.c_int), ("avg", c_float_p), ("tmp", c_float_p)]
+
+
+class ChannelDetector:
+    def __init__(self, n, alpha, gamma, snr, min_bins):
+        self.L = lib()
+        self.L.sdo_chdet_feed.restype = C.c_uint
+        self.d = ChDet()
+        assert self.L.sdo_chdet_init(C.byref(self.d), n, C.c_float(alpha), C.c_float(gamma), C.c_float(snr), min_bins) == 0
+        self.n = n
+
+    def feed(self, psd, cap=256):
+        """psd [frames, n] float32 -> (list of (bin_lo, bin_hi, s0, n0, snr), total)"""
+        psd = np.ascontiguousarray(psd, np.float32).reshape(-1, self.n)
+        out = (OChannel * cap)()
+        k = self.L.sdo_chdet_feed(C.byref(self.d), ptr(psd), psd.shape[0], out, cap)
+        return [(o.bin_lo, o.bin_hi, o.s0, o.n0, o.snr) for o in out[:k]], self.d.last_total
+
+    def close(self):
+        self.L.sdo_chdet_free(C.byref(self.d))

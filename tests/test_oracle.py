@@ -443,3 +443,67 @@ def test_no_device_fails_loudly():
         sdb.Engine(n_streams=1, psd_size=8192, max_feed=8192)
     with pytest.raises(sdb.SdbError, match="no CUDA device"):
         sdb.quad_demod(np.zeros(16, np.complex64))
+
+
+def test_spectrum_sources_and_baud_estimators(oracle):
+    """SPEC U on a QPSK capture at 8 samples/symbol with a 0.01 cycles/sample carrier offset."""
+    n, sps = 6000, 8.0
+    s, _ = synth.psk_signal(n, sps, order=4, seed=3)
+    rng = np.random.default_rng(3)
+    x = (0.3 * synth.mix(s, 0.01, 0.3) + synth.awgn(n, 1e-3, rng)).astype(np.complex64)
+    ns = 1024
+    w = signal.get_window("blackmanharris", ns, fftbins=False)
+    fr = x[-ns:].astype(np.complex128)
+    prev = x[-ns - 1:-1].astype(np.complex128)
+
+    def spec(p):
+        return np.abs(np.fft.fft(p * w)) ** 2 / ns
+
+    refs = {"psd": spec(fr), "cyclo": spec(fr * np.conj(prev)), "timediff": spec(fr - prev),
+            "abstimediff": spec(np.abs(fr - prev)), "exp_2": spec(fr ** 2), "exp_4": spec(fr ** 4),
+            "exp_8": spec(fr ** 8), "fmspect": spec(np.angle(fr * np.conj(prev)) / np.pi)}
+    for kind, ref in refs.items():
+        got = oracle.spectsrc_frame(kind, ns, x)
+        assert got is not None and len(got) == ns
+        assert np.max(np.abs(got - ref)) <= 2e-6 * ref.max(), kind
+    fac = oracle.spectsrc_frame("fac", ns, x)
+    r = np.abs(np.fft.ifft(np.abs(np.fft.fft(fr)) ** 2))[:ns // 2]      # FACTab.cpp:209-221 up to the 1/ns scale
+    assert len(fac) == ns // 2 and np.max(np.abs(fac - r)) <= 2e-6 * r.max()
+    # the 4th power of QPSK has a line at 4x the carrier offset; the estimators find the symbol rate
+    e4 = oracle.spectsrc_frame("exp_4", 4096, x)
+    assert int(np.argmax(e4)) == round(4 * 0.01 * 4096)
+    for est in ("baud-fac", "baud-nonlinear"):
+        for m in (1024, 4096):
+            assert oracle.estimate_baud(est, m, 1.0, x) == pytest.approx(1 / sps, rel=1e-6)
+    assert oracle.spectsrc_frame("psd", ns, x[:ns]) is None             # needs ns + 1 samples
+    assert oracle.estimate_baud("baud-fac", ns, 1.0, x[:ns]) is None
+
+
+def test_channel_detector_known_answers(oracle):
+    """SPEC K on synthetic spectra: averaging, exact quartile noise floor, runs, width filter, edges."""
+    N = 1024
+    psd = np.ones((1, N), np.float32)
+    psd[0, 100:110] = 50.0            # unshifted bins 100..109 -> ascending-frequency bins 612..621
+    psd[0, 700:702] = 50.0            # 2 bins wide: below min_bins = 3
+    psd[0, N // 2 - 5:N // 2 + 4] = 20.0   # wraps the ascending-frequency edges: [1019, 1024) and [0, 4)
+    d = oracle.ChannelDetector(N, alpha=0.5, gamma=0.5, snr=4.0, min_bins=3)
+    ch, total = d.feed(psd)
+    assert total == 3 and [(c[0], c[1]) for c in ch] == [(0, 4), (612, 622), (1019, 1024)]
+    assert [c[2] for c in ch] == [20.0, 50.0, 20.0] and all(c[3] == 1.0 for c in ch)
+    assert ch[1][4] == 50.0
+    # second update with the carrier gone: the average halves its excess, the floor stays
+    psd2 = np.ones((1, N), np.float32)
+    ch2, _ = d.feed(psd2)
+    assert (ch2[1][0], ch2[1][1], ch2[1][2]) == (612, 622, 25.5)
+    # noise floor = (N/4)-th smallest averaged bin, smoothed by gamma
+    rng = np.random.default_rng(0)
+    p3 = rng.exponential(1.0, (1, N)).astype(np.float32)
+    d3 = oracle.ChannelDetector(N, 1.0, 0.25, 1e9, 1)
+    d3.feed(p3)
+    assert d3.d.n0 == np.sort(p3[0])[N // 4]
+    p4 = (p3 * 3).astype(np.float32)
+    d3.feed(p4)
+    n0 = np.float32(np.sort(p3[0])[N // 4])
+    assert d3.d.n0 == np.float32(n0 + np.float32(0.25) * (np.float32(np.sort(p4[0])[N // 4]) - n0))
+    for x in (d, d3):
+        x.close()
