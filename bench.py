@@ -273,14 +273,15 @@ def run_cuda(args):
     fam = {f: e.kernel_time(f) for f in ("fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft", "inspector")}
     e.timing(False)
     wps, frames = H, H // 2
-    if "SDB_SCRATCH_MB" in os.environ:
-        chunk = max(1, (int(os.environ["SDB_SCRATCH_MB"]) << 20) // (N_FFT * 8))
-    else:
-        chunk = torch.cuda.get_device_properties(local).multi_processor_count   # one window per SM (engine.cu)
+    timed_steps = 2
     nb = sum(2 * (e.channel_info(h).width // 2) for h in hs)
-    alg = {"fft_cols": min(chunk, S * wps) * N_FFT * 8.0,
-           "fft_rows_psd": min(chunk, S * frames) * N_FFT * 4.0,
-           "fft_rows_chan": min(chunk, S * wps) * nb * 8.0,
+    # ALGORITHMIC bytes one step moves through each kernel family (DESIGN.md "Kernels"): pass A reads every
+    # window once (PSD frames + channeliser windows), pass B writes the PSD / the needed bins; the four-step
+    # scratch is not algorithmic.  Launches of a family differ in size (PSD and channeliser groups), so the
+    # rate is total bytes / total device time of the family over the timed steps.
+    alg = {"fft_cols": S * (frames + wps) * N_FFT * 8.0,
+           "fft_rows_psd": S * frames * N_FFT * 4.0,
+           "fft_rows_chan": S * wps * nb * 8.0,
            "chan_ifft": S * wps * nb * 8.0 + sum(S * wps * e.channel_info(h).size // 2 * 8.0 for h in hs),
            "inspector": sum(S * wps * e.channel_info(h).size // 2 * 8.0 for h in hs) * 1.5}
     tot = {f: fam[f][0] * fam[f][1] for f in fam}
@@ -295,9 +296,22 @@ def run_cuda(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach = alg[dom] / (fam[dom][0] * 1e-3) / 1e9 if fam[dom][0] > 0 else 0.0
+    ach = alg[dom] * timed_steps / (tot[dom] * 1e-3) / 1e9 if tot[dom] > 0 else 0.0
+    launches_dom = max(1, int(fam[dom][1]))
+    traffic = None
+    try:   # DRAM bytes per window of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom in tr:
+            traffic = tr[dom]["dram_bytes_per_window"] * S * (frames + wps if dom == "fft_cols" else
+                                                               frames if dom == "fft_rows_psd" else wps) \
+                * timed_steps / launches_dom
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg[dom] * timed_steps / launches_dom,
+                "note": "CUDA-event spans; the PSD and channeliser chains run on two streams, so a kernel's span "
+                        "includes the share of the GPU its concurrent sibling takes",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "kernel_share_of_step": tot[dom] / max(1e-9, sum(tot.values())),
                 "kernel_ms": {f: round(fam[f][0], 4) for f in fam},
@@ -428,7 +442,10 @@ def main():
     ap.add_argument("--no-formats", action="store_true")
     args = ap.parse_args()
     if args.streams == 0:
-        args.streams = 1024 if args.workload == "cfg2" else 128
+        # cfg2: the (latency-bound) inspector kernel of 1024 single-channel streams takes about as long as their
+        # transforms; 2048 streams put the transforms on the critical path (33.9 / 53.3 / 64.5 GS/s at 512 / 1024 /
+        # 2048 streams on one B200, profiles/r01_batch.md)
+        args.streams = 2048 if args.workload == "cfg2" else 128
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -67,7 +67,7 @@ struct sdb_engine {
   SdbFourStep fs_psd{}, fs_st{};
   bool psd_small = false;
   float *d_window = nullptr;
-  float2 *d_scratch = nullptr; int chunk_windows = 1; size_t l2_pinned_bytes = 0;
+  float2 *d_scratch = nullptr; int chunk_windows = 1; size_t l2_pinned_bytes = 0; int sm_count = 0;
   // The PSD transforms run on their own stream, concurrently with the channeliser transforms of the same
   // group of streams (feed_device): the two kernel chains fill each other's launch gaps and partial waves,
   // and both read the same input region while it is still in L2.
@@ -548,6 +548,7 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->prm.device) == cudaSuccess && sms > 0 &&
             (size_t) sms * big * sizeof(float2) <= (100u << 20))
           cw = (size_t) sms;
+        e->sm_count = sms;
       }
       if (const char *env = getenv("SDB_CHUNK_WINDOWS")) { long v = atol(env); if (v >= 1 && v <= 65536) cw = (size_t) v; }
       e->chunk_windows = (int) cw;
@@ -559,7 +560,7 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       }
       // Pin the scratch in L2.  Without this the streamed input and output evict it between the two passes
       // and every window costs two extra HBM round trips (ncu: 266 MB of DRAM traffic per 148-window chunk
-      // against 116 MB algorithmic, profiles/r02_l2.md).  Accesses of the transform streams inside the window
+      // against 116 MB algorithmic, profiles/r01_l2.md).  Accesses of the transform streams inside the window
       // are "persisting" (a set-aside part of L2 that normal traffic cannot evict); the kernels additionally
       // mark their one-shot outputs as streaming (st.global.cs).
       if (!getenv("SDB_NO_L2_PIN")) {
@@ -824,7 +825,14 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
   // Stream groups: G whole streams per step, PSD frames on psd_stream and channeliser windows on the main stream,
   // each with its own part of the pinned scratch (G * (frames + wps) windows <= chunk_windows).
   int G = 0;
-  if (e->psd_stream && Np && !e->psd_small && wps > 0) G = e->chunk_windows / (frames + wps);
+  if (e->psd_stream && Np && !e->psd_small && wps > 0) {
+    G = e->chunk_windows / (frames + wps);
+    // the largest group that fits the pinned scratch is the fastest (cfg2, 2048 streams: 12 streams 64.7 GS/s,
+    // 9 streams -- whole waves for either kernel alone -- 63.1, 8: 60.2, 6: 54.2; the two chains overlap, so
+    // wave quantisation of a single launch does not matter)
+    if (const char *env = getenv("SDB_GROUP_STREAMS")) { const long v = atol(env); if (v >= 1 && v <= G * 4) G = (int) v; }
+    if ((size_t) G * (frames + wps) > (size_t) e->chunk_windows) G = e->chunk_windows / (frames + wps);
+  }
   if (G > (int) S) G = (int) S;
 
   if (Np) {

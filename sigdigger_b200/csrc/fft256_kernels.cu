@@ -5,12 +5,14 @@
 //   pass A (k_cols256): a CTA owns 16 adjacent columns of a window: every thread issues 16 independent
 //       coalesced float2 loads (128 B per thread in flight), optional window multiply, radix-16 over the
 //       high row digit, twiddle W_256^(t ka), exchange, radix-16 over the low row digit, inter-pass twiddle
-//       W_65536^(n2 k1) from two 256-entry tables (coarse x fine), transposed coalesced store.
+//       W_65536^(n2 k1) = coarse x fine (SPEC F.4) read from a [k1][n2] table tabulated once with the same
+//       arithmetic, transposed coalesced store into the L2-pinned scratch.
 //   pass B (k_rows256): a CTA owns 32 rows of the scratch; same two butterflies; the second one is mapped
 //       so that a warp holds 32 consecutive output bins -> 128-byte PSD / compacted-spectrum stores.
 //
 // Same mathematics as the generic path in fft_kernels.cu (which remains for every other size); results
-// agree with the oracle to SPEC.md section T.  Replaces the forward FFTs of su_specttuner
+// are bit-identical to oracle/fft_spec.c (SPEC.md F.4).  Designs measured and rejected: profiles/r01_experiments.md.
+// Replaces the forward FFTs of su_specttuner
 // (Tasks/LPFTask.cpp:83-87) and of the PSD (Suscan/Messages/PSDMessage.cpp:26-39).
 #include "sdb_internal.h"
 #include "sdb_math.h"

@@ -14,8 +14,9 @@
 //     cross-fade with the previous half window, optional per-sample LO ("precise").
 //
 // Reference behaviour being replaced: su_specttuner feed (Tasks/LPFTask.cpp:52-69,83-87) and the PSD
-// message payload (Suscan/Messages/PSDMessage.cpp:26-39).  Compiled WITH fma contraction: results are
-// compared with the oracle to the float tolerance of SPEC.md section T, not bit-exactly.
+// message payload (Suscan/Messages/PSDMessage.cpp:26-39).  Compiled with -fmad=false; the only fused operations
+// are the explicit __fmaf_rn of SPEC F.1 (twiddle products, PSD power), so results are bit-identical to
+// oracle/fft_spec.c.
 #include "sdb_internal.h"
 #include "../../include/sigdigger_b200.h"
 #include "sdb_math.h"
