@@ -304,7 +304,17 @@ typedef struct {                  /* suscan_analyzer_sample_batch_msg (+ the GUI
 typedef struct {                  /* suscan_analyzer_inspector_msg, fields this path fills */
   int32_t kind; uint32_t inspector_id, req_id; int32_t handle; char *class_name; sdb_sigutils_channel channel;
   sdb_inspector_config config; float fs, equiv_fs, bandwidth, lo;
+  /* kind = OPEN: sizes of the spectrum-source / estimator lists (names: sdb_spectsrc_name(1..), sdb_estimator_name)
+   * (spectsrc_count / estimator_count, Suscan/Messages/InspectorMessage.cpp:40-61).
+   * kind = SPECTRUM: spectsrc_id, spectrum_data[spectrum_size] (linear power, DC at 0), samp_rate
+   * (InspectorMessage.cpp:75-100); kind = ESTIMATOR: estimator_id, enabled, value (:120-135). */
+  uint32_t spectsrc_count, estimator_count;
+  uint32_t spectsrc_id; float *spectrum_data; uint64_t spectrum_size; uint64_t samp_rate;
+  uint32_t estimator_id; int32_t enabled; float value;
 } sdb_analyzer_inspector_msg;
+/* suscan_analyzer_channel_msg (Suscan/Messages/ChannelMessage.cpp:25-70): posted every channel_update_int seconds
+ * of signal time when channel_update_int > 0 */
+typedef struct { const void *source; uint32_t channel_count; sdb_detected_channel *channel_list; } sdb_analyzer_channel_msg;
 typedef struct { int32_t code; char *err_msg; } sdb_analyzer_status_msg;   /* suscan_analyzer_status_msg */
 typedef struct {                  /* suscan_source_info, fields this path fills */
   uint64_t permissions, source_samp_rate, effective_samp_rate; float measured_samp_rate; double frequency;
@@ -324,6 +334,10 @@ int    sdb_analyzer_set_inspector_id_async(sdb_analyzer_t *a, int32_t handle, ui
 int    sdb_analyzer_set_inspector_config_async(sdb_analyzer_t *a, int32_t handle, const sdb_inspector_config *cfg,
                                                uint32_t req_id);
 int    sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint32_t req_id);
+/* suscan_analyzer_inspector_set_spectrum_async / _estimator_cmd_async (Suscan/Analyzer.cpp:539-565) */
+int    sdb_analyzer_inspector_set_spectrum_async(sdb_analyzer_t *a, int32_t handle, uint32_t spectsrc_id, uint32_t req_id);
+int    sdb_analyzer_inspector_estimator_cmd_async(sdb_analyzer_t *a, int32_t handle, uint32_t estimator_id,
+                                                  int enabled, uint32_t req_id);
 int    sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyzer_params *p, uint32_t req_id);
 uint64_t sdb_analyzer_get_samp_rate(const sdb_analyzer_t *a);
 float    sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a);

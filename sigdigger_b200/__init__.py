@@ -149,6 +149,8 @@ _PROTOS = {
     "sdb_analyzer_set_inspector_config_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32]),
     "sdb_analyzer_close_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
     "sdb_analyzer_set_params_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sdb_analyzer_inspector_set_spectrum_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32]),
+    "sdb_analyzer_inspector_estimator_cmd_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int, C.c_uint32]),
     "sdb_analyzer_get_samp_rate": (C.c_uint64, [C.c_void_p]),
     "sdb_analyzer_get_measured_samp_rate": (C.c_float, [C.c_void_p]),
     "sdb_sview_new": (C.c_void_p, [C.c_int]),

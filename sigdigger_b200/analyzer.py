@@ -56,7 +56,14 @@ class SampleBatchMsg(C.Structure):
 class InspectorMsg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("inspector_id", C.c_uint32), ("req_id", C.c_uint32), ("handle", C.c_int32),
                 ("class_name", C.c_char_p), ("channel", SigutilsChannel), ("config", InspectorConfig),
-                ("fs", C.c_float), ("equiv_fs", C.c_float), ("bandwidth", C.c_float), ("lo", C.c_float)]
+                ("fs", C.c_float), ("equiv_fs", C.c_float), ("bandwidth", C.c_float), ("lo", C.c_float),
+                ("spectsrc_count", C.c_uint32), ("estimator_count", C.c_uint32), ("spectsrc_id", C.c_uint32),
+                ("spectrum_data", C.POINTER(C.c_float)), ("spectrum_size", C.c_uint64), ("samp_rate", C.c_uint64),
+                ("estimator_id", C.c_uint32), ("enabled", C.c_int32), ("value", C.c_float)]
+
+
+class ChannelMsg(C.Structure):
+    _fields_ = [("source", C.c_void_p), ("channel_count", C.c_uint32), ("channel_list", C.c_void_p)]
 
 
 class StatusMsg(C.Structure):
@@ -65,13 +72,17 @@ class StatusMsg(C.Structure):
 
 class Analyzer:
     def __init__(self, samp_rate, window_size=8192, window="hann", psd_update_int=0.04, data=None, read=None,
-                 read_size=0, loop=False, freq=0.0, device=0):
+                 read_size=0, loop=False, freq=0.0, device=0, channel_update_int=0.0, alpha=0.25, beta=0.25,
+                 gamma=0.5, snr=8.0):
         self._L = load_library()
         p = AnalyzerParams()
         p.mode = 0
         p.detector_params.window_size = window_size
         p.detector_params.window = WINDOW[window] if isinstance(window, str) else window
+        p.detector_params.alpha, p.detector_params.beta = alpha, beta
+        p.detector_params.gamma, p.detector_params.snr = gamma, snr
         p.psd_update_int = psd_update_int
+        p.channel_update_int = channel_update_int
         self.params = p
         s = SourceConfig()
         s.samp_rate, s.freq, s.read_size, s.loop, s.device = samp_rate, freq, read_size, int(loop), device
@@ -108,6 +119,12 @@ class Analyzer:
     def set_inspector_config(self, handle, cfg, req_id=0):
         self._L.sdb_analyzer_set_inspector_config_async(self._h, handle, C.byref(cfg), req_id)
 
+    def set_spectrum_source(self, handle, spectsrc_id, req_id=0):
+        self._L.sdb_analyzer_inspector_set_spectrum_async(self._h, handle, spectsrc_id, req_id)
+
+    def estimator_cmd(self, handle, estimator_id, enabled=True, req_id=0):
+        self._L.sdb_analyzer_inspector_estimator_cmd_async(self._h, handle, estimator_id, int(enabled), req_id)
+
     def close_inspector(self, handle, req_id=0):
         self._L.sdb_analyzer_close_async(self._h, handle, req_id)
 
@@ -138,7 +155,18 @@ class Analyzer:
                 C.memmove(C.byref(cfg), C.byref(m.config), C.sizeof(cfg))
                 out = dict(kind=KIND.get(m.kind, m.kind), req_id=m.req_id, handle=m.handle,
                            inspector_id=m.inspector_id, class_name=(m.class_name or b"").decode(), config=cfg,
-                           fs=m.fs, equiv_fs=m.equiv_fs, bandwidth=m.bandwidth, lo=m.lo)
+                           fs=m.fs, equiv_fs=m.equiv_fs, bandwidth=m.bandwidth, lo=m.lo,
+                           spectsrc_count=m.spectsrc_count, estimator_count=m.estimator_count,
+                           spectsrc_id=m.spectsrc_id, estimator_id=m.estimator_id, enabled=m.enabled, value=m.value,
+                           samp_rate=m.samp_rate, spectrum=None)
+                if m.spectrum_data and m.spectrum_size:
+                    out["spectrum"] = np.ctypeslib.as_array(m.spectrum_data, shape=(m.spectrum_size,)).copy()
+            elif name == "CHANNEL":
+                from . import DetectedChannel
+                m = C.cast(ptr, C.POINTER(ChannelMsg)).contents
+                arr = C.cast(m.channel_list, C.POINTER(DetectedChannel))
+                out = dict(channels=[dict(fc=arr[i].fc, f_lo=arr[i].f_lo, f_hi=arr[i].f_hi, bw=arr[i].bw,
+                                          snr=arr[i].snr, S0=arr[i].S0, N0=arr[i].N0) for i in range(m.channel_count)])
             elif name in ("EOS", "READ_ERROR", "HALT", "SOURCE_INIT"):
                 m = C.cast(ptr, C.POINTER(StatusMsg)).contents
                 out = dict(code=m.code, err_msg=(m.err_msg or b"").decode())

@@ -33,8 +33,9 @@
 namespace {
 
 struct Cmd {
-  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS } kind;
+  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD } kind;
   uint32_t req_id = 0;
+  uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
   int32_t handle = -1;
   uint32_t inspector_id = 0;
   std::string cls;
@@ -55,6 +56,9 @@ struct Insp {
   sdb_inspector_config cfg;
   int engine_handle;      // handle inside the current engine, -1 if not mapped
   float fs, bandwidth, lo;
+  uint32_t spectsrc_id;   // 0 = none (index 0 of the GUI's combo)
+  uint32_t est_mask;
+  uint32_t spect_size;    // frame size chosen at rebuild time (0 = too few channel samples per block)
 };
 
 int class_id(const std::string &c)
@@ -118,10 +122,13 @@ struct sdb_analyzer {
     m->inspector_id = i ? i->inspector_id : c.inspector_id;
     m->class_name = dupstr(i ? (const char *[]){ "psk", "fsk", "ask", "audio", "raw" }[i->cls] : c.cls.c_str());
     if (i) { m->channel = i->channel; m->config = i->cfg; m->fs = (float) src.samp_rate; m->equiv_fs = i->fs;
-             m->bandwidth = i->bandwidth; m->lo = i->lo; }
+             m->bandwidth = i->bandwidth; m->lo = i->lo; m->spectsrc_id = i->spectsrc_id; }
     else m->channel = c.channel;
+    m->spectsrc_count = SDB_SPECTSRC_COUNT - 1; m->estimator_count = SDB_ESTIMATOR_COUNT;
+    if (kind == SDB_INSPECTOR_MSGKIND_ESTIMATOR) { m->estimator_id = c.aux_id; m->enabled = c.enabled; }
     post(SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR, m);
   }
+  double chan_credit = 0;
 
   // (re)build the engine from the open inspectors; returns false on failure (status message posted)
   bool rebuild()
@@ -155,7 +162,24 @@ struct sdb_analyzer {
       i.lo = (float) i.channel.fc;
       i.cfg.insp_class = i.cls;
       sdb_engine_set_inspector(eng, h, &i.cfg);
+      // spectrum source / estimators: the largest frame (<= 4096) a steady-state block can fill (SPEC U.1)
+      i.spect_size = 0;
+      if (i.spectsrc_id || i.est_mask) {
+        const size_t n_ch = block / (ep.psd_size / 2) * (info.size / 2);
+        uint32_t ns = 4096;
+        while (ns >= 64 && (size_t) ns + 1 > n_ch) ns >>= 1;
+        if (ns >= 64) {
+          i.spect_size = ns;
+          sdb_engine_set_spectrum_source(eng, h, (int) i.spectsrc_id, ns);
+          for (int e = 0; e < SDB_ESTIMATOR_COUNT; ++e)
+            if (i.est_mask & (1u << e)) sdb_engine_set_estimator(eng, h, e, 1);
+        }
+      }
     }
+    if (params.channel_update_int > 0)
+      sdb_engine_set_channel_detector(eng, params.detector_params.alpha, params.detector_params.beta,
+                                      params.detector_params.gamma,
+                                      params.detector_params.snr > 0 ? params.detector_params.snr : 4.0f, 2);
     if (sdb_engine_commit(eng)) {
       post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error());
       return false;
@@ -206,12 +230,23 @@ struct sdb_analyzer {
         }
         case Cmd::SET_ID:
         case Cmd::SET_CONFIG:
+        case Cmd::SET_SPECTRUM:
+        case Cmd::ESTIMATOR_CMD:
         case Cmd::CLOSE: {
           if (c.handle < 0 || c.handle >= (int32_t) insps.size() || !insps[c.handle].open) {
             post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_HANDLE, c, nullptr); break;
           }
           Insp &i = insps[c.handle];
-          if (c.kind == Cmd::SET_ID) {
+          if (c.kind == Cmd::SET_SPECTRUM) {
+            if (c.aux_id >= (uint32_t) SDB_SPECTSRC_COUNT) { post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_OBJECT, c, nullptr); break; }
+            i.spectsrc_id = c.aux_id; plan_dirty = true;
+            post_inspector(SDB_INSPECTOR_MSGKIND_SPECTRUM, c, &i);     // acknowledgement: no spectrum_data yet
+          } else if (c.kind == Cmd::ESTIMATOR_CMD) {
+            if (c.aux_id >= (uint32_t) SDB_ESTIMATOR_COUNT) { post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_OBJECT, c, nullptr); break; }
+            if (c.enabled) i.est_mask |= 1u << c.aux_id; else i.est_mask &= ~(1u << c.aux_id);
+            plan_dirty = true;
+            post_inspector(SDB_INSPECTOR_MSGKIND_ESTIMATOR, c, &i);    // acknowledgement: value follows per block
+          } else if (c.kind == Cmd::SET_ID) {
             i.inspector_id = c.inspector_id; i.has_id = true;
             post_inspector(SDB_INSPECTOR_MSGKIND_SET_ID, c, &i);
           } else if (c.kind == Cmd::SET_CONFIG) {
@@ -315,6 +350,52 @@ struct sdb_analyzer {
         memcpy(m->symbols, hard.data(), (size_t) n);
         post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
       }
+      // kind=SPECTRUM / kind=ESTIMATOR inspector messages (one per block that filled a frame)
+      for (auto &i : insps) {
+        if (!i.open || i.engine_handle < 0 || !i.spect_size) continue;
+        if (i.spectsrc_id) {
+          std::vector<float> sp(i.spect_size);
+          uint32_t emitted = 0;
+          if (sdb_engine_read_spectrum(eng, i.engine_handle, sp.data(), &emitted) == 0 && emitted) {
+            sdb_analyzer_inspector_msg *m = (sdb_analyzer_inspector_msg *) calloc(1, sizeof(*m));
+            m->kind = SDB_INSPECTOR_MSGKIND_SPECTRUM; m->handle = i.handle; m->inspector_id = i.inspector_id;
+            m->class_name = dupstr((const char *[]){ "psk", "fsk", "ask", "audio", "raw" }[i.cls]);
+            m->spectsrc_id = i.spectsrc_id; m->spectrum_size = emitted; m->samp_rate = (uint64_t) i.fs;
+            m->fs = (float) src.samp_rate; m->equiv_fs = i.fs;
+            m->spectrum_data = (float *) malloc(emitted * sizeof(float));
+            memcpy(m->spectrum_data, sp.data(), emitted * sizeof(float));
+            post(SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR, m);
+          }
+        }
+        for (int e = 0; e < SDB_ESTIMATOR_COUNT; ++e) {
+          if (!(i.est_mask & (1u << e))) continue;
+          float v = 0; int32_t ok = 0;
+          if (sdb_engine_read_estimate(eng, i.engine_handle, e, &v, &ok) == 0 && ok) {
+            sdb_analyzer_inspector_msg *m = (sdb_analyzer_inspector_msg *) calloc(1, sizeof(*m));
+            m->kind = SDB_INSPECTOR_MSGKIND_ESTIMATOR; m->handle = i.handle; m->inspector_id = i.inspector_id;
+            m->class_name = dupstr((const char *[]){ "psk", "fsk", "ask", "audio", "raw" }[i.cls]);
+            m->estimator_id = (uint32_t) e; m->enabled = 1; m->value = v;
+            post(SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR, m);
+          }
+        }
+      }
+      // MESSAGE_TYPE_CHANNEL at channel_update_int cadence of signal time
+      if (params.channel_update_int > 0) {
+        chan_credit += (double) block / src.samp_rate;
+        if (chan_credit + 1e-12 >= params.channel_update_int) {
+          chan_credit = fmod(chan_credit, params.channel_update_int);
+          std::vector<sdb_detected_channel> ch(256);
+          uint32_t total = 0;
+          long nc = sdb_engine_read_channels(eng, 0, src.freq, ch.data(), ch.size(), &total);
+          if (nc >= 0) {
+            sdb_analyzer_channel_msg *m = (sdb_analyzer_channel_msg *) calloc(1, sizeof(*m));
+            m->channel_count = (uint32_t) nc;
+            m->channel_list = (sdb_detected_channel *) malloc(std::max<long>(1, nc) * sizeof(sdb_detected_channel));
+            memcpy(m->channel_list, ch.data(), (size_t) nc * sizeof(sdb_detected_channel));
+            post(SDB_ANALYZER_MESSAGE_TYPE_CHANNEL, m);
+          }
+        }
+      }
     }
     if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
     post_status(exit_type, 0, exit_type == SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR ? sdb_last_error() : nullptr);
@@ -372,7 +453,10 @@ extern "C" void sdb_analyzer_dispose_message(uint32_t type, void *ptr)
       free(((sdb_analyzer_sample_batch_msg *) ptr)->samples);
       free(((sdb_analyzer_sample_batch_msg *) ptr)->symbols); break;
     case SDB_ANALYZER_MESSAGE_TYPE_INSPECTOR:
-      free(((sdb_analyzer_inspector_msg *) ptr)->class_name); break;
+      free(((sdb_analyzer_inspector_msg *) ptr)->class_name);
+      free(((sdb_analyzer_inspector_msg *) ptr)->spectrum_data); break;
+    case SDB_ANALYZER_MESSAGE_TYPE_CHANNEL:
+      free(((sdb_analyzer_channel_msg *) ptr)->channel_list); break;
     case SDB_ANALYZER_MESSAGE_TYPE_EOS:
     case SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR:
     case SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT:
@@ -430,6 +514,18 @@ extern "C" int sdb_analyzer_set_inspector_config_async(sdb_analyzer_t *a, int32_
 extern "C" int sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint32_t req_id)
 {
   Cmd c; c.kind = Cmd::CLOSE; c.req_id = req_id; c.handle = handle;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_inspector_set_spectrum_async(sdb_analyzer_t *a, int32_t handle, uint32_t spectsrc_id,
+                                                         uint32_t req_id)
+{
+  Cmd c; c.kind = Cmd::SET_SPECTRUM; c.req_id = req_id; c.handle = handle; c.aux_id = spectsrc_id;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_inspector_estimator_cmd_async(sdb_analyzer_t *a, int32_t handle, uint32_t estimator_id,
+                                                          int enabled, uint32_t req_id)
+{
+  Cmd c; c.kind = Cmd::ESTIMATOR_CMD; c.req_id = req_id; c.handle = handle; c.aux_id = estimator_id; c.enabled = enabled;
   return push_cmd(a, std::move(c));
 }
 extern "C" int sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyzer_params *p, uint32_t req_id)

@@ -103,3 +103,69 @@ def test_analyzer_memory_source_halt(sdb):
             break
     assert name == "HALT"
     a.close()
+
+
+def test_analyzer_spectrum_estimator_and_channel_messages(sdb, oracle):
+    """kind=SPECTRUM / kind=ESTIMATOR inspector messages and MESSAGE_TYPE_CHANNEL lists
+    (Suscan/Analyzer.cpp:539-565, GenericInspector.cpp:232-264, ChannelMessage.cpp:25-70)."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 8192, 1.0e6
+    baud = fs / 64.0
+    blocks, per_block = 5, N * 16
+    n = blocks * per_block
+    x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs, baud, -10.0, {})], noise_db=-50.0, seed=5)
+    go = threading.Event()
+    pos = [0]
+
+    def read(priv, dst, maxn):
+        go.wait(30)
+        take = min(maxn, n - pos[0])
+        if take > 0:
+            C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+            pos[0] += take
+        return take
+
+    a = Analyzer(fs, window_size=N, window="blackmann_harris", psd_update_int=1.0, read=read, read_size=per_block,
+                 channel_update_int=per_block / fs, alpha=0.5, gamma=0.5, snr=10.0, freq=433e6)
+    assert a.read(5000)[0] == "SOURCE_INFO"
+    a.open("psk", 0.125 * fs, 8 * baud, req_id=1)          # 8 samples per symbol at the channel rate
+    a.set_inspector_id(0, 77, req_id=2)
+    a.set_spectrum_source(0, sdb.SPECTSRC["exp_4"], req_id=3)
+    a.estimator_cmd(0, sdb.ESTIMATOR["baud-nonlinear"], True, req_id=4)
+    a.set_spectrum_source(0, 99, req_id=5)                  # unknown source -> WRONG_OBJECT
+    go.set()
+    spectra, estimates, channels, acks = [], [], [], []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "INSPECTOR":
+            if m["kind"] == "SPECTRUM" and m["spectrum"] is not None:
+                assert m["spectsrc_id"] == sdb.SPECTSRC["exp_4"] and m["inspector_id"] == 77
+                spectra.append(m)
+            elif m["kind"] == "ESTIMATOR" and m["req_id"] == 0:
+                estimates.append(m)
+            else:
+                acks.append((m["kind"], m["req_id"]))
+                if m["kind"] == "OPEN":
+                    assert (m["spectsrc_count"], m["estimator_count"]) == (9, 2)
+        elif name == "CHANNEL":
+            channels.append(m["channels"])
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    a.close()
+    assert name == "EOS"
+    assert acks == [("OPEN", 1), ("SET_ID", 2), ("SPECTRUM", 3), ("ESTIMATOR", 4), ("WRONG_OBJECT", 5)]
+    # requests are applied at block boundaries: blocks 2.. carry a spectrum and an estimate each
+    assert len(spectra) >= 3 and len(estimates) >= 3
+    fs_ch = spectra[0]["equiv_fs"]
+    assert spectra[0]["samp_rate"] == int(fs_ch) and len(spectra[0]["spectrum"]) in (1024, 2048, 4096)
+    for e in estimates:
+        assert e["estimator_id"] == 1 and abs(e["value"] - baud) / baud < 0.02
+    # the 4th power of QPSK: a line at 4x the residual carrier offset (here ~0) dominates the spectrum
+    s = spectra[-1]["spectrum"]
+    k = int(np.argmax(s))
+    assert min(k, len(s) - k) <= 2
+    # one CHANNEL list per block; the carrier is found at its place, reported in absolute frequency
+    assert len(channels) == blocks
+    hit = [c for c in channels[-1] if c["f_lo"] <= 433e6 + 0.125 * fs <= c["f_hi"]]
+    assert len(hit) == 1 and 0.7 * baud < hit[0]["bw"] < 2.5 * baud and hit[0]["snr"] > 10.0
