@@ -227,8 +227,8 @@ static __device__ __forceinline__ unsigned char decide(int mode, float dmin, flo
 // lives in registers for the whole feed.  Chains are ordered channel-major so a warp normally holds 32
 // streams of the SAME channel (uniform configuration, no divergence).
 #define CHUNK 32
-#define MF_RING 64      // longest matched filter kept in shared memory
-#define MF_SLOTS 80     // 8 margin + 2 * 32 (duplicated short line) or 64 (single long line), + slack
+// matched-filter line: 8 margin + 2 n slots (duplicated line, n <= 32 taps) or n slots (single line, up to 136);
+// the slot count of a launch comes from the channel plan (SdbInspDyn, sdb_internal.h)
 __device__ unsigned long long g_stage_cycles[8];
 
 cudaError_t sdb_stage_cycles(unsigned long long out[8], int reset)
@@ -248,14 +248,15 @@ static __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsr
 static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Fixed part of the CTA's shared memory.  The per-chain state lines that depend on the channel plan follow it,
+// sized per launch (SdbInspDyn): matched-filter line [mf_slots][32] float2, AGC delay line + magnitude history
+// [agc_rows][32] float, CMA weights and line 2 x [SDB_EQ_LEN][32] float2 when some chain equalises.  cfg2 (19 taps,
+// 36 AGC floats) needs 84 KB, cfg3 (75 taps, 144 AGC floats) 112 KB: both leave two CTAs per SM.  A chain whose
+// lines do not fit keeps them in the global pool (correct, slower: a global round trip inside the recurrence).
 struct ChainSmem {
   float2 tile[2][32][33];
   float2 ring[3][2][CHUNK][32];
-  float2 mfh[MF_SLOTS][32];
-  float  agc[48][32];
   float  lvl[CHUNK][32];
-  float2 eqw[SDB_EQ_LEN][32];     // CMA weights and line (SPEC E), one column per chain
-  float2 eqx[SDB_EQ_LEN][32];
 };
 
 // SPEC E: constant-modulus equaliser on the symbol stream.  Sums and updates run in index order.
@@ -319,10 +320,16 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
                                                      const float2 *__restrict__ chan_in,
                                                      size_t chan_stream_stride, uint32_t n_hops,
                                                      float2 *__restrict__ soft, unsigned char *__restrict__ hard,
-                                                     uint32_t *__restrict__ sym_counts, size_t sym_cap, int fresh)
+                                                     uint32_t *__restrict__ sym_counts, size_t sym_cap, int fresh,
+                                                     const SdbInspDyn dyn)
 {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
+  const int mf_slots = dyn.mf_slots, agc_rows = dyn.agc_rows;
+  float2 (*s_mfh)[32] = reinterpret_cast<float2 (*)[32]>(smem_raw + sizeof(ChainSmem));
+  float (*s_agc)[32] = reinterpret_cast<float (*)[32]>(smem_raw + sizeof(ChainSmem) + (size_t) mf_slots * 32 * sizeof(float2));
+  float2 (*s_eqw)[32] = reinterpret_cast<float2 (*)[32]>(reinterpret_cast<unsigned char *>(s_agc) + (size_t) agc_rows * 32 * sizeof(float));
+  float2 (*s_eqx)[32] = s_eqw + SDB_EQ_LEN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chains = n_channels * n_streams;
   const int g = blockIdx.x * 32 + lane;                // channel-major chain index
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
   float rot_re = 1, rot_im = 0, dc = 0, sq_level = 0, dc_alpha = 0, sq_alpha = 0, sq_thr = 0;
   int have_costas = 0, have_pll = 0, quad = 0, ask_ch = 0, ademod = 0, asquelch = 0;
   // stage 2
-  int mf_n = 0, have_mf = 0, alpf_n = 0; unsigned mf_ptr = 0; const float *taps = nullptr; float *mfl = nullptr;
+  int mf_n = 0, have_mf = 0, alpf_n = 0; unsigned mf_ptr = 0; bool mf_smem = false; const float *taps = nullptr; float *mfl = nullptr;
   float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
   float tp[32];     // matched-filter taps in registers when mf_n <= 32
   // stage 3
@@ -373,10 +380,10 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       ak.hang_max = cp->hang_max; ak.dl_size = cp->dl_size; ak.mh_size = cp->mh_size;
       as.fast = stp->fast_level; as.slow = stp->slow_level; as.peak = stp->peak;
       as.hang_n = stp->hang_n; as.dl_ptr = stp->dl_ptr; as.mh_ptr = stp->mh_ptr;
-      const bool in_smem = 2 * ak.dl_size + ak.mh_size <= 48;
+      const bool in_smem = 2 * ak.dl_size + ak.mh_size <= (unsigned) agc_rows;
       float *gdl = bpool + (size_t) cp->st_dl_off * 32, *gmh = bpool + (size_t) cp->st_mh_off * 32;
       if (in_smem && have_agc) {
-        dl = &sm.agc[0][lane]; mh = &sm.agc[2 * ak.dl_size][lane];
+        dl = &s_agc[0][lane]; mh = &s_agc[2 * ak.dl_size][lane];
         for (unsigned i = 0; i < 2 * ak.dl_size; ++i) dl[i * 32] = fresh ? 0.0f : gdl[i * 32];
         for (unsigned i = 0; i < ak.mh_size; ++i) mh[i * 32] = fresh ? -160.0f : gmh[i * 32];
       } else {
@@ -412,13 +419,14 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
 #pragma unroll
       for (int t = 0; t < 32; ++t) tp[t] = (have_mf && t < mf_n) ? __ldg(taps + t) : 0.0f;
       float *gmf = bpool + (size_t) cp->st_mf_off * 32;
-      for (int i = 0; i < MF_SLOTS; ++i) sm.mfh[i][lane] = make_float2(0.f, 0.f);
-      if (have_mf && mf_n <= MF_RING) {
-        mfl = reinterpret_cast<float *>(&sm.mfh[0][lane]);   // float2 ring, stride 32 float2 = 64 floats
+      for (int i = 0; i < mf_slots; ++i) s_mfh[i][lane] = make_float2(0.f, 0.f);
+      mf_smem = have_mf && (mf_n <= 32 ? 8 + 2 * mf_n <= mf_slots : mf_n <= mf_slots);
+      if (mf_smem) {
+        mfl = reinterpret_cast<float *>(&s_mfh[0][lane]);   // float2 ring, stride 32 float2 = 64 floats
         for (int i = 0; i < mf_n; ++i) {
           float2 v = fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * i) * 32], gmf[(2 * i + 1) * 32]);
-          if (mf_n <= 32) { sm.mfh[8 + i][lane] = v; sm.mfh[8 + i + mf_n][lane] = v; }   // duplicated line
-          else sm.mfh[i][lane] = v;
+          if (mf_n <= 32) { s_mfh[8 + i][lane] = v; s_mfh[8 + i + mf_n][lane] = v; }   // duplicated line
+          else s_mfh[i][lane] = v;
         }
       } else {
         mfl = gmf;
@@ -436,8 +444,8 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       eq_type = cp->eq_type; eq_locked = cp->eq_locked; eq_mu = cp->eq_mu;
       if (eq_type == 1) {
         for (int i = 0; i < SDB_EQ_LEN; ++i) {
-          sm.eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
-          sm.eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
+          s_eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
+          s_eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
         }
       }
     }
@@ -604,25 +612,37 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
             float2 y = in[i][lane];
             if (have_mf) {
               float accr = 0.0f, acci = 0.0f;
-              if (mf_n <= 32) {
+              if (mf_smem && mf_n <= 32) {
                 // taps in registers, duplicated line, branch-free unrolled sum (see mf_fir)
-                sm.mfh[8 + mf_ptr][lane] = y;
-                sm.mfh[8 + mf_ptr + mf_n][lane] = y;
+                s_mfh[8 + mf_ptr][lane] = y;
+                s_mfh[8 + mf_ptr + mf_n][lane] = y;
                 float2 r;
-                if (mf_n <= 8)       r = mf_fir<8>(sm.mfh, lane, mf_ptr, mf_n, tp);
-                else if (mf_n <= 16) r = mf_fir<16>(sm.mfh, lane, mf_ptr, mf_n, tp);
-                else if (mf_n <= 24) r = mf_fir<24>(sm.mfh, lane, mf_ptr, mf_n, tp);
-                else                 r = mf_fir<32>(sm.mfh, lane, mf_ptr, mf_n, tp);
+                if (mf_n <= 8)       r = mf_fir<8>(s_mfh, lane, mf_ptr, mf_n, tp);
+                else if (mf_n <= 16) r = mf_fir<16>(s_mfh, lane, mf_ptr, mf_n, tp);
+                else if (mf_n <= 24) r = mf_fir<24>(s_mfh, lane, mf_ptr, mf_n, tp);
+                else                 r = mf_fir<32>(s_mfh, lane, mf_ptr, mf_n, tp);
                 accr = r.x; acci = r.y;
-              } else if (mf_n <= MF_RING) {
-                sm.mfh[mf_ptr][lane] = y;
-                unsigned p = mf_ptr;
-                for (int t = 0; t < mf_n; ++t) {
+              } else if (mf_smem) {
+                // single line, two contiguous runs (newest ... slot 0, then slot mf_n-1 ... oldest): same tap order
+                // as SPEC I.1, but every address is affine in t, so the loads pipeline (the former per-tap
+                // "p = p ? p-1 : mf_n-1" chain made the 38-tap ASK filter of cfg3 the slowest stage of the kernel)
+                s_mfh[mf_ptr][lane] = y;
+                const int p0 = (int) mf_ptr;
+                const float2 *l0 = &s_mfh[p0][lane];
+                int t = 0;
+#pragma unroll 4
+                for (; t <= p0; ++t) {
                   const float b = __ldg(taps + t);
-                  const float2 v = sm.mfh[p][lane];
+                  const float2 v = l0[-t * 32];
                   accr = accr + b * v.x;
                   acci = acci + b * v.y;
-                  p = p == 0 ? mf_n - 1 : p - 1;
+                }
+#pragma unroll 4
+                for (; t < mf_n; ++t) {
+                  const float b = __ldg(taps + t);
+                  const float2 v = s_mfh[mf_n + p0 - t][lane];
+                  accr = accr + b * v.x;
+                  acci = acci + b * v.y;
                 }
               } else {
                 mfl[(2 * mf_ptr) * 32] = y.x; mfl[(2 * mf_ptr + 1) * 32] = y.y;
@@ -669,7 +689,7 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
               bool produced;
               if (clock_type == 1) produced = clock_step(clk_gain, clk_alpha, clk_beta, ks, y, o);
               else                 produced = sampler_step(smp_period, smp_phase0, s_phase, s_pr, s_pi, y, o);
-              if (produced && eq_type == 1) o = cma_step(sm.eqw, sm.eqx, lane, eq_mu, eq_locked, o);
+              if (produced && eq_type == 1) o = cma_step(s_eqw, s_eqx, lane, eq_mu, eq_locked, o);
               if (produced && clock_running && nout < sym_cap) {
                 o.x = 0.75f * o.x; o.y = 0.75f * o.y;
                 so[nout] = o;
@@ -695,7 +715,7 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       stp->fast_level = as.fast; stp->slow_level = as.slow; stp->peak = as.peak;
       stp->hang_n = as.hang_n; stp->dl_ptr = as.dl_ptr; stp->mh_ptr = as.mh_ptr;
       if (cls != SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
-      if (have_agc && 2 * ak.dl_size + ak.mh_size <= 48) {
+      if (have_agc && 2 * ak.dl_size + ak.mh_size <= (unsigned) agc_rows) {
         float *gdl = bpool + (size_t) cp->st_dl_off * 32, *gmh = bpool + (size_t) cp->st_mh_off * 32;
         for (unsigned i = 0; i < 2 * ak.dl_size; ++i) gdl[i * 32] = dl[i * 32];
         for (unsigned i = 0; i < ak.mh_size; ++i) gmh[i * 32] = mh[i * 32];
@@ -713,10 +733,10 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       stp->mf_ptr = mf_ptr;
 #pragma unroll
       for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
-      if (have_mf && mf_n <= MF_RING) {
+      if (mf_smem) {
         float *gmf = bpool + (size_t) cp->st_mf_off * 32;
         for (int i = 0; i < mf_n; ++i) {
-          float2 v = mf_n <= 32 ? sm.mfh[8 + i][lane] : sm.mfh[i][lane];
+          float2 v = mf_n <= 32 ? s_mfh[8 + i][lane] : s_mfh[i][lane];
           gmf[(2 * i) * 32] = v.x; gmf[(2 * i + 1) * 32] = v.y;
         }
       }
@@ -727,8 +747,8 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
       stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
       if (eq_type == 1) {
         for (int i = 0; i < SDB_EQ_LEN; ++i) {
-          stp->eq_wr[i] = sm.eqw[i][lane].x; stp->eq_wi[i] = sm.eqw[i][lane].y;
-          stp->eq_xr[i] = sm.eqx[i][lane].x; stp->eq_xi[i] = sm.eqx[i][lane].y;
+          stp->eq_wr[i] = s_eqw[i][lane].x; stp->eq_wi[i] = s_eqw[i][lane].y;
+          stp->eq_xr[i] = s_eqx[i][lane].x; stp->eq_xi[i] = s_eqx[i][lane].y;
         }
       }
       sym_counts[chain] = nout;
@@ -740,18 +760,22 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
                                     int n_streams, SdbChainState *state, float *pool, size_t pool_stride,
                                     const float *taps_pool, const SdbChannelDev *chans_dev,
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
-                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap, int fresh)
+                                    float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap, int fresh,
+                                    const SdbInspDyn &dyn)
 {
   const int chains = n_channels * n_streams;
   if (chains == 0) return cudaSuccess;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_inspectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ChainSmem));
+    cudaFuncSetAttribute(k_inspectors, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
     attr_done = true;
   }
-  k_inspectors<<<(chains + 31) / 32, 128, sizeof(ChainSmem), c.stream>>>(
+  const size_t smem = sizeof(ChainSmem) + (size_t) dyn.mf_slots * 32 * sizeof(float2) +
+                      (size_t) dyn.agc_rows * 32 * sizeof(float) +
+                      (dyn.use_eq ? 2 * (size_t) SDB_EQ_LEN * 32 * sizeof(float2) : 0);
+  k_inspectors<<<(chains + 31) / 32, 128, smem, c.stream>>>(
       cfg_dev, n_channels, n_streams, state, pool, pool_stride, taps_pool, chans_dev, chan_in,
-      chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap, fresh);
+      chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap, fresh, dyn);
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }

@@ -905,7 +905,8 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       e->span_begin(FAM_INSPECTOR, e->insp_stream);
       CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
                                  e->d_chans, e->d_chanb[b], e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
-                                 e->d_counts, e->sym_cap, e->chains_fresh ? 1 : 0));
+                                 e->d_counts, e->sym_cap, e->chains_fresh ? 1 : 0,
+                                 sdb_insp_dyn(e->h_cfg.data(), K)));
       e->chains_fresh = false;
       e->span_end(e->insp_stream);
       CK(cudaEventRecord(e->ev_insp[b], e->insp_stream));
@@ -1261,7 +1262,7 @@ extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_co
   SdbLaunchCtx ctx{ 0, nullptr };
   // every chain is "stream s, channel 0"; chan_stream_stride = n
   CK(sdb_launch_inspectors_n(ctx, d_cfg, 1, (int) batch, d_st, d_pool, pool, d_taps, d_cd, d_src, n,
-                             (uint32_t) n, d_soft, d_hard, d_cnt, cap, 1));
+                             (uint32_t) n, d_soft, d_hard, d_cnt, cap, 1, sdb_insp_dyn(&c, 1)));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(counts, d_cnt, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   if (soft) CK(cudaMemcpy(soft, d_soft, cap * batch * sizeof(float2), cudaMemcpyDeviceToHost));

@@ -156,6 +156,30 @@ struct SdbSpectCfg {
   size_t out_off;           // offset (floats) of this channel's spectrum inside one stream's block
 };
 
+// plan-dependent shared-memory lines of k_inspectors (chain_kernels.cu): sized from the channel plan
+struct SdbInspDyn {
+  int mf_slots;             // matched-filter line slots (8 + 2 n for n <= 32 taps, n above; >= 8)
+  int agc_rows;             // floats per chain for the AGC delay line + magnitude history
+  int use_eq;               // some chain runs the CMA equaliser
+};
+static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
+{
+  SdbInspDyn d = { 8, 8, 0 };
+  for (int k = 0; k < n; ++k) {
+    const SdbChainCfg &c = cfgs[k];
+    if (c.have_mf) {
+      const int need = c.mf_n <= 32 ? 8 + 2 * c.mf_n : c.mf_n;
+      if (need <= 136 && need > d.mf_slots) d.mf_slots = need;          // longer filters stay in the global pool
+    }
+    if (c.have_agc) {
+      const int need = (int) (2 * c.dl_size + c.mh_size);
+      if (need <= 160 && need > d.agc_rows) d.agc_rows = need;
+    }
+    if (c.eq_type == 1) d.use_eq = 1;
+  }
+  return d;
+}
+
 // host-callable launchers ----------------------------------------------------------------------
 struct SdbLaunchCtx {
   cudaStream_t stream;
@@ -185,7 +209,7 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
                                     const float *taps_pool, const SdbChannelDev *chans_dev,
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
                                     float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap,
-                                    int fresh);
+                                    int fresh, const SdbInspDyn &dyn);
 cudaError_t sdb_launch_spectsrc(const SdbLaunchCtx &c, const SdbSpectCfg *cfg_dev, const SdbChannelDev *chans_dev,
                                 int n_channels, int n_streams, int max_ns, const float2 *chan_in,
                                 size_t chan_stream_stride, uint32_t n_hops, float *spect, size_t spect_stream_stride,
