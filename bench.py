@@ -87,7 +87,31 @@ class Clocks:
         self.index, self.rows, self.stop = index, [], False
         self.t = threading.Thread(target=self.run, daemon=True)
 
+    def run_nvml(self):
+        """In-process NVML polling (~every 5 ms): a 40 ms timed region still gets several samples."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self.stop:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            row = [str(sm), str(mx), "", "", "", ""]
+            for bit, col in bits:
+                row[col] = "Active" if r & bit else "Not Active"
+            self.rows.append(row)
+            time.sleep(0.005)
+
     def run(self):
+        try:
+            self.run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop:
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
