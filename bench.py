@@ -124,6 +124,9 @@ class Clocks:
 
     def __enter__(self):
         self.t.start()
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < 3.0:      # NVML / nvidia-smi start-up stays outside the timed region
+            time.sleep(0.002)
         return self
 
     def __exit__(self, *a):
