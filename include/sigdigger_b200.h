@@ -248,6 +248,33 @@ int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batc
 int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
 
 /* ------------------------------------------------------------------------------------------------
+ * Capture files: the file source of Default/SourceConfig/FileSourcePage.cpp:68-140
+ * (SUSCAN_SOURCE_FORMAT_{AUTO, RAW_*, WAV, SIGMF} + metadata guessed from the file name; SigDigger's own
+ * recordings are "sigdigger_%Y%m%d_%H%M%SZ_<rate>_<freq>_float32_iq.raw", Default/Source/SourceWidget.cpp:1092-1100).
+ * The file is mapped read-only; samples stay in their native format and are converted inside the first load of the
+ * transforms (sdb_engine_params.input_format / sdb_source_config.input_format).  Host-only: works without a GPU.
+ * ---------------------------------------------------------------------------------------------- */
+enum { SDB_CONTAINER_AUTO = -1, SDB_CONTAINER_RAW = 0, SDB_CONTAINER_WAV = 1, SDB_CONTAINER_SIGMF = 2 };
+#define SDB_CAPTURE_GUESS_START_TIME 1u   /* SUSCAN_SOURCE_CONFIG_GUESS_START_TIME */
+#define SDB_CAPTURE_GUESS_SAMP_RATE  2u   /* ..._GUESS_SAMP_RATE */
+#define SDB_CAPTURE_GUESS_FREQ       4u   /* ..._GUESS_FREQ */
+#define SDB_CAPTURE_GUESS_FORMAT     8u
+typedef struct {
+  int32_t  container, sample_format;      /* SDB_CONTAINER_*, SDB_FORMAT_* */
+  double   samp_rate, frequency;          /* 0 when the container does not say */
+  uint64_t data_offset, n_samples;        /* byte offset of the first IQ pair, number of IQ pairs */
+  uint32_t guessed;                       /* SDB_CAPTURE_GUESS_* bits filled from the file name (raw files) */
+  int64_t  start_time;                    /* UTC seconds */
+} sdb_capture_info;
+typedef struct sdb_capture sdb_capture_t;
+/* container = SDB_CONTAINER_AUTO picks by extension (.wav, .sigmf-meta / .sigmf-data, anything else raw);
+ * sample_format < 0 = from the container or the file name (raw default: float32) */
+sdb_capture_t *sdb_capture_open(const char *path, int32_t container, int32_t sample_format, sdb_capture_info *info);
+const void    *sdb_capture_data(const sdb_capture_t *c);
+void           sdb_capture_close(sdb_capture_t *c);
+const char    *sdb_capture_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
  * suscan-style asynchronous analyzer: a worker thread reads the source, runs the
  * engine block by block and posts messages; requests are answered in order with messages carrying req_id.
  * Field names follow the structs the reference dereferences (Suscan/Messages/PSDMessage.cpp:30-112,
@@ -292,6 +319,7 @@ typedef struct {
   sdb_source_read_fn read; void *priv;
   const sdb_complex *data; size_t length; int32_t loop;
   int32_t device;
+  int32_t input_format;           /* SDB_FORMAT_* of `data` (length counts IQ pairs); callback sources deliver float32 */
 } sdb_source_config;
 
 typedef struct {                  /* suscan_analyzer_psd_msg */

@@ -38,6 +38,41 @@ class DetectedChannel(C.Structure):
                 ("bin_hi", C.c_uint32)]
 
 
+class CaptureInfo(C.Structure):
+    """sdb_capture_info"""
+    _fields_ = [("container", C.c_int32), ("sample_format", C.c_int32), ("samp_rate", C.c_double),
+                ("frequency", C.c_double), ("data_offset", C.c_uint64), ("n_samples", C.c_uint64),
+                ("guessed", C.c_uint32), ("start_time", C.c_int64)]
+
+
+CONTAINER = {"auto": -1, "raw": 0, "wav": 1, "sigmf": 2}
+
+
+class Capture:
+    """Capture file (raw / WAV / SigMF) mapped read-only; `.samples` is a numpy view in the native sample format
+    (complex64, or interleaved I,Q of uint8 / int8 / int16).  Host-only: needs no GPU."""
+
+    def __init__(self, path, container="auto", sample_format=None):
+        self._L = load_library()
+        self.info = CaptureInfo()
+        fmt = -1 if sample_format is None else (FORMAT[sample_format] if isinstance(sample_format, str) else sample_format)
+        self._h = self._L.sdb_capture_open(os.fsencode(path), CONTAINER[container], fmt, C.byref(self.info))
+        if not self._h:
+            raise SdbError((self._L.sdb_capture_last_error() or b"sdb_capture_open failed").decode())
+        dt = FORMAT_DTYPE[self.info.sample_format]
+        n = self.info.n_samples * (1 if dt is np.complex64 else 2)
+        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(self._L.sdb_capture_data(self._h))
+        self.samples = np.frombuffer(buf, dtype=dt, count=n)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.samples = None
+            self._L.sdb_capture_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 class ChannelDetector:
     """Stand-alone SPEC K detector on device-resident linear PSDs (e.g. a stitched SpectrumView)."""
 
@@ -127,6 +162,10 @@ _PROTOS = {
     "sdb_chdet_destroy": (None, [C.c_void_p]),
     "sdb_chdet_feed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
     "sdb_chdet_read": (C.c_long, [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sdb_capture_open": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "sdb_capture_data": (C.c_void_p, [C.c_void_p]),
+    "sdb_capture_close": (None, [C.c_void_p]),
+    "sdb_capture_last_error": (C.c_char_p, []),
     "sdb_engine_stream": (C.c_void_p, [C.c_void_p]),
     "sdb_engine_launch_count": (C.c_uint64, [C.c_void_p]),
     "sdb_engine_kernel_time": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

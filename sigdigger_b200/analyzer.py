@@ -39,7 +39,7 @@ READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.c_void_p, C.c_size_t)
 class SourceConfig(C.Structure):
     _fields_ = [("samp_rate", C.c_double), ("freq", C.c_double), ("read_size", C.c_size_t), ("read", READ_FN),
                 ("priv", C.c_void_p), ("data", C.c_void_p), ("length", C.c_size_t), ("loop", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("input_format", C.c_int32)]
 
 
 class PsdMsg(C.Structure):
@@ -87,8 +87,16 @@ class Analyzer:
         s = SourceConfig()
         s.samp_rate, s.freq, s.read_size, s.loop, s.device = samp_rate, freq, read_size, int(loop), device
         if data is not None:
-            self._data = np.ascontiguousarray(data, dtype=np.complex64)
-            s.data, s.length = self._data.ctypes.data, len(self._data)
+            data = np.asarray(data)
+            if data.dtype in (np.uint8, np.int8, np.int16):       # native capture formats: interleaved I,Q
+                from . import FORMAT
+                self._data = np.ascontiguousarray(data).reshape(-1)
+                s.input_format = {np.dtype(np.uint8): FORMAT["u8"], np.dtype(np.int8): FORMAT["s8"],
+                                  np.dtype(np.int16): FORMAT["s16"]}[self._data.dtype]
+                s.data, s.length = self._data.ctypes.data, len(self._data) // 2
+            else:
+                self._data = np.ascontiguousarray(data, dtype=np.complex64)
+                s.data, s.length = self._data.ctypes.data, len(self._data)
             s.read = READ_FN(0)
         else:
             self._cb = READ_FN(read)

@@ -143,6 +143,7 @@ struct sdb_analyzer {
     ep.max_feed = (uint32_t) block;
     ep.device = src.device;
     ep.flags = 0;
+    ep.input_format = src.read ? SDB_FORMAT_FLOAT32 : src.input_format;
     eng = sdb_engine_new(&ep, src.samp_rate);
     if (!eng) { post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error()); return false; }
     for (auto &i : insps) {
@@ -274,11 +275,15 @@ struct sdb_analyzer {
   {
     if (src.read) return src.read(src.priv, dst, n);
     if (!src.data) return -1;
+    // in-memory capture in its native sample format (bps bytes per IQ pair); dst is a byte buffer of n * 8
+    const size_t bps = src.input_format == SDB_FORMAT_FLOAT32 ? 8 : src.input_format == SDB_FORMAT_SIGNED16 ? 4 : 2;
+    const unsigned char *base = reinterpret_cast<const unsigned char *>(src.data);
+    unsigned char *out = reinterpret_cast<unsigned char *>(dst);
     size_t got = 0;
     while (got < n) {
       if (src_pos >= src.length) { if (!src.loop) break; src_pos = 0; }
       size_t take = std::min(n - got, src.length - src_pos);
-      memcpy(dst + got, src.data + src_pos, take * sizeof(sdb_complex));
+      memcpy(out + got * bps, base + src_pos * bps, take * bps);
       got += take; src_pos += take;
     }
     return (long) got;
@@ -408,6 +413,7 @@ extern "C" sdb_analyzer_t *sdb_analyzer_new(const sdb_analyzer_params *params, c
   if (sdb_device_count() <= 0) return nullptr;   // sdb_last_error() is set by the engine on first use; no CPU fallback
   const uint64_t N = params->detector_params.window_size;
   if (N < 16 || (N & (N - 1)) || !(src->samp_rate > 0) || (!src->read && !src->data)) return nullptr;
+  if (src->input_format < SDB_FORMAT_FLOAT32 || src->input_format > SDB_FORMAT_SIGNED16) return nullptr;
   sdb_analyzer *a = new sdb_analyzer();
   a->params = *params;
   a->src = *src;
