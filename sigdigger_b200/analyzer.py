@@ -115,10 +115,11 @@ class Analyzer:
     def halt(self):
         self._L.sdb_analyzer_req_halt(self._h)
 
-    def open(self, cls, fc, bw, precise=False, req_id=0):
+    def open(self, cls, fc, bw, precise=False, req_id=0, parent=-1):
+        """parent >= 0: sub-carrier inspector on that inspector's channel (fc relative to its centre)."""
         ch = SigutilsChannel(fc, 0.0, fc - bw / 2 - fc, fc + bw / 2 - fc, bw)
         ch.f_lo, ch.f_hi = -bw / 2, bw / 2          # as InspToolWidget.cpp:688-693 fills it
-        if self._L.sdb_analyzer_open_ex_async(self._h, cls.encode(), C.byref(ch), int(precise), -1, req_id):
+        if self._L.sdb_analyzer_open_ex_async(self._h, cls.encode(), C.byref(ch), int(precise), parent, req_id):
             raise SdbError("open_ex_async rejected")
 
     def set_inspector_id(self, handle, inspector_id, req_id=0):

@@ -37,6 +37,7 @@ struct Cmd {
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
   int32_t handle = -1;
+  int32_t parent = -1;                        // open_ex: handle of the inspector whose channel is the input
   uint32_t inspector_id = 0;
   std::string cls;
   sdb_sigutils_channel channel{};
@@ -56,6 +57,8 @@ struct Insp {
   sdb_inspector_config cfg;
   int engine_handle;      // handle inside the current engine, -1 if not mapped
   float fs, bandwidth, lo;
+  int32_t parent;         // -1 = fed by the baseband; else sub-carrier inspector on that inspector's channel
+  uint32_t size;          // channel IFFT size (samples per two hops) in the engine that feeds it
   uint32_t spectsrc_id;   // 0 = none (index 0 of the GUI's combo)
   uint32_t est_mask;
   uint32_t spect_size;    // frame size chosen at rebuild time (0 = too few channel samples per block)
@@ -96,6 +99,12 @@ struct sdb_analyzer {
   std::thread worker;
   std::vector<Insp> insps;
   sdb_engine_t *eng = nullptr;
+  // Sub-carrier inspection (GenericInspector.cpp:502-525: openInspectorTab(..., parent = this handle)): every
+  // parent with open children gets a second engine whose input is the parent's channel stream and whose
+  // channeliser window equals the parent's channel size, so that one parent hop is exactly one child hop.
+  struct Sub { int32_t parent; sdb_engine_t *eng; };
+  std::vector<Sub> subs;
+  void drop_subs() { for (auto &s : subs) if (s.eng) sdb_engine_destroy(s.eng); subs.clear(); }
   bool plan_dirty = true;
   size_t block = 0;
   double measured_rate = 0;
@@ -146,9 +155,10 @@ struct sdb_analyzer {
     ep.input_format = src.read ? SDB_FORMAT_FLOAT32 : src.input_format;
     eng = sdb_engine_new(&ep, src.samp_rate);
     if (!eng) { post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error()); return false; }
+    drop_subs();
     for (auto &i : insps) {
       i.engine_handle = -1;
-      if (!i.open) continue;
+      if (!i.open || i.parent >= 0) continue;
       sdb_channel_params cp;
       double f = fmod(i.channel.fc / src.samp_rate + 1.0, 1.0);
       cp.f0 = (float) (2.0 * 3.14159265358979323846 * f);
@@ -158,6 +168,7 @@ struct sdb_analyzer {
       int h = sdb_engine_open_channel(eng, &cp, &info);
       if (h < 0) continue;
       i.engine_handle = h;
+      i.size = info.size;
       i.fs = (float) (src.samp_rate / info.decimation);
       i.bandwidth = (float) (i.channel.f_hi - i.channel.f_lo);
       i.lo = (float) i.channel.fc;
@@ -185,6 +196,37 @@ struct sdb_analyzer {
       post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error());
       return false;
     }
+    // sub-carrier engines: one per parent that has open children
+    for (auto &p : insps) {
+      if (!p.open || p.parent >= 0 || p.engine_handle < 0) continue;
+      bool any = false;
+      for (auto &c : insps) any = any || (c.open && c.parent == p.handle);
+      if (!any || p.size < 16) continue;
+      sdb_engine_params sp;
+      memset(&sp, 0, sizeof(sp));
+      sp.n_streams = 1; sp.psd_size = 0; sp.st_window_size = p.size;
+      sp.max_feed = (uint32_t) (block / (ep.psd_size / 2) * (p.size / 2));
+      sp.device = src.device; sp.input_format = SDB_FORMAT_FLOAT32;
+      sdb_engine_t *se = sdb_engine_new(&sp, (double) p.fs);
+      if (!se) continue;
+      for (auto &c : insps) {
+        if (!c.open || c.parent != p.handle) continue;
+        sdb_channel_params cp;
+        cp.f0 = (float) (2.0 * 3.14159265358979323846 * fmod(c.channel.fc / (double) p.fs + 1.0, 1.0));
+        cp.bw = (float) (2.0 * 3.14159265358979323846 * (c.channel.f_hi - c.channel.f_lo) / (double) p.fs);
+        cp.guard = 1.0f; cp.precise = c.precise;
+        sdb_channel_info info;
+        int h = sdb_engine_open_channel(se, &cp, &info);
+        if (h < 0) continue;
+        c.engine_handle = h; c.size = info.size;
+        c.fs = (float) ((double) p.fs / info.decimation);
+        c.bandwidth = (float) (c.channel.f_hi - c.channel.f_lo); c.lo = (float) c.channel.fc;
+        c.cfg.insp_class = c.cls;
+        sdb_engine_set_inspector(se, h, &c.cfg);
+      }
+      if (sdb_engine_commit(se)) { sdb_engine_destroy(se); continue; }
+      subs.push_back(Sub{ p.handle, se });
+    }
     plan_dirty = false;
     return true;
   }
@@ -199,27 +241,40 @@ struct sdb_analyzer {
           int cls = class_id(c.cls);
           double bw = c.channel.f_hi - c.channel.f_lo;
           if (cls < 0) { post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_KIND, c, nullptr); break; }
-          if (!(bw > 0) || bw > src.samp_rate || fabs(c.channel.fc) > src.samp_rate / 2) {
+          // the input of the new inspector: the baseband, or (sub-carrier inspection) the channel of `parent`
+          double in_rate = src.samp_rate;
+          uint32_t in_window = (uint32_t) params.detector_params.window_size;
+          if (c.parent >= 0) {
+            if (c.parent >= (int32_t) insps.size() || !insps[c.parent].open || insps[c.parent].parent >= 0 ||
+                insps[c.parent].size < 16) {
+              Cmd w = c; w.handle = c.parent;
+              post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_HANDLE, w, nullptr); break;
+            }
+            in_rate = (double) insps[c.parent].fs; in_window = insps[c.parent].size;
+          }
+          if (!(bw > 0) || bw > in_rate || fabs(c.channel.fc) > in_rate / 2) {
             post_inspector(SDB_INSPECTOR_MSGKIND_INVALID_CHANNEL, c, nullptr); break;
           }
           Insp i;
           memset(&i, 0, sizeof(i));
           i.handle = (int32_t) insps.size(); i.open = true; i.has_id = false; i.cls = cls; i.channel = c.channel;
-          i.precise = c.precise; i.engine_handle = -1;
+          i.precise = c.precise; i.engine_handle = -1; i.parent = c.parent;
           // geometry -> equivalent rate, needed for the default config the OPEN reply carries
           {
             sdb_engine_params ep; memset(&ep, 0, sizeof(ep));
-            ep.n_streams = 1; ep.psd_size = (uint32_t) params.detector_params.window_size; ep.max_feed = (uint32_t) block;
+            ep.n_streams = 1; ep.psd_size = c.parent >= 0 ? 0 : in_window; ep.st_window_size = in_window;
+            ep.max_feed = c.parent >= 0 ? in_window : (uint32_t) block;
             ep.device = src.device;
-            sdb_engine_t *probe = sdb_engine_new(&ep, src.samp_rate);
+            sdb_engine_t *probe = sdb_engine_new(&ep, in_rate);
             sdb_channel_params cp;
-            cp.f0 = (float) (2.0 * 3.14159265358979323846 * fmod(c.channel.fc / src.samp_rate + 1.0, 1.0));
-            cp.bw = (float) (2.0 * 3.14159265358979323846 * bw / src.samp_rate); cp.guard = 1.0f; cp.precise = c.precise;
+            cp.f0 = (float) (2.0 * 3.14159265358979323846 * fmod(c.channel.fc / in_rate + 1.0, 1.0));
+            cp.bw = (float) (2.0 * 3.14159265358979323846 * bw / in_rate); cp.guard = 1.0f; cp.precise = c.precise;
             sdb_channel_info info; memset(&info, 0, sizeof(info));
             int h = probe ? sdb_engine_open_channel(probe, &cp, &info) : -1;
             if (probe) sdb_engine_destroy(probe);
             if (h < 0) { post_inspector(SDB_INSPECTOR_MSGKIND_INVALID_CHANNEL, c, nullptr); break; }
-            i.fs = (float) (src.samp_rate / info.decimation);
+            i.fs = (float) (in_rate / info.decimation);
+            i.size = info.size;
           }
           i.bandwidth = (float) bw; i.lo = (float) c.channel.fc;
           sdb_inspector_config_default(&i.cfg, cls, i.fs);
@@ -256,6 +311,7 @@ struct sdb_analyzer {
             post_inspector(SDB_INSPECTOR_MSGKIND_SET_CONFIG, c, &i);
           } else {
             i.open = false; plan_dirty = true;
+            for (auto &ch : insps) if (ch.parent == i.handle) ch.open = false;     // sub-carrier inspectors go with it
             post_inspector(SDB_INSPECTOR_MSGKIND_CLOSE, c, &i);
           }
           break;
@@ -341,8 +397,30 @@ struct sdb_analyzer {
         }
       }
       // sample batches, keyed by the caller-chosen inspector_id
+      // sub-carrier inspectors: the parent's channel samples of this block through the child engine
+      for (auto &sb : subs) {
+        const Insp &p = insps[sb.parent];
+        if (!p.open || p.engine_handle < 0) continue;
+        std::vector<sdb_complex> ch(block);
+        long nch = sdb_engine_read_channel(eng, 0, p.engine_handle, ch.data(), ch.size());
+        if (nch <= 0) continue;
+        if (sdb_engine_feed_host(sb.eng, ch.data(), (size_t) nch, (size_t) nch) || sdb_engine_sync(sb.eng)) continue;
+        for (auto &i : insps) {
+          if (!i.open || i.parent != p.handle || !i.has_id || i.engine_handle < 0) continue;
+          soft.resize((size_t) nch); hard.resize((size_t) nch);
+          long n = sdb_engine_read_symbols(sb.eng, 0, i.engine_handle, soft.data(), hard.data(), (size_t) nch);
+          if (n <= 0) continue;
+          sdb_analyzer_sample_batch_msg *m = (sdb_analyzer_sample_batch_msg *) calloc(1, sizeof(*m));
+          m->inspector_id = i.inspector_id; m->sample_count = (uint64_t) n;
+          m->samples = (sdb_complex *) malloc((size_t) n * sizeof(sdb_complex));
+          m->symbols = (uint8_t *) malloc((size_t) n);
+          memcpy(m->samples, soft.data(), (size_t) n * sizeof(sdb_complex));
+          memcpy(m->symbols, hard.data(), (size_t) n);
+          post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
+        }
+      }
       for (auto &i : insps) {
-        if (!i.open || !i.has_id || i.engine_handle < 0) continue;
+        if (!i.open || !i.has_id || i.engine_handle < 0 || i.parent >= 0) continue;
         size_t cap = block;
         soft.resize(cap); hard.resize(cap);
         long n = sdb_engine_read_symbols(eng, 0, i.engine_handle, soft.data(), hard.data(), cap);
@@ -357,7 +435,7 @@ struct sdb_analyzer {
       }
       // kind=SPECTRUM / kind=ESTIMATOR inspector messages (one per block that filled a frame)
       for (auto &i : insps) {
-        if (!i.open || i.engine_handle < 0 || !i.spect_size) continue;
+        if (!i.open || i.engine_handle < 0 || !i.spect_size || i.parent >= 0) continue;
         if (i.spectsrc_id) {
           std::vector<float> sp(i.spect_size);
           uint32_t emitted = 0;
@@ -402,6 +480,7 @@ struct sdb_analyzer {
         }
       }
     }
+    drop_subs();
     if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
     post_status(exit_type, 0, exit_type == SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR ? sdb_last_error() : nullptr);
   }
@@ -501,8 +580,11 @@ extern "C" int sdb_analyzer_open_ex_async(sdb_analyzer_t *a, const char *class_n
                                           int precise, int32_t parent, uint32_t req_id)
 {
   if (!class_name || !ch) return -1;
-  if (parent != -1) return -1;        // sub-carrier inspection (parent handles) is section 8(f), not built
+  if (parent < -1) return -1;
+  // parent >= 0: sub-carrier inspection (Default/GenericInspector/GenericInspector.cpp:502-525); the channel is
+  // given relative to the parent's channel centre, at the parent's equivalent sample rate
   Cmd c; c.kind = Cmd::OPEN; c.req_id = req_id; c.cls = class_name; c.channel = *ch; c.precise = precise;
+  c.parent = parent;
   return push_cmd(a, std::move(c));
 }
 extern "C" int sdb_analyzer_set_inspector_id_async(sdb_analyzer_t *a, int32_t handle, uint32_t inspector_id, uint32_t req_id)

@@ -563,7 +563,7 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       // against 116 MB algorithmic, profiles/r01_l2.md).  Accesses of the transform streams inside the window
       // are "persisting" (a set-aside part of L2 that normal traffic cannot evict); the kernels additionally
       // mark their one-shot outputs as streaming (st.global.cs).
-      if (!getenv("SDB_NO_L2_PIN")) {
+      if (big == 65536 && !getenv("SDB_NO_L2_PIN")) {   // the set-aside is device-wide: only the big plans claim it
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->prm.device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->prm.device);

@@ -105,6 +105,70 @@ def test_analyzer_memory_source_halt(sdb):
     a.close()
 
 
+def test_analyzer_subcarrier_inspector(sdb, oracle):
+    """open_ex with a parent handle (Default/GenericInspector/GenericInspector.cpp:502-525): a PSK inspector on a
+    sub-carrier of a raw inspector's channel = two channelisers in series; symbols bit-identical to the oracle."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 8192, 1.0e6
+    baud = fs / 512.0
+    blocks, per_block = 6, N * 8
+    n = blocks * per_block
+    x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs + fs / 64.0, baud, -10.0, {})], noise_db=-55.0, seed=17)
+    go = threading.Event()
+    pos = [0]
+
+    def read(priv, dst, maxn):
+        go.wait(30)
+        take = min(maxn, n - pos[0])
+        if take > 0:
+            C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+            pos[0] += take
+        return take
+
+    a = Analyzer(fs, window_size=N, window="hann", psd_update_int=1.0, read=read, read_size=per_block)
+    assert a.read(5000)[0] == "SOURCE_INFO"
+    a.open("raw", 0.125 * fs, fs / 8.0, req_id=1)                       # parent: 1024-point channel, fs / 8
+    a.open("psk", fs / 64.0, 3 * baud, req_id=2, parent=0)             # child, relative to the parent's centre
+    a.open("psk", 0.0, 1000.0, req_id=3, parent=1)                     # no grandchildren -> WRONG_HANDLE
+    a.open("psk", 0.0, 1000.0, req_id=4, parent=9)                     # unknown parent   -> WRONG_HANDLE
+    a.set_inspector_id(1, 0x51, req_id=5)
+    cfg = sdb.InspectorConfig()
+    fs_par = fs / 8.0
+    fs_ch = fs_par * 64 / 1024
+    sdb._check(sdb.load_library().sdb_inspector_config_default(C.byref(cfg), sdb.INSP["psk"], fs_ch))
+    kw = dict(baud=baud, costas_order=2, bits_per_symbol=2, loop_bw=fs_ch * 2e-3, mf_type=1, mf_rolloff=0.35,
+              clock_type=1, clock_gain=0.1, clock_running=1)
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    a.set_inspector_config(1, cfg, req_id=6)
+    go.set()
+    soft, hard, replies = [], [], []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "SAMPLES":
+            assert m["inspector_id"] == 0x51
+            soft.append(m["samples"]); hard.append(m["symbols"])
+        elif name == "INSPECTOR":
+            replies.append((m["kind"], m["req_id"], m["handle"]))
+            if m["req_id"] == 2:
+                assert abs(m["equiv_fs"] - fs_ch) < 1e-3
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    a.close()
+    assert name == "EOS"
+    assert replies == [("OPEN", 1, 0), ("OPEN", 2, 1), ("WRONG_HANDLE", 3, 1), ("WRONG_HANDLE", 4, 9), ("SET_ID", 5, 1),
+                       ("SET_CONFIG", 6, 1)]
+    # oracle: baseband -> parent channel (window N) -> child channel (window 1024) -> psk chain
+    f0p, bwp = float(np.float32(2.0 * np.pi * 0.125)), float(np.float32(2.0 * np.pi / 8.0))
+    par = oracle.specttuner_run(x[per_block:], N, [dict(f0=f0p, bw=bwp, guard=1.0)])[0]
+    f0c, bwc = float(np.float32(2.0 * np.pi * 0.125)), float(np.float32(2.0 * np.pi * (3 * baud) / fs_par))
+    chi = oracle.specttuner_run(par, 1024, [dict(f0=f0c, bw=bwc, guard=1.0)])[0]
+    rs, rh = oracle.inspector_run(oracle.insp_config("psk", fs_ch, **kw), chi)
+    assert len(rs) > 300
+    parity.assert_symbols_match(np.concatenate(soft), np.concatenate(hard), rs, rh, exact_soft=True)
+
+
 def test_analyzer_spectrum_estimator_and_channel_messages(sdb, oracle):
     """kind=SPECTRUM / kind=ESTIMATOR inspector messages and MESSAGE_TYPE_CHANNEL lists
     (Suscan/Analyzer.cpp:539-565, GenericInspector.cpp:232-264, ChannelMessage.cpp:25-70)."""
