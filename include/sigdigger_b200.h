@@ -36,6 +36,8 @@ enum { SDB_AUDIO_DISABLED = 0, SDB_AUDIO_AM, SDB_AUDIO_FM, SDB_AUDIO_USB, SDB_AU
 
 #define SDB_FLAG_PSD_SHIFT_DB 1u  /* fold the GUI's fft-shift + SU_POWER_DB pass
                                      (Suscan/Messages/PSDMessage.cpp:32-38) into the PSD kernel */
+#define SDB_FLAG_IQ_REVERSE   2u  /* suscan_analyzer_set_iq_reverse (Suscan/Analyzer.cpp:238-244): the source delivers
+                                     (Q, I); swapped inside the first load of the path, any sample format */
 
 /* Replaces struct suscan_analyzer_params.detector_params.{window_size, window}
  * (Suscan/AnalyzerParams.cpp:56-66) + the specttuner's sigutils_specttuner_params.window_size
@@ -362,11 +364,25 @@ int    sdb_analyzer_set_inspector_id_async(sdb_analyzer_t *a, int32_t handle, ui
 int    sdb_analyzer_set_inspector_config_async(sdb_analyzer_t *a, int32_t handle, const sdb_inspector_config *cfg,
                                                uint32_t req_id);
 int    sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint32_t req_id);
+/* suscan_analyzer_set_inspector_watermark_async (Suscan/Analyzer.cpp:527-537; Default/Audio/AudioProcessor.cpp:745-747):
+ * SAMPLES batches of this inspector are held back until they contain `watermark` samples (0 = one batch per block) */
+int    sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int32_t handle, uint64_t watermark, uint32_t req_id);
 /* suscan_analyzer_inspector_set_spectrum_async / _estimator_cmd_async (Suscan/Analyzer.cpp:539-565) */
 int    sdb_analyzer_inspector_set_spectrum_async(sdb_analyzer_t *a, int32_t handle, uint32_t spectsrc_id, uint32_t req_id);
 int    sdb_analyzer_inspector_estimator_cmd_async(sdb_analyzer_t *a, int32_t handle, uint32_t estimator_id,
                                                   int enabled, uint32_t req_id);
 int    sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyzer_params *p, uint32_t req_id);
+/* source-side options of the worker loop: suscan_analyzer_set_iq_reverse (Suscan/Analyzer.cpp:238-244; applied at
+ * the next block boundary, swap done inside the first load on the GPU), suscan_analyzer_set_throttle_async
+ * (Suscan/Analyzer.cpp:117-123; 0 = unthrottled) and suscan_analyzer_register_baseband_filter
+ * (Suscan/Analyzer.cpp:126-130; SUBOOL f(privdata, analyzer, samples, length, offset) as used by the GUI's baseband
+ * recorder, Default/Source/SourceWidget.cpp:1156-1184): called on the worker thread with every float32 block before
+ * it is analysed; it may rewrite the samples. */
+typedef int (*sdb_baseband_filter_fn)(void *privdata, sdb_analyzer_t *a, sdb_complex *samples, uint64_t length,
+                                      uint64_t offset);
+int    sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled);
+int    sdb_analyzer_set_throttle_async(sdb_analyzer_t *a, uint64_t samp_rate, uint32_t req_id);
+int    sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *privdata);
 uint64_t sdb_analyzer_get_samp_rate(const sdb_analyzer_t *a);
 float    sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a);
 

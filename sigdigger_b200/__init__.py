@@ -16,6 +16,7 @@ WINDOW = {"none": 0, "hamming": 1, "hann": 2, "flat_top": 3, "blackmann_harris":
 INSP = {"psk": 0, "fsk": 1, "ask": 2, "audio": 3, "raw": 4}
 AUDIO = {"disabled": 0, "am": 1, "fm": 2, "usb": 3, "lsb": 4}
 FLAG_PSD_SHIFT_DB = 1
+FLAG_IQ_REVERSE = 2
 SPECTSRC = {"none": 0, "psd": 1, "cyclo": 2, "fmspect": 3, "timediff": 4, "abstimediff": 5, "exp_2": 6,
             "exp_4": 7, "exp_8": 8, "fac": 9}
 ESTIMATOR = {"baud-fac": 0, "baud-nonlinear": 1}
@@ -188,6 +189,10 @@ _PROTOS = {
     "sdb_analyzer_set_inspector_config_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32]),
     "sdb_analyzer_close_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
     "sdb_analyzer_set_params_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sdb_analyzer_set_inspector_watermark_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32]),
+    "sdb_analyzer_set_iq_reverse": (C.c_int, [C.c_void_p, C.c_int]),
+    "sdb_analyzer_set_throttle_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
+    "sdb_analyzer_register_baseband_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdb_analyzer_inspector_set_spectrum_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32]),
     "sdb_analyzer_inspector_estimator_cmd_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int, C.c_uint32]),
     "sdb_analyzer_get_samp_rate": (C.c_uint64, [C.c_void_p]),

@@ -34,6 +34,7 @@ class AnalyzerParams(C.Structure):
 
 
 READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.c_void_p, C.c_size_t)
+BB_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64)
 
 
 class SourceConfig(C.Structure):
@@ -127,6 +128,24 @@ class Analyzer:
 
     def set_inspector_config(self, handle, cfg, req_id=0):
         self._L.sdb_analyzer_set_inspector_config_async(self._h, handle, C.byref(cfg), req_id)
+
+    def set_inspector_watermark(self, handle, watermark, req_id=0):
+        self._L.sdb_analyzer_set_inspector_watermark_async(self._h, handle, int(watermark), req_id)
+
+    def set_iq_reverse(self, enabled=True):
+        self._L.sdb_analyzer_set_iq_reverse(self._h, int(enabled))
+
+    def set_throttle(self, samp_rate, req_id=0):
+        self._L.sdb_analyzer_set_throttle_async(self._h, int(samp_rate), req_id)
+
+    def register_baseband_filter(self, fn):
+        """fn(samples: complex64 ndarray view (writable), offset) -> truthy; runs on the worker thread."""
+        def tramp(priv, a, ptr, length, offset):
+            buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(2 * length,)).view(np.complex64)
+            return 1 if fn(buf, offset) else 0
+        cb = BB_FN(tramp)
+        self._bb = getattr(self, "_bb", []) + [cb]          # keep the trampolines alive
+        self._L.sdb_analyzer_register_baseband_filter(self._h, C.cast(cb, C.c_void_p), None)
 
     def set_spectrum_source(self, handle, spectsrc_id, req_id=0):
         self._L.sdb_analyzer_inspector_set_spectrum_async(self._h, handle, spectsrc_id, req_id)

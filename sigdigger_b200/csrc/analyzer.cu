@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -33,9 +34,10 @@
 namespace {
 
 struct Cmd {
-  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD } kind;
+  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK } kind;
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
+  double value = 0;                           // throttle rate
   int32_t handle = -1;
   int32_t parent = -1;                        // open_ex: handle of the inspector whose channel is the input
   uint32_t inspector_id = 0;
@@ -110,6 +112,12 @@ struct sdb_analyzer {
   double measured_rate = 0;
   uint64_t total_samples = 0;
   double psd_credit = 0;
+  // source-side options of the worker loop (Suscan/Analyzer.cpp:117-135, 229-244; SourceWidget.cpp:1156-1184)
+  bool iq_reverse = false;
+  double throttle = 0;                                  // samples / s, 0 = as fast as the source delivers
+  std::chrono::steady_clock::time_point throttle_t0; uint64_t throttle_s0 = 0;
+  struct BbFilter { sdb_baseband_filter_fn fn; void *priv; };
+  std::vector<BbFilter> bb_filters;
 
   void post(uint32_t type, void *payload)
   {
@@ -139,6 +147,27 @@ struct sdb_analyzer {
   }
   double chan_credit = 0;
 
+  // SAMPLES batches: suscan flushes an inspector's sample buffer once it holds `watermark` samples
+  // (suscan_analyzer_set_inspector_watermark_async, Suscan/Analyzer.cpp:527-537; the audio path asks for half a
+  // playback buffer, Default/Audio/AudioProcessor.cpp:745-747).  watermark 0 = one batch per block.
+  struct Pending { std::vector<sdb_complex> soft; std::vector<uint8_t> hard; uint64_t watermark = 0; };
+  std::map<int32_t, Pending> pending;
+  void deliver(const Insp &i, const sdb_complex *s, const uint8_t *h, size_t n, bool flush)
+  {
+    Pending &p = pending[i.handle];
+    p.soft.insert(p.soft.end(), s, s + n);
+    p.hard.insert(p.hard.end(), h, h + n);
+    if (p.soft.empty() || (!flush && p.soft.size() < p.watermark)) return;
+    sdb_analyzer_sample_batch_msg *m = (sdb_analyzer_sample_batch_msg *) calloc(1, sizeof(*m));
+    m->inspector_id = i.inspector_id; m->sample_count = (uint64_t) p.soft.size();
+    m->samples = (sdb_complex *) malloc(p.soft.size() * sizeof(sdb_complex));
+    m->symbols = (uint8_t *) malloc(p.hard.size());
+    memcpy(m->samples, p.soft.data(), p.soft.size() * sizeof(sdb_complex));
+    memcpy(m->symbols, p.hard.data(), p.hard.size());
+    p.soft.clear(); p.hard.clear();
+    post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
+  }
+
   // (re)build the engine from the open inspectors; returns false on failure (status message posted)
   bool rebuild()
   {
@@ -151,7 +180,7 @@ struct sdb_analyzer {
     ep.st_window_size = 0;
     ep.max_feed = (uint32_t) block;
     ep.device = src.device;
-    ep.flags = 0;
+    ep.flags = iq_reverse ? SDB_FLAG_IQ_REVERSE : 0;
     ep.input_format = src.read ? SDB_FORMAT_FLOAT32 : src.input_format;
     eng = sdb_engine_new(&ep, src.samp_rate);
     if (!eng) { post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error()); return false; }
@@ -316,6 +345,19 @@ struct sdb_analyzer {
           }
           break;
         }
+        case Cmd::SET_WATERMARK:
+          if (c.handle < 0 || c.handle >= (int32_t) insps.size() || !insps[c.handle].open) {
+            post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_HANDLE, c, nullptr); break;
+          }
+          pending[c.handle].watermark = (uint64_t) c.value;
+          break;
+        case Cmd::SET_IQ_REVERSE:
+          if (iq_reverse != (c.enabled != 0)) { iq_reverse = c.enabled != 0; plan_dirty = true; }
+          break;
+        case Cmd::SET_THROTTLE:
+          throttle = c.value > 0 ? c.value : 0;
+          throttle_t0 = std::chrono::steady_clock::now(); throttle_s0 = total_samples;   // pace from here on
+          break;
         case Cmd::SET_PARAMS: {
           params = c.params; plan_dirty = true;
           sdb_analyzer_params *m = (sdb_analyzer_params *) malloc(sizeof(*m));
@@ -369,10 +411,21 @@ struct sdb_analyzer {
       long got = source_read(buf.data(), block);
       if (got < 0) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
       if ((size_t) got < block) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_EOS; break; }   // partial tail blocks are dropped
+      // baseband filters see (and may rewrite) every float32 block before the analyzer does, in registration order
+      if (src.read || src.input_format == SDB_FORMAT_FLOAT32) {
+        std::vector<BbFilter> fl;
+        { std::lock_guard<std::mutex> l(cmd_m); fl = bb_filters; }
+        for (auto &f : fl) f.fn(f.priv, this, buf.data(), (uint64_t) block, total_samples);
+      }
       if (sdb_engine_feed_host(eng, buf.data(), block, block) || sdb_engine_sync(eng)) {
         exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break;
       }
       total_samples += block;
+      if (throttle > 0) {                                // suscan_analyzer_set_throttle_async: pace to `throttle` samples/s
+        const double due = (double) (total_samples - throttle_s0) / throttle;
+        const double now = std::chrono::duration<double>(std::chrono::steady_clock::now() - throttle_t0).count();
+        if (due > now) std::this_thread::sleep_for(std::chrono::duration<double>(due - now));
+      }
       double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       measured_rate = el > 0 ? (double) total_samples / el : 0;
       // PSD messages at psd_update_int cadence of SIGNAL time (coverage = N / (fs * interval))
@@ -410,13 +463,7 @@ struct sdb_analyzer {
           soft.resize((size_t) nch); hard.resize((size_t) nch);
           long n = sdb_engine_read_symbols(sb.eng, 0, i.engine_handle, soft.data(), hard.data(), (size_t) nch);
           if (n <= 0) continue;
-          sdb_analyzer_sample_batch_msg *m = (sdb_analyzer_sample_batch_msg *) calloc(1, sizeof(*m));
-          m->inspector_id = i.inspector_id; m->sample_count = (uint64_t) n;
-          m->samples = (sdb_complex *) malloc((size_t) n * sizeof(sdb_complex));
-          m->symbols = (uint8_t *) malloc((size_t) n);
-          memcpy(m->samples, soft.data(), (size_t) n * sizeof(sdb_complex));
-          memcpy(m->symbols, hard.data(), (size_t) n);
-          post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
+          deliver(i, soft.data(), hard.data(), (size_t) n, false);
         }
       }
       for (auto &i : insps) {
@@ -425,13 +472,7 @@ struct sdb_analyzer {
         soft.resize(cap); hard.resize(cap);
         long n = sdb_engine_read_symbols(eng, 0, i.engine_handle, soft.data(), hard.data(), cap);
         if (n <= 0) continue;
-        sdb_analyzer_sample_batch_msg *m = (sdb_analyzer_sample_batch_msg *) calloc(1, sizeof(*m));
-        m->inspector_id = i.inspector_id; m->sample_count = (uint64_t) n;
-        m->samples = (sdb_complex *) malloc((size_t) n * sizeof(sdb_complex));
-        m->symbols = (uint8_t *) malloc((size_t) n);
-        memcpy(m->samples, soft.data(), (size_t) n * sizeof(sdb_complex));
-        memcpy(m->symbols, hard.data(), (size_t) n);
-        post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
+        deliver(i, soft.data(), hard.data(), (size_t) n, false);
       }
       // kind=SPECTRUM / kind=ESTIMATOR inspector messages (one per block that filled a frame)
       for (auto &i : insps) {
@@ -480,6 +521,8 @@ struct sdb_analyzer {
         }
       }
     }
+    for (auto &i : insps)                                // what the watermark still holds back goes out with the end
+      if (i.has_id && pending.count(i.handle)) deliver(i, nullptr, nullptr, 0, true);
     drop_subs();
     if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
     post_status(exit_type, 0, exit_type == SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR ? sdb_last_error() : nullptr);
@@ -603,6 +646,29 @@ extern "C" int sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint3
 {
   Cmd c; c.kind = Cmd::CLOSE; c.req_id = req_id; c.handle = handle;
   return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int32_t handle, uint64_t watermark,
+                                                          uint32_t req_id)
+{
+  Cmd c; c.kind = Cmd::SET_WATERMARK; c.req_id = req_id; c.handle = handle; c.value = (double) watermark;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled)
+{
+  Cmd c; c.kind = Cmd::SET_IQ_REVERSE; c.enabled = enabled;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_throttle_async(sdb_analyzer_t *a, uint64_t samp_rate, uint32_t req_id)
+{
+  Cmd c; c.kind = Cmd::SET_THROTTLE; c.req_id = req_id; c.value = (double) samp_rate;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *priv)
+{
+  if (!a || !fn) return -1;
+  std::lock_guard<std::mutex> l(a->cmd_m);
+  a->bb_filters.push_back({ fn, priv });
+  return 0;
 }
 extern "C" int sdb_analyzer_inspector_set_spectrum_async(sdb_analyzer_t *a, int32_t handle, uint32_t spectsrc_id,
                                                          uint32_t req_id)

@@ -772,7 +772,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
   if (K && n % (W / 2)) return fail("feed size must be a multiple of st_window_size / 2");
   CK(cudaSetDevice(e->prm.device));
   const void *x = reinterpret_cast<const void *>(xv);
-  const int fmt = e->prm.input_format;
+  const int fmt = e->prm.input_format | ((e->prm.flags & SDB_FLAG_IQ_REVERSE) ? SDB_FMT_SWAP : 0);
   const size_t bps = sdb_fmt_bytes(fmt);
   SdbLaunchCtx ctx{ e->stream, &e->launches };
   const int shift_db = (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) ? 1 : 0;

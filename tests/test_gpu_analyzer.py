@@ -105,6 +105,125 @@ def test_analyzer_memory_source_halt(sdb):
     a.close()
 
 
+def test_analyzer_inspector_watermark(sdb):
+    """suscan_analyzer_set_inspector_watermark_async (Default/Audio/AudioProcessor.cpp:745-747): batches are held
+    back until they carry `watermark` samples; the stream itself is unchanged."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 8192, 1.0e6
+    baud = fs / 100.0
+    n = 8 * N * 8
+    x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs, baud, -10.0, {})], noise_db=-50.0, seed=2)
+
+    def run(watermark):
+        go = threading.Event()
+        pos = [0]
+
+        def read(priv, dst, maxn):
+            go.wait(30)
+            take = min(maxn, n - pos[0])
+            if take > 0:
+                C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+                pos[0] += take
+            return take
+
+        a = Analyzer(fs, window_size=N, window="hann", psd_update_int=1.0, read=read, read_size=N * 8)
+        assert a.read(5000)[0] == "SOURCE_INFO"
+        a.open("psk", 0.125 * fs, 3 * baud, req_id=1)
+        a.set_inspector_id(0, 5, req_id=2)
+        cfg = sdb.InspectorConfig()
+        sdb._check(sdb.load_library().sdb_inspector_config_default(C.byref(cfg), sdb.INSP["psk"], fs * 256 / N))
+        cfg.baud, cfg.costas_order, cfg.bits_per_symbol, cfg.clock_type, cfg.clock_running = baud, 2, 2, 1, 1
+        a.set_inspector_config(0, cfg, req_id=3)
+        if watermark:
+            a.set_inspector_watermark(0, watermark, req_id=4)
+        go.set()
+        sizes, soft = [], []
+        while True:
+            name, m = a.read(20000)
+            assert name != "TIMEOUT"
+            if name == "SAMPLES":
+                sizes.append(len(m["samples"]))
+                soft.append(m["samples"])
+            elif name in ("EOS", "READ_ERROR", "HALT"):
+                break
+        a.close()
+        return sizes, np.concatenate(soft)
+
+    s0, a0 = run(0)
+    s1, a1 = run(1500)
+    assert len(s0) == 7 and all(600 < v < 700 for v in s0)             # one batch per block (~655 symbols)
+    assert all(v >= 1500 for v in s1[:-1]) and len(s1) < len(s0)        # held back; the tail is flushed at EOS
+    assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32))
+
+
+def test_analyzer_source_options(sdb, oracle):
+    """iq_reverse, baseband filter hook and throttle (Suscan/Analyzer.cpp:117-135, 238-244;
+    Default/Source/SourceWidget.cpp:1156-1184)."""
+    import time
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 4096, 1.0e6
+    blocks = 6
+    x = (0.2 * np.exp(2j * np.pi * 0.1 * np.arange(N * 4 * blocks))).astype(np.complex64)
+    seen = []
+
+    def recorder(samples, offset):               # the GUI's baseband recorder: sees every block, in order
+        seen.append((offset, samples.copy()))
+        return True
+
+    def scaler(samples, offset):                 # a filter may rewrite the block the analyzer will see
+        samples *= np.float32(0.5)
+        return True
+
+    go = threading.Event()
+    pos = [0]
+
+    def read(priv, dst, maxn):
+        go.wait(30)
+        take = min(maxn, len(x) - pos[0])
+        if take > 0:
+            C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+            pos[0] += take
+        return take
+
+    a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, read=read, read_size=N * 4)
+    assert a.read(5000)[0] == "SOURCE_INFO"
+    a.register_baseband_filter(recorder)
+    a.register_baseband_filter(scaler)
+    a.set_iq_reverse(True)
+    a.set_throttle(2e6)                          # 5 more blocks of 16384 samples at 2 MS/s: >= 41 ms
+    t0 = time.time()
+    go.set()
+    psd = []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "PSD":
+            psd.append(m["psd"])
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    dt = time.time() - t0
+    a.close()
+    assert name == "EOS" and len(psd) == 4 * blocks
+    # the options are requests: they apply from the block after the one in flight when they arrive, so compare
+    # frame by frame with the two possible inputs and require the swapped one from some block on
+    half = (x * np.float32(0.5)).astype(np.complex64)
+    ref_n = oracle.psd_frames(half, N, "hann")
+    ref_s = oracle.psd_frames((half.imag + 1j * half.real).astype(np.complex64), N, "hann")
+    kinds = []
+    for i, p in enumerate(psd):
+        if np.array_equal(p.view(np.uint32), ref_s[i].view(np.uint32)):
+            kinds.append("s")
+        else:
+            assert np.array_equal(p.view(np.uint32), ref_n[i].view(np.uint32)), i
+            kinds.append("n")
+    assert kinds[-4:] == ["s"] * 4 and "".join(kinds) == "n" * kinds.count("n") + "s" * kinds.count("s")
+    # the mirrored tone of (Q, I) sits at -0.1 fs
+    assert abs(int(np.argmax(psd[-1])) - round(0.9 * N)) <= 1
+    assert [o for o, _ in seen] == [i * N * 4 for i in range(blocks)]
+    assert np.array_equal(np.concatenate([s for _, s in seen]), x)       # recorder ran before the scaler
+    assert dt >= 0.035
+
+
 def test_analyzer_subcarrier_inspector(sdb, oracle):
     """open_ex with a parent handle (Default/GenericInspector/GenericInspector.cpp:502-525): a PSK inspector on a
     sub-carrier of a raw inspector's channel = two channelisers in series; symbols bit-identical to the oracle."""

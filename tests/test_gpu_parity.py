@@ -495,6 +495,39 @@ def test_native_sample_formats(sdb, oracle, fmt):
                                     exact_soft=True)
 
 
+@pytest.mark.parametrize("fmt,N", [("f32", 65536), ("f32", 4096), ("s16", 65536), ("u8", 8192)])
+def test_iq_reverse_flag(sdb, fmt, N):
+    """SDB_FLAG_IQ_REVERSE (suscan_analyzer_set_iq_reverse): the swap happens inside the first load, for every
+    transform size path and sample format, history across feeds included: bit-identical to feeding (Q, I)."""
+    S, n = 2, N * 4
+    rng = np.random.default_rng(N)
+    iq = (0.4 * rng.standard_normal((S, n, 2))).astype(np.float32)
+    if fmt == "s16":
+        q = np.clip(np.rint(iq * 32768.0), -32768, 32767).astype(np.int16)
+    elif fmt == "u8":
+        q = np.clip(np.rint(iq * 128.0 + 128.0), 0, 255).astype(np.uint8)
+    else:
+        q = iq.view(np.complex64)[..., 0]
+    swapped = np.ascontiguousarray(q[..., ::-1]) if fmt != "f32" else (q.imag + 1j * q.real).astype(np.complex64)
+
+    def run(data, flags):
+        e = sdb.Engine(n_streams=S, psd_size=N, psd_window="hann", max_feed=n, input_format=fmt, flags=flags)
+        h = e.open_channel(2 * np.pi * 0.2, 2 * np.pi / 16, 1.0)
+        e.commit()
+        out = []
+        for seg in (slice(0, n // 2), slice(n // 2, n)):
+            e.feed(data[:, seg])
+            out.append((e.read_psd().copy(), [e.read_channel(s, h) for s in range(S)]))
+        return out
+
+    a = run(q, sdb.FLAG_IQ_REVERSE)
+    b = run(swapped, 0)
+    for (pa, ca), (pb, cb) in zip(a, b):
+        assert np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+        for x, y in zip(ca, cb):
+            assert len(x) == len(y) and np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
 def test_async_pipeline_matches_sync(sdb):
     """feed_host + read_*_async queued back to back (H2D / kernels / D2H of neighbouring feeds overlap,
     results double-buffered) must give exactly what feed + blocking reads give."""
