@@ -367,6 +367,10 @@ int    sdb_analyzer_close_async(sdb_analyzer_t *a, int32_t handle, uint32_t req_
 /* suscan_analyzer_set_inspector_watermark_async (Suscan/Analyzer.cpp:527-537; Default/Audio/AudioProcessor.cpp:745-747):
  * SAMPLES batches of this inspector are held back until they contain `watermark` samples (0 = one batch per block) */
 int    sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int32_t handle, uint64_t watermark, uint32_t req_id);
+/* suscan_analyzer_set_inspector_freq_overridable / _bandwidth_overridable (Suscan/Analyzer.cpp:509-526): no reply, the
+ * latest value wins; freq in Hz relative to the tuner (or to the parent's centre), bw in Hz */
+int    sdb_analyzer_set_inspector_freq_overridable(sdb_analyzer_t *a, int32_t handle, double freq);
+int    sdb_analyzer_set_inspector_bandwidth_overridable(sdb_analyzer_t *a, int32_t handle, double bw);
 /* suscan_analyzer_inspector_set_spectrum_async / _estimator_cmd_async (Suscan/Analyzer.cpp:539-565) */
 int    sdb_analyzer_inspector_set_spectrum_async(sdb_analyzer_t *a, int32_t handle, uint32_t spectsrc_id, uint32_t req_id);
 int    sdb_analyzer_inspector_estimator_cmd_async(sdb_analyzer_t *a, int32_t handle, uint32_t estimator_id,

@@ -132,6 +132,12 @@ class Analyzer:
     def set_inspector_watermark(self, handle, watermark, req_id=0):
         self._L.sdb_analyzer_set_inspector_watermark_async(self._h, handle, int(watermark), req_id)
 
+    def set_inspector_freq(self, handle, freq):
+        self._L.sdb_analyzer_set_inspector_freq_overridable(self._h, handle, float(freq))
+
+    def set_inspector_bandwidth(self, handle, bw):
+        self._L.sdb_analyzer_set_inspector_bandwidth_overridable(self._h, handle, float(bw))
+
     def set_iq_reverse(self, enabled=True):
         self._L.sdb_analyzer_set_iq_reverse(self._h, int(enabled))
 

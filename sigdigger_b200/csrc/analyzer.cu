@@ -34,7 +34,8 @@
 namespace {
 
 struct Cmd {
-  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK } kind;
+  enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK,
+              SET_FREQ, SET_BANDWIDTH } kind;
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
   double value = 0;                           // throttle rate
@@ -351,6 +352,24 @@ struct sdb_analyzer {
           }
           pending[c.handle].watermark = (uint64_t) c.value;
           break;
+        case Cmd::SET_FREQ:
+        case Cmd::SET_BANDWIDTH: {
+          // "overridable" setters (Suscan/Analyzer.cpp:509-526): no reply; the latest value wins.  The channel is
+          // re-planned at the next block boundary (see the a18 limits in DESIGN.md).
+          if (c.handle < 0 || c.handle >= (int32_t) insps.size() || !insps[c.handle].open) break;
+          Insp &i = insps[c.handle];
+          const double rate = i.parent >= 0 ? (double) insps[i.parent].fs : src.samp_rate;
+          if (c.kind == Cmd::SET_FREQ) {
+            if (fabs(c.value) > rate / 2) break;
+            i.channel.fc = c.value; i.lo = (float) c.value;
+          } else {
+            if (!(c.value > 0) || c.value > rate) break;
+            i.channel.f_lo = -0.5 * c.value; i.channel.f_hi = 0.5 * c.value; i.channel.bw = (float) c.value;
+            i.bandwidth = (float) c.value;
+          }
+          plan_dirty = true;
+          break;
+        }
         case Cmd::SET_IQ_REVERSE:
           if (iq_reverse != (c.enabled != 0)) { iq_reverse = c.enabled != 0; plan_dirty = true; }
           break;
@@ -651,6 +670,16 @@ extern "C" int sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int
                                                           uint32_t req_id)
 {
   Cmd c; c.kind = Cmd::SET_WATERMARK; c.req_id = req_id; c.handle = handle; c.value = (double) watermark;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_inspector_freq_overridable(sdb_analyzer_t *a, int32_t handle, double freq)
+{
+  Cmd c; c.kind = Cmd::SET_FREQ; c.handle = handle; c.value = freq;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_inspector_bandwidth_overridable(sdb_analyzer_t *a, int32_t handle, double bw)
+{
+  Cmd c; c.kind = Cmd::SET_BANDWIDTH; c.handle = handle; c.value = bw;
   return push_cmd(a, std::move(c));
 }
 extern "C" int sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled)

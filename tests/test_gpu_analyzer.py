@@ -156,6 +156,65 @@ def test_analyzer_inspector_watermark(sdb):
     assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32))
 
 
+def test_analyzer_overridable_freq_and_bandwidth(sdb):
+    """suscan_analyzer_set_inspector_freq_overridable / _bandwidth_overridable (Suscan/Analyzer.cpp:509-526): a raw
+    inspector opened beside a tone is retuned onto it, then widened."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 4096, 1.0e6
+    n = 10 * N * 4
+    x = (0.3 * np.exp(2j * np.pi * 0.2 * np.arange(n))).astype(np.complex64)
+    go = threading.Event()
+    step = threading.Semaphore(0)
+    pos = [0]
+
+    def read(priv, dst, maxn):                        # one block per permit: the test decides when time advances
+        go.wait(30)
+        step.acquire(timeout=30)
+        take = min(maxn, n - pos[0])
+        if take > 0:
+            C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+            pos[0] += take
+        return take
+
+    a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, read=read, read_size=N * 4)
+    assert a.read(5000)[0] == "SOURCE_INFO"
+    a.open("raw", 0.1 * fs, fs / 16.0, req_id=1)
+    a.set_inspector_id(0, 9, req_id=2)
+    go.set()
+
+    def advance(k, batches=None):
+        """let k blocks through (4 PSD frames each, then one SAMPLES batch per block once the inspector runs) and
+        return the batches"""
+        batches = k if batches is None else batches
+        for _ in range(k):
+            step.release()
+        psds, out = 0, []
+        while psds < 4 * k or len(out) < batches:
+            name, m = a.read(20000)
+            assert name not in ("TIMEOUT", "EOS", "READ_ERROR", "HALT")
+            if name == "PSD":
+                psds += 1
+            elif name == "SAMPLES":
+                out.append(m["samples"])
+        return out
+
+    assert advance(1, 0) == []                        # block 0: the requests are still queued
+    off = advance(2)[-1]                              # tuned 0.1 fs away from the tone: almost nothing in the channel
+    a.set_inspector_freq(0, 0.2 * fs)
+    advance(1)                                        # the block in flight when the request lands: either tuning
+    on = advance(2)[-1]                               # retuned: the tone sits at the channel centre
+    p_off, p_on = np.mean(np.abs(off) ** 2), np.mean(np.abs(on) ** 2)
+    assert p_on > 0.05 and p_off < 1e-3 * p_on
+    a.set_inspector_bandwidth(0, fs / 4.0)
+    advance(1)
+    wide = advance(2)[-1]
+    assert len(wide) == 4 * len(on)                   # four times the bandwidth: four times the channel rate
+    a.halt()
+    for _ in range(4):
+        step.release()
+    a.close()
+
+
 def test_analyzer_source_options(sdb, oracle):
     """iq_reverse, baseband filter hook and throttle (Suscan/Analyzer.cpp:117-135, 238-244;
     Default/Source/SourceWidget.cpp:1156-1184)."""
