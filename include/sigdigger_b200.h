@@ -384,6 +384,9 @@ int    sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyzer_param
  * it is analysed; it may rewrite the samples. */
 typedef int (*sdb_baseband_filter_fn)(void *privdata, sdb_analyzer_t *a, sdb_complex *samples, uint64_t length,
                                       uint64_t offset);
+/* suscan_analyzer_seek (Suscan/Analyzer.cpp:151-155): position (signal time) in a seekable source, i.e. an in-memory
+ * / mapped capture; applied at the next block boundary; -1 for callback sources */
+int    sdb_analyzer_seek(sdb_analyzer_t *a, const struct timeval *pos);
 int    sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled);
 int    sdb_analyzer_set_throttle_async(sdb_analyzer_t *a, uint64_t samp_rate, uint32_t req_id);
 int    sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *privdata);

@@ -192,6 +192,7 @@ _PROTOS = {
     "sdb_analyzer_set_inspector_watermark_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32]),
     "sdb_analyzer_set_inspector_freq_overridable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "sdb_analyzer_set_inspector_bandwidth_overridable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
+    "sdb_analyzer_seek": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdb_analyzer_set_iq_reverse": (C.c_int, [C.c_void_p, C.c_int]),
     "sdb_analyzer_set_throttle_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "sdb_analyzer_register_baseband_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -138,6 +138,10 @@ class Analyzer:
     def set_inspector_bandwidth(self, handle, bw):
         self._L.sdb_analyzer_set_inspector_bandwidth_overridable(self._h, handle, float(bw))
 
+    def seek(self, seconds):
+        tv = Timeval(int(seconds), int(round((seconds - int(seconds)) * 1e6)))
+        return self._L.sdb_analyzer_seek(self._h, C.byref(tv)) == 0
+
     def set_iq_reverse(self, enabled=True):
         self._L.sdb_analyzer_set_iq_reverse(self._h, int(enabled))
 

@@ -35,7 +35,7 @@ namespace {
 
 struct Cmd {
   enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK,
-              SET_FREQ, SET_BANDWIDTH } kind;
+              SET_FREQ, SET_BANDWIDTH, SEEK } kind;
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
   double value = 0;                           // throttle rate
@@ -351,6 +351,12 @@ struct sdb_analyzer {
             post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_HANDLE, c, nullptr); break;
           }
           pending[c.handle].watermark = (uint64_t) c.value;
+          break;
+        case Cmd::SEEK:       // suscan_analyzer_seek (Suscan/Analyzer.cpp:151-155): in-memory captures only
+          if (!src.read && src.data && c.value >= 0) {
+            const double p = c.value * src.samp_rate;
+            src_pos = p >= (double) src.length ? src.length : (size_t) p;
+          }
           break;
         case Cmd::SET_FREQ:
         case Cmd::SET_BANDWIDTH: {
@@ -670,6 +676,12 @@ extern "C" int sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int
                                                           uint32_t req_id)
 {
   Cmd c; c.kind = Cmd::SET_WATERMARK; c.req_id = req_id; c.handle = handle; c.value = (double) watermark;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_seek(sdb_analyzer_t *a, const struct timeval *pos)
+{
+  if (!a || !pos || a->src.read || !a->src.data) return -1;      // seekable sources only (source_info.seekable)
+  Cmd c; c.kind = Cmd::SEEK; c.value = (double) pos->tv_sec + 1e-6 * (double) pos->tv_usec;
   return push_cmd(a, std::move(c));
 }
 extern "C" int sdb_analyzer_set_inspector_freq_overridable(sdb_analyzer_t *a, int32_t handle, double freq)

@@ -105,6 +105,33 @@ def test_analyzer_memory_source_halt(sdb):
     a.close()
 
 
+def test_analyzer_seek(sdb):
+    """suscan_analyzer_seek on a seekable (in-memory) source; callback sources refuse."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 4096, 1.0e6
+    blk = N * 4
+    na, nb = 400 * blk, 4 * blk
+    t = np.arange(na + nb)
+    x = np.where(t < na, np.exp(2j * np.pi * 0.1 * t), np.exp(2j * np.pi * 0.3 * t)).astype(np.complex64) * np.float32(0.2)
+    a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, data=x, read_size=blk)
+    assert a.seek(na / fs)                                   # jump over (most of) the first tone
+    peaks = []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "PSD":
+            peaks.append(int(np.argmax(m["psd"])))
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    a.close()
+    assert name == "EOS"
+    assert len(peaks) < (na + nb) // N                       # blocks were skipped
+    assert peaks[-16:] == [round(0.3 * N)] * 16              # and the capture ended on its last four blocks
+    b = Analyzer(fs, window_size=N, read=lambda priv, dst, n: 0, read_size=blk)
+    assert not b.seek(0.5)
+    b.close()
+
+
 def test_analyzer_inspector_watermark(sdb):
     """suscan_analyzer_set_inspector_watermark_async (Default/Audio/AudioProcessor.cpp:745-747): batches are held
     back until they carry `watermark` samples; the stream itself is unchanged."""
