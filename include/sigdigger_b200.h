@@ -322,7 +322,16 @@ typedef struct {
   const sdb_complex *data; size_t length; int32_t loop;
   int32_t device;
   int32_t input_format;           /* SDB_FORMAT_* of `data` (length counts IQ pairs); callback sources deliver float32 */
+  int (*set_frequency)(void *priv, double freq);   /* tuner of the source; used by the wide-spectrum mode (may be NULL) */
 } sdb_source_config;
+
+/* Wide-spectrum (panoramic) mode, sdb_analyzer_params.mode = SDB_ANALYZER_MODE_WIDE_SPECTRUM
+ * (Panoramic/Scanner.cpp:296-372): the worker retunes the source, drops `buffering_size` samples, takes one window and
+ * posts its PSD with the hop centre in psd_msg.fc; the hop plan follows min_freq / max_freq (set_hop_range),
+ * rel_bandwidth, the sweep strategy and the partitioning (Panoramic/Scanner.cpp:396-431, 452-503;
+ * include/Suscan/Analyzer.h:263-271, 321-333). */
+enum { SDB_SWEEP_STRATEGY_STOCHASTIC = 0, SDB_SWEEP_STRATEGY_PROGRESSIVE = 1 };
+enum { SDB_SPECTRUM_PARTITIONING_DISCRETE = 0, SDB_SPECTRUM_PARTITIONING_CONTINUOUS = 1 };
 
 typedef struct {                  /* suscan_analyzer_psd_msg */
   int64_t fc; uint32_t inspector_id; struct timeval timestamp, rt_time; int32_t looped; uint64_t history_size;
@@ -387,6 +396,11 @@ typedef int (*sdb_baseband_filter_fn)(void *privdata, sdb_analyzer_t *a, sdb_com
 /* suscan_analyzer_seek (Suscan/Analyzer.cpp:151-155): position (signal time) in a seekable source, i.e. an in-memory
  * / mapped capture; applied at the next block boundary; -1 for callback sources */
 int    sdb_analyzer_seek(sdb_analyzer_t *a, const struct timeval *pos);
+int    sdb_analyzer_set_hop_range(sdb_analyzer_t *a, double min_freq, double max_freq);   /* Analyzer.cpp:255-260 */
+int    sdb_analyzer_set_rel_bandwidth(sdb_analyzer_t *a, float rel_bw);
+int    sdb_analyzer_set_buffering_size(sdb_analyzer_t *a, uint64_t samples);
+int    sdb_analyzer_set_sweep_strategy(sdb_analyzer_t *a, int strategy);
+int    sdb_analyzer_set_spectrum_partitioning(sdb_analyzer_t *a, int partitioning);
 int    sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled);
 int    sdb_analyzer_set_throttle_async(sdb_analyzer_t *a, uint64_t samp_rate, uint32_t req_id);
 int    sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *privdata);

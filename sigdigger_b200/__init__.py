@@ -193,6 +193,11 @@ _PROTOS = {
     "sdb_analyzer_set_inspector_freq_overridable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "sdb_analyzer_set_inspector_bandwidth_overridable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "sdb_analyzer_seek": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_analyzer_set_hop_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "sdb_analyzer_set_rel_bandwidth": (C.c_int, [C.c_void_p, C.c_float]),
+    "sdb_analyzer_set_buffering_size": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sdb_analyzer_set_sweep_strategy": (C.c_int, [C.c_void_p, C.c_int]),
+    "sdb_analyzer_set_spectrum_partitioning": (C.c_int, [C.c_void_p, C.c_int]),
     "sdb_analyzer_set_iq_reverse": (C.c_int, [C.c_void_p, C.c_int]),
     "sdb_analyzer_set_throttle_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "sdb_analyzer_register_baseband_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

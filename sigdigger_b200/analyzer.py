@@ -35,12 +35,13 @@ class AnalyzerParams(C.Structure):
 
 READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.c_void_p, C.c_size_t)
 BB_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64)
+SETF_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double)
 
 
 class SourceConfig(C.Structure):
     _fields_ = [("samp_rate", C.c_double), ("freq", C.c_double), ("read_size", C.c_size_t), ("read", READ_FN),
                 ("priv", C.c_void_p), ("data", C.c_void_p), ("length", C.c_size_t), ("loop", C.c_int32),
-                ("device", C.c_int32), ("input_format", C.c_int32)]
+                ("device", C.c_int32), ("input_format", C.c_int32), ("set_frequency", SETF_FN)]
 
 
 class PsdMsg(C.Structure):
@@ -74,10 +75,11 @@ class StatusMsg(C.Structure):
 class Analyzer:
     def __init__(self, samp_rate, window_size=8192, window="hann", psd_update_int=0.04, data=None, read=None,
                  read_size=0, loop=False, freq=0.0, device=0, channel_update_int=0.0, alpha=0.25, beta=0.25,
-                 gamma=0.5, snr=8.0):
+                 gamma=0.5, snr=8.0, wide=False, min_freq=0.0, max_freq=0.0, set_frequency=None):
         self._L = load_library()
         p = AnalyzerParams()
-        p.mode = 0
+        p.mode = 1 if wide else 0                      # SDB_ANALYZER_MODE_{CHANNEL, WIDE_SPECTRUM}
+        p.min_freq, p.max_freq = min_freq, max_freq
         p.detector_params.window_size = window_size
         p.detector_params.window = WINDOW[window] if isinstance(window, str) else window
         p.detector_params.alpha, p.detector_params.beta = alpha, beta
@@ -102,6 +104,9 @@ class Analyzer:
         else:
             self._cb = READ_FN(read)
             s.read = self._cb
+        if set_frequency is not None:
+            self._setf = SETF_FN(lambda priv, f: int(set_frequency(f) or 0))
+            s.set_frequency = self._setf
         self._h = self._L.sdb_analyzer_new(C.byref(p), C.byref(s))
         if not self._h:
             raise SdbError(last_error() or "sdb_analyzer_new failed (no CUDA device or invalid parameters)")
@@ -137,6 +142,22 @@ class Analyzer:
 
     def set_inspector_bandwidth(self, handle, bw):
         self._L.sdb_analyzer_set_inspector_bandwidth_overridable(self._h, handle, float(bw))
+
+    # wide-spectrum (panoramic) mode controls, Panoramic/Scanner.cpp:396-503
+    def set_hop_range(self, fmin, fmax):
+        return self._L.sdb_analyzer_set_hop_range(self._h, float(fmin), float(fmax)) == 0
+
+    def set_rel_bandwidth(self, rel_bw):
+        self._L.sdb_analyzer_set_rel_bandwidth(self._h, float(rel_bw))
+
+    def set_buffering_size(self, samples):
+        self._L.sdb_analyzer_set_buffering_size(self._h, int(samples))
+
+    def set_sweep_strategy(self, progressive=True):
+        self._L.sdb_analyzer_set_sweep_strategy(self._h, 1 if progressive else 0)
+
+    def set_spectrum_partitioning(self, continuous=False):
+        self._L.sdb_analyzer_set_spectrum_partitioning(self._h, 1 if continuous else 0)
 
     def seek(self, seconds):
         tv = Timeval(int(seconds), int(round((seconds - int(seconds)) * 1e6)))

@@ -35,7 +35,9 @@ namespace {
 
 struct Cmd {
   enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK,
-              SET_FREQ, SET_BANDWIDTH, SEEK } kind;
+              SET_FREQ, SET_BANDWIDTH, SEEK, SET_HOP_RANGE, SET_REL_BW, SET_BUFFERING, SET_STRATEGY,
+              SET_PARTITIONING } kind;
+  double value2 = 0;
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
   double value = 0;                           // throttle rate
@@ -352,6 +354,15 @@ struct sdb_analyzer {
           }
           pending[c.handle].watermark = (uint64_t) c.value;
           break;
+        case Cmd::SET_HOP_RANGE:
+          if (c.value <= c.value2) { hop_min = c.value; hop_max = c.value2; hop_index = 0; }
+          break;
+        case Cmd::SET_REL_BW:
+          if (c.value > 0) rel_bw = (float) (c.value > 1 ? 1 : c.value);
+          break;
+        case Cmd::SET_BUFFERING: buffering = (uint64_t) c.value; break;
+        case Cmd::SET_STRATEGY: strategy = c.enabled; hop_index = 0; break;
+        case Cmd::SET_PARTITIONING: partitioning = c.enabled; break;
         case Cmd::SEEK:       // suscan_analyzer_seek (Suscan/Analyzer.cpp:151-155): in-memory captures only
           if (!src.read && src.data && c.value >= 0) {
             const double p = c.value * src.samp_rate;
@@ -385,6 +396,7 @@ struct sdb_analyzer {
           break;
         case Cmd::SET_PARAMS: {
           params = c.params; plan_dirty = true;
+          hop_min = params.min_freq; hop_max = params.max_freq; hop_index = 0;
           sdb_analyzer_params *m = (sdb_analyzer_params *) malloc(sizeof(*m));
           *m = params;
           post(SDB_ANALYZER_MESSAGE_TYPE_PARAMS, m);
@@ -412,12 +424,119 @@ struct sdb_analyzer {
     return (long) got;
   }
 
+  // ---------------------------------------------------------------------------------------------------------
+  // SUSCAN_ANALYZER_MODE_WIDE_SPECTRUM: the panoramic scanner's analyzer (Panoramic/Scanner.cpp:296-372, 419-523):
+  // retune, drop `buffering` samples (tuner round trip), take one window, post its PSD with the hop's centre; the GUI
+  // stitches the hops (SpectrumView).  Hops are independent, so HB of them go through the engine as HB streams.
+  // Hop plan (own definition, the upstream one is not in the reference): step = rel_bw fs; PROGRESSIVE: centres
+  // min + step/2 + i step while the hop still starts below max, then wrap; STOCHASTIC: uniform in [min, max] from a
+  // 32-bit LCG, snapped to the progressive grid when the partitioning is DISCRETE.  min == max: one centre.
+  // ---------------------------------------------------------------------------------------------------------
+  double hop_min = 0, hop_max = 0; float rel_bw = 0.5f; uint64_t buffering = 0;
+  int strategy = SDB_SWEEP_STRATEGY_PROGRESSIVE, partitioning = SDB_SPECTRUM_PARTITIONING_DISCRETE;
+  uint64_t hop_index = 0; uint32_t lcg = 0x5167D166u;
+  double next_hop()
+  {
+    const double step = (double) rel_bw * src.samp_rate;
+    if (!(hop_max > hop_min) || !(step > 0)) return hop_min;
+    const uint64_t n_grid = (uint64_t) ceil((hop_max - hop_min) / step);
+    if (strategy == SDB_SWEEP_STRATEGY_PROGRESSIVE) {
+      const uint64_t i = hop_index++ % (n_grid ? n_grid : 1);
+      return hop_min + 0.5 * step + (double) i * step;
+    }
+    lcg = lcg * 1664525u + 1013904223u;
+    const double u = (double) (lcg >> 8) / 16777216.0;
+    if (partitioning == SDB_SPECTRUM_PARTITIONING_DISCRETE) {
+      uint64_t i = (uint64_t) (u * (double) n_grid);
+      if (i >= n_grid) i = n_grid - 1;
+      return hop_min + 0.5 * step + (double) i * step;
+    }
+    return hop_min + u * (hop_max - hop_min);
+  }
+
+  void run_wide()
+  {
+    const size_t HB = 16;
+    uint32_t exit_type = SDB_WORKER_MSG_TYPE_HALT;
+    std::vector<sdb_complex> buf, drop;
+    std::vector<float> psd;
+    std::vector<double> fcs(HB);
+    hop_min = params.min_freq; hop_max = params.max_freq;
+    for (;;) {
+      { std::lock_guard<std::mutex> l(cmd_m); if (halt_req) break; }
+      handle_cmds();
+      const size_t N = (size_t) params.detector_params.window_size;
+      if (plan_dirty) {
+        if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
+        sdb_engine_params ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.n_streams = (uint32_t) HB; ep.psd_size = (uint32_t) N; ep.psd_window = params.detector_params.window;
+        ep.max_feed = (uint32_t) N; ep.device = src.device;
+        ep.flags = iq_reverse ? SDB_FLAG_IQ_REVERSE : 0;
+        eng = sdb_engine_new(&ep, src.samp_rate);
+        if (!eng || sdb_engine_commit(eng)) {
+          post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error());
+          exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break;
+        }
+        plan_dirty = false;
+      }
+      buf.resize(HB * N);
+      size_t got_hops = 0;
+      bool eos = false, err = false;
+      for (size_t h = 0; h < HB && !eos && !err; ++h) {
+        fcs[h] = next_hop();
+        if (src.set_frequency && src.set_frequency(src.priv, fcs[h]) != 0) { err = true; break; }
+        for (uint64_t left = buffering; left > 0 && !eos && !err;) {          // the tuner's round trip
+          const size_t take = (size_t) std::min<uint64_t>(left, 65536);
+          drop.resize(take);
+          const long g = source_read(drop.data(), take);
+          if (g < 0) err = true; else if ((size_t) g < take) eos = true;
+          left -= take;
+        }
+        if (eos || err) break;
+        const long g = source_read(buf.data() + h * N, N);
+        if (g < 0) err = true; else if ((size_t) g < N) eos = true; else ++got_hops;
+      }
+      if (err) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
+      if (got_hops) {
+        for (size_t h = got_hops; h < HB; ++h) memset(buf.data() + h * N, 0, N * sizeof(sdb_complex));
+        if (sdb_engine_feed_host(eng, buf.data(), N, N) || sdb_engine_sync(eng)) {
+          exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break;
+        }
+        psd.resize(HB * N);
+        if (sdb_engine_read_psd(eng, psd.data(), psd.size())) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
+        for (size_t h = 0; h < got_hops; ++h) {
+          sdb_analyzer_psd_msg *m = (sdb_analyzer_psd_msg *) calloc(1, sizeof(*m));
+          m->fc = (int64_t) llround(fcs[h]); m->samp_rate = (float) src.samp_rate;
+          m->measured_samp_rate = (float) measured_rate;
+          gettimeofday(&m->rt_time, nullptr);
+          m->psd_size = N;
+          m->psd_data = (float *) malloc(N * sizeof(float));
+          memcpy(m->psd_data, &psd[h * N], N * sizeof(float));
+          post(SDB_ANALYZER_MESSAGE_TYPE_PSD, m);
+        }
+        total_samples += got_hops * (N + buffering);
+      }
+      if (eos) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_EOS; break; }
+    }
+    if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
+    post_status(exit_type, 0, exit_type == SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR ? sdb_last_error() : nullptr);
+  }
+
   void run()
   {
     std::vector<sdb_complex> buf(block);
     std::vector<float> psd;
     std::vector<sdb_complex> soft;
     std::vector<uint8_t> hard;
+    if (params.mode == SDB_ANALYZER_MODE_WIDE_SPECTRUM) {
+      sdb_source_info *si = (sdb_source_info *) calloc(1, sizeof(*si));
+      si->source_samp_rate = (uint64_t) src.samp_rate; si->effective_samp_rate = (uint64_t) src.samp_rate;
+      si->frequency = src.freq; si->seekable = 0;
+      post(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INFO, si);
+      run_wide();
+      return;
+    }
     {
       sdb_source_info *si = (sdb_source_info *) calloc(1, sizeof(*si));
       si->source_samp_rate = (uint64_t) src.samp_rate; si->effective_samp_rate = (uint64_t) src.samp_rate;
@@ -676,6 +795,34 @@ extern "C" int sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int
                                                           uint32_t req_id)
 {
   Cmd c; c.kind = Cmd::SET_WATERMARK; c.req_id = req_id; c.handle = handle; c.value = (double) watermark;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_hop_range(sdb_analyzer_t *a, double min_freq, double max_freq)
+{
+  if (min_freq > max_freq) return -1;
+  Cmd c; c.kind = Cmd::SET_HOP_RANGE; c.value = min_freq; c.value2 = max_freq;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_rel_bandwidth(sdb_analyzer_t *a, float rel_bw)
+{
+  Cmd c; c.kind = Cmd::SET_REL_BW; c.value = rel_bw;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_buffering_size(sdb_analyzer_t *a, uint64_t samples)
+{
+  Cmd c; c.kind = Cmd::SET_BUFFERING; c.value = (double) samples;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_sweep_strategy(sdb_analyzer_t *a, int strategy)
+{
+  if (strategy != SDB_SWEEP_STRATEGY_STOCHASTIC && strategy != SDB_SWEEP_STRATEGY_PROGRESSIVE) return -1;
+  Cmd c; c.kind = Cmd::SET_STRATEGY; c.enabled = strategy;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_spectrum_partitioning(sdb_analyzer_t *a, int partitioning)
+{
+  if (partitioning != SDB_SPECTRUM_PARTITIONING_DISCRETE && partitioning != SDB_SPECTRUM_PARTITIONING_CONTINUOUS) return -1;
+  Cmd c; c.kind = Cmd::SET_PARTITIONING; c.enabled = partitioning;
   return push_cmd(a, std::move(c));
 }
 extern "C" int sdb_analyzer_seek(sdb_analyzer_t *a, const struct timeval *pos)

@@ -105,6 +105,69 @@ def test_analyzer_memory_source_halt(sdb):
     a.close()
 
 
+def test_analyzer_wide_spectrum_sweep(sdb, oracle):
+    """SUSCAN_ANALYZER_MODE_WIDE_SPECTRUM (Panoramic/Scanner.cpp:296-372, 492-523): retune, drop the buffering
+    samples, one PSD per hop with the hop centre in `fc`; hop PSDs bit-identical to the oracle on the samples the
+    source delivered; progressive plan, then a narrower range."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 4096, 1.0e6
+    fmin, fmax = 100.0e6, 104.0e6
+    carriers = [(100.6e6, 0.30), (102.1e6, 0.20), (103.3e6, 0.25)]
+    state = {"fc": 0.0, "t": 0, "hops": [], "retunes": []}
+    total_hops = 40
+
+    def set_frequency(f):
+        state["fc"] = f
+        state["retunes"].append(f)
+        return 0
+
+    def read(priv, dst, n):
+        if len(state["hops"]) >= total_hops:
+            return 0
+        t = state["t"] + np.arange(n)
+        state["t"] += n
+        x = np.zeros(n, np.complex128)
+        for f, amp in carriers:
+            if abs(f - state["fc"]) < fs / 2:
+                x += amp * np.exp(2j * np.pi * ((f - state["fc"]) / fs) * t)
+        x += 1e-3 * np.exp(2j * np.pi * 0.37 * t * t / n)             # a deterministic low-level chirp as "noise"
+        x = x.astype(np.complex64)
+        C.memmove(dst, x.ctypes.data, 8 * n)
+        if n == N:
+            state["hops"].append((state["fc"], x))
+        return n
+
+    a = Analyzer(fs, window_size=N, window="blackmann_harris", read=read, wide=True, min_freq=fmin, max_freq=fmax,
+                 set_frequency=set_frequency)
+    a.set_buffering_size(1000)
+    a.set_rel_bandwidth(0.5)
+    msgs = []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "PSD":
+            msgs.append(m)
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    a.close()
+    assert name == "EOS" and len(msgs) == total_hops == len(state["hops"])
+    # progressive plan: step = rel_bw fs = 0.5 MHz, centres min + step/2 + i step, wrapping after 8 hops
+    centres = [fmin + 0.25e6 + 0.5e6 * (i % 8) for i in range(total_hops)]
+    assert [m["fc"] for m in msgs] == [int(round(c)) for c in centres]
+    assert state["retunes"][:total_hops] == centres
+    for m, (fc, x) in zip(msgs, state["hops"]):
+        assert m["fc"] == int(round(fc))
+        ref = oracle.psd_frames(x, N, "blackmann_harris")[0]
+        assert np.array_equal(m["psd"].view(np.uint32), ref.view(np.uint32))
+        inband = [f for f, _ in carriers if abs(f - fc) < 0.2 * fs]
+        if inband:                                                       # the carrier shows where it should
+            k = int(np.argmax(m["psd"]))
+            assert abs(((k + N // 2) % N - N // 2) - round((inband[0] - fc) / fs * N)) <= 1
+    # the buffering samples were requested and dropped: 1000 + 4096 per hop (requests apply from the next batch of 16
+    # hops on, so the first batch may have run without them)
+    assert state["t"] in (total_hops * (1000 + N), total_hops * N + (total_hops - 16) * 1000)
+
+
 def test_analyzer_seek(sdb):
     """suscan_analyzer_seek on a seekable (in-memory) source; callback sources refuse."""
     from sigdigger_b200.analyzer import Analyzer
