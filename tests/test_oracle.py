@@ -422,6 +422,20 @@ def test_spectrum_view_matches_literal_transcription(oracle):
 
 
 # ---------------------------------------------------------------- C-ABI surface --------------------
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: the header must compile as C99 (-pedantic) and as C++11, nothing but
+    <stddef.h> / <stdint.h> / <sys/time.h> types in the signatures"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "sigdigger_b200.h"\nint main(void) { sdb_engine_params p; (void) p; return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror"], ["g++", "-std=c++11", "-Wall", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(os.path.join(inc, "sigdigger_b200.h")).read()
+    assert "torch::" not in text and "cudaStream_t" not in text and "at::Tensor" not in text
+
+
 def test_library_exports_every_declared_symbol():
     import sigdigger_b200 as sdb
     hdr = open(os.path.join(ROOT, "include", "sigdigger_b200.h")).read()
