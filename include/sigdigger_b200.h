@@ -396,6 +396,11 @@ typedef int (*sdb_baseband_filter_fn)(void *privdata, sdb_analyzer_t *a, sdb_com
 /* suscan_analyzer_seek (Suscan/Analyzer.cpp:151-155): position (signal time) in a seekable source, i.e. an in-memory
  * / mapped capture; applied at the next block boundary; -1 for callback sources */
 int    sdb_analyzer_seek(sdb_analyzer_t *a, const struct timeval *pos);
+/* suscan_analyzer_set_history_size / suscan_analyzer_replay (Suscan/Analyzer.cpp:157-167; GUI: Default/Source/
+ * SourceWidget.cpp:1070-1073, 1206, 1508): keep the last `samples` float32 baseband samples in a ring; replay pauses
+ * the source and plays the ring in a loop (psd_msg.looped / .history_size report it) */
+int    sdb_analyzer_set_history_size(sdb_analyzer_t *a, uint64_t samples);
+int    sdb_analyzer_replay(sdb_analyzer_t *a, int enabled);
 int    sdb_analyzer_set_hop_range(sdb_analyzer_t *a, double min_freq, double max_freq);   /* Analyzer.cpp:255-260 */
 int    sdb_analyzer_set_rel_bandwidth(sdb_analyzer_t *a, float rel_bw);
 int    sdb_analyzer_set_buffering_size(sdb_analyzer_t *a, uint64_t samples);

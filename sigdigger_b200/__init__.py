@@ -193,6 +193,8 @@ _PROTOS = {
     "sdb_analyzer_set_inspector_freq_overridable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "sdb_analyzer_set_inspector_bandwidth_overridable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "sdb_analyzer_seek": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_analyzer_set_history_size": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sdb_analyzer_replay": (C.c_int, [C.c_void_p, C.c_int]),
     "sdb_analyzer_set_hop_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "sdb_analyzer_set_rel_bandwidth": (C.c_int, [C.c_void_p, C.c_float]),
     "sdb_analyzer_set_buffering_size": (C.c_int, [C.c_void_p, C.c_uint64]),

@@ -159,6 +159,12 @@ class Analyzer:
     def set_spectrum_partitioning(self, continuous=False):
         self._L.sdb_analyzer_set_spectrum_partitioning(self._h, 1 if continuous else 0)
 
+    def set_history_size(self, samples):
+        return self._L.sdb_analyzer_set_history_size(self._h, int(samples)) == 0
+
+    def replay(self, enabled=True):
+        self._L.sdb_analyzer_replay(self._h, int(enabled))
+
     def seek(self, seconds):
         tv = Timeval(int(seconds), int(round((seconds - int(seconds)) * 1e6)))
         return self._L.sdb_analyzer_seek(self._h, C.byref(tv)) == 0
@@ -200,7 +206,8 @@ class Analyzer:
             if name == "PSD":
                 m = C.cast(ptr, C.POINTER(PsdMsg)).contents
                 out = dict(psd=np.ctypeslib.as_array(m.psd_data, shape=(m.psd_size,)).copy(), samp_rate=m.samp_rate,
-                           measured_samp_rate=m.measured_samp_rate, fc=m.fc,
+                           measured_samp_rate=m.measured_samp_rate, fc=m.fc, looped=m.looped,
+                           history_size=m.history_size,
                            timestamp=m.timestamp.tv_sec + 1e-6 * m.timestamp.tv_usec)
             elif name == "SAMPLES":
                 m = C.cast(ptr, C.POINTER(SampleBatchMsg)).contents

@@ -36,7 +36,7 @@ namespace {
 struct Cmd {
   enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK,
               SET_FREQ, SET_BANDWIDTH, SEEK, SET_HOP_RANGE, SET_REL_BW, SET_BUFFERING, SET_STRATEGY,
-              SET_PARTITIONING } kind;
+              SET_PARTITIONING, SET_HISTORY, REPLAY } kind;
   double value2 = 0;
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
@@ -119,6 +119,10 @@ struct sdb_analyzer {
   bool iq_reverse = false;
   double throttle = 0;                                  // samples / s, 0 = as fast as the source delivers
   std::chrono::steady_clock::time_point throttle_t0; uint64_t throttle_s0 = 0;
+  // history ring + replay (suscan_analyzer_set_history_size / _replay, Suscan/Analyzer.cpp:157-167;
+  // Default/Source/SourceWidget.cpp:1070-1073, 1206, 1508)
+  std::vector<sdb_complex> hist; size_t hist_start = 0, hist_fill = 0, replay_pos = 0;
+  bool replaying = false, replay_wrapped = false; int looped = 0;
   struct BbFilter { sdb_baseband_filter_fn fn; void *priv; };
   std::vector<BbFilter> bb_filters;
 
@@ -354,6 +358,14 @@ struct sdb_analyzer {
           }
           pending[c.handle].watermark = (uint64_t) c.value;
           break;
+        case Cmd::SET_HISTORY:
+          hist.assign((size_t) c.value, sdb_complex{ 0.0f, 0.0f });
+          hist_start = hist_fill = replay_pos = 0; replaying = false; looped = 0;
+          break;
+        case Cmd::REPLAY:
+          replaying = c.enabled != 0 && hist_fill > 0;
+          replay_pos = 0; looped = 0; replay_wrapped = false;
+          break;
         case Cmd::SET_HOP_RANGE:
           if (c.value <= c.value2) { hop_min = c.value; hop_max = c.value2; hop_index = 0; }
           break;
@@ -552,7 +564,25 @@ struct sdb_analyzer {
       if (block % N) block = std::max<size_t>(N, (block / N) * N);     // after a PARAMS change
       if (buf.size() != block) buf.resize(block);
       if (plan_dirty && !rebuild()) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
-      long got = source_read(buf.data(), block);
+      long got;
+      const bool f32_src = src.read || src.input_format == SDB_FORMAT_FLOAT32;
+      if (replaying && hist_fill > 0) {
+        // suscan_analyzer_replay: the source is paused and the history ring is played back, oldest sample first
+        for (size_t i = 0; i < block; ++i) {
+          if (replay_pos == 0 && replay_wrapped) looped = 1;         // playing the ring for the second time
+          buf[i] = hist[(hist_start + replay_pos) % hist.size()];
+          if (++replay_pos >= hist_fill) { replay_pos = 0; replay_wrapped = true; }
+        }
+        got = (long) block;
+      } else {
+        got = source_read(buf.data(), block);
+        if (got == (long) block && f32_src && !hist.empty()) {       // suscan_analyzer_set_history_size: keep the tail
+          for (size_t i = 0; i < block; ++i) {
+            hist[(hist_start + hist_fill) % hist.size()] = buf[i];
+            if (hist_fill < hist.size()) ++hist_fill; else hist_start = (hist_start + 1) % hist.size();
+          }
+        }
+      }
       if (got < 0) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
       if ((size_t) got < block) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_EOS; break; }   // partial tail blocks are dropped
       // baseband filters see (and may rewrite) every float32 block before the analyzer does, in registration order
@@ -586,6 +616,7 @@ struct sdb_analyzer {
             gettimeofday(&m->rt_time, nullptr);
             double ts = (double) (total_samples - block + f * N) / src.samp_rate;
             m->timestamp.tv_sec = (time_t) ts; m->timestamp.tv_usec = (suseconds_t) ((ts - floor(ts)) * 1e6);
+            m->looped = looped; m->history_size = (uint64_t) hist_fill;
             m->psd_size = N;
             m->psd_data = (float *) malloc(N * sizeof(float));
             memcpy(m->psd_data, &psd[f * N], N * sizeof(float));
@@ -795,6 +826,17 @@ extern "C" int sdb_analyzer_set_inspector_watermark_async(sdb_analyzer_t *a, int
                                                           uint32_t req_id)
 {
   Cmd c; c.kind = Cmd::SET_WATERMARK; c.req_id = req_id; c.handle = handle; c.value = (double) watermark;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_set_history_size(sdb_analyzer_t *a, uint64_t samples)
+{
+  if (samples > (1ull << 31)) return -1;
+  Cmd c; c.kind = Cmd::SET_HISTORY; c.value = (double) samples;
+  return push_cmd(a, std::move(c));
+}
+extern "C" int sdb_analyzer_replay(sdb_analyzer_t *a, int enabled)
+{
+  Cmd c; c.kind = Cmd::REPLAY; c.enabled = enabled;
   return push_cmd(a, std::move(c));
 }
 extern "C" int sdb_analyzer_set_hop_range(sdb_analyzer_t *a, double min_freq, double max_freq)

@@ -168,6 +168,59 @@ def test_analyzer_wide_spectrum_sweep(sdb, oracle):
     assert state["t"] in (total_hops * (1000 + N), total_hops * N + (total_hops - 16) * 1000)
 
 
+def test_analyzer_history_and_replay(sdb):
+    """suscan_analyzer_set_history_size / _replay (Suscan/Analyzer.cpp:157-167): the last samples stay in a ring;
+    replay pauses the source and loops over the ring."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 4096, 1.0e6
+    blk = N * 2
+    go = threading.Event()
+    step = threading.Semaphore(0)
+    calls = [0]
+
+    def read(priv, dst, n):                               # block k carries a tone in bin 100 + 50 k
+        go.wait(30)
+        if not step.acquire(timeout=30):
+            return 0
+        k = calls[0]
+        calls[0] += 1
+        x = (0.3 * np.exp(2j * np.pi * (100 + 50 * k) / N * np.arange(n))).astype(np.complex64)
+        C.memmove(dst, x.ctypes.data, 8 * n)
+        return n
+
+    a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, read=read, read_size=blk)
+    assert a.read(5000)[0] == "SOURCE_INFO"
+    assert a.set_history_size(3 * blk)
+    go.set()
+
+    def frames(k, release=True):
+        out = []
+        if release:
+            for _ in range(k):
+                step.release()
+        while len(out) < 2 * k:
+            name, m = a.read(20000)
+            assert name not in ("TIMEOUT", "EOS", "READ_ERROR", "HALT")
+            if name == "PSD":
+                out.append((int(np.argmax(m["psd"])), m["looped"], m["history_size"]))
+        return out
+
+    live = frames(6)                                      # blocks 0..5; the ring is armed from block 1 on
+    assert [p for p, _, _ in live] == [100 + 50 * (i // 2) for i in range(12)]
+    assert live[-1][2] == 3 * blk and all(lp == 0 for _, lp, _ in live)
+    a.replay(True)
+    frames(1)                                             # the block in flight when the request lands
+    n_calls = calls[0]
+    rep = frames(5, release=False)                        # the source is paused: the ring (blocks 4, 5, 6) loops
+    assert calls[0] == n_calls
+    assert [p for p, _, _ in rep] == [100 + 50 * b for b in (4, 4, 5, 5, 6, 6, 4, 4, 5, 5)]
+    assert [lp for _, lp, _ in rep] == [0] * 6 + [1] * 4  # looped is raised when the ring starts over
+    a.halt()
+    for _ in range(4):
+        step.release()
+    a.close()
+
+
 def test_analyzer_seek(sdb):
     """suscan_analyzer_seek on a seekable (in-memory) source; callback sources refuse."""
     from sigdigger_b200.analyzer import Analyzer
