@@ -431,6 +431,10 @@ uint32_t sdb_sview_max_bins(const sdb_sview_t *v);                /* row pitch o
 /* psd_dev: device pointer [n_hops][psd_size], PSDMessage layout (shifted, dB); centers: host doubles */
 int      sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t psd_size, const double *centers,
                            size_t n_hops, int adjust_sides);
+/* PSDMessage post-processing as a separate pass (Suscan/Messages/PSDMessage.cpp:32-38: swap halves,
+ * SU_POWER_DB) for engines that keep the linear PSD for the channel detector: db[f][(k+n/2)%n] =
+ * 10 log10(lin[f][k] + 1e-8), bit-identical to SDB_FLAG_PSD_SHIFT_DB.  Device pointers, out of place. */
+int      sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size_t n_frames, uint32_t psd_size);
 /* device pointers of the last projection: j0[n_hops], nb[n_hops], va/vc[n_hops][max_bins] */
 int      sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc);
 /* copy them into caller-owned device buffers (e.g. the send buffers of the NCCL gather) */

@@ -214,6 +214,7 @@ _PROTOS = {
     "sdb_sview_size": (C.c_uint32, [C.c_void_p]),
     "sdb_sview_max_bins": (C.c_uint32, [C.c_void_p]),
     "sdb_sview_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "sdb_psd_shift_db_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
     "sdb_sview_contrib": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sdb_sview_contrib_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -247,6 +248,11 @@ def last_error():
 
 def device_count():
     return load_library().sdb_device_count()
+
+
+def psd_shift_db(lin_ptr, db_ptr, n_frames, psd_size):
+    """Device pass: linear PSD (DC first) -> PSDMessage layout (halves swapped, dB); out of place."""
+    _check(load_library().sdb_psd_shift_db_device(lin_ptr, db_ptr, n_frames, psd_size))
 
 
 class SdbError(RuntimeError):

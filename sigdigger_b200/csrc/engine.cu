@@ -1403,6 +1403,17 @@ extern "C" int sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t ps
   return 0;
 }
 
+cudaError_t sdb_launch_psd_shift_db(cudaStream_t s, const float *lin, float *db, size_t n_frames, unsigned n);
+
+extern "C" int sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size_t n_frames, uint32_t psd_size)
+{
+  if (!lin_dev || !db_dev) return fail("null argument");
+  if (lin_dev == db_dev) return fail("in-place conversion is not supported (the halves swap)");
+  if (psd_size < 2 || (psd_size & (psd_size - 1))) return fail("psd_size must be a power of two");
+  CK(sdb_launch_psd_shift_db(0, lin_dev, db_dev, n_frames, psd_size));
+  return 0;
+}
+
 extern "C" int sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc)
 {
   if (!v) return fail("null view");

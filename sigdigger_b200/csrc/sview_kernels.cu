@@ -15,6 +15,7 @@
 // Between project and accumulate the (tiny) contribution lists are what crosses NVLink (NCCL gather).
 // Compiled with -fmad=false; double arithmetic for frequencies / positions exactly as in the C++.
 #include "sdb_internal.h"
+#include "sdb_math.h"
 
 struct SviewGeom {
   double freq_min, freq_range, fft_bandwidth;
@@ -179,5 +180,28 @@ cudaError_t sdb_launch_sview_accumulate(cudaStream_t s, unsigned spectrum_size, 
     k_sview_accumulate<<<(spectrum_size + 255) / 256, 256, 0, s>>>(spectrum_size, j0, nb, va, vc, n_hops, max_bins,
                                                                    psd, accum, count);
   k_sview_fill<<<1, 32, 0, s>>>(spectrum_size, psd, count);
+  return cudaGetLastError();
+}
+
+// PSDMessage post-processing as its own pass (Suscan/Messages/PSDMessage.cpp:32-38: fftshift + 10 log10),
+// for engines that keep the linear PSD because the channel detector reads it.  Same expression as the
+// fused epilogue of the PSD kernels (SDB_FLAG_PSD_SHIFT_DB), so the results are bit-identical to it.
+__global__ void k_psd_shift_db(const float *__restrict__ lin, float *__restrict__ db, size_t total, unsigned n)
+{
+  const unsigned half = n >> 1;
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+    const size_t f = i / n;
+    const unsigned k = (unsigned) (i - f * n);
+    db[f * n + ((k + half) & (n - 1))] = 10.0f * d_log10f(__ldg(lin + i) + 1e-8f);
+  }
+}
+
+cudaError_t sdb_launch_psd_shift_db(cudaStream_t s, const float *lin, float *db, size_t n_frames, unsigned n)
+{
+  const size_t total = n_frames * n;
+  if (total == 0) return cudaSuccess;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_psd_shift_db<<<(unsigned) blocks, 256, 0, s>>>(lin, db, total, n);
   return cudaGetLastError();
 }

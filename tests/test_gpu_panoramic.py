@@ -101,6 +101,68 @@ def test_panoramic_sweep_driver_single_rank(sdb, oracle):
     assert np.array_equal(psd.view(np.uint32), ref[0].view(np.uint32))
 
 
+def test_psd_shift_db_pass_equals_fused_epilogue(sdb):
+    """sdb_psd_shift_db_device on a linear-PSD engine == the engine's SDB_FLAG_PSD_SHIFT_DB output, bit for bit"""
+    import torch
+    for N, S, frames in ((65536, 3, 2), (1024, 5, 4)):
+        x = _hops(S, N * frames, 1.0, seed=N % 13)
+        outs = []
+        for flags in (0, sdb.FLAG_PSD_SHIFT_DB):
+            e = sdb.Engine(n_streams=S, psd_size=N, psd_window="hann", max_feed=N * frames, flags=flags)
+            e.commit()
+            e.feed(x)
+            outs.append(e.read_psd())
+            if flags == 0:
+                db = torch.empty((S, frames, N), dtype=torch.float32, device="cuda")
+                sdb.psd_shift_db(e.psd_device_ptr, db.data_ptr(), S * frames, N)
+                torch.cuda.synchronize()
+                got = db.cpu().numpy()
+            e.close()
+        assert np.array_equal(got.view(np.uint32), outs[1].view(np.uint32))
+        assert not np.array_equal(outs[0], outs[1])
+    with pytest.raises(sdb.SdbError):
+        sdb.psd_shift_db(db.data_ptr(), db.data_ptr(), 1, 1024)
+    with pytest.raises(sdb.SdbError):
+        sdb.psd_shift_db(db.data_ptr(), db.data_ptr() + 4096, 1, 1000)
+
+
+def test_panoramic_sweep_with_channel_detector(sdb, oracle):
+    """configs[4] in full: per-hop PSD -> channel detector on the rank that owns the hop + SpectrumView stitch.
+    The stitched spectrum must not change when the detector rides along (linear PSD + separate dB pass), and the
+    channel lists must equal the oracle detector's run on each hop's own PSD, at absolute frequencies."""
+    import torch
+    from sigdigger_b200 import panoramic
+    N, n_hops, frames, fs, rel_bw = 16384, 9, 3, 50e6, 0.5
+    fmin, fmax = 1.0e9, 1.0e9 + n_hops * fs * rel_bw
+    centers = fmin + fs * rel_bw * (0.5 + np.arange(n_hops))
+    x = _hops(n_hops, N * frames, fs, seed=11)
+    xt = torch.from_numpy(x).cuda()
+    det = dict(alpha=0.5, gamma=0.5, snr=10.0, min_bins=2)
+    psd, acc, cnt, chans = panoramic.sweep(sdb, torch, None, xt, centers, N, "hann", (fmin, fmax), fs, rel_bw,
+                                           detect=det)
+    # same stitch as a detector-less sweep over the last frame of every hop
+    last = np.ascontiguousarray(x[:, (frames - 1) * N:])
+    ref = panoramic.sweep(sdb, torch, None, torch.from_numpy(last).cuda(), centers, N, "hann", (fmin, fmax), fs,
+                          rel_bw)
+    for a, b in zip((psd, acc, cnt), ref):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert len(chans) == n_hops
+    found = 0
+    for h in range(n_hops):
+        lin = oracle.psd_frames(x[h], N, "hann")
+        d = oracle.ChannelDetector(N, det["alpha"], det["gamma"], det["snr"], det["min_bins"])
+        want, _ = d.feed(lin)
+        d.close()
+        assert len(chans[h]) == len(want)
+        for c, w in zip(chans[h], want):
+            for a, b in ((c["S0"], w[2]), (c["N0"], w[3]), (c["snr"], w[4])):
+                assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32)
+            assert centers[h] - fs / 2 <= c["f_lo"] <= c["fc"] <= c["f_hi"] <= centers[h] + fs / 2
+            assert c["fc"] == pytest.approx(0.5 * (c["f_lo"] + c["f_hi"]))
+        found += len(want)
+    assert found >= n_hops          # every hop carries three tones well above the noise
+
+
 def test_panoramic_histogram_mode(sdb, oracle):
     """hop narrower than two destination bins -> feedHistogramMode (Scanner.cpp:187-237)"""
     N, n_hops = 4096, 30
