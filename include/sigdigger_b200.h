@@ -249,6 +249,34 @@ int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batc
  * (Tasks/LPFTask.cpp:52-69,83-87,104-107) */
 int sdb_task_lpf(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
 
+/* Decision spaces of the TimeWindow samplers (enum SamplingSpace, include/SamplingProperties.h:27-31) */
+enum { SDB_SPACE_AMPLITUDE = 0, SDB_SPACE_PHASE = 1, SDB_SPACE_FREQUENCY = 2 };
+/* DelayedConjTask: dst[p] = 0 for p < delay, else x[p] conj(x[p-delay]) / (|x[p-delay]| + 1e-3)
+ * (Tasks/DelayedConjTask.cpp:58-100); delay == 0 is an error as in the constructor (:36-37) */
+int  sdb_task_delayed_conj(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, size_t delay);
+/* HistogramFeeder: the decision variable of every sample -- |x|, arg x, or arg(x[p] conj(x[p-1])) for p >= 1
+ * (Tasks/HistogramFeeder.cpp:35-87).  out: [batch][count]; returns count (n, or n - 1 for FREQUENCY) */
+long sdb_task_histogram_feed(const sdb_complex *src, float *out, size_t n, size_t batch, int space);
+/* WaveSampler, sync = MANUAL: box-car average over each of (long) symbol_count symbol periods of
+ * n / symbol_count samples with fractional edge weights; PHASE / FREQUENCY accumulate x conj(prev),
+ * AMPLITUDE the RMS (Tasks/WaveSampler.cpp:28-46, 96-175).  out: [batch][count]; returns count */
+long sdb_task_sample_manual(const sdb_complex *src, size_t n, size_t batch, int space, size_t symbol_sync,
+                            double symbol_count, sdb_complex *out);
+/* WaveSampler, sync = ZERO_CROSSING (Tasks/WaveSampler.cpp:222-292): run lengths between sign changes of
+ * the decision variable, rounded to symbols with bnor = min(rate / fs, 1) symbols per sample; sym:
+ * [batch][cap] bits (var > 0), counts[batch] = symbols produced (may exceed cap; the excess is dropped) */
+int  sdb_task_sample_zero_crossing(const sdb_complex *src, size_t n, size_t batch, int space, int amplitude,
+                                   float threshold_re, float threshold_im, float zc_angle_re, float zc_angle_im,
+                                   float bnor, uint8_t *sym, uint32_t *counts, size_t cap);
+/* CarrierDetector: Blackman-Harris, zero-padded power spectrum, strongest bin outside the DC notch, centroid
+ * over avg_rel_bw of the band (Tasks/CarrierDetector.cpp:49-147).  peak[batch]: rad / sample in (-pi, pi];
+ * n <= 2^20 */
+int  sdb_task_carrier_detect(const sdb_complex *src, size_t n, size_t batch, double avg_rel_bw,
+                             double dc_notch_rel_bw, float *peak);
+/* Decider over sampler output (Default/GenericInspector/InspectorUI.cpp:836-846; Tasks/WaveSampler.cpp:316-317):
+ * mode 0 = argument on [min, max), 1 = modulus; sym[i] in [0, 2^bps) */
+int  sdb_task_decide(const sdb_complex *soft, uint8_t *sym, size_t n, int mode, unsigned bps, float min, float max);
+
 /* ------------------------------------------------------------------------------------------------
  * Capture files: the file source of Default/SourceConfig/FileSourcePage.cpp:68-140
  * (SUSCAN_SOURCE_FORMAT_{AUTO, RAW_*, WAV, SIGMF} + metadata guessed from the file name; SigDigger's own

@@ -400,6 +400,18 @@ unsigned sdo_spectsrc_out_size(int kind, unsigned ns);
 unsigned sdo_spectsrc_frame(int kind, unsigned ns, const sdo_cpx *c, size_t n_ch, float *out);
 int      sdo_estimate_baud(int estimator, unsigned ns, float fs_ch, const sdo_cpx *c, size_t n_ch, float *baud);
 
+/* ------------------------------------------------------------------------------------------------
+ * Offline TimeWindow tasks that are fully specified in-repo (SPEC section Y; tasks.c).
+ * ---------------------------------------------------------------------------------------------- */
+enum sdo_space { SDO_SPACE_AMPLITUDE = 0, SDO_SPACE_PHASE = 1, SDO_SPACE_FREQUENCY = 2 }; /* SamplingProperties.h:27-31 */
+void   sdo_delayed_conj(const sdo_cpx *x, sdo_cpx *y, size_t n, size_t delay);
+size_t sdo_histogram_feed(const sdo_cpx *x, float *out, size_t n, int space);
+size_t sdo_sample_manual(const sdo_cpx *x, size_t n, int space, size_t symbol_sync, double symbol_count,
+                         sdo_cpx *out);
+size_t sdo_sample_zero_crossing(const sdo_cpx *x, size_t n, int space, int amplitude, sdo_cpx threshold,
+                                sdo_cpx zc_angle, float bnor, uint8_t *sym, size_t cap);
+float  sdo_carrier_detect(const sdo_cpx *x, size_t n, double avg_rel_bw, double dc_notch_rel_bw);
+
 /* multi-threaded CPU baseline: S independent streams, each n samples, same params (OpenMP). */
 double sdo_baseline_run(const sdo_an_params *p, const sdo_cpx *x, size_t n_streams, size_t n,
                         int n_threads, uint64_t *checksum);

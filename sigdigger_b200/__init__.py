@@ -178,6 +178,15 @@ _PROTOS = {
     "sdb_task_pll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_agc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_lpf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_task_delayed_conj": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "sdb_task_histogram_feed": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
+    "sdb_task_sample_manual": (C.c_long, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_double,
+                                          C.c_void_p]),
+    "sdb_task_sample_zero_crossing": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_float,
+                                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                                C.c_size_t]),
+    "sdb_task_carrier_detect": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_void_p]),
+    "sdb_task_decide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_float, C.c_float]),
     "sdb_analyzer_new": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "sdb_analyzer_read": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "sdb_analyzer_read_timeout": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint]),
@@ -492,6 +501,71 @@ def agc(x, tau):
 def lpf(x, bw):
     """Tasks/LPFTask.cpp"""
     return _task(load_library().sdb_task_lpf, x, bw)
+
+
+SPACE = {"amplitude": 0, "phase": 1, "frequency": 2}
+
+
+def _batch(x):
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    return (x[None, :], True) if x.ndim == 1 else (x, False)
+
+
+def delayed_conj(x, delay):
+    """Tasks/DelayedConjTask.cpp"""
+    return _task(load_library().sdb_task_delayed_conj, x, delay)
+
+
+def histogram_feed(x, space):
+    """Tasks/HistogramFeeder.cpp -> float32 [batch, n] (n - 1 for "frequency")"""
+    x, one = _batch(x)
+    sp = SPACE[space] if isinstance(space, str) else int(space)
+    out = np.empty((x.shape[0], x.shape[1] - (1 if sp == 2 else 0)), np.float32)
+    _check(load_library().sdb_task_histogram_feed(x.ctypes.data, out.ctypes.data, x.shape[1], x.shape[0], sp))
+    return out[0] if one else out
+
+
+def sample_manual(x, space, symbol_count, symbol_sync=0):
+    """Tasks/WaveSampler.cpp sampleManual -> complex64 [batch, int(symbol_count)]"""
+    x, one = _batch(x)
+    sp = SPACE[space] if isinstance(space, str) else int(space)
+    out = np.empty((x.shape[0], int(symbol_count)), np.complex64)
+    _check(load_library().sdb_task_sample_manual(x.ctypes.data, x.shape[1], x.shape[0], sp, symbol_sync,
+                                                 float(symbol_count), out.ctypes.data))
+    return out[0] if one else out
+
+
+def sample_zero_crossing(x, space, bnor, amplitude=False, threshold=0j, zc_angle=1 + 0j, cap=None):
+    """Tasks/WaveSampler.cpp sampleZeroCrossing -> list of uint8 bit arrays (one per buffer)"""
+    x, one = _batch(x)
+    sp = SPACE[space] if isinstance(space, str) else int(space)
+    cap = cap or x.shape[1]
+    sym = np.empty((x.shape[0], cap), np.uint8)
+    cnt = np.zeros(x.shape[0], np.uint32)
+    t, z = complex(threshold), complex(zc_angle)
+    _check(load_library().sdb_task_sample_zero_crossing(x.ctypes.data, x.shape[1], x.shape[0], sp, int(amplitude),
+                                                        t.real, t.imag, z.real, z.imag, bnor, sym.ctypes.data,
+                                                        cnt.ctypes.data, cap))
+    res = [sym[b, :min(int(cnt[b]), cap)].copy() for b in range(x.shape[0])]
+    return (res[0], int(cnt[0])) if one else (res, cnt)
+
+
+def carrier_detect(x, avg_rel_bw=0.01, dc_notch_rel_bw=0.0):
+    """Tasks/CarrierDetector.cpp -> carrier offset(s) in rad / sample"""
+    x, one = _batch(x)
+    peak = np.empty(x.shape[0], np.float32)
+    _check(load_library().sdb_task_carrier_detect(x.ctypes.data, x.shape[1], x.shape[0], avg_rel_bw, dc_notch_rel_bw,
+                                                  peak.ctypes.data))
+    return float(peak[0]) if one else peak
+
+
+def decide(soft, mode, bps, vmin, vmax):
+    """Decider (SPEC D): mode "argument" / "modulus" -> uint8 symbols"""
+    soft = np.ascontiguousarray(soft, dtype=np.complex64).ravel()
+    sym = np.empty(soft.size, np.uint8)
+    m = {"argument": 0, "modulus": 1}[mode] if isinstance(mode, str) else int(mode)
+    _check(load_library().sdb_task_decide(soft.ctypes.data, sym.ctypes.data, soft.size, m, bps, vmin, vmax))
+    return sym
 
 
 def inspector_run(cls, fs, x, **kw):

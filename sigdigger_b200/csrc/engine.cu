@@ -1219,6 +1219,151 @@ extern "C" int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, 
   return task_io_end(b, dst, n, batch);
 }
 
+// ---- TimeWindow tasks that are fully specified in-repo (SPEC Y; kernels in tasks_kernels.cu)
+struct DevMem {
+  void *p = nullptr;
+  ~DevMem() { cudaFree(p); }
+  template <typename T> T *as() { return (T *) p; }
+};
+
+static int task_src_begin(DevMem &src, const sdb_complex *host, size_t n, size_t batch)
+{
+  if (!host || n == 0 || batch == 0) return fail("invalid task buffer");
+  if (sdb_device_count() <= 0) return fail("no CUDA device: sigdigger_b200 has no CPU fallback");
+  CK(cudaMalloc(&src.p, n * batch * sizeof(float2)));
+  CK(cudaMemcpy(src.p, host, n * batch * sizeof(float2), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int sdb_task_delayed_conj(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, size_t delay)
+{
+  if (delay == 0) return fail("Delay is zero samples");   // DelayedConjTask.cpp:36-37
+  if (!dst) return fail("null argument");
+  TaskBufs b;
+  if (task_io_begin(b, src, n, batch)) return -1;
+  CK(sdb_launch_task_delayed_conj(0, b.src, b.dst, n, batch, delay));
+  return task_io_end(b, dst, n, batch);
+}
+
+extern "C" long sdb_task_histogram_feed(const sdb_complex *src, float *out, size_t n, size_t batch, int space)
+{
+  if (!out) return fail("null argument");
+  if (space < SDB_SPACE_AMPLITUDE || space > SDB_SPACE_FREQUENCY) return fail("unknown decision space");
+  DevMem s, o;
+  if (task_src_begin(s, src, n, batch)) return -1;
+  const size_t count = space == SDB_SPACE_FREQUENCY ? n - 1 : n;
+  if (count == 0) return 0;
+  CK(cudaMalloc(&o.p, count * batch * sizeof(float)));
+  CK(sdb_launch_task_hist(0, s.as<float2>(), o.as<float>(), n, batch, space));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, o.p, count * batch * sizeof(float), cudaMemcpyDeviceToHost));
+  return (long) count;
+}
+
+extern "C" long sdb_task_sample_manual(const sdb_complex *src, size_t n, size_t batch, int space, size_t symbol_sync,
+                                       double symbol_count, sdb_complex *out)
+{
+  if (!out) return fail("null argument");
+  if (space < SDB_SPACE_AMPLITUDE || space > SDB_SPACE_FREQUENCY) return fail("unknown decision space");
+  if (!(symbol_count >= 1.0) || symbol_count > (double) n) return fail("symbol_count must be in [1, n]");
+  DevMem s, o;
+  if (task_src_begin(s, src, n, batch)) return -1;
+  // WaveSampler.cpp:44-45: delta = length / symbolCount; sampOffset = symbolSync / delta
+  const double delta = (double) n / symbol_count;
+  const double samp_offset = (double) symbol_sync / delta;
+  const float delta_inv = 1.f / (float) delta;
+  const long long count = (long long) symbol_count;
+  CK(cudaMalloc(&o.p, (size_t) count * batch * sizeof(float2)));
+  CK(sdb_launch_task_sample_manual(0, s.as<float2>(), n, batch, space, (double) symbol_sync, delta, samp_offset,
+                                   delta_inv, count, o.as<float2>()));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, o.p, (size_t) count * batch * sizeof(float2), cudaMemcpyDeviceToHost));
+  return (long) count;
+}
+
+extern "C" int sdb_task_sample_zero_crossing(const sdb_complex *src, size_t n, size_t batch, int space, int amplitude,
+                                             float threshold_re, float threshold_im, float zc_angle_re,
+                                             float zc_angle_im, float bnor, uint8_t *sym, uint32_t *counts, size_t cap)
+{
+  if (!sym || !counts || cap == 0) return fail("null argument");
+  if (space < SDB_SPACE_AMPLITUDE || space > SDB_SPACE_FREQUENCY) return fail("unknown decision space");
+  if (!(bnor > 0.0f)) return fail("bnor must be positive");
+  if (bnor > 1.0f) bnor = 1.0f;                            // WaveSampler.cpp:50-51
+  DevMem s, ev, o, c;
+  if (task_src_begin(s, src, n, batch)) return -1;
+  const size_t pitch = (n + 15) & ~(size_t) 15;
+  CK(cudaMalloc(&ev.p, pitch * batch));
+  CK(cudaMalloc(&o.p, cap * batch));
+  CK(cudaMalloc(&c.p, batch * sizeof(unsigned)));
+  CK(cudaMemset(o.p, 0, cap * batch));
+  // WaveSampler.cpp:236-241
+  const float thres = amplitude ? threshold_re * threshold_re + threshold_im * threshold_im
+                                : threshold_re * zc_angle_re - threshold_im * zc_angle_im;
+  CK(sdb_launch_task_zero_crossing(0, s.as<float2>(), n, batch, space, amplitude ? 1 : 0, thres,
+                                   make_float2(zc_angle_re, zc_angle_im), bnor, ev.as<unsigned char>(), pitch,
+                                   o.as<unsigned char>(), c.as<unsigned>(), cap));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(sym, o.p, cap * batch, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts, c.p, batch * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int sdb_task_carrier_detect(const sdb_complex *src, size_t n, size_t batch, double avg_rel_bw,
+                                       double dc_notch_rel_bw, float *peak)
+{
+  if (!peak) return fail("null argument");
+  if (n > ((size_t) 1 << 20)) return fail("carrier detector: at most 2^20 samples");
+  if (!(avg_rel_bw >= 0.0 && avg_rel_bw <= 1.0)) return fail("avg_rel_bw must be in [0, 1]");
+  if (!(dc_notch_rel_bw >= 0.0)) dc_notch_rel_bw = 0.0;   // qBound(0., x, 1.), CarrierDetector.cpp:35
+  if (dc_notch_rel_bw > 1.0) dc_notch_rel_bw = 1.0;
+  DevMem s, w, buf, pk;
+  if (task_src_begin(s, src, n, batch)) return -1;
+  size_t alloc = 64;                                        // SPEC Y.5: transform size >= 64
+  while (alloc < n) alloc <<= 1;
+  std::vector<float> win;
+  sdbh::window_fill(win, (unsigned) n, SDB_WINDOW_BLACKMANN_HARRIS);
+  CK(cudaMalloc(&w.p, n * sizeof(float)));
+  CK(cudaMemcpy(w.p, win.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&buf.p, alloc * batch * sizeof(float2)));
+  CK(cudaMalloc(&pk.p, batch * sizeof(float)));
+  CK(sdb_launch_task_carrier_prep(0, s.as<float2>(), w.as<float>(), n, alloc, batch, buf.as<float2>()));
+  CK(cudaDeviceSynchronize());
+  // the transform is the engine's own PSD (rectangular window: the taps are already applied)
+  sdb_engine_params prm; memset(&prm, 0, sizeof(prm));
+  prm.n_streams = (uint32_t) batch; prm.psd_size = (uint32_t) alloc; prm.psd_window = SDB_WINDOW_NONE;
+  prm.max_feed = (uint32_t) alloc;
+  sdb_engine_t *e = sdb_engine_new(&prm, 1.0);
+  if (!e) return -1;
+  int rc = sdb_engine_commit(e);
+  if (!rc) rc = sdb_engine_feed_device(e, (const sdb_complex *) buf.p, alloc, alloc);
+  if (!rc) rc = sdb_engine_sync(e);
+  if (!rc) {
+    const int bins = (int) ((double) alloc * avg_rel_bw) + 1;
+    const int skip = (int) (.5 * dc_notch_rel_bw * (double) alloc);
+    cudaError_t ce = sdb_launch_task_carrier_find(0, sdb_engine_psd_device(e), alloc, batch, bins, (bins - 1) / 2, skip,
+                                                  pk.as<float>());
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    if (ce == cudaSuccess) ce = cudaMemcpy(peak, pk.p, batch * sizeof(float), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) { g_err = std::string("carrier detector: ") + cudaGetErrorString(ce); rc = -1; }
+  }
+  sdb_engine_destroy(e);
+  return rc;
+}
+
+extern "C" int sdb_task_decide(const sdb_complex *soft, uint8_t *sym, size_t n, int mode, unsigned bps, float min,
+                               float max)
+{
+  if (!sym) return fail("null argument");
+  if (mode < 0 || mode > 1 || bps < 1 || bps > 8 || !(max > min)) return fail("invalid decider");
+  DevMem s, o;
+  if (task_src_begin(s, soft, n, 1)) return -1;
+  CK(cudaMalloc(&o.p, n));
+  CK(sdb_launch_task_decide(0, s.as<float2>(), o.as<unsigned char>(), n, mode, min, max - min, 1 << bps));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(sym, o.p, n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // Offline inspector over `batch` captured channel-rate buffers (what the GUI's TimeWindow / SamplerDialog
 // do block-wise on the CPU, Components/TimeWindow.cpp:1571-2183): one GPU chain per buffer.
 extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_complex *src, size_t n,

@@ -219,3 +219,19 @@ cudaError_t sdb_launch_task_xlate(cudaStream_t s, const float2 *src, float2 *dst
 cudaError_t sdb_launch_task_quad(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch);
 cudaError_t sdb_launch_task_chain(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
                                   const SdbChainCfg *cfg_dev, int mode, float *pool, size_t pool_stride);
+// tasks_kernels.cu (SPEC Y)
+cudaError_t sdb_launch_task_delayed_conj(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
+                                         size_t delay);
+cudaError_t sdb_launch_task_hist(cudaStream_t s, const float2 *src, float *out, size_t n, size_t batch, int space);
+cudaError_t sdb_launch_task_sample_manual(cudaStream_t s, const float2 *src, size_t n, size_t batch, int space,
+                                          double sync, double delta, double samp_offset, float delta_inv,
+                                          long long count, float2 *out);
+cudaError_t sdb_launch_task_zero_crossing(cudaStream_t s, const float2 *src, size_t n, size_t batch, int space,
+                                          int amplitude, float thres, float2 zca, float bnor, unsigned char *ev,
+                                          size_t ev_pitch, unsigned char *sym, unsigned *counts, size_t cap);
+cudaError_t sdb_launch_task_carrier_prep(cudaStream_t s, const float2 *src, const float *w, size_t n, size_t alloc,
+                                         size_t batch, float2 *dst);
+cudaError_t sdb_launch_task_carrier_find(cudaStream_t s, const float *psd, size_t alloc, size_t batch, int bins,
+                                         int delta, int skip, float *peak);
+cudaError_t sdb_launch_task_decide(cudaStream_t s, const float2 *x, unsigned char *sym, size_t n, int mode, float dmin,
+                                   float dh, int intervals);

@@ -1,0 +1,294 @@
+// tasks_kernels.cu -- the GUI's offline TimeWindow tasks whose arithmetic is fully present in the reference
+// (SPEC.md section Y), over a batch of captured buffers:
+//   delayed conjugate product    Tasks/DelayedConjTask.cpp:58-100
+//   histogram feeder             Tasks/HistogramFeeder.cpp:35-87
+//   manual (box-car) sampler     Tasks/WaveSampler.cpp:28-46, 96-175
+//   zero-crossing sampler        Tasks/WaveSampler.cpp:222-292
+//   carrier detector             Tasks/CarrierDetector.cpp:49-147
+//   decider                      Default/GenericInspector/InspectorUI.cpp:836-846 (SPEC D)
+// The reference runs them as sequential loops on one buffer.  Here every loop iteration that carries no state
+// is one thread; where the reference carries state (the sampler's `prev`, the zero-crossing run lengths)
+// the state a thread needs is recomputed from the inputs or passed through a one-byte-per-sample event map.
+// Compiled with -fmad=false: float and double expressions round exactly as written.
+#include "sdb_internal.h"
+#include "sdb_math.h"
+
+#define TASK_BLOCK 4096  // SIGDIGGER_WAVESAMPLER_FEEDER_BLOCK_LENGTH (include/WaveSampler.h:28)
+
+__global__ void k_task_delayed_conj(const float2 *__restrict__ src, float2 *__restrict__ dst, size_t n, size_t batch,
+                                    size_t delay)
+{
+  const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (i >= n * batch) return;
+  const size_t p = i % n;
+  if (p < delay) { dst[i] = make_float2(0.0f, 0.0f); return; }
+  const float2 x = src[i], prev = src[i - delay];
+  const float kinv = (float) (1.0 / ((double) d_cabsf(prev.x, prev.y) + 1e-3));
+  const float tr = kinv * x.x, ti = kinv * x.y;
+  dst[i] = make_float2(tr * prev.x + ti * prev.y, ti * prev.x - tr * prev.y);
+}
+
+// space: 0 amplitude, 1 phase, 2 frequency (n - 1 values per buffer)
+__global__ void k_task_hist(const float2 *__restrict__ src, float *__restrict__ out, size_t n, size_t batch, int space)
+{
+  const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (i >= n * batch) return;
+  const float2 x = src[i];
+  if (space == 0) { out[i] = d_cabsf(x.x, x.y); return; }
+  if (space == 1) { out[i] = d_atan2f(x.y, x.x); return; }
+  const size_t b = i / n, p = i - b * n;
+  if (p == 0) return;
+  const float2 pv = src[i - 1];
+  out[b * (n - 1) + p - 1] = d_atan2f(x.y * pv.x - x.x * pv.y, x.x * pv.x + x.y * pv.y);
+}
+
+struct SymGeom { long long i0, i1; float t0, t1; };
+
+static __device__ __forceinline__ SymGeom sym_geom(long long p, double samp_offset, double delta, double sync)
+{
+  SymGeom g;
+  const double start = ((double) p - samp_offset) * delta + sync;
+  const double end = start + delta;
+  g.i0 = (long long) floor(start);
+  g.i1 = (long long) ceil(end);
+  g.t0 = (float) (1 - (start - (double) g.i0));
+  g.t1 = (float) (1 - ((double) g.i1 - end));
+  return g;
+}
+
+static __device__ __forceinline__ float2 sym_tap(const float2 *__restrict__ x, long long n, const SymGeom &g,
+                                                 long long i)
+{
+  if (i < 0 || i >= n) return make_float2(0.0f, 0.0f);
+  const float2 v = x[i];
+  if (i == g.i0) return make_float2(g.t0 * v.x, g.t0 * v.y);
+  if (i == g.i1) return make_float2(g.t1 * v.x, g.t1 * v.y);
+  return v;
+}
+
+// one thread per (buffer, symbol); `prev` at the start of a symbol is the last tap of the previous one
+__global__ void k_task_sample_manual(const float2 *__restrict__ src, size_t n, size_t batch, int space, double sync,
+                                     double delta, double samp_offset, float delta_inv, long long count,
+                                     float2 *__restrict__ out)
+{
+  const size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (t >= (size_t) count * batch) return;
+  const size_t b = t / (size_t) count;
+  const long long p = (long long) (t - b * (size_t) count);
+  const float2 *__restrict__ x = src + b * n;
+  float2 prev = make_float2(0.0f, 0.0f);
+  if (p > 0) {
+    const SymGeom q = sym_geom(p - 1, samp_offset, delta, sync);
+    if (q.i1 >= q.i0) prev = sym_tap(x, (long long) n, q, q.i1);
+  }
+  const SymGeom g = sym_geom(p, samp_offset, delta, sync);
+  float ar = 0.0f, ai = 0.0f;
+  for (long long i = g.i0; i <= g.i1; ++i) {
+    const float2 v = sym_tap(x, (long long) n, g, i);
+    if (space == 0) {
+      ar += v.x * v.x + v.y * v.y;
+      ai += v.y * v.x - v.x * v.y;
+    } else {
+      ar += v.x * prev.x + v.y * prev.y;
+      ai += v.y * prev.x - v.x * prev.y;
+    }
+    prev = v;
+  }
+  out[t] = space == 0 ? make_float2(sqrtf(delta_inv * ar), 0.0f) : make_float2(delta_inv * ar, delta_inv * ai);
+}
+
+// Zero-crossing sampler, pass 1: one thread per (buffer, 4096-sample work() block).  Every block starts from
+// prevVar = -1 and prev = 0 (the reference never stores them back), so blocks are independent here; what
+// couples them (lastZc, the per-block cap) is handled by pass 2.  ev[p]: 0 none, 1 crossing with var <= 0,
+// 2 crossing with var > 0.
+__global__ void k_task_zc_events(const float2 *__restrict__ src, size_t n, size_t batch, size_t blocks, int space,
+                                 int amplitude, float thres, float2 zca, unsigned char *__restrict__ ev,
+                                 size_t ev_pitch)
+{
+  const size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (t >= blocks * batch) return;
+  const size_t b = t / blocks, k = t - b * blocks;
+  const float2 *__restrict__ x = src + b * n;
+  unsigned char *__restrict__ e = ev + b * ev_pitch;
+  const size_t p0 = k * TASK_BLOCK;
+  const size_t p1 = p0 + TASK_BLOCK < n ? p0 + TASK_BLOCK : n;
+  const bool last = p1 >= n;
+  float2 prev = make_float2(0.0f, 0.0f);
+  float var = 0.0f, prev_var = -1.0f;
+  for (size_t p = p0; p < p1; ++p) {
+    const float2 d = x[p];
+    if (space == 0) {
+      var = amplitude ? d.x * d.x + d.y * d.y : d.x * zca.x - d.y * zca.y;
+      var -= thres;
+    } else if (space == 1) {
+      var = d_atan2f(d.x * zca.y + d.y * zca.x, d.x * zca.x - d.y * zca.y);
+    } else {
+      const float ir = -d.y, ii = d.x;
+      var = d_atan2f(ii * prev.x - ir * prev.y, ir * prev.x + ii * prev.y);
+      prev = d;
+    }
+    unsigned char c = 0;
+    if (((var > 0 || var < 0) || last) && (var * prev_var < 0 || last)) {
+      c = var > 0 ? 2 : 1;
+      prev_var = var;
+    }
+    e[p] = c;
+  }
+}
+
+// pass 2: one thread per buffer walks the event map (8 samples per load when nothing happened)
+__global__ void k_task_zc_emit(const unsigned char *__restrict__ ev, size_t ev_pitch, size_t n, size_t batch,
+                               float bnor, unsigned char *__restrict__ sym, unsigned *__restrict__ counts, size_t cap)
+{
+  const size_t b = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const unsigned char *__restrict__ e = ev + b * ev_pitch;
+  unsigned char *__restrict__ o = sym + b * cap;
+  size_t total = 0;
+  long long last_zc = 0;
+  for (size_t p0 = 0; p0 < n; p0 += TASK_BLOCK) {
+    const size_t p1 = p0 + TASK_BLOCK < n ? p0 + TASK_BLOCK : n;
+    long long i = 0;
+    size_t p = p0;
+    while (p < p1) {
+      if ((p & 7) == 0 && p + 8 <= p1 && *reinterpret_cast<const unsigned long long *>(e + p) == 0ull) { p += 8; continue; }
+      const unsigned char c = e[p];
+      if (c) {
+        const long long samples = (long long) p - last_zc;
+        long long symbols = (long long) round((double) ((float) samples * bnor));
+        while (symbols-- > 0 && i < TASK_BLOCK) {
+          if (total < cap) o[total] = c == 2;
+          ++total; ++i;
+        }
+        last_zc = (long long) p;
+      }
+      ++p;
+    }
+  }
+  counts[b] = (unsigned) total;
+}
+
+// carrier detector, step 1: window (length n) and zero-pad to the transform size
+__global__ void k_task_carrier_prep(const float2 *__restrict__ src, const float *__restrict__ w, size_t n, size_t alloc,
+                                    size_t batch, float2 *__restrict__ dst)
+{
+  const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (i >= alloc * batch) return;
+  const size_t b = i / alloc, k = i - b * alloc;
+  float2 v = make_float2(0.0f, 0.0f);
+  if (k < n) { const float2 x = src[b * n + k]; const float wk = w[k]; v = make_float2(x.x * wk, x.y * wk); }
+  dst[i] = v;
+}
+
+// step 3 (step 2 is the engine's PSD): strongest bin outside the notch (first one on ties), then the
+// power-weighted circular centroid around it, accumulated in bin order by one thread
+__global__ void __launch_bounds__(256) k_task_carrier_find(const float *__restrict__ psd, int alloc, int bins, int delta,
+                                                           int skip, float *__restrict__ peak)
+{
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const float *__restrict__ P = psd + (size_t) blockIdx.x * alloc;
+  float bv = 0.0f; int bi = 0;
+  for (int i = skip + threadIdx.x; i < alloc - skip; i += 256) {
+    const float v = P[i];
+    if (v > bv) { bv = v; bi = i; }
+  }
+  sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float ov = sv[threadIdx.x + s]; const int oi = si[threadIdx.x + s];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && ov > 0.0f && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = ov; si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const int start = si[0] - delta;
+  float ar = 0.0f, ai = 0.0f;
+  for (int i = 0; i < bins; ++i) {
+    int j = i + start;
+    if (j < 0) j += alloc;
+    j %= alloc;
+    const float nfreq = 2.f * (float) j / (float) alloc;
+    float s, c;
+    d_sincosf(3.14159265358979323846f * nfreq, &s, &c);
+    const float pw = P[j];
+    ar += pw * c;
+    ai += pw * s;
+  }
+  peak[blockIdx.x] = d_atan2f(ai, ar);
+}
+
+// SPEC D decider over a flat array: mode 0 argument, 1 modulus
+__global__ void k_task_decide(const float2 *__restrict__ x, unsigned char *__restrict__ sym, size_t n, int mode,
+                              float dmin, float dh, int intervals)
+{
+  const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 v2 = x[i];
+  const float v = mode == 0 ? d_atan2f(v2.y, v2.x) : d_cabsf(v2.x, v2.y);
+  const float s = floorf((v - dmin) / dh * (float) intervals);
+  int k = (int) s;
+  if (!(s >= 0.0f)) k = 0;
+  if (k > intervals - 1) k = intervals - 1;
+  sym[i] = (unsigned char) k;
+}
+
+static inline unsigned grid_for(size_t total, unsigned threads) { return (unsigned) ((total + threads - 1) / threads); }
+
+cudaError_t sdb_launch_task_delayed_conj(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
+                                         size_t delay)
+{
+  k_task_delayed_conj<<<grid_for(n * batch, 256), 256, 0, s>>>(src, dst, n, batch, delay);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_task_hist(cudaStream_t s, const float2 *src, float *out, size_t n, size_t batch, int space)
+{
+  k_task_hist<<<grid_for(n * batch, 256), 256, 0, s>>>(src, out, n, batch, space);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_task_sample_manual(cudaStream_t s, const float2 *src, size_t n, size_t batch, int space,
+                                          double sync, double delta, double samp_offset, float delta_inv,
+                                          long long count, float2 *out)
+{
+  if (count <= 0) return cudaSuccess;
+  k_task_sample_manual<<<grid_for((size_t) count * batch, 128), 128, 0, s>>>(src, n, batch, space, sync, delta,
+                                                                            samp_offset, delta_inv, count, out);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_task_zero_crossing(cudaStream_t s, const float2 *src, size_t n, size_t batch, int space,
+                                          int amplitude, float thres, float2 zca, float bnor, unsigned char *ev,
+                                          size_t ev_pitch, unsigned char *sym, unsigned *counts, size_t cap)
+{
+  const size_t blocks = (n + TASK_BLOCK - 1) / TASK_BLOCK;
+  k_task_zc_events<<<grid_for(blocks * batch, 64), 64, 0, s>>>(src, n, batch, blocks, space, amplitude, thres, zca,
+                                                               ev, ev_pitch);
+  k_task_zc_emit<<<grid_for(batch, 32), 32, 0, s>>>(ev, ev_pitch, n, batch, bnor, sym, counts, cap);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_task_carrier_prep(cudaStream_t s, const float2 *src, const float *w, size_t n, size_t alloc,
+                                         size_t batch, float2 *dst)
+{
+  k_task_carrier_prep<<<grid_for(alloc * batch, 256), 256, 0, s>>>(src, w, n, alloc, batch, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_task_carrier_find(cudaStream_t s, const float *psd, size_t alloc, size_t batch, int bins,
+                                         int delta, int skip, float *peak)
+{
+  k_task_carrier_find<<<(unsigned) batch, 256, 0, s>>>(psd, (int) alloc, bins, delta, skip, peak);
+  return cudaGetLastError();
+}
+
+cudaError_t sdb_launch_task_decide(cudaStream_t s, const float2 *x, unsigned char *sym, size_t n, int mode, float dmin,
+                                   float dh, int intervals)
+{
+  k_task_decide<<<grid_for(n, 256), 256, 0, s>>>(x, sym, n, mode, dmin, dh, intervals);
+  return cudaGetLastError();
+}

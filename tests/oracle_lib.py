@@ -495,3 +495,71 @@ class ChannelDetector:
 
     def close(self):
         self.L.sdo_chdet_free(C.byref(self.d))
+
+
+# ----------------------------------------------------------------------------------------------
+# Y: offline TimeWindow tasks (oracle/tasks.c)
+# ----------------------------------------------------------------------------------------------
+SPACE = {"amplitude": 0, "phase": 1, "frequency": 2}
+
+
+def delayed_conj(x, delay):
+    x = _c64(x)
+    y = np.empty_like(x)
+    L = lib()
+    L.sdo_delayed_conj.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.sdo_delayed_conj.restype = None
+    L.sdo_delayed_conj(ptr(x), ptr(y), len(x), delay)
+    return y
+
+
+def histogram_feed(x, space):
+    x = _c64(x)
+    out = np.empty(len(x), np.float32)
+    L = lib()
+    L.sdo_histogram_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.sdo_histogram_feed.restype = C.c_size_t
+    k = L.sdo_histogram_feed(ptr(x), ptr(out), len(x), SPACE[space])
+    return out[:k].copy()
+
+
+def sample_manual(x, space, symbol_count, symbol_sync=0):
+    x = _c64(x)
+    out = np.empty(int(symbol_count), np.complex64)
+    L = lib()
+    L.sdo_sample_manual.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_double, C.c_void_p]
+    L.sdo_sample_manual.restype = C.c_size_t
+    k = L.sdo_sample_manual(ptr(x), len(x), SPACE[space], symbol_sync, float(symbol_count), ptr(out))
+    return out[:k].copy()
+
+
+def sample_zero_crossing(x, space, bnor, amplitude=False, threshold=0j, zc_angle=1 + 0j, cap=None):
+    x = _c64(x)
+    cap = cap or len(x)
+    sym = np.empty(cap, np.uint8)
+    L = lib()
+    L.sdo_sample_zero_crossing.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, Cpx, Cpx, C.c_float,
+                                           C.c_void_p, C.c_size_t]
+    L.sdo_sample_zero_crossing.restype = C.c_size_t
+    t, z = complex(threshold), complex(zc_angle)
+    k = L.sdo_sample_zero_crossing(ptr(x), len(x), SPACE[space], int(amplitude), Cpx(t.real, t.imag),
+                                   Cpx(z.real, z.imag), min(float(bnor), 1.0), ptr(sym), cap)
+    return sym[:min(k, cap)].copy(), k
+
+
+def carrier_detect(x, avg_rel_bw=0.01, dc_notch_rel_bw=0.0):
+    x = _c64(x)
+    L = lib()
+    L.sdo_carrier_detect.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double]
+    L.sdo_carrier_detect.restype = C.c_float
+    return float(L.sdo_carrier_detect(ptr(x), len(x), avg_rel_bw, dc_notch_rel_bw))
+
+
+def decide(soft, mode, bps, vmin, vmax):
+    soft = _c64(soft)
+    d = Decider()
+    L = lib()
+    L.sdo_decider_init(C.byref(d), {"argument": 0, "modulus": 1}[mode], bps, C.c_float(vmin), C.c_float(vmax))
+    sym = np.empty(len(soft), np.uint8)
+    L.sdo_decider_decide(C.byref(d), ptr(soft), ptr(sym), len(soft))
+    return sym
