@@ -463,6 +463,18 @@ int      sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t psd_size
  * SU_POWER_DB) for engines that keep the linear PSD for the channel detector: db[f][(k+n/2)%n] =
  * 10 log10(lin[f][k] + 1e-8), bit-identical to SDB_FLAG_PSD_SHIFT_DB.  Device pointers, out of place. */
 int      sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size_t n_frames, uint32_t psd_size);
+/* Spectrum averager the GUI runs on every PSD message (Misc/Averager.cpp:25-60; fed at
+ * UIMediator/SpectrumMediator.cpp:128): per bin last += alpha (x - last), first frame (and alpha >= 1) copied.
+ * One state row of psd_size bins per stream, on the device; frames of a feed are applied in order.
+ * psd_dev: [n_streams] rows of `frames` frames, `stream_stride` floats apart (e.g. sdb_engine_psd_device) */
+typedef struct sdb_averager sdb_averager_t;
+sdb_averager_t *sdb_averager_new(uint32_t psd_size, uint32_t n_streams, float alpha, int device);
+void         sdb_averager_destroy(sdb_averager_t *a);
+int          sdb_averager_set_alpha(sdb_averager_t *a, float alpha);      /* Averager::setAlpha */
+int          sdb_averager_reset(sdb_averager_t *a);                       /* Averager::reset: next frame is copied */
+int          sdb_averager_feed_device(sdb_averager_t *a, const float *psd_dev, size_t frames, size_t stream_stride);
+const float *sdb_averager_device(const sdb_averager_t *a);                /* [n_streams][psd_size] */
+int          sdb_averager_read(sdb_averager_t *a, float *dst, size_t cap);
 /* device pointers of the last projection: j0[n_hops], nb[n_hops], va/vc[n_hops][max_bins] */
 int      sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc);
 /* copy them into caller-owned device buffers (e.g. the send buffers of the NCCL gather) */

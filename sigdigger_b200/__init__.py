@@ -224,6 +224,13 @@ _PROTOS = {
     "sdb_sview_max_bins": (C.c_uint32, [C.c_void_p]),
     "sdb_sview_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "sdb_psd_shift_db_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
+    "sdb_averager_new": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_float, C.c_int]),
+    "sdb_averager_destroy": (None, [C.c_void_p]),
+    "sdb_averager_set_alpha": (C.c_int, [C.c_void_p, C.c_float]),
+    "sdb_averager_reset": (C.c_int, [C.c_void_p]),
+    "sdb_averager_feed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "sdb_averager_device": (C.c_void_p, [C.c_void_p]),
+    "sdb_averager_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_sview_contrib": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sdb_sview_contrib_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -588,6 +595,50 @@ def inspector_run(cls, fs, x, **kw):
     _check(L.sdb_task_inspector(C.byref(cfg), x.ctypes.data, n, batch, soft.ctypes.data, hard.ctypes.data,
                                 counts.ctypes.data, cap))
     return [(soft[b, :counts[b]].copy(), hard[b, :counts[b]].copy()) for b in range(batch)]
+
+
+class Averager:
+    """Spectrum averager (Misc/Averager.cpp) over device PSD frames, one state row per stream."""
+
+    def __init__(self, psd_size, n_streams=1, alpha=1.0, device=0):
+        self._L = load_library()
+        self.psd_size, self.n_streams = psd_size, n_streams
+        self._h = self._L.sdb_averager_new(psd_size, n_streams, alpha, device)
+        if not self._h:
+            raise SdbError(last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_averager_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_alpha(self, alpha):
+        _check(self._L.sdb_averager_set_alpha(self._h, alpha))
+
+    def reset(self):
+        _check(self._L.sdb_averager_reset(self._h))
+
+    def feed_ptr(self, psd_ptr, frames, stream_stride=None):
+        _check(self._L.sdb_averager_feed_device(self._h, psd_ptr, frames,
+                                                frames * self.psd_size if stream_stride is None else stream_stride))
+
+    def feed(self, psd):
+        """psd: CUDA float32 tensor [n_streams, frames, psd_size]"""
+        assert psd.is_cuda and psd.dim() == 3 and psd.shape[0] == self.n_streams and psd.shape[2] == self.psd_size
+        psd = psd.contiguous()
+        self._keep = psd
+        self.feed_ptr(psd.data_ptr(), psd.shape[1])
+
+    @property
+    def device_ptr(self):
+        return self._L.sdb_averager_device(self._h)
+
+    def read(self):
+        out = np.empty((self.n_streams, self.psd_size), np.float32)
+        _check(self._L.sdb_averager_read(self._h, out.ctypes.data, out.size))
+        return out
 
 
 class SpectrumView:

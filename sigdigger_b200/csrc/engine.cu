@@ -1559,6 +1559,75 @@ extern "C" int sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size
   return 0;
 }
 
+// ---- spectrum averager (Misc/Averager.cpp:25-60)
+cudaError_t sdb_launch_psd_average(cudaStream_t s, const float *psd, size_t stream_stride, unsigned frames, unsigned n,
+                                   size_t n_streams, float alpha, int primed, float *last);
+struct sdb_averager {
+  int device = 0; unsigned n = 0; size_t n_streams = 0; float alpha = 1.0f; bool primed = false;
+  float *d_last = nullptr;
+};
+
+extern "C" sdb_averager_t *sdb_averager_new(uint32_t psd_size, uint32_t n_streams, float alpha, int device)
+{
+  if (sdb_device_count() <= 0) { g_err = "no CUDA device: sigdigger_b200 has no CPU fallback"; return nullptr; }
+  if (psd_size == 0 || n_streams == 0) { g_err = "averager: empty geometry"; return nullptr; }
+  CKP(cudaSetDevice(device));
+  sdb_averager *a = new sdb_averager();
+  a->device = device; a->n = psd_size; a->n_streams = n_streams; a->alpha = alpha;
+  if (cudaMalloc(&a->d_last, (size_t) psd_size * n_streams * sizeof(float)) != cudaSuccess) {
+    g_err = "out of device memory"; delete a; return nullptr;
+  }
+  cudaMemset(a->d_last, 0, (size_t) psd_size * n_streams * sizeof(float));
+  return a;
+}
+
+extern "C" void sdb_averager_destroy(sdb_averager_t *a)
+{
+  if (!a) return;
+  cudaSetDevice(a->device);
+  cudaFree(a->d_last);
+  delete a;
+}
+
+extern "C" int sdb_averager_set_alpha(sdb_averager_t *a, float alpha)
+{
+  if (!a) return fail("null averager");
+  a->alpha = alpha;
+  return 0;
+}
+
+extern "C" int sdb_averager_reset(sdb_averager_t *a)
+{
+  if (!a) return fail("null averager");
+  a->primed = false;
+  return 0;
+}
+
+extern "C" int sdb_averager_feed_device(sdb_averager_t *a, const float *psd_dev, size_t frames, size_t stream_stride)
+{
+  if (!a || !psd_dev) return fail("null argument");
+  if (frames == 0) return 0;
+  if (stream_stride < frames * a->n && a->n_streams > 1) return fail("stream stride smaller than the frames");
+  CK(cudaSetDevice(a->device));
+  CK(sdb_launch_psd_average(0, psd_dev, stream_stride, (unsigned) frames, a->n, a->n_streams, a->alpha,
+                            a->primed ? 1 : 0, a->d_last));
+  a->primed = true;
+  return 0;
+}
+
+extern "C" const float *sdb_averager_device(const sdb_averager_t *a) { return a ? a->d_last : nullptr; }
+
+extern "C" int sdb_averager_read(sdb_averager_t *a, float *dst, size_t cap)
+{
+  if (!a || !dst) return fail("null argument");
+  const size_t tot = (size_t) a->n * a->n_streams;
+  if (cap < tot) return fail("destination too small");
+  CK(cudaSetDevice(a->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, a->d_last, tot * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int sdb_sview_contrib(sdb_sview_t *v, int32_t **j0, int32_t **nb, float **va, float **vc)
 {
   if (!v) return fail("null view");

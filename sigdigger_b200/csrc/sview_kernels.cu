@@ -196,6 +196,36 @@ __global__ void k_psd_shift_db(const float *__restrict__ lin, float *__restrict_
   }
 }
 
+// Spectrum averager of the GUI (Misc/Averager.cpp:25-50, fed per PSD message at UIMediator/SpectrumMediator.cpp:128):
+// last += alpha * (x - last) per bin, frame after frame; the first frame (or alpha >= 1) is copied.
+// One thread per (stream, bin); the frames of a feed are applied in order.
+__global__ void k_psd_average(const float *__restrict__ psd, size_t stream_stride, unsigned frames, unsigned n,
+                              size_t n_streams, float alpha, int primed, float *__restrict__ last)
+{
+  const size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (t >= n_streams * n) return;
+  const size_t s = t / n;
+  const unsigned k = (unsigned) (t - s * n);
+  const float *__restrict__ x = psd + s * stream_stride + k;
+  float v = last[t];
+  for (unsigned f = 0; f < frames; ++f) {
+    const float xv = __ldg(x + (size_t) f * n);
+    if (!primed || alpha >= 1.0f) v = xv;
+    else v += alpha * (xv - v);
+    primed = 1;
+  }
+  last[t] = v;
+}
+
+cudaError_t sdb_launch_psd_average(cudaStream_t s, const float *psd, size_t stream_stride, unsigned frames, unsigned n,
+                                   size_t n_streams, float alpha, int primed, float *last)
+{
+  if (frames == 0 || n_streams * n == 0) return cudaSuccess;
+  k_psd_average<<<(unsigned) ((n_streams * n + 255) / 256), 256, 0, s>>>(psd, stream_stride, frames, n, n_streams,
+                                                                        alpha, primed, last);
+  return cudaGetLastError();
+}
+
 cudaError_t sdb_launch_psd_shift_db(cudaStream_t s, const float *lin, float *db, size_t n_frames, unsigned n)
 {
   const size_t total = n_frames * n;

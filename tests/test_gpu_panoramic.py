@@ -126,6 +126,42 @@ def test_psd_shift_db_pass_equals_fused_epilogue(sdb):
         sdb.psd_shift_db(db.data_ptr(), db.data_ptr() + 4096, 1, 1000)
 
 
+def test_spectrum_averager_bit_exact(sdb, oracle):
+    """Misc/Averager.cpp on the device: engine PSD (PSDMessage layout) -> per-stream EMA, frame after frame"""
+    N, S, frames, feeds = 4096, 3, 5, 3
+    x = _hops(S, N * frames * feeds, 1.0, seed=21)
+    e = sdb.Engine(n_streams=S, psd_size=N, psd_window="blackmann_harris", max_feed=N * frames,
+                   flags=sdb.FLAG_PSD_SHIFT_DB)
+    e.commit()
+    avg = sdb.Averager(N, S, alpha=0.25)
+    ref = np.zeros((S, N), np.float32)
+    L = oracle.lib()
+    primed = False
+    for f in range(feeds):
+        if f == 2:
+            avg.set_alpha(0.05)
+        alpha = 0.25 if f < 2 else 0.05
+        e.feed(x[:, f * N * frames:(f + 1) * N * frames])
+        avg.feed_ptr(e.psd_device_ptr, frames)
+        psd = e.read_psd()
+        for s in range(S):
+            for k in range(frames):
+                # the first frame is copied (Averager.cpp:30-38), like alpha >= 1
+                L.sdo_averager_feed(oracle.ptr(ref[s]), oracle.ptr(np.ascontiguousarray(psd[s, k])), N,
+                                    C.c_float(alpha if (primed or k > 0) else 1.0))
+        primed = True
+        assert np.array_equal(avg.read().view(np.uint32), ref.view(np.uint32))
+    # alpha >= 1 and reset() both copy the frame
+    avg.set_alpha(1.0)
+    e.feed(x[:, :N * frames])
+    avg.feed_ptr(e.psd_device_ptr, frames)
+    assert np.array_equal(avg.read().view(np.uint32), e.read_psd()[:, -1].view(np.uint32))
+    avg.set_alpha(0.5)
+    avg.reset()
+    avg.feed_ptr(e.psd_device_ptr, 1, frames * N)      # first frame of every stream's row
+    assert np.array_equal(avg.read().view(np.uint32), e.read_psd()[:, 0].view(np.uint32))
+
+
 def test_panoramic_sweep_with_channel_detector(sdb, oracle):
     """configs[4] in full: per-hop PSD -> channel detector on the rank that owns the hop + SpectrumView stitch.
     The stitched spectrum must not change when the detector rides along (linear PSD + separate dB pass), and the
