@@ -304,6 +304,36 @@ const void    *sdb_capture_data(const sdb_capture_t *c);
 void           sdb_capture_close(sdb_capture_t *c);
 const char    *sdb_capture_last_error(void);
 
+/* Recording side.  Host-only as well.
+ *  - baseband capture: what the GUI's baseband-filter hook writes (Default/Source/SourceWidget.cpp:1078-1100,
+ *    1156-1171; Misc/FileDataSaver.cpp:68-82): complex float32 blocks appended to
+ *    "sigdigger_%Y%m%d_%H%M%SZ_<rate>_<freq>_float32_iq.raw".  The recorder also stores u8 / s8 / s16 (inverse of
+ *    the loader's scaling, round to nearest, saturating) and the WAV / SigMF containers sdb_capture_open() reads.
+ *  - audio: mono PCM16 WAV of Re{x} named "audio-<AM|FM|USB|LSB|RAW>-<freq>-<rate>-<NNNN>.wav", first free index
+ *    (Audio/AudioFileSaver.cpp:57-107,131-152).
+ * Errors: NULL / -1 with the text in sdb_capture_last_error(). */
+typedef struct {
+  int32_t container, sample_format;       /* SDB_CONTAINER_RAW / WAV / SIGMF; SDB_FORMAT_* as stored */
+  double  samp_rate, frequency;
+  int64_t start_time;                     /* UTC seconds; 0 = now */
+} sdb_recorder_params;
+typedef struct sdb_recorder sdb_recorder_t;
+/* auto_name != 0: `path` is a directory and the file gets SigDigger's capture name */
+sdb_recorder_t *sdb_recorder_open(const char *path, int32_t auto_name, const sdb_recorder_params *p);
+sdb_recorder_t *sdb_audio_recorder_open(const char *dir, int32_t demod, double frequency, uint32_t samp_rate);
+const char     *sdb_recorder_path(const sdb_recorder_t *r);
+uint64_t        sdb_recorder_samples(const sdb_recorder_t *r);
+long            sdb_recorder_write(sdb_recorder_t *r, const sdb_complex *x, size_t n);   /* returns n or -1 */
+int             sdb_recorder_close(sdb_recorder_t *r);                                    /* patches WAV sizes */
+int             sdb_capture_file_name(char *dst, size_t cap, int64_t utc_seconds, int32_t sample_format,
+                                      double samp_rate, double frequency);
+/* Inspector recording / forwarding formats (Default/GenericInspector/InspectorUI.cpp:860-930): the bytes the data
+ * saver receives for each data variable.  decision_mode: 0 argument (arg(i x) / pi), 1 modulus.  Returns bytes. */
+enum { SDB_DATAVAR_DECISION_SPACE = 0, SDB_DATAVAR_SOFT_BITS, SDB_DATAVAR_SOFT_BITS_I, SDB_DATAVAR_SOFT_BITS_Q,
+       SDB_DATAVAR_SYMBOLS };
+long            sdb_inspector_forward(int32_t data_var, int32_t decision_mode, const sdb_complex *soft,
+                                      const uint8_t *hard, size_t n, void *dst);
+
 /* ------------------------------------------------------------------------------------------------
  * suscan-style asynchronous analyzer: a worker thread reads the source, runs the
  * engine block by block and posts messages; requests are answered in order with messages carrying req_id.

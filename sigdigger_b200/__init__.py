@@ -74,6 +74,85 @@ class Capture:
     __del__ = close
 
 
+class RecorderParams(C.Structure):
+    """sdb_recorder_params"""
+    _fields_ = [("container", C.c_int32), ("sample_format", C.c_int32), ("samp_rate", C.c_double),
+                ("frequency", C.c_double), ("start_time", C.c_int64)]
+
+
+AUDIO_DEMOD = {"am": 0, "fm": 1, "usb": 2, "lsb": 3, "raw": 4}
+DATAVAR = {"decision_space": 0, "soft_bits": 1, "soft_bits_i": 2, "soft_bits_q": 3, "symbols": 4}
+
+
+def _cap_err(L, what):
+    return SdbError((L.sdb_capture_last_error() or what.encode()).decode())
+
+
+class Recorder:
+    """Capture writer (raw / WAV / SigMF; float32 / u8 / s8 / s16), or with `audio=` the mono PCM16 audio saver.
+    Host-only.  write() takes complex64 blocks -- the body of the GUI's baseband-filter hook."""
+
+    def __init__(self, path, samp_rate=0.0, frequency=0.0, container="raw", sample_format="f32", start_time=0,
+                 auto_name=False, audio=None):
+        self._L = L = load_library()
+        if audio is not None:
+            self._h = L.sdb_audio_recorder_open(os.fsencode(path), AUDIO_DEMOD[audio], frequency, int(samp_rate))
+        else:
+            p = RecorderParams(CONTAINER[container], FORMAT[sample_format], samp_rate, frequency, start_time)
+            self._h = L.sdb_recorder_open(os.fsencode(path), int(auto_name), C.byref(p))
+        if not self._h:
+            raise _cap_err(L, "recorder open failed")
+        self.path = os.fsdecode(L.sdb_recorder_path(self._h))
+
+    def write(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        n = self._L.sdb_recorder_write(self._h, x.ctypes.data, x.size)
+        if n < 0:
+            raise _cap_err(self._L, "write failed")
+        return n
+
+    @property
+    def samples(self):
+        return self._L.sdb_recorder_samples(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            h, self._h = self._h, None
+            if self._L.sdb_recorder_close(h) != 0:
+                raise _cap_err(self._L, "close failed")
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def capture_file_name(utc_seconds, samp_rate, frequency, sample_format="f32"):
+    buf = C.create_string_buffer(128)
+    L = load_library()
+    if L.sdb_capture_file_name(buf, 128, int(utc_seconds), FORMAT[sample_format], samp_rate, frequency) < 0:
+        raise _cap_err(L, "file name failed")
+    return buf.value.decode()
+
+
+def inspector_forward(data_var, soft, hard=None, decision_mode="argument"):
+    """InspectorUI recording formats -> numpy array of what the data saver would receive"""
+    L = load_library()
+    soft = np.ascontiguousarray(soft, dtype=np.complex64)
+    n = soft.size
+    dv = DATAVAR[data_var]
+    out = np.empty(n, np.complex64 if dv == 1 else np.uint8 if dv == 4 else np.float32)
+    if hard is not None:
+        hard = np.ascontiguousarray(hard, dtype=np.uint8)
+    r = L.sdb_inspector_forward(dv, {"argument": 0, "modulus": 1}[decision_mode], soft.ctypes.data,
+                                hard.ctypes.data if hard is not None else None, n, out.ctypes.data)
+    if r < 0:
+        raise _cap_err(L, "forward failed")
+    assert r == out.nbytes
+    return out
+
+
 class ChannelDetector:
     """Stand-alone SPEC K detector on device-resident linear PSDs (e.g. a stitched SpectrumView)."""
 
@@ -223,6 +302,14 @@ _PROTOS = {
     "sdb_sview_size": (C.c_uint32, [C.c_void_p]),
     "sdb_sview_max_bins": (C.c_uint32, [C.c_void_p]),
     "sdb_sview_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "sdb_recorder_open": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_void_p]),
+    "sdb_audio_recorder_open": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_double, C.c_uint32]),
+    "sdb_recorder_path": (C.c_char_p, [C.c_void_p]),
+    "sdb_recorder_samples": (C.c_uint64, [C.c_void_p]),
+    "sdb_recorder_write": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_recorder_close": (C.c_int, [C.c_void_p]),
+    "sdb_capture_file_name": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int64, C.c_int32, C.c_double, C.c_double]),
+    "sdb_inspector_forward": (C.c_long, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sdb_psd_shift_db_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
     "sdb_averager_new": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_float, C.c_int]),
     "sdb_averager_destroy": (None, [C.c_void_p]),

@@ -208,3 +208,259 @@ extern "C" void sdb_capture_close(sdb_capture_t *c)
   if (c->fd >= 0) close(c->fd);
   delete c;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Recording side (SURVEY.md 8(f) rank 2 "source decode + recording").  Host code, no kernels.
+//
+// Reference behaviour:
+//  * baseband capture: the GUI registers a baseband filter whose body writes the analyzer's complex float32
+//    blocks to a file named "sigdigger_%Y%m%d_%H%M%SZ_<rate>_<freq>_float32_iq.raw"
+//    (Default/Source/SourceWidget.cpp:1078-1100,1156-1171; Misc/FileDataSaver.cpp:68-82: plain write()).
+//  * audio: mono 16-bit PCM WAV of Re{x}, "audio-<MOD>-<freq>-<rate>-<NNNN>.wav", first free index
+//    (Audio/AudioFileSaver.cpp:57-107,131-152).
+//  * inspector recording: one of five data variables (Default/GenericInspector/InspectorUI.cpp:860-930).
+// Beyond the reference (its writers are float32-only) the recorder also stores u8 / s8 / s16 and the WAV /
+// SigMF containers the capture reader above understands, with the inverse of the SPEC Q scaling, so that a
+// recording can be played back through sdb_capture_open() without an external tool.
+// ------------------------------------------------------------------------------------------------
+#include <errno.h>
+#include <math.h>
+#include <vector>
+#include "sdb_math.h"
+
+struct sdb_recorder {
+  int fd = -1;
+  int container = SDB_CONTAINER_RAW, format = SDB_FORMAT_FLOAT32;
+  bool audio = false;                       // mono PCM16 of the real part
+  double samp_rate = 0, frequency = 0;
+  int64_t start_time = 0;
+  uint64_t samples = 0, data_bytes = 0;
+  std::string path, meta_path;
+  std::vector<unsigned char> tmp;
+};
+
+static const char *fmt_token(int f)
+{
+  return f == SDB_FORMAT_UNSIGNED8 ? "unsigned8" : f == SDB_FORMAT_SIGNED8 ? "signed8"
+       : f == SDB_FORMAT_SIGNED16 ? "signed16" : "float32";
+}
+
+extern "C" int sdb_capture_file_name(char *dst, size_t cap, int64_t utc_seconds, int32_t sample_format,
+                                     double samp_rate, double frequency)
+{
+  if (!dst || cap == 0) { g_cap_err = "null argument"; return -1; }
+  time_t t = (time_t) utc_seconds;
+  struct tm tm;
+  char datetime[24];
+  gmtime_r(&t, &tm);
+  strftime(datetime, sizeof(datetime), "%Y%m%d_%H%M%SZ", &tm);
+  const int n = snprintf(dst, cap, "sigdigger_%s_%d_%.0lf_%s_iq.raw", datetime, (int) samp_rate, frequency,
+                         fmt_token(sample_format));
+  if (n < 0 || (size_t) n >= cap) { g_cap_err = "file name buffer too small"; return -1; }
+  return n;
+}
+
+static const char *demod_token(int d)
+{
+  switch (d) {                                // enum AudioDemod, include/SigDiggerHelpers.h:39-45
+    case 0: return "AM"; case 1: return "FM"; case 2: return "USB"; case 3: return "LSB"; default: return "RAW";
+  }
+}
+
+static void wr16(unsigned char *p, unsigned v) { p[0] = v & 0xff; p[1] = (v >> 8) & 0xff; }
+static void wr32(unsigned char *p, uint32_t v) { wr16(p, v & 0xffff); wr16(p + 2, v >> 16); }
+
+// 44-byte canonical header; sizes are patched again on close
+static bool write_wav_header(sdb_recorder *r)
+{
+  unsigned char h[44];
+  const unsigned ch = r->audio ? 1 : 2;
+  const unsigned bits = r->audio ? 16 : r->format == SDB_FORMAT_FLOAT32 ? 32 : r->format == SDB_FORMAT_SIGNED16 ? 16 : 8;
+  const unsigned tag = (!r->audio && r->format == SDB_FORMAT_FLOAT32) ? 3 : 1;
+  const uint32_t rate = (uint32_t) (r->samp_rate + 0.5);
+  const uint32_t data = r->data_bytes > 0xffffffffull - 36 ? 0xffffffffu - 36 : (uint32_t) r->data_bytes;
+  memcpy(h, "RIFF", 4); wr32(h + 4, 36 + data); memcpy(h + 8, "WAVEfmt ", 8); wr32(h + 16, 16);
+  wr16(h + 20, tag); wr16(h + 22, ch); wr32(h + 24, rate); wr32(h + 28, rate * ch * (bits / 8));
+  wr16(h + 32, ch * (bits / 8)); wr16(h + 34, bits); memcpy(h + 36, "data", 4); wr32(h + 40, data);
+  return pwrite(r->fd, h, sizeof(h), 0) == (ssize_t) sizeof(h);
+}
+
+static bool write_sigmf_meta(const sdb_recorder *r)
+{
+  FILE *f = fopen(r->meta_path.c_str(), "w");
+  if (!f) return false;
+  const char *dt = r->format == SDB_FORMAT_UNSIGNED8 ? "cu8" : r->format == SDB_FORMAT_SIGNED8 ? "ci8"
+                 : r->format == SDB_FORMAT_SIGNED16 ? "ci16_le" : "cf32_le";
+  time_t t = (time_t) r->start_time;
+  struct tm tm;
+  char iso[32];
+  gmtime_r(&t, &tm);
+  strftime(iso, sizeof(iso), "%Y-%m-%dT%H:%M:%SZ", &tm);
+  fprintf(f, "{\n  \"global\": {\n    \"core:datatype\": \"%s\",\n    \"core:sample_rate\": %.17g,\n"
+             "    \"core:version\": \"1.0.0\",\n    \"core:recorder\": \"sigdigger_b200\"\n  },\n"
+             "  \"captures\": [\n    { \"core:sample_start\": 0, \"core:frequency\": %.17g, \"core:datetime\": \"%s\" }\n  ],\n"
+             "  \"annotations\": []\n}\n", dt, r->samp_rate, r->frequency, iso);
+  return fclose(f) == 0;
+}
+
+static sdb_recorder_t *rec_fail(sdb_recorder *r, const std::string &msg)
+{
+  g_cap_err = msg;
+  if (r) { if (r->fd >= 0) close(r->fd); delete r; }
+  return nullptr;
+}
+
+extern "C" sdb_recorder_t *sdb_recorder_open(const char *path, int32_t auto_name, const sdb_recorder_params *p)
+{
+  if (!path || !p) return rec_fail(nullptr, "null argument");
+  if (p->sample_format < SDB_FORMAT_FLOAT32 || p->sample_format > SDB_FORMAT_SIGNED16)
+    return rec_fail(nullptr, "unknown sample format");
+  if (p->container < SDB_CONTAINER_RAW || p->container > SDB_CONTAINER_SIGMF) return rec_fail(nullptr, "unknown container");
+  if (p->container == SDB_CONTAINER_WAV && p->sample_format == SDB_FORMAT_SIGNED8)
+    return rec_fail(nullptr, "WAV has no signed 8-bit PCM");
+  if (!(p->samp_rate > 0)) return rec_fail(nullptr, "sample rate must be positive");
+  sdb_recorder *r = new sdb_recorder();
+  r->container = p->container; r->format = p->sample_format; r->samp_rate = p->samp_rate; r->frequency = p->frequency;
+  r->start_time = p->start_time ? p->start_time : (int64_t) time(nullptr);
+  r->path = path;
+  if (auto_name) {                              // `path` is the directory (DataSaverUI's record path)
+    char name[128];
+    if (sdb_capture_file_name(name, sizeof(name), r->start_time, r->format, r->samp_rate, r->frequency) < 0)
+      return rec_fail(r, "file name buffer too small");
+    std::string base(name);
+    if (r->container == SDB_CONTAINER_WAV) base.replace(base.size() - 4, 4, ".wav");
+    else if (r->container == SDB_CONTAINER_SIGMF) base.resize(base.size() - 4);
+    r->path = std::string(path) + "/" + base;
+  }
+  if (r->container == SDB_CONTAINER_SIGMF) {
+    std::string stem = r->path;
+    for (const char *suf : { ".sigmf-meta", ".sigmf-data", ".sigmf" })
+      if (ends_with(stem, suf)) { stem.resize(stem.size() - strlen(suf)); break; }
+    r->meta_path = stem + ".sigmf-meta";
+    r->path = stem + ".sigmf-data";
+  }
+  r->fd = open(r->path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0600);   // creat(path, 0600), SourceWidget.cpp:1102
+  if (r->fd < 0) return rec_fail(r, "cannot create " + r->path + ": " + strerror(errno));
+  if (r->container == SDB_CONTAINER_WAV) {
+    if (!write_wav_header(r) || lseek(r->fd, 44, SEEK_SET) != 44) return rec_fail(r, "cannot write the WAV header");
+  } else if (r->container == SDB_CONTAINER_SIGMF && !write_sigmf_meta(r)) {
+    return rec_fail(r, "cannot write " + r->meta_path);
+  }
+  return r;
+}
+
+extern "C" sdb_recorder_t *sdb_audio_recorder_open(const char *dir, int32_t demod, double frequency, uint32_t samp_rate)
+{
+  if (!dir || samp_rate == 0) return rec_fail(nullptr, "invalid argument");
+  sdb_recorder *r = new sdb_recorder();
+  r->audio = true; r->container = SDB_CONTAINER_WAV; r->format = SDB_FORMAT_SIGNED16;
+  r->samp_rate = samp_rate; r->frequency = frequency; r->start_time = (int64_t) time(nullptr);
+  char name[128];
+  unsigned index = 1;
+  do {
+    snprintf(name, sizeof(name), "audio-%s-%.0lf-%d-%04u.wav", demod_token(demod), frequency, (int) samp_rate, index++);
+    r->path = std::string(dir) + "/" + name;
+  } while (access(r->path.c_str(), F_OK) != -1 && index < 10000);
+  r->fd = open(r->path.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0644);
+  if (r->fd < 0) return rec_fail(r, "Save file " + r->path + " failed: " + strerror(errno));
+  if (!write_wav_header(r) || lseek(r->fd, 44, SEEK_SET) != 44) return rec_fail(r, "cannot write the WAV header");
+  return r;
+}
+
+extern "C" const char *sdb_recorder_path(const sdb_recorder_t *r) { return r ? r->path.c_str() : nullptr; }
+extern "C" uint64_t sdb_recorder_samples(const sdb_recorder_t *r) { return r ? r->samples : 0; }
+
+static bool write_all(sdb_recorder *r, const void *data, size_t len)
+{
+  const unsigned char *p = (const unsigned char *) data;
+  while (len) {
+    const ssize_t w = write(r->fd, p, len);
+    if (w < 1) { g_cap_err = std::string("write() failed: ") + strerror(errno); return false; }
+    p += w; len -= (size_t) w;
+  }
+  return true;
+}
+
+static inline long sat(float v, long lo, long hi, long nan_code = 0)
+{
+  if (!(v == v)) return nan_code;                         // NaN -> the code of 0.0
+  const float q = nearbyintf(v);
+  return q < (float) lo ? lo : q > (float) hi ? hi : (long) q;
+}
+
+// x: n complex float32 samples (the baseband-filter hook's `samples`, or a SAMPLES message)
+extern "C" long sdb_recorder_write(sdb_recorder_t *r, const sdb_complex *x, size_t n)
+{
+  if (!r || (!x && n)) { g_cap_err = "null argument"; return -1; }
+  if (r->fd < 0) return 0;
+  const float *f = (const float *) x;
+  size_t bytes;
+  const void *src;
+  if (r->audio) {
+    r->tmp.resize(n * 2);
+    for (size_t i = 0; i < n; ++i) wr16(&r->tmp[2 * i], (unsigned) (sat(f[2 * i] * 32767.0f, -32768, 32767) & 0xffff));
+    src = r->tmp.data(); bytes = n * 2;
+  } else if (r->format == SDB_FORMAT_FLOAT32) {
+    src = x; bytes = n * 8;
+  } else if (r->format == SDB_FORMAT_SIGNED16) {
+    r->tmp.resize(n * 4);
+    for (size_t i = 0; i < 2 * n; ++i) wr16(&r->tmp[2 * i], (unsigned) (sat(f[i] * 32768.0f, -32768, 32767) & 0xffff));
+    src = r->tmp.data(); bytes = n * 4;
+  } else {
+    r->tmp.resize(n * 2);
+    if (r->format == SDB_FORMAT_UNSIGNED8)
+      for (size_t i = 0; i < 2 * n; ++i) r->tmp[i] = (unsigned char) sat(f[i] * 128.0f + 128.0f, 0, 255, 128);
+    else
+      for (size_t i = 0; i < 2 * n; ++i) r->tmp[i] = (unsigned char) (sat(f[i] * 128.0f, -128, 127) & 0xff);
+    src = r->tmp.data(); bytes = n * 2;
+  }
+  if (!write_all(r, src, bytes)) return -1;
+  r->samples += n; r->data_bytes += bytes;
+  return (long) n;
+}
+
+extern "C" int sdb_recorder_close(sdb_recorder_t *r)
+{
+  if (!r) return 0;
+  bool ok = true;
+  if (r->fd >= 0) {
+    if (r->container == SDB_CONTAINER_WAV) ok = write_wav_header(r);
+    ok = (close(r->fd) == 0) && ok;
+  }
+  if (!ok) g_cap_err = "closing " + r->path + " failed";
+  delete r;
+  return ok ? 0 : -1;
+}
+
+// Inspector recording / forwarding formats (Default/GenericInspector/InspectorUI.cpp:860-930): what the data
+// saver receives for each "data variable".  dst must hold n floats, n complex or n bytes; returns bytes.
+extern "C" long sdb_inspector_forward(int32_t data_var, int32_t decision_mode, const sdb_complex *soft,
+                                      const uint8_t *hard, size_t n, void *dst)
+{
+  if (!dst || (n && !soft && data_var != SDB_DATAVAR_SYMBOLS)) { g_cap_err = "null argument"; return -1; }
+  const float *s = (const float *) soft;
+  float *o = (float *) dst;
+  switch (data_var) {
+    case SDB_DATAVAR_DECISION_SPACE:
+      if (decision_mode == 1) for (size_t i = 0; i < n; ++i) o[i] = d_cabsf(s[2 * i], s[2 * i + 1]);
+      else for (size_t i = 0; i < n; ++i)                               // arg(i x) / pi
+        o[i] = d_atan2f(s[2 * i], -s[2 * i + 1]) / 3.14159265358979323846f;
+      return (long) (n * sizeof(float));
+    case SDB_DATAVAR_SOFT_BITS:
+      memcpy(dst, soft, n * 8);
+      return (long) (n * 8);
+    case SDB_DATAVAR_SOFT_BITS_I:
+      for (size_t i = 0; i < n; ++i) o[i] = s[2 * i];
+      return (long) (n * sizeof(float));
+    case SDB_DATAVAR_SOFT_BITS_Q:
+      for (size_t i = 0; i < n; ++i) o[i] = s[2 * i + 1];
+      return (long) (n * sizeof(float));
+    case SDB_DATAVAR_SYMBOLS:
+      if (!hard && n) { g_cap_err = "no decision available"; return -1; }
+      memcpy(dst, hard, n);
+      return (long) n;
+    default:
+      g_cap_err = "unknown data variable";
+      return -1;
+  }
+}
