@@ -159,6 +159,40 @@ def oracle_params(name):
     return O, O.make_an_params(N_FFT, "blackmann_harris", chans)
 
 
+def usable_cores():
+    """Host threads the CPU legs may really use: the affinity mask, capped by the cgroup CPU quota (a container
+    that reports 128 CPUs but is throttled to 16 runs 128 OpenMP threads slower than 16).  SDB_CPU_THREADS overrides.
+    Returns (threads, description)."""
+    if os.environ.get("SDB_CPU_THREADS"):
+        t = max(1, int(os.environ["SDB_CPU_THREADS"]))
+        return t, "SDB_CPU_THREADS=%d" % t
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                      # cgroup v2: "<quota|max> <period>"
+            q, p = f.read().split()
+            if q != "max":
+                quota = float(q) / float(p)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:     # cgroup v1
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                p = float(f.read())
+            if q > 0 and p > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    t = aff
+    if quota is not None:
+        t = max(1, min(aff, int(quota + 0.999)))
+    return t, "cpu_count %d, affinity %d, cgroup quota %s" % (os.cpu_count() or 1, aff,
+                                                               "none" if quota is None else "%.1f CPUs" % quota)
+
+
 def cpu_run(name, n_streams, n, threads, reps=1, warm=0):
     import ctypes as C
     O, p = oracle_params(name)
@@ -175,17 +209,34 @@ def cpu_run(name, n_streams, n, threads, reps=1, warm=0):
     return times, n_streams * n
 
 
+def pick_threads(name):
+    """Thread count for the CPU legs: the usable cores, or a fraction of them when a short probe of the same
+    workload (4 frames per stream, one stream per thread, best of 2) runs faster that way (SMT siblings, throttled containers).
+    Returns (threads, description)."""
+    cores, how = usable_cores()
+    if os.environ.get("SDB_CPU_THREADS"):
+        return cores, how
+    best, table = (0.0, cores), []
+    for t in sorted({cores, max(1, cores // 2), max(1, cores // 4), max(1, cores // 8)}, reverse=True):
+        times, samples = cpu_run(name, t, 4 * N_FFT, t, reps=2, warm=1)
+        rate = samples / min(times) / 1e6
+        table.append("%d:%.0f" % (t, rate))
+        if rate > best[0] * 1.05:                      # prefer more threads unless fewer are clearly faster
+            best = (rate, t)
+    return best[1], "%s; probe threads:MS/s %s" % (how, " ".join(table))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores, how = pick_threads(args.workload)
     n = N_FFT // 2 * 16                      # 2^19 samples per stream: one stream per host thread
     streams = cores
     times, samples = cpu_run(args.workload, streams, n, cores, reps=args.steps, warm=args.warmup)
     total = sum(times)
     v = samples * len(times) / total / 1e6
-    sample = "%d streams x %d samples per step, %d OpenMP threads" % (streams, n, cores)
+    sample = "%d streams x %d samples per step, %d OpenMP threads (%s)" % (streams, n, cores, how)
     out = {"impl": "reference", "metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)",
            "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -434,11 +485,11 @@ def run_cuda(args):
     # ---- bounded CPU baseline on rank 0, N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores, how = pick_threads(name)
         times, samples = cpu_run(name, cores, N_FFT // 2 * 16, cores, reps=2, warm=0)
         cpu = {"value": samples * len(times) / sum(times) / 1e6, "unit": "MS/s", "cores": cores, "kind": "port",
                "sample": "%d streams x %d samples x %d reps of the same workload (oracle restatement, OpenMP, "
-                         "one stream per thread)" % (cores, N_FFT // 2 * 16, len(times))}
+                         "one stream per thread; %s)" % (cores, N_FFT // 2 * 16, len(times), how)}
 
     if rank == 0:
         out = {"metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)", "value": value,
