@@ -496,7 +496,8 @@ int      sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size_t n_f
 /* Spectrum averager the GUI runs on every PSD message (Misc/Averager.cpp:25-60; fed at
  * UIMediator/SpectrumMediator.cpp:128): per bin last += alpha (x - last), first frame (and alpha >= 1) copied.
  * One state row of psd_size bins per stream, on the device; frames of a feed are applied in order.
- * psd_dev: [n_streams] rows of `frames` frames, `stream_stride` floats apart (e.g. sdb_engine_psd_device) */
+ * psd_dev: [n_streams] rows of `frames` frames, `stream_stride` floats apart (e.g. sdb_engine_psd_device).
+ * Both passes run on the default stream: the producer of psd_dev must have completed (sdb_engine_sync). */
 typedef struct sdb_averager sdb_averager_t;
 sdb_averager_t *sdb_averager_new(uint32_t psd_size, uint32_t n_streams, float alpha, int device);
 void         sdb_averager_destroy(sdb_averager_t *a);
