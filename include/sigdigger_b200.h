@@ -327,6 +327,20 @@ long            sdb_recorder_write(sdb_recorder_t *r, const sdb_complex *x, size
 int             sdb_recorder_close(sdb_recorder_t *r);                                    /* patches WAV sizes */
 int             sdb_capture_file_name(char *dst, size_t cap, int64_t utc_seconds, int32_t sample_format,
                                       double samp_rate, double frequency);
+/* The audio inspector's caller (Default/Audio/AudioProcessor.cpp): which channel it opens, where LO and bandwidth
+ * really go for the side-band modes, and what it writes into the audio.* keys.  demod = SigDigger's AudioDemod
+ * (0 AM, 1 FM, 2 USB, 3 LSB, 4 RAW; include/SigDiggerHelpers.h:39-45).  Host-only parameter arithmetic. */
+typedef struct {
+  double   max_audio_bw;                     /* min(fs / 2, 2e5)                      (AudioProcessor.cpp:118-121) */
+  uint32_t sample_rate;                      /* requested rate floored to it          (:123-125) */
+  double   true_bw, true_lo;                 /* calcTrueBandwidth / calcTrueLoFreq    (:200-228) */
+  double   ch_fc, ch_ft, ch_bw, ch_f_lo, ch_f_hi;   /* channel of requestOpen("audio", ch)   (:143-151) */
+} sdb_audio_plan;
+int sdb_audio_plan_make(double analyzer_samp_rate, uint32_t requested_rate, int32_t demod, double lo, double bw,
+                        sdb_audio_plan *out);
+/* setParams() (:250-269): fills audio_cutoff / volume (1) / sample_rate / demod (+1 on the wire) / squelch / agc */
+int sdb_audio_plan_config(const sdb_audio_plan *plan, int32_t demod, float cutoff, int32_t squelch, float squelch_level,
+                          int32_t agc, float agc_ts, sdb_inspector_config *cfg);
 /* Inspector recording / forwarding formats (Default/GenericInspector/InspectorUI.cpp:860-930): the bytes the data
  * saver receives for each data variable.  decision_mode: 0 argument (arg(i x) / pi), 1 modulus.  Returns bytes. */
 enum { SDB_DATAVAR_DECISION_SPACE = 0, SDB_DATAVAR_SOFT_BITS, SDB_DATAVAR_SOFT_BITS_I, SDB_DATAVAR_SOFT_BITS_Q,

@@ -128,6 +128,35 @@ class Recorder:
             pass
 
 
+class AudioPlan(C.Structure):
+    """sdb_audio_plan"""
+    _fields_ = [("max_audio_bw", C.c_double), ("sample_rate", C.c_uint32), ("true_bw", C.c_double),
+                ("true_lo", C.c_double), ("ch_fc", C.c_double), ("ch_ft", C.c_double), ("ch_bw", C.c_double),
+                ("ch_f_lo", C.c_double), ("ch_f_hi", C.c_double)]
+
+
+def audio_plan(analyzer_samp_rate, requested_rate, demod, lo, bw):
+    """AudioProcessor's open / LO / bandwidth rules -> AudioPlan"""
+    L = load_library()
+    p = AudioPlan()
+    d = AUDIO_DEMOD[demod] if isinstance(demod, str) else int(demod)
+    if L.sdb_audio_plan_make(analyzer_samp_rate, int(requested_rate), d, lo, bw, C.byref(p)) != 0:
+        raise _cap_err(L, "audio plan failed")
+    return p
+
+
+def audio_plan_config(plan, demod, cutoff, squelch=False, squelch_level=0.0, agc=True, agc_ts=0.2, fs=None):
+    """AudioProcessor::setParams -> InspectorConfig of class "audio" """
+    L = load_library()
+    cfg = InspectorConfig()
+    _check(L.sdb_inspector_config_default(C.byref(cfg), INSP["audio"], fs if fs is not None else plan.max_audio_bw))
+    d = AUDIO_DEMOD[demod] if isinstance(demod, str) else int(demod)
+    if L.sdb_audio_plan_config(C.byref(plan), d, cutoff, int(squelch), squelch_level, int(agc), agc_ts,
+                               C.byref(cfg)) != 0:
+        raise _cap_err(L, "audio config failed")
+    return cfg
+
+
 def capture_file_name(utc_seconds, samp_rate, frequency, sample_format="f32"):
     buf = C.create_string_buffer(128)
     L = load_library()
@@ -309,6 +338,9 @@ _PROTOS = {
     "sdb_recorder_write": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_recorder_close": (C.c_int, [C.c_void_p]),
     "sdb_capture_file_name": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int64, C.c_int32, C.c_double, C.c_double]),
+    "sdb_audio_plan_make": (C.c_int, [C.c_double, C.c_uint32, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
+    "sdb_audio_plan_config": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_float,
+                                        C.c_void_p]),
     "sdb_inspector_forward": (C.c_long, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sdb_psd_shift_db_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
     "sdb_averager_new": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_float, C.c_int]),

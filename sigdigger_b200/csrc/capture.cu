@@ -464,3 +464,49 @@ extern "C" long sdb_inspector_forward(int32_t data_var, int32_t decision_mode, c
       return -1;
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Host-side rules of the audio inspector's caller (Default/Audio/AudioProcessor.cpp): which channel is
+// opened, where the LO and the bandwidth really go for the side-band modes, and what is written into the
+// audio.* configuration keys.  Pure parameter arithmetic in binary64, as in the reference.
+// ------------------------------------------------------------------------------------------------
+extern "C" int sdb_audio_plan_make(double analyzer_samp_rate, uint32_t requested_rate, int32_t demod, double lo,
+                                   double bw, sdb_audio_plan *out)
+{
+  if (!out || !(analyzer_samp_rate > 0) || demod < 0 || demod > 4) { g_cap_err = "invalid argument"; return -1; }
+  memset(out, 0, sizeof(*out));
+  // openAudio(), AudioProcessor.cpp:118-128: m_maxAudioBw = min(fs / 2, 2e5); the rate is floored to it
+  const double max_bw = analyzer_samp_rate / 2 < 2e5 ? analyzer_samp_rate / 2 : 2e5;
+  uint32_t rate = requested_rate;
+  if ((double) rate > max_bw) rate = (uint32_t) floor(max_bw);
+  if (rate < 1) { g_cap_err = "Audio device does not support the current sample rate"; return -1; }
+  // calcTrueBandwidth(), :200-214
+  double tbw = bw;
+  if (demod == 2 || demod == 3) tbw *= .5;
+  if (tbw > max_bw) tbw = max_bw; else if (tbw < 1) tbw = 1;
+  // calcTrueLoFreq(), :216-228
+  double delta = 0;
+  if (demod == 2) delta += .5 * tbw; else if (demod == 3) delta -= .5 * tbw;
+  out->max_audio_bw = max_bw; out->sample_rate = rate; out->true_bw = tbw; out->true_lo = lo + delta;
+  // the channel of requestOpen("audio", ch), :143-151
+  out->ch_bw = max_bw; out->ch_ft = 0; out->ch_fc = out->true_lo;
+  out->ch_f_lo = -.5 * max_bw; out->ch_f_hi = +.5 * max_bw;
+  if (out->ch_fc > max_bw || out->ch_fc < -max_bw) out->ch_fc = 0;
+  return 0;
+}
+
+// setParams(), AudioProcessor.cpp:250-269: volume is handled at UI level (1), the demodulator goes +1 on the wire
+extern "C" int sdb_audio_plan_config(const sdb_audio_plan *plan, int32_t demod, float cutoff, int32_t squelch,
+                                     float squelch_level, int32_t agc, float agc_ts, sdb_inspector_config *cfg)
+{
+  if (!plan || !cfg || demod < 0 || demod > 4) { g_cap_err = "invalid argument"; return -1; }
+  cfg->audio_cutoff = cutoff;
+  cfg->audio_volume = 1.f;
+  cfg->audio_sample_rate = plan->sample_rate;
+  cfg->audio_demod = (uint32_t) demod + 1;
+  cfg->audio_squelch = squelch ? 1 : 0;
+  cfg->audio_squelch_level = squelch_level;
+  cfg->agc_enabled = agc ? 1 : 0;
+  cfg->agc_ts = agc_ts;
+  return 0;
+}

@@ -125,6 +125,29 @@ def test_audio_saver_names_and_pcm(sdbh, tmp_path):
         sdbh.Recorder(str(tmp_path / "no" / "such" / "dir"), samp_rate=8000, audio="am")
 
 
+def test_audio_plan_follows_the_audio_processor(sdbh):
+    """Default/Audio/AudioProcessor.cpp:118-151,200-228,250-269 by hand"""
+    p = sdbh.audio_plan(2e6, 44100, "fm", lo=150e3, bw=12500.0)
+    assert (p.max_audio_bw, p.sample_rate, p.true_bw, p.true_lo) == (2e5, 44100, 12500.0, 150e3)
+    assert (p.ch_fc, p.ch_ft, p.ch_bw, p.ch_f_lo, p.ch_f_hi) == (150e3, 0.0, 2e5, -1e5, 1e5)
+    # side bands: half the bandwidth, LO moved by half of THAT (a quarter of the selected width)
+    u = sdbh.audio_plan(2e6, 44100, "usb", lo=7000.0, bw=2800.0)
+    l = sdbh.audio_plan(2e6, 44100, "lsb", lo=7000.0, bw=2800.0)
+    assert (u.true_bw, u.true_lo, l.true_bw, l.true_lo) == (1400.0, 7700.0, 1400.0, 6300.0)
+    # narrow analyzer: everything is limited by fs / 2, the playback rate is floored to it
+    n = sdbh.audio_plan(60000.0, 44100, "am", lo=0.0, bw=1e6)
+    assert (n.max_audio_bw, n.sample_rate, n.true_bw) == (30000.0, 30000, 30000.0)
+    assert sdbh.audio_plan(2e6, 8000, "am", lo=0.0, bw=0.2).true_bw == 1.0           # never below 1 Hz
+    assert sdbh.audio_plan(2e6, 8000, "am", lo=3e5, bw=1e4).ch_fc == 0.0             # outside +-maxAudioBw: opened at 0
+    assert sdbh.audio_plan(2e6, 8000, "am", lo=-2e5, bw=1e4).ch_fc == -2e5           # the limit itself is kept
+    with pytest.raises(sdbh.SdbError):
+        sdbh.audio_plan(1.5, 44100, "am", lo=0.0, bw=1.0)                            # rate floors to 0
+    cfg = sdbh.audio_plan_config(u, "usb", cutoff=3000.0, squelch=True, squelch_level=0.05, agc=False, agc_ts=0.5)
+    assert (cfg.audio_demod, cfg.audio_sample_rate, cfg.audio_volume) == (3, 44100, 1.0)   # USB = 2, +1 on the wire
+    assert (cfg.audio_cutoff, cfg.audio_squelch, cfg.agc_enabled, cfg.agc_ts) == (3000.0, 1, 0, 0.5)
+    assert abs(cfg.audio_squelch_level - 0.05) < 1e-9
+
+
 def test_inspector_recording_formats(sdbh):
     rng = np.random.default_rng(5)
     soft = (rng.standard_normal(1000) + 1j * rng.standard_normal(1000)).astype(np.complex64)
