@@ -528,6 +528,10 @@ int      sdb_sview_contrib_copy(sdb_sview_t *v, int32_t *j0, int32_t *nb, float 
 int      sdb_sview_accumulate(sdb_sview_t *v, const int32_t *j0, const int32_t *nb, const float *va,
                               const float *vc, size_t n_hops);
 int      sdb_sview_read(sdb_sview_t *v, float *psd, float *accum, float *count, size_t cap);
+/* SpectrumView::feed(SpectrumView const &detail) (Panoramic/Scanner.cpp:276-286): seed / refine a view with another
+ * one's accumulators weighted by its counts -- what Scanner::setViewRange does on zoom (:471-479: flip, setRange,
+ * feed(previous)).  Both views on the same device. */
+int      sdb_sview_feed_view(sdb_sview_t *v, const sdb_sview_t *detail);
 
 /* Offline inspector over captured channel-rate buffers (the block-wise CPU loops the GUI's TimeWindow
  * launches, Components/TimeWindow.cpp:1571-2183; sampler + decider of Tasks/WaveSampler.cpp:188-205,

@@ -338,6 +338,11 @@ void sdo_sview_feed_histogram(sdo_spectrum_view *v, const float *psd, size_t psd
 void sdo_sview_interpolate(sdo_spectrum_view *v);
 void sdo_sview_feed(sdo_spectrum_view *v, const float *psd, const float *count, size_t psd_size,
                     double center, int adjust_sides);
+/* the explicit-range overload (Scanner.cpp:239-256) and feed(SpectrumView const &) (Scanner.cpp:276-286): the
+ * zoom path of Scanner::setViewRange (Scanner.cpp:471-479) feeds the previous view into the new one */
+void sdo_sview_feed_range(sdo_spectrum_view *v, const float *psd, const float *count, size_t psd_size,
+                          double fmin, double fmax, int adjust_sides);
+void sdo_sview_feed_view(sdo_spectrum_view *v, const sdo_spectrum_view *detail);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole analyzer pass over one stream (SPEC section Z): main PSD over every non-overlapping

@@ -180,15 +180,29 @@ void sdo_sview_feed_histogram(sdo_spectrum_view *v, const float *psd, size_t psd
   }
 }
 
-/* Panoramic/Scanner.cpp:239-274 */
-void sdo_sview_feed(sdo_spectrum_view *v, const float *psd, const float *count, size_t psd_size,
-                    double center, int adjust_sides)
+/* Panoramic/Scanner.cpp:239-256 */
+void sdo_sview_feed_range(sdo_spectrum_view *v, const float *psd, const float *count, size_t psd_size,
+                          double fmin, double fmax, int adjust_sides)
 {
-  double fmin = center - v->fft_bandwidth / 2, fmax = center + v->fft_bandwidth / 2;
   double fft_count = (fmax - fmin) / v->freq_range;
   if (fft_count * v->spectrum_size >= 2)
     sdo_sview_feed_linear(v, psd, count, psd_size, fmin, fmax, adjust_sides);
   else
     sdo_sview_feed_histogram(v, psd, psd_size, fmin, fmax);
   sdo_sview_interpolate(v);
+}
+
+/* Panoramic/Scanner.cpp:258-274 */
+void sdo_sview_feed(sdo_spectrum_view *v, const float *psd, const float *count, size_t psd_size,
+                    double center, int adjust_sides)
+{
+  sdo_sview_feed_range(v, psd, count, psd_size, center - v->fft_bandwidth / 2, center + v->fft_bandwidth / 2,
+                       adjust_sides);
+}
+
+/* Panoramic/Scanner.cpp:276-286: the accumulators of the other view, weighted by its counts, sides untouched */
+void sdo_sview_feed_view(sdo_spectrum_view *v, const sdo_spectrum_view *detail)
+{
+  sdo_sview_feed_range(v, detail->psd_accum, detail->psd_count, detail->spectrum_size, detail->freq_min,
+                       detail->freq_max, 0);
 }

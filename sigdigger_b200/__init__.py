@@ -353,6 +353,7 @@ _PROTOS = {
     "sdb_sview_contrib": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sdb_sview_contrib_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_sview_feed_view": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdb_sview_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_sview_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_task_inspector": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
@@ -808,6 +809,10 @@ class SpectrumView:
             j0_ptr, nb_ptr, va_ptr, vc_ptr = self.contrib_ptrs()
             n_hops = self._n_hops
         _check(self._L.sdb_sview_accumulate(self._h, j0_ptr, nb_ptr, va_ptr, vc_ptr, n_hops))
+
+    def feed_view(self, detail):
+        """SpectrumView::feed(SpectrumView const &): the zoom path of the scanner"""
+        _check(self._L.sdb_sview_feed_view(self._h, detail._h))
 
     def read(self):
         n = self.size

@@ -1559,6 +1559,41 @@ extern "C" int sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size
   return 0;
 }
 
+// ---- SpectrumView::feed(SpectrumView const &) (Panoramic/Scanner.cpp:276-286; used by the zoom path of
+// ---- Scanner::setViewRange, :471-479): project the other view's accumulators / counts, then the same accumulate
+// ---- + interpolate pass a hop gets.
+cudaError_t sdb_launch_sview_project_view(cudaStream_t s, double freq_min, double freq_range, unsigned spectrum_size,
+                                          const float *src_acc, const float *src_cnt, unsigned src_size, double fmin,
+                                          double fmax, int *j0, int *nb, float *va, float *vc);
+
+extern "C" int sdb_sview_feed_view(sdb_sview_t *v, const sdb_sview_t *detail)
+{
+  if (!v || !detail) return fail("null view");
+  if (v == detail) return fail("a view cannot be fed into itself");
+  if (v->max_bins <= 0 || detail->max_bins <= 0) return fail("set_range first");
+  if (v->device != detail->device) return fail("both views must live on the same device");
+  CK(cudaSetDevice(v->device));
+  int *j0 = nullptr, *nb = nullptr; float *va = nullptr, *vc = nullptr;
+  const size_t row = 65536 * sizeof(float);
+  cudaError_t e = cudaMalloc(&j0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&nb, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&va, row);
+  if (e == cudaSuccess) e = cudaMalloc(&vc, row);
+  if (e == cudaSuccess) e = cudaMemset(j0, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(nb, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(va, 0, row);
+  if (e == cudaSuccess) e = cudaMemset(vc, 0, row);
+  if (e == cudaSuccess)
+    e = sdb_launch_sview_project_view(0, v->freq_min, v->freq_range, v->spectrum_size, detail->d_accum, detail->d_count,
+                                      detail->spectrum_size, detail->freq_min, detail->freq_max, j0, nb, va, vc);
+  if (e == cudaSuccess)
+    e = sdb_launch_sview_accumulate(0, v->spectrum_size, j0, nb, va, vc, 1, 65536, v->d_psd, v->d_accum, v->d_count);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(j0); cudaFree(nb); cudaFree(va); cudaFree(vc);
+  if (e != cudaSuccess) return fail(std::string("sdb_sview_feed_view: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- spectrum averager (Misc/Averager.cpp:25-60)
 cudaError_t sdb_launch_psd_average(cudaStream_t s, const float *psd, size_t stream_stride, unsigned frames, unsigned n,
                                    size_t n_streams, float alpha, int primed, float *last);

@@ -95,6 +95,82 @@ __global__ void k_sview_project(SviewGeom g, const float *__restrict__ psd, size
   }
 }
 
+// SpectrumView::feed(SpectrumView const &) (Scanner.cpp:276-286), the zoom path of Scanner::setViewRange: the other
+// view's accumulators, weighted by its counts, over its own frequency range, sides untouched.  One contribution
+// list of pitch spectrum_size (a view can cover every destination bin); k_sview_accumulate applies it like a hop.
+// Grid-stride over the destination bins; the histogram branch (source narrower than two destination bins) is one
+// thread, as in k_sview_project.
+__global__ void k_sview_project_view(SviewGeom g, const float *__restrict__ src_acc, const float *__restrict__ src_cnt,
+                                     unsigned src_size, double fmin, double fmax, int *__restrict__ j0_out,
+                                     int *__restrict__ nb_out, float *__restrict__ oa, float *__restrict__ oc)
+{
+  const double fft_count_rel = (fmax - fmin) / g.freq_range;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  if (fft_count_rel * g.spectrum_size >= 2) {
+    // ---- linear mode (Scanner.cpp:118-185) with adjustSides = false: skip = 0, freqSkip = 0
+    const double inp_bw = fmax - fmin;
+    const double freq_skip = (double) 0 / src_size * inp_bw;
+    const double bw = inp_bw - 2 * freq_skip;
+    const double fft_count = g.freq_range / bw;
+    const double bins = g.spectrum_size / fft_count;
+    const double src_bin_w = inp_bw / src_size;
+    const double dst_bin_w = g.freq_range / g.spectrum_size;
+    const double delta = dst_bin_w / src_bin_w;
+    double pos = (freq_skip + fmin - g.freq_min) / g.freq_range;
+    pos *= g.spectrum_size;
+    const int j0 = pos > 0 ? (int) pos : 0;
+    const int k = pos + bins < g.spectrum_size ? (int) (pos + bins) : (int) g.spectrum_size;
+    int nb = k - j0;
+    if (nb < 0) nb = 0;
+    if (lead) { *j0_out = j0; *nb_out = nb; }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {
+      const int j = j0 + t;
+      const double freq_j = g.freq_min + dst_bin_w * j;
+      const double src_bin = (freq_j - fmin) / src_bin_w;
+      int start_bin = (int) src_bin;
+      int end_bin = (int) (src_bin + delta);
+      start_bin = start_bin < 0 ? 0 : (start_bin > (int) src_size - 1 ? (int) src_size - 1 : start_bin);
+      end_bin = end_bin < start_bin + 1 ? start_bin + 1 : (end_bin > (int) src_size ? (int) src_size : end_bin);
+      float acc = 0, cnt = 0;
+      for (int i = start_bin; i < end_bin; ++i) { acc += src_acc[i]; cnt += src_cnt[i]; }
+      // `if (psdCount > 0)`: an empty source range contributes nothing (0 / 0 are no-ops in k_sview_accumulate)
+      oa[t] = cnt > 0 ? acc / cnt : 0.0f;
+      oc[t] = cnt > 0 ? 1.0f : 0.0f;
+    }
+  } else if (lead) {
+    // ---- histogram mode (Scanner.cpp:187-237); the counts are not used there
+    double rel_bw = (fmax - fmin) / g.freq_range;
+    double f_start = (fmin - g.freq_min) / g.freq_range;
+    double f_end = (fmax - g.freq_min) / g.freq_range;
+    f_start *= g.spectrum_size; f_end *= g.spectrum_size; rel_bw *= g.spectrum_size;
+    unsigned j = f_start < 0 ? 0u : (unsigned) f_start;
+    if (j > g.spectrum_size - 1) j = g.spectrum_size - 1;
+    const float inv = (float) (1. / src_size);
+    float accum = 0;
+    for (unsigned i = 0; i < src_size; ++i) accum += src_acc[i];
+    accum *= inv;
+    *j0_out = (int) j;
+    if (floor(f_start) != floor(f_end)) {
+      const float t = (float) ((f_start - floor(f_start)) / rel_bw);
+      oc[0] = 1 - t; oa[0] = (1 - t) * accum;
+      if (j + 1 < g.spectrum_size) { oc[1] = t; oa[1] = t * accum; *nb_out = 2; }
+      else *nb_out = 1;
+    } else {
+      oc[0] = 1; oa[0] = accum; *nb_out = 1;
+    }
+  }
+}
+
+cudaError_t sdb_launch_sview_project_view(cudaStream_t s, double freq_min, double freq_range, unsigned spectrum_size,
+                                          const float *src_acc, const float *src_cnt, unsigned src_size, double fmin,
+                                          double fmax, int *j0, int *nb, float *va, float *vc)
+{
+  SviewGeom g{ freq_min, freq_range, 0.0, 0.0f, spectrum_size };
+  k_sview_project_view<<<(spectrum_size + 255) / 256, 256, 0, s>>>(g, src_acc, src_cnt, src_size, fmin, fmax, j0, nb,
+                                                                  va, vc);
+  return cudaGetLastError();
+}
+
 // one thread per destination bin: contributions in hop order + the count > 5 forgetting rule that
 // interpolate() applies after every feed (Scanner.cpp:77-81).
 __global__ void k_sview_accumulate(unsigned spectrum_size, const int *__restrict__ j0, const int *__restrict__ nb,

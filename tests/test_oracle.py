@@ -335,11 +335,18 @@ def _sview_literal(fmin, fmax, feeds, rel_bw=0.5):
     psd = np.zeros(65536, f32)
     acc = np.zeros(65536, f32)
     cnt = np.zeros(65536, f32)
-    for data, center, fftbw in feeds:
+    for feed in feeds:
+        if isinstance(feed[0], str):                     # ("view", psdAccum, psdCount, freqMin, freqMax) of another
+            _, data, count, lo, hi = feed                # view: SpectrumView::feed(SpectrumView const &), :276-286
+            adjust = False
+        else:
+            data, center, fftbw = feed
+            count, adjust = None, True
+            lo, hi = center - fftbw / 2, center + fftbw / 2
         psize = len(data)
-        lo, hi = center - fftbw / 2, center + fftbw / 2
         inp_bw = hi - lo
-        skip = int(f32(0.5) * (f32(1) - f32(rel_bw)) * f32(psize))
+        assert (hi - lo) / rng_ * size >= 2              # linear mode only
+        skip = int(f32(0.5) * (f32(1) - f32(rel_bw)) * f32(psize)) if adjust else 0
         fskip = float(skip) / psize * inp_bw
         bw = inp_bw - 2 * fskip
         fft_count = rng_ / bw
@@ -359,7 +366,7 @@ def _sview_literal(fmin, fmax, feeds, rel_bw=0.5):
             c = f32(0)
             for i in range(a, b):
                 s = f32(s + data[i])
-                c = f32(c + f32(1))
+                c = f32(c + (f32(1) if count is None else count[i]))
             if c > 0:
                 acc[j] = f32(acc[j] + f32(s / c))
                 cnt[j] = f32(cnt[j] + f32(1))
@@ -419,6 +426,56 @@ def test_spectrum_view_matches_literal_transcription(oracle):
     assert np.array_equal(gcnt, cnt)
     assert np.array_equal(got.view(np.uint32), psd.view(np.uint32))
     L.sdo_sview_free(C.byref(v))
+
+
+def _zoom_case():
+    """Scanner::setViewRange (Panoramic/Scanner.cpp:444-487): sweep a wide range, zoom into a part of it -- the new
+    view is seeded with feed(previous view) -- keep sweeping there, then zoom out again."""
+    wide, narrow, fftbw, psize = (400e6, 460e6), (417.3e6, 431.9e6), 2e6, 1024
+    rng = np.random.default_rng(23)
+
+    def hops(lo, hi, n):
+        cs = lo + (hi - lo) * (np.arange(n) + 0.5) / n
+        return [((rng.random(psize).astype(np.float32) * 20 - 100), float(c), fftbw) for c in cs]
+    return wide, narrow, fftbw, psize, hops(*wide, 45), hops(*narrow, 25), hops(*wide, 10)
+
+
+def test_spectrum_view_zoom_feeds_previous_view(oracle):
+    """SpectrumView::feed(SpectrumView const &) (Scanner.cpp:276-286) against the literal transcription, both ways"""
+    L = oracle.lib()
+    L.sdo_sview_feed_view.argtypes = [C.c_void_p, C.c_void_p]
+    wide, narrow, fftbw, psize, h1, h2, h3 = _zoom_case()
+    views = [oracle.SpectrumView(), oracle.SpectrumView(), oracle.SpectrumView()]
+    for v, r in zip(views, (wide, narrow, wide)):
+        assert L.sdo_sview_init(C.byref(v)) == 0
+        L.sdo_sview_set_range(C.byref(v), *r)
+        v.fft_bandwidth = fftbw
+
+    def arr(p, n):
+        return np.ctypeslib.as_array(p, shape=(65536,))[:n].copy()
+    for d, c, _ in h1:
+        L.sdo_sview_feed(C.byref(views[0]), oracle.ptr(d), None, psize, c, 1)
+    _, a0, c0, s0 = _sview_literal(*wide, h1)
+    assert views[0].spectrum_size == s0
+    L.sdo_sview_feed_view(C.byref(views[1]), C.byref(views[0]))                      # zoom in
+    for d, c, _ in h2:
+        L.sdo_sview_feed(C.byref(views[1]), oracle.ptr(d), None, psize, c, 1)
+    p1, a1, c1, s1 = _sview_literal(*narrow, [("view", a0, c0, wide[0], wide[1])] + h2)
+    assert views[1].spectrum_size == s1 and s1 < s0
+    assert np.array_equal(arr(views[1].psd_count, s1), c1)
+    assert np.array_equal(arr(views[1].psd, s1).view(np.uint32), p1.view(np.uint32))
+    assert np.array_equal(arr(views[1].psd_accum, s1).view(np.uint32), a1.view(np.uint32))
+    L.sdo_sview_feed_view(C.byref(views[2]), C.byref(views[1]))                      # zoom out: detail into wide
+    for d, c, _ in h3:
+        L.sdo_sview_feed(C.byref(views[2]), oracle.ptr(d), None, psize, c, 1)
+    p2, a2, c2, s2 = _sview_literal(*wide, [("view", a1, c1, narrow[0], narrow[1])] + h3)
+    assert np.array_equal(arr(views[2].psd_count, s2), c2)
+    assert np.array_equal(arr(views[2].psd, s2).view(np.uint32), p2.view(np.uint32))
+    inside = (np.arange(s2) * (wide[1] - wide[0]) / s2 + wide[0] > narrow[0] + 1e6) & \
+             (np.arange(s2) * (wide[1] - wide[0]) / s2 + wide[0] < narrow[1] - 1e6)
+    assert np.all(c2[inside] >= 1)                                                   # the detail landed there
+    for v in views:
+        L.sdo_sview_free(C.byref(v))
 
 
 # ---------------------------------------------------------------- C-ABI surface --------------------
