@@ -273,6 +273,20 @@ int  sdb_task_sample_zero_crossing(const sdb_complex *src, size_t n, size_t batc
  * n <= 2^20 */
 int  sdb_task_carrier_detect(const sdb_complex *src, size_t n, size_t batch, double avg_rel_bw,
                              double dc_notch_rel_bw, float *peak);
+/* SNR estimator the inspector tab runs on its decision-space histogram (Misc/SNREstimator.cpp:30-169,
+ * include/SNREstimator.h; fed at Default/GenericInspector/InspectorUI.cpp:822-836): a comb of 2^bps Gaussians of
+ * width sigma fitted to the normalised histogram, one gradient step per feed.  A batch of estimators (one per
+ * inspector), histories of `length` bins each. */
+typedef struct sdb_snr_estimator sdb_snr_estimator_t;
+sdb_snr_estimator_t *sdb_snr_estimator_new(uint32_t n_estimators, uint32_t length, int device);
+void sdb_snr_estimator_destroy(sdb_snr_estimator_t *e);
+int  sdb_snr_estimator_set_bps(sdb_snr_estimator_t *e, uint32_t index, uint32_t bps);     /* restarts sigma at 1/8 */
+int  sdb_snr_estimator_set_alpha(sdb_snr_estimator_t *e, uint32_t index, float alpha);
+int  sdb_snr_estimator_set_sigma(sdb_snr_estimator_t *e, uint32_t index, float sigma);
+int  sdb_snr_estimator_feed(sdb_snr_estimator_t *e, const uint32_t *histories /* host, [n][length] */);
+/* sigma[n], snr[n] = 1 / (2^bps sigma), model[n][length]; any of them may be NULL */
+int  sdb_snr_estimator_read(sdb_snr_estimator_t *e, float *sigma, float *snr, float *model);
+
 /* Decider over sampler output (Default/GenericInspector/InspectorUI.cpp:836-846; Tasks/WaveSampler.cpp:316-317):
  * mode 0 = argument on [min, max), 1 = modulus; sym[i] in [0, 2^bps) */
 int  sdb_task_decide(const sdb_complex *soft, uint8_t *sym, size_t n, int mode, unsigned bps, float min, float max);

@@ -416,6 +416,17 @@ size_t sdo_sample_manual(const sdo_cpx *x, size_t n, int space, size_t symbol_sy
 size_t sdo_sample_zero_crossing(const sdo_cpx *x, size_t n, int space, int amplitude, sdo_cpx threshold,
                                 sdo_cpx zc_angle, float bnor, uint8_t *sym, size_t cap);
 float  sdo_carrier_detect(const sdo_cpx *x, size_t n, double avg_rel_bw, double dc_notch_rel_bw);
+/* SNR estimator on the decision-space histogram (Misc/SNREstimator.cpp:30-169; SPEC Y.7) */
+typedef struct {
+  float    sigma, alpha, hx, delta;
+  unsigned bps, intervals, length;
+  float   *gaussian, *hi, *htilde;
+} sdo_snr_estimator;
+void   sdo_snr_init(sdo_snr_estimator *e);
+void   sdo_snr_free(sdo_snr_estimator *e);
+void   sdo_snr_set_bps(sdo_snr_estimator *e, unsigned bps);
+void   sdo_snr_feed(sdo_snr_estimator *e, const unsigned *history, unsigned n);
+float  sdo_snr_get(const sdo_snr_estimator *e);
 
 /* multi-threaded CPU baseline: S independent streams, each n samples, same params (OpenMP). */
 double sdo_baseline_run(const sdo_an_params *p, const sdo_cpx *x, size_t n_streams, size_t n,

@@ -198,3 +198,101 @@ float sdo_carrier_detect(const sdo_cpx *x, size_t n, double avg_rel_bw, double d
   sdo_spec_plan_free(&plan);
   return sdo_atan2f(acc.im, acc.re);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * SNR estimator of the inspector's histogram (Misc/SNREstimator.cpp:30-169, include/SNREstimator.h): a
+ * comb of 2^bps Gaussians of width sigma on the unit circle is fitted to the normalised histogram by
+ * one gradient step per feed.  expf(t) is SPEC M's 10^(t log10 e).
+ * ---------------------------------------------------------------------------------------------- */
+static float snr_expf(float t) { return sdo_exp10f(t * 0.4342944819032518f); }
+
+void sdo_snr_init(sdo_snr_estimator *e)
+{
+  memset(e, 0, sizeof *e);
+  e->sigma = 1.f / 8.f;                       /* SNR_ESTIMATOR_DEFAULT_SIGMA */
+  e->alpha = 1.f;                             /* SNR_ESTIMATOR_DEFAULT_ALPHA */
+}
+
+void sdo_snr_free(sdo_snr_estimator *e)
+{
+  free(e->gaussian); free(e->hi); free(e->htilde);
+  memset(e, 0, sizeof *e);
+}
+
+/* setBps, SNREstimator.cpp:122-131 */
+void sdo_snr_set_bps(sdo_snr_estimator *e, unsigned bps)
+{
+  if (e->bps != bps) {
+    e->bps = bps;
+    e->sigma = 1.f / 8.f;
+    e->intervals = 1u << bps;
+    e->hx = 1.f / e->length;
+  }
+}
+
+/* recalculateModel, SNREstimator.cpp:30-78 */
+static void snr_model(sdo_snr_estimator *e)
+{
+  unsigned i, j;
+  float x, max = 0, intlen, start, sigma2 = e->sigma * e->sigma;
+  if (!(e->length > 0 && e->intervals > 0)) return;
+  for (i = 0; i < e->length; ++i) {
+    x = i * e->hx;
+    if (x >= .5f) x -= 1.f;
+    e->gaussian[i] = snr_expf(-x * x / sigma2);
+  }
+  intlen = 1.f / e->intervals;
+  start = .5f * intlen;
+  for (i = 0; i < e->length; ++i) e->hi[i] = 0.f;
+  for (j = 0; j < e->intervals; ++j) {
+    float skip = start + j * intlen;
+    float t = 1.f - (skip - floorf(skip));
+    unsigned skipint = (unsigned) floorf(e->length * skip), i1, i2;
+    for (i = 0; i < e->length; ++i) {
+      i1 = (unsigned) (e->length + i - skipint) % e->length;
+      i2 = (unsigned) (e->length + i1 - 1) % e->length;
+      e->hi[i] += t * e->gaussian[i1];
+      e->hi[i] += (1 - t) * e->gaussian[i2];
+    }
+  }
+  for (i = 0; i < e->length; ++i) if (e->hi[i] > max) max = e->hi[i];
+  if (max > 0.f) for (i = 0; i < e->length; ++i) e->hi[i] /= max;
+}
+
+/* feed + iterate, SNREstimator.cpp:80-120,133-158 */
+void sdo_snr_feed(sdo_snr_estimator *e, const unsigned *history, unsigned n)
+{
+  unsigned i, j, max = 0;
+  if (e->length != n) {
+    e->length = n;
+    e->gaussian = realloc(e->gaussian, n * sizeof(float));
+    e->hi = realloc(e->hi, n * sizeof(float));
+    e->htilde = realloc(e->htilde, n * sizeof(float));
+    e->hx = 1.f / e->length;
+  }
+  for (i = 0; i < n; ++i) if (max < history[i]) max = history[i];
+  if (max == 0) max = 1;
+  for (i = 0; i < n; ++i) e->htilde[i] = (float) history[i] / max;
+  if (e->length > 0 && e->intervals > 0) {
+    float delta = 0, x, term, intlen, start, skip;
+    float sigmainv = 1.f / e->sigma, sigma3inv = sigmainv * sigmainv * sigmainv;
+    snr_model(e);
+    intlen = 1.f / e->intervals;
+    start = .5f * intlen;
+    for (i = 0; i < e->length; ++i) {
+      x = i * e->hx;
+      if (x >= .5f) x -= 1.f;
+      term = 0;
+      for (j = 0; j < e->intervals; ++j) {
+        skip = start + j * intlen;
+        term += (x - skip) * (x - skip);
+      }
+      term *= (e->hi[i] - e->htilde[i]) / sigma3inv;
+      delta += term;
+    }
+    e->delta = delta / e->length;
+    e->sigma += -e->alpha * e->delta;
+  }
+}
+
+float sdo_snr_get(const sdo_snr_estimator *e) { return 1.f / (e->intervals * e->sigma); }

@@ -343,6 +343,13 @@ _PROTOS = {
                                         C.c_void_p]),
     "sdb_inspector_forward": (C.c_long, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sdb_psd_shift_db_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
+    "sdb_snr_estimator_new": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_int]),
+    "sdb_snr_estimator_destroy": (None, [C.c_void_p]),
+    "sdb_snr_estimator_set_bps": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "sdb_snr_estimator_set_alpha": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float]),
+    "sdb_snr_estimator_set_sigma": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float]),
+    "sdb_snr_estimator_feed": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_snr_estimator_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdb_averager_new": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_float, C.c_int]),
     "sdb_averager_destroy": (None, [C.c_void_p]),
     "sdb_averager_set_alpha": (C.c_int, [C.c_void_p, C.c_float]),
@@ -715,6 +722,45 @@ def inspector_run(cls, fs, x, **kw):
     _check(L.sdb_task_inspector(C.byref(cfg), x.ctypes.data, n, batch, soft.ctypes.data, hard.ctypes.data,
                                 counts.ctypes.data, cap))
     return [(soft[b, :counts[b]].copy(), hard[b, :counts[b]].copy()) for b in range(batch)]
+
+
+class SnrEstimator:
+    """Batch of the inspector tab's SNR estimators (Misc/SNREstimator.cpp) on decision-space histograms."""
+
+    def __init__(self, n_estimators, length, device=0):
+        self._L = load_library()
+        self.n, self.length = n_estimators, length
+        self._h = self._L.sdb_snr_estimator_new(n_estimators, length, device)
+        if not self._h:
+            raise SdbError(last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_snr_estimator_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_bps(self, index, bps):
+        _check(self._L.sdb_snr_estimator_set_bps(self._h, index, bps))
+
+    def set_alpha(self, index, alpha):
+        _check(self._L.sdb_snr_estimator_set_alpha(self._h, index, alpha))
+
+    def set_sigma(self, index, sigma):
+        _check(self._L.sdb_snr_estimator_set_sigma(self._h, index, sigma))
+
+    def feed(self, histories):
+        h = np.ascontiguousarray(histories, dtype=np.uint32)
+        assert h.shape == (self.n, self.length)
+        _check(self._L.sdb_snr_estimator_feed(self._h, h.ctypes.data))
+
+    def read(self, model=False):
+        sigma, snr = np.empty(self.n, np.float32), np.empty(self.n, np.float32)
+        m = np.empty((self.n, self.length), np.float32) if model else None
+        _check(self._L.sdb_snr_estimator_read(self._h, sigma.ctypes.data, snr.ctypes.data,
+                                              m.ctypes.data if model else None))
+        return (sigma, snr, m) if model else (sigma, snr)
 
 
 class Averager:

@@ -1594,6 +1594,116 @@ extern "C" int sdb_sview_feed_view(sdb_sview_t *v, const sdb_sview_t *detail)
   return 0;
 }
 
+// ---- SNR estimator on the inspectors' decision-space histograms (Misc/SNREstimator.cpp; SPEC Y.7)
+cudaError_t sdb_launch_snr_feed(cudaStream_t s, const unsigned *history, unsigned length, unsigned n, void *states,
+                                float *gaussian, float *hi, float *htilde, float *term);
+struct SnrHostState { float sigma, alpha, delta; unsigned intervals; };
+struct sdb_snr_estimator {
+  int device = 0; unsigned n = 0, length = 0;
+  std::vector<SnrHostState> st; std::vector<unsigned> bps;
+  bool dirty = true;                       // host copy of the states newer than the device copy
+  unsigned *d_hist = nullptr; void *d_states = nullptr; float *d_work = nullptr;   // gaussian | hi | htilde | term
+};
+
+extern "C" sdb_snr_estimator_t *sdb_snr_estimator_new(uint32_t n_estimators, uint32_t length, int device)
+{
+  if (sdb_device_count() <= 0) { g_err = "no CUDA device: sigdigger_b200 has no CPU fallback"; return nullptr; }
+  if (n_estimators == 0 || length == 0) { g_err = "snr estimator: empty geometry"; return nullptr; }
+  CKP(cudaSetDevice(device));
+  sdb_snr_estimator *e = new sdb_snr_estimator();
+  e->device = device; e->n = n_estimators; e->length = length;
+  e->st.assign(n_estimators, SnrHostState{ 1.f / 8.f, 1.f, 0.f, 0u });   // SNR_ESTIMATOR_DEFAULT_SIGMA / _ALPHA
+  e->bps.assign(n_estimators, 0u);
+  const size_t tot = (size_t) n_estimators * length;
+  if (cudaMalloc(&e->d_hist, tot * sizeof(unsigned)) != cudaSuccess ||
+      cudaMalloc(&e->d_states, n_estimators * sizeof(SnrHostState)) != cudaSuccess ||
+      cudaMalloc(&e->d_work, 4 * tot * sizeof(float)) != cudaSuccess) {
+    cudaFree(e->d_hist); cudaFree(e->d_states); cudaFree(e->d_work);
+    g_err = "out of device memory"; delete e; return nullptr;
+  }
+  cudaMemset(e->d_work, 0, 4 * tot * sizeof(float));
+  return e;
+}
+
+extern "C" void sdb_snr_estimator_destroy(sdb_snr_estimator_t *e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->d_hist); cudaFree(e->d_states); cudaFree(e->d_work);
+  delete e;
+}
+
+static int snr_pull(sdb_snr_estimator *e)
+{
+  if (e->dirty) return 0;
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy(e->st.data(), e->d_states, e->n * sizeof(SnrHostState), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// setBps (SNREstimator.cpp:122-131): a change of bps restarts sigma
+extern "C" int sdb_snr_estimator_set_bps(sdb_snr_estimator_t *e, uint32_t index, uint32_t bps)
+{
+  if (!e || index >= e->n) return fail("wrong estimator index");
+  if (bps > 8) return fail("bps out of range");
+  if (snr_pull(e)) return -1;
+  if (e->bps[index] != bps || e->st[index].intervals == 0) {
+    e->bps[index] = bps; e->st[index].sigma = 1.f / 8.f; e->st[index].intervals = 1u << bps;
+  }
+  e->dirty = true;
+  return 0;
+}
+
+extern "C" int sdb_snr_estimator_set_alpha(sdb_snr_estimator_t *e, uint32_t index, float alpha)
+{
+  if (!e || index >= e->n) return fail("wrong estimator index");
+  if (snr_pull(e)) return -1;
+  e->st[index].alpha = alpha; e->dirty = true;
+  return 0;
+}
+
+extern "C" int sdb_snr_estimator_set_sigma(sdb_snr_estimator_t *e, uint32_t index, float sigma)
+{
+  if (!e || index >= e->n) return fail("wrong estimator index");
+  if (snr_pull(e)) return -1;
+  e->st[index].sigma = sigma; e->dirty = true;
+  return 0;
+}
+
+// feed (SNREstimator.cpp:133-158) for every estimator: histories [n][length] counts, host memory
+extern "C" int sdb_snr_estimator_feed(sdb_snr_estimator_t *e, const uint32_t *histories)
+{
+  if (!e || !histories) return fail("null argument");
+  CK(cudaSetDevice(e->device));
+  const size_t tot = (size_t) e->n * e->length;
+  if (e->dirty) {
+    CK(cudaMemcpy(e->d_states, e->st.data(), e->n * sizeof(SnrHostState), cudaMemcpyHostToDevice));
+    e->dirty = false;
+  }
+  CK(cudaMemcpy(e->d_hist, histories, tot * sizeof(unsigned), cudaMemcpyHostToDevice));
+  CK(sdb_launch_snr_feed(0, e->d_hist, e->length, e->n, e->d_states, e->d_work, e->d_work + tot, e->d_work + 2 * tot,
+                         e->d_work + 3 * tot));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// getSigma / getSNR (include/SNREstimator.h:74-84) and getModel (:61-65); any pointer may be NULL
+extern "C" int sdb_snr_estimator_read(sdb_snr_estimator_t *e, float *sigma, float *snr, float *model)
+{
+  if (!e) return fail("null argument");
+  if (snr_pull(e)) return -1;
+  for (unsigned i = 0; i < e->n; ++i) {
+    if (sigma) sigma[i] = e->st[i].sigma;
+    if (snr) snr[i] = 1.f / (e->st[i].intervals * e->st[i].sigma);
+  }
+  if (model) {
+    const size_t tot = (size_t) e->n * e->length;
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpy(model, e->d_work + tot, tot * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 // ---- spectrum averager (Misc/Averager.cpp:25-60)
 cudaError_t sdb_launch_psd_average(cudaStream_t s, const float *psd, size_t stream_stride, unsigned frames, unsigned n,
                                    size_t n_streams, float alpha, int primed, float *last);

@@ -563,3 +563,41 @@ def decide(soft, mode, bps, vmin, vmax):
     sym = np.empty(len(soft), np.uint8)
     L.sdo_decider_decide(C.byref(d), ptr(soft), ptr(sym), len(soft))
     return sym
+
+
+class SnrEstimatorState(C.Structure):
+    _fields_ = [("sigma", C.c_float), ("alpha", C.c_float), ("hx", C.c_float), ("delta", C.c_float),
+                ("bps", C.c_uint), ("intervals", C.c_uint), ("length", C.c_uint),
+                ("gaussian", c_float_p), ("hi", c_float_p), ("htilde", c_float_p)]
+
+
+class SnrEstimator:
+    """Misc/SNREstimator.cpp restated (oracle/tasks.c)"""
+
+    def __init__(self, bps, length, alpha=1.0, sigma=None):
+        self.L = lib()
+        self.L.sdo_snr_get.restype = C.c_float
+        self.e = SnrEstimatorState()
+        self.L.sdo_snr_init(C.byref(self.e))
+        self.L.sdo_snr_set_bps(C.byref(self.e), bps)      # the length is learnt at the first feed, as in the GUI
+        self.e.alpha = alpha
+        if sigma is not None:
+            self.e.sigma = sigma
+
+    def feed(self, history):
+        h = np.ascontiguousarray(history, np.uint32)
+        self.L.sdo_snr_feed(C.byref(self.e), ptr(h), len(h))
+
+    @property
+    def sigma(self):
+        return float(self.e.sigma)
+
+    @property
+    def snr(self):
+        return float(self.L.sdo_snr_get(C.byref(self.e)))
+
+    def model(self):
+        return np.ctypeslib.as_array(self.e.hi, shape=(self.e.length,)).copy()
+
+    def close(self):
+        self.L.sdo_snr_free(C.byref(self.e))

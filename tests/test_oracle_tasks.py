@@ -119,6 +119,81 @@ def test_zero_crossing_blocks_cap_and_amplitude(oracle):
     assert t2 == total and len(s2) == 10 and np.array_equal(s2, sym[:10])
 
 
+def _snr_literal(history, bps, sigma, alpha):
+    """one SNREstimator::feed (Misc/SNREstimator.cpp:133-158 -> iterate :80-120 -> recalculateModel :30-78),
+    float32 statement by statement, numpy's exp"""
+    f = np.float32
+    L = len(history)
+    n_int = 1 << bps
+    hx = f(1) / f(L)
+    mx = max(int(history.max()), 1)
+    ht = (history.astype(np.float32) / f(mx)).astype(np.float32)
+    sigma = f(sigma)
+    sigma2 = f(sigma * sigma)
+    x = (np.arange(L).astype(np.float32) * hx).astype(np.float32)
+    x = np.where(x >= f(.5), x - f(1), x).astype(np.float32)
+    g = np.exp((-x * x / sigma2).astype(np.float32)).astype(np.float32)
+    intlen = f(1) / f(n_int)
+    start = f(.5) * intlen
+    hi = np.zeros(L, np.float32)
+    idx = np.arange(L)
+    for j in range(n_int):
+        skip = f(start + f(j) * intlen)
+        t = f(f(1) - f(skip - np.floor(skip)))
+        skipint = int(np.floor(f(f(L) * skip)))
+        i1 = (L + idx - skipint) % L
+        i2 = (L + i1 - 1) % L
+        hi = (hi + t * g[i1]).astype(np.float32)
+        hi = (hi + f(f(1) - t) * g[i2]).astype(np.float32)
+    if hi.max() > 0:
+        hi = (hi / hi.max()).astype(np.float32)
+    sinv = f(1) / sigma
+    s3 = f(f(sinv * sinv) * sinv)
+    delta = f(0)
+    for i in range(L):
+        term = f(0)
+        for j in range(n_int):
+            skip = f(start + f(j) * intlen)
+            d = f(x[i] - skip)
+            term = f(term + f(d * d))
+        term = f(term * f(f(hi[i] - ht[i]) / s3))
+        delta = f(delta + term)
+    delta = f(delta / f(L))
+    return f(sigma + f(-f(alpha) * delta)), hi
+
+
+def _histogram(bps, length, sigma, n=200000, seed=0):
+    rng = np.random.default_rng(seed)
+    k = 1 << bps
+    centres = (rng.integers(0, k, n) + 0.5) / k
+    v = (centres + sigma * rng.standard_normal(n)) % 1.0
+    return np.bincount((v * length).astype(int) % length, minlength=length).astype(np.uint32)
+
+
+def test_snr_estimator_matches_literal_and_converges(oracle):
+    for bps, length in ((1, 256), (2, 256), (3, 400)):
+        h = _histogram(bps, length, 0.03, seed=bps)
+        e = oracle.SnrEstimator(bps, length, alpha=1.0)
+        sigma = 1.0 / 8
+        for it in range(4):
+            want, hi = _snr_literal(h, bps, sigma, 1.0)
+            e.feed(h)
+            assert abs(e.sigma - want) <= 2e-5 * abs(want), (bps, it)
+            assert np.abs(e.model() - hi).max() < 2e-5
+            sigma = e.sigma                                   # keep the literal on the oracle's trajectory
+        assert e.snr == pytest.approx(1.0 / ((1 << bps) * e.sigma), rel=1e-6)
+        e.close()
+    # the fit moves sigma towards the histogram's true width (gradient descent on the model error)
+    h = _histogram(2, 256, 0.02, seed=9)
+    e = oracle.SnrEstimator(2, 256, alpha=0.05)
+    s0 = e.sigma
+    for _ in range(300):
+        e.feed(h)
+    assert abs(e.sigma - 0.02 * np.sqrt(2)) < abs(s0 - 0.02 * np.sqrt(2))
+    assert 0.02 < e.sigma < s0          # slowly: the step carries a factor sigma^3 (`/ sigma3inv`, :110)
+    e.close()
+
+
 def test_carrier_detect_finds_tone(oracle):
     rng = np.random.default_rng(6)
     for n, f in ((1000, 0.0371), (4096, -0.21), (50000, 0.3003)):
