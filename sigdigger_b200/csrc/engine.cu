@@ -1647,7 +1647,7 @@ extern "C" int sdb_snr_estimator_set_bps(sdb_snr_estimator_t *e, uint32_t index,
   if (!e || index >= e->n) return fail("wrong estimator index");
   if (bps > 8) return fail("bps out of range");
   if (snr_pull(e)) return -1;
-  if (e->bps[index] != bps || e->st[index].intervals == 0) {
+  if (e->bps[index] != bps) {                  // as the reference: setBps(0) on a fresh estimator leaves it idle
     e->bps[index] = bps; e->st[index].sigma = 1.f / 8.f; e->st[index].intervals = 1u << bps;
   }
   e->dirty = true;
