@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_FFT = 65536
-FS = 100e6
+FS_BY = {"cfg2": 100e6, "cfg3": 200e6}
+FS = 100e6     # replaced per workload in main()
 B_ALG = {"cfg2": 12.09, "cfg3": 14.41}     # BASELINE.md section 3, bytes per input sample
 
 
@@ -249,9 +250,9 @@ def run_reference(args):
 
 def workload_config(args, streams, hops):
     k = len(workload_channels(args.workload))
-    return {"workload": "%s: fs 100 MS/s nominal, 65536-pt Blackman-Harris PSD every frame + 65536-pt "
+    return {"workload": "%s: fs %g MS/s nominal, 65536-pt Blackman-Harris PSD every frame + 65536-pt "
                         "50%%-overlap FFT channeliser + %d inspector(s) (%s), Costas + RRC + Gardner + decision"
-                        % (args.workload, k, "QPSK 1 MBd" if args.workload == "cfg2" else "2-FSK / QPSK / ASK mix"),
+                        % (args.workload, FS / 1e6, k, "QPSK 1 MBd" if args.workload == "cfg2" else "2-FSK / QPSK / ASK mix"),
             "streams_per_gpu": streams, "samples_per_stream_per_step": hops * N_FFT // 2,
             "inputs": "larger than L2 (no flush needed)", "parallelism": "independent streams per GPU"}
 
@@ -512,13 +513,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3"])
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--hops", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-formats", action="store_true")
     args = ap.parse_args()
+    global FS
+    FS = FS_BY[args.workload]
     if args.streams == 0:
         # cfg2: the (latency-bound) inspector kernel of 1024 single-channel streams takes about as long as their
         # transforms; 2048 streams put the transforms on the critical path (33.9 / 53.3 / 64.5 GS/s at 512 / 1024 /

@@ -19,6 +19,7 @@
 #include "../../include/sigdigger_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
@@ -112,7 +113,7 @@ struct sdb_analyzer {
   void drop_subs() { for (auto &s : subs) if (s.eng) sdb_engine_destroy(s.eng); subs.clear(); }
   bool plan_dirty = true;
   size_t block = 0;
-  double measured_rate = 0;
+  std::atomic<double> measured_rate{ 0.0 };   // written by the worker, read by sdb_analyzer_get_measured_samp_rate
   uint64_t total_samples = 0;
   double psd_credit = 0;
   // source-side options of the worker loop (Suscan/Analyzer.cpp:117-135, 229-244; SourceWidget.cpp:1156-1184)
@@ -485,6 +486,7 @@ struct sdb_analyzer {
         ep.n_streams = (uint32_t) HB; ep.psd_size = (uint32_t) N; ep.psd_window = params.detector_params.window;
         ep.max_feed = (uint32_t) N; ep.device = src.device;
         ep.flags = iq_reverse ? SDB_FLAG_IQ_REVERSE : 0;
+        ep.input_format = src.read ? SDB_FORMAT_FLOAT32 : src.input_format;   // in-memory captures keep their format
         eng = sdb_engine_new(&ep, src.samp_rate);
         if (!eng || sdb_engine_commit(eng)) {
           post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error());
@@ -492,7 +494,12 @@ struct sdb_analyzer {
         }
         plan_dirty = false;
       }
+      // hops are packed back to back in the source's native sample format: bps bytes per IQ pair
+      const size_t bps = src.read || src.input_format == SDB_FORMAT_FLOAT32 ? 8
+                         : src.input_format == SDB_FORMAT_SIGNED16 ? 4 : 2;
+      unsigned char *bytes = nullptr;
       buf.resize(HB * N);
+      bytes = reinterpret_cast<unsigned char *>(buf.data());
       size_t got_hops = 0;
       bool eos = false, err = false;
       for (size_t h = 0; h < HB && !eos && !err; ++h) {
@@ -506,12 +513,13 @@ struct sdb_analyzer {
           left -= take;
         }
         if (eos || err) break;
-        const long g = source_read(buf.data() + h * N, N);
+        const long g = source_read(reinterpret_cast<sdb_complex *>(bytes + h * N * bps), N);
         if (g < 0) err = true; else if ((size_t) g < N) eos = true; else ++got_hops;
       }
       if (err) { exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break; }
       if (got_hops) {
-        for (size_t h = got_hops; h < HB; ++h) memset(buf.data() + h * N, 0, N * sizeof(sdb_complex));
+        for (size_t h = got_hops; h < HB; ++h)
+          memset(bytes + h * N * bps, src.input_format == SDB_FORMAT_UNSIGNED8 && !src.read ? 0x80 : 0, N * bps);
         if (sdb_engine_feed_host(eng, buf.data(), N, N) || sdb_engine_sync(eng)) {
           exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break;
         }
@@ -520,7 +528,7 @@ struct sdb_analyzer {
         for (size_t h = 0; h < got_hops; ++h) {
           sdb_analyzer_psd_msg *m = (sdb_analyzer_psd_msg *) calloc(1, sizeof(*m));
           m->fc = (int64_t) llround(fcs[h]); m->samp_rate = (float) src.samp_rate;
-          m->measured_samp_rate = (float) measured_rate;
+          m->measured_samp_rate = (float) measured_rate.load();
           gettimeofday(&m->rt_time, nullptr);
           m->psd_size = N;
           m->psd_data = (float *) malloc(N * sizeof(float));
@@ -601,7 +609,7 @@ struct sdb_analyzer {
         if (due > now) std::this_thread::sleep_for(std::chrono::duration<double>(due - now));
       }
       double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      measured_rate = el > 0 ? (double) total_samples / el : 0;
+      measured_rate.store(el > 0 ? (double) total_samples / el : 0);
       // PSD messages at psd_update_int cadence of SIGNAL time (coverage = N / (fs * interval))
       const size_t frames = block / N;
       psd.resize(frames * N);
@@ -612,7 +620,7 @@ struct sdb_analyzer {
           if (psd_credit + 1e-12 >= params.psd_update_int) {
             psd_credit = params.psd_update_int > 0 ? fmod(psd_credit, params.psd_update_int) : 0;
             sdb_analyzer_psd_msg *m = (sdb_analyzer_psd_msg *) calloc(1, sizeof(*m));
-            m->fc = (int64_t) src.freq; m->samp_rate = (float) src.samp_rate; m->measured_samp_rate = (float) measured_rate;
+            m->fc = (int64_t) src.freq; m->samp_rate = (float) src.samp_rate; m->measured_samp_rate = (float) measured_rate.load();
             gettimeofday(&m->rt_time, nullptr);
             double ts = (double) (total_samples - block + f * N) / src.samp_rate;
             m->timestamp.tv_sec = (time_t) ts; m->timestamp.tv_usec = (suseconds_t) ((ts - floor(ts)) * 1e6);
@@ -921,4 +929,4 @@ extern "C" int sdb_analyzer_set_params_async(sdb_analyzer_t *a, const sdb_analyz
   return push_cmd(a, std::move(c));
 }
 extern "C" uint64_t sdb_analyzer_get_samp_rate(const sdb_analyzer_t *a) { return a ? (uint64_t) a->src.samp_rate : 0; }
-extern "C" float sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a) { return a ? (float) a->measured_rate : 0; }
+extern "C" float sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a) { return a ? (float) a->measured_rate.load() : 0; }

@@ -765,10 +765,9 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
 {
   const int chains = n_channels * n_streams;
   if (chains == 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+  if (sdb_first_on_device(attr_done)) {
     cudaFuncSetAttribute(k_inspectors, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
-    attr_done = true;
   }
   const size_t smem = sizeof(ChainSmem) + (size_t) dyn.mf_slots * 32 * sizeof(float2) +
                       (size_t) dyn.agc_rows * 32 * sizeof(float) +

@@ -212,10 +212,9 @@ extern "C" sdb_chdet_t *sdb_chdet_new(int device, uint32_t n_bins, uint32_t n_st
     cudaMemset(d->d_n0_primed, 0, S * sizeof(int));
     cudaMemset(d->d_count, 0, S * sizeof(unsigned));
     cudaMemset(d->d_total, 0, S * sizeof(unsigned));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+    if (sdb_first_on_device(attr_done)) {
       cudaFuncSetAttribute(k_chdet_find, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CHDET_MAXRAW * (int) sizeof(int));
-      attr_done = true;
     }
   }
   if (!ok || cudaGetLastError() != cudaSuccess) { sdb_chdet_destroy(d); return nullptr; }

@@ -1459,7 +1459,7 @@ cudaError_t sdb_launch_sview_project(cudaStream_t s, double freq_min, double fre
                                      float *va, float *vc, int max_bins);
 cudaError_t sdb_launch_sview_accumulate(cudaStream_t s, unsigned spectrum_size, const int *j0, const int *nb,
                                         const float *va, const float *vc, int n_hops, int max_bins, float *psd,
-                                        float *accum, float *count);
+                                        float *accum, float *count, float *count_snapshot);
 
 struct sdb_sview {
   int device = 0;
@@ -1467,7 +1467,7 @@ struct sdb_sview {
   float rel_bw = 0.5f;                     // include/Scanner.h:70
   unsigned spectrum_size = 65536;          // SIGDIGGER_SCANNER_SPECTRUM_SIZE
   int max_bins = 0;
-  float *d_psd = nullptr, *d_accum = nullptr, *d_count = nullptr;
+  float *d_psd = nullptr, *d_accum = nullptr, *d_count = nullptr, *d_count_snap = nullptr;
   size_t hop_cap = 0;
   double *d_centers = nullptr; int *d_j0 = nullptr, *d_nb = nullptr; float *d_va = nullptr, *d_vc = nullptr;
 };
@@ -1480,7 +1480,7 @@ extern "C" sdb_sview_t *sdb_sview_new(int device)
   v->device = device;
   const size_t n = 65536 * sizeof(float);
   if (cudaMalloc(&v->d_psd, n) != cudaSuccess || cudaMalloc(&v->d_accum, n) != cudaSuccess ||
-      cudaMalloc(&v->d_count, n) != cudaSuccess) { g_err = "out of device memory"; delete v; return nullptr; }
+      cudaMalloc(&v->d_count, n) != cudaSuccess || cudaMalloc(&v->d_count_snap, n) != cudaSuccess) { g_err = "out of device memory"; delete v; return nullptr; }
   cudaMemset(v->d_psd, 0, n); cudaMemset(v->d_accum, 0, n); cudaMemset(v->d_count, 0, n);
   return v;
 }
@@ -1489,7 +1489,7 @@ extern "C" void sdb_sview_destroy(sdb_sview_t *v)
 {
   if (!v) return;
   cudaSetDevice(v->device);
-  cudaFree(v->d_psd); cudaFree(v->d_accum); cudaFree(v->d_count); cudaFree(v->d_centers);
+  cudaFree(v->d_psd); cudaFree(v->d_accum); cudaFree(v->d_count); cudaFree(v->d_count_snap); cudaFree(v->d_centers);
   cudaFree(v->d_j0); cudaFree(v->d_nb); cudaFree(v->d_va); cudaFree(v->d_vc);
   delete v;
 }
@@ -1587,7 +1587,8 @@ extern "C" int sdb_sview_feed_view(sdb_sview_t *v, const sdb_sview_t *detail)
     e = sdb_launch_sview_project_view(0, v->freq_min, v->freq_range, v->spectrum_size, detail->d_accum, detail->d_count,
                                       detail->spectrum_size, detail->freq_min, detail->freq_max, j0, nb, va, vc);
   if (e == cudaSuccess)
-    e = sdb_launch_sview_accumulate(0, v->spectrum_size, j0, nb, va, vc, 1, 65536, v->d_psd, v->d_accum, v->d_count);
+    e = sdb_launch_sview_accumulate(0, v->spectrum_size, j0, nb, va, vc, 1, 65536, v->d_psd, v->d_accum, v->d_count,
+                                    v->d_count_snap);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaFree(j0); cudaFree(nb); cudaFree(va); cudaFree(vc);
   if (e != cudaSuccess) return fail(std::string("sdb_sview_feed_view: ") + cudaGetErrorString(e));
@@ -1804,7 +1805,7 @@ extern "C" int sdb_sview_accumulate(sdb_sview_t *v, const int32_t *j0, const int
   if (!v) return fail("null view");
   CK(cudaSetDevice(v->device));
   CK(sdb_launch_sview_accumulate(0, v->spectrum_size, j0, nb, va, vc, (int) n_hops, v->max_bins, v->d_psd, v->d_accum,
-                                 v->d_count));
+                                 v->d_count, v->d_count_snap));
   return 0;
 }
 

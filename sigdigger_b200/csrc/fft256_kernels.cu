@@ -212,11 +212,10 @@ cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
   p.binmap = a.binmap; p.cspec = a.cspec; p.n_bins = a.n_bins; p.tw256 = fs.twN2;
   p.ka_mask = a.ka_mask ? a.ka_mask : 0xffffu;
   const size_t smem = (size_t) 32 * LDR * sizeof(float2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+  if (sdb_first_on_device(attr_done)) {
     cudaFuncSetAttribute(k_rows256<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(k_rows256<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    attr_done = true;
   }
   dim3 grid(8, a.n_windows);
   if (mode == 0) k_rows256<0><<<grid, 512, smem, c.stream>>>(p);

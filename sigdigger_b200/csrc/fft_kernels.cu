@@ -166,10 +166,9 @@ cudaError_t sdb_launch_pass_a_range(const SdbLaunchCtx &c, const SdbFourStep &fs
   p.CW = cw;
   const int threads = cw * (fs.N1 / 4);
   const size_t smem = (size_t) cw * (fs.N1 + 1) * sizeof(float2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+  if (sdb_first_on_device(attr_done)) {
     cudaFuncSetAttribute(k_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_done = true;
   }
   dim3 grid(fs.N2 / cw, n_win);
   k_pass_a<<<grid, threads, smem, c.stream>>>(p);
@@ -244,11 +243,10 @@ static cudaError_t launch_pass_b(const SdbLaunchCtx &c, const SdbFourStep &fs, c
   p.RW = rw;
   const int threads = rw * (fs.N2 / 4);
   const size_t smem = (size_t) rw * (fs.N2 + 1) * sizeof(float2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+  if (sdb_first_on_device(attr_done)) {
     cudaFuncSetAttribute(k_pass_b<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_done = true;
   }
   dim3 grid(fs.N1 / rw, a.n_windows);
   if (mode == 0) k_pass_b<0><<<grid, threads, smem, c.stream>>>(p);
@@ -573,12 +571,11 @@ cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDe
                                        float2 *tails, size_t tail_stream_stride, float *lo_phase,
                                        float2 *chan_out, size_t chan_stream_stride)
 {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+  if (sdb_first_on_device(attr_done)) {
     cudaFuncSetAttribute(k_chan_ifft<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_chan_ifft<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_chan_ifft<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   const size_t smem = (size_t) size * sizeof(float2) + (size_t) (size / 2) * sizeof(float2)
                       + (size_t) (size / 2) * sizeof(float);

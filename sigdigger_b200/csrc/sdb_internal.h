@@ -5,6 +5,18 @@
 #include <stdint.h>
 #include <stddef.h>
 #include "sdb_iq.h"
+#ifdef __cplusplus
+#include <atomic>
+// cudaFuncSetAttribute applies to the CURRENT device: a process that drives several GPUs (one GUI process, two
+// analyzers) must set it once per device, not once per process.  Returns true the first time on each device.
+static inline bool sdb_first_on_device(std::atomic<unsigned long long> &mask)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit) & bit) == 0;
+}
+#endif
 
 #define SDB_MAX_FIR      1024
 #define SDB_MAX_IIR      5        // coefficients (order <= 4)

@@ -176,12 +176,14 @@ cudaError_t sdb_launch_sview_project_view(cudaStream_t s, double freq_min, doubl
 __global__ void k_sview_accumulate(unsigned spectrum_size, const int *__restrict__ j0, const int *__restrict__ nb,
                                    const float *__restrict__ va, const float *__restrict__ vc, int n_hops,
                                    int max_bins, float *__restrict__ psd, float *__restrict__ accum,
-                                   float *__restrict__ count)
+                                   float *__restrict__ count, const float *__restrict__ count_before)
 {
   const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= spectrum_size) return;
   float a = accum[j], c = count[j], p = psd[j];
-  float cl = j > 0 ? count[j - 1] : 1.0f;     // left neighbour's count: only its emptiness matters
+  // left neighbour's count (only its emptiness matters), from the snapshot taken before this launch: thread j-1
+  // rewrites count[j-1] at the end of the kernel, possibly before this thread starts
+  float cl = j > 0 ? count_before[j - 1] : 1.0f;
   for (int h = 0; h < n_hops; ++h) {
     const int t = (int) j - j0[h], n = nb[h];
     if (t >= 0 && t < n) {
@@ -250,11 +252,15 @@ cudaError_t sdb_launch_sview_project(cudaStream_t s, double freq_min, double fre
 
 cudaError_t sdb_launch_sview_accumulate(cudaStream_t s, unsigned spectrum_size, const int *j0, const int *nb,
                                         const float *va, const float *vc, int n_hops, int max_bins, float *psd,
-                                        float *accum, float *count)
+                                        float *accum, float *count, float *count_snapshot)
 {
-  if (n_hops > 0)
+  if (n_hops > 0) {
+    cudaError_t e = cudaMemcpyAsync(count_snapshot, count, (size_t) spectrum_size * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
     k_sview_accumulate<<<(spectrum_size + 255) / 256, 256, 0, s>>>(spectrum_size, j0, nb, va, vc, n_hops, max_bins,
-                                                                   psd, accum, count);
+                                                                   psd, accum, count, count_snapshot);
+  }
   k_sview_fill<<<1, 32, 0, s>>>(spectrum_size, psd, count);
   return cudaGetLastError();
 }
