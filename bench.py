@@ -194,9 +194,47 @@ def usable_cores():
                                                                "none" if quota is None else "%.1f CPUs" % quota)
 
 
-def cpu_run(name, n_streams, n, threads, reps=1, warm=0):
+_CPU_LIBS = {}
+
+
+def cpu_lib(kind):
+    """CPU legs run the SPEED build of the oracle sources (oracle/Makefile: -O3, AVX2+FMA or the box's native ISA,
+    contraction on) with the vectorisable transforms of oracle/fft_fast.c; the parity build (-O2 -ffp-contract=off,
+    SPEC transforms) is for tests.  kind: "fast" (shipped, x86-64-v3), "native" (built here if gcc is present),
+    "parity".  Returns a ctypes library or None."""
+    import ctypes as C
+    if kind in _CPU_LIBS:
+        return _CPU_LIBS[kind]
+    odir = os.path.join(ROOT, "oracle")
+    path = {"fast": "libsdoracle_fast.so", "native": "libsdoracle_native.so", "parity": "libsdoracle.so"}[kind]
+    path = os.path.join(odir, "_build", path)
+    if kind == "native" and not os.path.exists(path):
+        subprocess.run(["make", "-C", odir, "native"], capture_output=True)
+    if kind == "fast" and not os.path.exists(path):
+        subprocess.run(["make", "-C", odir], capture_output=True)
+    L = None
+    if os.path.exists(path):
+        try:
+            L = C.CDLL(path)
+            L.sdo_baseline_run.restype = C.c_double
+            L.sdo_baseline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                           C.POINTER(C.c_uint64)]
+            L.sdo_set_fast_transforms(0 if kind == "parity" else 1)
+        except OSError:
+            L = None
+    _CPU_LIBS[kind] = L
+    return L
+
+
+CPU_FLAGS = {"fast": "gcc -O3 -march=x86-64-v3 -ffp-contract=fast + fft_fast.c (Stockham radix-4, vectorised)",
+             "native": "gcc -O3 -march=native -ffp-contract=fast + fft_fast.c (Stockham radix-4, vectorised)",
+             "parity": "gcc -O2 -ffp-contract=off, SPEC transforms (the build the parity tests use)"}
+
+
+def cpu_run(name, n_streams, n, threads, reps=1, warm=0, kind="fast"):
     import ctypes as C
     O, p = oracle_params(name)
+    L = cpu_lib(kind) or cpu_lib("fast") or O.lib()
     base = make_base_signal(name, n, seed=1)
     x = np.ascontiguousarray(np.tile(base, (n_streams, 1)))
     rng = np.random.default_rng(0)
@@ -204,46 +242,99 @@ def cpu_run(name, n_streams, n, threads, reps=1, warm=0):
     chk = C.c_uint64()
     times = []
     for i in range(warm + reps):
-        t = O.lib().sdo_baseline_run(C.byref(p), O.ptr(x), n_streams, n, threads, C.byref(chk))
+        t = L.sdo_baseline_run(C.byref(p), O.ptr(x), n_streams, n, threads, C.byref(chk))
         if i >= warm:
             times.append(t)
     return times, n_streams * n
 
 
 def pick_threads(name):
-    """Thread count for the CPU legs: the usable cores, or a fraction of them when a short probe of the same
-    workload (4 frames per stream, one stream per thread, best of 2) runs faster that way (SMT siblings, throttled containers).
-    Returns (threads, description)."""
+    """Thread count and build for the CPU legs: the usable cores, or a fraction of them when a short probe of the
+    same workload (4 frames per stream, one stream per thread, best of 2) runs faster that way (SMT siblings,
+    throttled containers); the native-ISA build when it beats the shipped AVX2 one on the same probe.
+    Returns (threads, build kind, description)."""
     cores, how = usable_cores()
+    kinds = ["fast"] + (["native"] if cpu_lib("native") is not None and not os.environ.get("SDB_CPU_NO_NATIVE") else [])
     if os.environ.get("SDB_CPU_THREADS"):
-        return cores, how
-    best, table = (0.0, cores), []
+        return cores, kinds[0], how
+    best, table = (0.0, cores, kinds[0]), []
     for t in sorted({cores, max(1, cores // 2), max(1, cores // 4), max(1, cores // 8)}, reverse=True):
-        times, samples = cpu_run(name, t, 4 * N_FFT, t, reps=2, warm=1)
-        rate = samples / min(times) / 1e6
-        table.append("%d:%.0f" % (t, rate))
-        if rate > best[0] * 1.05:                      # prefer more threads unless fewer are clearly faster
-            best = (rate, t)
-    return best[1], "%s; probe threads:MS/s %s" % (how, " ".join(table))
+        for kd in kinds:
+            times, samples = cpu_run(name, t, 4 * N_FFT, t, reps=2, warm=1, kind=kd)
+            rate = samples / min(times) / 1e6
+            table.append("%d/%s:%.0f" % (t, kd, rate))
+            if rate > best[0] * 1.05:                      # prefer more threads unless fewer are clearly faster
+                best = (rate, t, kd)
+    return best[1], best[2], "%s; probe threads/build:MS/s %s" % (how, " ".join(table))
+
+
+def fft_comparators():
+    """Single-thread time of one 65536-point complex64 transform: the oracle's parity (SPEC) transform, its speed
+    transform, numpy (pocketfft) and torch (MKL) -- shows the CPU arm's transform is not a straw man."""
+    import ctypes as C
+    out = {}
+    x = (np.random.default_rng(3).standard_normal(2 * N_FFT).astype(np.float32)).view(np.complex64)
+    y = np.empty_like(x)
+
+    def best(fn, reps=5):
+        fn()
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); t.append(time.perf_counter() - t0)
+        return round(min(t) * 1e3, 3)
+    for kd in ("fast", "native"):
+        L = cpu_lib(kd)
+        if L is not None:
+            L.sdo_fast_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int]
+            out["oracle_" + kd + "_ms"] = best(lambda: L.sdo_fast_fft(x.ctypes.data, None, y.ctypes.data, N_FFT, -1))
+    Lp = cpu_lib("parity")
+    if Lp is not None:
+        # the parity build's SPEC transform through the same entry point (fast transforms are off in that library)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            x8 = np.tile(x, 8)          # 8 frames per call: plan set-up amortised
+            out["oracle_spec_ms"] = round(best(lambda: O.psd_frames(x8, N_FFT, "none"), 2) / 8, 3)
+        except Exception:
+            pass
+    try:
+        out["numpy_pocketfft_ms"] = best(lambda: np.fft.fft(x))
+    except Exception:
+        pass
+    try:
+        import torch
+        nt = torch.get_num_threads()
+        torch.set_num_threads(1)
+        xt = torch.from_numpy(x)
+        out["torch_mkl_ms"] = best(lambda: torch.fft.fft(xt))
+        torch.set_num_threads(nt)
+    except Exception:
+        pass
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores, how = pick_threads(args.workload)
+    cores, kind, how = pick_threads(args.workload)
     n = N_FFT // 2 * 16                      # 2^19 samples per stream: one stream per host thread
     streams = cores
-    times, samples = cpu_run(args.workload, streams, n, cores, reps=args.steps, warm=args.warmup)
+    times, samples = cpu_run(args.workload, streams, n, cores, reps=args.steps, warm=args.warmup, kind=kind)
     total = sum(times)
     v = samples * len(times) / total / 1e6
     sample = "%d streams x %d samples per step, %d OpenMP threads (%s)" % (streams, n, cores, how)
+    # the round-1 arm (parity build, SPEC transforms) on a shorter sample, for the record
+    tp, sp = cpu_run(args.workload, streams, N_FFT * 2, cores, reps=1, warm=0, kind="parity")
     out = {"impl": "reference", "metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)",
            "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config(args, streams=streams, hops=16),
-           "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "sample": sample,
+                            "build": CPU_FLAGS[kind], "per_thread_msps": v / cores,
+                            "parity_build_msps": sp / sum(tp) / 1e6,
+                            "fft_65536_single_thread": fft_comparators()},
            "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -486,10 +577,12 @@ def run_cuda(args):
     # ---- bounded CPU baseline on rank 0, N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores, how = pick_threads(name)
-        times, samples = cpu_run(name, cores, N_FFT // 2 * 16, cores, reps=2, warm=0)
-        cpu = {"value": samples * len(times) / sum(times) / 1e6, "unit": "MS/s", "cores": cores, "kind": "port",
-               "sample": "%d streams x %d samples x %d reps of the same workload (oracle restatement, OpenMP, "
+        cores, kind, how = pick_threads(name)
+        times, samples = cpu_run(name, cores, N_FFT // 2 * 16, cores, reps=2, warm=0, kind=kind)
+        v = samples * len(times) / sum(times) / 1e6
+        cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "build": CPU_FLAGS[kind],
+               "per_thread_msps": v / cores,
+               "sample": "%d streams x %d samples x %d reps of the same workload (oracle sources, speed build, OpenMP, "
                          "one stream per thread; %s)" % (cores, N_FFT // 2 * 16, len(times), how)}
 
     if rank == 0:

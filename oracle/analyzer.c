@@ -154,49 +154,67 @@ int sdo_analyzer_feed(sdo_analyzer *a, const sdo_cpx *x, size_t n,
 }
 
 /* CPU baseline: S independent streams sharded over OpenMP threads, each a full analyzer pass.
- * Returns wall seconds; *checksum folds every output so the work cannot be optimised away. */
+ * Returns the wall seconds of the PROCESSING only: analyzers, plans and output buffers are created before the
+ * clock starts (a running analyzer does not rebuild its plans; round 1 timed the set-up too, ~40 ms per stream
+ * for 64 channels, which handicapped the CPU arm on short samples).  *checksum folds every output so the work
+ * cannot be optimised away. */
+typedef struct {
+  sdo_analyzer *a; float *psd; sdo_cpx **sym; uint8_t **hard; size_t *nsym; uint64_t acc;
+} baseline_stream;
+
 double sdo_baseline_run(const sdo_an_params *p, const sdo_cpx *x, size_t n_streams, size_t n,
                         int n_threads, uint64_t *checksum)
 {
   struct timespec t0, t1;
   uint64_t total = 0;
   long s;
+  const size_t N = p->psd_size, nf = n / N + 1, sym_cap = n / 2 + 16, nch = p->n_channels ? p->n_channels : 1;
+  baseline_stream *bs = (baseline_stream *) calloc(n_streams ? n_streams : 1, sizeof(*bs));
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
 #else
   (void) n_threads;
 #endif
-  clock_gettime(CLOCK_MONOTONIC, &t0);
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+#pragma omp parallel for schedule(dynamic, 1)
   for (s = 0; s < (long) n_streams; ++s) {
-    sdo_analyzer *a = sdo_analyzer_new(p);
-    const size_t N = p->psd_size, nf = n / N + 1;
-    const size_t sym_cap = n;  /* generous */
-    float *psd = (float *) malloc(sizeof(float) * N * nf);
-    sdo_cpx **sym = (sdo_cpx **) calloc(p->n_channels ? p->n_channels : 1, sizeof(*sym));
-    uint8_t **hard = (uint8_t **) calloc(p->n_channels ? p->n_channels : 1, sizeof(*hard));
-    size_t *nsym = (size_t *) calloc(p->n_channels ? p->n_channels : 1, sizeof(size_t));
+    baseline_stream *b = &bs[s];
+    unsigned k;
+    b->a = sdo_analyzer_new(p);
+    b->psd = (float *) malloc(sizeof(float) * N * nf);
+    b->sym = (sdo_cpx **) calloc(nch, sizeof(*b->sym));
+    b->hard = (uint8_t **) calloc(nch, sizeof(*b->hard));
+    b->nsym = (size_t *) calloc(nch, sizeof(size_t));
+    for (k = 0; k < p->n_channels; ++k) {
+      b->sym[k] = (sdo_cpx *) malloc(sizeof(sdo_cpx) * sym_cap);
+      b->hard[k] = (uint8_t *) malloc(sym_cap);
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (s = 0; s < (long) n_streams; ++s) {
+    baseline_stream *b = &bs[s];
     sdo_an_counts cnt;
     unsigned k;
     size_t i;
     uint64_t acc = 0;
-    for (k = 0; k < p->n_channels; ++k) {
-      size_t cap = sym_cap / 2 + 16;
-      sym[k] = (sdo_cpx *) malloc(sizeof(sdo_cpx) * cap);
-      hard[k] = (uint8_t *) malloc(cap);
-    }
     memset(&cnt, 0, sizeof(cnt));
-    cnt.n_sym = nsym;
-    sdo_analyzer_feed(a, x + (size_t) s * n, n, psd, nf, NULL, 0, sym, hard, sym_cap / 2 + 16, &cnt);
-    for (i = 0; i < cnt.n_frames * N; i += 97) { uint32_t u; memcpy(&u, &psd[i], 4); acc += u; }
+    cnt.n_sym = b->nsym;
+    sdo_analyzer_feed(b->a, x + (size_t) s * n, n, b->psd, nf, NULL, 0, b->sym, b->hard, sym_cap, &cnt);
+    for (i = 0; i < cnt.n_frames * N; i += 97) { uint32_t u; memcpy(&u, &b->psd[i], 4); acc += u; }
     for (k = 0; k < p->n_channels; ++k)
-      for (i = 0; i < nsym[k]; ++i) acc += hard[k][i];
-    total += acc;
-    for (k = 0; k < p->n_channels; ++k) { free(sym[k]); free(hard[k]); }
-    free(sym); free(hard); free(nsym); free(psd);
-    sdo_analyzer_destroy(a);
+      for (i = 0; i < b->nsym[k] && i < sym_cap; ++i) acc += b->hard[k][i];
+    b->acc = acc;
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
+  for (s = 0; s < (long) n_streams; ++s) {
+    baseline_stream *b = &bs[s];
+    unsigned k;
+    total += b->acc;
+    for (k = 0; k < p->n_channels; ++k) { free(b->sym[k]); free(b->hard[k]); }
+    free(b->sym); free(b->hard); free(b->nsym); free(b->psd);
+    sdo_analyzer_destroy(b->a);
+  }
+  free(bs);
   if (checksum) *checksum = total;
   return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
 }

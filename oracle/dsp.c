@@ -89,7 +89,10 @@ void sdo_filt_free(sdo_filt *f)
 }
 
 /* y[n] = sum_{i=0}^{nb-1} b[i] x[n-i] - sum_{i=1}^{na-1} a[i] y[n-i]   (a[0] == 1), single
- * accumulator, ascending i, feed-forward part first (su_iir_filt_feed, Tasks/WaveSampler.cpp:68-80). */
+ * accumulator, ascending i, feed-forward part first, every term one FUSED multiply-add
+ * acc <- fma(+-coef, sample, acc) (SPEC I.1; su_iir_filt_feed, Tasks/WaveSampler.cpp:68-80 -- upstream's
+ * own summation is a volk dot product / a compiler-contracted loop, i.e. unspecified, so the restatement
+ * picks the form the GPU executes in one FFMA per term). */
 sdo_cpx sdo_filt_feed(sdo_filt *f, sdo_cpx x)
 {
   unsigned i, p;
@@ -97,8 +100,8 @@ sdo_cpx sdo_filt_feed(sdo_filt *f, sdo_cpx x)
   f->x[f->xp] = x;
   p = f->xp;
   for (i = 0; i < f->nb; ++i) {
-    acc.re = acc.re + f->b[i] * f->x[p].re;
-    acc.im = acc.im + f->b[i] * f->x[p].im;
+    acc.re = fmaf(f->b[i], f->x[p].re, acc.re);
+    acc.im = fmaf(f->b[i], f->x[p].im, acc.im);
     p = p == 0 ? f->nb - 1 : p - 1;
   }
   f->xp = f->xp + 1 == f->nb ? 0 : f->xp + 1;
@@ -106,8 +109,8 @@ sdo_cpx sdo_filt_feed(sdo_filt *f, sdo_cpx x)
     /* y line holds y[n-1] at index yp, y[n-2] at yp-1 ... */
     p = f->yp;
     for (i = 1; i < f->na; ++i) {
-      acc.re = acc.re - f->a[i] * f->y[p].re;
-      acc.im = acc.im - f->a[i] * f->y[p].im;
+      acc.re = fmaf(-f->a[i], f->y[p].re, acc.re);
+      acc.im = fmaf(-f->a[i], f->y[p].im, acc.im);
       p = p == 0 ? f->na - 1 : p - 1;
     }
     f->yp = f->yp + 1 == f->na ? 0 : f->yp + 1;

@@ -48,6 +48,7 @@ void sdo_spec_fft_stockham(sdo_cpx *s, unsigned M, const sdo_cpx *tw, int sign, 
 {
   unsigned logM = 0, logNs = 0, j;
   const unsigned q = M >> 2;
+  if (sdo_fast_transforms && M >= 8) { sdo_fast_fft(s, NULL, s, M, sign); return; }   /* bench CPU legs only */
   while ((1u << logM) < M) ++logM;
   for (; logNs + 2 <= logM; logNs += 2) {
     const unsigned Ns = 1u << logNs;
@@ -173,6 +174,7 @@ void sdo_spec_forward(const sdo_spec_plan *p, const sdo_cpx *x, const float *win
 {
   const unsigned N = p->N, N1 = p->N1, N2 = p->N2;
   unsigned n1, n2, k1, i;
+  if (sdo_fast_transforms) { sdo_fast_fft(x, window, X, N, -1); return; }   /* bench CPU legs only (fft_fast.c) */
   if (p->kind == 2) {
     sdo_cpx col[256];
     for (n2 = 0; n2 < 256; ++n2) {

@@ -67,6 +67,11 @@ typedef struct {
   int      four, kind;       /* kind 0: single Stockham, 1: four-step, 2: 65536 = 256 x 256 fft16 form */
   sdo_cpx *tw_a, *tw_b, *tw_n, *scr, *buf, *tmp;
 } sdo_spec_plan;
+/* speed leg of the CPU baseline (fft_fast.c): vectorisable Stockham transform, float32-rounding-equal to the SPEC
+ * transforms, NOT bit-identical; enabled only by bench.py's CPU legs, never by a parity test */
+extern int sdo_fast_transforms;
+void sdo_set_fast_transforms(int on);
+void sdo_fast_fft(const sdo_cpx *in, const float *window, sdo_cpx *out, unsigned n, int sign);
 sdo_cpx *sdo_spec_twiddles(unsigned n);
 void sdo_spec_fft_stockham(sdo_cpx *s, unsigned M, const sdo_cpx *tw, int sign, sdo_cpx *tmp);
 int  sdo_spec_plan_init(sdo_spec_plan *p, unsigned N, int four);

@@ -19,6 +19,7 @@
 #define TWOPI_F 6.28318530717958647692f
 
 #include "sdb_math.h"
+#include "sdb_cpx.h"
 
 static __device__ __forceinline__ float wrap_once(float phi)
 {
@@ -37,7 +38,8 @@ static __device__ __forceinline__ float2 ncqo_read(float &phi, float omega)
 }
 
 // ------------------------------------------------------------------ small IIR/FIR, shift registers --
-// y[n] = sum_{i<N} b[i] x[n-i] - sum_{1<=i<N} a[i] y[n-i], single accumulator, ascending i (SPEC I.1).
+// y[n] = sum_{i<N} b[i] x[n-i] - sum_{1<=i<N} a[i] y[n-i], single accumulator, ascending i, every term one fused
+// multiply-add (SPEC I.1; explicit fma: the unit is compiled with -fmad=false).
 // Lines are shift registers ([0] newest) so every index is a compile-time constant -> registers.
 template <int N>
 static __device__ __forceinline__ float2 iir_step(const float (&b)[SDB_MAX_IIR], const float (&a)[SDB_MAX_IIR],
@@ -49,10 +51,10 @@ static __device__ __forceinline__ float2 iir_step(const float (&b)[SDB_MAX_IIR],
   xr[0] = in.x; xi[0] = in.y;
   float ar = 0.0f, ai = 0.0f;
 #pragma unroll
-  for (int i = 0; i < N; ++i) { ar = ar + b[i] * xr[i]; ai = ai + b[i] * xi[i]; }
+  for (int i = 0; i < N; ++i) { ar = __fmaf_rn(b[i], xr[i], ar); ai = __fmaf_rn(b[i], xi[i], ai); }
   if (N > 1) {
 #pragma unroll
-    for (int i = 1; i < N; ++i) { ar = ar - a[i] * yr[i - 1]; ai = ai - a[i] * yi[i - 1]; }
+    for (int i = 1; i < N; ++i) { ar = __fmaf_rn(-a[i], yr[i - 1], ar); ai = __fmaf_rn(-a[i], yi[i - 1], ai); }
 #pragma unroll
     for (int i = N - 1; i > 0; --i) { yr[i] = yr[i - 1]; yi[i] = yi[i - 1]; }
     yr[0] = ar; yi[0] = ai;
@@ -217,28 +219,46 @@ static __device__ __forceinline__ unsigned char decide(int mode, float dmin, flo
 }
 
 // ------------------------------------------------------------------ the chain kernel ------------
-// One CTA = 32 chains x 4 stage-warps.  Warp w runs stage w of every chain of the CTA (lane = chain):
-//   warp 0  gain      : manual offset LO, AGC / fixed gain                     -> ring A
-//   warp 1  carrier   : Costas | PLL + component select | FSK discriminator | audio demodulators -> ring B
-//   warp 2  filter    : RRC matched filter (FIR) | audio low-pass            -> ring C
-//   warp 3  clock     : Gardner | manual sampler | audio resampler, x0.75, decision, output
-// Stage w works on chunk (it - w) of CHUNK samples while stage w+1 works on the previous one, so the
-// serial latency per sample is that of the slowest stage (the carrier loop), not the sum; loop state
-// lives in registers for the whole feed.  Chains are ordered channel-major so a warp normally holds 32
-// streams of the SAME channel (uniform configuration, no divergence).
-#define CHUNK 32
-// matched-filter line: 8 margin + 2 n slots (duplicated line, n <= 32 taps) or n slots (single line, up to 136);
-// the slot count of a launch comes from the channel plan (SdbInspDyn, sdb_internal.h)
-__device__ unsigned long long g_stage_cycles[8];
+// One CTA = 32 chains (lane = chain) x 11 role warps.  A feed is cut into chunks of CH samples that move through
+// seven pipeline steps, one CTA-wide barrier per iteration; a step that is feed-forward (every output depends only
+// on inputs) is split over several warps by sample index, a step that is a true recurrence keeps one warp:
+//
+//   step  warps  role      work on its chunk                                                    hand-over
+//   0     0      load      cp.async tile of the chunk (coalesced rows of the 32 chains)          tile[2]
+//   1     1-2    pre       manual-offset LO, magnitude 10 log10 |y|^2 (8 samples per warp)       y[3], m[3]
+//   2     0      track     AGC delay line swap, peak tracker, fast / slow levels (recurrence)     in place
+//   3     3-4    post      gain 10^(level (slope - 1) / 20) x delayed sample (8 samples per warp) ringA[2]
+//   4     5      carrier   Costas | PLL + component | FSK discriminator | audio demod (recurrence) ringB (circular)
+//   5     6-9    filter    matched filter: 4 outputs per warp straight off ringB (its history IS
+//                          the filter line), one FFMA2 per complex sample x tap; audio LPF (IIR, 1 warp) ringC[2]
+//   6     10     clock     Gardner | sampler | resampler, CMA, x0.75, decision, output            global
+//
+// Round 1 ran four stage-warps per CTA (8 warps per SM: issue slots 10 % busy, half of all stall samples on
+// the barrier behind the slowest stage, profiles/r01_inspector_stages.md); the feed-forward work (two logarithm /
+// exponential evaluations, the 19...75-tap FIR) now runs beside the recurrences instead of in series with them, and
+// a CTA brings 11 warps (22-33 per SM).  Loop state lives in registers for the whole feed; the per-chain lines
+// (AGC delay line + magnitude history, CMA) in shared memory sized from the channel plan (SdbInspDyn).
+#define CH 16
+enum { W_TRACK = 0, W_PRE = 1, W_POST = 3, W_CARRIER = 5, W_MF = 6, W_CLOCK = 10, INSP_WARPS = 11 };
+#define INSP_STEPS 6          // pipeline depth after the load: a chunk loaded in iteration c leaves in iteration c + 6
 
+#ifdef SDB_STAGE_CYCLES
+__device__ unsigned long long g_stage_cycles[8];
+#endif
 cudaError_t sdb_stage_cycles(unsigned long long out[8], int reset)
 {
+#ifdef SDB_STAGE_CYCLES
   cudaError_t e = cudaMemcpyFromSymbol(out, g_stage_cycles, sizeof(unsigned long long) * 8);
   if (e == cudaSuccess && reset) {
     unsigned long long z[8] = { 0 };
     e = cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z));
   }
   return e;
+#else
+  (void) reset;
+  for (int i = 0; i < 8; ++i) out[i] = 0;     // the counters are compiled out of the product build
+  return cudaSuccess;
+#endif
 }
 static __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
@@ -247,16 +267,27 @@ static __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsr
 }
 static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+// CTA barrier reachable from the role functions (every role executes the same number of them)
+static __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// Fixed part of the CTA's shared memory.  The per-chain state lines that depend on the channel plan follow it,
-// sized per launch (SdbInspDyn): matched-filter line [mf_slots][32] float2, AGC delay line + magnitude history
-// [agc_rows][32] float, CMA weights and line 2 x [SDB_EQ_LEN][32] float2 when some chain equalises.  cfg2 (19 taps,
-// 36 AGC floats) needs 84 KB, cfg3 (75 taps, 144 AGC floats) 112 KB: both leave two CTAs per SM.  A chain whose
-// lines do not fit keeps them in the global pool (correct, slower: a global round trip inside the recurrence).
 struct ChainSmem {
-  float2 tile[2][32][33];
-  float2 ring[3][2][CHUNK][32];
-  float  lvl[CHUNK][32];
+  float2 tile[2][32][CH + 1];
+  float2 y[3][CH][32];
+  float  m[3][CH][32];
+  float2 ringA[2][CH][32];
+  float2 ringC[2][CH][32];
+};
+
+// what every role needs to know about its lane's chain
+struct ICtx {
+  ChainSmem *sm;
+  float2 (*rb)[32]; unsigned rb_mask;         // ringB: carrier output, circular, doubles as the matched-filter line
+  float  (*taps)[32];                         // per-lane matched-filter taps [t][lane]
+  float  (*agc)[32]; int agc_rows;
+  float2 (*eqw)[32]; float2 (*eqx)[32];
+  int lane, valid, cls, fresh;
+  uint32_t n, nchunks;
+  const SdbChainCfg *cp; SdbChainState *stp; float *bpool;
 };
 
 // SPEC E: constant-modulus equaliser on the symbol stream.  Sums and updates run in index order.
@@ -290,30 +321,509 @@ static __device__ __forceinline__ float2 cma_step(float2 (*w)[32], float2 (*x)[3
   return make_float2(yr, yi);
 }
 
-// Matched filter for mf_n <= 32 taps, NT = mf_n rounded up to a multiple of 8.  The line is kept twice
-// (slot p and p + mf_n, after a margin of 8 slots) so that x[n-t] is always at slot base - t: every
-// load has a compile-time offset from one base address and none depends on another.  Taps t >= mf_n
-// are zero: adding +-0 to a +0-initialised accumulator never changes its bits, so the result is exactly
-// the SPEC I.1 sum over mf_n taps.
-template <int NT>
-static __device__ __forceinline__ float2 mf_fir(const float2 (*mfh)[32], int lane, unsigned ptr, int mf_n,
-                                                const float (&tp)[32])
+// ---- steps 0 + 2: tile loader and AGC tracker (warp 0)
+static __device__ void role_track(const ICtx &c, const float2 *chan_row)
 {
-  const float2 *base = &mfh[8 + ptr + mf_n][lane];
-  float accr = 0.0f, acci = 0.0f;
-  float2 v[NT];
-#pragma unroll
-  for (int t = 0; t < NT; ++t) v[t] = base[-t * 32];
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    accr = accr + tp[t] * v[t].x;
-    acci = acci + tp[t] * v[t].y;
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane;
+  const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
+  const bool have_agc = c.valid && cp->have_agc && c.cls != SDB_INSP_RAW;
+  float far_ = 0, faf = 0, sar = 0, saf = 0; unsigned hang_max = 0, dl_size = 1, mh_size = 1;
+  AgcS as; as.fast = as.slow = as.peak = -160.0f; as.hang_n = as.dl_ptr = as.mh_ptr = 0;
+  float *dl = nullptr, *mh = nullptr; bool in_smem = false;
+  if (have_agc) {
+    far_ = cp->far_; faf = cp->faf; sar = cp->sar; saf = cp->saf;
+    hang_max = cp->hang_max; dl_size = cp->dl_size; mh_size = cp->mh_size;
+    as.fast = stp->fast_level; as.slow = stp->slow_level; as.peak = stp->peak;
+    as.hang_n = stp->hang_n; as.dl_ptr = stp->dl_ptr; as.mh_ptr = stp->mh_ptr;
+    in_smem = 2 * dl_size + mh_size <= (unsigned) c.agc_rows;
+    float *gdl = c.bpool + (size_t) cp->st_dl_off * 32, *gmh = c.bpool + (size_t) cp->st_mh_off * 32;
+    if (in_smem) {
+      dl = &c.agc[0][lane]; mh = &c.agc[2 * dl_size][lane];
+      for (unsigned i = 0; i < 2 * dl_size; ++i) dl[i * 32] = c.fresh ? 0.0f : gdl[i * 32];
+      for (unsigned i = 0; i < mh_size; ++i) mh[i * 32] = c.fresh ? -160.0f : gmh[i * 32];
+    } else {
+      dl = gdl; mh = gmh;
+      if (c.fresh) {
+        for (unsigned i = 0; i < 2 * dl_size; ++i) dl[i * 32] = 0.0f;
+        for (unsigned i = 0; i < mh_size; ++i) mh[i * 32] = -160.0f;
+      }
+    }
   }
-  return make_float2(accr, acci);
+  // coalesced, asynchronous tile load: row r of the tile = CH consecutive samples of the CTA's chain r; a warp
+  // instruction copies two rows (16 lanes x 8 bytes = 128 contiguous bytes each)
+  const unsigned long long rowp = (unsigned long long) chan_row;
+  const uint32_t n = c.n;
+  const int col = lane & (CH - 1), rsel = lane / CH;
+  auto issue_tile = [&](uint32_t ch) {
+    const uint32_t b0 = ch * CH;
+#pragma unroll 8
+    for (int j = 0; j < 32 / (32 / CH); ++j) {
+      const int r = j * (32 / CH) + rsel;
+      const unsigned long long pr = __shfl_sync(0xffffffffu, rowp, r);
+      const uint32_t nr = __shfl_sync(0xffffffffu, n, r);
+      if (b0 + col < nr) cp_async8(&sm.tile[ch & 1][r][col], (const float2 *) pr + b0 + col);
+    }
+    cp_async_commit();
+  };
+  const uint32_t total = c.nchunks + INSP_STEPS;
+#ifdef SDB_STAGE_CYCLES
+  long long busy = 0;
+#endif
+  for (uint32_t it = 0; it <= total; ++it) {
+#ifdef SDB_STAGE_CYCLES
+    const long long t0 = clock64();
+#endif
+    if (it < c.nchunks) issue_tile(it);
+    if (have_agc && it >= 2 && it - 2 < c.nchunks) {
+      const uint32_t ck = it - 2, base = ck * CH;
+      const int b3 = (int) (ck % 3u);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      for (int i = 0; i < cnt; ++i) {
+        // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
+        const float2 y = sm.y[b3][i][lane];
+        const unsigned dp = as.dl_ptr;
+        as.dl_ptr = dp + 1 >= dl_size ? 0 : dp + 1;
+        const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
+        dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
+        sm.y[b3][i][lane] = xd;
+        // magnitude history, running peak, fast / slow levels (SPEC A)
+        const float m = sm.m[b3][i][lane];
+        const float m_old = mh[as.mh_ptr * 32];
+        mh[as.mh_ptr * 32] = m;
+        if (++as.mh_ptr >= mh_size) as.mh_ptr = 0;
+        if (m > as.peak) {
+          as.peak = m;
+        } else if (as.peak == m_old) {
+          float pk = -160.0f;
+          for (unsigned q = 0; q < mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
+          as.peak = pk;
+        }
+        float d = as.peak - as.fast;
+        if (d > 0.0f) as.fast = as.fast + far_ * d;
+        else          as.fast = as.fast + faf * d;
+        d = as.peak - as.slow;
+        if (d > 0.0f) { as.slow = as.slow + sar * d; as.hang_n = 0; }
+        else if (as.hang_n >= hang_max) as.slow = as.slow + saf * d;
+        else ++as.hang_n;
+        sm.m[b3][i][lane] = as.fast > as.slow ? as.fast : as.slow;
+      }
+    }
+    cp_async_wait<0>();
+#ifdef SDB_STAGE_CYCLES
+    busy += clock64() - t0;
+#endif
+    cta_sync();
+  }
+#ifdef SDB_STAGE_CYCLES
+  if (lane == 0) { atomicAdd(&g_stage_cycles[0], (unsigned long long) busy);
+                   atomicAdd(&g_stage_cycles[4], (unsigned long long) c.nchunks * CH); }
+#endif
+  if (have_agc) {
+    stp->fast_level = as.fast; stp->slow_level = as.slow; stp->peak = as.peak;
+    stp->hang_n = as.hang_n; stp->dl_ptr = as.dl_ptr; stp->mh_ptr = as.mh_ptr;
+    if (in_smem) {
+      float *gdl = c.bpool + (size_t) cp->st_dl_off * 32, *gmh = c.bpool + (size_t) cp->st_mh_off * 32;
+      for (unsigned i = 0; i < 2 * dl_size; ++i) gdl[i * 32] = dl[i * 32];
+      for (unsigned i = 0; i < mh_size; ++i) gmh[i * 32] = mh[i * 32];
+    }
+  }
 }
 
-__global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
-                                                     int n_streams, SdbChainState *__restrict__ states,
+// ---- step 1: manual-offset LO + magnitude in dB (warps 1-2, half a chunk each)
+static __device__ void role_pre(const ICtx &c, int part)
+{
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane;
+  const bool have_agc = c.valid && c.cp->have_agc && c.cls != SDB_INSP_RAW;
+  const bool have_lo = c.valid && c.cls != SDB_INSP_AUDIO && c.cp->have_lo;
+  float lo_phi = have_lo ? c.stp->lo_phi : 0.0f;
+  const float lo_omega = have_lo ? c.cp->lo_omega : 0.0f;
+  const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+  const int i0 = part * (CH / 2), i1 = i0 + CH / 2;
+  for (uint32_t it = 0; it <= total; ++it) {
+    if (it >= 1 && it - 1 < c.nchunks) {
+      const uint32_t ck = it - 1, base = ck * CH;
+      const int b3 = (int) (ck % 3u);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*tl)[CH + 1] = sm.tile[ck & 1];
+      if (have_lo) {
+        // both pre warps run the (cheap) phase recurrence over the whole chunk and evaluate exp(i phi) only for
+        // their own samples: phi is the same sequence of binary32 additions as in the serial statement
+        for (int i = 0; i < cnt; ++i) {
+          if (i >= i0 && i < i1) {
+            float s, co;
+            d_sincosf(lo_phi, &s, &co);
+            float2 y = tl[lane][i];
+            y = make_float2(y.x * co + y.y * s, y.y * co - y.x * s);
+            sm.y[b3][i][lane] = y;
+            if (have_agc) sm.m[b3][i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
+          }
+          lo_phi = wrap_once(lo_phi + lo_omega);
+        }
+      } else {
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+          if (i < cnt) {
+            const float2 y = tl[lane][i];
+            sm.y[b3][i][lane] = y;
+            if (have_agc) sm.m[b3][i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
+          }
+        }
+      }
+    }
+    cta_sync();
+  }
+  if (have_lo && part == 0) c.stp->lo_phi = lo_phi;
+}
+
+// ---- step 3: gain (warps 3-4, half a chunk each)
+static __device__ void role_post(const ICtx &c, int part)
+{
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane, cls = c.cls;
+  const bool have_agc = c.valid && c.cp->have_agc && cls != SDB_INSP_RAW;
+  const float knee = c.valid ? c.cp->knee : 0.0f, slope_m1 = c.valid ? c.cp->gain_slope - 1.0f : 0.0f;
+  const float fixed_gain = c.valid ? c.cp->fixed_gain : 1.0f;
+  const float gain2 = (c.valid && cls != SDB_INSP_AUDIO) ? c.cp->gain2 : 1.0f;
+  const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+  const int i0 = part * (CH / 2), i1 = i0 + CH / 2;
+  for (uint32_t it = 0; it <= total; ++it) {
+    if (it >= 3 && it - 3 < c.nchunks) {
+      const uint32_t ck = it - 3, base = ck * CH;
+      const int b3 = (int) (ck % 3u);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*out)[32] = sm.ringA[ck & 1];
+#pragma unroll 4
+      for (int i = i0; i < i1; ++i) {
+        if (i < cnt) {
+          float2 y = sm.y[b3][i][lane];
+          if (have_agc) {
+            const float lvl = sm.m[b3][i][lane];
+            float g = lvl < knee ? fixed_gain : d_db_to_mag(lvl * slope_m1);
+            g = g * 0.7f;
+            y.x = y.x * g; y.y = y.y * g;
+            if (cls != SDB_INSP_AUDIO) { y.x = 2.0f * y.x; y.y = 2.0f * y.y; }
+          } else if (cls != SDB_INSP_RAW && cls != SDB_INSP_AUDIO) {
+            y.x = gain2 * y.x; y.y = gain2 * y.y;
+          }
+          out[i][lane] = y;
+        }
+      }
+    }
+    cta_sync();
+  }
+}
+
+// ---- step 4: carrier stage (warp 5)
+static __device__ void role_carrier(const ICtx &c)
+{
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane, cls = c.cls;
+  const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
+  CostasK ck; CostasS cs; float p_phi = 0, p_omega = 0, pll_a = 0, pll_b = 0, prev_re = 0, prev_im = 0;
+  float rot_re = 1, rot_im = 0, dc = 0, sq_level = 0, dc_alpha = 0, sq_alpha = 0, sq_thr = 0, lo_phi = 0, lo_omega = 0;
+  int have_costas = 0, have_pll = 0, quad = 0, ask_ch = 0, ademod = 0, asquelch = 0;
+  ck.kind = 0; ck.af_n = 1; ck.a = ck.b = 0;
+  cs.phi = cs.omega = cs.lock = cs.yre = cs.yim = 0;
+#pragma unroll
+  for (int i = 0; i < SDB_MAX_IIR; ++i) { ck.af_b[i] = ck.af_a[i] = 0; cs.xr[i] = cs.xi[i] = cs.yr[i] = cs.yi[i] = 0; }
+  if (c.valid) {
+    have_costas = cp->have_costas; have_pll = cp->have_pll;
+    ck.kind = cp->costas_kind; ck.af_n = cp->af_n; ck.a = cp->c_a; ck.b = cp->c_b;
+#pragma unroll
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      ck.af_b[i] = cp->af_b[i]; ck.af_a[i] = cp->af_a[i];
+      cs.xr[i] = stp->afx_re[i]; cs.xi[i] = stp->afx_im[i]; cs.yr[i] = stp->afy_re[i]; cs.yi[i] = stp->afy_im[i];
+    }
+    cs.phi = stp->c_phi; cs.omega = stp->c_omega; cs.lock = stp->c_lock; cs.yre = stp->c_yre; cs.yim = stp->c_yim;
+    p_phi = stp->p_phi; p_omega = stp->p_omega; pll_a = cp->pll_alpha; pll_b = cp->pll_beta;
+    prev_re = stp->prev_re; prev_im = stp->prev_im;
+    rot_re = cp->fsk_rot_re; rot_im = cp->fsk_rot_im; quad = cp->fsk_quad_demod; ask_ch = cp->ask_channel;
+    ademod = cp->audio_demod; asquelch = cp->audio_squelch; dc = stp->dc; sq_level = stp->sq_level;
+    dc_alpha = cp->dc_alpha; sq_alpha = cp->sq_alpha; sq_thr = cp->sq_thr;
+    if (cls == SDB_INSP_AUDIO) { lo_phi = stp->lo_phi; lo_omega = cp->lo_omega; }
+  }
+  const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+#ifdef SDB_STAGE_CYCLES
+  long long busy = 0;
+#endif
+  for (uint32_t it = 0; it <= total; ++it) {
+#ifdef SDB_STAGE_CYCLES
+    const long long t0 = clock64();
+#endif
+    if (it >= 4 && it - 4 < c.nchunks) {
+      const uint32_t ckk = it - 4, base = ckk * CH;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*in)[32] = sm.ringA[ckk & 1];
+      for (int i = 0; i < cnt; ++i) {
+        float2 y = in[i][lane];
+        if (cls == SDB_INSP_PSK) {
+          if (have_costas) y = costas_step(ck, cs, y);
+        } else if (cls == SDB_INSP_FSK) {
+          float dr = y.x * prev_re + y.y * prev_im;
+          float di = y.y * prev_re - y.x * prev_im;
+          prev_re = y.x; prev_im = y.y;
+          if (quad) { y.x = d_atan2f(di, dr) * 0.318309886183790671538f; y.y = 0.0f; }
+          else { y.x = dr * rot_re - di * rot_im; y.y = dr * rot_im + di * rot_re; }
+        } else if (cls == SDB_INSP_ASK) {
+          if (have_pll) y = pll_step(pll_a, pll_b, p_phi, p_omega, y);
+          if (ask_ch == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
+          else if (ask_ch == 1) { y.y = 0.0f; }
+          else                  { y.x = y.y; y.y = 0.0f; }
+        } else if (cls == SDB_INSP_AUDIO) {
+          float v = 0.0f;
+          float p = y.x * y.x + y.y * y.y;
+          sq_level = sq_level + sq_alpha * (p - sq_level);
+          if (ademod == SDB_AUDIO_AM) {
+            v = d_cabsf(y.x, y.y);
+            dc = dc + dc_alpha * (v - dc);
+            v = v - dc;
+          } else if (ademod == SDB_AUDIO_FM) {
+            float dr = y.x * prev_re + y.y * prev_im;
+            float di = y.y * prev_re - y.x * prev_im;
+            v = d_atan2f(di, dr) * 0.318309886183790671538f;
+            prev_re = y.x; prev_im = y.y;
+          } else if (ademod == SDB_AUDIO_USB || ademod == SDB_AUDIO_LSB) {
+            float2 ph = ncqo_read(lo_phi, lo_omega);
+            v = y.x * ph.x - y.y * ph.y;
+          }
+          if (asquelch && !(sq_level > sq_thr)) v = 0.0f;
+          y = make_float2(v, 0.0f);
+        }
+        c.rb[(base + i) & c.rb_mask][lane] = y;
+      }
+    }
+#ifdef SDB_STAGE_CYCLES
+    busy += clock64() - t0;
+#endif
+    cta_sync();
+  }
+#ifdef SDB_STAGE_CYCLES
+  if (lane == 0) atomicAdd(&g_stage_cycles[1], (unsigned long long) busy);
+#endif
+  if (c.valid) {
+#pragma unroll
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      stp->afx_re[i] = cs.xr[i]; stp->afx_im[i] = cs.xi[i]; stp->afy_re[i] = cs.yr[i]; stp->afy_im[i] = cs.yi[i];
+    }
+    stp->c_phi = cs.phi; stp->c_omega = cs.omega; stp->c_lock = cs.lock; stp->c_yre = cs.yre; stp->c_yim = cs.yim;
+    stp->p_phi = p_phi; stp->p_omega = p_omega; stp->prev_re = prev_re; stp->prev_im = prev_im;
+    stp->dc = dc; stp->sq_level = sq_level;
+    if (cls == SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
+  }
+}
+
+// ---- step 5: matched filter / audio low-pass (warps 6-9, a quarter of a chunk each)
+// The carrier ring IS the filter line: output p needs x[p - t], t < mf_n, which are the mf_n most recent ring
+// entries (the last mf_n - 1 samples of the previous feed are put back in front of position 0 at kernel start).
+// One thread produces 4 consecutive outputs of its chain from a sliding register window: per tap one ring load,
+// one tap load and four packed FFMA2 (complex sample x real tap, SPEC I.1: ascending taps, fused terms).
+static __device__ void role_filter(const ICtx &c, int part, const float *taps_pool)
+{
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane;
+  const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
+  const int have_mf = c.valid ? cp->have_mf : 0, mf_n = c.valid ? cp->mf_n : 0;
+  const int alpf_n = (c.valid && c.cls == SDB_INSP_AUDIO) ? cp->alpf_n : 0;
+  const bool mf_ring = have_mf && (unsigned) (mf_n - 1 + 2 * CH) <= c.rb_mask + 1u;
+  const bool mf_global = have_mf && !mf_ring;
+  const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+  float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
+  unsigned mf_ptr = 0; float *mfl = nullptr; const float *gtaps = nullptr;
+  if (part == 0) {
+#pragma unroll
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      al_b[i] = c.valid ? cp->alpf_b[i] : 0.0f; al_a[i] = c.valid ? cp->alpf_a[i] : 0.0f;
+      al_x[i] = c.valid ? stp->al_x[i] : 0.0f; al_y[i] = c.valid ? stp->al_y[i] : 0.0f;
+      al_xi[i] = 0.0f; al_yi[i] = 0.0f;
+    }
+    if (mf_ring) {
+      const float *tp = taps_pool + cp->mf_off;
+      const float *gmf = c.bpool + (size_t) cp->st_mf_off * 32;
+      for (int t = 0; t < mf_n; ++t) c.taps[t][lane] = __ldg(tp + t);
+      for (int k2 = 1; k2 < mf_n; ++k2)       // x[-k2]: the k2-th newest sample of the previous feed
+        c.rb[(0u - (unsigned) k2) & c.rb_mask][lane] =
+            c.fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * (k2 - 1)) * 32], gmf[(2 * (k2 - 1) + 1) * 32]);
+    } else if (mf_global) {
+      // filters too long for the ring keep a circular line in the global pool and run serially on one warp
+      gtaps = taps_pool + cp->mf_off; mf_ptr = stp->mf_ptr;
+      mfl = c.bpool + (size_t) cp->st_mf_off * 32;
+      if (c.fresh) for (int i = 0; i < 2 * mf_n; ++i) mfl[i * 32] = 0.0f;
+    }
+  }
+  for (uint32_t it = 0; it <= total; ++it) {
+    if (it >= 5 && it - 5 < c.nchunks) {
+      const uint32_t ck = it - 5, base = ck * CH;
+      float2 (*out)[32] = sm.ringC[ck & 1];
+      if (mf_ring) {
+        const uint32_t p0 = base + (uint32_t) part * 4u;
+        if (p0 < n) {
+          float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+          float2 w0 = c.rb[(p0 + 0) & c.rb_mask][lane], w1 = c.rb[(p0 + 1) & c.rb_mask][lane];
+          float2 w2 = c.rb[(p0 + 2) & c.rb_mask][lane], w3 = c.rb[(p0 + 3) & c.rb_mask][lane];
+#pragma unroll 4
+          for (int t = 0; t < mf_n; ++t) {
+            const float b = c.taps[t][lane];
+            const float2 bb = make_float2(b, b);
+            const float2 nx = c.rb[(p0 - 1u - (unsigned) t) & c.rb_mask][lane];
+            a0 = sdb_fma2(bb, w0, a0); a1 = sdb_fma2(bb, w1, a1);
+            a2 = sdb_fma2(bb, w2, a2); a3 = sdb_fma2(bb, w3, a3);
+            w3 = w2; w2 = w1; w1 = w0; w0 = nx;
+          }
+          const int j0 = part * 4;
+          out[j0][lane] = a0;
+          if (p0 + 1 < n) out[j0 + 1][lane] = a1;
+          if (p0 + 2 < n) out[j0 + 2][lane] = a2;
+          if (p0 + 3 < n) out[j0 + 3][lane] = a3;
+        }
+      } else if (mf_global || alpf_n > 0) {
+        if (part == 0) {
+          const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+          for (int i = 0; i < cnt; ++i) {
+            float2 y = c.rb[(base + i) & c.rb_mask][lane];
+            if (mf_global) {
+              float accr = 0.0f, acci = 0.0f;
+              mfl[(2 * mf_ptr) * 32] = y.x; mfl[(2 * mf_ptr + 1) * 32] = y.y;
+              unsigned p = mf_ptr;
+              for (int t = 0; t < mf_n; ++t) {
+                const float b = __ldg(gtaps + t);
+                accr = __fmaf_rn(b, mfl[(2 * p) * 32], accr);
+                acci = __fmaf_rn(b, mfl[(2 * p + 1) * 32], acci);
+                p = p == 0 ? mf_n - 1 : p - 1;
+              }
+              mf_ptr = mf_ptr + 1 == (unsigned) mf_n ? 0 : mf_ptr + 1;
+              y = make_float2(accr, acci);
+            } else {
+              y = iir_any(alpf_n, al_b, al_a, al_x, al_xi, al_y, al_yi, y);
+            }
+            out[i][lane] = y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t p = base + (uint32_t) (part * 4 + j);
+          if (p < n) out[part * 4 + j][lane] = c.rb[p & c.rb_mask][lane];
+        }
+      }
+    }
+    cta_sync();
+  }
+  if (part == 0 && c.valid) {
+#pragma unroll
+    for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
+    if (mf_ring) {
+      float *gmf = c.bpool + (size_t) cp->st_mf_off * 32;
+      for (int k2 = 1; k2 < mf_n; ++k2) {
+        const float2 v = c.rb[(n - (unsigned) k2) & c.rb_mask][lane];
+        gmf[(2 * (k2 - 1)) * 32] = v.x; gmf[(2 * (k2 - 1) + 1) * 32] = v.y;
+      }
+    } else if (mf_global) {
+      stp->mf_ptr = mf_ptr;
+    }
+  }
+}
+
+// ---- step 6: clock recovery / sampler / resampler, CMA, decision, output (warp 10)
+static __device__ void role_clock(const ICtx &c, float2 *__restrict__ so, unsigned char *__restrict__ ho,
+                                  uint32_t *__restrict__ sym_count, size_t sym_cap)
+{
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane, cls = c.cls;
+  const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
+  ClockS ks; float clk_gain = 0, clk_alpha = 0, clk_beta = 0, smp_period = 0, smp_phase0 = 0, s_phase = 0, s_pr = 0, s_pi = 0;
+  int clock_type = 1, clock_running = 1, dec_mode = 0, dec_int = 1; float dec_min = 0, dec_h = 1;
+  float avol = 1, rs_prev = 0; double rs_step = 0, rs_phase = 0;
+  int eq_type = 0, eq_locked = 0; float eq_mu = 0;
+  uint32_t nout = 0;
+  ks.phi = ks.bnor = ks.x0r = ks.x0i = ks.x1r = ks.x1i = ks.x2r = ks.x2i = ks.pr = ks.pi = 0; ks.half = 0;
+  if (c.valid) {
+    ks.phi = stp->k_phi; ks.bnor = stp->k_bnor; ks.x0r = stp->k_x0r; ks.x0i = stp->k_x0i; ks.x1r = stp->k_x1r;
+    ks.x1i = stp->k_x1i; ks.x2r = stp->k_x2r; ks.x2i = stp->k_x2i; ks.pr = stp->k_pr; ks.pi = stp->k_pi;
+    ks.half = stp->k_half;
+    clk_gain = cp->clk_gain; clk_alpha = cp->clk_alpha; clk_beta = cp->clk_beta;
+    smp_period = cp->smp_period; smp_phase0 = cp->smp_phase0; s_phase = stp->s_phase; s_pr = stp->s_pr; s_pi = stp->s_pi;
+    clock_type = cp->clock_type; clock_running = cp->clock_running;
+    dec_mode = cp->dec_mode; dec_int = cp->dec_intervals; dec_min = cp->dec_min; dec_h = cp->dec_h;
+    avol = cp->audio_volume; rs_prev = stp->rs_prev; rs_step = cp->rs_step; rs_phase = stp->rs_phase;
+    eq_type = cp->eq_type; eq_locked = cp->eq_locked; eq_mu = cp->eq_mu;
+    if (eq_type == 1) {
+      for (int i = 0; i < SDB_EQ_LEN; ++i) {
+        c.eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
+        c.eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
+      }
+    }
+  }
+  const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+#ifdef SDB_STAGE_CYCLES
+  long long busy = 0;
+#endif
+  for (uint32_t it = 0; it <= total; ++it) {
+#ifdef SDB_STAGE_CYCLES
+    const long long t0 = clock64();
+#endif
+    if (it >= 6 && it - 6 < c.nchunks) {
+      const uint32_t ck = it - 6, base = ck * CH;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*in)[32] = sm.ringC[ck & 1];
+      for (int i = 0; i < cnt; ++i) {
+        float2 y = in[i][lane], o;
+        if (cls == SDB_INSP_RAW) {
+          if (nout < sym_cap) { so[nout] = y; ho[nout] = 0; ++nout; }
+        } else if (cls == SDB_INSP_AUDIO) {
+          rs_phase += rs_step;
+          if (rs_phase >= 1.0) {
+            rs_phase -= 1.0;
+            float al = (float) (rs_phase / rs_step);
+            if (al > 1.0f) al = 1.0f;
+            if (nout < sym_cap) {
+              so[nout] = make_float2(avol * ((1.0f - al) * y.x + al * rs_prev), 0.0f);
+              ho[nout] = 0;
+              ++nout;
+            }
+          }
+          rs_prev = y.x;
+        } else {
+          bool produced;
+          if (clock_type == 1) produced = clock_step(clk_gain, clk_alpha, clk_beta, ks, y, o);
+          else                 produced = sampler_step(smp_period, smp_phase0, s_phase, s_pr, s_pi, y, o);
+          if (produced && eq_type == 1) o = cma_step(c.eqw, c.eqx, lane, eq_mu, eq_locked, o);
+          if (produced && clock_running && nout < sym_cap) {
+            o.x = 0.75f * o.x; o.y = 0.75f * o.y;
+            so[nout] = o;
+            ho[nout] = decide(dec_mode, dec_min, dec_h, dec_int, o);
+            ++nout;
+          }
+        }
+      }
+    }
+#ifdef SDB_STAGE_CYCLES
+    busy += clock64() - t0;
+#endif
+    cta_sync();
+  }
+#ifdef SDB_STAGE_CYCLES
+  if (lane == 0) atomicAdd(&g_stage_cycles[3], (unsigned long long) busy);
+#endif
+  if (c.valid) {
+    stp->k_phi = ks.phi; stp->k_bnor = ks.bnor; stp->k_x0r = ks.x0r; stp->k_x0i = ks.x0i; stp->k_x1r = ks.x1r;
+    stp->k_x1i = ks.x1i; stp->k_x2r = ks.x2r; stp->k_x2i = ks.x2i; stp->k_pr = ks.pr; stp->k_pi = ks.pi;
+    stp->k_half = ks.half; stp->s_phase = s_phase; stp->s_pr = s_pr; stp->s_pi = s_pi;
+    stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
+    if (eq_type == 1) {
+      for (int i = 0; i < SDB_EQ_LEN; ++i) {
+        stp->eq_wr[i] = c.eqw[i][lane].x; stp->eq_wi[i] = c.eqw[i][lane].y;
+        stp->eq_xr[i] = c.eqx[i][lane].x; stp->eq_xi[i] = c.eqx[i][lane].y;
+      }
+    }
+    *sym_count = nout;
+  }
+}
+
+__global__ void __launch_bounds__(INSP_WARPS * 32, 2) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
+                                                     int n_streams, const int *__restrict__ chain_map,
+                                                     SdbChainState *__restrict__ states,
                                                      float *__restrict__ pool, size_t pool_stride,
                                                      const float *__restrict__ taps_pool,
                                                      const SdbChannelDev *__restrict__ chans,
@@ -324,440 +834,59 @@ __global__ void __launch_bounds__(128) k_inspectors(const SdbChainCfg *__restric
                                                      const SdbInspDyn dyn)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
-  const int mf_slots = dyn.mf_slots, agc_rows = dyn.agc_rows;
-  float2 (*s_mfh)[32] = reinterpret_cast<float2 (*)[32]>(smem_raw + sizeof(ChainSmem));
-  float (*s_agc)[32] = reinterpret_cast<float (*)[32]>(smem_raw + sizeof(ChainSmem) + (size_t) mf_slots * 32 * sizeof(float2));
-  float2 (*s_eqw)[32] = reinterpret_cast<float2 (*)[32]>(reinterpret_cast<unsigned char *>(s_agc) + (size_t) agc_rows * 32 * sizeof(float));
-  float2 (*s_eqx)[32] = s_eqw + SDB_EQ_LEN;
+  ICtx c;
+  c.sm = reinterpret_cast<ChainSmem *>(smem_raw);
+  unsigned char *dp = smem_raw + sizeof(ChainSmem);
+  c.rb = reinterpret_cast<float2 (*)[32]>(dp); dp += (size_t) dyn.rb_slots * 32 * sizeof(float2);
+  c.rb_mask = (unsigned) dyn.rb_slots - 1u;
+  c.taps = reinterpret_cast<float (*)[32]>(dp); dp += (size_t) dyn.mf_rows * 32 * sizeof(float);
+  c.agc = reinterpret_cast<float (*)[32]>(dp); dp += (size_t) dyn.agc_rows * 32 * sizeof(float);
+  c.agc_rows = dyn.agc_rows;
+  c.eqw = reinterpret_cast<float2 (*)[32]>(dp); c.eqx = c.eqw + SDB_EQ_LEN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chains = n_channels * n_streams;
-  const int g = blockIdx.x * 32 + lane;                // channel-major chain index
-  const bool valid = g < chains;
+  const int slot = blockIdx.x * 32 + lane;
+  // chain_map: CTA slot -> channel-major chain index k * S + s, or -1 (padding so that a CTA holds one class)
+  const int g = chain_map ? chain_map[slot] : (slot < chains ? slot : -1);
+  const bool valid = g >= 0;
   const int k = valid ? g / n_streams : 0, s = valid ? g - k * n_streams : 0;
   const int chain = s * n_channels + k;                // index into states / outputs (stream-major)
-  const SdbChainCfg *__restrict__ cp = cfgs + k;
-  const int cls = valid ? cp->cls : -1;
-  const uint32_t n = valid ? n_hops * (uint32_t) chans[k].halfsz : 0;
-  // per-CTA pool, interleaved [slot][lane]
-  float *bpool = pool + (size_t) blockIdx.x * 32 * pool_stride + lane;
-  // number of chunks: CTA-wide maximum
+  c.lane = lane; c.valid = valid ? 1 : 0; c.fresh = fresh;
+  c.cp = cfgs + k; c.stp = states + chain;
+  c.cls = valid ? c.cp->cls : -1;
+  c.n = valid ? n_hops * (uint32_t) chans[k].halfsz : 0;
+  c.bpool = pool + (size_t) blockIdx.x * 32 * pool_stride + lane;     // per-CTA pool, interleaved [slot][lane]
   __shared__ uint32_t s_nmax;
   if (threadIdx.x == 0) s_nmax = 0;
   __syncthreads();
-  if (warp == 0) atomicMax(&s_nmax, n);
+  if (warp == 0) atomicMax(&s_nmax, c.n);
   __syncthreads();
-  const uint32_t nchunks = (s_nmax + CHUNK - 1) / CHUNK;
-  SdbChainState *__restrict__ stp = states + chain;
+  c.nchunks = (s_nmax + CH - 1) / CH;
 
-  // ------------------------------------------------------------------ stage set-up (registers)
-  // stage 0
-  AgcK ak; AgcS as; float lo_phi = 0.0f, lo_omega = 0.0f, gain2 = 1.0f;
-  int have_agc = 0, have_lo = 0;
-  float *dl = nullptr, *mh = nullptr;
-  // stage 1
-  CostasK ck; CostasS cs; float p_phi = 0, p_omega = 0, pll_a = 0, pll_b = 0, prev_re = 0, prev_im = 0;
-  float rot_re = 1, rot_im = 0, dc = 0, sq_level = 0, dc_alpha = 0, sq_alpha = 0, sq_thr = 0;
-  int have_costas = 0, have_pll = 0, quad = 0, ask_ch = 0, ademod = 0, asquelch = 0;
-  // stage 2
-  int mf_n = 0, have_mf = 0, alpf_n = 0; unsigned mf_ptr = 0; bool mf_smem = false; const float *taps = nullptr; float *mfl = nullptr;
-  float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
-  float tp[32];     // matched-filter taps in registers when mf_n <= 32
-  // stage 3
-  ClockS ks; float clk_gain = 0, clk_alpha = 0, clk_beta = 0, smp_period = 0, smp_phase0 = 0, s_phase = 0, s_pr = 0, s_pi = 0;
-  int clock_type = 1, clock_running = 1, dec_mode = 0, dec_int = 1; float dec_min = 0, dec_h = 1;
-  float avol = 1, rs_prev = 0; double rs_step = 0, rs_phase = 0;
-  int eq_type = 0, eq_locked = 0; float eq_mu = 0;
-  uint32_t nout = 0;
-
-  if (valid) {
-    if (warp == 0) {
-      have_agc = cp->have_agc; have_lo = cls != SDB_INSP_AUDIO ? cp->have_lo : 0;
-      gain2 = cls == SDB_INSP_AUDIO ? 1.0f : cp->gain2;
-      lo_omega = cp->lo_omega; lo_phi = stp->lo_phi;
-      ak.knee = cp->knee; ak.slope_m1 = cp->gain_slope - 1.0f; ak.fixed_gain = cp->fixed_gain;
-      ak.far_ = cp->far_; ak.faf = cp->faf; ak.sar = cp->sar; ak.saf = cp->saf;
-      ak.hang_max = cp->hang_max; ak.dl_size = cp->dl_size; ak.mh_size = cp->mh_size;
-      as.fast = stp->fast_level; as.slow = stp->slow_level; as.peak = stp->peak;
-      as.hang_n = stp->hang_n; as.dl_ptr = stp->dl_ptr; as.mh_ptr = stp->mh_ptr;
-      const bool in_smem = 2 * ak.dl_size + ak.mh_size <= (unsigned) agc_rows;
-      float *gdl = bpool + (size_t) cp->st_dl_off * 32, *gmh = bpool + (size_t) cp->st_mh_off * 32;
-      if (in_smem && have_agc) {
-        dl = &s_agc[0][lane]; mh = &s_agc[2 * ak.dl_size][lane];
-        for (unsigned i = 0; i < 2 * ak.dl_size; ++i) dl[i * 32] = fresh ? 0.0f : gdl[i * 32];
-        for (unsigned i = 0; i < ak.mh_size; ++i) mh[i * 32] = fresh ? -160.0f : gmh[i * 32];
-      } else {
-        dl = gdl; mh = gmh;
-        if (fresh && have_agc) {
-          for (unsigned i = 0; i < 2 * ak.dl_size; ++i) dl[i * 32] = 0.0f;
-          for (unsigned i = 0; i < ak.mh_size; ++i) mh[i * 32] = -160.0f;
-        }
-      }
-    } else if (warp == 1) {
-      have_costas = cp->have_costas; have_pll = cp->have_pll;
-      ck.kind = cp->costas_kind; ck.af_n = cp->af_n; ck.a = cp->c_a; ck.b = cp->c_b;
-#pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) {
-        ck.af_b[i] = cp->af_b[i]; ck.af_a[i] = cp->af_a[i];
-        cs.xr[i] = stp->afx_re[i]; cs.xi[i] = stp->afx_im[i]; cs.yr[i] = stp->afy_re[i]; cs.yi[i] = stp->afy_im[i];
-      }
-      cs.phi = stp->c_phi; cs.omega = stp->c_omega; cs.lock = stp->c_lock; cs.yre = stp->c_yre; cs.yim = stp->c_yim;
-      p_phi = stp->p_phi; p_omega = stp->p_omega; pll_a = cp->pll_alpha; pll_b = cp->pll_beta;
-      prev_re = stp->prev_re; prev_im = stp->prev_im;
-      rot_re = cp->fsk_rot_re; rot_im = cp->fsk_rot_im; quad = cp->fsk_quad_demod; ask_ch = cp->ask_channel;
-      ademod = cp->audio_demod; asquelch = cp->audio_squelch; dc = stp->dc; sq_level = stp->sq_level;
-      dc_alpha = cp->dc_alpha; sq_alpha = cp->sq_alpha; sq_thr = cp->sq_thr;
-      if (cls == SDB_INSP_AUDIO) { lo_phi = stp->lo_phi; lo_omega = cp->lo_omega; }
-    } else if (warp == 2) {
-      have_mf = cp->have_mf; mf_n = cp->mf_n; mf_ptr = stp->mf_ptr; taps = taps_pool + cp->mf_off;
-      alpf_n = cls == SDB_INSP_AUDIO ? cp->alpf_n : 0;
-#pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) {
-        al_b[i] = cp->alpf_b[i]; al_a[i] = cp->alpf_a[i]; al_x[i] = stp->al_x[i]; al_y[i] = stp->al_y[i];
-        al_xi[i] = 0.0f; al_yi[i] = 0.0f;
-      }
-#pragma unroll
-      for (int t = 0; t < 32; ++t) tp[t] = (have_mf && t < mf_n) ? __ldg(taps + t) : 0.0f;
-      float *gmf = bpool + (size_t) cp->st_mf_off * 32;
-      for (int i = 0; i < mf_slots; ++i) s_mfh[i][lane] = make_float2(0.f, 0.f);
-      mf_smem = have_mf && (mf_n <= 32 ? 8 + 2 * mf_n <= mf_slots : mf_n <= mf_slots);
-      if (mf_smem) {
-        mfl = reinterpret_cast<float *>(&s_mfh[0][lane]);   // float2 ring, stride 32 float2 = 64 floats
-        for (int i = 0; i < mf_n; ++i) {
-          float2 v = fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * i) * 32], gmf[(2 * i + 1) * 32]);
-          if (mf_n <= 32) { s_mfh[8 + i][lane] = v; s_mfh[8 + i + mf_n][lane] = v; }   // duplicated line
-          else s_mfh[i][lane] = v;
-        }
-      } else {
-        mfl = gmf;
-        if (fresh && have_mf) for (int i = 0; i < 2 * mf_n; ++i) gmf[i * 32] = 0.0f;
-      }
-    } else {
-      ks.phi = stp->k_phi; ks.bnor = stp->k_bnor; ks.x0r = stp->k_x0r; ks.x0i = stp->k_x0i; ks.x1r = stp->k_x1r;
-      ks.x1i = stp->k_x1i; ks.x2r = stp->k_x2r; ks.x2i = stp->k_x2i; ks.pr = stp->k_pr; ks.pi = stp->k_pi;
-      ks.half = stp->k_half;
-      clk_gain = cp->clk_gain; clk_alpha = cp->clk_alpha; clk_beta = cp->clk_beta;
-      smp_period = cp->smp_period; smp_phase0 = cp->smp_phase0; s_phase = stp->s_phase; s_pr = stp->s_pr; s_pi = stp->s_pi;
-      clock_type = cp->clock_type; clock_running = cp->clock_running;
-      dec_mode = cp->dec_mode; dec_int = cp->dec_intervals; dec_min = cp->dec_min; dec_h = cp->dec_h;
-      avol = cp->audio_volume; rs_prev = stp->rs_prev; rs_step = cp->rs_step; rs_phase = stp->rs_phase;
-      eq_type = cp->eq_type; eq_locked = cp->eq_locked; eq_mu = cp->eq_mu;
-      if (eq_type == 1) {
-        for (int i = 0; i < SDB_EQ_LEN; ++i) {
-          s_eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
-          s_eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
-        }
-      }
-    }
-  }
-  float2 *__restrict__ so = soft + (size_t) chain * sym_cap;
-  unsigned char *__restrict__ ho = hard + (size_t) chain * sym_cap;
-  // coalesced, asynchronous tile load: row r of the tile = CHUNK consecutive samples of the CTA's chain r
-  // (= lane r's own chain); lane L copies column L of every row.  Double-buffered one chunk ahead.
-  const unsigned long long rowp =
-      valid ? (unsigned long long) (chan_in + (size_t) s * chan_stream_stride + chans[k].out_off) : 0ull;
-  auto issue_tile = [&](uint32_t c) {
-    const uint32_t b0 = c * CHUNK;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const unsigned long long pr = __shfl_sync(0xffffffffu, rowp, r);
-      const uint32_t nr = __shfl_sync(0xffffffffu, n, r);
-      if (b0 + lane < nr) cp_async8(&sm.tile[c & 1][r][lane], (const float2 *) pr + b0 + lane);
-    }
-    cp_async_commit();
-  };
-  if (warp == 0 && nchunks > 0) issue_tile(0);
-  __syncthreads();
-
-  long long busy = 0;
-  for (uint32_t it = 0; it < nchunks + 3; ++it) {
-    const long long t_begin = clock64();
-    if (warp == 0) {
-      if (it < nchunks) {
-        const uint32_t base = it * CHUNK;
-        // chunk `it` was prefetched (cp.async) one iteration ago; start the copy of chunk it+1 now
-        if (it + 1 < nchunks) {
-          issue_tile(it + 1);
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
-        }
-        __syncwarp();
-        float2 (*out)[32] = sm.ring[0][it & 1];
-        float2 (*tl)[33] = sm.tile[it & 1];
-        const int cnt = base >= n ? 0 : (n - base < CHUNK ? (int) (n - base) : CHUNK);
-        if (have_agc && cls != SDB_INSP_RAW) {
-          // Same arithmetic as agc_step() per sample, regrouped so that the long independent parts
-          // (log10 of the magnitudes, 10^x of the gains) of different samples overlap; only the
-          // peak / level tracker in the middle is a true recurrence.
-          // pass 1: LO, delay-line swap, magnitude [dB]
-          unsigned dlp = as.dl_ptr;
-#pragma unroll 4
-          for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
-              float2 y = tl[lane][i];
-              if (have_lo) {
-                float2 ph = ncqo_read(lo_phi, lo_omega);
-                y = make_float2(y.x * ph.x + y.y * ph.y, y.y * ph.x - y.x * ph.y);
-              }
-              const unsigned dp = dlp;
-              dlp = dlp + 1 >= ak.dl_size ? 0 : dlp + 1;
-              const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
-              dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
-              out[i][lane] = xd;
-              sm.lvl[i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
-            }
-          }
-          as.dl_ptr = dlp;
-          // pass 2: magnitude history, running peak, fast / slow levels (serial)
-          for (int i = 0; i < cnt; ++i) {
-            const float m = sm.lvl[i][lane];
-            const float m_old = mh[as.mh_ptr * 32];
-            mh[as.mh_ptr * 32] = m;
-            if (++as.mh_ptr >= ak.mh_size) as.mh_ptr = 0;
-            if (m > as.peak) {
-              as.peak = m;
-            } else if (as.peak == m_old) {
-              float pk = -160.0f;
-              for (unsigned q = 0; q < ak.mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
-              as.peak = pk;
-            }
-            float d = as.peak - as.fast;
-            if (d > 0.0f) as.fast = as.fast + ak.far_ * d;
-            else          as.fast = as.fast + ak.faf * d;
-            d = as.peak - as.slow;
-            if (d > 0.0f) { as.slow = as.slow + ak.sar * d; as.hang_n = 0; }
-            else if (as.hang_n >= ak.hang_max) as.slow = as.slow + ak.saf * d;
-            else ++as.hang_n;
-            sm.lvl[i][lane] = as.fast > as.slow ? as.fast : as.slow;
-          }
-          // pass 3: gain and scaling of the delayed sample
-#pragma unroll 4
-          for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
-              const float lvl = sm.lvl[i][lane];
-              float g = lvl < ak.knee ? ak.fixed_gain : d_db_to_mag(lvl * ak.slope_m1);
-              g = g * 0.7f;
-              float2 y = out[i][lane];
-              y.x = y.x * g; y.y = y.y * g;
-              if (cls != SDB_INSP_AUDIO) { y.x = 2.0f * y.x; y.y = 2.0f * y.y; }
-              out[i][lane] = y;
-            }
-          }
-        } else {
-          for (int i = 0; i < cnt; ++i) {
-            float2 y = tl[lane][i];
-            if (have_lo) {
-              float2 ph = ncqo_read(lo_phi, lo_omega);
-              y = make_float2(y.x * ph.x + y.y * ph.y, y.y * ph.x - y.x * ph.y);
-            }
-            if (cls != SDB_INSP_RAW && cls != SDB_INSP_AUDIO) { y.x = gain2 * y.x; y.y = gain2 * y.y; }
-            out[i][lane] = y;
-          }
-        }
-        __syncwarp();
-      }
-    } else if (warp == 1) {
-      if (it >= 1 && it < nchunks + 1) {
-        const uint32_t c = it - 1, base = c * CHUNK;
-        float2 (*in)[32] = sm.ring[0][c & 1];
-        float2 (*out)[32] = sm.ring[1][c & 1];
-        for (int i = 0; i < CHUNK; ++i) {
-          if (base + i < n) {
-            float2 y = in[i][lane];
-            if (cls == SDB_INSP_PSK) {
-              if (have_costas) y = costas_step(ck, cs, y);
-            } else if (cls == SDB_INSP_FSK) {
-              float dr = y.x * prev_re + y.y * prev_im;
-              float di = y.y * prev_re - y.x * prev_im;
-              prev_re = y.x; prev_im = y.y;
-              if (quad) { y.x = d_atan2f(di, dr) * 0.318309886183790671538f; y.y = 0.0f; }
-              else { y.x = dr * rot_re - di * rot_im; y.y = dr * rot_im + di * rot_re; }
-            } else if (cls == SDB_INSP_ASK) {
-              if (have_pll) y = pll_step(pll_a, pll_b, p_phi, p_omega, y);
-              if (ask_ch == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
-              else if (ask_ch == 1) { y.y = 0.0f; }
-              else                  { y.x = y.y; y.y = 0.0f; }
-            } else if (cls == SDB_INSP_AUDIO) {
-              float v = 0.0f;
-              float p = y.x * y.x + y.y * y.y;
-              sq_level = sq_level + sq_alpha * (p - sq_level);
-              if (ademod == SDB_AUDIO_AM) {
-                v = d_cabsf(y.x, y.y);
-                dc = dc + dc_alpha * (v - dc);
-                v = v - dc;
-              } else if (ademod == SDB_AUDIO_FM) {
-                float dr = y.x * prev_re + y.y * prev_im;
-                float di = y.y * prev_re - y.x * prev_im;
-                v = d_atan2f(di, dr) * 0.318309886183790671538f;
-                prev_re = y.x; prev_im = y.y;
-              } else if (ademod == SDB_AUDIO_USB || ademod == SDB_AUDIO_LSB) {
-                float2 ph = ncqo_read(lo_phi, lo_omega);
-                v = y.x * ph.x - y.y * ph.y;
-              }
-              if (asquelch && !(sq_level > sq_thr)) v = 0.0f;
-              y = make_float2(v, 0.0f);
-            }
-            out[i][lane] = y;
-          }
-        }
-      }
-    } else if (warp == 2) {
-      if (it >= 2 && it < nchunks + 2) {
-        const uint32_t c = it - 2, base = c * CHUNK;
-        float2 (*in)[32] = sm.ring[1][c & 1];
-        float2 (*out)[32] = sm.ring[2][c & 1];
-        for (int i = 0; i < CHUNK; ++i) {
-          if (base + i < n) {
-            float2 y = in[i][lane];
-            if (have_mf) {
-              float accr = 0.0f, acci = 0.0f;
-              if (mf_smem && mf_n <= 32) {
-                // taps in registers, duplicated line, branch-free unrolled sum (see mf_fir)
-                s_mfh[8 + mf_ptr][lane] = y;
-                s_mfh[8 + mf_ptr + mf_n][lane] = y;
-                float2 r;
-                if (mf_n <= 8)       r = mf_fir<8>(s_mfh, lane, mf_ptr, mf_n, tp);
-                else if (mf_n <= 16) r = mf_fir<16>(s_mfh, lane, mf_ptr, mf_n, tp);
-                else if (mf_n <= 24) r = mf_fir<24>(s_mfh, lane, mf_ptr, mf_n, tp);
-                else                 r = mf_fir<32>(s_mfh, lane, mf_ptr, mf_n, tp);
-                accr = r.x; acci = r.y;
-              } else if (mf_smem) {
-                // single line, two contiguous runs (newest ... slot 0, then slot mf_n-1 ... oldest): same tap order
-                // as SPEC I.1, but every address is affine in t, so the loads pipeline (the former per-tap
-                // "p = p ? p-1 : mf_n-1" chain made the 38-tap ASK filter of cfg3 the slowest stage of the kernel)
-                s_mfh[mf_ptr][lane] = y;
-                const int p0 = (int) mf_ptr;
-                const float2 *l0 = &s_mfh[p0][lane];
-                int t = 0;
-#pragma unroll 4
-                for (; t <= p0; ++t) {
-                  const float b = __ldg(taps + t);
-                  const float2 v = l0[-t * 32];
-                  accr = accr + b * v.x;
-                  acci = acci + b * v.y;
-                }
-#pragma unroll 4
-                for (; t < mf_n; ++t) {
-                  const float b = __ldg(taps + t);
-                  const float2 v = s_mfh[mf_n + p0 - t][lane];
-                  accr = accr + b * v.x;
-                  acci = acci + b * v.y;
-                }
-              } else {
-                mfl[(2 * mf_ptr) * 32] = y.x; mfl[(2 * mf_ptr + 1) * 32] = y.y;
-                unsigned p = mf_ptr;
-                for (int t = 0; t < mf_n; ++t) {
-                  const float b = __ldg(taps + t);
-                  accr = accr + b * mfl[(2 * p) * 32];
-                  acci = acci + b * mfl[(2 * p + 1) * 32];
-                  p = p == 0 ? mf_n - 1 : p - 1;
-                }
-              }
-              mf_ptr = mf_ptr + 1 == (unsigned) mf_n ? 0 : mf_ptr + 1;
-              y = make_float2(accr, acci);
-            } else if (alpf_n > 0) {
-              y = iir_any(alpf_n, al_b, al_a, al_x, al_xi, al_y, al_yi, y);
-            }
-            out[i][lane] = y;
-          }
-        }
-      }
-    } else {
-      if (it >= 3) {
-        const uint32_t c = it - 3, base = c * CHUNK;
-        float2 (*in)[32] = sm.ring[2][c & 1];
-        for (int i = 0; i < CHUNK; ++i) {
-          if (base + i < n) {
-            float2 y = in[i][lane], o;
-            if (cls == SDB_INSP_RAW) {
-              if (nout < sym_cap) { so[nout] = y; ho[nout] = 0; ++nout; }
-            } else if (cls == SDB_INSP_AUDIO) {
-              rs_phase += rs_step;
-              if (rs_phase >= 1.0) {
-                rs_phase -= 1.0;
-                float al = (float) (rs_phase / rs_step);
-                if (al > 1.0f) al = 1.0f;
-                if (nout < sym_cap) {
-                  so[nout] = make_float2(avol * ((1.0f - al) * y.x + al * rs_prev), 0.0f);
-                  ho[nout] = 0;
-                  ++nout;
-                }
-              }
-              rs_prev = y.x;
-            } else {
-              bool produced;
-              if (clock_type == 1) produced = clock_step(clk_gain, clk_alpha, clk_beta, ks, y, o);
-              else                 produced = sampler_step(smp_period, smp_phase0, s_phase, s_pr, s_pi, y, o);
-              if (produced && eq_type == 1) o = cma_step(s_eqw, s_eqx, lane, eq_mu, eq_locked, o);
-              if (produced && clock_running && nout < sym_cap) {
-                o.x = 0.75f * o.x; o.y = 0.75f * o.y;
-                so[nout] = o;
-                ho[nout] = decide(dec_mode, dec_min, dec_h, dec_int, o);
-                ++nout;
-              }
-            }
-          }
-        }
-      }
-    }
-    busy += clock64() - t_begin;
-    __syncthreads();
-  }
-  if (lane == 0) {   // stage balance bookkeeping (profiles/): busy cycles per stage, samples processed
-    atomicAdd(&g_stage_cycles[warp], (unsigned long long) busy);
-    if (warp == 0) atomicAdd(&g_stage_cycles[4], (unsigned long long) nchunks * CHUNK);
-  }
-
-  // ------------------------------------------------------------------ write state back
-  if (valid) {
-    if (warp == 0) {
-      stp->fast_level = as.fast; stp->slow_level = as.slow; stp->peak = as.peak;
-      stp->hang_n = as.hang_n; stp->dl_ptr = as.dl_ptr; stp->mh_ptr = as.mh_ptr;
-      if (cls != SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
-      if (have_agc && 2 * ak.dl_size + ak.mh_size <= (unsigned) agc_rows) {
-        float *gdl = bpool + (size_t) cp->st_dl_off * 32, *gmh = bpool + (size_t) cp->st_mh_off * 32;
-        for (unsigned i = 0; i < 2 * ak.dl_size; ++i) gdl[i * 32] = dl[i * 32];
-        for (unsigned i = 0; i < ak.mh_size; ++i) gmh[i * 32] = mh[i * 32];
-      }
-    } else if (warp == 1) {
-#pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) {
-        stp->afx_re[i] = cs.xr[i]; stp->afx_im[i] = cs.xi[i]; stp->afy_re[i] = cs.yr[i]; stp->afy_im[i] = cs.yi[i];
-      }
-      stp->c_phi = cs.phi; stp->c_omega = cs.omega; stp->c_lock = cs.lock; stp->c_yre = cs.yre; stp->c_yim = cs.yim;
-      stp->p_phi = p_phi; stp->p_omega = p_omega; stp->prev_re = prev_re; stp->prev_im = prev_im;
-      stp->dc = dc; stp->sq_level = sq_level;
-      if (cls == SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
-    } else if (warp == 2) {
-      stp->mf_ptr = mf_ptr;
-#pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
-      if (mf_smem) {
-        float *gmf = bpool + (size_t) cp->st_mf_off * 32;
-        for (int i = 0; i < mf_n; ++i) {
-          float2 v = mf_n <= 32 ? s_mfh[8 + i][lane] : s_mfh[i][lane];
-          gmf[(2 * i) * 32] = v.x; gmf[(2 * i + 1) * 32] = v.y;
-        }
-      }
-    } else {
-      stp->k_phi = ks.phi; stp->k_bnor = ks.bnor; stp->k_x0r = ks.x0r; stp->k_x0i = ks.x0i; stp->k_x1r = ks.x1r;
-      stp->k_x1i = ks.x1i; stp->k_x2r = ks.x2r; stp->k_x2i = ks.x2i; stp->k_pr = ks.pr; stp->k_pi = ks.pi;
-      stp->k_half = ks.half; stp->s_phase = s_phase; stp->s_pr = s_pr; stp->s_pi = s_pi;
-      stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
-      if (eq_type == 1) {
-        for (int i = 0; i < SDB_EQ_LEN; ++i) {
-          stp->eq_wr[i] = s_eqw[i][lane].x; stp->eq_wi[i] = s_eqw[i][lane].y;
-          stp->eq_xr[i] = s_eqx[i][lane].x; stp->eq_xi[i] = s_eqx[i][lane].y;
-        }
-      }
-      sym_counts[chain] = nout;
-    }
+  if (warp == W_TRACK) {
+    role_track(c, valid ? chan_in + (size_t) s * chan_stream_stride + chans[k].out_off : nullptr);
+  } else if (warp < W_POST) {
+    role_pre(c, warp - W_PRE);
+  } else if (warp < W_CARRIER) {
+    role_post(c, warp - W_POST);
+  } else if (warp == W_CARRIER) {
+    role_carrier(c);
+  } else if (warp < W_CLOCK) {
+    role_filter(c, warp - W_MF, taps_pool);
+  } else {
+    role_clock(c, soft + (size_t) chain * sym_cap, hard + (size_t) chain * sym_cap, sym_counts + chain, sym_cap);
   }
 }
 
+size_t sdb_inspector_smem_bytes(const SdbInspDyn &dyn)
+{
+  return sizeof(ChainSmem) + (size_t) dyn.rb_slots * 32 * sizeof(float2) + (size_t) dyn.mf_rows * 32 * sizeof(float) +
+         (size_t) dyn.agc_rows * 32 * sizeof(float) + (dyn.use_eq ? 2 * (size_t) SDB_EQ_LEN * 32 * sizeof(float2) : 0);
+}
+
 cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cfg_dev, int n_channels,
-                                    int n_streams, SdbChainState *state, float *pool, size_t pool_stride,
+                                    int n_streams, const int *chain_map, int n_ctas, SdbChainState *state,
+                                    float *pool, size_t pool_stride,
                                     const float *taps_pool, const SdbChannelDev *chans_dev,
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
                                     float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap, int fresh,
@@ -766,14 +895,12 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
   const int chains = n_channels * n_streams;
   if (chains == 0) return cudaSuccess;
   static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
-  if (sdb_first_on_device(attr_done)) {
+  if (sdb_first_on_device(attr_done))
     cudaFuncSetAttribute(k_inspectors, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
-  }
-  const size_t smem = sizeof(ChainSmem) + (size_t) dyn.mf_slots * 32 * sizeof(float2) +
-                      (size_t) dyn.agc_rows * 32 * sizeof(float) +
-                      (dyn.use_eq ? 2 * (size_t) SDB_EQ_LEN * 32 * sizeof(float2) : 0);
-  k_inspectors<<<(chains + 31) / 32, 128, smem, c.stream>>>(
-      cfg_dev, n_channels, n_streams, state, pool, pool_stride, taps_pool, chans_dev, chan_in,
+  const size_t smem = sdb_inspector_smem_bytes(dyn);
+  if (!chain_map) n_ctas = (chains + 31) / 32;
+  k_inspectors<<<n_ctas, INSP_WARPS * 32, smem, c.stream>>>(
+      cfg_dev, n_channels, n_streams, chain_map, state, pool, pool_stride, taps_pool, chans_dev, chan_in,
       chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap, fresh, dyn);
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();

@@ -107,6 +107,7 @@ struct sdb_engine {
   SdbChainCfg *d_cfg = nullptr; std::vector<SdbChainCfg> h_cfg;
   SdbChainState *d_state = nullptr;
   float *d_pool = nullptr; size_t pool_stride = 0;
+  int *d_chain_map = nullptr; int insp_ctas = 0; std::vector<int> h_chain_map;
   float *d_taps = nullptr;
   float2 *d_soft = nullptr; uint8_t *d_hard = nullptr; uint32_t *d_counts = nullptr; size_t sym_cap = 0;
   // channel detector on the main PSD (SPEC K; chdet_kernels.cu)
@@ -720,7 +721,11 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     const size_t chains = (size_t) S * K;
     e->d_cfg = e->dalloc<SdbChainCfg>(K);
     e->d_state = e->dalloc<SdbChainState>(chains);
-    const size_t pool_floats = ((chains + 31) / 32) * 32 * pool;   // per-CTA interleaved [slot][lane]
+    e->insp_ctas = sdb_build_chain_map(e->h_cfg.data(), K, (int) S, e->h_chain_map);
+    e->d_chain_map = e->dalloc<int>(e->h_chain_map.size());
+    if (!e->d_chain_map) return fail("out of device memory (chain map)");
+    CK(cudaMemcpy(e->d_chain_map, e->h_chain_map.data(), e->h_chain_map.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const size_t pool_floats = (size_t) e->insp_ctas * 32 * pool;   // per-CTA interleaved [slot][lane]
     e->d_pool = e->dalloc<float>(pool_floats);
     e->d_taps = e->dalloc<float>(taps_pool.size());
     for (int i = 0; i < 2; ++i) {
@@ -903,7 +908,8 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
                                e->chan_stride, (uint32_t) wps, e->d_spect, e->spect_stride, e->d_spect_size,
                                e->d_est, e->d_est_valid));
       e->span_begin(FAM_INSPECTOR, e->insp_stream);
-      CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_state, e->d_pool, e->pool_stride, e->d_taps,
+      CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_chain_map, e->insp_ctas, e->d_state, e->d_pool,
+                                 e->pool_stride, e->d_taps,
                                  e->d_chans, e->d_chanb[b], e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
                                  e->d_counts, e->sym_cap, e->chains_fresh ? 1 : 0,
                                  sdb_insp_dyn(e->h_cfg.data(), K)));
@@ -1406,7 +1412,7 @@ extern "C" long sdb_task_inspector(const sdb_inspector_config *cfg, const sdb_co
   CK(cudaMemcpy(d_cd, &cd, sizeof(cd), cudaMemcpyHostToDevice));
   SdbLaunchCtx ctx{ 0, nullptr };
   // every chain is "stream s, channel 0"; chan_stream_stride = n
-  CK(sdb_launch_inspectors_n(ctx, d_cfg, 1, (int) batch, d_st, d_pool, pool, d_taps, d_cd, d_src, n,
+  CK(sdb_launch_inspectors_n(ctx, d_cfg, 1, (int) batch, nullptr, 0, d_st, d_pool, pool, d_taps, d_cd, d_src, n,
                              (uint32_t) n, d_soft, d_hard, d_cnt, cap, 1, sdb_insp_dyn(&c, 1)));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(counts, d_cnt, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost));

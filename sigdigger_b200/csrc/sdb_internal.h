@@ -169,19 +169,24 @@ struct SdbSpectCfg {
 };
 
 // plan-dependent shared-memory lines of k_inspectors (chain_kernels.cu): sized from the channel plan
+#define SDB_INSP_CHUNK 16          // samples per pipeline chunk (CH in chain_kernels.cu)
+#define SDB_INSP_MF_RING_MAX 225   // longest matched filter served from the shared-memory ring (256 slots)
 struct SdbInspDyn {
-  int mf_slots;             // matched-filter line slots (8 + 2 n for n <= 32 taps, n above; >= 8)
+  int rb_slots;             // carrier ring slots (power of two >= longest ring-served filter - 1 + 2 chunks)
+  int mf_rows;              // tap rows [t][lane] of the longest ring-served matched filter
   int agc_rows;             // floats per chain for the AGC delay line + magnitude history
   int use_eq;               // some chain runs the CMA equaliser
 };
 static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
 {
-  SdbInspDyn d = { 8, 8, 0 };
+  SdbInspDyn d = { 2 * SDB_INSP_CHUNK, 1, 8, 0 };
   for (int k = 0; k < n; ++k) {
     const SdbChainCfg &c = cfgs[k];
-    if (c.have_mf) {
-      const int need = c.mf_n <= 32 ? 8 + 2 * c.mf_n : c.mf_n;
-      if (need <= 136 && need > d.mf_slots) d.mf_slots = need;          // longer filters stay in the global pool
+    if (c.have_mf && c.mf_n <= SDB_INSP_MF_RING_MAX) {        // longer filters stay in the global pool
+      int need = c.mf_n - 1 + 2 * SDB_INSP_CHUNK, slots = 2 * SDB_INSP_CHUNK;
+      while (slots < need) slots <<= 1;
+      if (slots > d.rb_slots) d.rb_slots = slots;
+      if (c.mf_n > d.mf_rows) d.mf_rows = c.mf_n;
     }
     if (c.have_agc) {
       const int need = (int) (2 * c.dl_size + c.mh_size);
@@ -191,6 +196,41 @@ static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
   }
   return d;
 }
+
+#ifdef __cplusplus
+#include <vector>
+#include <algorithm>
+// CTA slot -> chain (channel-major index k * S + s) or -1.  A CTA holds chains of ONE inspector class so that its
+// role warps do not diverge (a single source with a psk / fsk / ask mix would otherwise execute all three carrier
+// stages in every warp); the classes with the longest recurrences come first so that their CTAs start first.
+static inline int sdb_build_chain_map(const SdbChainCfg *cfgs, int K, int S, std::vector<int> &map)
+{
+  auto cost = [&](const SdbChainCfg &c) {          // rough per-sample cost order of the carrier stage
+    if (c.cls == 2) return c.have_pll ? 0 : 3;     // ask (PLL: atan2 + sincos in the loop)
+    if (c.cls == 0) return c.have_costas ? 1 : 3;  // psk
+    if (c.cls == 3) return 2;                      // audio
+    if (c.cls == 1) return 3;                      // fsk
+    return 4;                                      // raw
+  };
+  std::vector<int> order(K);
+  for (int k = 0; k < K; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const int ca = cost(cfgs[a]) * 8 + cfgs[a].cls, cb = cost(cfgs[b]) * 8 + cfgs[b].cls;
+    return ca < cb;
+  });
+  map.clear();
+  int prev_key = -1;
+  for (int idx = 0; idx < K; ++idx) {
+    const int k = order[idx];
+    const int key = cost(cfgs[k]) * 8 + cfgs[k].cls;
+    if (key != prev_key) while (map.size() % 32) map.push_back(-1);
+    prev_key = key;
+    for (int s = 0; s < S; ++s) map.push_back(k * S + s);
+  }
+  while (map.size() % 32) map.push_back(-1);
+  return (int) (map.size() / 32);
+}
+#endif
 
 // host-callable launchers ----------------------------------------------------------------------
 struct SdbLaunchCtx {
@@ -216,8 +256,12 @@ cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDe
                                        int n_streams, const float2 *cspec, int n_bins, int wps,
                                        float2 *tails, size_t tail_stream_stride, float *lo_phase,
                                        float2 *chan_out, size_t chan_stream_stride);
+size_t sdb_inspector_smem_bytes(const SdbInspDyn &dyn);
+// chain_map / n_ctas from sdb_build_chain_map (null: identity, (chains + 31) / 32 CTAs); the pool holds
+// n_ctas * 32 * pool_stride floats
 cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cfg_dev, int n_channels,
-                                    int n_streams, SdbChainState *state, float *pool, size_t pool_stride,
+                                    int n_streams, const int *chain_map, int n_ctas, SdbChainState *state,
+                                    float *pool, size_t pool_stride,
                                     const float *taps_pool, const SdbChannelDev *chans_dev,
                                     const float2 *chan_in, size_t chan_stream_stride, uint32_t n_hops,
                                     float2 *soft, uint8_t *hard, uint32_t *sym_counts, size_t sym_cap,

@@ -578,3 +578,31 @@ def test_channel_detector_known_answers(oracle):
     assert d3.d.n0 == np.float32(n0 + np.float32(0.25) * (np.float32(np.sort(p4[0])[N // 4]) - n0))
     for x in (d, d3):
         x.close()
+
+
+def test_fast_transform_of_the_cpu_baseline_matches_the_spec_transform(oracle):
+    """oracle/fft_fast.c (speed leg of bench.py's CPU arm) against numpy float64 and the SPEC transform: equal to
+    float32 rounding, forward and inverse, with and without a window.  It is never used for parity."""
+    import ctypes as C
+    L = oracle.lib()
+    L.sdo_fast_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int]
+    rng = np.random.default_rng(5)
+    for n in (8, 32, 1024, 2048, 65536):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        w = oracle.window(n, "blackmann_harris")
+        y = np.empty_like(x)
+        L.sdo_fast_fft(x.ctypes.data, w.ctypes.data, y.ctypes.data, n, -1)
+        ref = np.fft.fft(x.astype(np.complex128) * w)
+        assert np.max(np.abs(y - ref)) <= 2e-6 * np.max(np.abs(ref))
+        z = np.empty_like(x)
+        L.sdo_fast_fft(y.ctypes.data, None, z.ctypes.data, n, +1)
+        assert np.max(np.abs(z / n - x * w)) <= 5e-6 * np.max(np.abs(x))
+    # PSD of the SPEC transform and of the fast one agree to the parity tolerance of tests/parity.py (1e-5 of the peak)
+    n = 65536
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    spec = oracle.psd_frames(x, n, "blackmann_harris")[0]
+    y = np.empty_like(x)
+    w = oracle.window(n, "blackmann_harris")
+    L.sdo_fast_fft(x.ctypes.data, w.ctypes.data, y.ctypes.data, n, -1)
+    fast = (y.real.astype(np.float64) ** 2 + y.imag.astype(np.float64) ** 2) / n
+    assert np.max(np.abs(fast - spec)) <= 1e-5 * np.max(spec)
