@@ -433,62 +433,56 @@ def run_cuda(args):
     launches = e.launches - l0
     value = samples_step * world * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- per-kernel device times (separate, untimed-for-value pass with event spans)
+    # ---- per-kernel device times: a separate pass in the engine's timing mode, which queues every kernel on ONE
+    # stream (no two kernels overlap), so the CUDA-event spans recorded on that stream are the kernels' own warm
+    # durations; the ncu launch list of the same command is committed under profiles/ (shares must agree)
     e.timing(True)
-    sdb.stage_cycles(reset=True)
-    for _ in range(2):
+    timed_steps = 2
+    for _ in range(timed_steps):
         step_dev()
     e.sync()
-    stage_bal = sdb.stage_cycles(reset=True)
     fam = {f: e.kernel_time(f) for f in ("fft_cols", "fft_rows_psd", "fft_rows_chan", "chan_ifft", "inspector")}
     e.timing(False)
-    wps, frames = H, H // 2
-    timed_steps = 2
-    nb = sum(2 * (e.channel_info(h).width // 2) for h in hs)
-    # ALGORITHMIC bytes one step moves through each kernel family (DESIGN.md "Kernels"): pass A reads every
-    # window once (PSD frames + channeliser windows), pass B writes the PSD / the needed bins; the four-step
-    # scratch is not algorithmic.  Launches of a family differ in size (PSD and channeliser groups), so the
-    # rate is total bytes / total device time of the family over the timed steps.
-    alg = {"fft_cols": S * (frames + wps) * N_FFT * 8.0,
-           "fft_rows_psd": S * frames * N_FFT * 4.0,
-           "fft_rows_chan": S * wps * nb * 8.0,
-           "chan_ifft": S * wps * nb * 8.0 + sum(S * wps * e.channel_info(h).size // 2 * 8.0 for h in hs),
-           "inspector": sum(S * wps * e.channel_info(h).size // 2 * 8.0 for h in hs) * 1.5}
-    tot = {f: fam[f][0] * fam[f][1] for f in fam}
-    # the inspector kernel runs on its own stream, overlapped with the next feed's FFT kernels, and is bound by
-    # the serial latency of its recurrences, not by bandwidth: the roofline kernel is the dominant one of the
-    # engine's main (critical) stream
-    main = {f: tot[f] for f in tot if f != "inspector"}
-    dom = max(main, key=main.get)
+    # the algorithmic bytes of the path are B_alg per INPUT sample (8 B read once, shared by the PSD and
+    # the channeliser, + 4 B of PSD + 9 B per symbol); intermediate streams are not algorithmic.  The dominant
+    # kernel (largest total device time per step, the inspector kernel included) is charged with the B_alg of every
+    # input sample its launches cover: achieved = B_alg x samples per launch / average launch duration.
+    tot = {f: fam[f][0] * fam[f][1] / timed_steps for f in fam}            # ms of device time per step
+    dom = max(tot, key=tot.get)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach = alg[dom] * timed_steps / (tot[dom] * 1e-3) / 1e9 if tot[dom] > 0 else 0.0
-    launches_dom = max(1, int(fam[dom][1]))
+    launches_dom = max(1.0, fam[dom][1] / timed_steps)                     # launches per step
+    alg_launch = B_ALG[name] * samples_step / launches_dom
+    ach = alg_launch / (fam[dom][0] * 1e-3) / 1e9 if fam[dom][0] > 0 else 0.0
     traffic = None
-    try:   # DRAM bytes per window of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if dom in tr:
-            traffic = tr[dom]["dram_bytes_per_window"] * S * (frames + wps if dom == "fft_cols" else
-                                                               frames if dom == "fft_rows_psd" else wps) \
-                * timed_steps / launches_dom
+    try:   # DRAM bytes per launch of that kernel from the committed single-pass ncu capture of this workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if tr.get("workload") == name and dom in tr.get("kernels", {}):
+            traffic = tr["kernels"][dom]["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg[dom] * timed_steps / launches_dom,
-                "note": "CUDA-event spans; the PSD and channeliser chains run on two streams, so a kernel's span "
-                        "includes the share of the GPU its concurrent sibling takes",
+                "algorithmic_bytes_per_launch": alg_launch, "launch_ms": fam[dom][0],
+                "note": "B_alg (SURVEY 8d) x input samples covered by one launch / its duration; durations are "
+                        "CUDA-event spans of a serialised pass (one stream, no overlap). The kernel is bound by "
+                        "instruction issue / recurrence latency, not by DRAM (profiles/r02_*.md)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "kernel_share_of_step": tot[dom] / max(1e-9, sum(tot.values())),
-                "kernel_ms": {f: round(fam[f][0], 4) for f in fam},
-                "inspector_stage_cycles_per_sample": {k_: round(v_, 1) for k_, v_ in stage_bal.items()},
+                "kernel_share_of_device_time": tot[dom] / max(1e-9, sum(tot.values())),
+                "device_ms_per_step": {f: round(tot[f], 4) for f in tot},
+                "launch_ms_avg": {f: round(fam[f][0], 4) for f in fam},
                 "path": {"b_alg_bytes_per_sample": B_ALG[name],
                          "achieved": B_ALG[name] * value * 1e6 / world / 1e9,
                          "frac": B_ALG[name] * value * 1e6 / world / 1e9 / peak}}
+    if os.environ.get("SDB_LIB"):      # instrumented twin: busy cycles per role warp per chunk sample
+        sdb.stage_cycles(reset=True)
+        step_dev(); e.sync()
+        roofline["inspector_role_cycles_per_sample"] = {k_: round(v_, 1) for k_, v_ in sdb.stage_cycles(reset=True).items()}
+    wps, frames = H, H // 2
 
     # ---- end to end: pinned host IQ -> H2D -> path -> D2H of PSD frames and symbols, every step
     # Every step: H2D of that step's IQ from pinned memory, the whole path, D2H of its PSD frames and symbols

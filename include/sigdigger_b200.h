@@ -38,6 +38,10 @@ enum { SDB_AUDIO_DISABLED = 0, SDB_AUDIO_AM, SDB_AUDIO_FM, SDB_AUDIO_USB, SDB_AU
                                      (Suscan/Messages/PSDMessage.cpp:32-38) into the PSD kernel */
 #define SDB_FLAG_IQ_REVERSE   2u  /* suscan_analyzer_set_iq_reverse (Suscan/Analyzer.cpp:238-244): the source delivers
                                      (Q, I); swapped inside the first load of the path, any sample format */
+#define SDB_FLAG_DC_REMOVE    4u  /* suscan_analyzer_set_dc_remove (Suscan/Analyzer.cpp:229-236): block-wise single-pole
+                                     DC estimate subtracted from every sample before the PSD and the channeliser
+                                     see it (SPEC R: c += alpha (mean(block) - c), alpha = 1 - exp(-n / (fs 0.1 s)));
+                                     one extra pass that also converts native formats to float32 */
 
 /* Replaces struct suscan_analyzer_params.detector_params.{window_size, window}
  * (Suscan/AnalyzerParams.cpp:56-66) + the specttuner's sigutils_specttuner_params.window_size
@@ -114,6 +118,8 @@ void          sdb_engine_destroy(sdb_engine_t *e);
 /* su_specttuner_open_channel (Tasks/LPFTask.cpp:69) / suscan_analyzer_open_ex_async
  * (Suscan/Analyzer.cpp:459-484).  Returns the channel handle (SUHANDLE). */
 int sdb_engine_open_channel(sdb_engine_t *e, const sdb_channel_params *p, sdb_channel_info *info);
+/* the same geometry without an engine (su_specttuner_open_channel reports it before any data flows) */
+int sdb_channel_geometry(uint32_t window_size, const sdb_channel_params *p, sdb_channel_info *info);
 /* suscan_analyzer_set_inspector_config_async (Suscan/Analyzer.cpp:486-495) */
 int sdb_engine_set_inspector(sdb_engine_t *e, int handle, const sdb_inspector_config *cfg);
 /* fills cfg with the class defaults the OPEN message would carry
@@ -121,6 +127,17 @@ int sdb_engine_set_inspector(sdb_engine_t *e, int handle, const sdb_inspector_co
 int sdb_inspector_config_default(sdb_inspector_config *cfg, int insp_class, float fs);
 /* freezes the channel plan and allocates device buffers; required before the first feed */
 int sdb_engine_commit(sdb_engine_t *e);
+/* Live re-plan: `dst` (committed, not yet fed) takes over the running state of `src` (same streams / window /
+ * device): input history, and per channel with identical parameters the cross-fade tail, the LO phase and -- if the
+ * inspector class and the sizes of its state lines are unchanged -- the loop state of every chain.  This is how an
+ * analyzer opens, closes, retunes or reconfigures ONE inspector at a block boundary while the others keep running
+ * (suscan_analyzer_open_ex_async / close_async / set_inspector_config_async / set_inspector_freq_overridable,
+ * Suscan/Analyzer.cpp:459-526).  `src` is synchronised and left intact. */
+int sdb_engine_migrate(sdb_engine_t *dst, sdb_engine_t *src);
+/* the same with the caller saying which old channel each new one continues: old_of_new[new handle] = old handle or
+ * -1 (a retuned inspector keeps its loops even though its channel moved; only the cross-fade tail restarts) */
+int sdb_engine_migrate_map(sdb_engine_t *dst, sdb_engine_t *src, const int32_t *old_of_new, size_t n);
+int sdb_engine_same_geometry(const sdb_engine_t *a, const sdb_engine_t *b);   /* 1: migrate would accept the pair */
 
 /* One pass of the hot path over `n` new samples of every stream (the body of suscan's source-worker
  * loop, SURVEY.md 3.2 HOT LOOP #1 + 3.3 HOT LOOP #2).  n must be a multiple of the PSD size and of
@@ -243,6 +260,13 @@ int sdb_task_costas(const sdb_complex *src, sdb_complex *dst, size_t n, size_t b
                     float tau, float loop_bw);
 /* PLLSyncTask: su_pll_init(0, bw) + su_pll_track loop (Tasks/PLLSyncTask.cpp:36,53-56) */
 int sdb_task_pll(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float bw);
+/* Bulk twins of the per-sample su_costas_feed / su_pll_track of the sigutils-named shim (include/sigutils/pll.h): one
+ * buffer, the loop continues from the caller's state and the final state is written back, so consecutive work()
+ * blocks of a Tasks/ object (Tasks/CostasRecoveryTask.cpp:49-61) chain exactly.  k / s: the configuration and state
+ * members of su_costas_t (sizes checked); state[2] = {phi, omega}. */
+int sdb_task_costas_state(const sdb_complex *src, sdb_complex *dst, size_t n, const void *k, size_t k_bytes,
+                          void *s, size_t s_bytes);
+int sdb_task_pll_state(const sdb_complex *src, sdb_complex *dst, size_t n, float alpha, float beta, float state[2]);
 /* AGCTask: su_agc_init with tau fractions + su_agc_feed loop (Tasks/AGCTask.cpp:41-53,70-73) */
 int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, size_t batch, float tau);
 /* LPFTask: su_specttuner low-pass with guard = 2 pi / bw, output length == input length
@@ -493,8 +517,16 @@ int    sdb_analyzer_set_buffering_size(sdb_analyzer_t *a, uint64_t samples);
 int    sdb_analyzer_set_sweep_strategy(sdb_analyzer_t *a, int strategy);
 int    sdb_analyzer_set_spectrum_partitioning(sdb_analyzer_t *a, int partitioning);
 int    sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled);
+int    sdb_analyzer_set_dc_remove(sdb_analyzer_t *a, int enabled);        /* Suscan/Analyzer.cpp:229-236; SPEC R */
 int    sdb_analyzer_set_throttle_async(sdb_analyzer_t *a, uint64_t samp_rate, uint32_t req_id);
 int    sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *privdata);
+/* suscan_analyzer_register_baseband_filter_with_prio (Suscan/Analyzer.cpp:137-143): ascending priority value */
+int    sdb_analyzer_register_baseband_filter_prio(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *privdata,
+                                                  int64_t prio);
+/* suscan_analyzer_get_source_time (Suscan/Analyzer.cpp:145-149): signal time since the start of the source, seconds */
+double sdb_analyzer_get_source_time(const sdb_analyzer_t *a);
+/* configuration an open inspector currently runs with (the payload of a GET_CONFIG reply); -1: not open */
+int    sdb_analyzer_get_inspector_config(sdb_analyzer_t *a, int32_t handle, sdb_inspector_config *cfg);
 uint64_t sdb_analyzer_get_samp_rate(const sdb_analyzer_t *a);
 float    sdb_analyzer_get_measured_samp_rate(const sdb_analyzer_t *a);
 

@@ -17,6 +17,7 @@ INSP = {"psk": 0, "fsk": 1, "ask": 2, "audio": 3, "raw": 4}
 AUDIO = {"disabled": 0, "am": 1, "fm": 2, "usb": 3, "lsb": 4}
 FLAG_PSD_SHIFT_DB = 1
 FLAG_IQ_REVERSE = 2
+FLAG_DC_REMOVE = 4
 SPECTSRC = {"none": 0, "psd": 1, "cyclo": 2, "fmspect": 3, "timediff": 4, "abstimediff": 5, "exp_2": 6,
             "exp_4": 7, "exp_8": 8, "fac": 9}
 ESTIMATOR = {"baud-fac": 0, "baud-nonlinear": 1}
@@ -245,6 +246,10 @@ _PROTOS = {
     "sdb_engine_set_inspector": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "sdb_inspector_config_default": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "sdb_engine_commit": (C.c_int, [C.c_void_p]),
+    "sdb_engine_migrate": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_engine_migrate_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_same_geometry": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_channel_geometry": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p]),
     "sdb_engine_feed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sdb_engine_feed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sdb_engine_sync": (C.c_int, [C.c_void_p]),
@@ -285,6 +290,8 @@ _PROTOS = {
     "sdb_task_costas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_float]),
     "sdb_task_pll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_agc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
+    "sdb_task_costas_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "sdb_task_pll_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_void_p]),
     "sdb_task_lpf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float]),
     "sdb_task_delayed_conj": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "sdb_task_histogram_feed": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
@@ -318,6 +325,10 @@ _PROTOS = {
     "sdb_analyzer_set_sweep_strategy": (C.c_int, [C.c_void_p, C.c_int]),
     "sdb_analyzer_set_spectrum_partitioning": (C.c_int, [C.c_void_p, C.c_int]),
     "sdb_analyzer_set_iq_reverse": (C.c_int, [C.c_void_p, C.c_int]),
+    "sdb_analyzer_set_dc_remove": (C.c_int, [C.c_void_p, C.c_int]),
+    "sdb_analyzer_register_baseband_filter_prio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "sdb_analyzer_get_source_time": (C.c_double, [C.c_void_p]),
+    "sdb_analyzer_get_inspector_config": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "sdb_analyzer_set_throttle_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "sdb_analyzer_register_baseband_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdb_analyzer_inspector_set_spectrum_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32]),
@@ -374,9 +385,12 @@ def load_library():
     """dlopen the native library and bind every symbol the header declares. No fallback."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError("native library %s missing: run `python __graft_entry__.py` (build())" % LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+        # SDB_LIB selects the instrumented twin (libsigdigger_b200_prof.so: per-role cycle counters compiled into
+        # the inspector kernel) for profiles/; the product library is the default and the only one tests load
+        path = os.environ.get("SDB_LIB") or LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError("native library %s missing: run `python __graft_entry__.py` (build())" % path)
+        L = C.CDLL(path)
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)      # AttributeError if the .so does not export it
             fn.restype = res
@@ -403,12 +417,13 @@ class SdbError(RuntimeError):
 
 
 def stage_cycles(reset=False):
-    """Inspector-kernel stage balance: dict of busy cycles per stage per processed chunk-sample."""
+    """Inspector-kernel role balance: busy cycles per role warp per processed chunk-sample (zeros unless the
+    instrumented library is loaded, SDB_LIB=.../libsigdigger_b200_prof.so)."""
     buf = (C.c_uint64 * 8)()
     _check(load_library().sdb_debug_stage_cycles(buf, int(reset)))
     n = max(1, buf[4])
-    return {"gain": buf[0] / n, "carrier": buf[1] / n, "filter": buf[2] / n, "clock": buf[3] / n,
-            "chunk_samples": int(buf[4])}
+    return {"track": buf[0] / n, "pre": buf[5] / n, "post": buf[6] / n, "carrier": buf[1] / n, "filter": buf[2] / n,
+            "clock": buf[3] / n, "chunk_samples": int(buf[4])}
 
 
 def _check(rc):

@@ -37,7 +37,7 @@ namespace {
 struct Cmd {
   enum Kind { OPEN, SET_ID, SET_CONFIG, CLOSE, SET_PARAMS, SET_SPECTRUM, ESTIMATOR_CMD, SET_IQ_REVERSE, SET_THROTTLE, SET_WATERMARK,
               SET_FREQ, SET_BANDWIDTH, SEEK, SET_HOP_RANGE, SET_REL_BW, SET_BUFFERING, SET_STRATEGY,
-              SET_PARTITIONING, SET_HISTORY, REPLAY } kind;
+              SET_PARTITIONING, SET_HISTORY, REPLAY, SET_DC_REMOVE } kind;
   double value2 = 0;
   uint32_t req_id = 0;
   uint32_t aux_id = 0; int enabled = 0;       // spectrum source id / estimator id + enable flag
@@ -115,16 +115,18 @@ struct sdb_analyzer {
   size_t block = 0;
   std::atomic<double> measured_rate{ 0.0 };   // written by the worker, read by sdb_analyzer_get_measured_samp_rate
   uint64_t total_samples = 0;
+  std::atomic<uint64_t> total_samples_pub{ 0 };   // copy for readers on other threads
+  std::mutex insp_m;                              // guards insps against readers on other threads
   double psd_credit = 0;
   // source-side options of the worker loop (Suscan/Analyzer.cpp:117-135, 229-244; SourceWidget.cpp:1156-1184)
-  bool iq_reverse = false;
+  bool iq_reverse = false, dc_remove = false;
   double throttle = 0;                                  // samples / s, 0 = as fast as the source delivers
   std::chrono::steady_clock::time_point throttle_t0; uint64_t throttle_s0 = 0;
   // history ring + replay (suscan_analyzer_set_history_size / _replay, Suscan/Analyzer.cpp:157-167;
   // Default/Source/SourceWidget.cpp:1070-1073, 1206, 1508)
   std::vector<sdb_complex> hist; size_t hist_start = 0, hist_fill = 0, replay_pos = 0;
   bool replaying = false, replay_wrapped = false; int looped = 0;
-  struct BbFilter { sdb_baseband_filter_fn fn; void *priv; };
+  struct BbFilter { sdb_baseband_filter_fn fn; void *priv; int64_t prio; };
   std::vector<BbFilter> bb_filters;
 
   void post(uint32_t type, void *payload)
@@ -176,10 +178,18 @@ struct sdb_analyzer {
     post(SDB_ANALYZER_MESSAGE_TYPE_SAMPLES, m);
   }
 
-  // (re)build the engine from the open inspectors; returns false on failure (status message posted)
+  // (re)build the engine from the open inspectors at a block boundary.  The new engine takes over the running
+  // state of the old one (sdb_engine_migrate_map): input history, DC estimate, and for every inspector that stays
+  // open its cross-fade tail, LO phase and loop state -- opening, closing, retuning or reconfiguring ONE inspector
+  // leaves the sample streams of the others untouched (suscan keeps them running too, Suscan/Analyzer.cpp:459-537).
+  // Returns false on failure (status message posted).
   bool rebuild()
   {
-    if (eng) { sdb_engine_destroy(eng); eng = nullptr; }
+    sdb_engine_t *old = eng; eng = nullptr;
+    std::vector<Sub> old_subs; old_subs.swap(subs);
+    std::vector<int> old_handle(insps.size(), -1);
+    for (size_t q = 0; q < insps.size(); ++q) old_handle[q] = insps[q].engine_handle;
+    auto drop_old = [&] { if (old) sdb_engine_destroy(old); for (auto &s : old_subs) if (s.eng) sdb_engine_destroy(s.eng); };
     sdb_engine_params ep;
     memset(&ep, 0, sizeof(ep));
     ep.n_streams = 1;
@@ -188,11 +198,11 @@ struct sdb_analyzer {
     ep.st_window_size = 0;
     ep.max_feed = (uint32_t) block;
     ep.device = src.device;
-    ep.flags = iq_reverse ? SDB_FLAG_IQ_REVERSE : 0;
+    ep.flags = (iq_reverse ? SDB_FLAG_IQ_REVERSE : 0) | (dc_remove ? SDB_FLAG_DC_REMOVE : 0);
     ep.input_format = src.read ? SDB_FORMAT_FLOAT32 : src.input_format;
     eng = sdb_engine_new(&ep, src.samp_rate);
-    if (!eng) { post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error()); return false; }
-    drop_subs();
+    if (!eng) { drop_old(); post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error()); return false; }
+    std::vector<int32_t> old_of_new;
     for (auto &i : insps) {
       i.engine_handle = -1;
       if (!i.open || i.parent >= 0) continue;
@@ -205,6 +215,7 @@ struct sdb_analyzer {
       int h = sdb_engine_open_channel(eng, &cp, &info);
       if (h < 0) continue;
       i.engine_handle = h;
+      old_of_new.push_back(old_handle[(size_t) i.handle]);
       i.size = info.size;
       i.fs = (float) (src.samp_rate / info.decimation);
       i.bandwidth = (float) (i.channel.f_hi - i.channel.f_lo);
@@ -230,9 +241,12 @@ struct sdb_analyzer {
                                       params.detector_params.gamma,
                                       params.detector_params.snr > 0 ? params.detector_params.snr : 4.0f, 2);
     if (sdb_engine_commit(eng)) {
+      drop_old();
       post_status(SDB_ANALYZER_MESSAGE_TYPE_SOURCE_INIT, SDB_ANALYZER_INIT_FAILURE, sdb_last_error());
       return false;
     }
+    if (old && sdb_engine_same_geometry(eng, old))
+      sdb_engine_migrate_map(eng, old, old_of_new.data(), old_of_new.size());
     // sub-carrier engines: one per parent that has open children
     for (auto &p : insps) {
       if (!p.open || p.parent >= 0 || p.engine_handle < 0) continue;
@@ -246,6 +260,7 @@ struct sdb_analyzer {
       sp.device = src.device; sp.input_format = SDB_FORMAT_FLOAT32;
       sdb_engine_t *se = sdb_engine_new(&sp, (double) p.fs);
       if (!se) continue;
+      std::vector<int32_t> sub_old_of_new;
       for (auto &c : insps) {
         if (!c.open || c.parent != p.handle) continue;
         sdb_channel_params cp;
@@ -256,14 +271,19 @@ struct sdb_analyzer {
         int h = sdb_engine_open_channel(se, &cp, &info);
         if (h < 0) continue;
         c.engine_handle = h; c.size = info.size;
+        sub_old_of_new.push_back(old_handle[(size_t) c.handle]);
         c.fs = (float) ((double) p.fs / info.decimation);
         c.bandwidth = (float) (c.channel.f_hi - c.channel.f_lo); c.lo = (float) c.channel.fc;
         c.cfg.insp_class = c.cls;
         sdb_engine_set_inspector(se, h, &c.cfg);
       }
       if (sdb_engine_commit(se)) { sdb_engine_destroy(se); continue; }
+      for (auto &os : old_subs)
+        if (os.parent == p.handle && os.eng && sdb_engine_same_geometry(se, os.eng))
+          sdb_engine_migrate_map(se, os.eng, sub_old_of_new.data(), sub_old_of_new.size());
       subs.push_back(Sub{ p.handle, se });
     }
+    drop_old();
     plan_dirty = false;
     return true;
   }
@@ -272,6 +292,7 @@ struct sdb_analyzer {
   {
     std::deque<Cmd> todo;
     { std::lock_guard<std::mutex> l(cmd_m); todo.swap(cmds); }
+    std::lock_guard<std::mutex> il(insp_m);
     for (auto &c : todo) {
       switch (c.kind) {
         case Cmd::OPEN: {
@@ -402,6 +423,9 @@ struct sdb_analyzer {
         }
         case Cmd::SET_IQ_REVERSE:
           if (iq_reverse != (c.enabled != 0)) { iq_reverse = c.enabled != 0; plan_dirty = true; }
+          break;
+        case Cmd::SET_DC_REMOVE:
+          if (dc_remove != (c.enabled != 0)) { dc_remove = c.enabled != 0; plan_dirty = true; }
           break;
         case Cmd::SET_THROTTLE:
           throttle = c.value > 0 ? c.value : 0;
@@ -603,6 +627,7 @@ struct sdb_analyzer {
         exit_type = SDB_ANALYZER_MESSAGE_TYPE_READ_ERROR; break;
       }
       total_samples += block;
+      total_samples_pub.store(total_samples);
       if (throttle > 0) {                                // suscan_analyzer_set_throttle_async: pace to `throttle` samples/s
         const double due = (double) (total_samples - throttle_s0) / throttle;
         const double now = std::chrono::duration<double>(std::chrono::steady_clock::now() - throttle_t0).count();
@@ -891,6 +916,11 @@ extern "C" int sdb_analyzer_set_inspector_bandwidth_overridable(sdb_analyzer_t *
   Cmd c; c.kind = Cmd::SET_BANDWIDTH; c.handle = handle; c.value = bw;
   return push_cmd(a, std::move(c));
 }
+extern "C" int sdb_analyzer_set_dc_remove(sdb_analyzer_t *a, int enabled)
+{
+  Cmd c; c.kind = Cmd::SET_DC_REMOVE; c.enabled = enabled;
+  return push_cmd(a, std::move(c));
+}
 extern "C" int sdb_analyzer_set_iq_reverse(sdb_analyzer_t *a, int enabled)
 {
   Cmd c; c.kind = Cmd::SET_IQ_REVERSE; c.enabled = enabled;
@@ -901,11 +931,34 @@ extern "C" int sdb_analyzer_set_throttle_async(sdb_analyzer_t *a, uint64_t samp_
   Cmd c; c.kind = Cmd::SET_THROTTLE; c.req_id = req_id; c.value = (double) samp_rate;
   return push_cmd(a, std::move(c));
 }
-extern "C" int sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *priv)
+// suscan_analyzer_register_baseband_filter_with_prio (Suscan/Analyzer.cpp:137-143): filters run in ascending priority
+// value, registration order among equals; the plain registration uses priority 0
+extern "C" int sdb_analyzer_register_baseband_filter_prio(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *priv,
+                                                          int64_t prio)
 {
   if (!a || !fn) return -1;
   std::lock_guard<std::mutex> l(a->cmd_m);
-  a->bb_filters.push_back({ fn, priv });
+  auto it = a->bb_filters.begin();
+  while (it != a->bb_filters.end() && it->prio <= prio) ++it;
+  a->bb_filters.insert(it, { fn, priv, prio });
+  return 0;
+}
+extern "C" int sdb_analyzer_register_baseband_filter(sdb_analyzer_t *a, sdb_baseband_filter_fn fn, void *priv)
+{
+  return sdb_analyzer_register_baseband_filter_prio(a, fn, priv, 0);
+}
+// signal time of the source in seconds since its start (suscan_analyzer_get_source_time, Suscan/Analyzer.cpp:145-149)
+extern "C" double sdb_analyzer_get_source_time(const sdb_analyzer_t *a)
+{
+  return a ? (double) a->total_samples_pub.load() / a->src.samp_rate : 0.0;
+}
+// current configuration of an open inspector (what a GET_CONFIG reply would carry); -1 if the handle is not open
+extern "C" int sdb_analyzer_get_inspector_config(sdb_analyzer_t *a, int32_t handle, sdb_inspector_config *cfg)
+{
+  if (!a || !cfg) return -1;
+  std::lock_guard<std::mutex> l(a->insp_m);
+  if (handle < 0 || handle >= (int32_t) a->insps.size() || !a->insps[handle].open) return -1;
+  *cfg = a->insps[handle].cfg;
   return 0;
 }
 extern "C" int sdb_analyzer_inspector_set_spectrum_async(sdb_analyzer_t *a, int32_t handle, uint32_t spectsrc_id,

@@ -90,6 +90,10 @@ struct sdb_engine {
   cudaEvent_t ev_chan[2] = { nullptr, nullptr }, ev_insp[2] = { nullptr, nullptr };
   bool ev_insp_valid[2] = { false, false };
   unsigned feed_index = 0; int last_buf = 0;
+  uint64_t n_fed = 0; std::vector<float2> last_x_tail;
+  // DC removal (SDB_FLAG_DC_REMOVE, SPEC R): per-stream estimate, the estimate the current block is corrected with,
+  // run sums, and the corrected float32 copy of the block the rest of the path reads
+  float2 *d_dc_state = nullptr, *d_dc_cur = nullptr, *d_xdc = nullptr; double2 *d_dc_part = nullptr;   // samples fed so far; (engines without channels keep no history)
   // Host-buffer pipeline: results and input staging are double-buffered by feed parity so that the H2D
   // copy of feed i+1 and the D2H reads of feed i-1 overlap the kernels of feed i (three copy/compute
   // streams).  d_psd / d_soft / d_hard / d_counts always point at the buffers of the latest feed.
@@ -286,6 +290,21 @@ extern "C" int sdb_engine_open_channel(sdb_engine_t *e, const sdb_channel_params
   if (info) { info->center = c.center; info->size = c.size; info->width = c.width;
               info->decimation = (float) e->W / (float) c.size; }
   return (int) e->channels.size() - 1;
+}
+
+// channel geometry without an engine (su_specttuner_open_channel computes it before any transform exists)
+extern "C" int sdb_channel_geometry(uint32_t window_size, const sdb_channel_params *p, sdb_channel_info *info)
+{
+  if (!p || !info) return fail("null argument");
+  if (!is_pow2(window_size) || window_size < 64) return fail("window size must be a power of two >= 64");
+  if (!(p->guard >= 1.0f) || !(p->bw > 0.0f) || p->bw > 6.28318530717958647692f * 1.0001f)
+    return fail("invalid channel: bw must be in (0, 2 pi], guard >= 1");
+  if (!(p->f0 >= 0.0f) || p->f0 >= 6.28318530717958647692f) return fail("invalid channel: f0 must be in [0, 2 pi)");
+  unsigned center, size, width;
+  sdbh::channel_geometry(window_size, p->f0, p->bw, p->guard, &center, &size, &width);
+  info->center = center; info->size = size; info->width = width;
+  info->decimation = (float) window_size / (float) size;
+  return 0;
 }
 
 extern "C" int sdb_engine_set_inspector(sdb_engine_t *e, int handle, const sdb_inspector_config *cfg)
@@ -750,8 +769,29 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       s.k_phi = 0.25f; s.k_bnor = c.bnor; s.eq_wr[0] = 1.0f;
     }
     CK(cudaMemcpy(e->d_state, st.data(), chains * sizeof(SdbChainState), cudaMemcpyHostToDevice));
-    CK(cudaMemset(e->d_pool, 0, pool_floats * sizeof(float)));   // the kernel initialises its lines when `fresh`
+    {
+      // lines start empty: delay line and filter line 0, magnitude history at the -160 dB floor (SPEC A); the engine
+      // never asks the kernel for a `fresh` start, so that a re-planned engine can take over running chains
+      std::vector<float> hp(pool_floats, 0.0f);
+      for (size_t q = 0; q < e->h_chain_map.size(); ++q) {
+        const int g = e->h_chain_map[q];
+        if (g < 0) continue;
+        const SdbChainCfg &c = e->h_cfg[g / (int) S];
+        if (!c.have_agc) continue;
+        float *base = hp.data() + (q / 32) * 32 * pool + (q % 32);
+        for (unsigned i = 0; i < c.mh_size; ++i) base[(size_t) (c.st_mh_off + (int) i) * 32] = -160.0f;
+      }
+      CK(cudaMemcpy(e->d_pool, hp.data(), pool_floats * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    e->chains_fresh = false;
     CK(cudaMemset(e->d_counts, 0, chains * sizeof(uint32_t)));
+  }
+  if (e->prm.flags & SDB_FLAG_DC_REMOVE) {
+    e->d_dc_state = e->dalloc<float2>(S); e->d_dc_cur = e->dalloc<float2>(S);
+    e->d_dc_part = e->dalloc<double2>((size_t) S * ((max_feed + 255) / 256));
+    e->d_xdc = e->dalloc<float2>((size_t) S * max_feed);
+    if (!e->d_dc_state || !e->d_dc_cur || !e->d_dc_part || !e->d_xdc) return fail("out of device memory (DC removal)");
+    CK(cudaMemset(e->d_dc_state, 0, S * sizeof(float2)));
   }
   CK(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
@@ -777,7 +817,16 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
   if (K && n % (W / 2)) return fail("feed size must be a multiple of st_window_size / 2");
   CK(cudaSetDevice(e->prm.device));
   const void *x = reinterpret_cast<const void *>(xv);
-  const int fmt = e->prm.input_format | ((e->prm.flags & SDB_FLAG_IQ_REVERSE) ? SDB_FMT_SWAP : 0);
+  int fmt = e->prm.input_format | ((e->prm.flags & SDB_FLAG_IQ_REVERSE) ? SDB_FMT_SWAP : 0);
+  if (e->d_xdc) {
+    // SPEC R: the block is corrected with the estimate of the blocks before it; everything downstream reads the
+    // corrected float32 copy (format conversion and I/Q swap happen in this pass)
+    const float alpha = (float) (1.0 - exp(-(double) n / (e->samp_rate * 0.1)));
+    CK(sdb_launch_dc_remove(e->stream, x, fmt, stride, n, (int) S, alpha, e->d_dc_state, e->d_dc_cur, e->d_dc_part,
+                            e->d_xdc));
+    e->launches += 3;
+    x = e->d_xdc; fmt = SDB_FMT_F32; stride = n;
+  }
   const size_t bps = sdb_fmt_bytes(fmt);
   SdbLaunchCtx ctx{ e->stream, &e->launches };
   const int shift_db = (e->prm.flags & SDB_FLAG_PSD_SHIFT_DB) ? 1 : 0;
@@ -845,7 +894,9 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
     e->d_psd = e->d_psdb[ob];
   }
   if (G >= 1) {
-    SdbLaunchCtx pctx{ e->psd_stream, &e->launches };
+    // timing mode (sdb_engine_timing): every kernel on the main stream, so that the CUDA-event spans are the
+    // kernels' own durations and not those of two chains sharing the SMs
+    SdbLaunchCtx pctx{ e->timing ? e->stream : e->psd_stream, &e->launches };
     CK(cudaEventRecord(e->ev_feed, e->stream));              // the input is valid from here on
     CK(cudaStreamWaitEvent(e->psd_stream, e->ev_feed, 0));
     if (e->psd_read_valid[ob]) CK(cudaStreamWaitEvent(e->psd_stream, e->ev_psd_read[ob], 0));   // async read of feed i-2
@@ -902,20 +953,20 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       CK(cudaStreamWaitEvent(e->insp_stream, e->ev_chan[b], 0));
       e->d_soft = e->d_softb[b]; e->d_hard = e->d_hardb[b]; e->d_counts = e->d_countsb[b];
       if (e->sym_read_valid[b]) CK(cudaStreamWaitEvent(e->insp_stream, e->ev_sym_read[b], 0));
-      SdbLaunchCtx ictx{ e->insp_stream, &e->launches };
+      SdbLaunchCtx ictx{ e->timing ? e->stream : e->insp_stream, &e->launches };
       if (e->d_spectcfg)
         CK(sdb_launch_spectsrc(ictx, e->d_spectcfg, e->d_chans, K, (int) S, e->spect_max_ns, e->d_chanb[b],
                                e->chan_stride, (uint32_t) wps, e->d_spect, e->spect_stride, e->d_spect_size,
                                e->d_est, e->d_est_valid));
-      e->span_begin(FAM_INSPECTOR, e->insp_stream);
+      e->span_begin(FAM_INSPECTOR, ictx.stream);
       CK(sdb_launch_inspectors_n(ictx, e->d_cfg, K, (int) S, e->d_chain_map, e->insp_ctas, e->d_state, e->d_pool,
                                  e->pool_stride, e->d_taps,
                                  e->d_chans, e->d_chanb[b], e->chan_stride, (uint32_t) wps, e->d_soft, e->d_hard,
                                  e->d_counts, e->sym_cap, e->chains_fresh ? 1 : 0,
                                  sdb_insp_dyn(e->h_cfg.data(), K)));
       e->chains_fresh = false;
-      e->span_end(e->insp_stream);
-      CK(cudaEventRecord(e->ev_insp[b], e->insp_stream));
+      e->span_end(ictx.stream);
+      CK(cudaEventRecord(e->ev_insp[b], ictx.stream));
       e->ev_insp_valid[b] = true;
     } else {
       e->d_counts = e->d_countsb[ob];
@@ -934,6 +985,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
     e->first_feed = false;
   }
   ++e->feed_index;
+  e->n_fed += n;
   return 0;
 }
 
@@ -1223,6 +1275,149 @@ extern "C" int sdb_task_agc(const sdb_complex *src, sdb_complex *dst, size_t n, 
   if (b.put_cfg(c)) return -1;
   CK(sdb_launch_task_chain(0, b.src, b.dst, n, batch, b.cfg, 2, b.pool, 60));
   return task_io_end(b, dst, n, batch);
+}
+
+// ---- bulk twins of the per-sample sigutils calls, continuing from (and returning) the caller's loop state
+static int task_state_run(const sdb_complex *src, sdb_complex *dst, size_t n, int mode, void *st, size_t st_bytes)
+{
+  if (!src || !dst || !st) return fail("null argument");
+  if (sdb_device_count() <= 0) return fail("no CUDA device: sigdigger_b200 has no CPU fallback");
+  if (n == 0) return 0;
+  float2 *d_x = nullptr, *d_y = nullptr; float *d_st = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&d_x, n * sizeof(float2)) != cudaSuccess || cudaMalloc(&d_y, n * sizeof(float2)) != cudaSuccess ||
+      cudaMalloc(&d_st, st_bytes) != cudaSuccess) rc = fail("out of device memory");
+  if (!rc && (cudaMemcpy(d_x, src, n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+              cudaMemcpy(d_st, st, st_bytes, cudaMemcpyHostToDevice) != cudaSuccess)) rc = fail("copy failed");
+  if (!rc && sdb_launch_task_chain_state(0, d_x, d_y, n, mode, d_st) != cudaSuccess) rc = fail("launch failed");
+  if (!rc && (cudaMemcpy(dst, d_y, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess ||
+              cudaMemcpy(st, d_st, st_bytes, cudaMemcpyDeviceToHost) != cudaSuccess)) rc = fail(cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_x); cudaFree(d_y); cudaFree(d_st);
+  return rc;
+}
+extern "C" int sdb_task_costas_state(const sdb_complex *src, sdb_complex *dst, size_t n, const void *k, size_t k_bytes,
+                                     void *s, size_t s_bytes)
+{
+  if (k_bytes != sdb_costas_k_bytes() || s_bytes != sdb_costas_s_bytes()) return fail("costas state size mismatch");
+  std::vector<unsigned char> st(k_bytes + s_bytes);
+  memcpy(st.data(), k, k_bytes); memcpy(st.data() + k_bytes, s, s_bytes);
+  if (task_state_run(src, dst, n, 0, st.data(), st.size())) return -1;
+  memcpy(s, st.data() + k_bytes, s_bytes);
+  return 0;
+}
+extern "C" int sdb_task_pll_state(const sdb_complex *src, sdb_complex *dst, size_t n, float alpha, float beta,
+                                  float state[2])
+{
+  float st[4] = { alpha, beta, state[0], state[1] };
+  if (task_state_run(src, dst, n, 1, st, sizeof(st))) return -1;
+  state[0] = st[2]; state[1] = st[3];
+  return 0;
+}
+
+// ---- take over the running state of another engine (live re-plan: suscan keeps every inspector that stays open
+// ---- running when one is opened, closed or reconfigured, Suscan/Analyzer.cpp:459-537).  Channels are matched by
+// ---- their parameters (f0, bw, guard, precise), first come first served: a matched channel keeps its cross-fade
+// ---- tail and LO phase; if its inspector class and the sizes of its state lines are unchanged it also keeps the
+// ---- loop state of every chain (AGC, Costas / PLL, matched-filter line, Gardner, CMA...), whatever else of its
+// ---- configuration changed (loop bandwidths, gains, thresholds take effect at this block boundary).
+static int migrate_impl(sdb_engine_t *dst, sdb_engine_t *src, const std::vector<int> &old_of_new)
+{
+  CK(cudaSetDevice(dst->prm.device));
+  if (sdb_engine_sync(src)) return -1;
+  const unsigned S = dst->prm.n_streams, W = dst->W;
+  const int Kn = (int) dst->channels.size(), Ko = (int) src->channels.size();
+  if (dst->d_hist && src->d_hist)
+    CK(cudaMemcpy(dst->d_hist, src->d_hist, (size_t) S * (W / 2) * sizeof(float2), cudaMemcpyDeviceToDevice));
+  if (dst->d_dc_state && src->d_dc_state)
+    CK(cudaMemcpy(dst->d_dc_state, src->d_dc_state, S * sizeof(float2), cudaMemcpyDeviceToDevice));
+  // an engine that had no channel so far kept no input history: its first window starts with this feed
+  dst->first_feed = src->d_hist ? src->first_feed : true;
+  dst->n_fed = src->n_fed;
+  auto slot_of = [](const sdb_engine_t *e, int chain_g) {
+    for (size_t q = 0; q < e->h_chain_map.size(); ++q) if (e->h_chain_map[q] == chain_g) return (long) q;
+    return -1L;
+  };
+  for (int kn = 0; kn < Kn; ++kn) {
+    const int ko = kn < (int) old_of_new.size() ? old_of_new[kn] : -1;
+    if (ko < 0 || ko >= Ko) continue;
+    const Channel &cn = dst->channels[kn], &co = src->channels[ko];
+    const SdbChannelDev &dn = dst->h_chans[kn], &dold = src->h_chans[ko];
+    const bool same_channel = co.p.f0 == cn.p.f0 && co.p.bw == cn.p.bw && co.p.guard == cn.p.guard &&
+                              co.p.precise == cn.p.precise && co.size == cn.size && co.center == cn.center;
+    if (same_channel && !src->first_feed) {
+      CK(cudaMemcpy2D(dst->d_tails + dn.tail_off, dst->tail_stride * sizeof(float2), src->d_tails + dold.tail_off,
+                      src->tail_stride * sizeof(float2), (size_t) cn.halfsz * sizeof(float2), S, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy2D(dst->d_lo_phase + kn, (size_t) Kn * sizeof(float), src->d_lo_phase + ko, (size_t) Ko * sizeof(float),
+                      sizeof(float), S, cudaMemcpyDeviceToDevice));
+    }
+    if (!cn.has_insp || !co.has_insp) continue;
+    const SdbChainCfg &a = dst->h_cfg[kn], &b = src->h_cfg[ko];
+    if (a.cls != b.cls || a.have_agc != b.have_agc || a.dl_size != b.dl_size || a.mh_size != b.mh_size ||
+        a.have_mf != b.have_mf || a.mf_n != b.mf_n || a.af_n != b.af_n || a.alpf_n != b.alpf_n ||
+        a.have_costas != b.have_costas || a.have_pll != b.have_pll || a.eq_type != b.eq_type ||
+        a.clock_type != b.clock_type)
+      continue;                                            // structural change: this inspector restarts
+    CK(cudaMemcpy2D(dst->d_state + kn, (size_t) Kn * sizeof(SdbChainState), src->d_state + ko,
+                    (size_t) Ko * sizeof(SdbChainState), sizeof(SdbChainState), S, cudaMemcpyDeviceToDevice));
+    // clock.baud is a parameter AND the start value of the Gardner loop's own estimate: a new baud restarts it
+    if (a.bnor != b.bnor) {
+      std::vector<SdbChainState> st(S);
+      CK(cudaMemcpy2D(st.data(), sizeof(SdbChainState), dst->d_state + kn, (size_t) Kn * sizeof(SdbChainState),
+                      sizeof(SdbChainState), S, cudaMemcpyDeviceToHost));
+      for (auto &q : st) q.k_bnor = a.bnor;
+      CK(cudaMemcpy2D(dst->d_state + kn, (size_t) Kn * sizeof(SdbChainState), st.data(), sizeof(SdbChainState),
+                      sizeof(SdbChainState), S, cudaMemcpyHostToDevice));
+    }
+    const size_t rows = (size_t) std::min(a.st_pool, b.st_pool);
+    for (unsigned s = 0; s < S; ++s) {
+      const long qn = slot_of(dst, kn * (int) S + (int) s), qo = slot_of(src, ko * (int) S + (int) s);
+      if (qn < 0 || qo < 0) continue;
+      float *pd = dst->d_pool + (size_t) (qn / 32) * 32 * dst->pool_stride + (qn % 32);
+      const float *ps = src->d_pool + (size_t) (qo / 32) * 32 * src->pool_stride + (qo % 32);
+      CK(cudaMemcpy2D(pd, 32 * sizeof(float), ps, 32 * sizeof(float), sizeof(float), rows, cudaMemcpyDeviceToDevice));
+    }
+  }
+  return 0;
+}
+
+static int migrate_check(sdb_engine_t *dst, sdb_engine_t *src)
+{
+  if (!dst || !src) return fail("null engine");
+  if (!dst->committed || !src->committed) return fail("both engines must be committed");
+  if (dst->prm.n_streams != src->prm.n_streams || dst->W != src->W || dst->prm.device != src->prm.device)
+    return fail("engines differ in streams / window / device");
+  return 0;
+}
+
+// can dst continue src (same streams, window, device)?  PSD size, window function, flags and feed size may differ
+extern "C" int sdb_engine_same_geometry(const sdb_engine_t *a, const sdb_engine_t *b)
+{
+  return a && b && a->prm.n_streams == b->prm.n_streams && a->W == b->W && a->prm.device == b->prm.device;
+}
+
+extern "C" int sdb_engine_migrate(sdb_engine_t *dst, sdb_engine_t *src)
+{
+  if (migrate_check(dst, src)) return -1;
+  const int Kn = (int) dst->channels.size(), Ko = (int) src->channels.size();
+  std::vector<int> map(Kn, -1);
+  std::vector<char> used(Ko, 0);
+  for (int kn = 0; kn < Kn; ++kn) {
+    const Channel &cn = dst->channels[kn];
+    for (int k = 0; k < Ko; ++k) {
+      const Channel &co = src->channels[k];
+      if (!used[k] && co.p.f0 == cn.p.f0 && co.p.bw == cn.p.bw && co.p.guard == cn.p.guard &&
+          co.p.precise == cn.p.precise) { map[kn] = k; used[k] = 1; break; }
+    }
+  }
+  return migrate_impl(dst, src, map);
+}
+
+extern "C" int sdb_engine_migrate_map(sdb_engine_t *dst, sdb_engine_t *src, const int32_t *old_of_new, size_t n)
+{
+  if (migrate_check(dst, src)) return -1;
+  if (!old_of_new && n) return fail("null map");
+  std::vector<int> map(old_of_new, old_of_new + n);
+  return migrate_impl(dst, src, map);
 }
 
 // ---- TimeWindow tasks that are fully specified in-repo (SPEC Y; kernels in tasks_kernels.cu)

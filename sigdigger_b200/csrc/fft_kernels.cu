@@ -21,6 +21,7 @@
 #include "../../include/sigdigger_b200.h"
 #include "sdb_math.h"
 #include <math_constants.h>
+#include <stdlib.h>
 
 // SPEC F.1 twiddle product: one rounded product + one fused multiply-add per component
 static __device__ __forceinline__ float2 cmul(float2 a, float2 b)
@@ -494,15 +495,17 @@ cudaError_t sdb_launch_spectsrc(const SdbLaunchCtx &c, const SdbSpectCfg *cfg_de
 }
 
 // ---------------------------------------------------------------------------------------------
-// channeliser inverse side.  One CTA per (channel, stream); hops are processed in order because the
-// cross-fade needs the second half of the previous hop's IFFT (kept in shared memory, carried
-// between feeds in `tails`).
+// channeliser inverse side.  One CTA per (channel, stream).  Only the cross-fade couples consecutive hops (it needs
+// the second half of the previous hop's IFFT), so the CTA transforms P hops at a time -- P x size/4 threads, every
+// barrier of the shared-memory transform paid once per P hops, P gathers in flight -- and cross-fades them from the
+// buffers of their left neighbours; the last hop's second half is carried in shared memory (and between feeds in
+// `tails`).  Round 1 ran one hop at a time with size/4 threads: 22 us per 2048-point hop against < 1 us of work.
 // ---------------------------------------------------------------------------------------------
 template <int BPT>
 __global__ void __launch_bounds__(1024) k_chan_ifft(const SdbChannelDev *__restrict__ chans,
                                                      const int *__restrict__ group, int n_channels,
                                                      const float2 *__restrict__ cspec, int n_bins,
-                                                     int wps, float2 *__restrict__ tails,
+                                                     int wps, int P, float2 *__restrict__ tails,
                                                      size_t tail_stream_stride, float *__restrict__ lo_phase,
                                                      float2 *__restrict__ chan_out, size_t chan_stream_stride)
 {
@@ -511,32 +514,41 @@ __global__ void __launch_bounds__(1024) k_chan_ifft(const SdbChannelDev *__restr
   const SdbChannelDev ch = chans[ci];
   const int s = blockIdx.y;
   const int size = ch.size, hs = ch.halfsz, hw = ch.halfw;
-  float2 *buf = sm, *prev = sm + size;
-  float *phase = reinterpret_cast<float *>(prev + hs);
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  float2 *bufs = sm;                                   // [P][size]
+  float2 *prevb[2] = { sm + (size_t) P * size, sm + (size_t) P * size + hs };
+  float *phase = reinterpret_cast<float *>(sm + (size_t) P * size + 2 * hs);   // [P][hs]
+  const int tid = threadIdx.x;
+  const int per = BPT == 1 ? (size >= 4 ? size >> 2 : 1) : (int) blockDim.x;   // threads per hop
+  const int g = tid / per, l = tid - g * per;
   float2 *__restrict__ tail = tails + (size_t) s * tail_stream_stride + ch.tail_off;
   float2 *__restrict__ out = chan_out + (size_t) s * chan_stream_stride + ch.out_off;
 
-  for (int i = tid; i < hs; i += nthr) prev[i] = tail[i];
+  for (int i = tid; i < hs; i += blockDim.x) prevb[0][i] = tail[i];
   float lo_phi = ch.precise ? lo_phase[(size_t) s * n_channels + ci] : 0.0f;
+  int pb = 0;
   __syncthreads();
 
-  for (int j = 0; j < wps; ++j) {
-    const float2 *__restrict__ cs = cspec + ((size_t) s * wps + j) * n_bins;
-    for (int i = tid; i < size; i += nthr) buf[i] = make_float2(0.0f, 0.0f);
-    __syncthreads();
-    for (int i = tid; i < 2 * hw; i += nthr) {
-      const int cidx = i < ch.L1 ? ch.c1 + i : i - ch.L1;
-      float2 X = __ldg(cs + cidx);
-      const float w = __ldg(ch.kh + i);
-      const int r = i - hw;
-      X.x *= w; X.y *= w;
-      buf[r >= 0 ? r : size + r] = X;
+  for (int j0 = 0; j0 < wps; j0 += P) {
+    const int Pg = wps - j0 < P ? wps - j0 : P;        // hops in this group
+    const bool active = g < Pg;
+    float2 *buf = bufs + (size_t) (active ? g : 0) * size;
+    if (active) {
+      const float2 *__restrict__ cs = cspec + ((size_t) s * wps + j0 + g) * n_bins;
+      // zero the guard region between the two sidebands, then gather + shape the channel's bins
+      for (int i = hw + l; i < size - hw; i += per) buf[i] = make_float2(0.0f, 0.0f);
+      for (int i = l; i < 2 * hw; i += per) {
+        const int cidx = i < ch.L1 ? ch.c1 + i : i - ch.L1;
+        float2 X = __ldg(cs + cidx);
+        const float w = __ldg(ch.kh + i);
+        const int r = i - hw;
+        X.x *= w; X.y *= w;
+        buf[r >= 0 ? r : size + r] = X;
+      }
     }
     if (ch.precise && tid == 0) {
       // sequential phase accumulation, exactly as the per-sample NCQO would do it
       float phi = lo_phi;
-      for (int i = 0; i < hs; ++i) {
+      for (int i = 0; i < Pg * hs; ++i) {
         phase[i] = phi;
         phi += ch.lo_omega;
         if (phi >= 6.28318530717958647692f) phi -= 6.28318530717958647692f;
@@ -545,22 +557,26 @@ __global__ void __launch_bounds__(1024) k_chan_ifft(const SdbChannelDev *__restr
       lo_phi = phi;
     }
     __syncthreads();
-    block_fft_inplace<+1, BPT>(buf, size, ch.log2size, tid, nthr, ch.tw);
-    for (int i = tid; i < hs; i += nthr) {
-      const float al = __ldg(ch.xfade + i), be = __ldg(ch.xfade + i + hs);
-      const float2 cu = buf[i], pv = prev[i];
-      float2 o = make_float2(al * cu.x + be * pv.x, al * cu.y + be * pv.y);
-      if (ch.precise) {
-        float sn, cs_;
-        d_sincosf(phase[i], &sn, &cs_);            // SPEC M.1, as the per-sample NCQO read does
-        o = cmulc(o, make_float2(cs_, sn));
+    block_fft_inplace<+1, BPT>(buf, size, ch.log2size, active ? l : size, per, ch.tw);
+    if (active) {
+      const float2 *pvb = g > 0 ? buf - size + hs : prevb[pb];
+      for (int i = l; i < hs; i += per) {
+        const float al = __ldg(ch.xfade + i), be = __ldg(ch.xfade + i + hs);
+        const float2 cu = buf[i], pv = pvb[i];
+        float2 o = make_float2(al * cu.x + be * pv.x, al * cu.y + be * pv.y);
+        if (ch.precise) {
+          float sn, cs_;
+          d_sincosf(phase[g * hs + i], &sn, &cs_);            // SPEC M.1, as the per-sample NCQO read does
+          o = cmulc(o, make_float2(cs_, sn));
+        }
+        out[(size_t) (j0 + g) * hs + i] = o;
+        if (g == Pg - 1) prevb[pb ^ 1][i] = buf[i + hs];
       }
-      out[(size_t) j * hs + i] = o;
-      prev[i] = buf[i + hs];
     }
+    pb ^= 1;
     __syncthreads();
   }
-  for (int i = tid; i < hs; i += nthr) tail[i] = prev[i];
+  for (int i = tid; i < hs; i += blockDim.x) tail[i] = prevb[pb][i];
   if (ch.precise && tid == 0) lo_phase[(size_t) s * n_channels + ci] = lo_phi;
 }
 
@@ -577,23 +593,39 @@ cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDe
     cudaFuncSetAttribute(k_chan_ifft<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_chan_ifft<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
-  const size_t smem = (size_t) size * sizeof(float2) + (size_t) (size / 2) * sizeof(float2)
-                      + (size_t) (size / 2) * sizeof(float);
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
   int bpt = 1, threads = size / 4;
   while (threads > 1024) { threads >>= 1; bpt <<= 1; }
+  // hops per pass.  Measured on cfg3 (1024-point channels, 8 hops): P = 4 (1024-thread CTAs, 2 per SM) 1.21 ms
+  // against 0.85 ms for P = 1 (256-thread CTAs, 8 per SM): the barriers of a big CTA cost more than the hops it
+  // overlaps, so one hop per pass stays the default (SDB_IFFT_HOPS overrides for experiments).
+  int P = 1;
+  static const int env_hops = getenv("SDB_IFFT_HOPS") ? atoi(getenv("SDB_IFFT_HOPS")) : 1;
+  if (bpt == 1 && env_hops > 1) {
+    const int per = size >= 4 ? size / 4 : 1;
+    P = 1024 / per;
+    if (P > env_hops) P = env_hops;
+    if (P > wps) P = wps;
+    if ((size_t) P * size > 8192) P = (int) (8192 / size);
+    if (P < 1) P = 1;
+    threads = ((P * per + 31) / 32) * 32;
+  } else if (bpt == 1) {
+    threads = size / 4;
+  }
   if (threads < 32) threads = 32;
+  const size_t smem = (size_t) P * size * sizeof(float2) + (size_t) size * sizeof(float2)
+                      + (size_t) P * (size / 2) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid(group_len, n_streams);
   if (bpt == 1)
-    k_chan_ifft<1><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+    k_chan_ifft<1><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps, P,
                                                       tails, tail_stream_stride, lo_phase, chan_out,
                                                       chan_stream_stride);
   else if (bpt == 2)
-    k_chan_ifft<2><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+    k_chan_ifft<2><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps, P,
                                                       tails, tail_stream_stride, lo_phase, chan_out,
                                                       chan_stream_stride);
   else if (bpt == 4)
-    k_chan_ifft<4><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+    k_chan_ifft<4><<<grid, threads, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps, P,
                                                       tails, tail_stream_stride, lo_phase, chan_out,
                                                       chan_stream_stride);
   else

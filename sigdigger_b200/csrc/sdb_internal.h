@@ -169,10 +169,10 @@ struct SdbSpectCfg {
 };
 
 // plan-dependent shared-memory lines of k_inspectors (chain_kernels.cu): sized from the channel plan
-#define SDB_INSP_CHUNK 16          // samples per pipeline chunk (CH in chain_kernels.cu)
-#define SDB_INSP_MF_RING_MAX 225   // longest matched filter served from the shared-memory ring (256 slots)
+#define SDB_INSP_CHUNK 8           // samples per pipeline chunk (CH in chain_kernels.cu)
+#define SDB_INSP_MF_RING_MAX 241   // longest matched filter served from the shared-memory ring (256 slots)
 struct SdbInspDyn {
-  int rb_slots;             // carrier ring slots (power of two >= longest ring-served filter - 1 + 2 chunks)
+  int rb_slots;             // carrier ring slots (longest ring-served filter - 1 + 2 chunks)
   int mf_rows;              // tap rows [t][lane] of the longest ring-served matched filter
   int agc_rows;             // floats per chain for the AGC delay line + magnitude history
   int use_eq;               // some chain runs the CMA equaliser
@@ -183,9 +183,8 @@ static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
   for (int k = 0; k < n; ++k) {
     const SdbChainCfg &c = cfgs[k];
     if (c.have_mf && c.mf_n <= SDB_INSP_MF_RING_MAX) {        // longer filters stay in the global pool
-      int need = c.mf_n - 1 + 2 * SDB_INSP_CHUNK, slots = 2 * SDB_INSP_CHUNK;
-      while (slots < need) slots <<= 1;
-      if (slots > d.rb_slots) d.rb_slots = slots;
+      const int need = c.mf_n - 1 + 2 * SDB_INSP_CHUNK;
+      if (need > d.rb_slots) d.rb_slots = need;
       if (c.mf_n > d.mf_rows) d.mf_rows = c.mf_n;
     }
     if (c.have_agc) {
@@ -272,6 +271,9 @@ cudaError_t sdb_launch_spectsrc(const SdbLaunchCtx &c, const SdbSpectCfg *cfg_de
                                 uint32_t *spect_size, float *est, int *est_valid);
 cudaError_t sdb_launch_task_xlate(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
                                   float omega, float phi0);
+cudaError_t sdb_launch_task_chain_state(cudaStream_t s, const float2 *src, float2 *dst, size_t n, int mode, float *st);
+size_t sdb_costas_k_bytes(void);
+size_t sdb_costas_s_bytes(void);
 cudaError_t sdb_launch_task_quad(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch);
 cudaError_t sdb_launch_task_chain(cudaStream_t s, const float2 *src, float2 *dst, size_t n, size_t batch,
                                   const SdbChainCfg *cfg_dev, int mode, float *pool, size_t pool_stride);
@@ -289,5 +291,7 @@ cudaError_t sdb_launch_task_carrier_prep(cudaStream_t s, const float2 *src, cons
                                          size_t batch, float2 *dst);
 cudaError_t sdb_launch_task_carrier_find(cudaStream_t s, const float *psd, size_t alloc, size_t batch, int bins,
                                          int delta, int skip, float *peak);
+cudaError_t sdb_launch_dc_remove(cudaStream_t st, const void *x, int fmt, size_t stream_stride, size_t n, int n_streams,
+                                 float alpha, float2 *state, float2 *cur, double2 *part, float2 *out);
 cudaError_t sdb_launch_task_decide(cudaStream_t s, const float2 *x, unsigned char *sym, size_t n, int mode, float dmin,
                                    float dh, int intervals);

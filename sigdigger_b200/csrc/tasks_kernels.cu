@@ -378,3 +378,58 @@ cudaError_t sdb_launch_task_decide(cudaStream_t s, const float2 *x, unsigned cha
   k_task_decide<<<grid_for(n, 256), 256, 0, s>>>(x, sym, n, mode, dmin, dh, intervals);
   return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// DC removal of the source worker (suscan_analyzer_set_dc_remove, Suscan/Analyzer.cpp:229-236; SPEC R).  Block-wise
+// single pole: every sample of block k has the estimate c_k subtracted (one binary32 subtraction per component),
+// then c_{k+1} = c_k + alpha (m_k - c_k) with m_k the mean of the RAW block.  The mean is a fixed two-level sum in
+// binary64 (runs of 256 samples in index order, then the run sums in index order), so it is reproducible bit for bit
+// (oracle/tasks.c sdo_dc_remove).  Output: complex float32 (native formats are converted in the same load).
+// ------------------------------------------------------------------------------------------------
+#define DC_RUN 256
+__global__ void k_dc_partial(const void *__restrict__ x, int fmt, size_t stream_stride, size_t n, size_t runs,
+                             double2 *__restrict__ part)
+{
+  const size_t r = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (r >= runs) return;
+  const char *xs = reinterpret_cast<const char *>(x) + (size_t) s * stream_stride * sdb_fmt_bytes(fmt);
+  const size_t i0 = r * DC_RUN, i1 = i0 + DC_RUN < n ? i0 + DC_RUN : n;
+  double ar = 0.0, ai = 0.0;
+  for (size_t i = i0; i < i1; ++i) { const float2 v = sdb_ld_iq(xs, (long) i, fmt); ar += (double) v.x; ai += (double) v.y; }
+  part[(size_t) s * runs + r] = make_double2(ar, ai);
+}
+// state[s] = {c.re, c.im}; cur[s] receives the estimate this block is corrected with
+__global__ void k_dc_finish(const double2 *__restrict__ part, size_t runs, size_t n, float alpha, float2 *__restrict__ state,
+                            float2 *__restrict__ cur, int n_streams)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  double ar = 0.0, ai = 0.0;
+  for (size_t r = 0; r < runs; ++r) { const double2 p = part[(size_t) s * runs + r]; ar += p.x; ai += p.y; }
+  const float mr = (float) (ar / (double) n), mi = (float) (ai / (double) n);
+  const float2 c = state[s];
+  cur[s] = c;
+  state[s] = make_float2(c.x + alpha * (mr - c.x), c.y + alpha * (mi - c.y));
+}
+__global__ void k_dc_apply(const void *__restrict__ x, int fmt, size_t stream_stride, size_t n,
+                           const float2 *__restrict__ cur, float2 *__restrict__ out)
+{
+  const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (i >= n) return;
+  const char *xs = reinterpret_cast<const char *>(x) + (size_t) s * stream_stride * sdb_fmt_bytes(fmt);
+  const float2 v = sdb_ld_iq(xs, (long) i, fmt), c = cur[s];
+  out[(size_t) s * n + i] = make_float2(v.x - c.x, v.y - c.y);
+}
+cudaError_t sdb_launch_dc_remove(cudaStream_t st, const void *x, int fmt, size_t stream_stride, size_t n, int n_streams,
+                                 float alpha, float2 *state, float2 *cur, double2 *part, float2 *out)
+{
+  const size_t runs = (n + DC_RUN - 1) / DC_RUN;
+  dim3 g1((unsigned) ((runs + 127) / 128), n_streams);
+  k_dc_partial<<<g1, 128, 0, st>>>(x, fmt, stream_stride, n, runs, part);
+  k_dc_finish<<<(n_streams + 63) / 64, 64, 0, st>>>(part, runs, n, alpha, state, cur, n_streams);
+  dim3 g2((unsigned) ((n + 255) / 256), n_streams);
+  k_dc_apply<<<g2, 256, 0, st>>>(x, fmt, stream_stride, n, cur, out);
+  return cudaGetLastError();
+}
