@@ -27,16 +27,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_FFT = 65536
-FS_BY = {"cfg2": 100e6, "cfg3": 200e6}
+FS_BY = {"cfg2": 100e6, "cfg3": 200e6, "cfg4": 50e6, "cfg5": 100e6}
+NFFT_BY = {"cfg2": 65536, "cfg3": 65536, "cfg4": 32768, "cfg5": 65536}
 FS = 100e6     # replaced per workload in main()
-B_ALG = {"cfg2": 12.09, "cfg3": 14.41}     # BASELINE.md section 3, bytes per input sample
+B_ALG = {"cfg2": 12.09, "cfg3": 14.41, "cfg4": 12.06, "cfg5": 12.0}     # SURVEY 8(d), bytes per input sample
 
 
 # --------------------------------------------------------------------------------------------------
 # workload definition (shared by both arms)
 # --------------------------------------------------------------------------------------------------
 def workload_channels(name):
-    """-> list of (kind, f_hz, baud, bw_hz, inspector class, config kwargs builder(fs_ch))."""
+    """-> list of (kind, f_hz, baud, bw_hz)."""
     if name == "cfg2":
         return [("qpsk", 12.5e6 + 300.0, 1e6, 3e6)]
     if name == "cfg3":
@@ -47,6 +48,10 @@ def workload_channels(name):
             baud = 0.5e6 if kind == "ask" else 1e6
             out.append((kind, f + 300.0, baud, 2.5e6))
         return out
+    if name == "cfg4":      # 8 audio channels, 200 kHz wide (Default/Audio/AudioProcessor.cpp:118-121)
+        return [(d, (k - 3.5) * 2.0e6 + 300.0, 0.0, 200e3) for k, d in enumerate(["am"] * 3 + ["fm"] * 3 + ["usb"] * 2)]
+    if name == "cfg5":
+        return []
     raise ValueError(name)
 
 
@@ -59,6 +64,10 @@ def insp_kwargs(kind, baud, fs_ch):
     if kind == "ask":
         return "ask", dict(baud=baud, bits_per_symbol=1, ask_use_pll=1, ask_channel=0, loop_bw=fs_ch * 5e-3,
                            mf_type=1, mf_rolloff=0.35, clock_type=1, clock_gain=0.2)
+    if kind in ("am", "fm", "usb"):
+        return "audio", dict(audio_demod={"am": 1, "fm": 2, "usb": 3}[kind], audio_cutoff=5000.0,
+                             audio_sample_rate=44100, agc_enabled=1, agc_ts=0.0005, offset=1300.0, audio_squelch=0,
+                             audio_volume=1.0)
     raise ValueError(kind)
 
 
@@ -69,6 +78,19 @@ def chan_angular(f_hz, bw_hz):
 
 def make_base_signal(name, n, seed):
     from sigdigger_b200 import synth
+    if name == "cfg4":      # 3 AM (m = 0.5), 3 FM (5 kHz deviation), 2 USB two-tone, 1 kHz programme tone
+        t = np.arange(n) / FS
+        tone = np.cos(2 * np.pi * 1000 * t)
+        x = synth.awgn(n, 10 ** (-60 / 20), np.random.default_rng(seed))
+        for kind, f, _, _ in workload_channels(name):
+            if kind == "am":
+                sg = (1 + 0.5 * tone) * 0.2
+            elif kind == "fm":
+                sg = 0.2 * np.exp(1j * 2 * np.pi * 5000 * np.cumsum(tone) / FS)
+            else:
+                sg = 0.1 * (np.exp(2j * np.pi * 700 * t) + 0.5 * np.exp(2j * np.pi * 1900 * t))
+            x = x + sg * np.exp(2j * np.pi * (f - 300.0) * t)
+        return x.astype(np.complex64)
     carriers = []
     for kind, f, baud, _ in workload_channels(name):
         kw = {"levels": 2} if kind == "ask" else {}
@@ -317,6 +339,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "cfg5":
+        t0 = time.perf_counter()
+        reps = []
+        for _ in range(max(1, args.warmup) + args.steps):
+            reps.append(cfg5_cpu(min(128, CFG5_HOPS)))
+        reps = reps[max(1, args.warmup):]
+        v = float(np.mean([r["value"] for r in reps]))
+        cb = dict(reps[-1], value=v)
+        print(json.dumps({"impl": "reference", "metric": "complex MSamples/s ingested (65536-pt PSD per tuner hop, stitched)",
+                          "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * 128 * N_FFT / (v * 1e6), "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg5_config(),
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     cores, kind, how = pick_threads(args.workload)
     n = N_FFT // 2 * 16                      # 2^19 samples per stream: one stream per host thread
     streams = cores
@@ -326,7 +363,7 @@ def run_reference(args):
     sample = "%d streams x %d samples per step, %d OpenMP threads (%s)" % (streams, n, cores, how)
     # the round-1 arm (parity build, SPEC transforms) on a shorter sample, for the record
     tp, sp = cpu_run(args.workload, streams, N_FFT * 2, cores, reps=1, warm=0, kind="parity")
-    out = {"impl": "reference", "metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)",
+    out = {"impl": "reference", "metric": "complex MSamples/s ingested (%d-pt PSD + N inspectors)" % N_FFT,
            "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -341,11 +378,196 @@ def run_reference(args):
 
 def workload_config(args, streams, hops):
     k = len(workload_channels(args.workload))
-    return {"workload": "%s: fs %g MS/s nominal, 65536-pt Blackman-Harris PSD every frame + 65536-pt "
-                        "50%%-overlap FFT channeliser + %d inspector(s) (%s), Costas + RRC + Gardner + decision"
-                        % (args.workload, FS / 1e6, k, "QPSK 1 MBd" if args.workload == "cfg2" else "2-FSK / QPSK / ASK mix"),
+    what = {"cfg2": "QPSK 1 MBd, Costas + RRC + Gardner + decision",
+            "cfg3": "2-FSK / QPSK / ASK mix on a 3 MHz raster, Costas / PLL + RRC + Gardner + decision",
+            "cfg4": "3 AM + 3 FM + 2 USB audio channels, AGC + demodulator + LPF + resampler to 44.1 kS/s"}[args.workload]
+    return {"workload": "%s: fs %g MS/s nominal, %d-pt Blackman-Harris PSD every frame + %d-pt "
+                        "50%%-overlap FFT channeliser + %d inspector(s) (%s)"
+                        % (args.workload, FS / 1e6, N_FFT, N_FFT, k, what),
             "streams_per_gpu": streams, "samples_per_stream_per_step": hops * N_FFT // 2,
             "inputs": "larger than L2 (no flush needed)", "parallelism": "independent streams per GPU"}
+
+
+# --------------------------------------------------------------------------------------------------
+# cfg5: panoramic sweep (BASELINE.json configs[4]): 1024 tuner hops x 65536-pt PSD, per-GPU channel detector,
+# stitched on rank 0 -- the one workload with a collective (NCCL gather of the contribution lists)
+# --------------------------------------------------------------------------------------------------
+CFG5_HOPS = 1024
+
+
+def cfg5_geometry():
+    rel_bw = 0.5
+    fmin = 1.0e9
+    fmax = fmin + CFG5_HOPS * FS * rel_bw
+    centers = fmin + FS * rel_bw * (0.5 + np.arange(CFG5_HOPS))
+    return fmin, fmax, rel_bw, centers
+
+
+def cfg5_hops(lo, hi, seed=17):
+    """hops [lo, hi): noise + 3 carriers per hop at seeded offsets (the same bits on every rank layout)."""
+    out = np.empty((hi - lo, N_FFT), np.complex64)
+    t = np.arange(N_FFT)
+    for h in range(lo, hi):
+        rng = np.random.default_rng(seed * 100003 + h)
+        x = 0.02 * (rng.standard_normal(N_FFT) + 1j * rng.standard_normal(N_FFT))
+        for _ in range(3):
+            x = x + 0.3 * np.exp(2j * np.pi * rng.uniform(-0.2, 0.2) * t)
+        out[h - lo] = x.astype(np.complex64)
+    return out
+
+
+def cfg5_config():
+    return {"workload": "cfg5: panoramic sweep, %d tuner hops x %d-pt Blackman-Harris PSD at %g MS/s per hop, relBw 0.5, "
+                        "per-hop channel detector on the owning GPU, SpectrumView (65536 bins) stitched on rank 0"
+                        % (CFG5_HOPS, N_FFT, FS / 1e6),
+            "hops": CFG5_HOPS, "samples_per_hop": N_FFT,
+            "inputs": "hop buffers larger than L2 at 1-2 GPUs (537 MB in total); L2 flushed between steps otherwise",
+            "parallelism": "hops sharded contiguously over ranks; one NCCL gather of the contribution lists per sweep"}
+
+
+def run_cuda_cfg5(args):
+    import torch
+    import sigdigger_b200 as sdb
+    from sigdigger_b200 import panoramic
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if sdb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fmin, fmax, rel_bw, centers = cfg5_geometry()
+    lo, hi = panoramic.shard(CFG5_HOPS, world, rank)
+    xh = torch.from_numpy(cfg5_hops(lo, hi)).pin_memory()
+    x = xh.cuda()
+    det = dict(alpha=1.0, gamma=0.5, snr=6.0, min_bins=2)
+    p = sdb.Panoramic(N_FFT, "blackmann_harris", FS, (fmin, fmax), rel_bw, device=local, rank=rank, world=world,
+                      unique_id=panoramic.exchange_unique_id(sdb, torch, dist), detect=det)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(fn, steps, do_flush):
+        tot = 0.0
+        for _ in range(steps):
+            if do_flush:
+                flush.fill_(1)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        if dist is not None:
+            t = torch.tensor([tot], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t.item())
+        return tot
+
+    small = x.numel() * 8 < (256 << 20)
+    step_dev = lambda: (p.reset(), p.sweep(x, centers))
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    with Clocks(local) as clk:
+        ms = run(step_dev, args.steps, small)
+    samples = CFG5_HOPS * N_FFT
+    value = samples * args.steps / (ms * 1e-3) / 1e6
+    tm = p.timing()
+    # end to end: pinned host hop buffers -> H2D -> sweep -> D2H of the stitched view (+ channel lists) on rank 0
+    def step_e2e():
+        p.reset()
+        p.sweep(xh.numpy(), centers)
+        if rank == 0:
+            p.read()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_v = samples * args.steps / dt / 1e6
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dominant kernels: the two passes of the hop PSDs (inside psd_project_ms); B_alg = 8 B in + 4 B out per sample
+    ach = B_ALG["cfg5"] * (hi - lo) * N_FFT / (tm["psd_project_ms"] * 1e-3) / 1e9 if tm["psd_project_ms"] > 0 else 0.0
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cfg5_cpu(min(128, CFG5_HOPS))
+    if rank == 0:
+        out = {"metric": "complex MSamples/s ingested (65536-pt PSD per tuner hop, stitched)", "value": value,
+               "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": cfg5_config(), "clocks": clk.summary(),
+               "gpu_launches": None,
+               "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(samples * 8),
+                       "d2h_bytes_per_step": int(3 * 65536 * 4)},
+               "roofline": {"bound": "hbm", "kernel": "hop PSD passes + projection (rank 0's shard)", "achieved": ach,
+                            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                            "phases_ms": {k: round(v, 4) for k, v in tm.items() if k.endswith("_ms")},
+                            "gather_bytes": tm["gather_bytes"],
+                            "note": "phase times of the LAST sweep on rank 0 (CUDA events inside sdb_panoramic_sweep)"},
+               "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cfg5_cpu(n_hops):
+    """CPU arm of cfg5 on a bounded sample: hop PSDs (speed build, one hop per thread) + the sequential stitch."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    cores, how = usable_cores()
+    L = cpu_lib("fast") or O.lib()
+    L.sdo_fast_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int]
+    fmin, fmax, rel_bw, centers = cfg5_geometry()
+    x = cfg5_hops(0, n_hops)
+    w = O.window(N_FFT, "blackmann_harris")
+    psd = np.empty((n_hops, N_FFT), np.float32)
+
+    def one(h):
+        y = np.empty(N_FFT, np.complex64)
+        L.sdo_fast_fft(x[h].ctypes.data, w.ctypes.data, y.ctypes.data, N_FFT, -1)
+        p_ = ((y.real * y.real + y.imag * y.imag) / np.float32(N_FFT)).astype(np.float32)
+        O.lib().sdo_psd_shift_db(O.ptr(p_), N_FFT)
+        psd[h] = p_
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(one, range(n_hops)))
+    v = O.SpectrumView()
+    Lo = O.lib()
+    assert Lo.sdo_sview_init(C.byref(v)) == 0
+    Lo.sdo_sview_set_range(C.byref(v), fmin, fmin + n_hops * FS * rel_bw)
+    v.fft_bandwidth = FS
+    v.fft_rel_bw = rel_bw
+    for h in range(n_hops):
+        Lo.sdo_sview_feed(C.byref(v), O.ptr(psd[h]), None, N_FFT, float(centers[h]), 1)
+    dt = time.perf_counter() - t0
+    val = n_hops * N_FFT / dt / 1e6
+    return {"value": val, "unit": "MS/s", "cores": cores, "kind": "port", "build": CPU_FLAGS["fast"],
+            "sample": "%d of the %d hops: windowed PSD per hop (one hop per thread, %d threads; %s) + sequential "
+                      "SpectrumView feed, no detector" % (n_hops, CFG5_HOPS, cores, how)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -580,7 +802,7 @@ def run_cuda(args):
                          "one stream per thread; %s)" % (cores, N_FFT // 2 * 16, len(times), how)}
 
     if rank == 0:
-        out = {"metric": "complex MSamples/s ingested (65536-pt PSD + N inspectors)", "value": value,
+        out = {"metric": "complex MSamples/s ingested (%d-pt PSD + N inspectors)" % N_FFT, "value": value,
                "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": workload_config(args, S, H),
@@ -600,22 +822,25 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--hops", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-formats", action="store_true")
     args = ap.parse_args()
-    global FS
+    global FS, N_FFT
     FS = FS_BY[args.workload]
+    N_FFT = NFFT_BY[args.workload]
     if args.streams == 0:
         # cfg2: the (latency-bound) inspector kernel of 1024 single-channel streams takes about as long as their
         # transforms; 2048 streams put the transforms on the critical path (33.9 / 53.3 / 64.5 GS/s at 512 / 1024 /
         # 2048 streams on one B200, profiles/r01_batch.md)
-        args.streams = 2048 if args.workload == "cfg2" else 128
+        args.streams = {"cfg2": 2048, "cfg3": 128, "cfg4": 1024, "cfg5": 0}[args.workload]
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cuda_cfg5(args)
     else:
         run_cuda(args)
 

@@ -574,6 +574,50 @@ int      sdb_sview_contrib_copy(sdb_sview_t *v, int32_t *j0, int32_t *nb, float 
 int      sdb_sview_accumulate(sdb_sview_t *v, const int32_t *j0, const int32_t *nb, const float *va,
                               const float *vc, size_t n_hops);
 int      sdb_sview_read(sdb_sview_t *v, float *psd, float *accum, float *count, size_t cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Panoramic sweep over the GPUs of one node (BASELINE.json configs[4]: tuner hops x PSD stitched over NVLink, per-GPU
+ * channel detector, gather to rank 0).  One process per GPU; rank r owns a contiguous shard of the hop list
+ * (sdb_panoramic_shard), computes its hop PSDs, projects them onto the SpectrumView grid (and detects channels per
+ * hop), and the packed contribution lists are gathered on rank 0 with NCCL -- the one collective of the path -- where
+ * they are applied in global hop order: the result equals the reference's sequential view.feed(psd, nullptr, fftSize,
+ * fc) series (Panoramic/Scanner.cpp:503-523) value by value.  world = 1 needs no NCCL.
+ * The 128-byte NCCL id comes from sdb_panoramic_unique_id() on rank 0 and reaches the peers by whatever the launcher
+ * offers (torch.distributed broadcast, MPI, a file); NCCL itself is bound at run time (dlopen "libnccl.so.2").
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t psd_size; int32_t psd_window;      /* points per hop, SDB_WINDOW_* */
+  double   fft_bandwidth;                     /* sample rate of a hop (Hz) */
+  float    rel_bw;                            /* kept fraction of a hop, include/Scanner.h:70 (0 -> 0.5) */
+  double   freq_min, freq_max;                /* view range (Hz) */
+  int32_t  device;
+  int32_t  detect;                            /* per-hop channel detector (SPEC K) on the owning rank */
+  float    det_alpha, det_gamma, det_snr; uint32_t det_min_bins, channel_cap;
+  uint32_t frames_per_hop;                    /* windows per hop (0 = 1): the detector averages them, the view takes the last */
+} sdb_panoramic_params;
+typedef struct {
+  float    psd_project_ms, gather_ms, accumulate_ms;   /* device time of the three phases of the last sweep */
+  uint64_t gather_bytes;                               /* bytes rank 0 received (0 on one GPU) */
+  uint64_t n_hops_local;
+} sdb_panoramic_timing;
+typedef struct sdb_panoramic sdb_panoramic_t;
+int              sdb_panoramic_unique_id(void *id128);
+sdb_panoramic_t *sdb_panoramic_new(const sdb_panoramic_params *p, int rank, int world, const void *id128);
+void             sdb_panoramic_destroy(sdb_panoramic_t *s);
+void             sdb_panoramic_shard(size_t n_hops, int world, int rank, size_t *lo, size_t *hi);
+/* hops_local: this rank's shard [hi - lo][psd_size] complex64, one window per hop (device / host pointer);
+ * centers_all: host, all n_hops hop centres in sweep order.  Collective: every rank calls it. */
+int      sdb_panoramic_sweep_device(sdb_panoramic_t *s, const sdb_complex *hops_local_dev, const double *centers_all,
+                                    size_t n_hops);
+int      sdb_panoramic_sweep_host(sdb_panoramic_t *s, const sdb_complex *hops_local, const double *centers_all,
+                                  size_t n_hops);
+int      sdb_panoramic_reset(sdb_panoramic_t *s);                       /* SpectrumView::reset */
+uint32_t sdb_panoramic_size(const sdb_panoramic_t *s);
+int      sdb_panoramic_read(sdb_panoramic_t *s, float *psd, float *accum, float *count, size_t cap);   /* rank 0 */
+long     sdb_panoramic_read_channels(sdb_panoramic_t *s, size_t hop, sdb_detected_channel *out, size_t cap);
+int      sdb_panoramic_last_timing(const sdb_panoramic_t *s, sdb_panoramic_timing *t);
+const char *sdb_panoramic_last_error(void);
+
 /* SpectrumView::feed(SpectrumView const &detail) (Panoramic/Scanner.cpp:276-286): seed / refine a view with another
  * one's accumulators weighted by its counts -- what Scanner::setViewRange does on zoom (:471-479: flip, setRange,
  * feed(previous)).  Both views on the same device. */

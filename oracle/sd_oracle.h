@@ -67,6 +67,8 @@ typedef struct {
   int      four, kind;       /* kind 0: single Stockham, 1: four-step, 2: 65536 = 256 x 256 fft16 form */
   sdo_cpx *tw_a, *tw_b, *tw_n, *scr, *buf, *tmp;
 } sdo_spec_plan;
+/* SPEC R: block-wise DC removal of the source worker (tasks.c) */
+void sdo_dc_remove(float c[2], const sdo_cpx *x, sdo_cpx *y, size_t n, float alpha);
 /* speed leg of the CPU baseline (fft_fast.c): vectorisable Stockham transform, float32-rounding-equal to the SPEC
  * transforms, NOT bit-identical; enabled only by bench.py's CPU legs, never by a parity test */
 extern int sdo_fast_transforms;

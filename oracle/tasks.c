@@ -296,3 +296,27 @@ void sdo_snr_feed(sdo_snr_estimator *e, const unsigned *history, unsigned n)
 }
 
 float sdo_snr_get(const sdo_snr_estimator *e) { return 1.f / (e->intervals * e->sigma); }
+
+/* ------------------------------------------------------------------ R: DC removal ------------------
+ * suscan_analyzer_set_dc_remove (Suscan/Analyzer.cpp:229-236; toggled from Default/Source/SourceWidget.cpp).  The
+ * estimator lives in suscan (absent); SPEC R fixes a block-wise single pole: every sample of the block has the
+ * estimate c of the blocks before it subtracted (one binary32 subtraction per component), then
+ * c <- c + alpha (m - c) with m the mean of the RAW block, summed in binary64 in two fixed levels (runs of 256
+ * samples in index order, then the run sums in index order) and rounded to binary32 once. */
+void sdo_dc_remove(float c[2], const sdo_cpx *x, sdo_cpx *y, size_t n, float alpha)
+{
+  const size_t runs = (n + 255) / 256;
+  double tr = 0.0, ti = 0.0;
+  size_t r, i;
+  float mr, mi;
+  for (r = 0; r < runs; ++r) {
+    const size_t i0 = r * 256, i1 = i0 + 256 < n ? i0 + 256 : n;
+    double ar = 0.0, ai = 0.0;
+    for (i = i0; i < i1; ++i) { ar += (double) x[i].re; ai += (double) x[i].im; }
+    tr += ar; ti += ai;
+  }
+  mr = (float) (tr / (double) n); mi = (float) (ti / (double) n);
+  for (i = 0; i < n; ++i) { y[i].re = x[i].re - c[0]; y[i].im = x[i].im - c[1]; }
+  c[0] = c[0] + alpha * (mr - c[0]);
+  c[1] = c[1] + alpha * (mi - c[1]);
+}

@@ -246,6 +246,18 @@ _PROTOS = {
     "sdb_engine_set_inspector": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "sdb_inspector_config_default": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "sdb_engine_commit": (C.c_int, [C.c_void_p]),
+    "sdb_panoramic_unique_id": (C.c_int, [C.c_void_p]),
+    "sdb_panoramic_new": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "sdb_panoramic_destroy": (None, [C.c_void_p]),
+    "sdb_panoramic_shard": (None, [C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "sdb_panoramic_sweep_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_panoramic_sweep_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_panoramic_reset": (C.c_int, [C.c_void_p]),
+    "sdb_panoramic_size": (C.c_uint32, [C.c_void_p]),
+    "sdb_panoramic_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_panoramic_read_channels": (C.c_long, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "sdb_panoramic_last_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_panoramic_last_error": (C.c_char_p, []),
     "sdb_engine_migrate": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdb_engine_migrate_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_same_geometry": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -820,6 +832,94 @@ class Averager:
         out = np.empty((self.n_streams, self.psd_size), np.float32)
         _check(self._L.sdb_averager_read(self._h, out.ctypes.data, out.size))
         return out
+
+
+class PanoramicParams(C.Structure):
+    """sdb_panoramic_params"""
+    _fields_ = [("psd_size", C.c_uint32), ("psd_window", C.c_int32), ("fft_bandwidth", C.c_double),
+                ("rel_bw", C.c_float), ("freq_min", C.c_double), ("freq_max", C.c_double), ("device", C.c_int32),
+                ("detect", C.c_int32), ("det_alpha", C.c_float), ("det_gamma", C.c_float), ("det_snr", C.c_float),
+                ("det_min_bins", C.c_uint32), ("channel_cap", C.c_uint32), ("frames_per_hop", C.c_uint32)]
+
+
+class PanoramicTiming(C.Structure):
+    """sdb_panoramic_timing"""
+    _fields_ = [("psd_project_ms", C.c_float), ("gather_ms", C.c_float), ("accumulate_ms", C.c_float),
+                ("gather_bytes", C.c_uint64), ("n_hops_local", C.c_uint64)]
+
+
+def panoramic_unique_id():
+    """128-byte NCCL id (rank 0); hand it to the other ranks before they build their Panoramic."""
+    buf = (C.c_ubyte * 128)()
+    L = load_library()
+    if L.sdb_panoramic_unique_id(buf) != 0:
+        raise SdbError(L.sdb_panoramic_last_error().decode())
+    return bytes(buf)
+
+
+class Panoramic:
+    """sdb_panoramic_*: the sharded sweep + NCCL gather + stitch, all behind the C-ABI."""
+
+    def __init__(self, psd_size, window, fft_bandwidth, view_range, rel_bw=0.5, device=0, rank=0, world=1,
+                 unique_id=None, detect=None, channel_cap=64, frames_per_hop=1):
+        self._L = L = load_library()
+        d = detect or {}
+        p = PanoramicParams(psd_size, WINDOW[window] if isinstance(window, str) else window, fft_bandwidth, rel_bw,
+                            view_range[0], view_range[1], device, 1 if detect is not None else 0,
+                            d.get("alpha", 1.0), d.get("gamma", 0.5), d.get("snr", 6.0), d.get("min_bins", 2), channel_cap,
+                            frames_per_hop)
+        idb = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._h = L.sdb_panoramic_new(C.byref(p), rank, world, idb)
+        if not self._h:
+            raise SdbError(L.sdb_panoramic_last_error().decode())
+        self.rank, self.world, self.channel_cap = rank, world, channel_cap
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_panoramic_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def shard(n_hops, world, rank):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        load_library().sdb_panoramic_shard(n_hops, world, rank, C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def sweep(self, hops_local, centers_all):
+        """hops_local: this rank's shard [hi - lo, psd_size]: torch cuda complex64 tensor or numpy array."""
+        c = np.ascontiguousarray(centers_all, dtype=np.float64)
+        if _is_torch(hops_local):
+            assert hops_local.is_cuda and hops_local.is_contiguous()
+            rc = self._L.sdb_panoramic_sweep_device(self._h, hops_local.data_ptr() if hops_local.numel() else None,
+                                                    c.ctypes.data, len(c))
+        else:
+            x = np.ascontiguousarray(hops_local, dtype=np.complex64)
+            rc = self._L.sdb_panoramic_sweep_host(self._h, x.ctypes.data if x.size else None, c.ctypes.data, len(c))
+        if rc != 0:
+            raise SdbError(self._L.sdb_panoramic_last_error().decode())
+
+    def reset(self):
+        _check(self._L.sdb_panoramic_reset(self._h))
+
+    def read(self):
+        n = self._L.sdb_panoramic_size(self._h)
+        out = [np.empty(n, np.float32) for _ in range(3)]
+        if self._L.sdb_panoramic_read(self._h, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n) != 0:
+            raise SdbError(self._L.sdb_panoramic_last_error().decode())
+        return tuple(out)
+
+    def read_channels(self, hop):
+        buf = (DetectedChannel * self.channel_cap)()
+        n = self._L.sdb_panoramic_read_channels(self._h, hop, buf, self.channel_cap)
+        return [buf[i] for i in range(max(0, n))]
+
+    def timing(self):
+        t = PanoramicTiming()
+        self._L.sdb_panoramic_last_timing(self._h, C.byref(t))
+        return {"psd_project_ms": t.psd_project_ms, "gather_ms": t.gather_ms, "accumulate_ms": t.accumulate_ms,
+                "gather_bytes": int(t.gather_bytes), "n_hops_local": int(t.n_hops_local)}
 
 
 class SpectrumView:

@@ -191,6 +191,8 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
     cp_async_commit();
   };
   const uint32_t total = c.nchunks + INSP_STEPS;
+  // voted once by the whole warp (lanes without AGC or without a chain do not take part in the tracker below)
+  const bool fast_lines = __all_sync(0xffffffffu, !have_agc || (dl_size >= CH && mh_size >= CH));
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
@@ -206,7 +208,7 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
       float2 yv[CH]; float mv[CH];
 #pragma unroll
       for (int i = 0; i < CH; ++i) { yv[i] = sm.y[b3][i][lane]; mv[i] = sm.m[b3][i][lane]; }
-      if (__all_sync(0xffffffffu, dl_size >= CH && mh_size >= CH)) {
+      if (fast_lines) {
         // the CH slots a chunk touches are distinct: old values first, then the recurrence with stores only
         float2 xd[CH]; float mo[CH]; unsigned di[CH], mi[CH];
         unsigned dp = as.dl_ptr, mp = as.mh_ptr;
