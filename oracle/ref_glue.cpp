@@ -1,0 +1,111 @@
+// ref_glue.cpp -- ORACLE SUPPORT (test infrastructure): C entry points around DSP code of the reference that is
+// COMPILED FROM /root/reference where it lies (oracle/Makefile target `ref` -> oracle/_ref/libsdref.so; nothing of the
+// reference is copied into this repository).  It pins the restatements of oracle/*.c to the reference itself for the
+// arithmetic the reference does contain:
+//   Panoramic/Scanner.cpp:36-293   SigDigger::SpectrumView (setRange, feed x3, feedLinearMode, feedHistogramMode,
+//                                  interpolate, reset)            -> oracle/spectrumview.c
+//   Tasks/QuadDemodTask.cpp        QuadDemodTask::work            -> sdo_quad_demod
+//   Tasks/DelayedConjTask.cpp      DelayedConjTask::work          -> sdo_delayed_conj
+//   Tasks/WaveSampler.cpp          sampleManual / sampleZeroCrossing / sampleGardner (the latter over this repo's
+//                                  su_clock_detector shim)        -> sdo_sample_manual / _zero_crossing
+//   Misc/Averager.cpp              Averager::feed                 -> sdo_averager_feed
+// The Qt base classes are the no-behaviour stubs of oracle/ref_shim/; what moc would generate (the signal bodies) and
+// the CancellableTask plumbing are defined here.
+#include <Scanner.h>
+#include <QuadDemodTask.h>
+#include <DelayedConjTask.h>
+#include <WaveSampler.h>
+#include <Averager.h>
+
+// ---- Suscan::CancellableTask plumbing (Suscan/CancellableTask.cpp is Qt glue, not DSP)
+Suscan::CancellableTask::CancellableTask(QObject *parent) : QObject(parent) { prog = 0; }
+Suscan::CancellableTask::~CancellableTask(void) {}
+void Suscan::CancellableTask::setProgress(qreal p) { prog = p; }
+void Suscan::CancellableTask::setStatus(QString s) { status = s; }
+void Suscan::CancellableTask::setDataSize(quint64 s) { dataSize = s; }
+void Suscan::CancellableTask::done(void) {}
+void Suscan::CancellableTask::cancelled(void) {}
+void Suscan::CancellableTask::progress(qreal, QString) {}
+void Suscan::CancellableTask::error(QString) {}
+
+// ---- WaveSampler::data signal: collects what the task delivers
+static thread_local std::vector<SUCOMPLEX> *g_ws_out = nullptr;
+static thread_local std::vector<Symbol> *g_ws_sym = nullptr;
+void SigDigger::WaveSampler::data(SigDigger::WaveSampleSet set)
+{
+  if (g_ws_out) g_ws_out->insert(g_ws_out->end(), set.block, set.block + set.len);
+  if (g_ws_sym) g_ws_sym->insert(g_ws_sym->end(), set.symbols, set.symbols + set.len);
+}
+
+extern "C" {
+
+// ---- SpectrumView
+void *ref_sview_new(void) { return new SigDigger::SpectrumView(); }
+void ref_sview_free(void *v) { delete (SigDigger::SpectrumView *) v; }
+void ref_sview_set_range(void *v, double fmin, double fmax, double fft_bandwidth, float rel_bw)
+{
+  SigDigger::SpectrumView *s = (SigDigger::SpectrumView *) v;
+  s->setRange(fmin, fmax);
+  s->fftBandwidth = fft_bandwidth; s->fftRelBw = rel_bw;
+}
+void ref_sview_feed(void *v, const float *psd, const float *count, unsigned long size, double center, int adjust_sides)
+{ ((SigDigger::SpectrumView *) v)->feed(psd, count, size, center, adjust_sides != 0); }
+void ref_sview_feed_range(void *v, const float *psd, const float *count, unsigned long size, double fmin, double fmax, int adjust)
+{ ((SigDigger::SpectrumView *) v)->feed(psd, count, size, fmin, fmax, adjust != 0); }
+void ref_sview_feed_view(void *v, const void *detail) { ((SigDigger::SpectrumView *) v)->feed(*(const SigDigger::SpectrumView *) detail); }
+void ref_sview_interpolate(void *v) { ((SigDigger::SpectrumView *) v)->interpolate(); }
+void ref_sview_reset(void *v) { ((SigDigger::SpectrumView *) v)->reset(); }
+unsigned ref_sview_read(const void *v, float *psd, float *accum, float *count)
+{
+  const SigDigger::SpectrumView *s = (const SigDigger::SpectrumView *) v;
+  const unsigned n = s->spectrumSize;
+  memcpy(psd, s->psd, n * sizeof(float)); memcpy(accum, s->psdAccum, n * sizeof(float)); memcpy(count, s->psdCount, n * sizeof(float));
+  return n;
+}
+
+// ---- Tasks
+void ref_quad_demod(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n)
+{
+  QuadDemodTask t(data, dst, n);
+  while (t.work()) ;
+}
+void ref_delayed_conj(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, unsigned long delay)
+{
+  DelayedConjTask t(data, dst, n, delay);
+  while (t.work()) ;
+}
+// sync: 0 MANUAL, 1 GARDNER, 2 ZERO_CROSSING; space: 0 AMPLITUDE, 1 PHASE, 2 FREQUENCY.  Returns the number of soft
+// samples written to out (cap respected).
+long ref_wave_sampler(const SUCOMPLEX *data, size_t n, int sync, int space, double fs, double rate, double loop_gain,
+                      int amplitude, float thr_re, float thr_im, float zc_re, float zc_im, size_t symbol_sync,
+                      double symbol_count, SUCOMPLEX *out, unsigned char *sym_out, size_t cap)
+{
+  SigDigger::SamplingProperties p;
+  p.sync = (SigDigger::SamplingClockSync) sync; p.space = (SigDigger::SamplingSpace) space;
+  p.fs = fs; p.loopGain = loop_gain; p.amplitude = amplitude != 0;
+  p.threshold = SUCOMPLEX(thr_re, thr_im); p.zeroCrossingAngle = SUCOMPLEX(zc_re, zc_im);
+  p.data = data; p.length = n; p.symbolSync = symbol_sync; p.symbolCount = symbol_count; p.rate = rate;
+  Decider d;
+  std::vector<SUCOMPLEX> got; std::vector<Symbol> syms;
+  g_ws_out = &got; g_ws_sym = &syms;
+  {
+    SigDigger::WaveSampler ws(p, &d);
+    while (ws.work()) ;
+  }
+  g_ws_out = nullptr; g_ws_sym = nullptr;
+  const size_t m = got.size() < cap ? got.size() : cap;
+  if (out) memcpy(out, got.data(), m * sizeof(SUCOMPLEX));
+  if (sym_out) memcpy(sym_out, syms.data(), m);
+  return (long) got.size();
+}
+
+// ---- Averager: frames [n_frames][size] in order, result = averager state after the last
+void ref_averager(const float *frames, unsigned n_frames, unsigned size, float alpha, float *out)
+{
+  SigDigger::Averager a;
+  a.setAlpha(alpha);
+  for (unsigned f = 0; f < n_frames; ++f) a.feed(Suscan::PSDMessage(frames + (size_t) f * size, size));
+  memcpy(out, a.get(), size * sizeof(float));
+}
+
+}  // extern "C"

@@ -21,7 +21,15 @@ def reference_tu():
                         "-lsigutils", "-Wl,-rpath," + libdir, "-lpthread"], check=True)
         L = C.CDLL(so)
         L.tu_analyzer_session.restype = C.c_long
+        L.tu_analyzer_session.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_size_t, C.c_double, C.c_double,
+                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.tu_gardner_task.restype = C.c_long
+        L.tu_gardner_task.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_void_p, C.c_size_t]
+        L.tu_costas_task.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.tu_pll_task.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_int]
+        L.tu_agc_task.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float]
+        L.tu_xlate_task.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_int]
+        L.tu_lpf_task.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float]
         _lib = L
     return _lib
 

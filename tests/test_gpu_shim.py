@@ -90,9 +90,8 @@ def test_analyzer_session_through_the_suscan_names(tu, oracle):
     cap = n
     soft = np.zeros(cap, np.complex64); hard = np.zeros(cap, np.uint8); psd = np.zeros(N, np.float32)
     cnt = C.c_ulong(0)
-    got = tu.tu_analyzer_session(x.ctypes.data, C.c_size_t(n), fs, N, C.c_size_t(per_block), C.c_double(0.125 * fs),
-                                 C.c_double(3 * baud), C.c_float(baud), C.c_float(fs_ch * 2e-3), soft.ctypes.data,
-                                 hard.ctypes.data, C.c_size_t(cap), psd.ctypes.data, C.byref(cnt))
+    got = tu.tu_analyzer_session(x.ctypes.data, n, fs, N, per_block, 0.125 * fs, 3 * baud, baud, fs_ch * 2e-3,
+                                 soft.ctypes.data, hard.ctypes.data, cap, psd.ctypes.data, C.addressof(cnt))
     assert got > 0, got
     assert cnt.value == n // N
     ref_psd = oracle.psd_frames(x, N, "blackmann_harris")

@@ -1,0 +1,170 @@
+"""CPU: the oracle pinned to the REFERENCE ITSELF where the reference contains the arithmetic.  oracle/_ref/libsdref.so
+is built by `make -C oracle ref` from the sources under /root/reference where they lie (Panoramic/Scanner.cpp:1-293,
+Tasks/QuadDemodTask.cpp, Tasks/DelayedConjTask.cpp, Tasks/WaveSampler.cpp, Misc/Averager.cpp) behind no-behaviour Qt
+stubs (oracle/ref_shim/, oracle/ref_glue.cpp); nothing of the reference is copied.  The restatements of oracle/*.c are
+compared with it here; the Python transcriptions of tests/golden/make_golden.py stay as a second opinion.
+Skipped when the library was not built (no /root/reference and no prebuilt file)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libsdref.so")
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF) and os.path.isdir("/root/reference"):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], capture_output=True)
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/libsdref.so not built (needs /root/reference)")
+    L = C.CDLL(REF)
+    L.ref_sview_new.restype = C.c_void_p
+    L.ref_sview_read.restype = C.c_uint
+    L.ref_wave_sampler.restype = C.c_long
+    L.ref_wave_sampler.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_size_t, C.c_double, C.c_void_p,
+                                   C.c_void_p, C.c_size_t]
+    L.ref_sview_set_range.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_float]
+    L.ref_sview_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulong, C.c_double, C.c_int]
+    L.ref_sview_feed_view.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_sview_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_quad_demod.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.ref_delayed_conj.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_ulong]
+    L.ref_averager.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_void_p]
+    return L
+
+
+def _sview_ref(L, fmin, fmax, feeds, rel_bw=0.5):
+    v = C.c_void_p(L.ref_sview_new())
+    L.ref_sview_set_range(v, C.c_double(fmin), C.c_double(fmax), C.c_double(feeds[0][2]), C.c_float(rel_bw))
+    for psd, fc, bw in feeds:
+        L.ref_sview_set_range  # (range fixed)
+        p = np.ascontiguousarray(psd, np.float32)
+        L.ref_sview_feed(v, p.ctypes.data, None, C.c_ulong(len(p)), C.c_double(fc), 1)
+    out = [np.zeros(65536, np.float32) for _ in range(3)]
+    n = L.ref_sview_read(v, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+    return [o[:n].copy() for o in out], v
+
+
+def _sview_oracle(oracle, fmin, fmax, feeds, rel_bw=0.5):
+    L = oracle.lib()
+    v = oracle.SpectrumView()
+    assert L.sdo_sview_init(C.byref(v)) == 0
+    L.sdo_sview_set_range(C.byref(v), fmin, fmax)
+    v.fft_bandwidth = feeds[0][2]
+    v.fft_rel_bw = rel_bw
+    for psd, fc, bw in feeds:
+        p = np.ascontiguousarray(psd, np.float32)
+        L.sdo_sview_feed(C.byref(v), oracle.ptr(p), None, len(p), float(fc), 1)
+    n = v.spectrum_size
+    return [np.ctypeslib.as_array(q, shape=(65536,))[:n].copy() for q in (v.psd, v.psd_accum, v.psd_count)], v
+
+
+def test_spectrumview_restatement_equals_the_compiled_reference(ref, oracle):
+    """linear mode with revisits (forgetting rule, gap filling), histogram mode, and view-to-view feed"""
+    import make_golden as G
+    fmin, fmax, fftbw, psize, feeds = G.sview_case()
+    got, ov = _sview_oracle(oracle, fmin, fmax, feeds)
+    want, rv = _sview_ref(ref, fmin, fmax, feeds)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # histogram mode: hops narrower than two destination bins
+    rng = np.random.default_rng(3)
+    fmin2, fmax2 = 1.0e9, 1.0e9 + 65536 * 1000.0 * 40
+    feeds2 = [((rng.random(512).astype(np.float32) * 10 - 80), fmin2 + (5 + 37.3 * h) * 40e3, 30e3) for h in range(200)]
+    got, ov2 = _sview_oracle(oracle, fmin2, fmax2, feeds2)
+    want, rv2 = _sview_ref(ref, fmin2, fmax2, feeds2)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # SpectrumView::feed(SpectrumView const &): zoom path of Scanner::setViewRange
+    L = oracle.lib()
+    wide_o = oracle.SpectrumView(); assert L.sdo_sview_init(C.byref(wide_o)) == 0
+    L.sdo_sview_set_range(C.byref(wide_o), fmin - 10e6, fmax + 25e6)
+    wide_o.fft_bandwidth = fftbw; wide_o.fft_rel_bw = 0.5
+    L.sdo_sview_feed_view(C.byref(wide_o), C.byref(ov))
+    L.sdo_sview_interpolate(C.byref(wide_o))
+    wide_r = C.c_void_p(ref.ref_sview_new())
+    ref.ref_sview_set_range(wide_r, C.c_double(fmin - 10e6), C.c_double(fmax + 25e6), C.c_double(fftbw), C.c_float(0.5))
+    ref.ref_sview_feed_view(wide_r, rv)
+    out = [np.zeros(65536, np.float32) for _ in range(3)]
+    n = ref.ref_sview_read(wide_r, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+    assert n == wide_o.spectrum_size
+    for a, q in zip(out, (wide_o.psd, wide_o.psd_accum, wide_o.psd_count)):
+        assert np.array_equal(a[:n].view(np.uint32), np.ctypeslib.as_array(q, shape=(65536,))[:n].view(np.uint32))
+
+
+def test_timewindow_tasks_equal_the_compiled_reference(ref, oracle):
+    import make_golden as G
+    c = G.timewindow_case()
+    # QuadDemodTask: the reference calls std::arg (libm), the oracle its SPEC M atan2: equal to rounding
+    x = c["tone"][:5000]
+    y = np.zeros_like(x)
+    ref.ref_quad_demod(x.ctypes.data, y.ctypes.data, C.c_size_t(len(x)))
+    o = np.empty_like(x)
+    prev = oracle.Cpx(0, 0); primed = C.c_int(0)
+    oracle.lib().sdo_quad_demod(oracle.ptr(x), oracle.ptr(o), len(x), C.byref(prev), C.byref(primed))
+    assert y[0] == 0 and np.all(y.real == 0) and np.max(np.abs(y.imag - o.imag)) < 2e-7
+    # DelayedConjTask: to one ulp of cabsf (libm's hypot vs sqrtf of the sum of squares)
+    for delay in (7, 500):
+        x = c["tone"][:3000]
+        y = np.zeros_like(x)
+        ref.ref_delayed_conj(x.ctypes.data, y.ctypes.data, C.c_size_t(len(x)), C.c_ulong(delay))
+        o = oracle.delayed_conj(x, delay)
+        assert np.max(np.abs(y - o)) <= 4e-7 * np.max(np.abs(y))
+    # WaveSampler MANUAL in the three decision spaces: soft symbols bit for bit
+    for space, sig in (("amplitude", "ask"), ("phase", "psk"), ("frequency", "psk")):
+        x = np.ascontiguousarray(c[sig][:6000])
+        out = np.zeros(1024, np.complex64)
+        n = ref.ref_wave_sampler(x.ctypes.data, C.c_size_t(len(x)), 0, oracle.SPACE[space], C.c_double(1.0), C.c_double(0.1),
+                                 C.c_double(0.1), 0, C.c_float(0), C.c_float(0), C.c_float(1), C.c_float(0), C.c_size_t(5),
+                                 C.c_double(487.3), out.ctypes.data, None, C.c_size_t(1024))
+        o = oracle.sample_manual(x, space, 487.3, 5)
+        assert n == len(o) == 487
+        assert np.array_equal(out[:n].view(np.uint32), o.view(np.uint32)), space
+    # WaveSampler ZERO_CROSSING: recovered bit streams bit for bit
+    cases = [("ask", "amplitude", True, 0.6 + 0.1j, 1 + 0j, 1.0 / 12), ("ask", "amplitude", False, 0.55 + 0.2j, np.exp(-0.3j), 1.0 / 12),
+             ("psk", "phase", False, 0j, np.exp(0.1j), 1.0 / 12), ("ask", "amplitude", True, 0.6 + 0.1j, 1 + 0j, 1.0)]
+    for sig, space, amp, thr, zc, bnor in cases:
+        x = np.ascontiguousarray(c[sig])
+        sym = np.zeros(len(x), np.uint8)
+        n = ref.ref_wave_sampler(x.ctypes.data, C.c_size_t(len(x)), 2, oracle.SPACE[space], C.c_double(1.0), C.c_double(bnor),
+                                 C.c_double(0.1), int(amp), C.c_float(thr.real), C.c_float(thr.imag), C.c_float(np.real(zc)),
+                                 C.c_float(np.imag(zc)), C.c_size_t(0), C.c_double(100.0), None, sym.ctypes.data, C.c_size_t(len(x)))
+        o, k = oracle.sample_zero_crossing(x, space, bnor, amp, thr, zc)
+        assert n == k and np.array_equal(sym[:n], o), (sig, space, amp)
+
+
+def test_gardner_sampler_of_the_reference_over_the_clock_detector_shim(ref, oracle):
+    """Tasks/WaveSampler.cpp sampleGardner() compiled from the reference, running on THIS repo's su_clock_detector
+    (libsigutils.so): equal to the oracle's Gardner detector fed the same way."""
+    import make_golden as G
+    import shim_build as SB
+    x = np.ascontiguousarray(G.timewindow_case()["psk"])
+    out = np.zeros(len(x), np.complex64)
+    n = ref.ref_wave_sampler(x.ctypes.data, C.c_size_t(len(x)), 1, oracle.SPACE["frequency"], C.c_double(1.0),
+                             C.c_double(1.0 / 12), C.c_double(0.2), 0, C.c_float(0), C.c_float(0), C.c_float(1), C.c_float(0),
+                             C.c_size_t(0), C.c_double(100.0), out.ctypes.data, None, C.c_size_t(len(x)))
+    want = SB.oracle_gardner_frequency(oracle, x, 0.2, 1.0 / 12)
+    assert n == len(want) and np.array_equal(out[:n].view(np.uint32), want.view(np.uint32))
+
+
+def test_averager_restatement_equals_the_compiled_reference(ref, oracle):
+    rng = np.random.default_rng(9)
+    frames = (rng.random((7, 4096)).astype(np.float32) * 40 - 100)
+    for alpha in (0.25, 1.0):
+        out = np.zeros(4096, np.float32)
+        ref.ref_averager(frames.ctypes.data, 7, 4096, C.c_float(alpha), out.ctypes.data)
+        last = frames[0].copy()
+        L = oracle.lib()
+        for f in range(1, 7):
+            if alpha < 1.0:
+                L.sdo_averager_feed(oracle.ptr(last), oracle.ptr(np.ascontiguousarray(frames[f])), 4096, C.c_float(alpha))
+            else:
+                last = frames[f].copy()
+        assert np.array_equal(out.view(np.uint32), last.view(np.uint32)), alpha
