@@ -836,7 +836,7 @@ def main():
         # cfg2: the (latency-bound) inspector kernel of 1024 single-channel streams takes about as long as their
         # transforms; 2048 streams put the transforms on the critical path (33.9 / 53.3 / 64.5 GS/s at 512 / 1024 /
         # 2048 streams on one B200, profiles/r01_batch.md)
-        args.streams = {"cfg2": 2048, "cfg3": 128, "cfg4": 1024, "cfg5": 0}[args.workload]
+        args.streams = {"cfg2": 2048, "cfg3": 148, "cfg4": 1024, "cfg5": 0}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg5":

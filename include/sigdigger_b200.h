@@ -217,6 +217,9 @@ int  sdb_engine_set_channel_detector(sdb_engine_t *e, float alpha, float beta, f
  * 256-entry cap.  center_freq shifts the reported frequencies (source tuner frequency, sigutils_channel.ft). */
 long sdb_engine_read_channels(sdb_engine_t *e, uint32_t stream, double center_freq, sdb_detected_channel *out,
                               size_t cap, uint32_t *total);
+/* the lists of all streams in one read: centers[n_streams] (host), out[n_streams][cap], counts[n_streams] */
+int  sdb_engine_read_all_channels(sdb_engine_t *e, const double *centers, sdb_detected_channel *out, size_t cap,
+                                  uint32_t *counts);
 /* stand-alone detector on any device-resident linear PSD (e.g. the stitched SpectrumView of the panoramic
  * scanner, BASELINE config 5 "per-GPU channel detector"): psd_dev[stream][frame][n_bins], DC at index 0 */
 typedef struct sdb_chdet sdb_chdet_t;
@@ -226,6 +229,8 @@ void sdb_chdet_destroy(sdb_chdet_t *d);
 int  sdb_chdet_feed_device(sdb_chdet_t *d, const float *psd_dev, uint32_t frames, size_t stream_stride);
 long sdb_chdet_read(sdb_chdet_t *d, uint32_t stream, double samp_rate, double center_freq,
                     sdb_detected_channel *out, size_t cap, uint32_t *total);
+int  sdb_chdet_read_all(sdb_chdet_t *d, double samp_rate, const double *centers, sdb_detected_channel *out, size_t cap,
+                        uint32_t *counts);
 
 /* device-side views for zero-copy consumers / benchmarks */
 const uint32_t *sdb_engine_symbol_counts_device(const sdb_engine_t *e);

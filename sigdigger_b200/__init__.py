@@ -258,6 +258,8 @@ _PROTOS = {
     "sdb_panoramic_read_channels": (C.c_long, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "sdb_panoramic_last_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdb_panoramic_last_error": (C.c_char_p, []),
+    "sdb_engine_read_all_channels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sdb_chdet_read_all": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sdb_engine_migrate": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdb_engine_migrate_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_same_geometry": (C.c_int, [C.c_void_p, C.c_void_p]),

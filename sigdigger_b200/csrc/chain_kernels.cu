@@ -19,30 +19,33 @@
 #include "sdb_cpx.h"
 
 // ------------------------------------------------------------------ the chain kernel ------------
-// One CTA = 32 chains (lane = chain) x 6 role warps.  A feed is cut into chunks of CH samples that move through
-// eight pipeline steps, one CTA-wide barrier per iteration.  Recurrences keep one warp each and carry their loop
-// state in registers for the whole feed; everything feed-forward was pulled out of them:
+// One CTA = 32 chains (lane = chain) x 12 role warps.  A feed is cut into chunks of CH samples that move through
+// eight pipeline steps, one CTA-wide barrier per iteration; a step that is feed-forward (every output depends only
+// on inputs) is split over several warps by sample index, a step that is a true recurrence keeps one warp:
 //
-//   step  warp  role      work on its chunk                                                       hand-over
-//   0     0     load      cp.async tile of the chunk (coalesced rows of the 32 chains)             tile[2]
-//   1     1     pre       manual-offset LO, magnitude 10 log10 |y|^2                               y[3], m[3]
-//   2     0     track     AGC delay-line swap, peak tracker, fast / slow levels (recurrence)        in place
-//   3     1     post      gain 10^(level (slope - 1) / 20) x delayed sample                        ringA[2]
-//   4     2     carrier   Costas | PLL + component | FSK discriminator | audio demod (recurrence)   ringB (circular)
-//   5     3     filter    matched filter, 4 outputs per pass straight off ringB (the ring IS the
-//                         filter line), one packed FFMA2 per complex sample x tap; audio LPF (IIR)  ringC[2]
-//   6     4     clock     Gardner | sampler | resampler, CMA (recurrence)                          sym[2], cnt[2]
-//   7     5     out       x0.75, decision (atan2 / modulus quantiser), symbol stores                global
+//   step  warps  role      work on its chunk                                                    hand-over
+//   0     0      load      cp.async tile of the chunk (coalesced rows of the 32 chains)          tile[2]
+//   1     1-2    pre       manual-offset LO, magnitude 10 log10 |y|^2 (8 samples per warp)       y[3], m[3]
+//   2     0      track     AGC delay line swap, peak tracker, fast / slow levels (recurrence)     in place
+//   3     3-4    post      gain 10^(level (slope - 1) / 20) x delayed sample; for ask + PLL also
+//                          the phase detector's atan2 of the sample (feed-forward)               ringA[2], ang[2]
+//   4     5      carrier   Costas | PLL + component | FSK discriminator | audio demod (recurrence) ringB (circular)
+//   5     6-9    filter    matched filter: 4 outputs per warp straight off ringB (its history IS
+//                          the filter line), one FFMA2 per complex sample x tap; audio LPF (IIR, 1 warp) ringC[2]
+//   6     10     clock     Gardner | sampler | resampler, CMA (recurrence)                       sym[2], cnt[2]
+//   7     11     out       x0.75, decision (atan2 / modulus quantiser), symbol stores            global
 //
-// History (profiles/r02_inspector.md): round 1 ran four stage-warps per CTA at 2 CTAs per SM (issue slots 10 % busy,
-// half of the stall samples on the barrier behind the slowest stage).  The first re-map of this round (11 warps,
-// feed-forward steps split over several warps) showed where the time is: the carrier and clock warps were 82 % /
-// 76 % busy, every feed-forward warp 75-90 % idle, and with 90 KB per CTA only 1.7 CTAs were resident per SM.  So:
-// short chunks and a ring sized to the filter (37-55 KB per CTA: 4-5 CTAs per SM), one warp per step, the decision
-// and the stores moved out of the clock recurrence, and the roles specialised per inspector class (a CTA holds
-// chains of one class, sdb_build_chain_map) so that the per-sample class dispatch and its spills are gone.
-#define CH 8
-enum { W_TRACK = 0, W_GAIN = 1, W_CARRIER = 2, W_FILTER = 3, W_CLOCK = 4, W_OUT = 5, INSP_WARPS = 6 };
+// Round 1 ran four stage-warps per CTA (8 warps per SM: issue slots 10 % busy, half of all stall samples on
+// the barrier behind the slowest stage, profiles/r01_inspector_stages.md); the feed-forward work (two logarithm /
+// exponential evaluations, the 19...75-tap FIR, the decision) now runs beside the recurrences instead of in series
+// with them.  Loop state lives in registers for the whole feed; the per-chain lines (AGC delay line + magnitude
+// history, CMA) in shared memory sized from the channel plan (SdbInspDyn).  Two other mappings were built, measured
+// and dropped this round (profiles/r02_inspector.md): 6 warps x chunks of 8 with the roles specialised per inspector
+// class, and the same with every chunk loop unrolled over register arrays -- both correct, both slower: the kernel
+// grew to 360 KB / 676 KB of code and every role warp starved on instruction fetch.  The recurrences run at about
+// six cycles per instruction whatever the mapping, so this kernel keeps its loops rolled and its code small (84 KB).
+#define CH 16
+enum { W_TRACK = 0, W_PRE = 1, W_POST = 3, W_CARRIER = 5, W_MF = 6, W_CLOCK = 10, W_OUT = 11, INSP_WARPS = 12 };
 #define INSP_STEPS 7          // pipeline depth after the load: a chunk loaded in iteration c leaves in iteration c + 7
 
 #ifdef SDB_STAGE_CYCLES
@@ -93,17 +96,18 @@ struct ChainSmem {
   float2 ringA[2][CH][32];
   float2 ringC[2][CH][32];
   float2 sym[2][CH][32];
+  float  ang[2][CH][32];
   int    cnt[2][32];
 };
 
 // what every role needs to know about its lane's chain
 struct ICtx {
   ChainSmem *sm;
-  float2 (*rb)[32]; int rb_slots;             // ringB: carrier output, circular, doubles as the matched-filter line
+  float2 (*rb)[32]; unsigned rb_mask;         // ringB: carrier output, circular, doubles as the matched-filter line
   float  (*taps)[32];                         // per-lane matched-filter taps [t][lane]
   float  (*agc)[32]; int agc_rows;
   float2 (*eqw)[32]; float2 (*eqx)[32];
-  int lane, valid, fresh;
+  int lane, valid, cls, fresh;
   uint32_t n, nchunks;
   const SdbChainCfg *cp; SdbChainState *stp; float *bpool;
 };
@@ -139,19 +143,13 @@ static __device__ __forceinline__ float2 cma_step(float2 (*w)[32], float2 (*x)[3
   return make_float2(yr, yi);
 }
 
-static __device__ __forceinline__ int chunk_count(uint32_t base, uint32_t n)
-{
-  return base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
-}
-
 // ---- steps 0 + 2: tile loader and AGC tracker (warp 0)
-template <int CLS>
 static __device__ void role_track(const ICtx &c, const float2 *chan_row)
 {
   ChainSmem &sm = *c.sm;
   const int lane = c.lane;
   const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
-  const bool have_agc = CLS != SDB_INSP_RAW && c.valid && cp->have_agc;
+  const bool have_agc = c.valid && cp->have_agc && c.cls != SDB_INSP_RAW;
   float far_ = 0, faf = 0, sar = 0, saf = 0; unsigned hang_max = 0, dl_size = 1, mh_size = 1;
   AgcS as; as.fast = as.slow = as.peak = -160.0f; as.hang_n = as.dl_ptr = as.mh_ptr = 0;
   float *dl = nullptr, *mh = nullptr; bool in_smem = false;
@@ -175,14 +173,14 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
     }
   }
   // coalesced, asynchronous tile load: row r of the tile = CH consecutive samples of the CTA's chain r; a warp
-  // instruction copies 32 / CH rows (CH lanes x 8 bytes contiguous each)
+  // instruction copies two rows (16 lanes x 8 bytes = 128 contiguous bytes each)
   const unsigned long long rowp = (unsigned long long) chan_row;
   const uint32_t n = c.n;
   const int col = lane & (CH - 1), rsel = lane / CH;
   auto issue_tile = [&](uint32_t ch) {
     const uint32_t b0 = ch * CH;
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
+#pragma unroll 8
+    for (int j = 0; j < 32 / (32 / CH); ++j) {
       const int r = j * (32 / CH) + rsel;
       const unsigned long long pr = __shfl_sync(0xffffffffu, rowp, r);
       const uint32_t nr = __shfl_sync(0xffffffffu, n, r);
@@ -191,8 +189,6 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
     cp_async_commit();
   };
   const uint32_t total = c.nchunks + INSP_STEPS;
-  // voted once by the whole warp (lanes without AGC or without a chain do not take part in the tracker below)
-  const bool fast_lines = __all_sync(0xffffffffu, !have_agc || (dl_size >= CH && mh_size >= CH));
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
@@ -200,84 +196,35 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
     if (have_agc && it >= 2 && it - 2 < c.nchunks) {
       const uint32_t ck = it - 2, base = ck * CH;
       const int b3 = (int) (ck % 3u);
-      const int cnt = chunk_count(base, n);
-      // Everything the chunk needs is read BEFORE the first store: the delay line, the magnitude history and the
-      // hand-over buffers all live in the same shared-memory array, so a load that follows a store has to wait for
-      // it (the compiler cannot prove they do not alias), and with per-sample load / store pairs the recurrence
-      // was a chain of shared-memory round trips (profiles/r02_inspector.md: 760 cycles per sample).
-      float2 yv[CH]; float mv[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) { yv[i] = sm.y[b3][i][lane]; mv[i] = sm.m[b3][i][lane]; }
-      if (fast_lines) {
-        // the CH slots a chunk touches are distinct: old values first, then the recurrence with stores only
-        float2 xd[CH]; float mo[CH]; unsigned di[CH], mi[CH];
-        unsigned dp = as.dl_ptr, mp = as.mh_ptr;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          di[i] = dp; mi[i] = mp;
-          dp = dp + 1 >= dl_size ? 0 : dp + 1;
-          mp = mp + 1 >= mh_size ? 0 : mp + 1;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      for (int i = 0; i < cnt; ++i) {
+        // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
+        const float2 y = sm.y[b3][i][lane];
+        const unsigned dp = as.dl_ptr;
+        as.dl_ptr = dp + 1 >= dl_size ? 0 : dp + 1;
+        const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
+        dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
+        sm.y[b3][i][lane] = xd;
+        // magnitude history, running peak, fast / slow levels (SPEC A)
+        const float m = sm.m[b3][i][lane];
+        const float m_old = mh[as.mh_ptr * 32];
+        mh[as.mh_ptr * 32] = m;
+        if (++as.mh_ptr >= mh_size) as.mh_ptr = 0;
+        if (m > as.peak) {
+          as.peak = m;
+        } else if (as.peak == m_old) {
+          float pk = -160.0f;
+          for (unsigned q = 0; q < mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
+          as.peak = pk;
         }
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          xd[i] = make_float2(dl[(2 * di[i]) * 32], dl[(2 * di[i] + 1) * 32]);
-          mo[i] = mh[mi[i] * 32];
-        }
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          if (i < cnt) {
-            dl[(2 * di[i]) * 32] = yv[i].x; dl[(2 * di[i] + 1) * 32] = yv[i].y;
-            sm.y[b3][i][lane] = xd[i];
-            const float m = mv[i];
-            mh[mi[i] * 32] = m;
-            if (m > as.peak) {
-              as.peak = m;
-            } else if (as.peak == mo[i]) {
-              float pk = -160.0f;
-              for (unsigned q = 0; q < mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
-              as.peak = pk;
-            }
-            float d = as.peak - as.fast;
-            if (d > 0.0f) as.fast = as.fast + far_ * d;
-            else          as.fast = as.fast + faf * d;
-            d = as.peak - as.slow;
-            if (d > 0.0f) { as.slow = as.slow + sar * d; as.hang_n = 0; }
-            else if (as.hang_n >= hang_max) as.slow = as.slow + saf * d;
-            else ++as.hang_n;
-            sm.m[b3][i][lane] = as.fast > as.slow ? as.fast : as.slow;
-            as.dl_ptr = di[i] + 1 >= dl_size ? 0 : di[i] + 1;
-            as.mh_ptr = mi[i] + 1 >= mh_size ? 0 : mi[i] + 1;
-          }
-        }
-      } else {
-        // lines shorter than a chunk: a slot can be read after it was rewritten within the chunk, keep program order
-        for (int i = 0; i < cnt; ++i) {
-          const float2 y = yv[i];
-          const unsigned dp = as.dl_ptr;
-          as.dl_ptr = dp + 1 >= dl_size ? 0 : dp + 1;
-          const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
-          dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
-          sm.y[b3][i][lane] = xd;
-          const float m = mv[i];
-          const float m_old = mh[as.mh_ptr * 32];
-          mh[as.mh_ptr * 32] = m;
-          if (++as.mh_ptr >= mh_size) as.mh_ptr = 0;
-          if (m > as.peak) {
-            as.peak = m;
-          } else if (as.peak == m_old) {
-            float pk = -160.0f;
-            for (unsigned q = 0; q < mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
-            as.peak = pk;
-          }
-          float d = as.peak - as.fast;
-          if (d > 0.0f) as.fast = as.fast + far_ * d;
-          else          as.fast = as.fast + faf * d;
-          d = as.peak - as.slow;
-          if (d > 0.0f) { as.slow = as.slow + sar * d; as.hang_n = 0; }
-          else if (as.hang_n >= hang_max) as.slow = as.slow + saf * d;
-          else ++as.hang_n;
-          sm.m[b3][i][lane] = as.fast > as.slow ? as.fast : as.slow;
-        }
+        float d = as.peak - as.fast;
+        if (d > 0.0f) as.fast = as.fast + far_ * d;
+        else          as.fast = as.fast + faf * d;
+        d = as.peak - as.slow;
+        if (d > 0.0f) { as.slow = as.slow + sar * d; as.hang_n = 0; }
+        else if (as.hang_n >= hang_max) as.slow = as.slow + saf * d;
+        else ++as.hang_n;
+        sm.m[b3][i][lane] = as.fast > as.slow ? as.fast : as.slow;
       }
     }
     cp_async_wait<0>();
@@ -299,92 +246,109 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
   }
 }
 
-// ---- steps 1 + 3: manual-offset LO + magnitude in dB of chunk it-1, gain of chunk it-3 (warp 1; all feed-forward)
-template <int CLS>
-static __device__ void role_gain(const ICtx &c)
+// ---- step 1: manual-offset LO + magnitude in dB (warps 1-2, half a chunk each)
+static __device__ void role_pre(const ICtx &c, int part)
 {
   ChainSmem &sm = *c.sm;
   const int lane = c.lane;
-  const bool have_agc = CLS != SDB_INSP_RAW && c.valid && c.cp->have_agc;
-  const bool have_lo = CLS != SDB_INSP_AUDIO && c.valid && c.cp->have_lo;
+  const bool have_agc = c.valid && c.cp->have_agc && c.cls != SDB_INSP_RAW;
+  const bool have_lo = c.valid && c.cls != SDB_INSP_AUDIO && c.cp->have_lo;
   float lo_phi = have_lo ? c.stp->lo_phi : 0.0f;
   const float lo_omega = have_lo ? c.cp->lo_omega : 0.0f;
-  const float knee = c.valid ? c.cp->knee : 0.0f, slope_m1 = c.valid ? c.cp->gain_slope - 1.0f : 0.0f;
-  const float fixed_gain = c.valid ? c.cp->fixed_gain : 1.0f;
-  const float gain2 = (c.valid && CLS != SDB_INSP_AUDIO) ? c.cp->gain2 : 1.0f;
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+  const int i0 = part * (CH / 2), i1 = i0 + CH / 2;
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
     if (it >= 1 && it - 1 < c.nchunks) {
       const uint32_t ck = it - 1, base = ck * CH;
       const int b3 = (int) (ck % 3u);
-      const int cnt = chunk_count(base, n);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       float2 (*tl)[CH + 1] = sm.tile[ck & 1];
-      // all CH samples are evaluated unconditionally (independent instruction streams the scheduler can interleave);
-      // only the stores look at the sample count.  Slots past the count hold stale data: harmless, never stored.
-      float2 yy[CH]; float mm[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) yy[i] = tl[lane][i];
       if (have_lo) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
+        // both pre warps run the (cheap) phase recurrence over the whole chunk and evaluate exp(i phi) only for
+        // their own samples: phi is the same sequence of binary32 additions as in the serial statement
+        for (int i = 0; i < cnt; ++i) {
+          if (i >= i0 && i < i1) {
+            float s, co;
+            d_sincosf(lo_phi, &s, &co);
+            float2 y = tl[lane][i];
+            y = make_float2(y.x * co + y.y * s, y.y * co - y.x * s);
+            sm.y[b3][i][lane] = y;
+            if (have_agc) sm.m[b3][i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
+          }
+          lo_phi = wrap_once(lo_phi + lo_omega);
+        }
+      } else {
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
           if (i < cnt) {
-            const float2 ph = ncqo_read(lo_phi, lo_omega);
-            yy[i] = make_float2(yy[i].x * ph.x + yy[i].y * ph.y, yy[i].y * ph.x - yy[i].x * ph.y);
+            const float2 y = tl[lane][i];
+            sm.y[b3][i][lane] = y;
+            if (have_agc) sm.m[b3][i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
           }
         }
       }
-      if (have_agc) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) mm[i] = 10.0f * d_log10f(yy[i].x * yy[i].x + yy[i].y * yy[i].y + 1e-16f);
-      }
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i < cnt) {
-          sm.y[b3][i][lane] = yy[i];
-          if (have_agc) sm.m[b3][i][lane] = mm[i];
-        }
-      }
-    }
-    if (it >= 3 && it - 3 < c.nchunks) {
-      const uint32_t ck = it - 3, base = ck * CH;
-      const int b3 = (int) (ck % 3u);
-      const int cnt = chunk_count(base, n);
-      float2 (*out)[32] = sm.ringA[ck & 1];
-      float2 yy[CH]; float gg[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) { yy[i] = sm.y[b3][i][lane]; gg[i] = sm.m[b3][i][lane]; }
-      if (have_agc) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const float lvl = gg[i];
-          float g = lvl < knee ? fixed_gain : d_db_to_mag(lvl * slope_m1);
-          g = g * 0.7f;
-          yy[i].x = yy[i].x * g; yy[i].y = yy[i].y * g;
-          if (CLS != SDB_INSP_AUDIO) { yy[i].x = 2.0f * yy[i].x; yy[i].y = 2.0f * yy[i].y; }
-        }
-      } else if (CLS != SDB_INSP_RAW && CLS != SDB_INSP_AUDIO) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) { yy[i].x = gain2 * yy[i].x; yy[i].y = gain2 * yy[i].y; }
-      }
-#pragma unroll
-      for (int i = 0; i < CH; ++i)
-        if (i < cnt) out[i][lane] = yy[i];
     }
     ROLE_T1;
     cta_sync();
   }
-  ROLE_T_END(5);
-  if (have_lo) c.stp->lo_phi = lo_phi;
+  if (part == 0) ROLE_T_END(5);
+  if (have_lo && part == 0) c.stp->lo_phi = lo_phi;
 }
 
-// ---- step 4: carrier stage (warp 2)
-template <int CLS>
+// ---- step 3: gain (warps 3-4, half a chunk each)
+static __device__ void role_post(const ICtx &c, int part)
+{
+  ChainSmem &sm = *c.sm;
+  const int lane = c.lane, cls = c.cls;
+  const bool have_agc = c.valid && c.cp->have_agc && cls != SDB_INSP_RAW;
+  const float knee = c.valid ? c.cp->knee : 0.0f, slope_m1 = c.valid ? c.cp->gain_slope - 1.0f : 0.0f;
+  const float fixed_gain = c.valid ? c.cp->fixed_gain : 1.0f;
+  const float gain2 = (c.valid && cls != SDB_INSP_AUDIO) ? c.cp->gain2 : 1.0f;
+  const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
+  const int i0 = part * (CH / 2), i1 = i0 + CH / 2;
+  // ask + PLL: the phase detector's atan2 depends on the sample alone, not on the loop: evaluated here, beside the
+  // recurrence instead of inside it (same function on the same argument: bit-identical to pll_step)
+  const bool want_ang = c.valid && cls == SDB_INSP_ASK && c.cp->have_pll;
+  ROLE_T_DECL;
+  for (uint32_t it = 0; it <= total; ++it) {
+    ROLE_T0;
+    if (it >= 3 && it - 3 < c.nchunks) {
+      const uint32_t ck = it - 3, base = ck * CH;
+      const int b3 = (int) (ck % 3u);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*out)[32] = sm.ringA[ck & 1];
+      float (*ang)[32] = sm.ang[ck & 1];
+#pragma unroll 4
+      for (int i = i0; i < i1; ++i) {
+        if (i < cnt) {
+          float2 y = sm.y[b3][i][lane];
+          if (have_agc) {
+            const float lvl = sm.m[b3][i][lane];
+            float g = lvl < knee ? fixed_gain : d_db_to_mag(lvl * slope_m1);
+            g = g * 0.7f;
+            y.x = y.x * g; y.y = y.y * g;
+            if (cls != SDB_INSP_AUDIO) { y.x = 2.0f * y.x; y.y = 2.0f * y.y; }
+          } else if (cls != SDB_INSP_RAW && cls != SDB_INSP_AUDIO) {
+            y.x = gain2 * y.x; y.y = gain2 * y.y;
+          }
+          out[i][lane] = y;
+          if (want_ang) ang[i][lane] = d_atan2f(y.y, y.x);
+        }
+      }
+    }
+    ROLE_T1;
+    cta_sync();
+  }
+  if (part == 0) ROLE_T_END(6);
+}
+
+// ---- step 4: carrier stage (warp 5)
 static __device__ void role_carrier(const ICtx &c)
 {
   ChainSmem &sm = *c.sm;
-  const int lane = c.lane;
+  const int lane = c.lane, cls = c.cls;
   const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
   CostasK ck; CostasS cs; float p_phi = 0, p_omega = 0, pll_a = 0, pll_b = 0, prev_re = 0, prev_im = 0;
   float rot_re = 1, rot_im = 0, dc = 0, sq_level = 0, dc_alpha = 0, sq_alpha = 0, sq_thr = 0, lo_phi = 0, lo_omega = 0;
@@ -394,60 +358,45 @@ static __device__ void role_carrier(const ICtx &c)
 #pragma unroll
   for (int i = 0; i < SDB_MAX_IIR; ++i) { ck.af_b[i] = ck.af_a[i] = 0; cs.xr[i] = cs.xi[i] = cs.yr[i] = cs.yi[i] = 0; }
   if (c.valid) {
-    if (CLS == SDB_INSP_PSK) {
-      have_costas = cp->have_costas;
-      ck.kind = cp->costas_kind; ck.af_n = cp->af_n; ck.a = cp->c_a; ck.b = cp->c_b;
+    have_costas = cp->have_costas; have_pll = cp->have_pll;
+    ck.kind = cp->costas_kind; ck.af_n = cp->af_n; ck.a = cp->c_a; ck.b = cp->c_b;
 #pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) {
-        ck.af_b[i] = cp->af_b[i]; ck.af_a[i] = cp->af_a[i];
-        cs.xr[i] = stp->afx_re[i]; cs.xi[i] = stp->afx_im[i]; cs.yr[i] = stp->afy_re[i]; cs.yi[i] = stp->afy_im[i];
-      }
-      cs.phi = stp->c_phi; cs.omega = stp->c_omega; cs.lock = stp->c_lock; cs.yre = stp->c_yre; cs.yim = stp->c_yim;
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      ck.af_b[i] = cp->af_b[i]; ck.af_a[i] = cp->af_a[i];
+      cs.xr[i] = stp->afx_re[i]; cs.xi[i] = stp->afx_im[i]; cs.yr[i] = stp->afy_re[i]; cs.yi[i] = stp->afy_im[i];
     }
-    if (CLS == SDB_INSP_ASK) {
-      have_pll = cp->have_pll; ask_ch = cp->ask_channel;
-      p_phi = stp->p_phi; p_omega = stp->p_omega; pll_a = cp->pll_alpha; pll_b = cp->pll_beta;
-    }
-    if (CLS == SDB_INSP_FSK || CLS == SDB_INSP_AUDIO) { prev_re = stp->prev_re; prev_im = stp->prev_im; }
-    if (CLS == SDB_INSP_FSK) { rot_re = cp->fsk_rot_re; rot_im = cp->fsk_rot_im; quad = cp->fsk_quad_demod; }
-    if (CLS == SDB_INSP_AUDIO) {
-      ademod = cp->audio_demod; asquelch = cp->audio_squelch; dc = stp->dc; sq_level = stp->sq_level;
-      dc_alpha = cp->dc_alpha; sq_alpha = cp->sq_alpha; sq_thr = cp->sq_thr;
-      lo_phi = stp->lo_phi; lo_omega = cp->lo_omega;
-    }
+    cs.phi = stp->c_phi; cs.omega = stp->c_omega; cs.lock = stp->c_lock; cs.yre = stp->c_yre; cs.yim = stp->c_yim;
+    p_phi = stp->p_phi; p_omega = stp->p_omega; pll_a = cp->pll_alpha; pll_b = cp->pll_beta;
+    prev_re = stp->prev_re; prev_im = stp->prev_im;
+    rot_re = cp->fsk_rot_re; rot_im = cp->fsk_rot_im; quad = cp->fsk_quad_demod; ask_ch = cp->ask_channel;
+    ademod = cp->audio_demod; asquelch = cp->audio_squelch; dc = stp->dc; sq_level = stp->sq_level;
+    dc_alpha = cp->dc_alpha; sq_alpha = cp->sq_alpha; sq_thr = cp->sq_thr;
+    if (cls == SDB_INSP_AUDIO) { lo_phi = stp->lo_phi; lo_omega = cp->lo_omega; }
   }
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
-  int wr = 0;                                   // ring slot of the chunk's first sample
-  const int rb_slots = c.rb_slots;
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
     if (it >= 4 && it - 4 < c.nchunks) {
       const uint32_t ckk = it - 4, base = ckk * CH;
-      const int cnt = chunk_count(base, n);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       float2 (*in)[32] = sm.ringA[ckk & 1];
-      int slot = wr;
-      float2 xin[CH];                            // the chunk in registers before the first ring store (see role_track)
-#pragma unroll
-      for (int i = 0; i < CH; ++i) xin[i] = in[i][lane];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i >= cnt) break;
-        float2 y = xin[i];
-        if (CLS == SDB_INSP_PSK) {
+      for (int i = 0; i < cnt; ++i) {
+        float2 y = in[i][lane];
+        if (cls == SDB_INSP_PSK) {
           if (have_costas) y = costas_step(ck, cs, y);
-        } else if (CLS == SDB_INSP_FSK) {
+        } else if (cls == SDB_INSP_FSK) {
           float dr = y.x * prev_re + y.y * prev_im;
           float di = y.y * prev_re - y.x * prev_im;
           prev_re = y.x; prev_im = y.y;
           if (quad) { y.x = d_atan2f(di, dr) * 0.318309886183790671538f; y.y = 0.0f; }
           else { y.x = dr * rot_re - di * rot_im; y.y = dr * rot_im + di * rot_re; }
-        } else if (CLS == SDB_INSP_ASK) {
-          if (have_pll) y = pll_step(pll_a, pll_b, p_phi, p_omega, y);
+        } else if (cls == SDB_INSP_ASK) {
+          if (have_pll) y = pll_step_ang(pll_a, pll_b, p_phi, p_omega, y, sm.ang[ckk & 1][i][lane]);
           if (ask_ch == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
           else if (ask_ch == 1) { y.y = 0.0f; }
           else                  { y.x = y.y; y.y = 0.0f; }
-        } else if (CLS == SDB_INSP_AUDIO) {
+        } else if (cls == SDB_INSP_AUDIO) {
           float v = 0.0f;
           float p = y.x * y.x + y.y * y.y;
           sq_level = sq_level + sq_alpha * (p - sq_level);
@@ -467,69 +416,63 @@ static __device__ void role_carrier(const ICtx &c)
           if (asquelch && !(sq_level > sq_thr)) v = 0.0f;
           y = make_float2(v, 0.0f);
         }
-        c.rb[slot][lane] = y;
-        slot = slot + 1 == rb_slots ? 0 : slot + 1;
+        c.rb[(base + i) & c.rb_mask][lane] = y;
       }
-      wr += CH; if (wr >= rb_slots) wr -= rb_slots;
     }
     ROLE_T1;
     cta_sync();
   }
   ROLE_T_END(1);
   if (c.valid) {
-    if (CLS == SDB_INSP_PSK) {
 #pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) {
-        stp->afx_re[i] = cs.xr[i]; stp->afx_im[i] = cs.xi[i]; stp->afy_re[i] = cs.yr[i]; stp->afy_im[i] = cs.yi[i];
-      }
-      stp->c_phi = cs.phi; stp->c_omega = cs.omega; stp->c_lock = cs.lock; stp->c_yre = cs.yre; stp->c_yim = cs.yim;
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      stp->afx_re[i] = cs.xr[i]; stp->afx_im[i] = cs.xi[i]; stp->afy_re[i] = cs.yr[i]; stp->afy_im[i] = cs.yi[i];
     }
-    if (CLS == SDB_INSP_ASK) { stp->p_phi = p_phi; stp->p_omega = p_omega; }
-    if (CLS == SDB_INSP_FSK || CLS == SDB_INSP_AUDIO) { stp->prev_re = prev_re; stp->prev_im = prev_im; }
-    if (CLS == SDB_INSP_AUDIO) { stp->dc = dc; stp->sq_level = sq_level; stp->lo_phi = lo_phi; }
+    stp->c_phi = cs.phi; stp->c_omega = cs.omega; stp->c_lock = cs.lock; stp->c_yre = cs.yre; stp->c_yim = cs.yim;
+    stp->p_phi = p_phi; stp->p_omega = p_omega; stp->prev_re = prev_re; stp->prev_im = prev_im;
+    stp->dc = dc; stp->sq_level = sq_level;
+    if (cls == SDB_INSP_AUDIO) stp->lo_phi = lo_phi;
   }
 }
 
-// ---- step 5: matched filter / audio low-pass (warp 3)
+// ---- step 5: matched filter / audio low-pass (warps 6-9, a quarter of a chunk each)
 // The carrier ring IS the filter line: output p needs x[p - t], t < mf_n, which are the mf_n most recent ring
 // entries (the last mf_n - 1 samples of the previous feed are put back in front of position 0 at kernel start).
 // One thread produces 4 consecutive outputs of its chain from a sliding register window: per tap one ring load,
 // one tap load and four packed FFMA2 (complex sample x real tap, SPEC I.1: ascending taps, fused terms).
-template <int CLS>
-static __device__ void role_filter(const ICtx &c, const float *taps_pool)
+static __device__ void role_filter(const ICtx &c, int part, const float *taps_pool)
 {
   ChainSmem &sm = *c.sm;
   const int lane = c.lane;
   const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
-  const int have_mf = (CLS != SDB_INSP_RAW && CLS != SDB_INSP_AUDIO && c.valid) ? cp->have_mf : 0;
-  const int mf_n = have_mf ? cp->mf_n : 0;
-  const int alpf_n = (c.valid && CLS == SDB_INSP_AUDIO) ? cp->alpf_n : 0;
-  const int rb_slots = c.rb_slots;
-  const bool mf_ring = have_mf && mf_n - 1 + 2 * CH <= rb_slots;
+  const int have_mf = c.valid ? cp->have_mf : 0, mf_n = c.valid ? cp->mf_n : 0;
+  const int alpf_n = (c.valid && c.cls == SDB_INSP_AUDIO) ? cp->alpf_n : 0;
+  const bool mf_ring = have_mf && (unsigned) (mf_n - 1 + 2 * CH) <= c.rb_mask + 1u;
   const bool mf_global = have_mf && !mf_ring;
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
   float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
   unsigned mf_ptr = 0; float *mfl = nullptr; const float *gtaps = nullptr;
+  if (part == 0) {
 #pragma unroll
-  for (int i = 0; i < SDB_MAX_IIR; ++i) {
-    al_b[i] = c.valid ? cp->alpf_b[i] : 0.0f; al_a[i] = c.valid ? cp->alpf_a[i] : 0.0f;
-    al_x[i] = c.valid ? stp->al_x[i] : 0.0f; al_y[i] = c.valid ? stp->al_y[i] : 0.0f;
-    al_xi[i] = 0.0f; al_yi[i] = 0.0f;
+    for (int i = 0; i < SDB_MAX_IIR; ++i) {
+      al_b[i] = c.valid ? cp->alpf_b[i] : 0.0f; al_a[i] = c.valid ? cp->alpf_a[i] : 0.0f;
+      al_x[i] = c.valid ? stp->al_x[i] : 0.0f; al_y[i] = c.valid ? stp->al_y[i] : 0.0f;
+      al_xi[i] = 0.0f; al_yi[i] = 0.0f;
+    }
+    if (mf_ring) {
+      const float *tp = taps_pool + cp->mf_off;
+      const float *gmf = c.bpool + (size_t) cp->st_mf_off * 32;
+      for (int t = 0; t < mf_n; ++t) c.taps[t][lane] = __ldg(tp + t);
+      for (int k2 = 1; k2 < mf_n; ++k2)       // x[-k2]: the k2-th newest sample of the previous feed
+        c.rb[(0u - (unsigned) k2) & c.rb_mask][lane] =
+            c.fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * (k2 - 1)) * 32], gmf[(2 * (k2 - 1) + 1) * 32]);
+    } else if (mf_global) {
+      // filters too long for the ring keep a circular line in the global pool and run serially on one warp
+      gtaps = taps_pool + cp->mf_off; mf_ptr = stp->mf_ptr;
+      mfl = c.bpool + (size_t) cp->st_mf_off * 32;
+      if (c.fresh) for (int i = 0; i < 2 * mf_n; ++i) mfl[i * 32] = 0.0f;
+    }
   }
-  if (mf_ring) {
-    const float *tp = taps_pool + cp->mf_off;
-    const float *gmf = c.bpool + (size_t) cp->st_mf_off * 32;
-    for (int t = 0; t < mf_n; ++t) c.taps[t][lane] = __ldg(tp + t);
-    for (int k2 = 1; k2 < mf_n; ++k2)       // x[-k2]: the k2-th newest sample of the previous feed
-      c.rb[rb_slots - k2][lane] =
-          c.fresh ? make_float2(0.f, 0.f) : make_float2(gmf[(2 * (k2 - 1)) * 32], gmf[(2 * (k2 - 1) + 1) * 32]);
-  } else if (mf_global) {
-    // filters too long for the ring keep a circular line in the global pool and run serially
-    gtaps = taps_pool + cp->mf_off; mf_ptr = stp->mf_ptr;
-    mfl = c.bpool + (size_t) cp->st_mf_off * 32;
-    if (c.fresh) for (int i = 0; i < 2 * mf_n; ++i) mfl[i * 32] = 0.0f;
-  }
-  int rd = 0;                                   // ring slot of the chunk's first sample
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
@@ -537,76 +480,68 @@ static __device__ void role_filter(const ICtx &c, const float *taps_pool)
       const uint32_t ck = it - 5, base = ck * CH;
       float2 (*out)[32] = sm.ringC[ck & 1];
       if (mf_ring) {
-#pragma unroll
-        for (int blk = 0; blk < CH / 4; ++blk) {
-          const uint32_t p0 = base + (uint32_t) blk * 4u;
-          if (p0 < n) {
-            int s0 = rd + blk * 4; if (s0 >= rb_slots) s0 -= rb_slots;        // slot of x[p0]
-            int s3 = s0 + 3; if (s3 >= rb_slots) s3 -= rb_slots;              // slot of x[p0 + 3]
-            int s2 = s3 == 0 ? rb_slots - 1 : s3 - 1, s1 = s2 == 0 ? rb_slots - 1 : s2 - 1;
-            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-            float2 w3 = c.rb[s3][lane], w2 = c.rb[s2][lane], w1 = c.rb[s1][lane], w0 = c.rb[s0][lane];
-            int sx = s0;                                                      // slot of the next older sample
+        const uint32_t p0 = base + (uint32_t) part * 4u;
+        if (p0 < n) {
+          float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+          float2 w0 = c.rb[(p0 + 0) & c.rb_mask][lane], w1 = c.rb[(p0 + 1) & c.rb_mask][lane];
+          float2 w2 = c.rb[(p0 + 2) & c.rb_mask][lane], w3 = c.rb[(p0 + 3) & c.rb_mask][lane];
 #pragma unroll 4
-            for (int t = 0; t < mf_n; ++t) {
-              const float b = c.taps[t][lane];
-              const float2 bb = make_float2(b, b);
-              sx = sx == 0 ? rb_slots - 1 : sx - 1;
-              const float2 nx = c.rb[sx][lane];
-              a0 = sdb_fma2(bb, w0, a0); a1 = sdb_fma2(bb, w1, a1);
-              a2 = sdb_fma2(bb, w2, a2); a3 = sdb_fma2(bb, w3, a3);
-              w3 = w2; w2 = w1; w1 = w0; w0 = nx;
+          for (int t = 0; t < mf_n; ++t) {
+            const float b = c.taps[t][lane];
+            const float2 bb = make_float2(b, b);
+            const float2 nx = c.rb[(p0 - 1u - (unsigned) t) & c.rb_mask][lane];
+            a0 = sdb_fma2(bb, w0, a0); a1 = sdb_fma2(bb, w1, a1);
+            a2 = sdb_fma2(bb, w2, a2); a3 = sdb_fma2(bb, w3, a3);
+            w3 = w2; w2 = w1; w1 = w0; w0 = nx;
+          }
+          const int j0 = part * 4;
+          out[j0][lane] = a0;
+          if (p0 + 1 < n) out[j0 + 1][lane] = a1;
+          if (p0 + 2 < n) out[j0 + 2][lane] = a2;
+          if (p0 + 3 < n) out[j0 + 3][lane] = a3;
+        }
+      } else if (mf_global || alpf_n > 0) {
+        if (part == 0) {
+          const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+          for (int i = 0; i < cnt; ++i) {
+            float2 y = c.rb[(base + i) & c.rb_mask][lane];
+            if (mf_global) {
+              float accr = 0.0f, acci = 0.0f;
+              mfl[(2 * mf_ptr) * 32] = y.x; mfl[(2 * mf_ptr + 1) * 32] = y.y;
+              unsigned p = mf_ptr;
+              for (int t = 0; t < mf_n; ++t) {
+                const float b = __ldg(gtaps + t);
+                accr = __fmaf_rn(b, mfl[(2 * p) * 32], accr);
+                acci = __fmaf_rn(b, mfl[(2 * p + 1) * 32], acci);
+                p = p == 0 ? mf_n - 1 : p - 1;
+              }
+              mf_ptr = mf_ptr + 1 == (unsigned) mf_n ? 0 : mf_ptr + 1;
+              y = make_float2(accr, acci);
+            } else {
+              y = iir_any(alpf_n, al_b, al_a, al_x, al_xi, al_y, al_yi, y);
             }
-            const int j0 = blk * 4;
-            out[j0][lane] = a0;
-            if (p0 + 1 < n) out[j0 + 1][lane] = a1;
-            if (p0 + 2 < n) out[j0 + 2][lane] = a2;
-            if (p0 + 3 < n) out[j0 + 3][lane] = a3;
+            out[i][lane] = y;
           }
         }
       } else {
-        const int cnt = chunk_count(base, n);
-        int slot = rd;
-        for (int i = 0; i < cnt; ++i) {
-          float2 y = c.rb[slot][lane];
-          slot = slot + 1 == rb_slots ? 0 : slot + 1;
-          if (mf_global) {
-            float accr = 0.0f, acci = 0.0f;
-            mfl[(2 * mf_ptr) * 32] = y.x; mfl[(2 * mf_ptr + 1) * 32] = y.y;
-            unsigned p = mf_ptr;
-            for (int t = 0; t < mf_n; ++t) {
-              const float b = __ldg(gtaps + t);
-              accr = fmaf(b, mfl[(2 * p) * 32], accr);
-              acci = fmaf(b, mfl[(2 * p + 1) * 32], acci);
-              p = p == 0 ? mf_n - 1 : p - 1;
-            }
-            mf_ptr = mf_ptr + 1 == (unsigned) mf_n ? 0 : mf_ptr + 1;
-            y = make_float2(accr, acci);
-          } else if (CLS == SDB_INSP_AUDIO && alpf_n > 0) {
-            y = iir_any(alpf_n, al_b, al_a, al_x, al_xi, al_y, al_yi, y);
-          }
-          out[i][lane] = y;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t p = base + (uint32_t) (part * 4 + j);
+          if (p < n) out[part * 4 + j][lane] = c.rb[p & c.rb_mask][lane];
         }
       }
-      rd += CH; if (rd >= rb_slots) rd -= rb_slots;
     }
     ROLE_T1;
     cta_sync();
   }
-  ROLE_T_END(2);
-  if (c.valid) {
-    if (CLS == SDB_INSP_AUDIO) {
+  if (part == 0) ROLE_T_END(2);
+  if (part == 0 && c.valid) {
 #pragma unroll
-      for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
-    }
+    for (int i = 0; i < SDB_MAX_IIR; ++i) { stp->al_x[i] = al_x[i]; stp->al_y[i] = al_y[i]; }
     if (mf_ring) {
-      // x[n - k2] sits k2 slots behind the write position rd (= n mod rb_slots for this lane only if n is a
-      // multiple of CH; compute it from n directly)
       float *gmf = c.bpool + (size_t) cp->st_mf_off * 32;
-      const int wn = (int) (n % (uint32_t) rb_slots);
       for (int k2 = 1; k2 < mf_n; ++k2) {
-        int sl = wn - k2; if (sl < 0) sl += rb_slots;
-        const float2 v = c.rb[sl][lane];
+        const float2 v = c.rb[(n - (unsigned) k2) & c.rb_mask][lane];
         gmf[(2 * (k2 - 1)) * 32] = v.x; gmf[(2 * (k2 - 1) + 1) * 32] = v.y;
       }
     } else if (mf_global) {
@@ -615,13 +550,12 @@ static __device__ void role_filter(const ICtx &c, const float *taps_pool)
   }
 }
 
-// ---- step 6: clock recovery / sampler / resampler, CMA (warp 4).  Emits the chunk's symbols (before the x0.75 and
-// the decision) into sym[] and their number into cnt[].
-template <int CLS>
+// ---- step 6: clock recovery / sampler / resampler, CMA (warp 10).  Emits the chunk's symbols (before the x0.75
+// and the decision) into sym[] and their number into cnt[]; the out role finishes them.
 static __device__ void role_clock(const ICtx &c)
 {
   ChainSmem &sm = *c.sm;
-  const int lane = c.lane;
+  const int lane = c.lane, cls = c.cls;
   const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
   ClockS ks; float clk_gain = 0, clk_alpha = 0, clk_beta = 0, smp_period = 0, smp_phase0 = 0, s_phase = 0, s_pr = 0, s_pi = 0;
   int clock_type = 1, clock_running = 1;
@@ -629,21 +563,18 @@ static __device__ void role_clock(const ICtx &c)
   int eq_type = 0, eq_locked = 0; float eq_mu = 0;
   ks.phi = ks.bnor = ks.x0r = ks.x0i = ks.x1r = ks.x1i = ks.x2r = ks.x2i = ks.pr = ks.pi = 0; ks.half = 0;
   if (c.valid) {
-    if (CLS == SDB_INSP_AUDIO) {
-      avol = cp->audio_volume; rs_prev = stp->rs_prev; rs_step = cp->rs_step; rs_phase = stp->rs_phase;
-    } else if (CLS != SDB_INSP_RAW) {
-      ks.phi = stp->k_phi; ks.bnor = stp->k_bnor; ks.x0r = stp->k_x0r; ks.x0i = stp->k_x0i; ks.x1r = stp->k_x1r;
-      ks.x1i = stp->k_x1i; ks.x2r = stp->k_x2r; ks.x2i = stp->k_x2i; ks.pr = stp->k_pr; ks.pi = stp->k_pi;
-      ks.half = stp->k_half;
-      clk_gain = cp->clk_gain; clk_alpha = cp->clk_alpha; clk_beta = cp->clk_beta;
-      smp_period = cp->smp_period; smp_phase0 = cp->smp_phase0; s_phase = stp->s_phase; s_pr = stp->s_pr; s_pi = stp->s_pi;
-      clock_type = cp->clock_type; clock_running = cp->clock_running;
-      eq_type = cp->eq_type; eq_locked = cp->eq_locked; eq_mu = cp->eq_mu;
-      if (eq_type == 1) {
-        for (int i = 0; i < SDB_EQ_LEN; ++i) {
-          c.eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
-          c.eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
-        }
+    ks.phi = stp->k_phi; ks.bnor = stp->k_bnor; ks.x0r = stp->k_x0r; ks.x0i = stp->k_x0i; ks.x1r = stp->k_x1r;
+    ks.x1i = stp->k_x1i; ks.x2r = stp->k_x2r; ks.x2i = stp->k_x2i; ks.pr = stp->k_pr; ks.pi = stp->k_pi;
+    ks.half = stp->k_half;
+    clk_gain = cp->clk_gain; clk_alpha = cp->clk_alpha; clk_beta = cp->clk_beta;
+    smp_period = cp->smp_period; smp_phase0 = cp->smp_phase0; s_phase = stp->s_phase; s_pr = stp->s_pr; s_pi = stp->s_pi;
+    clock_type = cp->clock_type; clock_running = cp->clock_running;
+    avol = cp->audio_volume; rs_prev = stp->rs_prev; rs_step = cp->rs_step; rs_phase = stp->rs_phase;
+    eq_type = cp->eq_type; eq_locked = cp->eq_locked; eq_mu = cp->eq_mu;
+    if (eq_type == 1) {
+      for (int i = 0; i < SDB_EQ_LEN; ++i) {
+        c.eqw[i][lane] = make_float2(stp->eq_wr[i], stp->eq_wi[i]);
+        c.eqx[i][lane] = make_float2(stp->eq_xr[i], stp->eq_xi[i]);
       }
     }
   }
@@ -653,20 +584,15 @@ static __device__ void role_clock(const ICtx &c)
     ROLE_T0;
     if (it >= 6 && it - 6 < c.nchunks) {
       const uint32_t ck = it - 6, base = ck * CH;
-      const int cnt = chunk_count(base, n);
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       float2 (*in)[32] = sm.ringC[ck & 1];
       float2 (*sy)[32] = sm.sym[ck & 1];
       int k = 0;
-      float2 xin[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) xin[i] = in[i][lane];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i >= cnt) break;
-        float2 y = xin[i], o;
-        if (CLS == SDB_INSP_RAW) {
+      for (int i = 0; i < cnt; ++i) {
+        float2 y = in[i][lane], o;
+        if (cls == SDB_INSP_RAW) {
           sy[k++][lane] = y;
-        } else if (CLS == SDB_INSP_AUDIO) {
+        } else if (cls == SDB_INSP_AUDIO) {
           rs_phase += rs_step;
           if (rs_phase >= 1.0) {
             rs_phase -= 1.0;
@@ -690,79 +616,54 @@ static __device__ void role_clock(const ICtx &c)
   }
   ROLE_T_END(3);
   if (c.valid) {
-    if (CLS == SDB_INSP_AUDIO) {
-      stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
-    } else if (CLS != SDB_INSP_RAW) {
-      stp->k_phi = ks.phi; stp->k_bnor = ks.bnor; stp->k_x0r = ks.x0r; stp->k_x0i = ks.x0i; stp->k_x1r = ks.x1r;
-      stp->k_x1i = ks.x1i; stp->k_x2r = ks.x2r; stp->k_x2i = ks.x2i; stp->k_pr = ks.pr; stp->k_pi = ks.pi;
-      stp->k_half = ks.half; stp->s_phase = s_phase; stp->s_pr = s_pr; stp->s_pi = s_pi;
-      if (eq_type == 1) {
-        for (int i = 0; i < SDB_EQ_LEN; ++i) {
-          stp->eq_wr[i] = c.eqw[i][lane].x; stp->eq_wi[i] = c.eqw[i][lane].y;
-          stp->eq_xr[i] = c.eqx[i][lane].x; stp->eq_xi[i] = c.eqx[i][lane].y;
-        }
+    stp->k_phi = ks.phi; stp->k_bnor = ks.bnor; stp->k_x0r = ks.x0r; stp->k_x0i = ks.x0i; stp->k_x1r = ks.x1r;
+    stp->k_x1i = ks.x1i; stp->k_x2r = ks.x2r; stp->k_x2i = ks.x2i; stp->k_pr = ks.pr; stp->k_pi = ks.pi;
+    stp->k_half = ks.half; stp->s_phase = s_phase; stp->s_pr = s_pr; stp->s_pi = s_pi;
+    stp->rs_prev = rs_prev; stp->rs_phase = rs_phase;
+    if (eq_type == 1) {
+      for (int i = 0; i < SDB_EQ_LEN; ++i) {
+        stp->eq_wr[i] = c.eqw[i][lane].x; stp->eq_wi[i] = c.eqw[i][lane].y;
+        stp->eq_xr[i] = c.eqx[i][lane].x; stp->eq_xi[i] = c.eqx[i][lane].y;
       }
     }
   }
 }
 
-// ---- step 7: -2.5 dB, decision, symbol stores (warp 5; feed-forward)
-template <int CLS>
+// ---- step 7: -2.5 dB, decision, symbol stores (warp 11; feed-forward, off the clock recurrence)
 static __device__ void role_out(const ICtx &c, float2 *__restrict__ so, unsigned char *__restrict__ ho,
                                 uint32_t *__restrict__ sym_count, size_t sym_cap)
 {
   ChainSmem &sm = *c.sm;
-  const int lane = c.lane;
+  const int lane = c.lane, cls = c.cls;
   int dec_mode = 0, dec_int = 1; float dec_min = 0, dec_h = 1;
   if (c.valid) { dec_mode = c.cp->dec_mode; dec_int = c.cp->dec_intervals; dec_min = c.cp->dec_min; dec_h = c.cp->dec_h; }
+  const bool decided = cls != SDB_INSP_RAW && cls != SDB_INSP_AUDIO;
   uint32_t nout = 0;
   const uint32_t total = c.nchunks + INSP_STEPS;
-  ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
-    ROLE_T0;
     if (it >= 7 && it - 7 < c.nchunks) {
       const uint32_t ck = it - 7;
       const int k = c.valid ? sm.cnt[ck & 1][lane] : 0;
       float2 (*sy)[32] = sm.sym[ck & 1];
-      float2 ov[CH]; unsigned char hv[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        float2 o = sy[j][lane];
-        unsigned char h = 0;
-        if (CLS != SDB_INSP_RAW && CLS != SDB_INSP_AUDIO) {
-          o.x = 0.75f * o.x; o.y = 0.75f * o.y;
-          h = decide(dec_mode, dec_min, dec_h, dec_int, o);
-        }
-        ov[j] = o; hv[j] = h;
-      }
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        if (j < k && nout < sym_cap) {
-          so[nout] = ov[j]; ho[nout] = hv[j];
+      for (int j = 0; j < k; ++j) {
+        if (nout < sym_cap) {
+          float2 o = sy[j][lane];
+          unsigned char h = 0;
+          if (decided) {
+            o.x = 0.75f * o.x; o.y = 0.75f * o.y;
+            h = decide(dec_mode, dec_min, dec_h, dec_int, o);
+          }
+          so[nout] = o; ho[nout] = h;
           ++nout;
         }
       }
     }
-    ROLE_T1;
     cta_sync();
   }
-  ROLE_T_END(6);
   if (c.valid) *sym_count = nout;
 }
 
-template <int CLS>
-static __device__ __forceinline__ void run_roles(const ICtx &c, int warp, const float2 *chan_row, const float *taps_pool,
-                                                 float2 *so, unsigned char *ho, uint32_t *sym_count, size_t sym_cap)
-{
-  if (warp == W_TRACK) role_track<CLS>(c, chan_row);
-  else if (warp == W_GAIN) role_gain<CLS>(c);
-  else if (warp == W_CARRIER) role_carrier<CLS>(c);
-  else if (warp == W_FILTER) role_filter<CLS>(c, taps_pool);
-  else if (warp == W_CLOCK) role_clock<CLS>(c);
-  else role_out<CLS>(c, so, ho, sym_count, sym_cap);
-}
-
-__global__ void __launch_bounds__(INSP_WARPS * 32, 3) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
+__global__ void __launch_bounds__(INSP_WARPS * 32, 2) k_inspectors(const SdbChainCfg *__restrict__ cfgs, int n_channels,
                                                      int n_streams, const int *__restrict__ chain_map,
                                                      SdbChainState *__restrict__ states,
                                                      float *__restrict__ pool, size_t pool_stride,
@@ -779,7 +680,7 @@ __global__ void __launch_bounds__(INSP_WARPS * 32, 3) k_inspectors(const SdbChai
   c.sm = reinterpret_cast<ChainSmem *>(smem_raw);
   unsigned char *dp = smem_raw + sizeof(ChainSmem);
   c.rb = reinterpret_cast<float2 (*)[32]>(dp); dp += (size_t) dyn.rb_slots * 32 * sizeof(float2);
-  c.rb_slots = dyn.rb_slots;
+  c.rb_mask = (unsigned) dyn.rb_slots - 1u;
   c.taps = reinterpret_cast<float (*)[32]>(dp); dp += (size_t) dyn.mf_rows * 32 * sizeof(float);
   c.agc = reinterpret_cast<float (*)[32]>(dp); dp += (size_t) dyn.agc_rows * 32 * sizeof(float);
   c.agc_rows = dyn.agc_rows;
@@ -794,31 +695,30 @@ __global__ void __launch_bounds__(INSP_WARPS * 32, 3) k_inspectors(const SdbChai
   const int chain = s * n_channels + k;                // index into states / outputs (stream-major)
   c.lane = lane; c.valid = valid ? 1 : 0; c.fresh = fresh;
   c.cp = cfgs + k; c.stp = states + chain;
+  c.cls = valid ? c.cp->cls : -1;
   c.n = valid ? n_hops * (uint32_t) chans[k].halfsz : 0;
   c.bpool = pool + (size_t) blockIdx.x * 32 * pool_stride + lane;     // per-CTA pool, interleaved [slot][lane]
-  __shared__ uint32_t s_nmax; __shared__ int s_cls;
-  if (threadIdx.x == 0) { s_nmax = 0; s_cls = SDB_INSP_RAW; }
+  __shared__ uint32_t s_nmax;
+  if (threadIdx.x == 0) s_nmax = 0;
   __syncthreads();
-  if (warp == 0) {
-    atomicMax(&s_nmax, c.n);
-    // the CTA's class: that of its first valid chain (a CTA holds one class, sdb_build_chain_map)
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-    if (vm && lane == __ffs(vm) - 1) s_cls = c.cp->cls;
-  }
+  if (warp == 0) atomicMax(&s_nmax, c.n);
   __syncthreads();
   c.nchunks = (s_nmax + CH - 1) / CH;
-  if (valid && c.cp->cls != s_cls) { c.valid = 0; c.n = 0; }   // never happens with a chain map; keeps a mixed CTA safe
 
-  const float2 *row = valid ? chan_in + (size_t) s * chan_stream_stride + chans[k].out_off : nullptr;
-  float2 *so = soft + (size_t) chain * sym_cap;
-  unsigned char *ho = hard + (size_t) chain * sym_cap;
-  uint32_t *sc = sym_counts + chain;
-  switch (s_cls) {
-    case SDB_INSP_PSK:   run_roles<SDB_INSP_PSK>(c, warp, row, taps_pool, so, ho, sc, sym_cap); break;
-    case SDB_INSP_FSK:   run_roles<SDB_INSP_FSK>(c, warp, row, taps_pool, so, ho, sc, sym_cap); break;
-    case SDB_INSP_ASK:   run_roles<SDB_INSP_ASK>(c, warp, row, taps_pool, so, ho, sc, sym_cap); break;
-    case SDB_INSP_AUDIO: run_roles<SDB_INSP_AUDIO>(c, warp, row, taps_pool, so, ho, sc, sym_cap); break;
-    default:             run_roles<SDB_INSP_RAW>(c, warp, row, taps_pool, so, ho, sc, sym_cap); break;
+  if (warp == W_TRACK) {
+    role_track(c, valid ? chan_in + (size_t) s * chan_stream_stride + chans[k].out_off : nullptr);
+  } else if (warp < W_POST) {
+    role_pre(c, warp - W_PRE);
+  } else if (warp < W_CARRIER) {
+    role_post(c, warp - W_POST);
+  } else if (warp == W_CARRIER) {
+    role_carrier(c);
+  } else if (warp < W_CLOCK) {
+    role_filter(c, warp - W_MF, taps_pool);
+  } else if (warp == W_CLOCK) {
+    role_clock(c);
+  } else {
+    role_out(c, soft + (size_t) chain * sym_cap, hard + (size_t) chain * sym_cap, sym_counts + chain, sym_cap);
   }
 }
 

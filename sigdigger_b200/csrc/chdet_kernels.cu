@@ -245,6 +245,35 @@ extern "C" int sdb_chdet_feed_device(sdb_chdet_t *d, const float *psd_dev, uint3
   return cudaStreamSynchronize(nullptr) == cudaSuccess ? 0 : -1;
 }
 
+// every stream's list in three copies instead of three per stream (the panoramic sweep reads 128...1024 hops):
+// centers[S] host, out[S][cap], counts[S] (clamped to cap)
+extern "C" int sdb_chdet_read_all(sdb_chdet_t *d, double samp_rate, const double *centers, sdb_detected_channel *out,
+                                  size_t cap, uint32_t *counts)
+{
+  if (!d || !centers || !out || !counts) return -1;
+  if (cudaSetDevice(d->device) != cudaSuccess) return -1;
+  const size_t S = d->S;
+  std::vector<unsigned> cnt(S);
+  std::vector<SdbDetectedDev> h(S * CHDET_CAP);
+  if (cudaMemcpy(cnt.data(), d->d_count, S * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (cudaMemcpy(h.data(), d->d_out, h.size() * sizeof(SdbDetectedDev), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  const double df = samp_rate / (double) d->N, half = (double) (d->N / 2);
+  for (size_t s = 0; s < S; ++s) {
+    const size_t n = cnt[s] < cap ? cnt[s] : cap;
+    counts[s] = (uint32_t) n;
+    for (size_t i = 0; i < n; ++i) {
+      const SdbDetectedDev &q = h[s * CHDET_CAP + i];
+      sdb_detected_channel &c = out[s * cap + i];
+      c.bin_lo = q.bin_lo; c.bin_hi = q.bin_hi;
+      c.f_lo = centers[s] + ((double) q.bin_lo - half) * df;
+      c.f_hi = centers[s] + ((double) q.bin_hi - half) * df;
+      c.fc = 0.5 * (c.f_lo + c.f_hi); c.bw = c.f_hi - c.f_lo;
+      c.S0 = q.s0; c.N0 = q.n0; c.snr = q.snr;
+    }
+  }
+  return 0;
+}
+
 extern "C" long sdb_chdet_read(sdb_chdet_t *d, uint32_t stream, double samp_rate, double center_freq,
                                sdb_detected_channel *out, size_t cap, uint32_t *total)
 {

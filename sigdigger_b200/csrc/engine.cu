@@ -351,6 +351,21 @@ extern "C" long sdb_engine_read_channels(sdb_engine_t *e, uint32_t stream, doubl
   return n;
 }
 
+extern "C" int sdb_chdet_read_all(struct sdb_chdet *d, double samp_rate, const double *centers, sdb_detected_channel *out,
+                                  size_t cap, uint32_t *counts);
+// all streams at once: centers[S] (host), out[S][cap], counts[S]
+extern "C" int sdb_engine_read_all_channels(sdb_engine_t *e, const double *centers, sdb_detected_channel *out, size_t cap,
+                                            uint32_t *counts)
+{
+  if (!e || !centers || !out || !counts) return fail("null argument");
+  if (!e->committed || !e->chdet) return fail("channel detector not enabled");
+  CK(cudaSetDevice(e->prm.device));
+  CK(cudaStreamSynchronize(e->psd_stream ? e->psd_stream : e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (sdb_chdet_read_all(e->chdet, e->samp_rate, centers, out, cap, counts)) return fail("channel read failed");
+  return 0;
+}
+
 static const char *kSpectNames[SDB_SPECTSRC_COUNT] = { "none", "psd", "cyclo", "fmspect", "timediff", "abstimediff",
                                                       "exp_2", "exp_4", "exp_8", "fac" };
 static const char *kEstNames[SDB_ESTIMATOR_COUNT] = { "baud-fac", "baud-nonlinear" };

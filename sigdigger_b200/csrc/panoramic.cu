@@ -224,11 +224,8 @@ static int sweep_impl(sdb_panoramic *s, const sdb_complex *hops_local, int on_de
       const size_t cap = s->prm.channel_cap;
       std::vector<int32_t> cnt(pl, 0);
       std::vector<sdb_detected_channel> ch(pl * cap);
-      for (size_t h = 0; h < n_local; ++h) {
-        uint32_t total = 0;
-        const long n = sdb_engine_read_channels(s->eng, (uint32_t) h, centers_all[lo + h], &ch[h * cap], cap, &total);
-        cnt[h] = n > 0 ? (int32_t) n : 0;
-      }
+      if (sdb_engine_read_all_channels(s->eng, centers_all + lo, ch.data(), cap, (uint32_t *) cnt.data()))
+        return pfail(sdb_last_error());
       PCK(cudaMemcpy(scnt, cnt.data(), pl * sizeof(int32_t), cudaMemcpyHostToDevice));
       PCK(cudaMemcpy(sch, ch.data(), pl * cap * sizeof(sdb_detected_channel), cudaMemcpyHostToDevice));
     }

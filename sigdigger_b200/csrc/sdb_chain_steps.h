@@ -155,6 +155,19 @@ SDB_HD float2 pll_step(float alpha, float beta, float &phi, float &omega, float2
   return mix;
 }
 
+// the same with the phase detector's angle atan2(x.im, x.re) supplied by the caller (it depends on the sample only)
+SDB_HD float2 pll_step_ang(float alpha, float beta, float &phi, float &omega, float2 x, float ang)
+{
+  float2 ref = ncqo_read(phi, omega);
+  float2 mix = make_float2(x.x * ref.x + x.y * ref.y, x.y * ref.x - x.x * ref.y);
+  float err = ang - phi;
+  if (err > PI_F) err = err - TWOPI_F;
+  else if (err < -PI_F) err = err + TWOPI_F;
+  omega = omega + alpha * err;
+  phi = wrap_once(phi + beta * err);
+  return mix;
+}
+
 struct ClockS { float phi, bnor, x0r, x0i, x1r, x1i, x2r, x2i, pr, pi; int half; };
 
 SDB_HD bool clock_step(float gain, float alpha, float beta, ClockS &s, float2 v, float2 &out)

@@ -169,10 +169,10 @@ struct SdbSpectCfg {
 };
 
 // plan-dependent shared-memory lines of k_inspectors (chain_kernels.cu): sized from the channel plan
-#define SDB_INSP_CHUNK 8           // samples per pipeline chunk (CH in chain_kernels.cu)
-#define SDB_INSP_MF_RING_MAX 241   // longest matched filter served from the shared-memory ring (256 slots)
+#define SDB_INSP_CHUNK 16          // samples per pipeline chunk (CH in chain_kernels.cu)
+#define SDB_INSP_MF_RING_MAX 225   // longest matched filter served from the shared-memory ring (256 slots)
 struct SdbInspDyn {
-  int rb_slots;             // carrier ring slots (longest ring-served filter - 1 + 2 chunks)
+  int rb_slots;             // carrier ring slots (power of two >= longest ring-served filter - 1 + 2 chunks)
   int mf_rows;              // tap rows [t][lane] of the longest ring-served matched filter
   int agc_rows;             // floats per chain for the AGC delay line + magnitude history
   int use_eq;               // some chain runs the CMA equaliser
@@ -183,8 +183,9 @@ static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
   for (int k = 0; k < n; ++k) {
     const SdbChainCfg &c = cfgs[k];
     if (c.have_mf && c.mf_n <= SDB_INSP_MF_RING_MAX) {        // longer filters stay in the global pool
-      const int need = c.mf_n - 1 + 2 * SDB_INSP_CHUNK;
-      if (need > d.rb_slots) d.rb_slots = need;
+      int need = c.mf_n - 1 + 2 * SDB_INSP_CHUNK, slots = 2 * SDB_INSP_CHUNK;
+      while (slots < need) slots <<= 1;
+      if (slots > d.rb_slots) d.rb_slots = slots;
       if (c.mf_n > d.mf_rows) d.mf_rows = c.mf_n;
     }
     if (c.have_agc) {

@@ -203,40 +203,40 @@ __global__ void k_sview_accumulate(unsigned spectrum_size, const int *__restrict
   accum[j] = a; count[j] = c; psd[j] = p;
 }
 
-// final gap filling: exactly interpolate()'s treatment of runs of empty bins (Scanner.cpp:56-116).
-// A single thread walks the array (65536 bins, once per sweep): the loop carries `left` from the
-// possibly just-filled previous bin, as the reference does.
+// final gap filling: exactly interpolate()'s treatment of runs of empty bins (Scanner.cpp:56-116).  A gap's fill
+// values depend only on the non-empty bins on either side of it (which the fill never touches), so gaps are
+// independent: every thread owns the gaps that START in its 64-bin segment, walks each to its end and fills it.
+// (Round 1 walked the whole array with one thread: 6.8 ms per sweep for 65536 bins.)
+#define SVIEW_SEG 64
 __global__ void k_sview_fill(unsigned spectrum_size, float *__restrict__ psd, const float *__restrict__ count)
 {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  unsigned i, j, cnt = 1, zero_pos = 0;
-  bool first = true, in_gap = false;
-  float left = -200.0f, right, t;
-  for (i = 0; i < spectrum_size; ++i) {
-    const bool empty = count[i] <= .5f;
-    if (!in_gap) {
-      if (empty) {
-        in_gap = true; zero_pos = i; cnt = 1;
-        first = i == 0;
-        if (!first) left = psd[i - 1];
-      }
-    } else if (empty) {
-      ++cnt;
+  const unsigned seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned i0 = seg * SVIEW_SEG;
+  if (i0 >= spectrum_size) return;
+  const unsigned i1 = i0 + SVIEW_SEG < spectrum_size ? i0 + SVIEW_SEG : spectrum_size;
+  for (unsigned i = i0; i < i1; ++i) {
+    if (!(count[i] <= .5f)) continue;
+    if (i > 0 && count[i - 1] <= .5f) continue;           // not the first bin of its gap
+    const unsigned zero_pos = i;
+    const bool first = i == 0;
+    const float left = first ? -200.0f : psd[i - 1];
+    unsigned e = i;
+    while (e < spectrum_size && count[e] <= .5f) ++e;     // e = first non-empty bin after the gap (or the end)
+    const unsigned cnt = e - zero_pos;
+    if (e == spectrum_size) {
+      for (unsigned j = 0; j < cnt; ++j) psd[j + zero_pos] = left;
     } else {
-      in_gap = false;
-      right = psd[i];
+      const float right = psd[e];
       if (first) {
-        for (j = 0; j < cnt; ++j) psd[j + zero_pos] = right;
+        for (unsigned j = 0; j < cnt; ++j) psd[j + zero_pos] = right;
       } else {
-        for (j = 0; j < cnt; ++j) {
-          t = (float) (j + .5f) / cnt;
+        for (unsigned j = 0; j < cnt; ++j) {
+          const float t = (float) (j + .5f) / cnt;
           psd[j + zero_pos] = (1 - t) * left + t * right;
         }
       }
     }
   }
-  if (in_gap)
-    for (j = 0; j < cnt; ++j) psd[j + zero_pos] = left;
 }
 
 cudaError_t sdb_launch_sview_project(cudaStream_t s, double freq_min, double freq_range, double fft_bandwidth,
@@ -261,7 +261,7 @@ cudaError_t sdb_launch_sview_accumulate(cudaStream_t s, unsigned spectrum_size, 
     k_sview_accumulate<<<(spectrum_size + 255) / 256, 256, 0, s>>>(spectrum_size, j0, nb, va, vc, n_hops, max_bins,
                                                                    psd, accum, count, count_snapshot);
   }
-  k_sview_fill<<<1, 32, 0, s>>>(spectrum_size, psd, count);
+  k_sview_fill<<<((spectrum_size + SVIEW_SEG - 1) / SVIEW_SEG + 127) / 128, 128, 0, s>>>(spectrum_size, psd, count);
   return cudaGetLastError();
 }
 

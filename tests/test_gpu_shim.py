@@ -107,5 +107,5 @@ def test_analyzer_session_through_the_suscan_names(tu, oracle):
     hops = per_block // (N // 2)
     skip = (hops - 1) * 128 + hops * 128           # channel samples of blocks 2 and 3 (halfsz = 128)
     rs = oracle.inspector_run(ic, chan[skip:])
-    rh = oracle.decide(rs, 0, 2, -np.pi, np.pi)
+    rh = oracle.decide(rs, "argument", 2, -np.pi, np.pi)
     parity.assert_symbols_match(soft[:got], hard[:got], rs, rh, exact_soft=True)
