@@ -704,6 +704,9 @@ def run_cuda(args):
         sdb.stage_cycles(reset=True)
         step_dev(); e.sync()
         roofline["inspector_role_cycles_per_sample"] = {k_: round(v_, 1) for k_, v_ in sdb.stage_cycles(reset=True).items()}
+        sdb.cta_cycles(reset=True)
+        step_dev(); e.sync()
+        roofline["inspector_cta_by_class"] = sdb.cta_cycles(reset=True)
     wps, frames = H, H // 2
 
     # ---- end to end: pinned host IQ -> H2D -> path -> D2H of PSD frames and symbols, every step
@@ -714,8 +717,12 @@ def run_cuda(args):
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
     psd_h = [pin((S, frames, N_FFT), torch.float32) for _ in range(2)]
     cnt_h = [pin((S * K,), torch.int32).view(np.uint32) for _ in range(2)]
-    soft_h = [pin((S * K, cap), torch.complex64) for _ in range(2)]
-    hard_h = [pin((S * K, cap), torch.uint8) for _ in range(2)]
+    # symbols come back packed (sdb_engine_read_symbols_packed_async: chain after chain, written by the GPU straight
+    # into these pinned buffers), so PCIe carries the symbols that exist, not the [chains][cap] array they sit in
+    cap_total = S * K * ((cap + 15) // 16 * 16)
+    off_h = [pin((S * K + 1,), torch.int64).view(np.uint64) for _ in range(2)]
+    soft_h = [pin((cap_total,), torch.complex64) for _ in range(2)]
+    hard_h = [pin((cap_total,), torch.uint8) for _ in range(2)]
     e.sync()
 
     def run_e2e(eng, host_ptr, stride):
@@ -726,7 +733,7 @@ def run_cuda(args):
             step_no[0] += 1
             eng.feed_host_ptr(host_ptr, stride, n)
             eng.read_psd_async(psd_h[b])
-            eng.read_all_symbols_async(cnt_h[b], soft_h[b], hard_h[b], cap)
+            eng.read_symbols_packed_async(cnt_h[b], off_h[b], soft_h[b], hard_h[b], cap_total)
 
         for _ in range(3):
             step_e2e()
@@ -745,7 +752,8 @@ def run_cuda(args):
 
     e2e_v = run_e2e(e, xh.data_ptr(), xh.stride(0))
     h2d = samples_step * 8
-    d2h = psd_h[0].nbytes + cnt_h[0].nbytes + soft_h[0].nbytes + hard_h[0].nbytes
+    sym_extent = int(off_h[(args.steps + 3 - 1) & 1][-1])            # symbols (with alignment gaps) of the last step
+    d2h = psd_h[0].nbytes + cnt_h[0].nbytes + off_h[0].nbytes + sym_extent * 9
 
     # ---- the same end-to-end loop with the IQ in native SDR sample formats (converted inside the first load):
     # 4 and 2 bytes per complex sample over PCIe instead of 8.  Extra information; `e2e` above is float32.

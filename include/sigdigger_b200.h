@@ -176,6 +176,18 @@ int          sdb_engine_read_all_symbols(sdb_engine_t *e, uint32_t *counts, sdb_
 int          sdb_engine_read_psd_async(sdb_engine_t *e, float *dst, size_t cap_floats);
 int          sdb_engine_read_all_symbols_async(sdb_engine_t *e, uint32_t *counts, sdb_complex *soft,
                                                uint8_t *hard, size_t cap);
+/* Packed read of the last feed's symbols (the batch counterpart of suscan's per-inspector SAMPLES messages,
+ * Suscan/Messages/SamplesMessage.cpp): chain c = stream * n_channels + channel has counts[c] symbols at
+ * soft[offsets[c] ...] / hard[offsets[c] ...]; every start is a multiple of 16 symbols (the gap is zero-filled) and
+ * offsets[chains] is the total extent.  A chain whose row would pass cap_total is skipped (offsets[chains] >
+ * cap_total tells).  The GPU writes soft / hard directly: they must be 16-byte-aligned PINNED host memory
+ * (cudaHostAlloc / cudaHostRegister) or device memory, anything else is refused; counts and offsets (chains and
+ * chains + 1 entries) are ordinary async copies.  PCIe carries ~9 bytes per symbol instead of 9 bytes per channel
+ * sample. */
+int          sdb_engine_read_symbols_packed_async(sdb_engine_t *e, uint32_t *counts, uint64_t *offsets,
+                                                  sdb_complex *soft, uint8_t *hard, size_t cap_total);
+int          sdb_engine_read_symbols_packed(sdb_engine_t *e, uint32_t *counts, uint64_t *offsets,
+                                            sdb_complex *soft, uint8_t *hard, size_t cap_total);
 /* ---- inspector spectrum sources and parameter estimators (SPEC.md section U) ----
  * suscan_analyzer_inspector_set_spectrum_async(analyzer, handle, spectsrc_id, req_id) (Suscan/Analyzer.cpp:539-548)
  * and suscan_analyzer_inspector_estimator_cmd_async(analyzer, handle, estimator_id, enabled, req_id)
@@ -248,6 +260,11 @@ void     sdb_engine_timing(sdb_engine_t *e, int enable);
 /* inspector-kernel stage balance since the last reset: out[0..3] = busy SM cycles of the gain / carrier /
  * filter / clock stage warps summed over CTAs, out[4] = chunk-samples processed (profiling aid) */
 int      sdb_debug_stage_cycles(uint64_t out[8], int reset);
+/* instrumented twin only (zeros otherwise), per inspector class c = 0..4 (SDB_INSP_*): out[c] = sum of CTA lifetimes
+ * in SM cycles, out[5 + c] = CTAs, out[10 + c] = longest CTA, out[15 + c] = latest CTA end and out[20] = earliest CTA
+ * start (ns, global timer); out[24 + 8 c + r] = busy cycles of role r (0 track, 1 carrier, 2 filter, 3 clock,
+ * 5 pre, 6 post) and [24 + 8 c + 4] = chunk samples, in CTAs of class c */
+int      sdb_debug_cta_cycles(uint64_t out[64], int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * Offline Tasks/ primitives over a whole capture buffer (host pointers; one GPU chain each; the

@@ -276,6 +276,10 @@ _PROTOS = {
     "sdb_engine_read_all_symbols": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_read_psd_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_engine_read_all_symbols_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_engine_read_symbols_packed_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                       C.c_size_t]),
+    "sdb_engine_read_symbols_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_size_t]),
     "sdb_engine_symbol_counts_device": (C.c_void_p, [C.c_void_p]),
     "sdb_engine_symbol_capacity": (C.c_size_t, [C.c_void_p]),
     "sdb_spectsrc_name": (C.c_char_p, [C.c_int]),
@@ -299,6 +303,7 @@ _PROTOS = {
     "sdb_engine_kernel_time": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "sdb_engine_timing": (None, [C.c_void_p, C.c_int]),
     "sdb_debug_stage_cycles": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
+    "sdb_debug_cta_cycles": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "sdb_task_carrier_xlate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_float]),
     "sdb_task_quad_demod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sdb_task_costas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_float]),
@@ -438,6 +443,24 @@ def stage_cycles(reset=False):
     n = max(1, buf[4])
     return {"track": buf[0] / n, "pre": buf[5] / n, "post": buf[6] / n, "carrier": buf[1] / n, "filter": buf[2] / n,
             "clock": buf[3] / n, "chunk_samples": int(buf[4])}
+
+
+def cta_cycles(reset=False):
+    """Inspector CTAs by class since the last reset (instrumented library only): mean / longest lifetime in SM cycles
+    and the time of the class's last CTA end after the kernel's first CTA start (ns)."""
+    buf = (C.c_uint64 * 64)()
+    _check(load_library().sdb_debug_cta_cycles(buf, int(reset)))
+    names = ["psk", "fsk", "ask", "audio", "raw"]
+    out = {}
+    for c in range(5):
+        if buf[5 + c]:
+            out[names[c]] = {"ctas": int(buf[5 + c]), "mean_cycles": buf[c] / buf[5 + c], "max_cycles": int(buf[10 + c]),
+                             "last_end_ns": int(buf[15 + c]) - int(buf[20])}
+            r, ns = buf[24 + 8 * c:32 + 8 * c], max(1, buf[24 + 8 * c + 4])
+            out[names[c]]["role_cycles_per_sample"] = {"track": round(r[0] / ns, 1), "pre": round(r[5] / ns, 1),
+                                                       "post": round(r[6] / ns, 1), "carrier": round(r[1] / ns, 1),
+                                                       "filter": round(r[2] / ns, 1), "clock": round(r[3] / ns, 1)}
+    return out
 
 
 def _check(rc):
@@ -596,6 +619,17 @@ class Engine:
         _check(self._L.sdb_engine_read_all_symbols_async(self._h, counts.ctypes.data,
                                                          soft.ctypes.data if soft is not None else None,
                                                          hard.ctypes.data if hard is not None else None, cap))
+
+    def read_symbols_packed_async(self, counts, offsets, soft, hard, cap_total):
+        """soft / hard: pinned host arrays (or device pointers as ints); the GPU writes them directly"""
+        ptr = lambda a: None if a is None else (a if isinstance(a, int) else a.ctypes.data)
+        _check(self._L.sdb_engine_read_symbols_packed_async(self._h, counts.ctypes.data, offsets.ctypes.data,
+                                                            ptr(soft), ptr(hard), cap_total))
+
+    def read_symbols_packed(self, counts, offsets, soft, hard, cap_total):
+        ptr = lambda a: None if a is None else (a if isinstance(a, int) else a.ctypes.data)
+        _check(self._L.sdb_engine_read_symbols_packed(self._h, counts.ctypes.data, offsets.ctypes.data,
+                                                      ptr(soft), ptr(hard), cap_total))
 
     def read_all_symbols(self, counts, soft, hard, cap):
         _check(self._L.sdb_engine_read_all_symbols(self._h, counts.ctypes.data,

@@ -29,11 +29,14 @@
 //   2     0      track     AGC delay line swap, peak tracker, fast / slow levels (recurrence)     in place
 //   3     3-4    post      gain 10^(level (slope - 1) / 20) x delayed sample; for ask + PLL also
 //                          the phase detector's atan2 of the sample (feed-forward)               ringA[2], ang[2]
-//   4     5      carrier   Costas | PLL + component | FSK discriminator | audio demod (recurrence) ringB (circular)
-//   5     6-9    filter    matched filter: 4 outputs per warp straight off ringB (its history IS
+//   4     5      carrier   Costas | FSK discriminator | audio demod | ask: the PLL's phase / frequency
+//                          recurrence only (recurrence)                                          ringB (circular), phs[2]
+//   5     6-9    demod     ask: exp(-i phase), mix, component (|.| / I / Q), in place in ringB -- feed-forward
+//                          once the phases are known (4 samples per warp)                        ringB
+//   6     6-9    filter    matched filter: 4 outputs per warp straight off ringB (its history IS
 //                          the filter line), one FFMA2 per complex sample x tap; audio LPF (IIR, 1 warp) ringC[2]
-//   6     10     clock     Gardner | sampler | resampler, CMA (recurrence)                       sym[2], cnt[2]
-//   7     11     out       x0.75, decision (atan2 / modulus quantiser), symbol stores            global
+//   7     10     clock     Gardner | sampler | resampler, CMA (recurrence)                       sym[2], cnt[2]
+//   8     11     out       x0.75, decision (atan2 / modulus quantiser), symbol stores            global
 //
 // Round 1 ran four stage-warps per CTA (8 warps per SM: issue slots 10 % busy, half of all stall samples on
 // the barrier behind the slowest stage, profiles/r01_inspector_stages.md); the feed-forward work (two logarithm /
@@ -46,20 +49,45 @@
 // six cycles per instruction whatever the mapping, so this kernel keeps its loops rolled and its code small (84 KB).
 #define CH 16
 enum { W_TRACK = 0, W_PRE = 1, W_POST = 3, W_CARRIER = 5, W_MF = 6, W_CLOCK = 10, W_OUT = 11, INSP_WARPS = 12 };
-#define INSP_STEPS 7          // pipeline depth after the load: a chunk loaded in iteration c leaves in iteration c + 7
+#define INSP_STEPS 8          // pipeline depth after the load: a chunk loaded in iteration c leaves in iteration c + 8
 
 #ifdef SDB_STAGE_CYCLES
 __device__ unsigned long long g_stage_cycles[8];
 #define ROLE_T_DECL long long busy_ = 0
 #define ROLE_T0 const long long t0_ = clock64()
 #define ROLE_T1 busy_ += clock64() - t0_
-#define ROLE_T_END(slot) do { if (c.lane == 0) atomicAdd(&g_stage_cycles[slot], (unsigned long long) busy_); } while (0)
+__device__ unsigned long long g_role_cls[5][8];      // the same, by inspector class of the CTA
+#define ROLE_T_END(slot) do { if (c.lane == 0) { atomicAdd(&g_stage_cycles[slot], (unsigned long long) busy_); \
+  if (c.cls >= 0 && c.cls < 5) atomicAdd(&g_role_cls[c.cls][slot], (unsigned long long) busy_); } } while (0)
 #else
 #define ROLE_T_DECL
 #define ROLE_T0
 #define ROLE_T1
 #define ROLE_T_END(slot)
 #endif
+// instrumented twin only: per inspector class c = 0..4: [c] sum of CTA lifetimes (cycles), [5 + c] CTAs,
+// [10 + c] longest CTA (cycles), [15 + c] latest CTA end (ns, globaltimer), [20] earliest CTA start (ns)
+#ifdef SDB_STAGE_CYCLES
+__device__ unsigned long long g_cta_cycles[24];
+#endif
+cudaError_t sdb_stage_cta_cycles(unsigned long long out[64], int reset)
+{
+#ifdef SDB_STAGE_CYCLES
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_cta_cycles, sizeof(unsigned long long) * 24);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out + 24, g_role_cls, sizeof(unsigned long long) * 40);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[40] = { 0 };
+    e = cudaMemcpyToSymbol(g_role_cls, z, sizeof(z));
+    z[20] = ~0ull;
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_cta_cycles, z, sizeof(unsigned long long) * 24);
+  }
+  return e;
+#else
+  (void) reset;
+  for (int i = 0; i < 64; ++i) out[i] = 0;
+  return cudaSuccess;
+#endif
+}
 cudaError_t sdb_stage_cycles(unsigned long long out[8], int reset)
 {
 #ifdef SDB_STAGE_CYCLES
@@ -97,6 +125,7 @@ struct ChainSmem {
   float2 ringC[2][CH][32];
   float2 sym[2][CH][32];
   float  ang[2][CH][32];
+  float  phs[2][CH][32];
   int    cnt[2][32];
 };
 
@@ -233,7 +262,10 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
   }
   ROLE_T_END(0);
 #ifdef SDB_STAGE_CYCLES
-  if (lane == 0) atomicAdd(&g_stage_cycles[4], (unsigned long long) c.nchunks * CH);
+  if (lane == 0) {
+    atomicAdd(&g_stage_cycles[4], (unsigned long long) c.nchunks * CH);
+    if (c.cls >= 0 && c.cls < 5) atomicAdd(&g_role_cls[c.cls][4], (unsigned long long) c.nchunks * CH);
+  }
 #endif
   if (have_agc) {
     stp->fast_level = as.fast; stp->slow_level = as.slow; stp->peak = as.peak;
@@ -392,10 +424,18 @@ static __device__ void role_carrier(const ICtx &c)
           if (quad) { y.x = d_atan2f(di, dr) * 0.318309886183790671538f; y.y = 0.0f; }
           else { y.x = dr * rot_re - di * rot_im; y.y = dr * rot_im + di * rot_re; }
         } else if (cls == SDB_INSP_ASK) {
-          if (have_pll) y = pll_step_ang(pll_a, pll_b, p_phi, p_omega, y, sm.ang[ckk & 1][i][lane]);
-          if (ask_ch == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
-          else if (ask_ch == 1) { y.y = 0.0f; }
-          else                  { y.x = y.y; y.y = 0.0f; }
+          // Only (phi, omega) is a recurrence: phi <- wrap(phi + omega); err = wrap(ang - phi); omega += alpha err;
+          // phi <- wrap(phi + beta err) -- pll_step statement by statement.  The oscillator read exp(i phi), the mix
+          // and the component selection need this sample's phase only and run in the demod step (role_filter).
+          if (have_pll) {
+            sm.phs[ckk & 1][i][lane] = p_phi;
+            p_phi = wrap_once(p_phi + p_omega);
+            float err = sm.ang[ckk & 1][i][lane] - p_phi;
+            if (err > PI_F) err = err - TWOPI_F;
+            else if (err < -PI_F) err = err + TWOPI_F;
+            p_omega = p_omega + pll_a * err;
+            p_phi = wrap_once(p_phi + pll_b * err);
+          }
         } else if (cls == SDB_INSP_AUDIO) {
           float v = 0.0f;
           float p = y.x * y.x + y.y * y.y;
@@ -447,7 +487,7 @@ static __device__ void role_filter(const ICtx &c, int part, const float *taps_po
   const SdbChainCfg *cp = c.cp; SdbChainState *stp = c.stp;
   const int have_mf = c.valid ? cp->have_mf : 0, mf_n = c.valid ? cp->mf_n : 0;
   const int alpf_n = (c.valid && c.cls == SDB_INSP_AUDIO) ? cp->alpf_n : 0;
-  const bool mf_ring = have_mf && (unsigned) (mf_n - 1 + 2 * CH) <= c.rb_mask + 1u;
+  const bool mf_ring = have_mf && (unsigned) (mf_n - 1 + 3 * CH) <= c.rb_mask + 1u;
   const bool mf_global = have_mf && !mf_ring;
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
   float al_b[SDB_MAX_IIR], al_a[SDB_MAX_IIR], al_x[SDB_MAX_IIR], al_xi[SDB_MAX_IIR], al_y[SDB_MAX_IIR], al_yi[SDB_MAX_IIR];
@@ -473,11 +513,36 @@ static __device__ void role_filter(const ICtx &c, int part, const float *taps_po
       if (c.fresh) for (int i = 0; i < 2 * mf_n; ++i) mfl[i * 32] = 0.0f;
     }
   }
+  const bool ask = c.valid && c.cls == SDB_INSP_ASK;
+  const bool ask_pll = ask && cp->have_pll;
+  const int ask_ch = ask ? cp->ask_channel : 0;
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
-    if (it >= 5 && it - 5 < c.nchunks) {
+    // ---- step 5, ask only: finish the carrier stage of chunk it - 5 in place (4 samples per warp)
+    if (ask && it >= 5 && it - 5 < c.nchunks) {
       const uint32_t ck = it - 5, base = ck * CH;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = part * 4 + j;
+        const uint32_t p = base + (uint32_t) i;
+        if (p < n) {
+          float2 y = c.rb[p & c.rb_mask][lane];
+          if (ask_pll) {
+            float sn, cs;
+            d_sincosf(sm.phs[ck & 1][i][lane], &sn, &cs);            // the NCQO read of pll_step
+            y = make_float2(y.x * cs + y.y * sn, y.y * cs - y.x * sn);
+          }
+          if (ask_ch == 0)      { y.x = d_cabsf(y.x, y.y); y.y = 0.0f; }
+          else if (ask_ch == 1) { y.y = 0.0f; }
+          else                  { y.x = y.y; y.y = 0.0f; }
+          c.rb[p & c.rb_mask][lane] = y;
+        }
+      }
+    }
+    // ---- step 6: filter chunk it - 6
+    if (it >= 6 && it - 6 < c.nchunks) {
+      const uint32_t ck = it - 6, base = ck * CH;
       float2 (*out)[32] = sm.ringC[ck & 1];
       if (mf_ring) {
         const uint32_t p0 = base + (uint32_t) part * 4u;
@@ -582,8 +647,8 @@ static __device__ void role_clock(const ICtx &c)
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
-    if (it >= 6 && it - 6 < c.nchunks) {
-      const uint32_t ck = it - 6, base = ck * CH;
+    if (it >= 7 && it - 7 < c.nchunks) {
+      const uint32_t ck = it - 7, base = ck * CH;
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       float2 (*in)[32] = sm.ringC[ck & 1];
       float2 (*sy)[32] = sm.sym[ck & 1];
@@ -641,8 +706,8 @@ static __device__ void role_out(const ICtx &c, float2 *__restrict__ so, unsigned
   uint32_t nout = 0;
   const uint32_t total = c.nchunks + INSP_STEPS;
   for (uint32_t it = 0; it <= total; ++it) {
-    if (it >= 7 && it - 7 < c.nchunks) {
-      const uint32_t ck = it - 7;
+    if (it >= 8 && it - 8 < c.nchunks) {
+      const uint32_t ck = it - 8;
       const int k = c.valid ? sm.cnt[ck & 1][lane] : 0;
       float2 (*sy)[32] = sm.sym[ck & 1];
       for (int j = 0; j < k; ++j) {
@@ -704,6 +769,11 @@ __global__ void __launch_bounds__(INSP_WARPS * 32, 2) k_inspectors(const SdbChai
   if (warp == 0) atomicMax(&s_nmax, c.n);
   __syncthreads();
   c.nchunks = (s_nmax + CH - 1) / CH;
+#ifdef SDB_STAGE_CYCLES
+  const long long cta_t0 = clock64();
+  unsigned long long cta_ns0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_ns0));
+#endif
 
   if (warp == W_TRACK) {
     role_track(c, valid ? chan_in + (size_t) s * chan_stream_stride + chans[k].out_off : nullptr);
@@ -720,6 +790,19 @@ __global__ void __launch_bounds__(INSP_WARPS * 32, 2) k_inspectors(const SdbChai
   } else {
     role_out(c, soft + (size_t) chain * sym_cap, hard + (size_t) chain * sym_cap, sym_counts + chain, sym_cap);
   }
+#ifdef SDB_STAGE_CYCLES
+  __syncthreads();
+  if (threadIdx.x == 0 && c.cls >= 0 && c.cls < 5) {
+    const unsigned long long el = (unsigned long long) (clock64() - cta_t0);
+    unsigned long long ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    atomicAdd(&g_cta_cycles[c.cls], el);
+    atomicAdd(&g_cta_cycles[5 + c.cls], 1ull);
+    atomicMax(&g_cta_cycles[10 + c.cls], el);
+    atomicMax(&g_cta_cycles[15 + c.cls], ns1);
+    atomicMin(&g_cta_cycles[20], cta_ns0);
+  }
+#endif
 }
 
 size_t sdb_inspector_smem_bytes(const SdbInspDyn &dyn)

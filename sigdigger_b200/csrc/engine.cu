@@ -79,7 +79,7 @@ struct sdb_engine {
   int *d_binmap = nullptr; int n_bins = 0; unsigned ka_mask = 0;
   float2 *d_cspec = nullptr; size_t max_hops = 0;
   std::vector<SdbChannelDev> h_chans; SdbChannelDev *d_chans = nullptr;
-  struct Group { int size; int len; int *d_ids; };
+  struct Group { int size; int len; int *d_ids; int any_precise; };
   std::vector<Group> groups;
   float2 *d_tails = nullptr; size_t tail_stride = 0;
   float *d_lo_phase = nullptr;
@@ -100,6 +100,7 @@ struct sdb_engine {
   float *d_psdb[2] = { nullptr, nullptr };
   float2 *d_softb[2] = { nullptr, nullptr }; uint8_t *d_hardb[2] = { nullptr, nullptr };
   uint32_t *d_countsb[2] = { nullptr, nullptr };
+  unsigned long long *d_sym_off[2] = { nullptr, nullptr };   // packed read-out: start of every chain, 16-symbol aligned
   float2 *d_xinb[2] = { nullptr, nullptr };
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_psd_ready[2] = { nullptr, nullptr }, ev_psd_read[2] = { nullptr, nullptr },
@@ -691,7 +692,8 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
     CK(cudaMemset(e->d_tails, 0, (size_t) S * tail_off * sizeof(float2)));
     CK(cudaMemset(e->d_lo_phase, 0, (size_t) S * K * sizeof(float)));
     for (auto &kv : by_size) {
-      sdb_engine::Group g; g.size = kv.first; g.len = (int) kv.second.size();
+      sdb_engine::Group g; g.size = kv.first; g.len = (int) kv.second.size(); g.any_precise = 0;
+      for (int id : kv.second) if (e->h_chans[id].precise) g.any_precise = 1;
       g.d_ids = e->dalloc<int>(kv.second.size());
       if (!g.d_ids) return fail("out of device memory");
       CK(cudaMemcpy(g.d_ids, kv.second.data(), kv.second.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -962,7 +964,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
       for (auto &g : e->groups)
         CK(sdb_launch_chan_ifft_group(ctx, e->d_chans, g.d_ids, g.len, g.size, K, (int) S, e->d_cspec,
                                       e->n_bins, wps, e->d_tails, e->tail_stride, e->d_lo_phase, e->d_chanb[b],
-                                      e->chan_stride));
+                                      e->chan_stride, g.any_precise));
       e->span_end();
       CK(cudaEventRecord(e->ev_chan[b], e->stream));
       CK(cudaStreamWaitEvent(e->insp_stream, e->ev_chan[b], 0));
@@ -1158,6 +1160,54 @@ extern "C" int sdb_engine_read_all_symbols_async(sdb_engine_t *e, uint32_t *coun
   return 0;
 }
 
+// destination of a device-written read: device memory as is, pinned / registered host memory through its device
+// alias; anything else cannot be written by a kernel and is refused
+static int device_writable(void *p, void **dev, const char *what)
+{
+  *dev = nullptr;
+  if (!p) return 0;
+  if (((uintptr_t) p & 15u) != 0) return fail(std::string("packed symbol read: ") + what + " must be 16-byte aligned");
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return fail(std::string("packed symbol read: ") + what + " is not pinned host or device memory"); }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { *dev = p; return 0; }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) { *dev = at.devicePointer; return 0; }
+  return fail(std::string("packed symbol read: ") + what + " must be pinned (cudaHostAlloc / cudaHostRegister) host "
+              "memory or device memory: the GPU writes it directly");
+}
+
+extern "C" int sdb_engine_read_symbols_packed_async(sdb_engine_t *e, uint32_t *counts, uint64_t *offsets,
+                                                    sdb_complex *soft, uint8_t *hard, size_t cap_total)
+{
+  if (!e || !counts || !offsets) return fail("null argument");
+  const size_t chains = (size_t) e->prm.n_streams * e->channels.size();
+  if (chains == 0) return 0;
+  if (e->feed_index == 0) return fail("no symbols available");
+  const int ob = (int) ((e->feed_index - 1) & 1u);
+  CK(cudaSetDevice(e->prm.device));
+  void *dsoft = nullptr, *dhard = nullptr;
+  if (device_writable(soft, &dsoft, "soft") || device_writable(hard, &dhard, "hard")) return -1;
+  if (!e->d_sym_off[ob]) {
+    e->d_sym_off[ob] = e->dalloc<unsigned long long>(chains + 1);
+    if (!e->d_sym_off[ob]) return fail("out of device memory (symbol offsets)");
+  }
+  if (e->ev_insp_valid[ob]) CK(cudaStreamWaitEvent(e->d2h_stream, e->ev_insp[ob], 0));
+  CK(sdb_launch_sym_pack(e->d2h_stream, e->d_countsb[ob], e->d_sym_off[ob], chains, e->d_softb[ob], e->d_hardb[ob],
+                         e->sym_cap, dsoft, dhard, (unsigned long long) cap_total, &e->launches));
+  CK(cudaMemcpyAsync(counts, e->d_countsb[ob], chains * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->d2h_stream));
+  CK(cudaMemcpyAsync(offsets, e->d_sym_off[ob], (chains + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->d2h_stream));
+  CK(cudaEventRecord(e->ev_sym_read[ob], e->d2h_stream));
+  e->sym_read_valid[ob] = true;
+  return 0;
+}
+
+extern "C" int sdb_engine_read_symbols_packed(sdb_engine_t *e, uint32_t *counts, uint64_t *offsets, sdb_complex *soft,
+                                              uint8_t *hard, size_t cap_total)
+{
+  if (sdb_engine_read_symbols_packed_async(e, counts, offsets, soft, hard, cap_total)) return -1;
+  CK(cudaStreamSynchronize(e->d2h_stream));
+  return 0;
+}
+
 extern "C" const uint32_t *sdb_engine_symbol_counts_device(const sdb_engine_t *e) { return e ? e->d_counts : nullptr; }
 extern "C" size_t sdb_engine_symbol_capacity(const sdb_engine_t *e) { return e ? e->sym_cap : 0; }
 extern "C" void *sdb_engine_stream(const sdb_engine_t *e) { return e ? (void *) e->stream : nullptr; }
@@ -1175,6 +1225,16 @@ extern "C" int sdb_debug_stage_cycles(uint64_t out[8], int reset)
   CK(cudaDeviceSynchronize());
   CK(sdb_stage_cycles(tmp, reset));
   for (int i = 0; i < 8; ++i) out[i] = tmp[i];
+  return 0;
+}
+
+cudaError_t sdb_stage_cta_cycles(unsigned long long out[64], int reset);
+extern "C" int sdb_debug_cta_cycles(uint64_t out[64], int reset)
+{
+  unsigned long long tmp[64];
+  CK(cudaDeviceSynchronize());
+  CK(sdb_stage_cta_cycles(tmp, reset));
+  for (int i = 0; i < 64; ++i) out[i] = tmp[i];
   return 0;
 }
 

@@ -20,6 +20,7 @@
 #include "sdb_internal.h"
 #include "../../include/sigdigger_b200.h"
 #include "sdb_math.h"
+#include "sdb_cpx.h"
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -66,25 +67,28 @@ static __device__ __forceinline__ void block_fft_inplace(float2 *s, const int M,
       const int j = lane + b * nthr;
       if (j < q) {
         const int k = j & (Ns - 1);
+        // packed FP32x2 arithmetic (sdb_cpx.h): the same IEEE operations per component as the scalar statement of
+        // SPEC F.1 / F.2 (a complex add is one FADD2, the twiddle product one FMUL2 + one FFMA2), so the results
+        // are bit-identical and the butterfly issues ~14 instead of ~34 arithmetic instructions
         if (logNs > 0) {
           const int step = M >> (logNs + 2);
           float2 w1 = ldtw(tw, k * step), w2 = ldtw(tw, 2 * k * step), w3 = ldtw(tw, 3 * k * step);
           if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-          v[b][1] = cmul(v[b][1], w1);
-          v[b][2] = cmul(v[b][2], w2);
-          v[b][3] = cmul(v[b][3], w3);
+          v[b][1] = cmulf(v[b][1], w1);
+          v[b][2] = cmulf(v[b][2], w2);
+          v[b][3] = cmulf(v[b][3], w3);
         }
-        const float2 a = make_float2(v[b][0].x + v[b][2].x, v[b][0].y + v[b][2].y);
-        const float2 bb = make_float2(v[b][0].x - v[b][2].x, v[b][0].y - v[b][2].y);
-        const float2 c = make_float2(v[b][1].x + v[b][3].x, v[b][1].y + v[b][3].y);
-        const float2 dd = make_float2(v[b][1].x - v[b][3].x, v[b][1].y - v[b][3].y);
+        const float2 a = cadd(v[b][0], v[b][2]);
+        const float2 bb = csub(v[b][0], v[b][2]);
+        const float2 c = cadd(v[b][1], v[b][3]);
+        const float2 dd = csub(v[b][1], v[b][3]);
         // forward: d = -i * dd ; inverse: d = +i * dd
         const float2 d = DIR < 0 ? make_float2(dd.y, -dd.x) : make_float2(-dd.y, dd.x);
         const int j0 = ((j - k) << 2) + k;
-        s[j0]          = make_float2(a.x + c.x, a.y + c.y);
-        s[j0 + Ns]     = make_float2(bb.x + d.x, bb.y + d.y);
-        s[j0 + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
-        s[j0 + 3 * Ns] = make_float2(bb.x - d.x, bb.y - d.y);
+        s[j0]          = cadd(a, c);
+        s[j0 + Ns]     = cadd(bb, d);
+        s[j0 + 2 * Ns] = csub(a, c);
+        s[j0 + 3 * Ns] = csub(bb, d);
       }
     }
     __syncthreads();
@@ -97,9 +101,9 @@ static __device__ __forceinline__ void block_fft_inplace(float2 *s, const int M,
       if (j < h) {
         float2 w = ldtw(tw, j);
         if (DIR > 0) w.y = -w.y;
-        const float2 a = s[j], t = cmul(s[j + h], w);
-        s[j]     = make_float2(a.x + t.x, a.y + t.y);
-        s[j + h] = make_float2(a.x - t.x, a.y - t.y);
+        const float2 a = s[j], t = cmulf(s[j + h], w);
+        s[j]     = cadd(a, t);
+        s[j + h] = csub(a, t);
       }
     }
     __syncthreads();
@@ -580,14 +584,228 @@ __global__ void __launch_bounds__(1024) k_chan_ifft(const SdbChannelDev *__restr
   if (ch.precise && tid == 0) lo_phase[(size_t) s * n_channels + ci] = lo_phi;
 }
 
+// ---------------------------------------------------------------------------------------------
+// channeliser inverse side, sizes 512 ... 4096: the same Stockham radix-4 dataflow (SPEC F.2: levels Ns = 1, 4, 16 ...
+// then one radix-2 level when log2(size) is odd, butterflies and twiddle products statement for statement those of
+// block_fft_inplace, hence bit-identical), but TWO levels per trip through shared memory: a thread owns 16 points,
+// runs the four level-Ns butterflies that feed the four level-4Ns butterflies in registers and writes their 16
+// results.  size/16 threads per hop (1024 points: two warps), synchronised with a named barrier of their own, so a
+// 256-thread CTA transforms 256/(size/16) hops side by side and only the cross-fade -- which needs the left
+// neighbour's second half -- pays a CTA-wide barrier.  Against the one-level kernel above (1024-point channels):
+// 3 trips instead of 5, 6 two-warp barriers instead of 10 eight-warp ones, a quarter of the index arithmetic.
+// The buffers carry one float2 of padding per 16 (PADI): every access pattern of the three kinds of trip is then
+// conflict-free per half-warp.
+// ---------------------------------------------------------------------------------------------
+#define PADI(i) ((i) + ((i) >> 4))
+
+template <int DIR>
+static __device__ __forceinline__ void r4_core(float2 &x0, float2 &x1, float2 &x2, float2 &x3)
+{
+  const float2 a = cadd(x0, x2), bb = csub(x0, x2), c = cadd(x1, x3), dd = csub(x1, x3);
+  const float2 d = DIR < 0 ? make_float2(dd.y, -dd.x) : make_float2(-dd.y, dd.x);
+  x0 = cadd(a, c); x1 = cadd(bb, d); x2 = csub(a, c); x3 = csub(bb, d);
+}
+template <int DIR>
+static __device__ __forceinline__ float2 twd(const float2 *__restrict__ tw, int i)
+{
+  float2 w = __ldg(tw + i);
+  if (DIR > 0) w.y = -w.y;
+  return w;
+}
+static __device__ __forceinline__ void group_sync(int bar_id, int per)
+{
+  if (per <= 32) __syncwarp();
+  else asm volatile("barrier.sync %0, %1;" :: "r"(bar_id), "r"(per) : "memory");
+}
+
+// s: padded buffer of M points; jb = 0 .. M/16-1 (the `per` = M/16 threads of one group); M >= 16
+template <int DIR>
+static __device__ __forceinline__ void group_fft16(float2 *s, const int M, const int logM, const int jb,
+                                                   const int per, const int bar_id,
+                                                   const float2 *__restrict__ tw)
+{
+  const int q = M >> 2, e = M >> 4;
+  float2 v[4][4];                                      // v[u][t] = s[jb + u e + t q]
+  int logNs = 0;
+  for (; logNs + 4 <= logM; logNs += 4) {
+    const int Ns = 1 << logNs, k = jb & (Ns - 1);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[u][t] = s[PADI(jb + u * e + t * q)];
+    group_sync(bar_id, per);
+    // level Ns: butterflies j = jb + u e, all with the same k (e is a multiple of Ns)
+    if (logNs > 0) {
+      const int step = M >> (logNs + 2);
+      const float2 w1 = twd<DIR>(tw, k * step), w2 = twd<DIR>(tw, 2 * k * step), w3 = twd<DIR>(tw, 3 * k * step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u][1] = cmulf(v[u][1], w1); v[u][2] = cmulf(v[u][2], w2); v[u][3] = cmulf(v[u][3], w3);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r4_core<DIR>(v[u][0], v[u][1], v[u][2], v[u][3]);
+    // level 4 Ns: butterfly j' = 4 (jb - k) + k + t Ns takes output t of the four butterflies above (its inputs
+    // j' + u q); k' = k + t Ns
+    {
+      const int step = M >> (logNs + 4);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int kp = (k + t * Ns) * step;
+        const float2 w1 = twd<DIR>(tw, kp), w2 = twd<DIR>(tw, 2 * kp), w3 = twd<DIR>(tw, 3 * kp);
+        v[1][t] = cmulf(v[1][t], w1); v[2][t] = cmulf(v[2][t], w2); v[3][t] = cmulf(v[3][t], w3);
+        r4_core<DIR>(v[0][t], v[1][t], v[2][t], v[3][t]);
+      }
+    }
+    const int base = ((jb - k) << 4) + k;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s[PADI(base + (t + 4 * u) * Ns)] = v[u][t];
+    group_sync(bar_id, per);
+  }
+  if (logNs + 2 <= logM) {                             // one level left over: four independent butterflies
+    const int Ns = 1 << logNs, step = M >> (logNs + 2);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[u][t] = s[PADI(jb + u * e + t * q)];
+    group_sync(bar_id, per);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb + u * e, k = j & (Ns - 1);
+      if (logNs > 0) {
+        const float2 w1 = twd<DIR>(tw, k * step), w2 = twd<DIR>(tw, 2 * k * step), w3 = twd<DIR>(tw, 3 * k * step);
+        v[u][1] = cmulf(v[u][1], w1); v[u][2] = cmulf(v[u][2], w2); v[u][3] = cmulf(v[u][3], w3);
+      }
+      r4_core<DIR>(v[u][0], v[u][1], v[u][2], v[u][3]);
+      const int j0 = ((j - k) << 2) + k;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s[PADI(j0 + t * Ns)] = v[u][t];
+    }
+    group_sync(bar_id, per);
+    logNs += 2;
+  }
+  if (logNs < logM) {                                  // radix-2 level, in place
+    const int h = M >> 1;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int j = jb + b * e;
+      const float2 w = twd<DIR>(tw, j);
+      const float2 a = s[PADI(j)], t = cmulf(s[PADI(j + h)], w);
+      s[PADI(j)]     = cadd(a, t);
+      s[PADI(j + h)] = csub(a, t);
+    }
+    group_sync(bar_id, per);
+  }
+}
+
+#define IFFT16_THREADS 256
+__global__ void __launch_bounds__(IFFT16_THREADS, 3)
+k_chan_ifft16(const SdbChannelDev *__restrict__ chans, const int *__restrict__ group, int n_channels,
+              const float2 *__restrict__ cspec, int n_bins, int wps, int any_precise,
+              float2 *__restrict__ tails, size_t tail_stream_stride, float *__restrict__ lo_phase,
+              float2 *__restrict__ chan_out, size_t chan_stream_stride)
+{
+  extern __shared__ float2 sm[];
+  const int ci = group[blockIdx.x];
+  const SdbChannelDev ch = chans[ci];
+  const int s = blockIdx.y;
+  const int size = ch.size, hs = ch.halfsz, hw = ch.halfw;
+  const int per = size >> 4, P = IFFT16_THREADS / per;  // threads per hop, hops per round
+  const int padsz = size + (size >> 4);
+  float2 *bufs = sm;                                    // [P][padsz]
+  float2 *prevb[2] = { sm + (size_t) P * padsz, sm + (size_t) P * padsz + hs };
+  float *phase = reinterpret_cast<float *>(sm + (size_t) P * padsz + 2 * hs);   // [P][hs], precise channels only
+  const int tid = threadIdx.x;
+  const int g = tid / per, l = tid - g * per;
+  float2 *__restrict__ tail = tails + (size_t) s * tail_stream_stride + ch.tail_off;
+  float2 *__restrict__ out = chan_out + (size_t) s * chan_stream_stride + ch.out_off;
+
+  for (int i = tid; i < hs; i += IFFT16_THREADS) prevb[0][i] = tail[i];
+  float lo_phi = (any_precise && ch.precise) ? lo_phase[(size_t) s * n_channels + ci] : 0.0f;
+  int pb = 0;
+  __syncthreads();
+
+  for (int j0 = 0; j0 < wps; j0 += P) {
+    const int Pg = wps - j0 < P ? wps - j0 : P;         // hops in this round
+    const bool active = g < Pg;
+    float2 *buf = bufs + (size_t) g * padsz;
+    if (active) {
+      const float2 *__restrict__ cs = cspec + ((size_t) s * wps + j0 + g) * n_bins;
+      for (int i = hw + l; i < size - hw; i += per) buf[PADI(i)] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+      for (int i = l; i < 2 * hw; i += per) {
+        const int cidx = i < ch.L1 ? ch.c1 + i : i - ch.L1;
+        float2 X = __ldg(cs + cidx);
+        const float w = __ldg(ch.kh + i);
+        const int r = i - hw;
+        X.x *= w; X.y *= w;
+        const int o = r >= 0 ? r : size + r;
+        buf[PADI(o)] = X;
+      }
+    }
+    if (any_precise && ch.precise && tid == IFFT16_THREADS - 1) {
+      // sequential phase accumulation, exactly as the per-sample NCQO would do it
+      float phi = lo_phi;
+      for (int i = 0; i < Pg * hs; ++i) {
+        phase[i] = phi;
+        phi += ch.lo_omega;
+        if (phi >= 6.28318530717958647692f) phi -= 6.28318530717958647692f;
+        else if (phi < 0.0f) phi += 6.28318530717958647692f;
+      }
+      lo_phi = phi;
+    }
+    if (active) {
+      group_sync(1 + g, per);
+      group_fft16<+1>(buf, size, ch.log2size, l, per, 1 + g, ch.tw);
+    }
+    __syncthreads();
+    if (active) {
+      const float2 *pvb = g > 0 ? buf - padsz : nullptr;
+      for (int i = l; i < hs; i += per) {
+        const float al = __ldg(ch.xfade + i), be = __ldg(ch.xfade + i + hs);
+        const float2 cu = buf[PADI(i)], pv = g > 0 ? pvb[PADI(i + hs)] : prevb[pb][i];
+        float2 o = make_float2(al * cu.x + be * pv.x, al * cu.y + be * pv.y);
+        if (any_precise && ch.precise) {
+          float sn, cs_;
+          d_sincosf(phase[g * hs + i], &sn, &cs_);            // SPEC M.1, as the per-sample NCQO read does
+          o = cmulc(o, make_float2(cs_, sn));
+        }
+        out[(size_t) (j0 + g) * hs + i] = o;
+        if (g == Pg - 1) prevb[pb ^ 1][i] = buf[PADI(i + hs)];
+      }
+    }
+    pb ^= 1;
+    __syncthreads();
+  }
+  for (int i = tid; i < hs; i += IFFT16_THREADS) tail[i] = prevb[pb][i];
+  if (any_precise && ch.precise && tid == IFFT16_THREADS - 1) lo_phase[(size_t) s * n_channels + ci] = lo_phi;
+}
+
 // host side: channels grouped by size so that every CTA of a launch has the right block size
 cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDev *chans_dev,
                                        const int *group_dev, int group_len, int size, int n_channels,
                                        int n_streams, const float2 *cspec, int n_bins, int wps,
                                        float2 *tails, size_t tail_stream_stride, float *lo_phase,
-                                       float2 *chan_out, size_t chan_stream_stride)
+                                       float2 *chan_out, size_t chan_stream_stride, int any_precise)
 {
   static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
+  static const int use16 = getenv("SDB_IFFT16") ? atoi(getenv("SDB_IFFT16")) : 1;
+  if (use16 && size >= 512 && size <= 4096) {
+    static std::atomic<unsigned long long> attr16_done{ 0 };
+    if (sdb_first_on_device(attr16_done))
+      cudaFuncSetAttribute(k_chan_ifft16, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const int per = size / 16, P = IFFT16_THREADS / per;
+    const size_t smem = (size_t) P * (size + size / 16) * sizeof(float2) + (size_t) size * sizeof(float2)
+                        + (any_precise ? (size_t) P * (size / 2) * sizeof(float) : 0);
+    dim3 grid(group_len, n_streams);
+    k_chan_ifft16<<<grid, IFFT16_THREADS, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+                                                            any_precise, tails, tail_stream_stride, lo_phase,
+                                                            chan_out, chan_stream_stride);
+    if (c.launch_counter) ++*c.launch_counter;
+    return cudaGetLastError();
+  }
   if (sdb_first_on_device(attr_done)) {
     cudaFuncSetAttribute(k_chan_ifft<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_chan_ifft<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

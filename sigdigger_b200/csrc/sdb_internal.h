@@ -170,7 +170,7 @@ struct SdbSpectCfg {
 
 // plan-dependent shared-memory lines of k_inspectors (chain_kernels.cu): sized from the channel plan
 #define SDB_INSP_CHUNK 16          // samples per pipeline chunk (CH in chain_kernels.cu)
-#define SDB_INSP_MF_RING_MAX 225   // longest matched filter served from the shared-memory ring (256 slots)
+#define SDB_INSP_MF_RING_MAX 209   // longest matched filter served from the shared-memory ring (256 slots)
 struct SdbInspDyn {
   int rb_slots;             // carrier ring slots (power of two >= longest ring-served filter - 1 + 2 chunks)
   int mf_rows;              // tap rows [t][lane] of the longest ring-served matched filter
@@ -179,11 +179,11 @@ struct SdbInspDyn {
 };
 static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
 {
-  SdbInspDyn d = { 2 * SDB_INSP_CHUNK, 1, 8, 0 };
+  SdbInspDyn d = { 4 * SDB_INSP_CHUNK, 1, 8, 0 };   // the ring holds the chunks of the carrier, demod and filter steps
   for (int k = 0; k < n; ++k) {
     const SdbChainCfg &c = cfgs[k];
     if (c.have_mf && c.mf_n <= SDB_INSP_MF_RING_MAX) {        // longer filters stay in the global pool
-      int need = c.mf_n - 1 + 2 * SDB_INSP_CHUNK, slots = 2 * SDB_INSP_CHUNK;
+      int need = c.mf_n - 1 + 3 * SDB_INSP_CHUNK, slots = 4 * SDB_INSP_CHUNK;
       while (slots < need) slots <<= 1;
       if (slots > d.rb_slots) d.rb_slots = slots;
       if (c.mf_n > d.mf_rows) d.mf_rows = c.mf_n;
@@ -255,7 +255,10 @@ cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDe
                                        const int *group_dev, int group_len, int size, int n_channels,
                                        int n_streams, const float2 *cspec, int n_bins, int wps,
                                        float2 *tails, size_t tail_stream_stride, float *lo_phase,
-                                       float2 *chan_out, size_t chan_stream_stride);
+                                       float2 *chan_out, size_t chan_stream_stride, int any_precise = 1);
+cudaError_t sdb_launch_sym_pack(cudaStream_t stream, const uint32_t *counts, unsigned long long *offsets, size_t chains,
+                                const float2 *soft, const unsigned char *hard, size_t cap, void *out_soft,
+                                void *out_hard, unsigned long long cap_total, uint64_t *launch_counter);
 size_t sdb_inspector_smem_bytes(const SdbInspDyn &dyn);
 // chain_map / n_ctas from sdb_build_chain_map (null: identity, (chains + 31) / 32 CTAs); the pool holds
 // n_ctas * 32 * pool_stride floats

@@ -433,3 +433,104 @@ cudaError_t sdb_launch_dc_remove(cudaStream_t st, const void *x, int fmt, size_t
   k_dc_apply<<<g2, 256, 0, st>>>(x, fmt, stream_stride, n, cur, out);
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// packed symbol read-out.  The inspector kernel leaves chain c's symbols at [c][0 .. counts[c]) of a [chains][cap]
+// array (cap = channel samples per feed, the only static bound: the Gardner loop's baud is free in [0, 1]).  Copying
+// the array wholesale moves cap / symbols-per-feed times more bytes over PCIe than there are symbols (cfg3: 3.1 x).
+// k_sym_offsets lays the chains out back to back (each start rounded up to 16 symbols, so that every row of the
+// copy starts on a 128-byte line of `soft` and a 16-byte word of `hard`); k_sym_pack then WRITES the packed rows
+// straight into the destination -- pinned host memory mapped into the device's address space, or device memory --
+// with 16-byte stores.  No size has to be known on the host before the copy, so the read stays asynchronous.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sym_offsets(const uint32_t *__restrict__ counts, size_t chains,
+                                                      unsigned long long *__restrict__ offsets)
+{
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < chains; base += 1024) {
+    const size_t c = base + threadIdx.x;
+    const unsigned long long v = c < chains ? (unsigned long long) ((counts[c] + 15u) & ~15u) : 0ull;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long t = warp_tot[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, t, d);
+        if (lane >= d) t += y;
+      }
+      warp_tot[lane] = t;                                 // inclusive totals of the warps
+    }
+    __syncthreads();
+    const unsigned long long before = carry + (warp ? warp_tot[warp - 1] : 0ull) + (x - v);
+    if (c < chains) offsets[c] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[chains] = carry;
+}
+
+__global__ void __launch_bounds__(128) k_sym_pack(const uint32_t *__restrict__ counts,
+                                                  const unsigned long long *__restrict__ offsets, size_t chains,
+                                                  const float2 *__restrict__ soft, const unsigned char *__restrict__ hard,
+                                                  size_t cap, float4 *__restrict__ out_soft, uint4 *__restrict__ out_hard,
+                                                  unsigned long long cap_total)
+{
+  for (size_t c = blockIdx.x; c < chains; c += gridDim.x) {
+    const uint32_t cnt = counts[c];
+    const unsigned long long off = offsets[c];            // multiple of 16
+    const uint32_t padded = (cnt + 15u) & ~15u;
+    if (off + padded > cap_total) continue;               // does not fit: the caller sees it from offsets[chains]
+    if (out_soft) {
+      const float2 *__restrict__ src = soft + c * cap;
+      float4 *__restrict__ dst = out_soft + off / 2;
+      for (uint32_t i = threadIdx.x; i < padded / 2; i += blockDim.x) {
+        const uint32_t a = 2 * i, b = 2 * i + 1;
+        const float2 u = a < cnt ? src[a] : make_float2(0.0f, 0.0f), v = b < cnt ? src[b] : make_float2(0.0f, 0.0f);
+        dst[i] = make_float4(u.x, u.y, v.x, v.y);
+      }
+    }
+    if (out_hard) {
+      const unsigned char *__restrict__ src = hard + c * cap;
+      uint4 *__restrict__ dst = out_hard + off / 16;
+      for (uint32_t i = threadIdx.x; i < padded / 16; i += blockDim.x) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t x = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t idx = 16 * i + 4 * k + j;
+            x |= (idx < cnt ? (uint32_t) src[idx] : 0u) << (8 * j);
+          }
+          w[k] = x;
+        }
+        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+
+cudaError_t sdb_launch_sym_pack(cudaStream_t stream, const uint32_t *counts, unsigned long long *offsets, size_t chains,
+                                const float2 *soft, const unsigned char *hard, size_t cap, void *out_soft,
+                                void *out_hard, unsigned long long cap_total, uint64_t *launch_counter)
+{
+  if (chains == 0) return cudaSuccess;
+  k_sym_offsets<<<1, 1024, 0, stream>>>(counts, chains, offsets);
+  const unsigned grid = (unsigned) (chains < 148 * 16 ? chains : 148 * 16);
+  k_sym_pack<<<grid, 128, 0, stream>>>(counts, offsets, chains, soft, hard, cap, (float4 *) out_soft, (uint4 *) out_hard,
+                                       cap_total);
+  if (launch_counter) *launch_counter += 2;
+  return cudaGetLastError();
+}

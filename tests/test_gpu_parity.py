@@ -580,6 +580,70 @@ def test_async_pipeline_matches_sync(sdb):
             assert np.array_equal(outs[i][4][c, :m], ref[i][3][c, :m])
 
 
+def test_packed_symbol_read_matches_unpacked(sdb):
+    """sdb_engine_read_symbols_packed_async: the GPU lays the chains' symbols back to back (16-symbol aligned starts,
+    zero-filled gaps) straight into pinned host memory; same symbols as the [chains][cap] read, queued asynchronously
+    behind two feeds; pageable destinations and too small buffers are refused / reported"""
+    import torch
+    N, S, feeds = 16384, 5, 3
+    n = N * 4
+    specs = [("qpsk", 0.10, 1 / 128., -14.0, {}), ("fsk", 0.30, 1 / 160., -14.0, {}), ("qpsk", 0.55, 1 / 256., -14.0, {})]
+    x, _ = _pipeline_case(N, 8 * feeds, 71, specs, S=S)
+    e = sdb.Engine(n_streams=S, psd_size=N, psd_window="hann", max_feed=n)
+    for kind, f, baud, _, _ in specs:
+        h = e.open_channel(2 * np.pi * f, 2 * np.pi * 3 * baud, 1.0)
+        if kind == "qpsk":
+            e.set_inspector(h, "psk", baud=baud, costas_order=2, bits_per_symbol=2,
+                            loop_bw=e.channel_rate(h) * 2e-3, mf_type=1, clock_type=1, clock_gain=0.1)
+        else:
+            e.set_inspector(h, "fsk", baud=baud, bits_per_symbol=1, mf_type=1, clock_type=1, clock_gain=0.2)
+    e.commit()
+    cap, chains = e.symbol_capacity, S * len(specs)
+    total_cap = chains * ((cap + 15) // 16 * 16)
+    pin = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=True).numpy()
+    outs = []
+    for i in range(feeds):
+        seg = np.ascontiguousarray(x[:, i * n:(i + 1) * n])
+        o = dict(seg=seg, cnt=pin((chains,), torch.int32).view(np.uint32), off=pin((chains + 1,), torch.int64).view(np.uint64),
+                 soft=pin((total_cap,), torch.complex64), hard=pin((total_cap,), torch.uint8))
+        o["soft"][:] = 7 + 7j
+        o["hard"][:] = 77
+        e.feed_host_ptr(seg.ctypes.data, n, n)
+        e.read_symbols_packed_async(o["cnt"], o["off"], o["soft"], o["hard"], total_cap)
+        # the unpacked read of the same feed, for comparison
+        o["rc"], o["rs"], o["rh"] = (np.zeros(chains, np.uint32), np.zeros((chains, cap), np.complex64),
+                                     np.zeros((chains, cap), np.uint8))
+        e.read_all_symbols_async(o["rc"], o["rs"], o["rh"], cap)
+        outs.append(o)
+    e.sync()
+    for i, o in enumerate(outs):
+        assert np.array_equal(o["cnt"], o["rc"]) and o["cnt"].sum() > 0
+        assert o["off"][0] == 0 and np.all(o["off"] % 16 == 0)
+        assert np.array_equal(np.diff(o["off"].astype(np.int64)), (o["cnt"].astype(np.int64) + 15) // 16 * 16)
+        for c in range(chains):
+            m, a = int(o["cnt"][c]), int(o["off"][c])
+            assert np.array_equal(o["soft"][a:a + m].view(np.uint32), o["rs"][c, :m].view(np.uint32)), (i, c)
+            assert np.array_equal(o["hard"][a:a + m], o["rh"][c, :m]), (i, c)
+            pad = int(o["off"][c + 1]) - a - m
+            assert not o["soft"][a + m:a + m + pad].any() and not o["hard"][a + m:a + m + pad].any()
+        assert np.all(o["hard"][int(o["off"][-1]):] == 77)       # nothing written past the extent
+    # a destination that is too small: the rows that fit are written, the extent tells
+    o = outs[-1]
+    small = int(o["off"][chains // 2])
+    cnt2, off2 = np.zeros(chains, np.uint32), np.zeros(chains + 1, np.uint64)
+    soft2 = pin((total_cap,), torch.complex64)
+    soft2[:] = 9
+    e.read_symbols_packed(cnt2, off2, soft2, None, small)
+    assert int(off2[-1]) > small and np.array_equal(soft2[:small].view(np.uint32), o["soft"][:small].view(np.uint32))
+    assert np.all(soft2[small:] == 9)
+    # device destination
+    dsoft = torch.zeros(total_cap, dtype=torch.complex64, device="cuda")
+    e.read_symbols_packed(cnt2, off2, dsoft.data_ptr(), None, total_cap)
+    assert np.array_equal(dsoft.cpu().numpy()[:int(off2[-1])].view(np.uint32), o["soft"][:int(off2[-1])].view(np.uint32))
+    with pytest.raises(sdb.SdbError):                          # pageable memory cannot be written by the GPU
+        e.read_symbols_packed(cnt2, off2, np.zeros(total_cap + 2, np.complex64)[2:], None, total_cap)
+
+
 def test_error_paths(sdb):
     e = sdb.Engine(n_streams=1, psd_size=8192, max_feed=8192)
     with pytest.raises(sdb.SdbError):

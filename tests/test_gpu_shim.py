@@ -106,6 +106,5 @@ def test_analyzer_session_through_the_suscan_names(tu, oracle):
     chan = ref["chan"][0]
     hops = per_block // (N // 2)
     skip = (hops - 1) * 128 + hops * 128           # channel samples of blocks 2 and 3 (halfsz = 128)
-    rs = oracle.inspector_run(ic, chan[skip:])
-    rh = oracle.decide(rs, "argument", 2, -np.pi, np.pi)
+    rs, rh = oracle.inspector_run(ic, chan[skip:])
     parity.assert_symbols_match(soft[:got], hard[:got], rs, rh, exact_soft=True)

@@ -1,18 +1,15 @@
-"""-m gpu: two device paths added after the round's GPU minutes were spent, against the oracle (which the CPU suite
-pins to literal transcriptions of the reference):
+"""-m gpu: two device paths against the oracle (which the CPU suite pins to the compiled reference / literal
+transcriptions of it):
   * SpectrumView::feed(SpectrumView const &) (Panoramic/Scanner.cpp:276-286, the zoom path of Scanner::setViewRange):
-    k_sview_project_view + the verified accumulate / fill passes;
+    k_sview_project_view + the accumulate / fill passes;
   * the inspector tab's SNR estimator (Misc/SNREstimator.cpp:30-169): k_snr_feed.
-Both compile for sm_100a but have not run on hardware yet.  The file sorts last and is marked xfail(strict=False) so
-that a first-run surprise cannot mask the verified suite; XPASS = they work as written (then drop the mark)."""
+First hardware run: round 2 (both bit-exact as written)."""
 import ctypes as C
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="first hardware run pending (added after the round's GPU budget was spent)",
-                                strict=False)]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_snr_estimator_batch_bit_exact(sdb, oracle):
