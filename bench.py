@@ -425,6 +425,41 @@ def cfg5_config():
             "parallelism": "hops sharded contiguously over ranks; one NCCL gather of the contribution lists per sweep"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs off, so that the
+    H2D / D2H copies of N ranks do not all cross the socket interconnect.  Returns a description for the JSON line;
+    never fatal (containers without /sys topology just keep their affinity)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local
+        if vis:
+            toks = [t for t in vis.split(",") if t.strip()]
+            if local < len(toks) and toks[local].strip().isdigit():
+                idx = int(toks[local])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()
+        if len(bdf.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for " + bdf}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"numa_node": node, "note": "node CPUs outside this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as ex:                                   # noqa: BLE001
+        return {"numa_node": None, "note": "not bound: %s" % type(ex).__name__}
+
+
 def run_cuda_cfg5(args):
     import torch
     import sigdigger_b200 as sdb
@@ -435,6 +470,8 @@ def run_cuda_cfg5(args):
     if sdb.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -509,6 +546,10 @@ def run_cuda_cfg5(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # dominant kernels: the two passes of the hop PSDs (inside psd_project_ms); B_alg = 8 B in + 4 B out per sample
     ach = B_ALG["cfg5"] * (hi - lo) * N_FFT / (tm["psd_project_ms"] * 1e-3) / 1e9 if tm["psd_project_ms"] > 0 else 0.0
+    try:
+        os.sched_setaffinity(0, affinity0)
+    except OSError:
+        pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cfg5_cpu(min(128, CFG5_HOPS))
@@ -516,7 +557,7 @@ def run_cuda_cfg5(args):
         out = {"metric": "complex MSamples/s ingested (65536-pt PSD per tuner hop, stitched)", "value": value,
                "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": cfg5_config(), "clocks": clk.summary(),
+               "dtype": "f32", "data": "synthetic", "config": dict(cfg5_config(), host_binding=numa), "clocks": clk.summary(),
                "gpu_launches": None,
                "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(samples * 8),
                        "d2h_bytes_per_step": int(3 * 65536 * 4)},
@@ -597,6 +638,8 @@ def run_cuda(args):
     if sdb.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)                      # undone before the CPU baseline leg below
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -799,6 +842,10 @@ def run_cuda(args):
         e1.close()
 
     # ---- bounded CPU baseline on rank 0, N=1 only
+    try:
+        os.sched_setaffinity(0, affinity0)                   # the CPU arm gets every core the process was given
+    except OSError:
+        pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores, kind, how = pick_threads(name)
@@ -813,7 +860,7 @@ def run_cuda(args):
         out = {"metric": "complex MSamples/s ingested (%d-pt PSD + N inspectors)" % N_FFT, "value": value,
                "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": workload_config(args, S, H),
+               "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, S, H), host_binding=numa),
                "clocks": clk.summary(), "gpu_launches": int(launches),
                "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                "roofline": roofline, "cpu_baseline": cpu, "single_stream_msps": single,

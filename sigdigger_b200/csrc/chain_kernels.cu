@@ -228,32 +228,15 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       for (int i = 0; i < cnt; ++i) {
         // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
+        // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
         const float2 y = sm.y[b3][i][lane];
         const unsigned dp = as.dl_ptr;
         as.dl_ptr = dp + 1 >= dl_size ? 0 : dp + 1;
         const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
         dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
         sm.y[b3][i][lane] = xd;
-        // magnitude history, running peak, fast / slow levels (SPEC A)
-        const float m = sm.m[b3][i][lane];
-        const float m_old = mh[as.mh_ptr * 32];
-        mh[as.mh_ptr * 32] = m;
-        if (++as.mh_ptr >= mh_size) as.mh_ptr = 0;
-        if (m > as.peak) {
-          as.peak = m;
-        } else if (as.peak == m_old) {
-          float pk = -160.0f;
-          for (unsigned q = 0; q < mh_size; ++q) { float v = mh[q * 32]; if (pk < v) pk = v; }
-          as.peak = pk;
-        }
-        float d = as.peak - as.fast;
-        if (d > 0.0f) as.fast = as.fast + far_ * d;
-        else          as.fast = as.fast + faf * d;
-        d = as.peak - as.slow;
-        if (d > 0.0f) { as.slow = as.slow + sar * d; as.hang_n = 0; }
-        else if (as.hang_n >= hang_max) as.slow = as.slow + saf * d;
-        else ++as.hang_n;
-        sm.m[b3][i][lane] = as.fast > as.slow ? as.fast : as.slow;
+        // magnitude history, running peak, fast / slow levels (SPEC A), select form
+        sm.m[b3][i][lane] = agc_level_sel<32>(far_, faf, sar, saf, hang_max, mh_size, as, mh, sm.m[b3][i][lane]);
       }
     }
     cp_async_wait<0>();
@@ -405,11 +388,39 @@ static __device__ void role_carrier(const ICtx &c)
     dc_alpha = cp->dc_alpha; sq_alpha = cp->sq_alpha; sq_thr = cp->sq_thr;
     if (cls == SDB_INSP_AUDIO) { lo_phi = stp->lo_phi; lo_omega = cp->lo_omega; }
   }
+  // Costas: when every chain of the warp runs the same loop kind and arm-filter length (the usual case: a CTA holds
+  // one inspector class), the sample loop is the compile-time variant -- no per-lane branches between the dependent
+  // operations of the recurrence, which is the slowest role of the psk CTAs (988 cycles per sample with them)
+  int psk_sel = 0;
+  {
+    const unsigned vm = __ballot_sync(0xffffffffu, c.valid != 0);
+    const int src = vm ? __ffs(vm) - 1 : 0;
+    const int kind0 = __shfl_sync(0xffffffffu, ck.kind, src), afn0 = __shfl_sync(0xffffffffu, ck.af_n, src);
+    const int hc0 = __shfl_sync(0xffffffffu, have_costas, src);
+    const bool same = __all_sync(0xffffffffu, !c.valid || (ck.kind == kind0 && ck.af_n == afn0 && have_costas == hc0));
+    if (cls == SDB_INSP_PSK && same && hc0 && kind0 >= 1 && kind0 <= 3 && (afn0 == 1 || afn0 == 3))
+      psk_sel = kind0 * 4 + afn0;
+  }
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
-    if (it >= 4 && it - 4 < c.nchunks) {
+    if (psk_sel && it >= 4 && it - 4 < c.nchunks) {
+      const uint32_t ckk = it - 4, base = ckk * CH;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*in)[32] = sm.ringA[ckk & 1];
+#define PSK_LOOP(K_, A_) for (int i = 0; i < cnt; ++i) \
+        c.rb[(base + i) & c.rb_mask][lane] = costas_step_t<K_, A_>(ck, cs, in[i][lane]); break
+      switch (psk_sel) {
+        case 1 * 4 + 1: PSK_LOOP(1, 1);
+        case 1 * 4 + 3: PSK_LOOP(1, 3);
+        case 2 * 4 + 1: PSK_LOOP(2, 1);
+        case 2 * 4 + 3: PSK_LOOP(2, 3);
+        case 3 * 4 + 1: PSK_LOOP(3, 1);
+        default:        PSK_LOOP(3, 3);
+      }
+#undef PSK_LOOP
+    } else if (it >= 4 && it - 4 < c.nchunks) {
       const uint32_t ckk = it - 4, base = ckk * CH;
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       float2 (*in)[32] = sm.ringA[ckk & 1];
@@ -643,11 +654,27 @@ static __device__ void role_clock(const ICtx &c)
       }
     }
   }
+  // every chain of the warp a symbol inspector on the Gardner loop without equaliser (the usual CTA): the sample
+  // loop is the select form of clock_step alone, with none of the other classes' state live in it
+  const bool gardner_only = __all_sync(0xffffffffu, !c.valid || (cls != SDB_INSP_RAW && cls != SDB_INSP_AUDIO &&
+                                                               clock_type == 1 && eq_type == 0));
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
-    if (it >= 7 && it - 7 < c.nchunks) {
+    if (gardner_only && it >= 7 && it - 7 < c.nchunks) {
+      const uint32_t ck = it - 7, base = ck * CH;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*in)[32] = sm.ringC[ck & 1];
+      float2 (*sy)[32] = sm.sym[ck & 1];
+      int k = 0;
+      for (int i = 0; i < cnt; ++i) {
+        float2 o;
+        const bool produced = clock_step_sel(clk_gain, clk_alpha, clk_beta, ks, in[i][lane], o);
+        if (produced && clock_running) sy[k++][lane] = o;
+      }
+      sm.cnt[ck & 1][lane] = k;
+    } else if (it >= 7 && it - 7 < c.nchunks) {
       const uint32_t ck = it - 7, base = ck * CH;
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       float2 (*in)[32] = sm.ringC[ck & 1];

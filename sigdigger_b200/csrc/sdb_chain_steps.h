@@ -116,21 +116,56 @@ SDB_HD float2 agc_step(const AgcK &k, AgcS &s, float *dl, float *mh, float2 x)
   return xd;
 }
 
+// The level tracker of agc_step (magnitude history, running peak, fast / slow levels) alone, with every per-lane
+// `if` written as a select: the inspector kernel's track warp.  The chains of a warp disagree on these conditions at
+// almost every sample, and a divergent branch costs the warp a reconvergence barrier plus an instruction-fetch bubble
+// on either side (ncu: `no instruction` was the top stall of the recurrence warps).  Same operations on the same
+// operands as agc_step, so the same bits.  Returns max(fast, slow).
+template <int STRIDE = 32>
+SDB_HD float agc_level_sel(float far_, float faf, float sar, float saf, unsigned hang_max, unsigned mh_size, AgcS &s,
+                           float *mh, float m)
+{
+  const unsigned mp = s.mh_ptr;
+  const float m_old = mh[mp * STRIDE];
+  mh[mp * STRIDE] = m;
+  s.mh_ptr = mp + 1 >= mh_size ? 0 : mp + 1;
+  const bool rescan = !(m > s.peak) && s.peak == m_old;
+  s.peak = m > s.peak ? m : s.peak;
+  if (rescan) {                                          // the window's maximum left it: rare
+    float pk = -160.0f;
+    for (unsigned q = 0; q < mh_size; ++q) { float v = mh[q * STRIDE]; if (pk < v) pk = v; }
+    s.peak = pk;
+  }
+  float d = s.peak - s.fast;
+  s.fast = s.fast + (d > 0.0f ? far_ : faf) * d;
+  d = s.peak - s.slow;
+  const bool up = d > 0.0f, fall = !up && s.hang_n >= hang_max;
+  const float slow_n = s.slow + (up ? sar : saf) * d;
+  s.slow = (up || fall) ? slow_n : s.slow;
+  s.hang_n = up ? 0u : (fall ? s.hang_n : s.hang_n + 1u);
+  return s.fast > s.slow ? s.fast : s.slow;
+}
+
 struct CostasK { int kind, af_n; float a, b; float af_b[SDB_MAX_IIR], af_a[SDB_MAX_IIR]; };
 struct CostasS { float phi, omega, lock, yre, yim; float xr[SDB_MAX_IIR], xi[SDB_MAX_IIR], yr[SDB_MAX_IIR], yi[SDB_MAX_IIR]; };
 
-SDB_HD float2 costas_step(const CostasK &k, CostasS &s, float2 x)
+// KIND / AFN >= 0: loop kind and arm-filter length known at compile time (the inspector kernel's carrier warp, when
+// every chain of the warp agrees); -1: read from k.  Same statements either way.
+template <int KIND, int AFN>
+SDB_HD float2 costas_step_t(const CostasK &k, CostasS &s, float2 x)
 {
+  const int kind = KIND >= 0 ? KIND : k.kind;
   float2 n = ncqo_read(s.phi, s.omega);
   float2 mixed = make_float2(x.x * n.x + x.y * n.y, x.y * n.x - x.x * n.y);
-  float2 z = iir_any(k.af_n, k.af_b, k.af_a, s.xr, s.xi, s.yr, s.yi, mixed);
+  float2 z = AFN >= 1 ? iir_step<(AFN >= 1 ? AFN : 1)>(k.af_b, k.af_a, s.xr, s.xi, s.yr, s.yi, mixed)
+                      : iir_any(k.af_n, k.af_b, k.af_a, s.xr, s.xi, s.yr, s.yi, mixed);
   float e = 0.0f, lr, li;
-  if (k.kind == 1) {
+  if (kind == 1) {
     e = -(z.x * z.y);
-  } else if (k.kind == 2) {
+  } else if (kind == 2) {
     lr = sgnf(z.x); li = sgnf(z.y);
     e = lr * z.y - li * z.x;
-  } else if (k.kind == 3) {
+  } else if (kind == 3) {
     lr = sgnf(z.x); li = sgnf(z.y);
     if (fabsf(z.x) >= fabsf(z.y)) e = lr * z.y - li * z.x * 0.41421356237309504f;
     else                          e = lr * z.y * 0.41421356237309504f - li * z.x;
@@ -142,6 +177,8 @@ SDB_HD float2 costas_step(const CostasK &k, CostasS &s, float2 x)
   s.phi = wrap_once(s.phi + k.a * e);
   return make_float2(s.yre, s.yim);
 }
+
+SDB_HD float2 costas_step(const CostasK &k, CostasS &s, float2 x) { return costas_step_t<-1, -1>(k, s, x); }
 
 SDB_HD float2 pll_step(float alpha, float beta, float &phi, float &omega, float2 x)
 {
@@ -200,6 +237,35 @@ SDB_HD bool clock_step(float gain, float alpha, float beta, ClockS &s, float2 v,
   }
   s.pr = v.x; s.pi = v.y;
   return produced;
+}
+
+// clock_step with every per-lane `if` written as a select (the inspector kernel's clock warp: its 32 chains cross
+// the half-symbol mark at different samples, so a branching body is executed in full at almost every sample anyway,
+// plus the reconvergence overhead).  Same operations on the same operands as clock_step: `phi - 0.5f` is evaluated
+// once there too (for `al` and for the new phase), x0 - x2 after the shift is p - (old x0).
+SDB_HD bool clock_step_sel(float gain, float alpha, float beta, ClockS &s, float2 v, float2 &out)
+{
+  const float phi1 = s.phi + s.bnor;
+  const bool cross = phi1 >= 0.5f;
+  const float ph = phi1 - 0.5f;
+  const float al = s.bnor * ph, om = 1.0f - al;
+  const float pr = om * v.x + al * s.pr, pi = om * v.y + al * s.pi;
+  const bool full = cross && s.half != 0, halfc = cross && s.half == 0;
+  const float dr = pr - s.x0r, di = pi - s.x0i;
+  const float e = gain * (s.x1r * dr + s.x1i * di);
+  const float phi_full = ph + alpha * e;
+  float bn = s.bnor + beta * e;
+  bn = bn > 1.0f ? 1.0f : bn;
+  bn = bn < 0.0f ? 0.0f : bn;
+  s.x2r = full ? s.x0r : s.x2r; s.x2i = full ? s.x0i : s.x2i;
+  s.x0r = full ? pr : s.x0r;    s.x0i = full ? pi : s.x0i;
+  s.x1r = halfc ? pr : s.x1r;   s.x1i = halfc ? pi : s.x1i;
+  s.phi = cross ? (full ? phi_full : ph) : phi1;
+  s.bnor = full ? bn : s.bnor;
+  s.half = cross ? !s.half : s.half;
+  s.pr = v.x; s.pi = v.y;
+  out = make_float2(pr, pi);
+  return full;
 }
 
 SDB_HD bool sampler_step(float period, float phase0, float &phase, float &pr, float &pi,

@@ -46,18 +46,16 @@ SDB_HD void d_sincosf(float x, float *s, float *c)
   *c = ((n + 1) & 2) ? -c0 : c0;
 }
 
+// SPEC M.2 in select form: the three reduction ranges share one division (t/1 is exact, so the small range is
+// unchanged) and every `if` of the statement is a select -- the same operations on the same operands, hence the same
+// bits, without per-lane branches (32 chains of a warp rarely agree on the octant).
 SDB_HD float d_atanf_pos(float t)
 {
-  float y0;
-  if (t > 2.414213562373095f) {
-    y0 = 1.5707963267948966f;
-    t = -1.0f / t;
-  } else if (t > 0.4142135623730950f) {
-    y0 = 0.7853981633974483f;
-    t = (t - 1.0f) / (t + 1.0f);
-  } else {
-    y0 = 0.0f;
-  }
+  const bool big = t > 2.414213562373095f, mid = !big && t > 0.4142135623730950f;
+  const float y0 = big ? 1.5707963267948966f : (mid ? 0.7853981633974483f : 0.0f);
+  const float num = big ? -1.0f : (mid ? t - 1.0f : t);
+  const float den = big ? t : (mid ? t + 1.0f : 1.0f);
+  t = num / den;
   float z = t * t;
   float y = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z
              - 3.33329491539e-1f) * z * t + t;
@@ -66,13 +64,12 @@ SDB_HD float d_atanf_pos(float t)
 
 SDB_HD float d_atan2f(float y, float x)
 {
-  float ax = fabsf(x), ay = fabsf(y), a;
-  if (ax == 0.0f && ay == 0.0f) return 0.0f;
-  if (ax == 0.0f) a = 1.5707963267948966f;
-  else a = d_atanf_pos(ay / ax);
-  if (x < 0.0f) a = 3.14159265358979323846f - a;
-  if (y < 0.0f) a = -a;
-  return a;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a = d_atanf_pos(ay / ax);
+  a = ax == 0.0f ? 1.5707963267948966f : a;
+  a = x < 0.0f ? 3.14159265358979323846f - a : a;
+  a = y < 0.0f ? -a : a;
+  return (ax == 0.0f && ay == 0.0f) ? 0.0f : a;
 }
 
 SDB_HD float d_log10f(float x)
