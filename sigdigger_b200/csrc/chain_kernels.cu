@@ -14,6 +14,8 @@
 //   chain order            doc/SigDigger_User_Manual.pdf pp.50-52
 #include "sdb_internal.h"
 #include "../../include/sigdigger_b200.h"
+#include <stdlib.h>
+#include <string.h>
 
 #include "sdb_chain_steps.h"
 #include "sdb_cpx.h"
@@ -48,7 +50,7 @@
 // grew to 360 KB / 676 KB of code and every role warp starved on instruction fetch.  The recurrences run at about
 // six cycles per instruction whatever the mapping, so this kernel keeps its loops rolled and its code small (84 KB).
 #define CH 16
-enum { W_TRACK = 0, W_PRE = 1, W_POST = 3, W_CARRIER = 5, W_MF = 6, W_CLOCK = 10, W_OUT = 11, INSP_WARPS = 12 };
+enum { INSP_WARPS = 12 };              // role of each warp: see the dispatch at the end of k_inspectors
 #define INSP_STEPS 8          // pipeline depth after the load: a chunk loaded in iteration c leaves in iteration c + 8
 
 #ifdef SDB_STAGE_CYCLES
@@ -226,18 +228,23 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
       const uint32_t ck = it - 2, base = ck * CH;
       const int b3 = (int) (ck % 3u);
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
-      for (int i = 0; i < cnt; ++i) {
-        // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
-        // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
-        const float2 y = sm.y[b3][i][lane];
-        const unsigned dp = as.dl_ptr;
-        as.dl_ptr = dp + 1 >= dl_size ? 0 : dp + 1;
-        const float2 xd = make_float2(dl[(2 * dp) * 32], dl[(2 * dp + 1) * 32]);
-        dl[(2 * dp) * 32] = y.x; dl[(2 * dp + 1) * 32] = y.y;
-        sm.y[b3][i][lane] = xd;
-        // magnitude history, running peak, fast / slow levels (SPEC A), select form
-        sm.m[b3][i][lane] = agc_level_sel<32>(far_, faf, sar, saf, hang_max, mh_size, as, mh, sm.m[b3][i][lane]);
-      }
+      auto run = [&](float *dl_, float *mh_) {
+        for (int i = 0; i < cnt; ++i) {
+          // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
+          const float2 y = sm.y[b3][i][lane];
+          const unsigned dp = as.dl_ptr;
+          as.dl_ptr = dp + 1 >= dl_size ? 0 : dp + 1;
+          const float2 xd = make_float2(dl_[(2 * dp) * 32], dl_[(2 * dp + 1) * 32]);
+          dl_[(2 * dp) * 32] = y.x; dl_[(2 * dp + 1) * 32] = y.y;
+          sm.y[b3][i][lane] = xd;
+          // magnitude history, running peak, fast / slow levels (SPEC A), select form
+          sm.m[b3][i][lane] = agc_level_sel<32>(far_, faf, sar, saf, hang_max, mh_size, as, mh_, sm.m[b3][i][lane]);
+        }
+      };
+      // lines in shared memory (the usual case): pointers the compiler can see are shared, so LDS / STS and not
+      // generic loads and stores (the merged `in_smem ? shared : global` pointer made every access generic)
+      if (in_smem) run(&c.agc[0][lane], &c.agc[2 * dl_size][lane]);
+      else         run(dl, mh);
     }
     cp_async_wait<0>();
     ROLE_T1;
@@ -326,10 +333,35 @@ static __device__ void role_post(const ICtx &c, int part)
   // ask + PLL: the phase detector's atan2 depends on the sample alone, not on the loop: evaluated here, beside the
   // recurrence instead of inside it (same function on the same argument: bit-identical to pll_step)
   const bool want_ang = c.valid && cls == SDB_INSP_ASK && c.cp->have_pll;
+  // the usual CTA -- every chain a symbol inspector behind an AGC, all or none of them wanting the angle -- on a full
+  // chunk: the statements below without their per-sample guards (the general loop spends 8 branches per sample on
+  // them), 1 = gain only, 2 = gain + angle
+  int fast = 0;
+  if (__all_sync(0xffffffffu, !c.valid || (have_agc && cls != SDB_INSP_AUDIO)))
+    fast = __all_sync(0xffffffffu, !c.valid || want_ang) ? 2 : (__all_sync(0xffffffffu, !want_ang) ? 1 : 0);
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
-    if (it >= 3 && it - 3 < c.nchunks) {
+    const bool active = it >= 3 && it - 3 < c.nchunks;
+    const bool full_chunk = active && fast && __all_sync(0xffffffffu, !c.valid || ((it - 3) * CH + CH <= n));
+    if (full_chunk) {
+      const uint32_t ck = it - 3;
+      const int b3 = (int) (ck % 3u);
+      float2 (*out)[32] = sm.ringA[ck & 1];
+      float (*ang)[32] = sm.ang[ck & 1];
+#pragma unroll 4
+      for (int i = i0; i < i1; ++i) {
+        float2 y = sm.y[b3][i][lane];
+        const float lvl = sm.m[b3][i][lane];
+        const float gx = d_db_to_mag(lvl * slope_m1);
+        float g = lvl < knee ? fixed_gain : gx;
+        g = g * 0.7f;
+        y.x = y.x * g; y.y = y.y * g;
+        y.x = 2.0f * y.x; y.y = 2.0f * y.y;
+        out[i][lane] = y;
+        if (fast == 2) ang[i][lane] = d_atan2f(y.y, y.x);
+      }
+    } else if (active) {
       const uint32_t ck = it - 3, base = ck * CH;
       const int b3 = (int) (ck % 3u);
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
@@ -401,6 +433,13 @@ static __device__ void role_carrier(const ICtx &c)
     if (cls == SDB_INSP_PSK && same && hc0 && kind0 >= 1 && kind0 <= 3 && (afn0 == 1 || afn0 == 3))
       psk_sel = kind0 * 4 + afn0;
   }
+  // the same for the other classes: one compact loop per class when the warp is uniform (1: ask + PLL, 2: fsk).  The
+  // general loop below branches over every class per sample; its body is several hundred instructions long and the
+  // jumps between its far-apart blocks showed up as instruction-fetch stalls on the warp that sets the CTA's pace.
+  int uni_sel = 0;
+  if (__all_sync(0xffffffffu, !c.valid || (cls == SDB_INSP_ASK && have_pll))) uni_sel = 1;
+  const int quad_u = __shfl_sync(0xffffffffu, quad, __ffs(__ballot_sync(0xffffffffu, c.valid != 0) | 0x80000000u) - 1);
+  if (!uni_sel && __all_sync(0xffffffffu, !c.valid || (cls == SDB_INSP_FSK && quad == quad_u))) uni_sel = 2;
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
@@ -420,6 +459,35 @@ static __device__ void role_carrier(const ICtx &c)
         default:        PSK_LOOP(3, 3);
       }
 #undef PSK_LOOP
+    } else if (uni_sel == 1 && it >= 4 && it - 4 < c.nchunks) {
+      // ask + PLL, every chain of the warp: the (phi, omega) recurrence alone (see the general loop below)
+      const uint32_t ckk = it - 4, base = ckk * CH;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*in)[32] = sm.ringA[ckk & 1];
+      float (*ang)[32] = sm.ang[ckk & 1], (*phs)[32] = sm.phs[ckk & 1];
+      for (int i = 0; i < cnt; ++i) {
+        phs[i][lane] = p_phi;
+        p_phi = wrap_once(p_phi + p_omega);
+        float err = ang[i][lane] - p_phi;
+        err = err > PI_F ? err - TWOPI_F : (err < -PI_F ? err + TWOPI_F : err);
+        p_omega = p_omega + pll_a * err;
+        p_phi = wrap_once(p_phi + pll_b * err);
+        c.rb[(base + i) & c.rb_mask][lane] = in[i][lane];
+      }
+    } else if (uni_sel == 2 && it >= 4 && it - 4 < c.nchunks) {
+      // fsk, every chain of the warp: the discriminator alone
+      const uint32_t ckk = it - 4, base = ckk * CH;
+      const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
+      float2 (*in)[32] = sm.ringA[ckk & 1];
+      for (int i = 0; i < cnt; ++i) {
+        float2 y = in[i][lane];
+        const float dr = y.x * prev_re + y.y * prev_im;
+        const float di = y.y * prev_re - y.x * prev_im;
+        prev_re = y.x; prev_im = y.y;
+        if (quad_u) { y.x = d_atan2f(di, dr) * 0.318309886183790671538f; y.y = 0.0f; }     // warp-uniform
+        else { y.x = dr * rot_re - di * rot_im; y.y = dr * rot_im + di * rot_re; }
+        c.rb[(base + i) & c.rb_mask][lane] = y;
+      }
     } else if (it >= 4 && it - 4 < c.nchunks) {
       const uint32_t ckk = it - 4, base = ckk * CH;
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
@@ -561,15 +629,24 @@ static __device__ void role_filter(const ICtx &c, int part, const float *taps_po
           float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
           float2 w0 = c.rb[(p0 + 0) & c.rb_mask][lane], w1 = c.rb[(p0 + 1) & c.rb_mask][lane];
           float2 w2 = c.rb[(p0 + 2) & c.rb_mask][lane], w3 = c.rb[(p0 + 3) & c.rb_mask][lane];
-#pragma unroll 4
-          for (int t = 0; t < mf_n; ++t) {
-            const float b = c.taps[t][lane];
-            const float2 bb = make_float2(b, b);
-            const float2 nx = c.rb[(p0 - 1u - (unsigned) t) & c.rb_mask][lane];
-            a0 = sdb_fma2(bb, w0, a0); a1 = sdb_fma2(bb, w1, a1);
-            a2 = sdb_fma2(bb, w2, a2); a3 = sdb_fma2(bb, w3, a3);
-            w3 = w2; w2 = w1; w1 = w0; w0 = nx;
-          }
+          // tap t needs ring entry (p0 - 1 - t) mod ring: two linear runs (before / after the ring's wrap), so the
+          // loads are [pointer + immediate] instead of a mask and a shift per load (the address arithmetic was
+          // 20 of the 45 instructions of a 4-tap trip, on the one role that can fill a scheduler's issue slots)
+          const unsigned q = (p0 - 1u) & c.rb_mask;
+          const float2 *xp = &c.rb[q][lane];               // rows are 32 float2 apart
+          const float *tp = &c.taps[0][lane];
+          int t = 0;
+#define MF_TAP(o_) { const float b = tp[(o_) * 32]; const float2 bb = make_float2(b, b); const float2 nx = xp[-(o_) * 32]; \
+            a0 = sdb_fma2(bb, w0, a0); a1 = sdb_fma2(bb, w1, a1); a2 = sdb_fma2(bb, w2, a2); a3 = sdb_fma2(bb, w3, a3); \
+            w3 = w2; w2 = w1; w1 = w0; w0 = nx; }
+#define MF_RUN(end_) { _Pragma("unroll 1") for (; t + 4 <= (end_); t += 4) { MF_TAP(0) MF_TAP(1) MF_TAP(2) MF_TAP(3) xp -= 4 * 32; tp += 4 * 32; } \
+            _Pragma("unroll 1") for (; t < (end_); ++t) { MF_TAP(0) xp -= 32; tp += 32; } }
+          const int t_wrap = mf_n < (int) q + 1 ? mf_n : (int) q + 1;
+          MF_RUN(t_wrap)
+          xp += (size_t) (c.rb_mask + 1u) * 32;
+          MF_RUN(mf_n)
+#undef MF_RUN
+#undef MF_TAP
           const int j0 = part * 4;
           out[j0][lane] = a0;
           if (p0 + 1 < n) out[j0 + 1][lane] = a1;
@@ -802,17 +879,25 @@ __global__ void __launch_bounds__(INSP_WARPS * 32, 2) k_inspectors(const SdbChai
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_ns0));
 #endif
 
-  if (warp == W_TRACK) {
+  // Role of each warp.  Warps go to the SM's four schedulers by warp index modulo 4, and the matched filter is the one
+  // role that can issue every cycle (independent FFMA2s): three of its four warps share scheduler 1 among themselves,
+  // so that the recurrence warps (track, carrier -- the roles that set the CTA's pace) never compete with one for
+  // an issue slot:  scheduler 0: track, pre 0, out;  1: filter 0-2;  2: carrier, pre 1, post 0;  3: clock, post 1, filter 3
+  // (one call site per role with the part as a run-time value: a call per warp index would inline four copies of the
+  // filter role and two of pre / post, and the kernel, at 290 KB of code, ran three times slower)
+  const unsigned role = ((dyn.role_lut ? dyn.role_lut : 0x343641315230ull) >> (4 * warp)) & 15u;   // nibble w: role of warp w
+  const unsigned part = ((dyn.role_lut ? dyn.part_lut : 0x302011100000ull) >> (4 * warp)) & 15u;   //           its part
+  if (role == 0) {
     role_track(c, valid ? chan_in + (size_t) s * chan_stream_stride + chans[k].out_off : nullptr);
-  } else if (warp < W_POST) {
-    role_pre(c, warp - W_PRE);
-  } else if (warp < W_CARRIER) {
-    role_post(c, warp - W_POST);
-  } else if (warp == W_CARRIER) {
+  } else if (role == 1) {
+    role_pre(c, (int) part);
+  } else if (role == 2) {
     role_carrier(c);
-  } else if (warp < W_CLOCK) {
-    role_filter(c, warp - W_MF, taps_pool);
-  } else if (warp == W_CLOCK) {
+  } else if (role == 3) {
+    role_filter(c, (int) part, taps_pool);
+  } else if (role == 4) {
+    role_post(c, (int) part);
+  } else if (role == 5) {
     role_clock(c);
   } else {
     role_out(c, soft + (size_t) chain * sym_cap, hard + (size_t) chain * sym_cap, sym_counts + chain, sym_cap);
@@ -853,9 +938,14 @@ cudaError_t sdb_launch_inspectors_n(const SdbLaunchCtx &c, const SdbChainCfg *cf
     cudaFuncSetAttribute(k_inspectors, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
   const size_t smem = sdb_inspector_smem_bytes(dyn);
   if (!chain_map) n_ctas = (chains + 31) / 32;
+  // SDB_INSP_PLACEMENT=linear: roles in warp order (track, pre x2, post x2, carrier, filter x4, clock, out), the
+  // placement of the first builds -- kept for A/B measurements (profiles/r02_inspector.md)
+  static const bool linear = getenv("SDB_INSP_PLACEMENT") && !strcmp(getenv("SDB_INSP_PLACEMENT"), "linear");
+  SdbInspDyn d2 = dyn;
+  if (linear) { d2.role_lut = 0x653333244110ull; d2.part_lut = 0x3210010100ull; }
   k_inspectors<<<n_ctas, INSP_WARPS * 32, smem, c.stream>>>(
       cfg_dev, n_channels, n_streams, chain_map, state, pool, pool_stride, taps_pool, chans_dev, chan_in,
-      chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap, fresh, dyn);
+      chan_stream_stride, n_hops, soft, hard, sym_counts, sym_cap, fresh, d2);
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }

@@ -176,10 +176,11 @@ struct SdbInspDyn {
   int mf_rows;              // tap rows [t][lane] of the longest ring-served matched filter
   int agc_rows;             // floats per chain for the AGC delay line + magnitude history
   int use_eq;               // some chain runs the CMA equaliser
+  unsigned long long role_lut, part_lut;   // nibble w = role / part of warp w (0 = the kernel's default placement)
 };
 static inline SdbInspDyn sdb_insp_dyn(const SdbChainCfg *cfgs, int n)
 {
-  SdbInspDyn d = { 4 * SDB_INSP_CHUNK, 1, 8, 0 };   // the ring holds the chunks of the carrier, demod and filter steps
+  SdbInspDyn d = { 4 * SDB_INSP_CHUNK, 1, 8, 0, 0ull, 0ull };   // the ring holds the chunks of the carrier, demod and filter steps
   for (int k = 0; k < n; ++k) {
     const SdbChainCfg &c = cfgs[k];
     if (c.have_mf && c.mf_n <= SDB_INSP_MF_RING_MAX) {        // longer filters stay in the global pool
