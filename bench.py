@@ -728,6 +728,10 @@ def run_cuda(args):
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tr.get("workload") == name and dom in tr.get("kernels", {}):
             traffic = tr["kernels"][dom]["dram_bytes_per_launch"]
+            # the capture was taken at tr["streams_per_gpu"] streams; the inspector / inverse-transform kernels
+            # cover every stream in one launch, so their per-launch traffic scales with the stream count
+            if dom in ("inspector", "chan_ifft") and tr.get("streams_per_gpu"):
+                traffic = int(traffic * S / tr["streams_per_gpu"])
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -891,7 +895,10 @@ def main():
         # cfg2: the (latency-bound) inspector kernel of 1024 single-channel streams takes about as long as their
         # transforms; 2048 streams put the transforms on the critical path (33.9 / 53.3 / 64.5 GS/s at 512 / 1024 /
         # 2048 streams on one B200, profiles/r01_batch.md)
-        args.streams = {"cfg2": 2048, "cfg3": 148, "cfg4": 1024, "cfg5": 0}[args.workload]
+        # cfg3: 148 streams are one wave of inspector CTAs (2 per SM); with 296 the CTAs of the faster inspector
+        # classes are back-filled as they retire (15.2 / 15.8 / 16.1 / 16.1 GS/s at 148 / 222 / 296 / 444 streams,
+        # profiles/r02_summary.md)
+        args.streams = {"cfg2": 2048, "cfg3": 296, "cfg4": 1024, "cfg5": 0}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg5":

@@ -74,5 +74,38 @@ def full(path):
         print()
 
 
+def traffic(path, workload="cfg3"):
+    """Single-pass DRAM capture (dram__bytes_read/write + duration per launch) -> the JSON bench.py reads."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ki, mi, vi, ui, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+    fam_of = [("k_inspectors", "inspector"), ("k_chan_ifft", "chan_ifft"), ("k_cols256", "fft_cols"),
+              ("k_rows256<1>", "fft_rows_chan"), ("k_rows256<(int)1>", "fft_rows_chan"),
+              ("k_rows256<0>", "fft_rows_psd"), ("k_rows256<(int)0>", "fft_rows_psd"), ("k_sym_pack", "sym_pack")]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    per = collections.OrderedDict()
+    for r in data:
+        if len(r) <= vi:
+            continue
+        fam = next((f for k, f in fam_of if k in r[ki]), None)
+        if fam is None:
+            continue
+        a = per.setdefault(fam, {}).setdefault(r[ii], {})
+        a[r[mi]] = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+    out = {"workload": workload, "source": path + ": ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
+           "gpu__time_duration.sum --clock-control none --cache-control none (single pass, no replay), "
+           "bench.py --workload %s --steps 2 --warmup 3" % workload, "kernels": {}}
+    for fam, ls in per.items():
+        n = len(ls)
+        rd = sum(l.get("dram__bytes_read.sum", 0) for l in ls.values()) / n
+        wr = sum(l.get("dram__bytes_write.sum", 0) for l in ls.values()) / n
+        ms = sum(l.get("gpu__time_duration.sum", 0) for l in ls.values()) / n
+        out["kernels"][fam] = {"dram_bytes_per_launch": round(rd + wr), "read": round(rd), "write": round(wr),
+                               "launch_ms_under_ncu": round(ms, 4), "launches": n}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

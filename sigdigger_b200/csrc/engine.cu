@@ -1779,6 +1779,15 @@ extern "C" int sdb_sview_reset(sdb_sview_t *v)
   return 0;
 }
 
+int sdb_sview_reset_async(sdb_sview_t *v, cudaStream_t st)     // the same, ordered on the caller's stream
+{
+  if (!v) return fail("null view");
+  const size_t n = 65536 * sizeof(float);
+  CK(cudaMemsetAsync(v->d_psd, 0, n, st)); CK(cudaMemsetAsync(v->d_accum, 0, n, st));
+  CK(cudaMemsetAsync(v->d_count, 0, n, st));
+  return 0;
+}
+
 extern "C" int sdb_sview_set_range(sdb_sview_t *v, double fmin, double fmax, double fft_bandwidth, float rel_bw)
 {
   if (!v) return fail("null view");
@@ -1824,7 +1833,63 @@ extern "C" int sdb_sview_project(sdb_sview_t *v, const float *psd_dev, size_t ps
   return 0;
 }
 
+// ---- stream-ordered variants for the panoramic sweep (panoramic.cu): caller-owned device buffers, no host copies,
+// ---- no default-stream work.  `centers_dev` holds the hop centres on the device.
+cudaError_t sdb_launch_sview_project_tiled(cudaStream_t s, double freq_min, double freq_range, double fft_bandwidth,
+                                           float rel_bw, unsigned spectrum_size, const float *psd, size_t psd_size,
+                                           size_t hop_stride, int psd_is_linear, const double *centers_dev, int n_hops,
+                                           int adjust_sides, int *j0, int *nb, float *va, float *vc, int max_bins);
+// psd_dev: hop h's frame at psd_dev + h * hop_stride; psd_is_linear: the engine's linear natural-order PSD (the
+// PSDMessage conversion happens inside the projection) instead of shifted dB.  Returns 1 when the geometry needs the
+// general kernel (histogram mode or a very wide hop): the caller then converts and calls with psd_is_linear = 0.
+int sdb_sview_project_async(sdb_sview_t *v, cudaStream_t st, const float *psd_dev, size_t psd_size, size_t hop_stride,
+                            int psd_is_linear, const double *centers_dev, size_t n_hops, int adjust_sides, int32_t *j0,
+                            int32_t *nb, float *va, float *vc)
+{
+  if (!v || !psd_dev || !centers_dev || !j0 || !nb || !va || !vc) return fail("null argument");
+  if (v->max_bins <= 0) return fail("set_range first");
+  const bool linear_mode = v->fft_bandwidth / v->freq_range * v->spectrum_size >= 2.001;  // every hop, with margin
+                                                                                              // for the kernel's own test
+  if (linear_mode && v->max_bins <= 384) {
+    CK(sdb_launch_sview_project_tiled(st, v->freq_min, v->freq_range, v->fft_bandwidth, v->rel_bw, v->spectrum_size,
+                                      psd_dev, psd_size, hop_stride, psd_is_linear, centers_dev, (int) n_hops,
+                                      adjust_sides, j0, nb, va, vc, v->max_bins));
+    return 0;
+  }
+  if (psd_is_linear || hop_stride != psd_size) return 1;
+  CK(sdb_launch_sview_project(st, v->freq_min, v->freq_range, v->fft_bandwidth, v->rel_bw, v->spectrum_size, psd_dev,
+                              psd_size, centers_dev, (int) n_hops, adjust_sides, j0, nb, va, vc, v->max_bins));
+  return 0;
+}
+
+int sdb_sview_accumulate_async(sdb_sview_t *v, cudaStream_t st, const int32_t *j0, const int32_t *nb, const float *va,
+                               const float *vc, size_t n_hops)
+{
+  if (!v) return fail("null view");
+  CK(sdb_launch_sview_accumulate(st, v->spectrum_size, j0, nb, va, vc, (int) n_hops, v->max_bins, v->d_psd, v->d_accum,
+                                 v->d_count, v->d_count_snap));
+  return 0;
+}
+
+cudaError_t sdb_chdet_pack_device(sdb_chdet_t *d, double samp_rate, const double *centers_dev, sdb_detected_channel *out_dev,
+                                  size_t cap, int *counts_dev, cudaStream_t stream);
+// channel lists of the last feed, converted to Hz on the device (sdb_engine_read_all_channels without the host)
+int sdb_engine_pack_channels_device(sdb_engine_t *e, const double *centers_dev, sdb_detected_channel *out_dev, size_t cap,
+                                    int *counts_dev, cudaStream_t st)
+{
+  if (!e || !e->committed || !e->chdet) return fail("channel detector not enabled");
+  CK(sdb_chdet_pack_device(e->chdet, e->samp_rate, centers_dev, out_dev, cap, counts_dev, st));
+  return 0;
+}
+
 cudaError_t sdb_launch_psd_shift_db(cudaStream_t s, const float *lin, float *db, size_t n_frames, unsigned n);
+int sdb_psd_shift_db_async(cudaStream_t st, const float *lin_dev, float *db_dev, size_t n_frames, uint32_t psd_size)
+{
+  if (!lin_dev || !db_dev || lin_dev == db_dev) return fail("invalid argument");
+  CK(sdb_launch_psd_shift_db(st, lin_dev, db_dev, n_frames, psd_size));
+  return 0;
+}
+
 
 extern "C" int sdb_psd_shift_db_device(const float *lin_dev, float *db_dev, size_t n_frames, uint32_t psd_size)
 {

@@ -63,6 +63,17 @@ void shard(size_t n_hops, int world, int rank, size_t *lo, size_t *hi)
 }
 }  // namespace
 
+// One rank's outputs of a sweep, section by section (rows = hops of the shard):
+//   j0[rows] i32 | nb[rows] i32 | va[rows][mb] f32 | vc[rows][mb] f32 | ccnt[rows] i32 | chan[rows][cap]   (last two: detector)
+// Rank 0 owns the GLOBAL arrays ([n_hops] rows, hop order) and writes its own shard straight into rows [0, hi_0);
+// the peers own arrays of their shard's size and send them section by section to the rows [lo_r, hi_r) of rank 0
+// (one NCCL group of ncclSend / ncclRecv): nothing is unpacked or copied after the gather.
+struct HopLists {
+  int32_t *j0 = nullptr, *nb = nullptr; float *va = nullptr, *vc = nullptr;
+  int32_t *ccnt = nullptr; sdb_detected_channel *chan = nullptr;
+  size_t rows = 0;
+};
+
 struct sdb_panoramic {
   sdb_panoramic_params prm;
   int rank = 0, world = 1;
@@ -70,13 +81,13 @@ struct sdb_panoramic {
   cudaStream_t stream = nullptr;
   sdb_engine_t *eng = nullptr; size_t eng_hops = 0;
   sdb_sview_t *view = nullptr;
-  // packed exchange buffers: one row block per rank, pl rows each
-  size_t pl = 0, mb = 0, row_bytes = 0;
-  unsigned char *d_send = nullptr, *d_recv = nullptr; size_t send_cap = 0, recv_cap = 0;
-  std::vector<unsigned char> h_pack;
+  size_t mb = 0;
+  HopLists lists;
+  double *d_centers = nullptr; size_t centers_cap = 0;
   float *d_db = nullptr; size_t db_cap = 0;
-  int32_t *d_j0 = nullptr, *d_nb = nullptr; float *d_va = nullptr, *d_vc = nullptr; size_t lists_cap = 0;
-  std::vector<std::vector<sdb_detected_channel>> channels;   // rank 0: per hop, after a sweep with the detector
+  // rank 0, detector: the gathered channel lists land in pinned host memory behind ev_chan
+  int32_t *h_ccnt = nullptr; sdb_detected_channel *h_chan = nullptr; size_t h_rows = 0, n_hops_last = 0;
+  cudaEvent_t ev_chan = nullptr, ev_eng = nullptr; bool chan_pending = false;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   sdb_panoramic_timing last{};
 };
@@ -113,6 +124,8 @@ extern "C" sdb_panoramic_t *sdb_panoramic_new(const sdb_panoramic_params *p, int
   }
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   for (auto &e : s->ev) cudaEventCreate(&e);
+  cudaEventCreateWithFlags(&s->ev_chan, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&s->ev_eng, cudaEventDisableTiming);
   s->view = sdb_sview_new(p->device);
   if (!s->view || sdb_sview_set_range(s->view, p->freq_min, p->freq_max, p->fft_bandwidth, p->rel_bw > 0 ? p->rel_bw : 0.5f)) {
     g_perr = "SpectrumView set-up failed"; sdb_panoramic_destroy(s); return nullptr;
@@ -121,42 +134,67 @@ extern "C" sdb_panoramic_t *sdb_panoramic_new(const sdb_panoramic_params *p, int
   return s;
 }
 
+static void free_lists(HopLists &l)
+{
+  cudaFree(l.j0); cudaFree(l.nb); cudaFree(l.va); cudaFree(l.vc); cudaFree(l.ccnt); cudaFree(l.chan);
+  l = HopLists();
+}
+
 extern "C" void sdb_panoramic_destroy(sdb_panoramic_t *s)
 {
   if (!s) return;
   cudaSetDevice(s->prm.device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
   if (s->eng) sdb_engine_destroy(s->eng);
   if (s->view) sdb_sview_destroy(s->view);
-  cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_db);
-  cudaFree(s->d_j0); cudaFree(s->d_nb); cudaFree(s->d_va); cudaFree(s->d_vc);
+  free_lists(s->lists);
+  cudaFree(s->d_centers); cudaFree(s->d_db);
+  cudaFreeHost(s->h_ccnt); cudaFreeHost(s->h_chan);
   for (auto &e : s->ev) if (e) cudaEventDestroy(e);
+  if (s->ev_chan) cudaEventDestroy(s->ev_chan);
+  if (s->ev_eng) cudaEventDestroy(s->ev_eng);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
 
-// layout of one rank's packed block (pl rows): j0[pl] i32 | nb[pl] i32 | va[pl][mb] f32 | vc[pl][mb] f32
-//                                              | ccnt[pl] i32 | chan[pl][cap] sdb_detected_channel   (detector only)
-static size_t block_bytes(const sdb_panoramic *s)
-{
-  size_t b = s->pl * (2 * sizeof(int32_t) + 2 * s->mb * sizeof(float));
-  if (s->prm.detect) b += s->pl * (sizeof(int32_t) + (size_t) s->prm.channel_cap * sizeof(sdb_detected_channel));
-  return (b + 15) & ~(size_t) 15;
-}
+// stream-ordered pieces of engine.cu / chdet_kernels.cu (same library, not part of the C-ABI)
+int sdb_sview_project_async(sdb_sview_t *v, cudaStream_t st, const float *psd_dev, size_t psd_size, size_t hop_stride,
+                            int psd_is_linear, const double *centers_dev, size_t n_hops, int adjust_sides, int32_t *j0,
+                            int32_t *nb, float *va, float *vc);
+int sdb_sview_accumulate_async(sdb_sview_t *v, cudaStream_t st, const int32_t *j0, const int32_t *nb, const float *va,
+                               const float *vc, size_t n_hops);
+int sdb_engine_pack_channels_device(sdb_engine_t *e, const double *centers_dev, sdb_detected_channel *out_dev, size_t cap,
+                                    int *counts_dev, cudaStream_t st);
+int sdb_psd_shift_db_async(cudaStream_t st, const float *lin_dev, float *db_dev, size_t n_frames, uint32_t psd_size);
 
 static int ensure(sdb_panoramic *s, size_t n_hops, size_t n_local)
 {
-  s->pl = (n_hops + (size_t) s->world - 1) / (size_t) s->world;
-  const size_t bb = block_bytes(s);
-  if (s->send_cap < bb) { cudaFree(s->d_send); PCK(cudaMalloc(&s->d_send, bb)); s->send_cap = bb; }
-  if (s->rank == 0 && s->recv_cap < bb * (size_t) s->world) {
-    cudaFree(s->d_recv); PCK(cudaMalloc(&s->d_recv, bb * (size_t) s->world)); s->recv_cap = bb * (size_t) s->world;
+  const size_t rows = s->rank == 0 ? n_hops : n_local, mb = s->mb, cap = s->prm.channel_cap;
+  if (s->lists.rows < rows) {
+    PCK(cudaStreamSynchronize(s->stream));
+    free_lists(s->lists);
+    HopLists &l = s->lists;
+    PCK(cudaMalloc(&l.j0, rows * sizeof(int32_t))); PCK(cudaMalloc(&l.nb, rows * sizeof(int32_t)));
+    PCK(cudaMalloc(&l.va, rows * mb * sizeof(float))); PCK(cudaMalloc(&l.vc, rows * mb * sizeof(float)));
+    if (s->prm.detect) {
+      PCK(cudaMalloc(&l.ccnt, rows * sizeof(int32_t)));
+      PCK(cudaMalloc(&l.chan, rows * cap * sizeof(sdb_detected_channel)));
+    }
+    l.rows = rows;
   }
-  if (s->rank == 0 && s->lists_cap < n_hops) {
-    cudaFree(s->d_j0); cudaFree(s->d_nb); cudaFree(s->d_va); cudaFree(s->d_vc);
-    PCK(cudaMalloc(&s->d_j0, n_hops * sizeof(int32_t))); PCK(cudaMalloc(&s->d_nb, n_hops * sizeof(int32_t)));
-    PCK(cudaMalloc(&s->d_va, n_hops * s->mb * sizeof(float))); PCK(cudaMalloc(&s->d_vc, n_hops * s->mb * sizeof(float)));
-    s->lists_cap = n_hops;
+  if (s->centers_cap < n_hops) {
+    PCK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_centers); s->d_centers = nullptr;
+    PCK(cudaMalloc(&s->d_centers, n_hops * sizeof(double)));
+    s->centers_cap = n_hops;
+  }
+  if (s->rank == 0 && s->prm.detect && s->h_rows < n_hops) {
+    PCK(cudaStreamSynchronize(s->stream));
+    cudaFreeHost(s->h_ccnt); cudaFreeHost(s->h_chan); s->h_ccnt = nullptr; s->h_chan = nullptr;
+    PCK(cudaMallocHost(&s->h_ccnt, n_hops * sizeof(int32_t)));
+    PCK(cudaMallocHost(&s->h_chan, n_hops * cap * sizeof(sdb_detected_channel)));
+    s->h_rows = n_hops;
   }
   if (n_local && (!s->eng || s->eng_hops != n_local)) {
     if (s->eng) sdb_engine_destroy(s->eng);
@@ -172,14 +210,14 @@ static int ensure(sdb_panoramic *s, size_t n_hops, size_t n_local)
       return pfail(sdb_last_error());
     if (sdb_engine_commit(s->eng)) return pfail(sdb_last_error());
     s->eng_hops = n_local;
-    if ((s->prm.detect || s->prm.frames_per_hop > 1) && s->db_cap < n_local * s->prm.psd_size) {
-      cudaFree(s->d_db); PCK(cudaMalloc(&s->d_db, n_local * s->prm.psd_size * sizeof(float))); s->db_cap = n_local * s->prm.psd_size;
-    }
   }
   return 0;
 }
 
-// hops_local: this rank's contiguous shard [hi - lo][psd_size] (device pointer if on_device), one window per hop
+// hops_local: this rank's contiguous shard [hi - lo][psd_size] (device pointer if on_device), one window per hop.
+// Everything between the first and the last event is queued on streams: the engine's feed (its own streams), then
+// on s->stream behind an event the dB pass, the projection, the channel-list conversion, the NCCL group and rank 0's
+// accumulate + fill.  The host blocks once, at the end, for the phase times.
 static int sweep_impl(sdb_panoramic *s, const sdb_complex *hops_local, int on_device, const double *centers_all,
                       size_t n_hops)
 {
@@ -187,99 +225,91 @@ static int sweep_impl(sdb_panoramic *s, const sdb_complex *hops_local, int on_de
   PCK(cudaSetDevice(s->prm.device));
   size_t lo, hi;
   shard(n_hops, s->world, s->rank, &lo, &hi);
-  const size_t n_local = hi - lo, N = s->prm.psd_size;
+  const size_t n_local = hi - lo, N = s->prm.psd_size, mb = s->mb, cap = s->prm.channel_cap;
   if (n_local && !hops_local) return pfail("null hop buffer");
   if (ensure(s, n_hops, n_local)) return -1;
-  const size_t bb = block_bytes(s), pl = s->pl, mb = s->mb;
-  PCK(cudaEventRecord(s->ev[0], s->stream));
-  PCK(cudaMemsetAsync(s->d_send, 0, bb, s->stream));
-  int32_t *sj0 = (int32_t *) s->d_send, *snb = sj0 + pl;
-  float *sva = (float *) (snb + pl), *svc = sva + pl * mb;
-  int32_t *scnt = (int32_t *) (svc + pl * mb);
-  sdb_detected_channel *sch = (sdb_detected_channel *) (scnt + pl);
-  PCK(cudaStreamSynchronize(s->stream));
+  cudaStream_t st = s->stream;
+  HopLists &l = s->lists;
+  const size_t row0 = s->rank == 0 ? lo : 0;          // rank 0 writes into the global arrays (lo = 0 there)
+  PCK(cudaEventRecord(s->ev[0], st));
+  PCK(cudaMemcpyAsync(s->d_centers, centers_all, n_hops * sizeof(double), cudaMemcpyHostToDevice, st));
   if (n_local) {
     // frames_per_hop > 1: the detector averages over the hop's frames, the view takes the last one
     const size_t F = s->prm.frames_per_hop ? s->prm.frames_per_hop : 1, L = N * F;
     if (on_device ? sdb_engine_feed_device(s->eng, hops_local, L, L) : sdb_engine_feed_host(s->eng, hops_local, L, L))
       return pfail(sdb_last_error());
-    if (sdb_engine_sync(s->eng)) return pfail(sdb_last_error());
-    const float *psd = sdb_engine_psd_device(s->eng);
-    if (s->prm.detect) {
-      if (F == 1) {
-        if (sdb_psd_shift_db_device(psd, s->d_db, n_local, (uint32_t) N)) return pfail(sdb_last_error());
-      } else {
-        for (size_t h = 0; h < n_local; ++h)
-          if (sdb_psd_shift_db_device(psd + (h * F + F - 1) * N, s->d_db + h * N, 1, (uint32_t) N)) return pfail(sdb_last_error());
+    if (sdb_engine_join(s->eng)) return pfail(sdb_last_error());
+    PCK(cudaEventRecord(s->ev_eng, (cudaStream_t) sdb_engine_stream(s->eng)));
+    PCK(cudaStreamWaitEvent(st, s->ev_eng, 0));
+    // the view takes the hop's last frame; with the detector on, the engine keeps the linear PSD and the projection
+    // converts what it reads (fftshift + dB, Suscan/Messages/PSDMessage.cpp:32-38)
+    const float *psd = sdb_engine_psd_device(s->eng) + (F - 1) * N;
+    int rc = sdb_sview_project_async(s->view, st, psd, N, L, s->prm.detect ? 1 : 0, s->d_centers + lo, n_local, 1,
+                                     l.j0 + row0, l.nb + row0, l.va + row0 * mb, l.vc + row0 * mb);
+    if (rc == 1) {
+      // geometry outside the tiled kernel (a hop narrower than two view bins, or very wide): dB frames, contiguous
+      if (s->db_cap < n_local * N) {
+        PCK(cudaStreamSynchronize(st));
+        cudaFree(s->d_db); s->d_db = nullptr;
+        PCK(cudaMalloc(&s->d_db, n_local * N * sizeof(float))); s->db_cap = n_local * N;
       }
-      psd = s->d_db;
-    } else if (F > 1) {
-      PCK(cudaMemcpy2D(s->d_db, N * sizeof(float), psd + (F - 1) * N, L * sizeof(float), N * sizeof(float), n_local,
-                       cudaMemcpyDeviceToDevice));
-      psd = s->d_db;
+      if (s->prm.detect) {
+        for (size_t h = 0; h < (F == 1 ? 1 : n_local); ++h)
+          if (sdb_psd_shift_db_async(st, psd + h * L, s->d_db + h * N, F == 1 ? n_local : 1, (uint32_t) N))
+            return pfail(sdb_last_error());
+      } else {
+        PCK(cudaMemcpy2DAsync(s->d_db, N * sizeof(float), psd, L * sizeof(float), N * sizeof(float), n_local,
+                              cudaMemcpyDeviceToDevice, st));
+      }
+      rc = sdb_sview_project_async(s->view, st, s->d_db, N, N, 0, s->d_centers + lo, n_local, 1, l.j0 + row0,
+                                   l.nb + row0, l.va + row0 * mb, l.vc + row0 * mb);
     }
-    if (sdb_sview_project(s->view, psd, N, centers_all + lo, n_local, 1)) return pfail(sdb_last_error());
-    if (sdb_sview_contrib_copy(s->view, sj0, snb, sva, svc, n_local)) return pfail(sdb_last_error());
-    if (s->prm.detect) {
-      const size_t cap = s->prm.channel_cap;
-      std::vector<int32_t> cnt(pl, 0);
-      std::vector<sdb_detected_channel> ch(pl * cap);
-      if (sdb_engine_read_all_channels(s->eng, centers_all + lo, ch.data(), cap, (uint32_t *) cnt.data()))
-        return pfail(sdb_last_error());
-      PCK(cudaMemcpy(scnt, cnt.data(), pl * sizeof(int32_t), cudaMemcpyHostToDevice));
-      PCK(cudaMemcpy(sch, ch.data(), pl * cap * sizeof(sdb_detected_channel), cudaMemcpyHostToDevice));
-    }
+    if (rc) return pfail(rc == 1 ? "projection geometry not supported" : sdb_last_error());
+    if (s->prm.detect &&
+        sdb_engine_pack_channels_device(s->eng, s->d_centers + lo, l.chan + row0 * cap, cap, l.ccnt + row0, st))
+      return pfail(sdb_last_error());
   }
-  PCK(cudaDeviceSynchronize());
-  PCK(cudaEventRecord(s->ev[1], s->stream));
-  // ---- the one exchange of the path: gather the packed blocks on rank 0
+  PCK(cudaEventRecord(s->ev[1], st));
+  // ---- the one exchange of the path: every peer's sections go to their rows of rank 0's global arrays
+  uint64_t gathered = 0;
   if (s->world > 1) {
     NCK(g_nccl.GroupStart());
-    if (s->rank == 0) {
-      for (int r = 1; r < s->world; ++r)
-        NCK(g_nccl.Recv(s->d_recv + (size_t) r * bb, bb, ncclUint8, r, s->comm, s->stream));
-    } else {
-      NCK(g_nccl.Send(s->d_send, bb, ncclUint8, 0, s->comm, s->stream));
+    for (int r = 1; r < s->world; ++r) {
+      if (s->rank != 0 && s->rank != r) continue;
+      size_t rlo, rhi;
+      shard(n_hops, s->world, r, &rlo, &rhi);
+      const size_t cnt = rhi - rlo, at = s->rank == 0 ? rlo : 0;
+      if (!cnt) continue;
+      struct { void *p; size_t bytes; } sec[6] = {
+        { l.j0 + at, cnt * sizeof(int32_t) }, { l.nb + at, cnt * sizeof(int32_t) },
+        { l.va + at * mb, cnt * mb * sizeof(float) }, { l.vc + at * mb, cnt * mb * sizeof(float) },
+        { s->prm.detect ? (void *) (l.ccnt + at) : nullptr, cnt * sizeof(int32_t) },
+        { s->prm.detect ? (void *) (l.chan + at * cap) : nullptr, cnt * cap * sizeof(sdb_detected_channel) } };
+      for (auto &q : sec) {
+        if (!q.p) continue;
+        if (s->rank == 0) { NCK(g_nccl.Recv(q.p, q.bytes, ncclUint8, r, s->comm, st)); gathered += q.bytes; }
+        else NCK(g_nccl.Send(q.p, q.bytes, ncclUint8, 0, s->comm, st));
+      }
     }
     NCK(g_nccl.GroupEnd());
   }
-  if (s->rank == 0) PCK(cudaMemcpyAsync(s->d_recv, s->d_send, bb, cudaMemcpyDeviceToDevice, s->stream));
-  PCK(cudaEventRecord(s->ev[2], s->stream));
-  PCK(cudaStreamSynchronize(s->stream));
-  s->last.gather_bytes = s->world > 1 ? (uint64_t) bb * (uint64_t) (s->world - 1) : 0;
+  PCK(cudaEventRecord(s->ev[2], st));
+  s->last.gather_bytes = gathered;
   if (s->rank == 0) {
-    // unpack in rank order = global hop order, then accumulate + fill exactly as one sequential feed() series
-    size_t row = 0;
-    if (s->prm.detect) s->channels.assign(n_hops, {});
-    for (int r = 0; r < s->world; ++r) {
-      size_t rlo, rhi;
-      shard(n_hops, s->world, r, &rlo, &rhi);
-      const size_t cnt = rhi - rlo;
-      if (!cnt) continue;
-      const unsigned char *blk = s->d_recv + (size_t) r * bb;
-      const int32_t *bj0 = (const int32_t *) blk, *bnb = bj0 + pl;
-      const float *bva = (const float *) (bnb + pl), *bvc = bva + pl * mb;
-      PCK(cudaMemcpyAsync(s->d_j0 + row, bj0, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, s->stream));
-      PCK(cudaMemcpyAsync(s->d_nb + row, bnb, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, s->stream));
-      PCK(cudaMemcpyAsync(s->d_va + row * mb, bva, cnt * mb * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-      PCK(cudaMemcpyAsync(s->d_vc + row * mb, bvc, cnt * mb * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-      if (s->prm.detect) {
-        const size_t cap = s->prm.channel_cap;
-        std::vector<int32_t> c(cnt); std::vector<sdb_detected_channel> ch(cnt * cap);
-        const int32_t *bcnt = (const int32_t *) (bvc + pl * mb);
-        const sdb_detected_channel *bch = (const sdb_detected_channel *) (bcnt + pl);
-        PCK(cudaMemcpy(c.data(), bcnt, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        PCK(cudaMemcpy(ch.data(), bch, cnt * cap * sizeof(sdb_detected_channel), cudaMemcpyDeviceToHost));
-        for (size_t h = 0; h < cnt; ++h) s->channels[row + h].assign(&ch[h * cap], &ch[h * cap] + c[h]);
-      }
-      row += cnt;
+    // rows are in global hop order already: accumulate + fill exactly as one sequential feed() series
+    if (sdb_sview_accumulate_async(s->view, st, l.j0, l.nb, l.va, l.vc, n_hops)) return pfail(sdb_last_error());
+    if (s->prm.detect) {
+      PCK(cudaMemcpyAsync(s->h_ccnt, l.ccnt, n_hops * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      PCK(cudaMemcpyAsync(s->h_chan, l.chan, n_hops * cap * sizeof(sdb_detected_channel), cudaMemcpyDeviceToHost, st));
+      PCK(cudaEventRecord(s->ev_chan, st));
+      s->chan_pending = true;
     }
-    PCK(cudaStreamSynchronize(s->stream));
-    if (sdb_sview_accumulate(s->view, s->d_j0, s->d_nb, s->d_va, s->d_vc, n_hops)) return pfail(sdb_last_error());
-    PCK(cudaDeviceSynchronize());
+    s->n_hops_last = n_hops;
   }
-  PCK(cudaEventRecord(s->ev[3], s->stream));
+  PCK(cudaEventRecord(s->ev[3], st));
   PCK(cudaEventSynchronize(s->ev[3]));
+  s->chan_pending = false;
+  if (n_local && sdb_engine_sync(s->eng)) return pfail(sdb_last_error());
   float a = 0, b = 0, c = 0;
   cudaEventElapsedTime(&a, s->ev[0], s->ev[1]); cudaEventElapsedTime(&b, s->ev[1], s->ev[2]); cudaEventElapsedTime(&c, s->ev[2], s->ev[3]);
   s->last.psd_project_ms = a; s->last.gather_ms = b; s->last.accumulate_ms = c;
@@ -294,7 +324,13 @@ extern "C" int sdb_panoramic_sweep_host(sdb_panoramic_t *s, const sdb_complex *h
                                         size_t n_hops)
 { return sweep_impl(s, hops_local, 0, centers_all, n_hops); }
 
-extern "C" int sdb_panoramic_reset(sdb_panoramic_t *s) { return s ? sdb_sview_reset(s->view) : pfail("null"); }
+int sdb_sview_reset_async(sdb_sview_t *v, cudaStream_t st);
+extern "C" int sdb_panoramic_reset(sdb_panoramic_t *s)
+{
+  if (!s) return pfail("null");
+  if (cudaSetDevice(s->prm.device) != cudaSuccess) return pfail("cudaSetDevice failed");
+  return sdb_sview_reset_async(s->view, s->stream) ? pfail(sdb_last_error()) : 0;
+}
 extern "C" int sdb_panoramic_read(sdb_panoramic_t *s, float *psd, float *accum, float *count, size_t cap)
 {
   if (!s) return pfail("null");
@@ -304,9 +340,10 @@ extern "C" int sdb_panoramic_read(sdb_panoramic_t *s, float *psd, float *accum, 
 extern "C" uint32_t sdb_panoramic_size(const sdb_panoramic_t *s) { return s ? sdb_sview_size(s->view) : 0; }
 extern "C" long sdb_panoramic_read_channels(sdb_panoramic_t *s, size_t hop, sdb_detected_channel *out, size_t cap)
 {
-  if (!s || s->rank != 0 || hop >= s->channels.size()) return -1;
-  const size_t n = std::min(cap, s->channels[hop].size());
-  if (n && out) memcpy(out, s->channels[hop].data(), n * sizeof(sdb_detected_channel));
+  if (!s || s->rank != 0 || !s->prm.detect || hop >= s->n_hops_last || !s->h_ccnt) return -1;
+  if (s->chan_pending) { cudaEventSynchronize(s->ev_chan); s->chan_pending = false; }
+  const size_t n = std::min(cap, (size_t) s->h_ccnt[hop]);
+  if (n && out) memcpy(out, s->h_chan + hop * s->prm.channel_cap, n * sizeof(sdb_detected_channel));
   return (long) n;
 }
 extern "C" int sdb_panoramic_last_timing(const sdb_panoramic_t *s, sdb_panoramic_timing *t)
