@@ -645,6 +645,47 @@ const char *sdb_panoramic_last_error(void);
  * feed(previous)).  Both views on the same device. */
 int      sdb_sview_feed_view(sdb_sview_t *v, const sdb_sview_t *detail);
 
+/* ------------------------------------------------------------------------------------------------
+ * Analog-TV processor of the inspector's TV tab (SPEC.md section TV), a batch of processors,
+ * one warp each.  sdb_tv_params has the fields of struct sigutils_tv_processor_params as the reference fills them
+ * (Default/GenericInspector/TVProcessorTab.cpp:549-597; lengths in samples, time constants in their own units).
+ * The input is the TV tab's real-valued signal with the sync tips HIGH (TVProcessorTab::feed, :601-620:
+ * sdb_tv_feed_transform).  The sigutils-named per-sample interface (su_tv_processor_feed ...) is <sigutils/tvproc.h>.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t  enable_sync, reverse, interlace, enable_agc;
+  float    x_off;
+  int32_t  dominance;
+  uint32_t frame_lines;
+  float    frame_spacing;                     /* fractional lines per frame beyond frame_lines (TVProcessorTab.cpp:559) */
+  int32_t  enable_comb, comb_reverse;
+  float    hsync_len, vsync_len, line_len;    /* samples */
+  uint32_t vsync_odd_trigger;                 /* equalising pulses that end a field */
+  float    t_tol, l_tol, g_tol;
+  float    hsync_huge_err, hsync_max_err, hsync_min_err;
+  float    hsync_len_tau, line_len_tau, agc_tau, hsync_fast_track_tau, hsync_slow_track_tau;
+} sdb_tv_params;
+typedef struct sdb_tv_processor sdb_tv_processor_t;
+/* su_tv_processor_params_pal / _ntsc (TVProcessorTab.cpp:629,633) */
+void sdb_tv_params_pal(sdb_tv_params *p, float samp_rate);
+void sdb_tv_params_ntsc(sdb_tv_params *p, float samp_rate);
+/* su_tv_processor_new / _destroy / _set_params (TVProcessorWorker.cpp:204, :175, :222) */
+sdb_tv_processor_t *sdb_tv_processor_new(const sdb_tv_params *p, uint32_t batch, int device);
+void sdb_tv_processor_destroy(sdb_tv_processor_t *t);
+int  sdb_tv_processor_set_params(sdb_tv_processor_t *t, const sdb_tv_params *p);
+int  sdb_tv_processor_geometry(const sdb_tv_processor_t *t, uint32_t *width, uint32_t *height);
+/* TVProcessorWorker::work (TVProcessorWorker.cpp:120-151) over the batch: x[batch][stride], n samples each;
+ * frames_done[batch]; returns the frames completed in this call (-1 on error) */
+long sdb_tv_processor_feed(sdb_tv_processor_t *t, const float *x, size_t stride, size_t n, uint32_t *frames_done);
+long sdb_tv_processor_feed_device(sdb_tv_processor_t *t, const float *x_dev, size_t stride, size_t n, uint32_t *frames_done);
+int  sdb_tv_processor_frames(sdb_tv_processor_t *t, uint64_t *counts);
+/* su_tv_processor_take_frame (TVProcessorWorker.cpp:143): completed frame `frame_no` of processor `which`,
+ * [height][width] floats (0 = black ... 1 = white before contrast / brightness) */
+int  sdb_tv_processor_read_frame(sdb_tv_processor_t *t, uint32_t which, uint64_t frame_no, float *out, size_t cap);
+int  sdb_tv_processor_estimates(sdb_tv_processor_t *t, uint32_t which, float *line_len, float *hsync_len, float *gain);
+/* TVProcessorTab::feed (TVProcessorTab.cpp:601-620): mode 0 = k |x| + dc, 1 = k arg(x) / pi + dc */
+int  sdb_tv_feed_transform(const sdb_complex *x, size_t n, int mode, float k, float dc, float *out);
+
 /* Offline inspector over captured channel-rate buffers (the block-wise CPU loops the GUI's TimeWindow
  * launches, Components/TimeWindow.cpp:1571-2183; sampler + decider of Tasks/WaveSampler.cpp:188-205,
  * 316-317): `batch` buffers of n samples -> soft [batch][cap], hard [batch][cap], counts [batch].

@@ -435,6 +435,41 @@ void   sdo_snr_set_bps(sdo_snr_estimator *e, unsigned bps);
 void   sdo_snr_feed(sdo_snr_estimator *e, const unsigned *history, unsigned n);
 float  sdo_snr_get(const sdo_snr_estimator *e);
 
+/* ------------------------------------------------------------------------------------------------
+ * Analog-TV processor (SPEC section TV; tvproc.c).  Field names of sdo_tv_params are those of
+ * sigutils_tv_processor_params as the reference fills them (Default/GenericInspector/TVProcessorTab.cpp:549-597).
+ * ---------------------------------------------------------------------------------------------- */
+#define SDO_TV_RING 4
+#define SDO_TV_MAX_W 4096
+#define SDO_TV_MAX_H 4096
+typedef struct {
+  int32_t  enable_sync, reverse, interlace, enable_agc;
+  float    x_off;
+  int32_t  dominance;
+  uint32_t frame_lines;
+  float    frame_spacing;
+  int32_t  enable_comb, comb_reverse;
+  float    hsync_len, vsync_len, line_len;
+  uint32_t vsync_odd_trigger;
+  float    t_tol, l_tol, g_tol;
+  float    hsync_huge_err, hsync_max_err, hsync_min_err;
+  float    hsync_len_tau, line_len_tau, agc_tau, hsync_fast_track_tau, hsync_slow_track_tau;
+} sdo_tv_params;
+typedef struct sdo_tv sdo_tv;
+void     sdo_tv_params_pal(sdo_tv_params *p, float fs);
+void     sdo_tv_params_ntsc(sdo_tv_params *p, float fs);
+int      sdo_tv_params_valid(const sdo_tv_params *p);
+sdo_tv  *sdo_tv_new(const sdo_tv_params *p);
+void     sdo_tv_destroy(sdo_tv *t);
+int      sdo_tv_set_params(sdo_tv *t, const sdo_tv_params *p);
+void     sdo_tv_geometry(const sdo_tv *t, int *w, int *h);
+int      sdo_tv_feed(sdo_tv *t, float x);
+size_t   sdo_tv_feed_bulk(sdo_tv *t, const float *x, size_t n);
+uint64_t sdo_tv_frames(const sdo_tv *t);
+const float *sdo_tv_frame(const sdo_tv *t, uint64_t frame_no);
+void     sdo_tv_estimates(const sdo_tv *t, float *line_len, float *hsync_len, float *gain);
+void     sdo_tv_feed_transform(const sdo_cpx *x, size_t n, int mode, float k, float dc, float *out);
+
 /* multi-threaded CPU baseline: S independent streams, each n samples, same params (OpenMP). */
 double sdo_baseline_run(const sdo_an_params *p, const sdo_cpx *x, size_t n_streams, size_t n,
                         int n_threads, uint64_t *checksum);

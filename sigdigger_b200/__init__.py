@@ -393,6 +393,18 @@ _PROTOS = {
     "sdb_sview_feed_view": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdb_sview_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sdb_sview_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sdb_tv_params_pal": (None, [C.c_void_p, C.c_float]),
+    "sdb_tv_params_ntsc": (None, [C.c_void_p, C.c_float]),
+    "sdb_tv_processor_new": (C.c_void_p, [C.c_void_p, C.c_uint32, C.c_int]),
+    "sdb_tv_processor_destroy": (None, [C.c_void_p]),
+    "sdb_tv_processor_set_params": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_tv_processor_geometry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdb_tv_processor_feed": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "sdb_tv_processor_feed_device": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "sdb_tv_processor_frames": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdb_tv_processor_read_frame": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "sdb_tv_processor_estimates": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdb_tv_feed_transform": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "sdb_task_inspector": (C.c_long, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t]),
 }
@@ -1016,3 +1028,79 @@ class SpectrumView:
         psd, acc, cnt = (np.empty(n, np.float32) for _ in range(3))
         _check(self._L.sdb_sview_read(self._h, psd.ctypes.data, acc.ctypes.data, cnt.ctypes.data, n))
         return psd, acc, cnt
+
+
+class TvParams(C.Structure):
+    """sdb_tv_params == struct sigutils_tv_processor_params (Default/GenericInspector/TVProcessorTab.cpp:549-597)."""
+    _fields_ = [("enable_sync", C.c_int32), ("reverse", C.c_int32), ("interlace", C.c_int32), ("enable_agc", C.c_int32),
+                ("x_off", C.c_float), ("dominance", C.c_int32), ("frame_lines", C.c_uint32),
+                ("frame_spacing", C.c_float), ("enable_comb", C.c_int32), ("comb_reverse", C.c_int32),
+                ("hsync_len", C.c_float), ("vsync_len", C.c_float), ("line_len", C.c_float),
+                ("vsync_odd_trigger", C.c_uint32), ("t_tol", C.c_float), ("l_tol", C.c_float), ("g_tol", C.c_float),
+                ("hsync_huge_err", C.c_float), ("hsync_max_err", C.c_float), ("hsync_min_err", C.c_float),
+                ("hsync_len_tau", C.c_float), ("line_len_tau", C.c_float), ("agc_tau", C.c_float),
+                ("hsync_fast_track_tau", C.c_float), ("hsync_slow_track_tau", C.c_float)]
+
+
+def tv_params(standard="pal", samp_rate=1e6, **kw):
+    p = TvParams()
+    getattr(load_library(), "sdb_tv_params_" + standard)(C.byref(p), samp_rate)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class TvProcessor:
+    """A batch of analog-TV processors (one warp each): TVProcessorWorker::work over [batch][n] float samples."""
+
+    def __init__(self, params, batch=1, device=0):
+        self._L = load_library()
+        self.batch = batch
+        self._h = self._L.sdb_tv_processor_new(C.byref(params), batch, device)
+        if not self._h:
+            raise SdbError(last_error())
+        w, h = C.c_uint32(), C.c_uint32()
+        _check(self._L.sdb_tv_processor_geometry(self._h, C.byref(w), C.byref(h)))
+        self.width, self.height = w.value, h.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sdb_tv_processor_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_params(self, params):
+        _check(self._L.sdb_tv_processor_set_params(self._h, C.byref(params)))
+
+    def feed(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.batch, -1)
+        done = np.zeros(self.batch, np.uint32)
+        rc = self._L.sdb_tv_processor_feed(self._h, x.ctypes.data, x.shape[1], x.shape[1], done.ctypes.data)
+        if rc < 0:
+            raise SdbError(last_error())
+        return done
+
+    def frames(self):
+        c = np.zeros(self.batch, np.uint64)
+        _check(self._L.sdb_tv_processor_frames(self._h, c.ctypes.data))
+        return c
+
+    def read_frame(self, which, frame_no):
+        out = np.empty((self.height, self.width), np.float32)
+        _check(self._L.sdb_tv_processor_read_frame(self._h, which, int(frame_no), out.ctypes.data, out.size))
+        return out
+
+    def estimates(self, which=0):
+        a, b, g = C.c_float(), C.c_float(), C.c_float()
+        _check(self._L.sdb_tv_processor_estimates(self._h, which, C.byref(a), C.byref(b), C.byref(g)))
+        return a.value, b.value, g.value
+
+
+def tv_feed_transform(x, mode, k=1.0, dc=0.0):
+    """TVProcessorTab::feed: mode "modulus" -> k |x| + dc, "argument" -> k arg(x) / pi + dc."""
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    out = np.empty(x.size, np.float32)
+    _check(load_library().sdb_tv_feed_transform(x.ctypes.data, x.size, {"modulus": 0, "argument": 1}[mode], k, dc,
+                                                out.ctypes.data))
+    return out

@@ -29,6 +29,7 @@ static int fail(const std::string &m) { g_err = m; return -1; }
   g_err = std::string(#expr) + ": " + cudaGetErrorString(e__); return nullptr; } } while (0)
 
 extern "C" const char *sdb_last_error(void) { return g_err.c_str(); }
+int sdb_set_error(const char *m) { g_err = m ? m : ""; return -1; }     // other units of the library (tv_kernels.cu)
 
 extern "C" int sdb_device_count(void)
 {

@@ -21,8 +21,10 @@
 #include <sigutils/taps.h>
 #include <sigutils/specttuner.h>
 #include <sigutils/version.h>
+#include <sigutils/tvproc.h>
 
 #include "sdb_chain_steps.h"
+#include "sdb_tv_steps.h"
 #include "host_design.h"
 
 #include <stdlib.h>
@@ -490,5 +492,96 @@ void su_specttuner_destroy(su_specttuner_t *st)
   if (st->eng) sdb_engine_destroy(st->eng);
   delete st;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// <sigutils/tvproc.h>: the TV tab's processor, per-sample on the caller's thread (TVProcessorWorker::work)
+// ---------------------------------------------------------------------------------------------------------
+struct sigutils_tv_processor {
+  struct sigutils_tv_processor_params prm;
+  SdbTvCfg cfg; SdbTvState st;
+  std::vector<float> delay, line, ring;          // ring: SDB_TV_RING frames of H x W
+  struct sigutils_tv_frame_buffer *pool = nullptr;
+};
+
+void su_tv_processor_params_pal(struct sigutils_tv_processor_params *p, SUFLOAT samp_rate) { if (p) sdb_tv_preset(*p, samp_rate, true); }
+void su_tv_processor_params_ntsc(struct sigutils_tv_processor_params *p, SUFLOAT samp_rate) { if (p) sdb_tv_preset(*p, samp_rate, false); }
+
+su_tv_processor_t *su_tv_processor_new(const struct sigutils_tv_processor_params *p)
+{
+  if (!p || !sdb_tv_params_valid(*p)) return nullptr;
+  su_tv_processor_t *t = new sigutils_tv_processor();
+  t->prm = *p;
+  sdb_tv_derive(*p, t->cfg);
+  sdb_tv_state_init(t->cfg, t->st);
+  t->delay.assign((size_t) t->cfg.delay_len, 0.0f);
+  t->line.assign((size_t) t->cfg.W, 0.0f);
+  t->ring.assign((size_t) SDB_TV_RING * t->cfg.W * t->cfg.H, 0.0f);
+  return t;
+}
+
+SUBOOL su_tv_processor_set_params(su_tv_processor_t *t, const struct sigutils_tv_processor_params *p)
+{
+  if (!t || !p || !sdb_tv_params_valid(*p)) return SU_FALSE;
+  SdbTvCfg c; sdb_tv_derive(*p, c);
+  if (c.W != t->cfg.W || c.delay_len != t->cfg.delay_len || c.H != t->cfg.H || c.interlace != t->cfg.interlace)
+    return SU_FALSE;                             // the caller stops / starts the processor for a new geometry
+  t->prm = *p; t->cfg = c;
+  return SU_TRUE;
+}
+
+SUBOOL su_tv_processor_feed(su_tv_processor_t *t, SUFLOAT x)
+{
+  int row = -1, slot = 0;
+  const int flags = sdb_tv_step(t->cfg, t->st, t->delay.data(), t->line.data(), x, &row, &slot);
+  if (flags & SDB_TV_LINE_DONE) {
+    const size_t W = (size_t) t->cfg.W;
+    if (row >= 0) memcpy(t->ring.data() + ((size_t) slot * t->cfg.H + (size_t) row) * W, t->line.data(), W * sizeof(float));
+    memset(t->line.data(), 0, W * sizeof(float));
+  }
+  return (flags & SDB_TV_FRAME_DONE) ? SU_TRUE : SU_FALSE;
+}
+
+// the frame completed last, as a buffer the caller owns until su_tv_processor_return_frame / su_tv_frame_buffer_destroy
+struct sigutils_tv_frame_buffer *su_tv_processor_take_frame(su_tv_processor_t *t)
+{
+  if (!t || t->st.frames == 0) return nullptr;
+  const size_t px = (size_t) t->cfg.W * t->cfg.H;
+  struct sigutils_tv_frame_buffer *f = t->pool;
+  if (f) t->pool = f->next;
+  else {
+    f = (struct sigutils_tv_frame_buffer *) calloc(1, sizeof(*f));
+    if (!f) return nullptr;
+    f->buffer = (SUFLOAT *) malloc(px * sizeof(SUFLOAT));
+    if (!f->buffer) { free(f); return nullptr; }
+  }
+  f->width = t->cfg.W; f->height = t->cfg.H; f->next = nullptr;
+  memcpy(f->buffer, t->ring.data() + (size_t) ((t->st.frames - 1) % SDB_TV_RING) * px, px * sizeof(SUFLOAT));
+  return f;
+}
+
+void su_tv_frame_buffer_destroy(struct sigutils_tv_frame_buffer *f)
+{
+  if (!f) return;
+  free(f->buffer); free(f);
+}
+
+void su_tv_processor_return_frame(su_tv_processor_t *t, struct sigutils_tv_frame_buffer *f)
+{
+  if (!f) return;
+  if (!t || f->width != t->cfg.W || f->height != t->cfg.H) { su_tv_frame_buffer_destroy(f); return; }
+  f->next = t->pool; t->pool = f;
+}
+
+void su_tv_processor_destroy(su_tv_processor_t *t)
+{
+  if (!t) return;
+  while (t->pool) { struct sigutils_tv_frame_buffer *n = t->pool->next; su_tv_frame_buffer_destroy(t->pool); t->pool = n; }
+  delete t;
+}
+
+// test hooks (tests/test_oracle_tv.py): estimates and the picture in progress
+void sdb_shim_tv_estimates(const su_tv_processor_t *t, float *line_len, float *hsync_len, float *gain, unsigned long long *frames)
+{ *line_len = t->st.est_line_len; *hsync_len = t->st.est_hsync_len; *gain = t->st.agc_gain; *frames = t->st.frames; }
 
 }  // extern "C"

@@ -131,3 +131,41 @@ def multi_carrier(n, fs, carriers, noise_db=-60.0, seed=0):
         x = x + mix(s, f / fs, phase=0.1 * i) * 10 ** (amp_db / 20)
         meta.append(ref)
     return x.astype(np.complex64), meta
+
+
+def tv_composite(line_len, hsync, short, lines, interlace, n_frames, picture, amp=0.8, noise=0.0, seed=1, n_eq=5):
+    """Composite video with the sync tips HIGH (what TVProcessorTab::feed hands to the processor for a negatively
+    modulated carrier): tip 1.0, blanking 0.7, picture 0.65 (black) ... 0.1 (white), times `amp`.
+    picture[l] is sent on frame line l ([lines][C]).  Vertical intervals -- n_eq equalising pulses, n_eq broad pulses,
+    n_eq equalising pulses, half a line apart -- start at the frame start and, when interlaced, half a frame later
+    (mid-line for an odd line count).  line_len may be fractional.  Returns (float32 samples, (act0, act1)): the
+    active part of a line spans [act0, act1) samples."""
+    rng = np.random.default_rng(seed)
+    total = int(line_len * lines * n_frames) + 10
+    t = np.arange(total, dtype=np.float64)
+    frame_len = line_len * lines
+    tf = t - np.floor(t / frame_len) * frame_len
+    ln = np.floor(tf / line_len).astype(np.int64)
+    pos = tf - ln * line_len
+    y = np.full(total, 0.7)
+    act0, act1 = hsync * 2.2, line_len * 0.97
+    cols = picture.shape[1]
+    col = np.clip(((pos - act0) / (act1 - act0) * cols).astype(np.int64), 0, cols - 1)
+    pic = (pos >= act0) & (pos < act1)
+    y[pic] = 0.65 - 0.55 * picture[np.clip(ln, 0, lines - 1)[pic], col[pic]]
+    y[pos < hsync] = 1.0
+    half = line_len / 2
+    for s0 in [0.0] + ([frame_len / 2] if interlace else []):
+        m = (tf >= s0) & (tf < s0 + 3 * n_eq * half)
+        u = tf[m] - s0
+        k = np.floor(u / half).astype(np.int64)
+        hp = u - k * half
+        v = np.full(u.shape, 0.7)
+        broad = (k >= n_eq) & (k < 2 * n_eq)
+        v[(~broad) & (hp < short)] = 1.0
+        v[broad & (hp < half - hsync)] = 1.0
+        y[m] = v
+    y *= amp
+    if noise > 0:
+        y += noise * rng.standard_normal(total)
+    return y.astype(np.float32), (act0, act1)

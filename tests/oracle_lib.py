@@ -33,6 +33,18 @@ class Ncqo(C.Structure):
     _fields_ = [("phi", C.c_float), ("omega", C.c_float)]
 
 
+class TvParams(C.Structure):
+    """sdo_tv_params"""
+    _fields_ = [("enable_sync", C.c_int32), ("reverse", C.c_int32), ("interlace", C.c_int32), ("enable_agc", C.c_int32),
+                ("x_off", C.c_float), ("dominance", C.c_int32), ("frame_lines", C.c_uint32),
+                ("frame_spacing", C.c_float), ("enable_comb", C.c_int32), ("comb_reverse", C.c_int32),
+                ("hsync_len", C.c_float), ("vsync_len", C.c_float), ("line_len", C.c_float),
+                ("vsync_odd_trigger", C.c_uint32), ("t_tol", C.c_float), ("l_tol", C.c_float), ("g_tol", C.c_float),
+                ("hsync_huge_err", C.c_float), ("hsync_max_err", C.c_float), ("hsync_min_err", C.c_float),
+                ("hsync_len_tau", C.c_float), ("line_len_tau", C.c_float), ("agc_tau", C.c_float),
+                ("hsync_fast_track_tau", C.c_float), ("hsync_slow_track_tau", C.c_float)]
+
+
 class FftPlan(C.Structure):
     _fields_ = [("n", C.c_uint), ("log2n", C.c_uint), ("tw_re", c_float_p), ("tw_im", c_float_p),
                 ("rev", C.POINTER(C.c_uint))]

@@ -21,8 +21,10 @@
 #include <sigutils/iir.h>
 #include <sigutils/taps.h>
 #include <sigutils/specttuner.h>
+#include <sigutils/tvproc.h>
 #include <analyzer/analyzer.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <mutex>
 #include <stdexcept>
@@ -185,6 +187,97 @@ extern "C" int tu_lpf_task(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, floa
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- TV tab worker
+// TVProcessorWorker (Default/GenericInspector/TVProcessorWorker.cpp): start() :200-209, setParams() :220-239,
+// work() :120-151 with its frame acknowledgement window, returnFrame() :212-218, stop() :172-184 -- the Qt signal
+// `frame` is a callback here, and the display acknowledges every frame at once (TVProcessorTab::onTVProcessorFrame,
+// TVProcessorTab.cpp:657-663: acknowledgeFrame + tvProcessorDisposeFrame).
+#define TV_PROCESSOR_WORKER_MAX_NACK_FRAMES   100
+#define TV_PROCESSOR_WORKER_MIN_NACK_RESTART   50
+#define TV_PROCESSOR_MAX_PENDING_FRAMES       120
+class TVWorker {
+  struct sigutils_tv_processor_params defaultParams;
+  su_tv_processor_t *processor = nullptr;
+  bool blocked = false;
+  SUSCOUNT frameCount = 0, maxProcessingBlock = 0, frameAck = 0;
+public:
+  std::vector<std::vector<SUFLOAT>> frames;      // what the display received
+  int width = 0, height = 0;
+  ~TVWorker() { stop(); }
+  bool start(void)
+  {
+    if (processor == nullptr) processor = su_tv_processor_new(&defaultParams);
+    return processor != nullptr;
+  }
+  void stop(void)
+  {
+    if (processor != nullptr) {
+      su_tv_processor_destroy(processor);
+      processor = nullptr; frameAck = 0; frameCount = 0; blocked = false;
+    }
+  }
+  bool setParams(sigutils_tv_processor_params params)
+  {
+    bool success = false;
+    if (processor != nullptr) {
+      if (su_tv_processor_set_params(processor, &params)) success = true;
+    } else {
+      success = true;
+    }
+    if (success) {
+      defaultParams = params;
+      maxProcessingBlock = static_cast<SUSCOUNT>(TV_PROCESSOR_MAX_PENDING_FRAMES * params.line_len * params.frame_lines);
+    }
+    return success;
+  }
+  void onFrame(struct sigutils_tv_frame_buffer *frame)
+  {
+    ++frameAck;                                   // acknowledgeFrame
+    width = frame->width; height = frame->height;
+    frames.emplace_back(frame->buffer, frame->buffer + (size_t) frame->width * frame->height);
+    if (processor != nullptr) su_tv_processor_return_frame(processor, frame);   // returnFrame
+    else su_tv_frame_buffer_destroy(frame);
+  }
+  void work(const SUFLOAT *samples, SUSCOUNT size)
+  {
+    SUSCOUNT currAck, diff;
+    bool frameSent = false;
+    if (processor != nullptr) {
+      if (size > maxProcessingBlock) size = maxProcessingBlock;
+      while (size-- > 0) {
+        if (su_tv_processor_feed(processor, *samples++)) {
+          if (!frameSent) {
+            currAck = frameAck;
+            if (currAck > frameCount) frameCount = currAck;
+            diff = frameCount - currAck;
+            if (blocked) blocked = diff > TV_PROCESSOR_WORKER_MIN_NACK_RESTART;
+            else blocked = diff > TV_PROCESSOR_WORKER_MAX_NACK_FRAMES;
+            if (!blocked) {
+              ++frameCount;
+              onFrame(su_tv_processor_take_frame(processor));
+              frameSent = true;
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
+// feeds `n` samples in blocks of `block` (one work() call per pushed buffer, TVProcessorWorker::process :188-198);
+// out: up to cap frames of height x width.  Returns the number of frames the display received, -1 on a refused start.
+extern "C" long tu_tv_worker(const struct sigutils_tv_processor_params *params, const SUFLOAT *x, size_t n, size_t block,
+                             SUFLOAT *out, size_t cap, int *width, int *height)
+{
+  TVWorker w;
+  if (!w.setParams(*params) || !w.start()) return -1;
+  for (size_t p = 0; p < n; p += block) w.work(x + p, std::min(block, n - p));
+  *width = w.width; *height = w.height;
+  const size_t px = (size_t) w.width * w.height;
+  for (size_t f = 0; f < w.frames.size() && f < cap; ++f) memcpy(out + f * px, w.frames[f].data(), px * sizeof(SUFLOAT));
+  return (long) w.frames.size();
+}
+
 // ---------------------------------------------------------------------------------------------- Suscan::Analyzer
 class AnalyzerSession {
   struct suscan_mq mq;
@@ -315,13 +408,20 @@ public:
 // request took effect (requests are handled between blocks, as in suscan's worker loop)
 struct GatedSource {
   const SUCOMPLEX *iq; size_t n, pos = 0;
-  std::mutex m; std::condition_variable cv; size_t allowed = 0, calls = 0;
+  std::mutex m; std::condition_variable cv, cvp; size_t allowed = 0, calls = 0; bool parked = false;
   void release(size_t blocks) { std::lock_guard<std::mutex> l(m); allowed = blocks; cv.notify_all(); }
+  // the analyzer's worker handles requests, THEN reads: once it is parked in read() a request sent now takes effect
+  // after the block about to be released -- without this the test raced the worker's request loop
+  void waitParked(void) { std::unique_lock<std::mutex> l(m); cvp.wait(l, [this] { return parked && !(calls < allowed); }); }
   static SUSDIFF read(void *priv, SUCOMPLEX *dst, SUSCOUNT max)
   {
     GatedSource *g = reinterpret_cast<GatedSource *>(priv);
     std::unique_lock<std::mutex> l(g->m);
-    g->cv.wait(l, [g] { return g->calls < g->allowed; });
+    if (!(g->calls < g->allowed)) {
+      g->parked = true; g->cvp.notify_all();
+      g->cv.wait(l, [g] { return g->calls < g->allowed; });
+      g->parked = false;
+    }
     ++g->calls;
     size_t take = g->n - g->pos < max ? g->n - g->pos : (size_t) max;
     memcpy(dst, g->iq + g->pos, take * sizeof(SUCOMPLEX));
@@ -353,6 +453,7 @@ extern "C" long tu_analyzer_session(const SUCOMPLEX *iq, size_t n, unsigned samp
     long result;
     {
       AnalyzerSession s(params, config);
+      gate.waitParked();                                          // block 1 runs without inspector
       s.openEx("psk", fc, -bw / 2, bw / 2, false, -1, 1000);
       gate.release(1);
       if (!s.waitFor([&] { return s.opened; })) return -2;       // captureMessage answers with set_inspector_id
@@ -368,6 +469,7 @@ extern "C" long tu_analyzer_session(const SUCOMPLEX *iq, size_t n, unsigned samp
       SU_ATTEMPT(suscan_config_set_float(cfg, "clock.baud", baud));
       SU_ATTEMPT(suscan_config_set_float(cfg, "clock.gain", 0.1f));
       SU_ATTEMPT(suscan_config_set_bool(cfg, "clock.running", SU_TRUE));
+      gate.waitParked();                                          // block 3 still runs the default configuration
       s.setInspectorConfig(s.handle, cfg, 1002);
       suscan_config_destroy(cfg);
       gate.release(3);
