@@ -106,11 +106,20 @@ struct sdb_analyzer {
   std::vector<Insp> insps;
   sdb_engine_t *eng = nullptr;
   // Sub-carrier inspection (GenericInspector.cpp:502-525: openInspectorTab(..., parent = this handle)): every
-  // parent with open children gets a second engine whose input is the parent's channel stream and whose
-  // channeliser window equals the parent's channel size, so that one parent hop is exactly one child hop.
+  // inspector with open children -- at any depth: a sub-carrier inspector can be a parent itself -- gets an engine
+  // whose input is its channel stream and whose channeliser window equals its channel size, so that one parent hop
+  // is exactly one child hop.  Children have inspector chains, spectrum sources and estimators like any other.
   struct Sub { int32_t parent; sdb_engine_t *eng; };
   std::vector<Sub> subs;
   void drop_subs() { for (auto &s : subs) if (s.eng) sdb_engine_destroy(s.eng); subs.clear(); }
+  // the engine that runs inspector i's chain: the analyzer's own for a baseband inspector, its parent's
+  // sub-carrier engine otherwise
+  template <class I> sdb_engine_t *engine_of(const I &i) const
+  {
+    if (i.parent < 0) return eng;
+    for (auto &sb : subs) if (sb.parent == i.parent) return sb.eng;
+    return nullptr;
+  }
   bool plan_dirty = true;
   size_t block = 0;
   std::atomic<double> measured_rate{ 0.0 };   // written by the worker, read by sdb_analyzer_get_measured_samp_rate
@@ -247,16 +256,20 @@ struct sdb_analyzer {
     }
     if (old && sdb_engine_same_geometry(eng, old))
       sdb_engine_migrate_map(eng, old, old_of_new.data(), old_of_new.size());
-    // sub-carrier engines: one per parent that has open children
-    for (auto &p : insps) {
-      if (!p.open || p.parent >= 0 || p.engine_handle < 0) continue;
+    // sub-carrier engines: one per inspector that has open children, parents before children (an inspector's handle
+    // is larger than its parent's, so one pass in handle order visits every parent after it was planned itself).
+    // Every level runs the same number of hops per block: a child's window is its parent's channel size.
+    const size_t hops_per_block = block / (ep.psd_size / 2);
+    for (size_t pi = 0; pi < insps.size(); ++pi) {
+      Insp &p = insps[pi];
+      if (!p.open || p.engine_handle < 0) continue;
       bool any = false;
       for (auto &c : insps) any = any || (c.open && c.parent == p.handle);
       if (!any || p.size < 16) continue;
       sdb_engine_params sp;
       memset(&sp, 0, sizeof(sp));
       sp.n_streams = 1; sp.psd_size = 0; sp.st_window_size = p.size;
-      sp.max_feed = (uint32_t) (block / (ep.psd_size / 2) * (p.size / 2));
+      sp.max_feed = (uint32_t) (hops_per_block * (p.size / 2));
       sp.device = src.device; sp.input_format = SDB_FORMAT_FLOAT32;
       sdb_engine_t *se = sdb_engine_new(&sp, (double) p.fs);
       if (!se) continue;
@@ -276,8 +289,25 @@ struct sdb_analyzer {
         c.bandwidth = (float) (c.channel.f_hi - c.channel.f_lo); c.lo = (float) c.channel.fc;
         c.cfg.insp_class = c.cls;
         sdb_engine_set_inspector(se, h, &c.cfg);
+        // spectrum source / estimators of a sub-carrier inspector: as for a baseband one (SPEC U.1)
+        c.spect_size = 0;
+        if (c.spectsrc_id || c.est_mask) {
+          const size_t n_ch = hops_per_block * (info.size / 2);
+          uint32_t ns = 4096;
+          while (ns >= 64 && (size_t) ns + 1 > n_ch) ns >>= 1;
+          if (ns >= 64) {
+            c.spect_size = ns;
+            sdb_engine_set_spectrum_source(se, h, (int) c.spectsrc_id, ns);
+            for (int e = 0; e < SDB_ESTIMATOR_COUNT; ++e)
+              if (c.est_mask & (1u << e)) sdb_engine_set_estimator(se, h, e, 1);
+          }
+        }
       }
-      if (sdb_engine_commit(se)) { sdb_engine_destroy(se); continue; }
+      if (sdb_engine_commit(se)) {
+        sdb_engine_destroy(se);
+        for (auto &c : insps) if (c.open && c.parent == p.handle) c.engine_handle = -1;
+        continue;
+      }
       for (auto &os : old_subs)
         if (os.parent == p.handle && os.eng && sdb_engine_same_geometry(se, os.eng))
           sdb_engine_migrate_map(se, os.eng, sub_old_of_new.data(), sub_old_of_new.size());
@@ -303,8 +333,7 @@ struct sdb_analyzer {
           double in_rate = src.samp_rate;
           uint32_t in_window = (uint32_t) params.detector_params.window_size;
           if (c.parent >= 0) {
-            if (c.parent >= (int32_t) insps.size() || !insps[c.parent].open || insps[c.parent].parent >= 0 ||
-                insps[c.parent].size < 16) {
+            if (c.parent >= (int32_t) insps.size() || !insps[c.parent].open || insps[c.parent].size < 16) {
               Cmd w = c; w.handle = c.parent;
               post_inspector(SDB_INSPECTOR_MSGKIND_WRONG_HANDLE, w, nullptr); break;
             }
@@ -369,7 +398,8 @@ struct sdb_analyzer {
             post_inspector(SDB_INSPECTOR_MSGKIND_SET_CONFIG, c, &i);
           } else {
             i.open = false; plan_dirty = true;
-            for (auto &ch : insps) if (ch.parent == i.handle) ch.open = false;     // sub-carrier inspectors go with it
+            // sub-carrier inspectors go with it, to any depth (handles grow with the order of opening: one pass)
+            for (auto &ch : insps) if (ch.open && ch.parent >= 0 && !insps[ch.parent].open) ch.open = false;
             post_inspector(SDB_INSPECTOR_MSGKIND_CLOSE, c, &i);
           }
           break;
@@ -658,12 +688,14 @@ struct sdb_analyzer {
         }
       }
       // sample batches, keyed by the caller-chosen inspector_id
-      // sub-carrier inspectors: the parent's channel samples of this block through the child engine
+      // sub-carrier inspectors: the parent's channel samples of this block through the child engine.  `subs` is in
+      // parent-before-child order (rebuild), so a nested parent's engine has been fed by the time it is read.
       for (auto &sb : subs) {
         const Insp &p = insps[sb.parent];
-        if (!p.open || p.engine_handle < 0) continue;
+        sdb_engine_t *host = engine_of(p);
+        if (!p.open || p.engine_handle < 0 || !host) continue;
         std::vector<sdb_complex> ch(block);
-        long nch = sdb_engine_read_channel(eng, 0, p.engine_handle, ch.data(), ch.size());
+        long nch = sdb_engine_read_channel(host, 0, p.engine_handle, ch.data(), ch.size());
         if (nch <= 0) continue;
         if (sdb_engine_feed_host(sb.eng, ch.data(), (size_t) nch, (size_t) nch) || sdb_engine_sync(sb.eng)) continue;
         for (auto &i : insps) {
@@ -684,11 +716,12 @@ struct sdb_analyzer {
       }
       // kind=SPECTRUM / kind=ESTIMATOR inspector messages (one per block that filled a frame)
       for (auto &i : insps) {
-        if (!i.open || i.engine_handle < 0 || !i.spect_size || i.parent >= 0) continue;
+        sdb_engine_t *ie = engine_of(i);
+        if (!i.open || i.engine_handle < 0 || !i.spect_size || !ie) continue;
         if (i.spectsrc_id) {
           std::vector<float> sp(i.spect_size);
           uint32_t emitted = 0;
-          if (sdb_engine_read_spectrum(eng, i.engine_handle, sp.data(), &emitted) == 0 && emitted) {
+          if (sdb_engine_read_spectrum(ie, i.engine_handle, sp.data(), &emitted) == 0 && emitted) {
             sdb_analyzer_inspector_msg *m = (sdb_analyzer_inspector_msg *) calloc(1, sizeof(*m));
             m->kind = SDB_INSPECTOR_MSGKIND_SPECTRUM; m->handle = i.handle; m->inspector_id = i.inspector_id;
             m->class_name = dupstr((const char *[]){ "psk", "fsk", "ask", "audio", "raw" }[i.cls]);
@@ -702,7 +735,7 @@ struct sdb_analyzer {
         for (int e = 0; e < SDB_ESTIMATOR_COUNT; ++e) {
           if (!(i.est_mask & (1u << e))) continue;
           float v = 0; int32_t ok = 0;
-          if (sdb_engine_read_estimate(eng, i.engine_handle, e, &v, &ok) == 0 && ok) {
+          if (sdb_engine_read_estimate(ie, i.engine_handle, e, &v, &ok) == 0 && ok) {
             sdb_analyzer_inspector_msg *m = (sdb_analyzer_inspector_msg *) calloc(1, sizeof(*m));
             m->kind = SDB_INSPECTOR_MSGKIND_ESTIMATOR; m->handle = i.handle; m->inspector_id = i.inspector_id;
             m->class_name = dupstr((const char *[]){ "psk", "fsk", "ask", "audio", "raw" }[i.cls]);

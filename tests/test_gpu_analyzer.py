@@ -450,7 +450,7 @@ def test_analyzer_subcarrier_inspector(sdb, oracle):
     assert a.read(5000)[0] == "SOURCE_INFO"
     a.open("raw", 0.125 * fs, fs / 8.0, req_id=1)                       # parent: 1024-point channel, fs / 8
     a.open("psk", fs / 64.0, 3 * baud, req_id=2, parent=0)             # child, relative to the parent's centre
-    a.open("psk", 0.0, 1000.0, req_id=3, parent=1)                     # no grandchildren -> WRONG_HANDLE
+    a.open("psk", 0.0, 1e9, req_id=3, parent=1)                        # wider than the parent's channel -> INVALID_CHANNEL
     a.open("psk", 0.0, 1000.0, req_id=4, parent=9)                     # unknown parent   -> WRONG_HANDLE
     a.set_inspector_id(1, 0x51, req_id=5)
     cfg = sdb.InspectorConfig()
@@ -478,8 +478,9 @@ def test_analyzer_subcarrier_inspector(sdb, oracle):
             break
     a.close()
     assert name == "EOS"
-    assert replies == [("OPEN", 1, 0), ("OPEN", 2, 1), ("WRONG_HANDLE", 3, 1), ("WRONG_HANDLE", 4, 9), ("SET_ID", 5, 1),
-                       ("SET_CONFIG", 6, 1)]
+    assert [r[:2] for r in replies] == [("OPEN", 1), ("OPEN", 2), ("INVALID_CHANNEL", 3), ("WRONG_HANDLE", 4),
+                                        ("SET_ID", 5), ("SET_CONFIG", 6)]
+    assert [r[2] for r in replies[:2]] == [0, 1] and replies[3][2] == 9 and replies[4][2] == replies[5][2] == 1
     # oracle: baseband -> parent channel (window N) -> child channel (window 1024) -> psk chain
     f0p, bwp = float(np.float32(2.0 * np.pi * 0.125)), float(np.float32(2.0 * np.pi / 8.0))
     par = oracle.specttuner_run(x[per_block:], N, [dict(f0=f0p, bw=bwp, guard=1.0)])[0]
@@ -488,6 +489,89 @@ def test_analyzer_subcarrier_inspector(sdb, oracle):
     rs, rh = oracle.inspector_run(oracle.insp_config("psk", fs_ch, **kw), chi)
     assert len(rs) > 300
     parity.assert_symbols_match(np.concatenate(soft), np.concatenate(hard), rs, rh, exact_soft=True)
+
+
+def test_analyzer_nested_subcarrier_inspectors(sdb, oracle):
+    """Sub-carrier inspection two levels deep (a sub-carrier tab opens sub-carrier tabs of its own,
+    Default/GenericInspector/GenericInspector.cpp:502-525), with a spectrum source on the middle inspector: three
+    channelisers in series; the grandchild's symbols are bit-identical to the oracle, the middle inspector emits
+    SPECTRUM messages of its own channel."""
+    from sigdigger_b200.analyzer import Analyzer
+    N, fs = 8192, 1.0e6
+    baud = fs / 1024.0
+    blocks, per_block = 6, N * 16
+    n = blocks * per_block
+    # carrier at fs/8 (parent centre) + fs/64 (child centre, in the parent) + fs/512 (grandchild centre, in the child)
+    x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs + fs / 64.0 + fs / 512.0, baud, -10.0, {})], noise_db=-55.0,
+                               seed=23)
+    go = threading.Event()
+    pos = [0]
+
+    def read(priv, dst, maxn):
+        go.wait(30)
+        take = min(maxn, n - pos[0])
+        if take > 0:
+            C.memmove(dst, x.ctypes.data + 8 * pos[0], 8 * take)
+            pos[0] += take
+        return take
+
+    a = Analyzer(fs, window_size=N, window="hann", psd_update_int=1.0, read=read, read_size=per_block)
+    assert a.read(5000)[0] == "SOURCE_INFO"
+    fs_par = fs / 8.0                                                   # 1024-point channel
+    fs_mid = fs_par / 4.0                                               # 256-point channel of the parent's 1024
+    a.open("raw", 0.125 * fs, fs / 8.0, req_id=1)                       # handle 0
+    a.open("raw", fs / 64.0, fs_par / 4.0, req_id=2, parent=0)          # handle 1, in the parent's channel
+    a.open("psk", fs / 512.0, 3 * baud, req_id=3, parent=1)             # handle 2, in the child's channel
+    a.set_inspector_id(2, 0x77, req_id=4)
+    a.set_inspector_id(1, 0x66, req_id=5)
+    a.set_spectrum_source(1, sdb.SPECTSRC["psd"], req_id=6)
+    fs_ch = fs_mid * 32 / 256                                           # 3 baud -> 24 of 256 bins -> 32-point channel
+    cfg = sdb.InspectorConfig()
+    sdb._check(sdb.load_library().sdb_inspector_config_default(C.byref(cfg), sdb.INSP["psk"], fs_ch))
+    kw = dict(baud=baud, costas_order=2, bits_per_symbol=2, loop_bw=fs_ch * 2e-3, mf_type=1, mf_rolloff=0.35,
+              clock_type=1, clock_gain=0.1, clock_running=1)
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    a.set_inspector_config(2, cfg, req_id=7)
+    go.set()
+    soft, hard, opens, spectra = [], [], {}, []
+    while True:
+        name, m = a.read(20000)
+        assert name != "TIMEOUT"
+        if name == "SAMPLES" and m["inspector_id"] == 0x77:
+            soft.append(m["samples"]); hard.append(m["symbols"])
+        elif name == "INSPECTOR":
+            if m["kind"] == "OPEN":
+                opens[m["req_id"]] = (m["handle"], m["equiv_fs"])
+            if m["kind"] == "SPECTRUM" and m["spectrum"] is not None:
+                assert m["inspector_id"] == 0x66
+                spectra.append(m)
+        elif name in ("EOS", "READ_ERROR", "HALT"):
+            break
+    a.close()
+    assert name == "EOS"
+    assert opens[1][0] == 0 and opens[2][0] == 1 and opens[3][0] == 2
+    assert abs(opens[2][1] - fs_mid) < 1e-3 and abs(opens[3][1] - fs_ch) < 1e-3
+    # oracle: baseband -> parent (window N) -> child (window 1024) -> grandchild (window 256) -> psk chain
+    f0p, bwp = float(np.float32(2.0 * np.pi * 0.125)), float(np.float32(2.0 * np.pi / 8.0))
+    par = oracle.specttuner_run(x[per_block:], N, [dict(f0=f0p, bw=bwp, guard=1.0)])[0]
+    f0c, bwc = float(np.float32(2.0 * np.pi * 0.125)), float(np.float32(2.0 * np.pi / 4.0))
+    mid = oracle.specttuner_run(par, 1024, [dict(f0=f0c, bw=bwc, guard=1.0)])[0]
+    f0g, bwg = float(np.float32(2.0 * np.pi * 0.0625)), float(np.float32(2.0 * np.pi * (3 * baud) / fs_mid))
+    gch = oracle.specttuner_run(mid, 256, [dict(f0=f0g, bw=bwg, guard=1.0)])[0]
+    rs, rh = oracle.inspector_run(oracle.insp_config("psk", fs_ch, **kw), gch)
+    assert len(rs) > 100
+    parity.assert_symbols_match(np.concatenate(soft), np.concatenate(hard), rs, rh, exact_soft=True)
+    # the middle inspector's spectrum source: the PSD of the tail of its channel samples of every block (SPEC U).
+    # A fresh engine's first feed yields one window less, at every level: the first block gives H - 2 child hops.
+    H = per_block // (N // 2)
+    ends = np.cumsum([(H - 2) * 128] + [H * 128] * (blocks - 2))
+    starts = [0] + list(ends[:-1])
+    ns = len(spectra[0]["spectrum"])
+    assert ns == 2048 and abs(spectra[0]["equiv_fs"] - fs_mid) < 1e-3 and len(spectra) == blocks - 1
+    for sp, s0, e0 in zip(spectra, starts, ends):
+        ref = oracle.spectsrc_frame("psd", ns, mid[s0:e0])
+        assert np.array_equal(sp["spectrum"].view(np.uint32), ref.view(np.uint32))
 
 
 def test_analyzer_spectrum_estimator_and_channel_messages(sdb, oracle):
