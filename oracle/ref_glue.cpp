@@ -9,6 +9,9 @@
 //   Tasks/WaveSampler.cpp          sampleManual / sampleZeroCrossing / sampleGardner (the latter over this repo's
 //                                  su_clock_detector shim)        -> sdo_sample_manual / _zero_crossing
 //   Misc/Averager.cpp              Averager::feed                 -> sdo_averager_feed
+//   Default/GenericInspector/TVProcessorWorker.cpp   the TV tab's worker (setParams / start / pushData / process /
+//                                  work with its frame acknowledgement window) over this repo's <sigutils/tvproc.h>
+//                                                                  -> the reference drives su_tv_processor_* unmodified
 // The Qt base classes are the no-behaviour stubs of oracle/ref_shim/; what moc would generate (the signal bodies) and
 // the CancellableTask plumbing are defined here.
 #include <Scanner.h>
@@ -16,6 +19,7 @@
 #include <DelayedConjTask.h>
 #include <WaveSampler.h>
 #include <Averager.h>
+#include <TVProcessorWorker.h>
 
 // ---- Suscan::CancellableTask plumbing (Suscan/CancellableTask.cpp is Qt glue, not DSP)
 Suscan::CancellableTask::CancellableTask(QObject *parent) : QObject(parent) { prog = 0; }
@@ -36,6 +40,23 @@ void SigDigger::WaveSampler::data(SigDigger::WaveSampleSet set)
   if (g_ws_out) g_ws_out->insert(g_ws_out->end(), set.block, set.block + set.len);
   if (g_ws_sym) g_ws_sym->insert(g_ws_sym->end(), set.symbols, set.symbols + set.len);
 }
+
+// ---- TVProcessorWorker: the signals moc would generate deliver to this collector, which answers as TVProcessorTab
+// ---- does (onTVProcessorFrame, Default/GenericInspector/TVProcessorTab.cpp:657-663: acknowledgeFrame, then
+// ---- tvProcessorDisposeFrame -> returnFrame)
+struct RefTvSink { SigDigger::TVProcessorWorker *w; std::vector<std::vector<SUFLOAT>> frames; int width = 0, height = 0; bool failed = false; };
+static thread_local RefTvSink *g_tv_sink = nullptr;
+void SigDigger::TVProcessorWorker::frame(struct sigutils_tv_frame_buffer *f)
+{
+  RefTvSink *s = g_tv_sink;
+  if (!s || !f) return;
+  s->w->acknowledgeFrame();
+  s->width = f->width; s->height = f->height;
+  s->frames.emplace_back(f->buffer, f->buffer + (size_t) f->width * f->height);
+  s->w->returnFrame(f);
+}
+void SigDigger::TVProcessorWorker::error(QString) { if (g_tv_sink) g_tv_sink->failed = true; }
+void SigDigger::TVProcessorWorker::paramsChanged(sigutils_tv_processor_params) {}
 
 extern "C" {
 
@@ -106,6 +127,33 @@ void ref_averager(const float *frames, unsigned n_frames, unsigned size, float a
   a.setAlpha(alpha);
   for (unsigned f = 0; f < n_frames; ++f) a.feed(Suscan::PSDMessage(frames + (size_t) f * size, size));
   memcpy(out, a.get(), size * sizeof(float));
+}
+
+
+// same contract as tu_tv_worker of tests/shim/reference_tu.cpp: one pushData + process per block
+long ref_tv_worker(const struct sigutils_tv_processor_params *params, const float *x, size_t n, size_t block, float *out,
+                   size_t cap, int *width, int *height)
+{
+  SigDigger::TVProcessorWorker w;
+  RefTvSink sink; sink.w = &w;
+  g_tv_sink = &sink;
+  w.setParams(*params);
+  w.start();
+  long result = -1;
+  if (!sink.failed) {
+    for (size_t p = 0; p < n; p += block) {
+      std::vector<SUFLOAT> buf(x + p, x + p + (block < n - p ? block : n - p));
+      w.pushData(buf);
+      w.process();
+    }
+    *width = sink.width; *height = sink.height;
+    const size_t px = (size_t) sink.width * sink.height;
+    for (size_t f = 0; f < sink.frames.size() && f < cap; ++f) memcpy(out + f * px, sink.frames[f].data(), px * sizeof(float));
+    result = (long) sink.frames.size();
+  }
+  w.stop();
+  g_tv_sink = nullptr;
+  return result;
 }
 
 }  // extern "C"

@@ -184,12 +184,18 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
   float far_ = 0, faf = 0, sar = 0, saf = 0; unsigned hang_max = 0, dl_size = 1, mh_size = 1;
   AgcS as; as.fast = as.slow = as.peak = -160.0f; as.hang_n = as.dl_ptr = as.mh_ptr = 0;
   float *dl = nullptr, *mh = nullptr; bool in_smem = false;
+  // the delay line is a pure delay (feed-forward): with the lines in shared memory and at least a chunk long, the
+  // two pre warps swap their own samples through it (distinct slots within a chunk) and this warp keeps only the
+  // level tracker, the recurrence (role_pre; 546 -> see profiles/r02_summary.md cycles per sample)
+  bool dl_in_pre = false; unsigned dl_ptr0 = 0;
   if (have_agc) {
     far_ = cp->far_; faf = cp->faf; sar = cp->sar; saf = cp->saf;
     hang_max = cp->hang_max; dl_size = cp->dl_size; mh_size = cp->mh_size;
     as.fast = stp->fast_level; as.slow = stp->slow_level; as.peak = stp->peak;
     as.hang_n = stp->hang_n; as.dl_ptr = stp->dl_ptr; as.mh_ptr = stp->mh_ptr;
     in_smem = 2 * dl_size + mh_size <= (unsigned) c.agc_rows;
+    dl_in_pre = in_smem && dl_size >= CH;
+    dl_ptr0 = as.dl_ptr;
     float *gdl = c.bpool + (size_t) cp->st_dl_off * 32, *gmh = c.bpool + (size_t) cp->st_mh_off * 32;
     if (in_smem) {
       dl = &c.agc[0][lane]; mh = &c.agc[2 * dl_size][lane];
@@ -229,6 +235,11 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
       const int b3 = (int) (ck % 3u);
       const int cnt = base >= n ? 0 : (n - base < CH ? (int) (n - base) : CH);
       auto run = [&](float *dl_, float *mh_) {
+        if (dl_in_pre) {
+          for (int i = 0; i < cnt; ++i)
+            sm.m[b3][i][lane] = agc_level_sel<32>(far_, faf, sar, saf, hang_max, mh_size, as, mh_, sm.m[b3][i][lane]);
+          return;
+        }
         for (int i = 0; i < cnt; ++i) {
           // delay line: the sample that entered dl_size samples ago leaves, this one takes its slot
           const float2 y = sm.y[b3][i][lane];
@@ -258,6 +269,7 @@ static __device__ void role_track(const ICtx &c, const float2 *chan_row)
   }
 #endif
   if (have_agc) {
+    if (dl_in_pre) as.dl_ptr = (dl_ptr0 + c.n % dl_size) % dl_size;     // where the pre warps left it
     stp->fast_level = as.fast; stp->slow_level = as.slow; stp->peak = as.peak;
     stp->hang_n = as.hang_n; stp->dl_ptr = as.dl_ptr; stp->mh_ptr = as.mh_ptr;
     if (in_smem) {
@@ -279,6 +291,25 @@ static __device__ void role_pre(const ICtx &c, int part)
   const float lo_omega = have_lo ? c.cp->lo_omega : 0.0f;
   const uint32_t n = c.n, total = c.nchunks + INSP_STEPS;
   const int i0 = part * (CH / 2), i1 = i0 + CH / 2;
+  // AGC delay line (SPEC A: the sample that entered dl_size samples ago leaves, the new one takes its slot): a pure
+  // delay, so each pre warp swaps its own half of the chunk -- sample i of the chunk uses slot (start + i) mod dl_size,
+  // distinct within a chunk when dl_size >= CH.  Same condition as in role_track, which then skips the line.
+  unsigned dl_size = 1, dl_base = 0;
+  bool dl_here = false;
+  if (have_agc) {
+    dl_size = c.cp->dl_size;
+    dl_here = 2 * dl_size + c.cp->mh_size <= (unsigned) c.agc_rows && dl_size >= CH;
+    dl_base = c.stp->dl_ptr;                      // (read before role_track rewrites it at the end of the kernel)
+  }
+  float *dl = &c.agc[0][lane];
+  auto through_delay = [&](int i, float2 y) -> float2 {
+    unsigned sl = dl_base + (unsigned) i;
+    if (sl >= dl_size) sl -= dl_size;
+    const float2 xd = make_float2(dl[(2 * sl) * 32], dl[(2 * sl + 1) * 32]);
+    dl[(2 * sl) * 32] = y.x; dl[(2 * sl + 1) * 32] = y.y;
+    return xd;
+  };
+  __syncwarp();
   ROLE_T_DECL;
   for (uint32_t it = 0; it <= total; ++it) {
     ROLE_T0;
@@ -296,7 +327,7 @@ static __device__ void role_pre(const ICtx &c, int part)
             d_sincosf(lo_phi, &s, &co);
             float2 y = tl[lane][i];
             y = make_float2(y.x * co + y.y * s, y.y * co - y.x * s);
-            sm.y[b3][i][lane] = y;
+            sm.y[b3][i][lane] = dl_here ? through_delay(i, y) : y;
             if (have_agc) sm.m[b3][i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
           }
           lo_phi = wrap_once(lo_phi + lo_omega);
@@ -306,11 +337,12 @@ static __device__ void role_pre(const ICtx &c, int part)
         for (int i = i0; i < i1; ++i) {
           if (i < cnt) {
             const float2 y = tl[lane][i];
-            sm.y[b3][i][lane] = y;
+            sm.y[b3][i][lane] = dl_here ? through_delay(i, y) : y;
             if (have_agc) sm.m[b3][i][lane] = 10.0f * d_log10f(y.x * y.x + y.y * y.y + 1e-16f);
           }
         }
       }
+      if (dl_here) { dl_base += (unsigned) cnt; if (dl_base >= dl_size) dl_base -= dl_size; }
     }
     ROLE_T1;
     cta_sync();

@@ -701,7 +701,9 @@ static __device__ __forceinline__ void group_fft16(float2 *s, const int M, const
 }
 
 #define IFFT16_THREADS 256
-__global__ void __launch_bounds__(IFFT16_THREADS, 3)
+// MINB = resident CTAs per SM the register allocation aims at: 3 -> 80 registers, 4 -> 64 (72 bytes of spills)
+template <int MINB>
+__global__ void __launch_bounds__(IFFT16_THREADS, MINB)
 k_chan_ifft16(const SdbChannelDev *__restrict__ chans, const int *__restrict__ group, int n_channels,
               const float2 *__restrict__ cspec, int n_bins, int wps, int any_precise,
               float2 *__restrict__ tails, size_t tail_stream_stride, float *__restrict__ lo_phase,
@@ -794,15 +796,23 @@ cudaError_t sdb_launch_chan_ifft_group(const SdbLaunchCtx &c, const SdbChannelDe
   static const int use16 = getenv("SDB_IFFT16") ? atoi(getenv("SDB_IFFT16")) : 1;
   if (use16 && size >= 512 && size <= 4096) {
     static std::atomic<unsigned long long> attr16_done{ 0 };
-    if (sdb_first_on_device(attr16_done))
-      cudaFuncSetAttribute(k_chan_ifft16, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    static const int occ = getenv("SDB_IFFT16_OCC") ? atoi(getenv("SDB_IFFT16_OCC")) : 3;
+    if (sdb_first_on_device(attr16_done)) {
+      cudaFuncSetAttribute(k_chan_ifft16<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(k_chan_ifft16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    }
     const int per = size / 16, P = IFFT16_THREADS / per;
     const size_t smem = (size_t) P * (size + size / 16) * sizeof(float2) + (size_t) size * sizeof(float2)
                         + (any_precise ? (size_t) P * (size / 2) * sizeof(float) : 0);
     dim3 grid(group_len, n_streams);
-    k_chan_ifft16<<<grid, IFFT16_THREADS, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
-                                                            any_precise, tails, tail_stream_stride, lo_phase,
-                                                            chan_out, chan_stream_stride);
+    if (occ == 4)
+      k_chan_ifft16<4><<<grid, IFFT16_THREADS, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+                                                                 any_precise, tails, tail_stream_stride, lo_phase,
+                                                                 chan_out, chan_stream_stride);
+    else
+      k_chan_ifft16<3><<<grid, IFFT16_THREADS, smem, c.stream>>>(chans_dev, group_dev, n_channels, cspec, n_bins, wps,
+                                                                 any_precise, tails, tail_stream_stride, lo_phase,
+                                                                 chan_out, chan_stream_stride);
     if (c.launch_counter) ++*c.launch_counter;
     return cudaGetLastError();
   }

@@ -1,6 +1,7 @@
 """CPU: the oracle pinned to the REFERENCE ITSELF where the reference contains the arithmetic.  oracle/_ref/libsdref.so
 is built by `make -C oracle ref` from the sources under /root/reference where they lie (Panoramic/Scanner.cpp:1-293,
-Tasks/QuadDemodTask.cpp, Tasks/DelayedConjTask.cpp, Tasks/WaveSampler.cpp, Misc/Averager.cpp) behind no-behaviour Qt
+Tasks/QuadDemodTask.cpp, Tasks/DelayedConjTask.cpp, Tasks/WaveSampler.cpp, Misc/Averager.cpp,
+Default/GenericInspector/TVProcessorWorker.cpp) behind no-behaviour Qt
 stubs (oracle/ref_shim/, oracle/ref_glue.cpp); nothing of the reference is copied.  The restatements of oracle/*.c are
 compared with it here; the Python transcriptions of tests/golden/make_golden.py stay as a second opinion.
 Skipped when the library was not built (no /root/reference and no prebuilt file)."""
@@ -168,3 +169,38 @@ def test_averager_restatement_equals_the_compiled_reference(ref, oracle):
             else:
                 last = frames[f].copy()
         assert np.array_equal(out.view(np.uint32), last.view(np.uint32)), alpha
+
+
+@pytest.mark.parametrize("interlace,lines", [(False, 40), (True, 61)])
+def test_tv_worker_of_the_reference_over_the_tvproc_shim(ref, oracle, interlace, lines):
+    """Default/GenericInspector/TVProcessorWorker.cpp COMPILED FROM THE REFERENCE (setParams / start / pushData /
+    process / work with its acknowledgement window / returnFrame) drives this repo's <sigutils/tvproc.h> unmodified:
+    the frames it emits are, bit for bit, the oracle's (SPEC TV) and those of the reference-shaped TU."""
+    import shim_build as SB
+    import test_oracle_tv as T
+    ref.ref_tv_worker.restype = C.c_long
+    ref.ref_tv_worker.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                  C.c_void_p]
+    x, _, _ = T.toy_signal(lines, interlace, frames=10)
+    sp = T.toy_params(lines, interlace, 4, cls=T.ShimTvParams)
+    W, H, cap, block = int(np.floor(T.LINE)), lines, 16, 7000
+    out = np.zeros((cap, H, W), np.float32)
+    w, h = C.c_int(), C.c_int()
+    got = ref.ref_tv_worker(C.byref(sp), x.ctypes.data, x.size, block, out.ctypes.data, cap, C.byref(w), C.byref(h))
+    assert got >= 5 and (w.value, h.value) == (W, H)
+    out_tu = np.zeros_like(out)
+    assert SB.reference_tu().tu_tv_worker(C.byref(sp), x.ctypes.data, x.size, block, out_tu.ctypes.data, cap,
+                                          C.byref(w), C.byref(h)) == got
+    assert np.array_equal(out.view(np.uint32), out_tu.view(np.uint32))
+    t = T.OracleTv(T.toy_params(lines, interlace, 4))
+    k = 0
+    for p0 in range(0, x.size, block):
+        blk, sent = x[p0:p0 + block], False
+        for pos in range(0, blk.size, 64):
+            f0 = t.frames
+            t.feed(blk[pos:pos + 64])
+            if t.frames > f0 and not sent:
+                assert np.array_equal(out[k].view(np.uint32), t.frame(f0).view(np.uint32))
+                k, sent = k + 1, True
+    assert k == got
+    t.close()
