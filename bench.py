@@ -367,7 +367,9 @@ def run_reference(args):
            "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args, streams=streams, hops=16),
+           # the CUDA arm's own configuration (the workload this arm is a bounded sample of; the sample itself is
+           # described in cpu_baseline.sample)
+           "config": workload_config(args, streams=args.streams, hops=args.hops),
            "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "sample": sample,
                             "build": CPU_FLAGS[kind], "per_thread_msps": v / cores,
                             "parity_build_msps": sp / sum(tp) / 1e6,
@@ -557,7 +559,7 @@ def run_cuda_cfg5(args):
         out = {"metric": "complex MSamples/s ingested (65536-pt PSD per tuner hop, stitched)", "value": value,
                "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": dict(cfg5_config(), host_binding=numa), "clocks": clk.summary(),
+               "dtype": "f32", "data": "synthetic", "config": cfg5_config(), "host_binding": numa, "clocks": clk.summary(),
                "gpu_launches": None,
                "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(samples * 8),
                        "d2h_bytes_per_step": int(3 * 65536 * 4)},
@@ -864,7 +866,7 @@ def run_cuda(args):
         out = {"metric": "complex MSamples/s ingested (%d-pt PSD + N inspectors)" % N_FFT, "value": value,
                "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, S, H), host_binding=numa),
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args, S, H), "host_binding": numa,
                "clocks": clk.summary(), "gpu_launches": int(launches),
                "e2e": {"value": e2e_v, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                "roofline": roofline, "cpu_baseline": cpu, "single_stream_msps": single,

@@ -1799,6 +1799,9 @@ extern "C" int sdb_sview_set_range(sdb_sview_t *v, double fmin, double fmax, dou
   if (sz > 65536) sz = 65536;
   v->spectrum_size = sz;
   v->fft_bandwidth = fft_bandwidth; v->rel_bw = rel_bw;
+  // a hop contributes at most sz * (fft_bandwidth - 2 skip) / freq_range + 1 bins, and every projection uses THIS
+  // fft_bandwidth (the kernels take the geometry from the view, not from the call): the `nb > max_bins` clamp in the
+  // projection kernels is a guard that cannot bind
   double mb = (double) sz * fft_bandwidth / v->freq_range + 4.0;
   v->max_bins = mb > (double) sz ? (int) sz : (int) mb;
   if (v->max_bins < 2) v->max_bins = 2;
