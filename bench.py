@@ -749,6 +749,25 @@ def run_cuda(args):
                 "path": {"b_alg_bytes_per_sample": B_ALG[name],
                          "achieved": B_ALG[name] * value * 1e6 / world / 1e9,
                          "frac": B_ALG[name] * value * 1e6 / world / 1e9 / peak}}
+    # The path's other roofline: instruction issue.  Every input sample costs a fixed number of warp instructions
+    # (64 inspectors' recurrences, filters and transforms; counted by ncu, profiles/r02_traffic.json), and an SM issues
+    # at most 4 warp instructions per clock: the ceiling that count sets, whatever the memory system does.
+    try:
+        wi = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if wi.get("workload") == name and "warp_instructions" in wi:
+            w = wi["warp_instructions"]
+            per_sample = sum(w["per_step_148_streams"].values()) / float(w["input_samples_per_step"])
+            sm_clock = (clk.summary().get("sm_mhz") or 1965.0) * 1e6
+            ceiling = 148 * 4 * sm_clock / per_sample / 1e6          # MS/s per GPU
+            roofline["issue"] = {"warp_instructions_per_input_sample": round(per_sample, 2),
+                                 "ceiling_msps_per_gpu": round(ceiling, 1),
+                                 "frac": round(value / world / ceiling, 4),
+                                 "ceiling_as_hbm_frac": round(B_ALG[name] * ceiling * 1e6 / 1e9 / peak, 4),
+                                 "note": "148 SMs x 4 warp instructions per clock / instructions per sample: even a "
+                                         "perfectly issue-bound run of this instruction stream stays below this "
+                                         "fraction of the HBM roofline"}
+    except Exception:
+        pass
     if os.environ.get("SDB_LIB"):      # instrumented twin: busy cycles per role warp per chunk sample
         sdb.stage_cycles(reset=True)
         step_dev(); e.sync()
