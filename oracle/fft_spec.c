@@ -134,8 +134,51 @@ static void fft256_16x16(const sdo_cpx *in, size_t stride, const float *win, siz
   }
 }
 
+/* ---- F.5 building block: forward 8-point DFT = one radix-2 stage + two DFT4; X[kb] is left in v[4 (kb & 1) + (kb >> 1)] ---- */
+#define REV8(p) (2 * ((p) & 3) + ((p) >> 2))
+static void fft8(sdo_cpx *v)
+{
+  int i;
+  const sdo_cpx w1 = { SR2, -SR2 }, w3 = { -SR2, -SR2 };
+  for (i = 0; i < 4; ++i) {
+    const sdo_cpx a = cadd(v[i], v[i + 4]), b = csub(v[i], v[i + 4]);
+    v[i] = a; v[i + 4] = b;
+  }
+  v[5] = cmul(v[5], w1); v[6] = mul_mi(v[6]); v[7] = cmul(v[7], w3);
+  fft4(&v[0], &v[1], &v[2], &v[3]);
+  fft4(&v[4], &v[5], &v[6], &v[7]);
+}
+
+/* 128-point forward transform of 128 values at stride `stride` of `in`, = 8 x 16: n = t + 8 j -> fft16 over j ->
+ * x W_128^(t ka) -> fft8 over t (F.5).  out[k], k = ka + 16 kb. */
+static void fft128_16x8(const sdo_cpx *in, size_t stride, const float *win, size_t wstride,
+                        const sdo_cpx *tw128, sdo_cpx *out)
+{
+  sdo_cpx y[16][8];    /* [ka][t] */
+  int t, j, q, ka;
+  for (t = 0; t < 8; ++t) {
+    sdo_cpx v[16];
+    for (j = 0; j < 16; ++j) {
+      v[j] = in[(size_t) (t + 8 * j) * stride];
+      if (win) { float w = win[(size_t) (t + 8 * j) * wstride]; v[j].re *= w; v[j].im *= w; }
+    }
+    fft16(v);
+    for (q = 0; q < 16; ++q) {
+      ka = REV16(q);
+      y[ka][t] = ka ? cmul(v[q], tw128[t * ka]) : v[q];
+    }
+  }
+  for (ka = 0; ka < 16; ++ka) {
+    sdo_cpx v[8];
+    for (t = 0; t < 8; ++t) v[t] = y[ka][t];
+    fft8(v);
+    for (q = 0; q < 8; ++q) out[ka + 16 * REV8(q)] = v[q];
+  }
+}
+
 /* Plans: tables and scratch for one transform size.
  *   N == 65536            -> F.4 (256 x 256, fft16 butterflies, coarse x fine inter-pass twiddle)
+ *   N == 32768            -> F.5 (128 x 256: columns 8 x 16 = fft16 + fft8, rows as F.4)
  *   N <= 4096 && !four    -> F.2 single Stockham transform
  *   otherwise             -> F.3 four-step N1 x N2 with Stockham sub-transforms
  * `four` forces the four-step form (the channeliser's forward transform always uses it). */
@@ -149,6 +192,10 @@ int sdo_spec_plan_init(sdo_spec_plan *p, unsigned N, int four)
   if (N == 65536) {
     p->kind = 2; p->N1 = 256; p->N2 = 256;
     p->tw_a = sdo_spec_twiddles(256);
+  } else if (N == 32768) {
+    p->kind = 3; p->N1 = 128; p->N2 = 256;         /* F.5 */
+    p->tw_a = sdo_spec_twiddles(128);
+    p->tw_b = sdo_spec_twiddles(256);
   } else if (N <= 4096 && !four) {
     p->kind = 0; p->N1 = N; p->N2 = 1;
   } else {
@@ -188,6 +235,23 @@ void sdo_spec_forward(const sdo_spec_plan *p, const sdo_cpx *x, const float *win
     for (k1 = 0; k1 < 256; ++k1) {
       fft256_16x16(p->scr + (size_t) k1 * 256, 1, NULL, 0, p->tw_a, col);
       for (n2 = 0; n2 < 256; ++n2) X[k1 + 256 * n2] = col[n2];
+    }
+    return;
+  }
+  if (p->kind == 3) {
+    /* F.5: 256 columns of 128 (8 x 16), inter-pass twiddle W_32768^p = W_128^(p >> 8) x W_32768^(p & 255), 128 rows of 256 */
+    sdo_cpx col[256];
+    for (n2 = 0; n2 < 256; ++n2) {
+      fft128_16x8(x + n2, 256, window ? window + n2 : NULL, 256, p->tw_a, col);
+      for (k1 = 0; k1 < 128; ++k1) {
+        unsigned pw = n2 * k1;
+        sdo_cpx tw = cmul(p->tw_a[pw >> 8], p->tw_n[pw & 255]);
+        p->scr[(size_t) k1 * 256 + n2] = cmul(col[k1], tw);
+      }
+    }
+    for (k1 = 0; k1 < 128; ++k1) {
+      fft256_16x16(p->scr + (size_t) k1 * 256, 1, NULL, 0, p->tw_b, col);
+      for (n2 = 0; n2 < 256; ++n2) X[k1 + 128 * n2] = col[n2];
     }
     return;
   }

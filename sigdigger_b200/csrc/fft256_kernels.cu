@@ -143,6 +143,103 @@ cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// N = 32768 = 128 x 256 (SPEC F.5; BASELINE configs[3]).  Pass A: columns of 128 = 8 x 16 -- the same first butterfly
+// (fft16 over the high row digit), twiddle W_128^(t ka), exchange, then an 8-point butterfly (one radix-2 stage + two
+// DFT4) over the low row digit; pass B is k_rows256 with 128 rows per window.
+// forward 8-point DFT of v[0..7] (natural order in).  Result X[kb] is left in v[4 (kb & 1) + (kb >> 1)].
+static __device__ __forceinline__ void fft8(float2 (&v)[8])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = cadd(v[i], v[i + 4]), b = csub(v[i], v[i + 4]);
+    v[i] = a; v[i + 4] = b;
+  }
+  v[5] = cmulf(v[5], make_float2(R2, -R2));
+  v[6] = mul_mi(v[6]);
+  v[7] = cmulf(v[7], make_float2(-R2, -R2));
+  fft4(v[0], v[1], v[2], v[3]);
+  fft4(v[4], v[5], v[6], v[7]);
+}
+#define REV8(p) (2 * ((p) & 3) + ((p) >> 2))
+#define LDC8 145   // pitch of one column's [ka][9] block (odd)
+
+__global__ void __launch_bounds__(128, 8) k_cols128(const Cols256K p)
+{
+  __shared__ float2 sm[16 * LDC8];
+  __shared__ float2 s_tw[128];
+  const int tid = threadIdx.x;
+  s_tw[tid] = __ldg(p.tw256 + tid);                 // W_128^i
+  const int c = tid & 15, t = tid >> 4;             // 16 columns x 8 low row digits
+  const int w = p.win_base + blockIdx.y;
+  const int stream = w / p.windows_per_stream;
+  const int j0 = p.first_window + (w - stream * p.windows_per_stream);
+  const int col = blockIdx.x * 16 + c;
+  const long v0 = (long) p.base_off + (long) j0 * p.hop;
+  const int fmt = p.fmt;
+  const char *__restrict__ xs = reinterpret_cast<const char *>(p.x) + (size_t) stream * p.stream_stride * sdb_fmt_bytes(fmt);
+  const float2 *__restrict__ hs = p.hist ? p.hist + (size_t) stream * p.hist_len : nullptr;
+
+  float2 v[16];
+  if (fmt == SDB_FMT_F32 && v0 >= p.hist_len) {     // CTA-uniform: the window lies wholly in the new samples
+    const float2 *__restrict__ src = reinterpret_cast<const float2 *>(xs) + (v0 - p.hist_len) + t * 256 + col;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j * 2048);      // row n1 = t + 8 j
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const long vi = v0 + (long) (t + 8 * j) * 256 + col;
+      v[j] = vi < p.hist_len ? __ldg(hs + vi)
+                             : (fmt == SDB_FMT_F32 ? __ldg(reinterpret_cast<const float2 *>(xs) + (vi - p.hist_len))
+                                                   : sdb_ld_iq(xs, vi - p.hist_len, fmt));
+    }
+  }
+  if (p.window) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float wv = __ldg(p.window + (t + 8 * j) * 256 + col);
+      v[j] = sdb_mul2(v[j], make_float2(wv, wv));
+    }
+  }
+  fft16(v);                                         // over j: Y[t][ka], ka = REV16(position)
+  __syncthreads();                                  // table loaded
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int ka = REV16(q);
+    float2 y = v[q];
+    if (ka) y = cmulf(y, s_tw[t * ka]);             // W_128^(t ka)
+    sm[c * LDC8 + ka * 9 + t] = y;
+  }
+  __syncthreads();
+  float2 *__restrict__ out = p.scratch + (size_t) blockIdx.y * 32768;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {                     // second butterfly: thread (c, ka) gathers all t, two ka per thread
+    const int ka = t + 8 * h;
+    float2 u[8];
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) u[tt] = sm[c * LDC8 + ka * 9 + tt];
+    fft8(u);                                        // over t: X[ka + 16 kb], kb = REV8(position)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k1 = ka + 16 * REV8(q);
+      out[(size_t) k1 * 256 + col] = cmulf(u[q], __ldg(p.twpq + k1 * 256 + col));   // SPEC F.5 inter-pass twiddle
+    }
+  }
+}
+
+cudaError_t sdb_launch_cols128(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a, int win_base, int n_win)
+{
+  Cols256K p;
+  p.x = a.x; p.fmt = a.fmt; p.stream_stride = a.stream_stride; p.hist = a.hist; p.hist_len = a.hist_len;
+  p.windows_per_stream = a.windows_per_stream; p.first_window = a.first_window; p.hop = a.hop;
+  p.base_off = a.base_off; p.win_base = win_base; p.window = a.window; p.scratch = a.scratch;
+  p.tw256 = fs.twN1; p.twfine = nullptr; p.twpq = fs.twPQ;
+  dim3 grid(16, n_win);
+  k_cols128<<<grid, 128, 0, c.stream>>>(p);
+  if (c.launch_counter) ++*c.launch_counter;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 struct Rows256K {
   const float2 *scratch;
   float *psd; float inv_n; int shift_db;
@@ -153,15 +250,17 @@ struct Rows256K {
 
 #define LDR 273
 
-template <int MODE>
+// N1 = rows per window: 256 (N = 65536, SPEC F.4) or 128 (N = 32768, SPEC F.5); output bin k = k1 + N1 (ka + 16 kb)
+template <int MODE, int N1 = 256>
 __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
 {
+  constexpr int NN = N1 * 256;
   extern __shared__ float2 smr[];                   // 32 rows x LDR
   __shared__ float2 s_tw[256];
   const int tid = threadIdx.x;
   if (tid < 256) s_tw[tid] = __ldg(p.tw256 + tid);
   const int win = blockIdx.y, k1_0 = blockIdx.x * 32;
-  const float2 *__restrict__ in = p.scratch + (size_t) win * 65536 + (size_t) k1_0 * 256;
+  const float2 *__restrict__ in = p.scratch + (size_t) win * NN + (size_t) k1_0 * 256;
   {
     const int t = tid & 15, r = tid >> 4;           // 32 rows x 16 t
     float2 v[16];
@@ -190,12 +289,12 @@ __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int kb = REV16(q);
-      const int k = k1_0 + r + 256 * (ka + 16 * kb);
+      const int k = k1_0 + r + N1 * (ka + 16 * kb);
       if (MODE == 0) {
         float pw = __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y) * p.inv_n;
-        float *__restrict__ psd = p.psd + (size_t) win * 65536;
+        float *__restrict__ psd = p.psd + (size_t) win * NN;
         // one-shot outputs: streaming stores, so that they do not displace the scratch / input in L2
-        if (p.shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); __stcs(psd + ((k + 32768) & 65535), pw); }
+        if (p.shift_db) { pw = 10.0f * d_log10f(pw + 1e-8f); __stcs(psd + ((k + NN / 2) & (NN - 1)), pw); }
         else __stcs(psd + k, pw);
       } else {
         const int m = __ldg(p.binmap + k);
@@ -214,12 +313,20 @@ cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
   const size_t smem = (size_t) 32 * LDR * sizeof(float2);
   static std::atomic<unsigned long long> attr_done{ 0 };   // one bit per device: function attributes are per context
   if (sdb_first_on_device(attr_done)) {
-    cudaFuncSetAttribute(k_rows256<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    cudaFuncSetAttribute(k_rows256<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   }
-  dim3 grid(8, a.n_windows);
-  if (mode == 0) k_rows256<0><<<grid, 512, smem, c.stream>>>(p);
-  else           k_rows256<1><<<grid, 512, smem, c.stream>>>(p);
+  if (fs.N1 == 128) {
+    dim3 grid(4, a.n_windows);
+    if (mode == 0) k_rows256<0, 128><<<grid, 512, smem, c.stream>>>(p);
+    else           k_rows256<1, 128><<<grid, 512, smem, c.stream>>>(p);
+  } else {
+    dim3 grid(8, a.n_windows);
+    if (mode == 0) k_rows256<0, 256><<<grid, 512, smem, c.stream>>>(p);
+    else           k_rows256<1, 256><<<grid, 512, smem, c.stream>>>(p);
+  }
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }

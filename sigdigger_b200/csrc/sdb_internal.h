@@ -31,7 +31,7 @@ struct SdbFourStep {
   const float2 *twN1;       // W_N1^i, i < N1 (forward sign)
   const float2 *twN2;
   const float2 *twN;        // W_N^i, i < N
-  const float2 *twPQ;       // N = 65536 only: SPEC F.4 inter-pass twiddle [k1][n2] = W_256^(p>>8) x W_65536^(p&255), p = n2 k1
+  const float2 *twPQ;       // N = 65536 / 32768: SPEC F.4 / F.5 inter-pass twiddle [k1][n2] = W_N1^(p>>8) x W_N^(p&255), p = n2 k1
 };
 
 struct SdbPassAArgs {
@@ -242,6 +242,7 @@ struct SdbLaunchCtx {
 cudaError_t sdb_launch_pass_a_range(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
                                     int win_base, int n_win);
 // 65536 = 256 x 256 specialisation (fft256_kernels.cu)
+cudaError_t sdb_launch_cols128(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a, int win_base, int n_win);
 cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassAArgs &a,
                                const float2 *twfine, int win_base, int n_win);
 cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, const SdbPassBArgs &a, int mode);
