@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local std::string g_perr;
 static int pfail(const std::string &m) { g_perr = m; return -1; }
@@ -74,6 +75,50 @@ struct HopLists {
   size_t rows = 0;
 };
 
+// Rank 0, after the gather: the per-hop channel lists ([hops][cap], mostly empty) packed hop after hop, so that the
+// read-back carries the channels that exist (a few hundred KB) instead of the 3.7 MB array they sit in.
+//   k_chan_offsets: one CTA; off[h] = sum of the counts before hop h, off[n_hops] = total
+//   k_chan_dense  : one block per hop copies its channels to dense[off[h] ...] while they fit in dense_cap
+__global__ void k_chan_offsets(const int32_t *__restrict__ cnt, int n_hops, int32_t *__restrict__ off)
+{
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_hops; base += 1024) {
+    const int h = base + tid;
+    const int v = h < n_hops ? cnt[h] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_w[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    if (h < n_hops) off[h] = carry + (warp ? s_w[warp - 1] : 0) + incl - v;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + s_w[31];
+    __syncthreads();
+  }
+  if (tid == 0) off[n_hops] = s_carry;
+}
+
+__global__ void k_chan_dense(const int32_t *__restrict__ cnt, const int32_t *__restrict__ off,
+                             const sdb_detected_channel *__restrict__ chan, int cap, sdb_detected_channel *__restrict__ dense,
+                             int dense_cap)
+{
+  const int h = blockIdx.x, n = cnt[h], o = off[h];
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (o + i < dense_cap) dense[o + i] = chan[(size_t) h * cap + i];
+}
+
 struct sdb_panoramic {
   sdb_panoramic_params prm;
   int rank = 0, world = 1;
@@ -86,7 +131,10 @@ struct sdb_panoramic {
   double *d_centers = nullptr; size_t centers_cap = 0;
   float *d_db = nullptr; size_t db_cap = 0;
   // rank 0, detector: the gathered channel lists land in pinned host memory behind ev_chan
-  int32_t *h_ccnt = nullptr; sdb_detected_channel *h_chan = nullptr; size_t h_rows = 0, n_hops_last = 0;
+  int32_t *h_off = nullptr; sdb_detected_channel *h_chan = nullptr; size_t h_rows = 0, n_hops_last = 0;
+  int32_t *d_off = nullptr; sdb_detected_channel *d_dense = nullptr; size_t dense_cap = 0;
+  std::vector<sdb_detected_channel> h_full; std::vector<int32_t> h_full_cnt; bool full_valid = false;   // overflow path
+  std::vector<double> centers_last;            // hop centres of the last sweep (already on the device)
   cudaEvent_t ev_chan = nullptr, ev_eng = nullptr; bool chan_pending = false;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   sdb_panoramic_timing last{};
@@ -150,7 +198,7 @@ extern "C" void sdb_panoramic_destroy(sdb_panoramic_t *s)
   if (s->view) sdb_sview_destroy(s->view);
   free_lists(s->lists);
   cudaFree(s->d_centers); cudaFree(s->d_db);
-  cudaFreeHost(s->h_ccnt); cudaFreeHost(s->h_chan);
+  cudaFreeHost(s->h_off); cudaFreeHost(s->h_chan); cudaFree(s->d_off); cudaFree(s->d_dense);
   for (auto &e : s->ev) if (e) cudaEventDestroy(e);
   if (s->ev_chan) cudaEventDestroy(s->ev_chan);
   if (s->ev_eng) cudaEventDestroy(s->ev_eng);
@@ -191,9 +239,19 @@ static int ensure(sdb_panoramic *s, size_t n_hops, size_t n_local)
   }
   if (s->rank == 0 && s->prm.detect && s->h_rows < n_hops) {
     PCK(cudaStreamSynchronize(s->stream));
-    cudaFreeHost(s->h_ccnt); cudaFreeHost(s->h_chan); s->h_ccnt = nullptr; s->h_chan = nullptr;
-    PCK(cudaMallocHost(&s->h_ccnt, n_hops * sizeof(int32_t)));
-    PCK(cudaMallocHost(&s->h_chan, n_hops * cap * sizeof(sdb_detected_channel)));
+    cudaFreeHost(s->h_off); cudaFreeHost(s->h_chan); cudaFree(s->d_off); cudaFree(s->d_dense);
+    s->h_off = nullptr; s->h_chan = nullptr; s->d_off = nullptr; s->d_dense = nullptr;
+    // room for 8 channels per hop on average (the lists hold up to `cap` each); a sweep that finds more is read
+    // back in full, on demand (sdb_panoramic_read_channels)
+    s->dense_cap = std::min(n_hops * cap, 8 * n_hops + 256);
+    if (const char *env = getenv("SDB_PANORAMIC_DENSE_CAP")) {        // tests: force the overflow path
+      const long v = atol(env);
+      if (v >= 1) s->dense_cap = std::min(s->dense_cap, (size_t) v);
+    }
+    PCK(cudaMallocHost(&s->h_off, (n_hops + 1) * sizeof(int32_t)));
+    PCK(cudaMallocHost(&s->h_chan, s->dense_cap * sizeof(sdb_detected_channel)));
+    PCK(cudaMalloc(&s->d_off, (n_hops + 1) * sizeof(int32_t)));
+    PCK(cudaMalloc(&s->d_dense, s->dense_cap * sizeof(sdb_detected_channel)));
     s->h_rows = n_hops;
   }
   if (n_local && (!s->eng || s->eng_hops != n_local)) {
@@ -232,7 +290,10 @@ static int sweep_impl(sdb_panoramic *s, const sdb_complex *hops_local, int on_de
   HopLists &l = s->lists;
   const size_t row0 = s->rank == 0 ? lo : 0;          // rank 0 writes into the global arrays (lo = 0 there)
   PCK(cudaEventRecord(s->ev[0], st));
-  PCK(cudaMemcpyAsync(s->d_centers, centers_all, n_hops * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (s->centers_last.size() != n_hops || memcmp(s->centers_last.data(), centers_all, n_hops * sizeof(double))) {
+    s->centers_last.assign(centers_all, centers_all + n_hops);       // a scanner repeats its hop plan sweep after sweep
+    PCK(cudaMemcpyAsync(s->d_centers, s->centers_last.data(), n_hops * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   if (n_local) {
     // frames_per_hop > 1: the detector averages over the hop's frames, the view takes the last one
     const size_t F = s->prm.frames_per_hop ? s->prm.frames_per_hop : 1, L = N * F;
@@ -299,10 +360,13 @@ static int sweep_impl(sdb_panoramic *s, const sdb_complex *hops_local, int on_de
     // rows are in global hop order already: accumulate + fill exactly as one sequential feed() series
     if (sdb_sview_accumulate_async(s->view, st, l.j0, l.nb, l.va, l.vc, n_hops)) return pfail(sdb_last_error());
     if (s->prm.detect) {
-      PCK(cudaMemcpyAsync(s->h_ccnt, l.ccnt, n_hops * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      PCK(cudaMemcpyAsync(s->h_chan, l.chan, n_hops * cap * sizeof(sdb_detected_channel), cudaMemcpyDeviceToHost, st));
+      k_chan_offsets<<<1, 1024, 0, st>>>(l.ccnt, (int) n_hops, s->d_off);
+      k_chan_dense<<<(unsigned) n_hops, 64, 0, st>>>(l.ccnt, s->d_off, l.chan, (int) cap, s->d_dense, (int) s->dense_cap);
+      PCK(cudaGetLastError());
+      PCK(cudaMemcpyAsync(s->h_off, s->d_off, (n_hops + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      PCK(cudaMemcpyAsync(s->h_chan, s->d_dense, s->dense_cap * sizeof(sdb_detected_channel), cudaMemcpyDeviceToHost, st));
       PCK(cudaEventRecord(s->ev_chan, st));
-      s->chan_pending = true;
+      s->chan_pending = true; s->full_valid = false;
     }
     s->n_hops_last = n_hops;
   }
@@ -340,10 +404,25 @@ extern "C" int sdb_panoramic_read(sdb_panoramic_t *s, float *psd, float *accum, 
 extern "C" uint32_t sdb_panoramic_size(const sdb_panoramic_t *s) { return s ? sdb_sview_size(s->view) : 0; }
 extern "C" long sdb_panoramic_read_channels(sdb_panoramic_t *s, size_t hop, sdb_detected_channel *out, size_t cap)
 {
-  if (!s || s->rank != 0 || !s->prm.detect || hop >= s->n_hops_last || !s->h_ccnt) return -1;
+  if (!s || s->rank != 0 || !s->prm.detect || hop >= s->n_hops_last || !s->h_off) return -1;
   if (s->chan_pending) { cudaEventSynchronize(s->ev_chan); s->chan_pending = false; }
-  const size_t n = std::min(cap, (size_t) s->h_ccnt[hop]);
-  if (n && out) memcpy(out, s->h_chan + hop * s->prm.channel_cap, n * sizeof(sdb_detected_channel));
+  const size_t n_hops = s->n_hops_last, pc = s->prm.channel_cap;
+  if ((size_t) s->h_off[n_hops] <= s->dense_cap) {
+    const size_t n = std::min(cap, (size_t) (s->h_off[hop + 1] - s->h_off[hop]));
+    if (n && out) memcpy(out, s->h_chan + s->h_off[hop], n * sizeof(sdb_detected_channel));
+    return (long) n;
+  }
+  // more channels than the packed read-back holds: fetch the whole [hops][cap] array once
+  if (!s->full_valid) {
+    if (cudaSetDevice(s->prm.device) != cudaSuccess) return -1;
+    s->h_full.resize(n_hops * pc); s->h_full_cnt.resize(n_hops);
+    if (cudaMemcpy(s->h_full_cnt.data(), s->lists.ccnt, n_hops * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(s->h_full.data(), s->lists.chan, n_hops * pc * sizeof(sdb_detected_channel), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -1;
+    s->full_valid = true;
+  }
+  const size_t n = std::min(cap, (size_t) s->h_full_cnt[hop]);
+  if (n && out) memcpy(out, s->h_full.data() + hop * pc, n * sizeof(sdb_detected_channel));
   return (long) n;
 }
 extern "C" int sdb_panoramic_last_timing(const sdb_panoramic_t *s, sdb_panoramic_timing *t)

@@ -222,3 +222,43 @@ def test_panoramic_histogram_mode(sdb, oracle):
     assert np.array_equal(cnt.view(np.uint32), ref[2].view(np.uint32))
     assert np.array_equal(acc.view(np.uint32), ref[1].view(np.uint32))
     assert np.array_equal(psd.view(np.uint32), ref[0].view(np.uint32))
+
+
+@pytest.mark.parametrize("detect", [False, True])
+def test_panoramic_sweep_histogram_mode_geometry(sdb, oracle, detect):
+    """The sweep's stream-ordered path with hops narrower than two view bins (feedHistogramMode): the tiled projection
+    does not apply, the sweep converts to dB (detector on: linear PSD + separate pass) and runs the general kernel."""
+    import torch
+    from sigdigger_b200 import panoramic
+    N, n_hops, fftbw = 4096, 30, 1e6
+    fmin = 100e6
+    fmax = fmin + 65536 * 1.2e6
+    rng = np.random.default_rng(3)
+    cs = fmin + rng.uniform(0.01, 0.99, n_hops) * (fmax - fmin)
+    x = _hops(n_hops, N, fftbw, seed=5)
+    psd_db = np.stack([oracle.psd_frames(x[h], N, "hann")[0] for h in range(n_hops)])
+    for h in range(n_hops):
+        oracle.lib().sdo_psd_shift_db(oracle.ptr(psd_db[h]), N)
+    ref = _oracle_view(oracle, psd_db, cs, fmin, fmax, fftbw, 0.5)
+    det = dict(alpha=0.5, gamma=0.5, snr=10.0, min_bins=2) if detect else None
+    out = panoramic.sweep(sdb, torch, None, torch.from_numpy(x).cuda(), cs, N, "hann", (fmin, fmax), fftbw, 0.5,
+                          detect=det)
+    for a, b in zip(out[:3], ref):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_panoramic_channel_lists_beyond_the_packed_read_back(sdb, oracle, monkeypatch):
+    """The sweep reads the channel lists back packed (a few per hop); a sweep that finds more than the packed buffer
+    holds is served from the full [hops][cap] array on demand: same lists either way."""
+    import torch
+    from sigdigger_b200 import panoramic
+    N, n_hops, fs, rel_bw = 16384, 9, 50e6, 0.5
+    fmin, fmax = 1.0e9, 1.0e9 + n_hops * fs * rel_bw
+    centers = fmin + fs * rel_bw * (0.5 + np.arange(n_hops))
+    xt = torch.from_numpy(_hops(n_hops, N, fs, seed=11)).cuda()
+    det = dict(alpha=1.0, gamma=0.5, snr=10.0, min_bins=2)
+    want = panoramic.sweep(sdb, torch, None, xt, centers, N, "hann", (fmin, fmax), fs, rel_bw, detect=det)[3]
+    assert sum(len(c) for c in want) > 4
+    monkeypatch.setenv("SDB_PANORAMIC_DENSE_CAP", "4")
+    got = panoramic.sweep(sdb, torch, None, xt, centers, N, "hann", (fmin, fmax), fs, rel_bw, detect=det)[3]
+    assert got == want
