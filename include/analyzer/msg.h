@@ -6,10 +6,15 @@
 #ifndef _SUSCAN_MSG_H
 #define _SUSCAN_MSG_H
 #include <sigutils/types.h>
+#include <sigutils/softtune.h>
+#include <analyzer/source/info.h>
 #include <sys/time.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* released exactly once per payload, from any thread (Suscan/Message.cpp:43-48) */
+void   suscan_analyzer_dispose_message(uint32_t type, void *ptr);
 
 /* ---- message types (Suscan/Analyzer.cpp:75-98) */
 #define SUSCAN_ANALYZER_MESSAGE_TYPE_SOURCE_INFO 0
@@ -42,14 +47,7 @@ enum suscan_analyzer_inspector_msgkind {
   SUSCAN_ANALYZER_INSPECTOR_MSGKIND_ORBIT_REPORT
 };
 
-/* ---- struct sigutils_channel (Suscan/Analyzer.cpp:417-424; include/Suscan/Channel.h:26-32) */
-struct sigutils_channel {
-  SUFREQ  fc, f_lo, f_hi;
-  SUFLOAT bw, snr, S0, N0;
-  SUFREQ  ft;
-  uint32_t age, present;
-};
-#define sigutils_channel_INITIALIZER { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }
+/* ---- struct sigutils_channel: <sigutils/softtune.h> */
 
 /* ---- typed key / value bag (include/Suscan/Config.h:36-76, Suscan/Config.cpp:72-73) */
 enum suscan_field_type {
@@ -185,24 +183,7 @@ struct suscan_analyzer_channel_msg {
   unsigned int channel_count;
 };
 
-struct suscan_source_gain_info { char *name; SUFLOAT min, max, step, value; };
-struct suscan_source_info {
-  uint64_t permissions;
-  SUSCOUNT source_samp_rate, effective_samp_rate;
-  SUFLOAT  measured_samp_rate;
-  SUFREQ   frequency, freq_min, freq_max, lnb;
-  SUFLOAT  bandwidth, ppm;
-  char    *antenna;
-  SUBOOL   dc_remove, iq_reverse, agc, seekable, replay;
-  SUSCOUNT history_length;
-  struct timeval source_time, source_start, source_end;
-  struct suscan_source_gain_info **gain_list; unsigned int gain_count;
-  char   **antenna_list; unsigned int antenna_count;
-};
-void   suscan_source_info_init(struct suscan_source_info *info);
-SUBOOL suscan_source_info_init_copy(struct suscan_source_info *dst, const struct suscan_source_info *src);
-void   suscan_source_info_finalize(struct suscan_source_info *info);
-
+/* struct suscan_source_info: <analyzer/source/info.h> */
 /* permissions (include/Suscan/Analyzer.h:113-123) */
 #define SUSCAN_ANALYZER_PERM_HALT            (1ull << 0)
 #define SUSCAN_ANALYZER_PERM_SET_FREQ        (1ull << 1)

@@ -45,6 +45,12 @@ typedef int      SUBOOL;
 typedef int32_t  SUHANDLE;
 typedef uint32_t SUBITS;
 
+/* sigutils/types.h carries these for its callers (SU_ATTEMPT, include/Suscan/Compat.h:28-36) */
+#ifndef STRINGIFY
+#  define _STRINGIFY(x) #x
+#  define STRINGIFY(x) _STRINGIFY(x)
+#endif
+
 #define SU_TRUE  1
 #define SU_FALSE 0
 
@@ -71,8 +77,9 @@ typedef uint32_t SUBITS;
 
 /* decibels: "power" = 10 log10, "magnitude" = 20 log10 (Suscan/Messages/PSDMessage.cpp:32-38 applies SU_POWER_DB
  * to the PSD bins; Default/GenericInspector/GenericInspector.cpp:232-254 adds 1e-20 by hand) */
+#define SUFLOAT_MIN_REF_MAG  1e-8f                     /* SPEC M.6: the floor the PSD kernels' dB epilogue uses too */
 #define SU_POWER_DB_RAW(p)  (10 * SU_LOG(p))
-#define SU_POWER_DB(p)      SU_POWER_DB_RAW((p) + 1e-20f)
+#define SU_POWER_DB(p)      SU_POWER_DB_RAW((p) + SUFLOAT_MIN_REF_MAG)
 #define SU_DB_RAW(m)        (20 * SU_LOG(m))
 #define SU_DB(m)            SU_DB_RAW((m) + 1e-10f)
 #define SU_POWER_MAG_RAW(d) SU_POW(10, (d) * .1f)

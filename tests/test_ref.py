@@ -204,3 +204,60 @@ def test_tv_worker_of_the_reference_over_the_tvproc_shim(ref, oracle, interlace,
                 k, sent = k + 1, True
     assert k == got
     t.close()
+
+
+REF2 = os.path.join(ROOT, "oracle", "_ref", "libsdref_suscan.so")
+
+
+@pytest.fixture(scope="module")
+def ref_suscan():
+    if not os.path.exists(REF2) and os.path.isdir("/root/reference"):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], capture_output=True)
+    if not os.path.exists(REF2):
+        pytest.skip("oracle/_ref/libsdref_suscan.so not built (needs /root/reference)")
+    L = C.CDLL(REF2)
+    L.ref_suscan_psd_message.restype = C.c_long
+    L.ref_suscan_psd_message.argtypes = [C.c_void_p, C.c_ulong, C.c_double, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_suscan_mq_samples.restype = C.c_long
+    L.ref_suscan_mq_samples.argtypes = [C.c_void_p, C.c_ulong, C.c_uint, C.c_void_p, C.c_void_p]
+    L.ref_suscan_status_message.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+    return L
+
+
+def test_psd_message_of_the_reference_over_the_shim_headers(ref_suscan, oracle):
+    """Suscan/Messages/PSDMessage.cpp + Suscan/Message.cpp COMPILED FROM THE REFERENCE against include/analyzer/msg.h:
+    the constructor's fft-shift + SU_POWER_DB pass (:26-39) is the reference's own; the oracle's sdo_psd_shift_db
+    (= the PSD kernels' SDB_FLAG_PSD_SHIFT_DB epilogue, bit for bit) is held to it -- the layout exactly, the values to
+    the difference between libm's log10f and the SPEC M polynomial."""
+    rng = np.random.default_rng(21)
+    n = 8192
+    lin = (rng.standard_normal(n) ** 2 * 10.0 ** rng.uniform(-9, 1, n)).astype(np.float32)
+    lin[:4] = [0.0, 1e-12, 1.0, 123.5]
+    out = np.zeros(n, np.float32)
+    fc, rate = C.c_double(), C.c_uint()
+    assert ref_suscan.ref_suscan_psd_message(lin.ctypes.data, n, 433.92e6, 2000000, out.ctypes.data, C.byref(fc),
+                                             C.byref(rate)) == n
+    assert fc.value == 433920000.0 and rate.value == 2000000
+    mine = lin.copy()
+    oracle.lib().sdo_psd_shift_db(oracle.ptr(mine), n)
+    assert np.all(np.isfinite(out)) and out.min() >= -80.0 - 1e-3          # the 1e-8 floor of SU_POWER_DB
+    assert np.max(np.abs(out - mine)) < 2e-5                                # dB; same bins in the same places
+    want = 10.0 * np.log10(np.concatenate([lin[n // 2:], lin[:n // 2]]).astype(np.float64) + 1e-8)
+    assert np.max(np.abs(out - want)) < 2e-5
+
+
+def test_mq_and_message_wrappers_of_the_reference_over_libsuscan(ref_suscan):
+    """Suscan/MQ.cpp (caller-owned suscan_mq: init / read / finalize), SamplesMessage and StatusMessage over the shim
+    library: payloads posted with suscan_mq_write come back through the reference's wrapper classes and are released by
+    their shared_ptr deleter (suscan_analyzer_dispose_message)."""
+    rng = np.random.default_rng(22)
+    x = (rng.standard_normal(1000) + 1j * rng.standard_normal(1000)).astype(np.complex64)
+    out = np.zeros_like(x)
+    iid = C.c_uint()
+    assert ref_suscan.ref_suscan_mq_samples(x.ctypes.data, x.size, 0xBEEF, out.ctypes.data, C.byref(iid)) == x.size
+    assert iid.value == 0xBEEF and np.array_equal(out, x)
+    buf = C.create_string_buffer(64)
+    assert ref_suscan.ref_suscan_status_message(-1, b"source failed to start", buf, 64) == -1
+    assert buf.value == b"source failed to start"
+    assert ref_suscan.ref_suscan_status_message(0, None, buf, 64) == 0 and buf.value == b""
