@@ -8,6 +8,7 @@
 #ifndef _SIGUTILS_SPECTTUNER_H
 #define _SIGUTILS_SPECTTUNER_H
 #include <sigutils/types.h>
+#include <sigutils/sampling.h>   /* SU_NORM2ANG_FREQ and friends: Tasks/LPFTask.cpp:64 uses them through this header */
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -9,6 +9,10 @@
 //   Tasks/WaveSampler.cpp          sampleManual / sampleZeroCrossing / sampleGardner (the latter over this repo's
 //                                  su_clock_detector shim)        -> sdo_sample_manual / _zero_crossing
 //   Misc/Averager.cpp              Averager::feed                 -> sdo_averager_feed
+//   Tasks/CostasRecoveryTask.cpp, PLLSyncTask.cpp, AGCTask.cpp, CarrierXlator.cpp, LPFTask.cpp   constructor + work()
+//                                  loops over this repo's <sigutils/{pll,agc,ncqo,specttuner}.h> (the Tasks/ of the
+//                                  north-star, drop-in)           -> sdo_costas / sdo_pll / sdo_agc / sdo_ncqo / specttuner
+//   Tasks/HistogramFeeder.cpp      HistogramFeeder::work          -> sdo_histogram_feed
 //   Default/GenericInspector/TVProcessorWorker.cpp   the TV tab's worker (setParams / start / pushData / process /
 //                                  work with its frame acknowledgement window) over this repo's <sigutils/tvproc.h>
 //                                                                  -> the reference drives su_tv_processor_* unmodified
@@ -20,6 +24,12 @@
 #include <WaveSampler.h>
 #include <Averager.h>
 #include <TVProcessorWorker.h>
+#include <CostasRecoveryTask.h>
+#include <PLLSyncTask.h>
+#include <AGCTask.h>
+#include <CarrierXlator.h>
+#include <HistogramFeeder.h>
+#include <LPFTask.h>
 
 // ---- Suscan::CancellableTask plumbing (Suscan/CancellableTask.cpp is Qt glue, not DSP)
 Suscan::CancellableTask::CancellableTask(QObject *parent) : QObject(parent) { prog = 0; }
@@ -57,6 +67,13 @@ void SigDigger::TVProcessorWorker::frame(struct sigutils_tv_frame_buffer *f)
 }
 void SigDigger::TVProcessorWorker::error(QString) { if (g_tv_sink) g_tv_sink->failed = true; }
 void SigDigger::TVProcessorWorker::paramsChanged(sigutils_tv_processor_params) {}
+
+// ---- HistogramFeeder::data signal
+static thread_local std::vector<float> *g_hist_out = nullptr;
+void SigDigger::HistogramFeeder::data(const float *d, unsigned int size)
+{
+  if (g_hist_out) g_hist_out->insert(g_hist_out->end(), d, d + size);
+}
 
 extern "C" {
 
@@ -154,6 +171,42 @@ long ref_tv_worker(const struct sigutils_tv_processor_params *params, const floa
   w.stop();
   g_tv_sink = nullptr;
   return result;
+}
+
+
+// ---- the Tasks/ of the north-star, from the reference: constructor + work() until it returns false
+int ref_task_costas(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, float tau, float loopbw, int kind)
+{
+  try { CostasRecoveryTask t(data, dst, n, tau, loopbw, (enum sigutils_costas_kind) kind); while (t.work()) ; return 0; }
+  catch (...) { return -1; }
+}
+int ref_task_pll(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, float cutoff)
+{
+  try { PLLSyncTask t(data, dst, n, cutoff); while (t.work()) ; return 0; } catch (...) { return -1; }
+}
+int ref_task_agc(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, float tau)
+{
+  try { AGCTask t(data, dst, n, tau); while (t.work()) ; return 0; } catch (...) { return -1; }
+}
+int ref_task_xlate(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, float relFreq, float phase)
+{
+  try { SigDigger::CarrierXlator t(data, dst, n, relFreq, phase); while (t.work()) ; return 0; } catch (...) { return -1; }
+}
+int ref_task_lpf(const SUCOMPLEX *data, SUCOMPLEX *dst, size_t n, float bw)        // specttuner: needs the GPU
+{
+  try { LPFTask t(data, dst, n, bw); while (t.work()) ; return 0; } catch (...) { return -1; }
+}
+long ref_task_histogram(const SUCOMPLEX *data, size_t n, int space, float *out, size_t cap)
+{
+  SigDigger::SamplingProperties props;
+  memset(&props, 0, sizeof(props));
+  props.space = (SigDigger::SamplingSpace) space; props.data = data; props.length = n;
+  std::vector<float> got;
+  g_hist_out = &got;
+  { SigDigger::HistogramFeeder t(props); while (t.work()) ; }
+  g_hist_out = nullptr;
+  for (size_t i = 0; i < got.size() && i < cap; ++i) out[i] = got[i];
+  return (long) got.size();
 }
 
 }  // extern "C"

@@ -261,3 +261,58 @@ def test_mq_and_message_wrappers_of_the_reference_over_libsuscan(ref_suscan):
     assert ref_suscan.ref_suscan_status_message(-1, b"source failed to start", buf, 64) == -1
     assert buf.value == b"source failed to start"
     assert ref_suscan.ref_suscan_status_message(0, None, buf, 64) == 0 and buf.value == b""
+
+
+def _qpsk(n, seed=5):
+    from sigdigger_b200 import synth
+    x, _ = synth.multi_carrier(n, 1.0, [("qpsk", 0.01, 0.1, -6.0, {})], noise_db=-40.0, seed=seed)
+    return np.ascontiguousarray(x, np.complex64)
+
+
+def test_tasks_of_the_reference_over_the_sigutils_shim(ref, oracle):
+    """Tasks/CostasRecoveryTask.cpp, PLLSyncTask.cpp, AGCTask.cpp, CarrierXlator.cpp COMPILED FROM THE REFERENCE
+    (constructor + work() loops, `destination[p] = su_costas_feed(&costas, origin[p])`) over this repo's
+    <sigutils/{pll,agc,ncqo}.h> and libsigutils.so: the north-star's "Tasks/ are drop-in".  Outputs equal the oracle's
+    bit for bit (the shim's per-sample entry points run the kernels' step functions on the host)."""
+    import shim_build as SB
+    n = 2 * 4096 + 777
+    x = _qpsk(n)
+    y = np.zeros(n, np.complex64)
+    for fn, args in (("ref_task_costas", [C.c_float(10.0), C.c_float(2e-3), 2]),
+                     ("ref_task_pll", [C.c_float(5e-3)]), ("ref_task_agc", [C.c_float(20.0)]),
+                     ("ref_task_xlate", [C.c_float(0.0123), C.c_float(0.5)])):
+        getattr(ref, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [type(a) if not isinstance(a, int) else C.c_int
+                                                                            for a in args]
+    for kind in (1, 2, 3):
+        assert ref.ref_task_costas(x.ctypes.data, y.ctypes.data, n, C.c_float(10.0), C.c_float(2e-3), kind) == 0
+        assert np.array_equal(y.view(np.uint32), SB.oracle_costas(oracle, x, kind, 0.1, 2e-3).view(np.uint32))
+    assert ref.ref_task_pll(x.ctypes.data, y.ctypes.data, n, C.c_float(5e-3)) == 0
+    assert np.array_equal(y.view(np.uint32), SB.oracle_pll(oracle, x, 5e-3).view(np.uint32))
+    assert ref.ref_task_agc(x.ctypes.data, y.ctypes.data, n, C.c_float(20.0)) == 0
+    assert np.array_equal(y.view(np.uint32), SB.oracle_agc(oracle, x, 20.0).view(np.uint32))
+    assert ref.ref_task_xlate(x.ctypes.data, y.ctypes.data, n, C.c_float(0.0123), C.c_float(0.5)) == 0
+    assert np.array_equal(y.view(np.uint32), SB.oracle_xlate(oracle, x, 0.0123, 0.5).view(np.uint32))
+
+
+def test_histogram_feeder_of_the_reference(ref, oracle):
+    """Tasks/HistogramFeeder.cpp compiled from the reference against the oracle's restatement (SPEC Y.2): amplitude
+    exactly; phase / frequency to one ulp of libm's cargf against the SPEC M atan2."""
+    ref.ref_task_histogram.restype = C.c_long
+    ref.ref_task_histogram.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+    L = oracle.lib()
+    L.sdo_histogram_feed.restype = C.c_size_t
+    L.sdo_histogram_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    n = 3 * 4096 + 55
+    x = _qpsk(n, seed=8)
+    for space, tol in ((0, 0.0), (1, 4e-7), (2, 4e-7)):
+        got = np.zeros(n, np.float32)
+        mine = np.zeros(n, np.float32)
+        k = ref.ref_task_histogram(x.ctypes.data, n, space, got.ctypes.data, n)
+        m = L.sdo_histogram_feed(x.ctypes.data, mine.ctypes.data, n, space)
+        assert k == m == (n - 1 if space == 2 else n)
+        if tol == 0.0:
+            assert np.max(np.abs(got[:k] - mine[:k]) / np.maximum(np.abs(mine[:k]), 1e-30)) < 2e-7   # cabsf vs SPEC M
+        else:
+            d = np.abs(got[:k] - mine[:k])
+            d = np.minimum(d, np.abs(d - 2 * np.pi))                  # +-pi branch
+            assert d.max() < tol
