@@ -91,8 +91,15 @@ typedef uint32_t SUBITS;
 #define SU_SPLPF_ALPHA(tau)     (1.f - SU_EXP(-1.f / (tau)))
 #define SU_SPLPF_FEED(y, x, a)  (y) += (a) * ((x) - (y))
 
-/* the FFTW prefix the GUI-side tasks paste (Tasks/CarrierDetector.cpp:58-75); FFTW itself is not part of this shim */
+/* the FFTW prefix the GUI-side tasks paste (Tasks/CarrierDetector.cpp:58-75); FFTW itself is not part of this shim:
+ * the GUI links fftw3f on its own (SigDigger.pro:486), and like upstream's types.h this header pulls <fftw3.h> in when
+ * the build has it */
 #define SU_FFTW(method) fftwf##method
+#if defined(__has_include)
+#  if __has_include(<fftw3.h>)
+#    include <fftw3.h>
+#  endif
+#endif
 
 #ifdef __cplusplus
 extern "C" {

@@ -13,6 +13,11 @@
 //                                  loops over this repo's <sigutils/{pll,agc,ncqo,specttuner}.h> (the Tasks/ of the
 //                                  north-star, drop-in)           -> sdo_costas / sdo_pll / sdo_agc / sdo_ncqo / specttuner
 //   Tasks/HistogramFeeder.cpp      HistogramFeeder::work          -> sdo_histogram_feed
+//   Tasks/CarrierDetector.cpp      CarrierDetector::work (Blackman-Harris taps of this repo's <sigutils/taps.h>, FFT
+//                                  through the ref_shim/fftw3.h stand-in, notch, arg-max, circular centroid)
+//                                                                  -> sdo_carrier_detect
+//   Misc/SNREstimator.cpp          SNREstimator (setBps / setAlpha / setSigma / feed / getSigma / getSNR / getModel)
+//                                                                  -> sdo_snr_*
 //   Default/GenericInspector/TVProcessorWorker.cpp   the TV tab's worker (setParams / start / pushData / process /
 //                                  work with its frame acknowledgement window) over this repo's <sigutils/tvproc.h>
 //                                                                  -> the reference drives su_tv_processor_* unmodified
@@ -30,6 +35,9 @@
 #include <CarrierXlator.h>
 #include <HistogramFeeder.h>
 #include <LPFTask.h>
+#include <SNREstimator.h>
+#include <CarrierDetector.h>
+#include <cmath>
 
 // ---- Suscan::CancellableTask plumbing (Suscan/CancellableTask.cpp is Qt glue, not DSP)
 Suscan::CancellableTask::CancellableTask(QObject *parent) : QObject(parent) { prog = 0; }
@@ -73,6 +81,42 @@ static thread_local std::vector<float> *g_hist_out = nullptr;
 void SigDigger::HistogramFeeder::data(const float *d, unsigned int size)
 {
   if (g_hist_out) g_hist_out->insert(g_hist_out->end(), d, d + size);
+}
+
+// ---- the FFTW stand-in of ref_shim/fftw3.h: radix-2, binary64 inside
+struct ref_fftwf_plan_s { int n; fftwf_complex *in, *out; int sign; };
+extern "C" void *fftwf_malloc(size_t n) { return malloc(n); }
+extern "C" void fftwf_free(void *p) { free(p); }
+extern "C" fftwf_plan fftwf_plan_dft_1d(int n, fftwf_complex *in, fftwf_complex *out, int sign, unsigned)
+{
+  if (n < 1 || (n & (n - 1))) return nullptr;
+  ref_fftwf_plan_s *p = new ref_fftwf_plan_s{ n, in, out, sign };
+  return p;
+}
+extern "C" void fftwf_destroy_plan(fftwf_plan p) { delete p; }
+extern "C" void fftwf_execute(const fftwf_plan p)
+{
+  const int n = p->n;
+  std::vector<double> re(n), im(n);
+  for (int i = 0, j = 0; i < n; ++i) {            // bit reversal
+    re[j] = p->in[i][0]; im[j] = p->in[i][1];
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    const double ang = (p->sign < 0 ? -2.0 : 2.0) * M_PI / len;
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const double wr = cos(ang * k), wi = sin(ang * k);
+        const double ur = re[i + k], ui = im[i + k];
+        const double vr = re[i + k + len / 2] * wr - im[i + k + len / 2] * wi;
+        const double vi = re[i + k + len / 2] * wi + im[i + k + len / 2] * wr;
+        re[i + k] = ur + vr; im[i + k] = ui + vi;
+        re[i + k + len / 2] = ur - vr; im[i + k + len / 2] = ui - vi;
+      }
+  }
+  for (int i = 0; i < n; ++i) { p->out[i][0] = (float) re[i]; p->out[i][1] = (float) im[i]; }
 }
 
 extern "C" {
@@ -207,6 +251,34 @@ long ref_task_histogram(const SUCOMPLEX *data, size_t n, int space, float *out, 
   g_hist_out = nullptr;
   for (size_t i = 0; i < got.size() && i < cap; ++i) out[i] = got[i];
   return (long) got.size();
+}
+
+
+// ---- Misc/SNREstimator.cpp: `feeds` successive histories of `length` bins each
+int ref_snr_estimator(unsigned bps, float alpha, float sigma0, const unsigned *histories, unsigned length, unsigned feeds,
+                      float *sigma_out, float *snr_out, float *model_out)
+{
+  SigDigger::SNREstimator e;
+  e.setBps(bps);
+  e.setAlpha(alpha);
+  if (sigma0 > 0) e.setSigma(sigma0);
+  for (unsigned f = 0; f < feeds; ++f) {
+    std::vector<unsigned int> h(histories + (size_t) f * length, histories + (size_t) (f + 1) * length);
+    e.feed(h);
+    sigma_out[f] = e.getSigma(); snr_out[f] = e.getSNR();
+  }
+  const std::vector<float> &m = e.getModel();
+  for (size_t i = 0; i < m.size() && i < length; ++i) model_out[i] = m[i];
+  return (int) m.size();
+}
+
+
+// ---- Tasks/CarrierDetector.cpp: the four work() states, then the peak (rad / sample)
+float ref_carrier_detect(const SUCOMPLEX *data, size_t n, double avgRelBw, double dcNotchRelBw)
+{
+  SigDigger::CarrierDetector d(data, n, avgRelBw, dcNotchRelBw);
+  while (d.work()) ;
+  return d.getPeak();
 }
 
 }  // extern "C"

@@ -316,3 +316,45 @@ def test_histogram_feeder_of_the_reference(ref, oracle):
             d = np.abs(got[:k] - mine[:k])
             d = np.minimum(d, np.abs(d - 2 * np.pi))                  # +-pi branch
             assert d.max() < tol
+
+
+def test_snr_estimator_restatement_tracks_the_compiled_reference(ref, oracle):
+    """Misc/SNREstimator.cpp compiled from the reference against the oracle's restatement (SPEC Y.7): same trajectory
+    of sigma over successive feeds and the same model histogram, to the difference between libm's exp and SPEC M's."""
+    ref.ref_snr_estimator.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(4)
+    for bps, length in ((1, 256), (2, 256), (3, 400)):
+        k = 1 << bps
+        centres = (rng.integers(0, k, 200000) + 0.5) / k
+        v = (centres + 0.03 * rng.standard_normal(200000)) % 1.0
+        h = np.bincount((v * length).astype(int) % length, minlength=length).astype(np.uint32)
+        feeds = 6
+        hs = np.ascontiguousarray(np.tile(h, (feeds, 1)))
+        sig, snr, model = np.zeros(feeds, np.float32), np.zeros(feeds, np.float32), np.zeros(length, np.float32)
+        assert ref.ref_snr_estimator(bps, C.c_float(0.5), C.c_float(0.0), hs.ctypes.data, length, feeds,
+                                     sig.ctypes.data, snr.ctypes.data, model.ctypes.data) == length
+        e = oracle.SnrEstimator(bps, length, alpha=0.5)
+        for f in range(feeds):
+            e.feed(h)
+            assert abs(e.sigma - sig[f]) <= 5e-5 * abs(sig[f]), (bps, f, e.sigma, sig[f])
+            assert abs(e.snr - snr[f]) <= 1e-4 * abs(snr[f])
+        assert np.abs(e.model() - model).max() < 5e-5
+        e.close()
+
+
+def test_carrier_detector_restatement_tracks_the_compiled_reference(ref, oracle):
+    """Tasks/CarrierDetector.cpp compiled from the reference (Blackman-Harris taps from this repo's <sigutils/taps.h>,
+    its FFT through a binary64 stand-in for FFTW) against sdo_carrier_detect (SPEC Y.5, binary32 SPEC transform): the
+    same peak to the transforms' rounding."""
+    ref.ref_carrier_detect.restype = C.c_float
+    ref.ref_carrier_detect.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double]
+    rng = np.random.default_rng(12)
+    for n, f0, notch in ((5000, 0.0371, 0.0), (16384, -0.212, 0.0), (3000, 0.11, 0.05), (9000, -0.4, 0.02)):
+        t = np.arange(n)
+        x = (np.exp(2j * np.pi * f0 * t) * (1 + 0.3 * np.cos(2 * np.pi * 0.001 * t))
+             + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) + 0.5).astype(np.complex64)
+        got = float(ref.ref_carrier_detect(x.ctypes.data, n, 0.01, notch))
+        mine = float(oracle.carrier_detect(x, 0.01, notch))
+        assert abs(got - mine) < 2e-5, (n, f0, got, mine)
+        assert abs(got - 2 * np.pi * f0) < 2e-3 or notch > 0
