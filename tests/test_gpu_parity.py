@@ -56,8 +56,8 @@ def test_psd_multistream_and_chunks(sdb, oracle):
     assert np.array_equal(np.concatenate([a, b], axis=1), got)
 
 
-def test_psd_shift_db_epilogue(sdb, oracle):
-    N = 16384
+@pytest.mark.parametrize("N", [16384, 32768, 65536])          # generic four-step, SPEC F.5 and F.4 row kernels
+def test_psd_shift_db_epilogue(sdb, oracle, N):
     x = _noise(N * 2, seed=5, scale=0.2)
     e = sdb.Engine(n_streams=1, psd_size=N, psd_window="hann", max_feed=N * 2, flags=sdb.FLAG_PSD_SHIFT_DB)
     e.commit()
@@ -495,7 +495,8 @@ def test_native_sample_formats(sdb, oracle, fmt):
                                     exact_soft=True)
 
 
-@pytest.mark.parametrize("fmt,N", [("f32", 65536), ("f32", 4096), ("s16", 65536), ("u8", 8192)])
+@pytest.mark.parametrize("fmt,N", [("f32", 65536), ("f32", 4096), ("s16", 65536), ("u8", 8192), ("f32", 32768),
+                                   ("s16", 32768), ("u8", 32768)])
 def test_iq_reverse_flag(sdb, fmt, N):
     """SDB_FLAG_IQ_REVERSE (suscan_analyzer_set_iq_reverse): the swap happens inside the first load, for every
     transform size path and sample format, history across feeds included: bit-identical to feeding (Q, I)."""
