@@ -34,6 +34,11 @@ def main():
     xl = torch.from_numpy(x[lo:hi]).cuda()
     res = panoramic.sweep(sdb, torch, dist, xl, centers, N, "blackmann_harris", (fmin, fmax), fs, rel_bw,
                           device=local)
+    # the same sweep with the per-hop channel detector: the lists cross NVLink section by section and are read back
+    # packed on rank 0; they must equal those of a single-rank sweep over all hops
+    det = dict(alpha=1.0, gamma=0.5, snr=8.0, min_bins=2)
+    res_det = panoramic.sweep(sdb, torch, dist, xl, centers, N, "blackmann_harris", (fmin, fmax), fs, rel_bw,
+                              device=local, detect=det)
     ok = True
     if rank == 0:
         import oracle_lib as O
@@ -52,7 +57,13 @@ def main():
         psd, acc, cnt = res
         ok = (np.array_equal(cnt, ref[2]) and np.array_equal(acc.view(np.uint32), ref[1].view(np.uint32))
               and np.array_equal(psd.view(np.uint32), ref[0].view(np.uint32)))
-        print("panoramic multi-GPU sweep: world=%d hops=%d bins=%d exact=%s" % (world, n_hops, n, ok))
+        one = panoramic.sweep(sdb, torch, None, torch.from_numpy(x).cuda(), centers, N, "blackmann_harris", (fmin, fmax),
+                              fs, rel_bw, device=local, detect=det)
+        same_view = all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(res_det[:3], res))
+        same_lists = res_det[3] == one[3] and sum(len(c) for c in one[3]) >= n_hops
+        ok = ok and same_view and same_lists
+        print("panoramic multi-GPU sweep: world=%d hops=%d bins=%d exact=%s (detector lists equal: %s)"
+              % (world, n_hops, n, ok, same_lists))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
