@@ -13,6 +13,23 @@ from sigdigger_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+class Gate:
+    """Gate of the in-memory source: the analyzer's worker handles its request queue, then reads a block.  The read
+    callback parks in wait(); `parked` tells the test that the worker is past its request loop, so that requests sent
+    now take effect after the block about to be released (without it the tests raced the worker's start-up)."""
+
+    def __init__(self):
+        self.go, self.parked = threading.Event(), threading.Event()
+
+    def wait(self, timeout):
+        self.parked.set()
+        return self.go.wait(timeout)
+
+    def set(self):
+        self.go.set()
+
+
+
 def test_analyzer_message_flow_and_parity(sdb, oracle):
     from sigdigger_b200.analyzer import Analyzer
     N, fs = 8192, 1.0e6
@@ -20,7 +37,7 @@ def test_analyzer_message_flow_and_parity(sdb, oracle):
     blocks, per_block = 6, N * 8
     n = blocks * per_block
     x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs + 3.0, baud, -10.0, {})], noise_db=-50.0, seed=31)
-    go = threading.Event()
+    go = Gate()
     pos = [0]
 
     def read(priv, dst, maxn):                    # plays the role of a file / SDR source back-end
@@ -34,6 +51,7 @@ def test_analyzer_message_flow_and_parity(sdb, oracle):
     a = Analyzer(fs, window_size=N, window="blackmann_harris", psd_update_int=N / fs, read=read, read_size=per_block)
     name, info = a.read(5000)
     assert name == "SOURCE_INFO"
+    assert go.parked.wait(10)
     # the worker is now blocked in the first read; queue the handshake, then let the source run
     a.open("psk", 0.125 * fs, 3 * baud, req_id=11)
     a.open("nope", 0.0, 1000.0, req_id=12)                       # unknown class -> WRONG_KIND
@@ -174,7 +192,7 @@ def test_analyzer_history_and_replay(sdb):
     from sigdigger_b200.analyzer import Analyzer
     N, fs = 4096, 1.0e6
     blk = N * 2
-    go = threading.Event()
+    go = Gate()
     step = threading.Semaphore(0)
     calls = [0]
 
@@ -190,6 +208,7 @@ def test_analyzer_history_and_replay(sdb):
 
     a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, read=read, read_size=blk)
     assert a.read(5000)[0] == "SOURCE_INFO"
+    assert go.parked.wait(10)          # requests sent from here on are handled after the first block
     assert a.set_history_size(3 * blk)
     go.set()
 
@@ -258,7 +277,7 @@ def test_analyzer_inspector_watermark(sdb):
     x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs, baud, -10.0, {})], noise_db=-50.0, seed=2)
 
     def run(watermark):
-        go = threading.Event()
+        go = Gate()
         pos = [0]
 
         def read(priv, dst, maxn):
@@ -271,6 +290,7 @@ def test_analyzer_inspector_watermark(sdb):
 
         a = Analyzer(fs, window_size=N, window="hann", psd_update_int=1.0, read=read, read_size=N * 8)
         assert a.read(5000)[0] == "SOURCE_INFO"
+        assert go.parked.wait(10)          # requests sent from here on are handled after the first block
         a.open("psk", 0.125 * fs, 3 * baud, req_id=1)
         a.set_inspector_id(0, 5, req_id=2)
         cfg = sdb.InspectorConfig()
@@ -306,7 +326,7 @@ def test_analyzer_overridable_freq_and_bandwidth(sdb):
     N, fs = 4096, 1.0e6
     n = 10 * N * 4
     x = (0.3 * np.exp(2j * np.pi * 0.2 * np.arange(n))).astype(np.complex64)
-    go = threading.Event()
+    go = Gate()
     step = threading.Semaphore(0)
     pos = [0]
 
@@ -321,6 +341,7 @@ def test_analyzer_overridable_freq_and_bandwidth(sdb):
 
     a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, read=read, read_size=N * 4)
     assert a.read(5000)[0] == "SOURCE_INFO"
+    assert go.parked.wait(10)          # requests sent from here on are handled after the first block
     a.open("raw", 0.1 * fs, fs / 16.0, req_id=1)
     a.set_inspector_id(0, 9, req_id=2)
     go.set()
@@ -376,7 +397,7 @@ def test_analyzer_source_options(sdb, oracle):
         samples *= np.float32(0.5)
         return True
 
-    go = threading.Event()
+    go = Gate()
     pos = [0]
 
     def read(priv, dst, maxn):
@@ -389,6 +410,7 @@ def test_analyzer_source_options(sdb, oracle):
 
     a = Analyzer(fs, window_size=N, window="hann", psd_update_int=0.0, read=read, read_size=N * 4)
     assert a.read(5000)[0] == "SOURCE_INFO"
+    assert go.parked.wait(10)          # requests sent from here on are handled after the first block
     a.register_baseband_filter(recorder)
     a.register_baseband_filter(scaler)
     a.set_iq_reverse(True)
@@ -435,7 +457,7 @@ def test_analyzer_subcarrier_inspector(sdb, oracle):
     blocks, per_block = 6, N * 8
     n = blocks * per_block
     x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs + fs / 64.0, baud, -10.0, {})], noise_db=-55.0, seed=17)
-    go = threading.Event()
+    go = Gate()
     pos = [0]
 
     def read(priv, dst, maxn):
@@ -448,6 +470,7 @@ def test_analyzer_subcarrier_inspector(sdb, oracle):
 
     a = Analyzer(fs, window_size=N, window="hann", psd_update_int=1.0, read=read, read_size=per_block)
     assert a.read(5000)[0] == "SOURCE_INFO"
+    assert go.parked.wait(10)          # requests sent from here on are handled after the first block
     a.open("raw", 0.125 * fs, fs / 8.0, req_id=1)                       # parent: 1024-point channel, fs / 8
     a.open("psk", fs / 64.0, 3 * baud, req_id=2, parent=0)             # child, relative to the parent's centre
     a.open("psk", 0.0, 1e9, req_id=3, parent=1)                        # wider than the parent's channel -> INVALID_CHANNEL
@@ -504,7 +527,7 @@ def test_analyzer_nested_subcarrier_inspectors(sdb, oracle):
     # carrier at fs/8 (parent centre) + fs/64 (child centre, in the parent) + fs/512 (grandchild centre, in the child)
     x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs + fs / 64.0 + fs / 512.0, baud, -10.0, {})], noise_db=-55.0,
                                seed=23)
-    go = threading.Event()
+    go = Gate()
     pos = [0]
 
     def read(priv, dst, maxn):
@@ -517,6 +540,7 @@ def test_analyzer_nested_subcarrier_inspectors(sdb, oracle):
 
     a = Analyzer(fs, window_size=N, window="hann", psd_update_int=1.0, read=read, read_size=per_block)
     assert a.read(5000)[0] == "SOURCE_INFO"
+    assert go.parked.wait(10)          # requests sent from here on are handled after the first block
     fs_par = fs / 8.0                                                   # 1024-point channel
     fs_mid = fs_par / 4.0                                               # 256-point channel of the parent's 1024
     a.open("raw", 0.125 * fs, fs / 8.0, req_id=1)                       # handle 0
@@ -583,7 +607,7 @@ def test_analyzer_spectrum_estimator_and_channel_messages(sdb, oracle):
     blocks, per_block = 5, N * 16
     n = blocks * per_block
     x, _ = synth.multi_carrier(n, fs, [("qpsk", 0.125 * fs, baud, -10.0, {})], noise_db=-50.0, seed=5)
-    go = threading.Event()
+    go = Gate()
     pos = [0]
 
     def read(priv, dst, maxn):
@@ -597,6 +621,7 @@ def test_analyzer_spectrum_estimator_and_channel_messages(sdb, oracle):
     a = Analyzer(fs, window_size=N, window="blackmann_harris", psd_update_int=1.0, read=read, read_size=per_block,
                  channel_update_int=per_block / fs, alpha=0.5, gamma=0.5, snr=10.0, freq=433e6)
     assert a.read(5000)[0] == "SOURCE_INFO"
+    assert go.parked.wait(10)          # requests sent from here on are handled after the first block
     a.open("psk", 0.125 * fs, 8 * baud, req_id=1)          # 8 samples per symbol at the channel rate
     a.set_inspector_id(0, 77, req_id=2)
     a.set_spectrum_source(0, sdb.SPECTSRC["exp_4"], req_id=3)
