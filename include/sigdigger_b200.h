@@ -636,6 +636,9 @@ int      sdb_panoramic_sweep_host(sdb_panoramic_t *s, const sdb_complex *hops_lo
 int      sdb_panoramic_reset(sdb_panoramic_t *s);                       /* SpectrumView::reset */
 uint32_t sdb_panoramic_size(const sdb_panoramic_t *s);
 int      sdb_panoramic_read(sdb_panoramic_t *s, float *psd, float *accum, float *count, size_t cap);   /* rank 0 */
+/* channels the detector found in hop `hop` of the LAST sweep (rank 0, detector enabled; valid until the next sweep).
+ * The sweep reads the lists back packed behind an event; a sweep with more than ~8 channels per hop on average is
+ * served from the full device array on the first call. */
 long     sdb_panoramic_read_channels(sdb_panoramic_t *s, size_t hop, sdb_detected_channel *out, size_t cap);
 int      sdb_panoramic_last_timing(const sdb_panoramic_t *s, sdb_panoramic_timing *t);
 const char *sdb_panoramic_last_error(void);
