@@ -149,36 +149,45 @@ static void fft8(sdo_cpx *v)
   fft4(&v[4], &v[5], &v[6], &v[7]);
 }
 
-/* 128-point forward transform of 128 values at stride `stride` of `in`, = 8 x 16: n = t + 8 j -> fft16 over j ->
- * x W_128^(t ka) -> fft8 over t (F.5).  out[k], k = ka + 16 kb. */
-static void fft128_16x8(const sdo_cpx *in, size_t stride, const float *win, size_t wstride,
-                        const sdo_cpx *tw128, sdo_cpx *out)
+/* (16 T)-point forward transform of 16 T values at stride `stride` of `in`, T = 2, 4 or 8: n = t + T j -> fft16 over j ->
+ * x W_(16T)^(t ka) -> T-point butterfly over t (F.5).  out[k], k = ka + 16 kb; X[kb] of the T-point butterfly sits at
+ * position pos(kb): T = 8: 4 (kb & 1) + (kb >> 1) (fft8); T = 4: kb (DFT4); T = 2: kb. */
+static void fft16T(const sdo_cpx *in, size_t stride, const float *win, size_t wstride, const sdo_cpx *twN1, int T,
+                   sdo_cpx *out)
 {
   sdo_cpx y[16][8];    /* [ka][t] */
   int t, j, q, ka;
-  for (t = 0; t < 8; ++t) {
+  for (t = 0; t < T; ++t) {
     sdo_cpx v[16];
     for (j = 0; j < 16; ++j) {
-      v[j] = in[(size_t) (t + 8 * j) * stride];
-      if (win) { float w = win[(size_t) (t + 8 * j) * wstride]; v[j].re *= w; v[j].im *= w; }
+      v[j] = in[(size_t) (t + T * j) * stride];
+      if (win) { float w = win[(size_t) (t + T * j) * wstride]; v[j].re *= w; v[j].im *= w; }
     }
     fft16(v);
     for (q = 0; q < 16; ++q) {
       ka = REV16(q);
-      y[ka][t] = ka ? cmul(v[q], tw128[t * ka]) : v[q];
+      y[ka][t] = ka ? cmul(v[q], twN1[t * ka]) : v[q];
     }
   }
   for (ka = 0; ka < 16; ++ka) {
     sdo_cpx v[8];
-    for (t = 0; t < 8; ++t) v[t] = y[ka][t];
-    fft8(v);
-    for (q = 0; q < 8; ++q) out[ka + 16 * REV8(q)] = v[q];
+    for (t = 0; t < T; ++t) v[t] = y[ka][t];
+    if (T == 8) {
+      fft8(v);
+      for (q = 0; q < 8; ++q) out[ka + 16 * REV8(q)] = v[q];
+    } else if (T == 4) {
+      fft4(&v[0], &v[1], &v[2], &v[3]);
+      for (q = 0; q < 4; ++q) out[ka + 16 * q] = v[q];
+    } else {
+      out[ka] = cadd(v[0], v[1]);
+      out[ka + 16] = csub(v[0], v[1]);
+    }
   }
 }
 
 /* Plans: tables and scratch for one transform size.
  *   N == 65536            -> F.4 (256 x 256, fft16 butterflies, coarse x fine inter-pass twiddle)
- *   N == 32768            -> F.5 (128 x 256: columns 8 x 16 = fft16 + fft8, rows as F.4)
+ *   N == 32768 / 16384 / 8192 -> F.5 (N1 x 256, N1 = 16 T: columns = fft16 + T-point butterfly, rows as F.4)
  *   N <= 4096 && !four    -> F.2 single Stockham transform
  *   otherwise             -> F.3 four-step N1 x N2 with Stockham sub-transforms
  * `four` forces the four-step form (the channeliser's forward transform always uses it). */
@@ -192,9 +201,9 @@ int sdo_spec_plan_init(sdo_spec_plan *p, unsigned N, int four)
   if (N == 65536) {
     p->kind = 2; p->N1 = 256; p->N2 = 256;
     p->tw_a = sdo_spec_twiddles(256);
-  } else if (N == 32768) {
-    p->kind = 3; p->N1 = 128; p->N2 = 256;         /* F.5 */
-    p->tw_a = sdo_spec_twiddles(128);
+  } else if (N == 32768 || N == 16384 || N == 8192) {
+    p->kind = 3; p->N1 = N / 256; p->N2 = 256;     /* F.5: N1 = 16 T, T = 8 / 4 / 2 */
+    p->tw_a = sdo_spec_twiddles(p->N1);
     p->tw_b = sdo_spec_twiddles(256);
   } else if (N <= 4096 && !four) {
     p->kind = 0; p->N1 = N; p->N2 = 1;
@@ -239,19 +248,20 @@ void sdo_spec_forward(const sdo_spec_plan *p, const sdo_cpx *x, const float *win
     return;
   }
   if (p->kind == 3) {
-    /* F.5: 256 columns of 128 (8 x 16), inter-pass twiddle W_32768^p = W_128^(p >> 8) x W_32768^(p & 255), 128 rows of 256 */
+    /* F.5: 256 columns of N1 = 16 T, inter-pass twiddle W_N^p = W_N1^(p >> 8) x W_N^(p & 255), N1 rows of 256 */
     sdo_cpx col[256];
+    const int T = (int) N1 / 16;
     for (n2 = 0; n2 < 256; ++n2) {
-      fft128_16x8(x + n2, 256, window ? window + n2 : NULL, 256, p->tw_a, col);
-      for (k1 = 0; k1 < 128; ++k1) {
+      fft16T(x + n2, 256, window ? window + n2 : NULL, 256, p->tw_a, T, col);
+      for (k1 = 0; k1 < N1; ++k1) {
         unsigned pw = n2 * k1;
         sdo_cpx tw = cmul(p->tw_a[pw >> 8], p->tw_n[pw & 255]);
         p->scr[(size_t) k1 * 256 + n2] = cmul(col[k1], tw);
       }
     }
-    for (k1 = 0; k1 < 128; ++k1) {
+    for (k1 = 0; k1 < N1; ++k1) {
       fft256_16x16(p->scr + (size_t) k1 * 256, 1, NULL, 0, p->tw_b, col);
-      for (n2 = 0; n2 < 256; ++n2) X[k1 + 128 * n2] = col[n2];
+      for (n2 = 0; n2 < 256; ++n2) X[k1 + (size_t) N1 * n2] = col[n2];
     }
     return;
   }

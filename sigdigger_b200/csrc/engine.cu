@@ -183,6 +183,7 @@ struct sdb_engine {
 static bool make_four_step(sdb_engine *e, unsigned N, SdbFourStep *fs)
 {
   int l = ilog2u(N), l1 = l / 2;
+  if (N == 32768 || N == 16384 || N == 8192) l1 = l - 8;        // SPEC F.5: N1 x 256 on the register-butterfly passes
   fs->N = (int) N; fs->N1 = 1 << l1; fs->N2 = (int) N / fs->N1;
   fs->twN1 = e->twiddle(fs->N1); fs->twN2 = e->twiddle(fs->N2); fs->twN = e->twiddle(N);
   fs->twPQ = nullptr;
@@ -207,23 +208,24 @@ static bool make_four_step(sdb_engine *e, unsigned N, SdbFourStep *fs)
     e->tw[0x10000u | 1u] = d;
     fs->twPQ = d;
   }
-  if (N == 32768) {
-    // SPEC F.5: 128 x 256, inter-pass twiddle [k1][n2] = W_128^(p >> 8) x W_32768^(p & 255), p = n2 k1
-    auto it = e->tw.find(0x8000u | 1u);
+  if (N == 32768 || N == 16384 || N == 8192) {
+    // SPEC F.5: N1 x 256, inter-pass twiddle [k1][n2] = W_N1^(p >> 8) x W_N^(p & 255), p = n2 k1
+    const unsigned N1 = N / 256;
+    auto it = e->tw.find(N | 1u);
     if (it != e->tw.end()) { fs->twPQ = it->second; return true; }
-    std::vector<float2> c, f, pq((size_t) 32768);
-    sdbh::twiddle_fill(128, c); sdbh::twiddle_fill(32768, f);
-    for (unsigned k1 = 0; k1 < 128; ++k1)
+    std::vector<float2> c, f, pq((size_t) N);
+    sdbh::twiddle_fill(N1, c); sdbh::twiddle_fill(N, f);
+    for (unsigned k1 = 0; k1 < N1; ++k1)
       for (unsigned n2 = 0; n2 < 256; ++n2) {
         const unsigned p = n2 * k1;
         const float2 a = c[p >> 8], b = f[p & 255];
         pq[(size_t) k1 * 256 + n2].x = fmaf(a.x, b.x, -(a.y * b.y));
         pq[(size_t) k1 * 256 + n2].y = fmaf(a.x, b.y, a.y * b.x);
       }
-    float2 *d = e->dalloc<float2>(32768);
+    float2 *d = e->dalloc<float2>(N);
     if (!d) return false;
-    cudaMemcpy(d, pq.data(), 32768 * sizeof(float2), cudaMemcpyHostToDevice);
-    e->tw[0x8000u | 1u] = d;
+    cudaMemcpy(d, pq.data(), (size_t) N * sizeof(float2), cudaMemcpyHostToDevice);
+    e->tw[N | 1u] = d;
     fs->twPQ = d;
   }
   return true;
@@ -596,14 +598,14 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       if (const char *env = getenv("SDB_SCRATCH_MB")) { long v = atol(env); if (v >= 1 && v <= 4096) scratch_mb = (size_t) v; }
       size_t cw = (scratch_mb << 20) / ((size_t) big * sizeof(float2));
       if (cw < 1) cw = 1;
-      if ((big == 65536 || big == 32768) && !getenv("SDB_SCRATCH_MB")) {
+      if ((big == 65536 || big == 32768 || big == 16384 || big == 8192) && !getenv("SDB_SCRATCH_MB")) {
         // 65536 path: 16 (pass A, 4 CTAs/SM) and 8 (pass B, 2 CTAs/SM) CTAs per window, all of equal duration:
         // one window per SM is exactly 4 waves of either kernel.  148 SMs -> 148 windows -> 77.6 MB, inside
         // the 82.9 MB of L2 that can be set aside for persisting lines on B200.
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->prm.device) == cudaSuccess && sms > 0 &&
             (size_t) sms * 65536 * sizeof(float2) <= (100u << 20))
-          cw = (size_t) sms * (65536 / big);          // the same 77.6 MB: two 32768-point windows per SM
+          cw = (size_t) sms * (65536 / big);          // the same 77.6 MB: two 32768-point windows per SM, ...
         e->sm_count = sms;
       }
       if (const char *env = getenv("SDB_CHUNK_WINDOWS")) { long v = atol(env); if (v >= 1 && v <= 65536) cw = (size_t) v; }
@@ -619,7 +621,7 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       // against 116 MB algorithmic, profiles/r01_l2.md).  Accesses of the transform streams inside the window
       // are "persisting" (a set-aside part of L2 that normal traffic cannot evict); the kernels additionally
       // mark their one-shot outputs as streaming (st.global.cs).
-      if ((big == 65536 || big == 32768) && !getenv("SDB_NO_L2_PIN")) {   // the set-aside is device-wide: only the big plans claim it
+      if ((big == 65536 || big == 32768 || big == 16384 || big == 8192) && !getenv("SDB_NO_L2_PIN")) {   // the set-aside is device-wide: only the big plans claim it
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->prm.device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->prm.device);
@@ -652,7 +654,8 @@ extern "C" int sdb_engine_commit(sdb_engine_t *e)
       for (unsigned i = 0; i < 2 * c.halfw; ++i) need[(c.center + W - c.halfw + i) % W] = 1;
     int nb = 0;
     e->ka_mask = 0;
-    const unsigned ka_shift = W == 32768 ? 7u : 8u;      // bin k = k1 + N1 (ka + 16 kb): N1 = 128 (F.5) or 256 (F.4)
+    // bin k = k1 + N1 (ka + 16 kb): N1 = 256 (F.4) or W / 256 (F.5); the generic passes ignore the mask
+    const unsigned ka_shift = W == 32768 ? 7u : (W == 16384 ? 6u : (W == 8192 ? 5u : 8u));
     for (unsigned b = 0; b < W; ++b) if (need[b]) { binmap[b] = nb++; e->ka_mask |= 1u << ((b >> ka_shift) & 15u); }
     e->n_bins = nb;
     e->d_binmap = e->dalloc<int>(W);
@@ -876,7 +879,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
     a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = nullptr; a.hist_len = 0;
     a.windows_per_stream = frames; a.first_window = 0; a.hop = (int) Np; a.base_off = 0;
     a.window = e->d_window; a.scratch = scr;
-    const bool fast = e->fs_psd.N2 == 256 && (e->fs_psd.N1 == 256 || e->fs_psd.N1 == 128);     // SPEC F.4 / F.5
+    const bool fast = e->fs_psd.N2 == 256 && e->fs_psd.N1 >= 32 && e->fs_psd.N1 <= 256;        // SPEC F.4 / F.5
     e->span_begin(FAM_COLS, lc.stream);
     if (fast && e->fs_psd.N1 == 256) CK(sdb_launch_cols256(lc, e->fs_psd, a, e->fs_psd.twN, w0, cw));
     else if (fast)                   CK(sdb_launch_cols128(lc, e->fs_psd, a, w0, cw));
@@ -896,7 +899,7 @@ extern "C" int sdb_engine_feed_device(sdb_engine_t *e, const sdb_complex *xv, si
     a.x = x; a.fmt = fmt; a.stream_stride = stride; a.hist = e->d_hist; a.hist_len = (int) (W / 2);
     a.windows_per_stream = wps; a.first_window = first; a.hop = (int) (W / 2); a.base_off = 0;
     a.window = nullptr; a.scratch = scr;
-    const bool fast = e->fs_st.N2 == 256 && (e->fs_st.N1 == 256 || e->fs_st.N1 == 128);
+    const bool fast = e->fs_st.N2 == 256 && e->fs_st.N1 >= 32 && e->fs_st.N1 <= 256;
     e->span_begin(FAM_COLS, lc.stream);
     if (fast && e->fs_st.N1 == 256) CK(sdb_launch_cols256(lc, e->fs_st, a, e->fs_st.twN, w0, cw));
     else if (fast)                  CK(sdb_launch_cols128(lc, e->fs_st, a, w0, cw));

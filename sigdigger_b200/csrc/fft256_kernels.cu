@@ -143,9 +143,10 @@ cudaError_t sdb_launch_cols256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// N = 32768 = 128 x 256 (SPEC F.5; BASELINE configs[3]).  Pass A: columns of 128 = 8 x 16 -- the same first butterfly
-// (fft16 over the high row digit), twiddle W_128^(t ka), exchange, then an 8-point butterfly (one radix-2 stage + two
-// DFT4) over the low row digit; pass B is k_rows256 with 128 rows per window.
+// N = 32768 / 16384 / 8192 = N1 x 256 with N1 = 16 T, T = 8 / 4 / 2 (SPEC F.5; BASELINE configs[3] and [0]).  Pass A:
+// columns of 16 T -- the same first butterfly (fft16 over the high row digit), twiddle W_N1^(t ka), exchange, then a
+// T-point butterfly over the low row digit (T = 8: one radix-2 stage + two DFT4); pass B is k_rows256 with N1 rows per
+// window.
 // forward 8-point DFT of v[0..7] (natural order in).  Result X[kb] is left in v[4 (kb & 1) + (kb >> 1)].
 static __device__ __forceinline__ void fft8(float2 (&v)[8])
 {
@@ -161,19 +162,24 @@ static __device__ __forceinline__ void fft8(float2 (&v)[8])
   fft4(v[4], v[5], v[6], v[7]);
 }
 #define REV8(p) (2 * ((p) & 3) + ((p) >> 2))
-#define LDC8 145   // pitch of one column's [ka][9] block (odd)
-
-__global__ void __launch_bounds__(128, 8) k_cols128(const Cols256K p)
+// Pass A for N1 = 16 T rows, T = 8 (N = 32768), 4 (16384), 2 (8192): 128-thread CTAs that own C = 128 / T adjacent columns
+// (thread = (column c, low row digit t)); the first butterfly is the 65536 kernel's fft16 over the high row digit, the
+// second a T-point butterfly over the low one, 16 / T of them per thread (ka = t + T h).
+template <int T>
+__global__ void __launch_bounds__(128, 8) k_cols16T(const Cols256K p)
 {
-  __shared__ float2 sm[16 * LDC8];
-  __shared__ float2 s_tw[128];
+  constexpr int C = 128 / T;                        // columns per CTA
+  constexpr int N1 = 16 * T;
+  constexpr int LD = 16 * (T + 1) + 1;              // pitch of one column's [ka][T + 1] block (odd)
+  __shared__ float2 sm[C * LD];
+  __shared__ float2 s_tw[N1];
   const int tid = threadIdx.x;
-  s_tw[tid] = __ldg(p.tw256 + tid);                 // W_128^i
-  const int c = tid & 15, t = tid >> 4;             // 16 columns x 8 low row digits
+  if (tid < N1) s_tw[tid] = __ldg(p.tw256 + tid);   // W_N1^i
+  const int c = tid % C, t = tid / C;
   const int w = p.win_base + blockIdx.y;
   const int stream = w / p.windows_per_stream;
   const int j0 = p.first_window + (w - stream * p.windows_per_stream);
-  const int col = blockIdx.x * 16 + c;
+  const int col = blockIdx.x * C + c;
   const long v0 = (long) p.base_off + (long) j0 * p.hop;
   const int fmt = p.fmt;
   const char *__restrict__ xs = reinterpret_cast<const char *>(p.x) + (size_t) stream * p.stream_stride * sdb_fmt_bytes(fmt);
@@ -183,11 +189,11 @@ __global__ void __launch_bounds__(128, 8) k_cols128(const Cols256K p)
   if (fmt == SDB_FMT_F32 && v0 >= p.hist_len) {     // CTA-uniform: the window lies wholly in the new samples
     const float2 *__restrict__ src = reinterpret_cast<const float2 *>(xs) + (v0 - p.hist_len) + t * 256 + col;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j * 2048);      // row n1 = t + 8 j
+    for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j * (T * 256));      // row n1 = t + T j
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const long vi = v0 + (long) (t + 8 * j) * 256 + col;
+      const long vi = v0 + (long) (t + T * j) * 256 + col;
       v[j] = vi < p.hist_len ? __ldg(hs + vi)
                              : (fmt == SDB_FMT_F32 ? __ldg(reinterpret_cast<const float2 *>(xs) + (vi - p.hist_len))
                                                    : sdb_ld_iq(xs, vi - p.hist_len, fmt));
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(128, 8) k_cols128(const Cols256K p)
   if (p.window) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float wv = __ldg(p.window + (t + 8 * j) * 256 + col);
+      const float wv = __ldg(p.window + (t + T * j) * 256 + col);
       v[j] = sdb_mul2(v[j], make_float2(wv, wv));
     }
   }
@@ -206,21 +212,24 @@ __global__ void __launch_bounds__(128, 8) k_cols128(const Cols256K p)
   for (int q = 0; q < 16; ++q) {
     const int ka = REV16(q);
     float2 y = v[q];
-    if (ka) y = cmulf(y, s_tw[t * ka]);             // W_128^(t ka)
-    sm[c * LDC8 + ka * 9 + t] = y;
+    if (ka) y = cmulf(y, s_tw[t * ka]);             // W_N1^(t ka)
+    sm[c * LD + ka * (T + 1) + t] = y;
   }
   __syncthreads();
-  float2 *__restrict__ out = p.scratch + (size_t) blockIdx.y * 32768;
+  float2 *__restrict__ out = p.scratch + (size_t) blockIdx.y * (N1 * 256);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {                     // second butterfly: thread (c, ka) gathers all t, two ka per thread
-    const int ka = t + 8 * h;
+  for (int h = 0; h < 16 / T; ++h) {                // second butterfly: thread (c, ka) gathers all t
+    const int ka = t + T * h;
     float2 u[8];
 #pragma unroll
-    for (int tt = 0; tt < 8; ++tt) u[tt] = sm[c * LDC8 + ka * 9 + tt];
-    fft8(u);                                        // over t: X[ka + 16 kb], kb = REV8(position)
+    for (int tt = 0; tt < T; ++tt) u[tt] = sm[c * LD + ka * (T + 1) + tt];
+    if (T == 8) fft8(u);                            // X[kb] at position REV8^-1: kb = REV8(position)
+    else if (T == 4) fft4(u[0], u[1], u[2], u[3]);  // natural order
+    else { const float2 a = cadd(u[0], u[1]), b = csub(u[0], u[1]); u[0] = a; u[1] = b; }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int k1 = ka + 16 * REV8(q);
+    for (int q = 0; q < T; ++q) {
+      const int kb = T == 8 ? REV8(q) : q;
+      const int k1 = ka + 16 * kb;
       out[(size_t) k1 * 256 + col] = cmulf(u[q], __ldg(p.twpq + k1 * 256 + col));   // SPEC F.5 inter-pass twiddle
     }
   }
@@ -233,8 +242,12 @@ cudaError_t sdb_launch_cols128(const SdbLaunchCtx &c, const SdbFourStep &fs, con
   p.windows_per_stream = a.windows_per_stream; p.first_window = a.first_window; p.hop = a.hop;
   p.base_off = a.base_off; p.win_base = win_base; p.window = a.window; p.scratch = a.scratch;
   p.tw256 = fs.twN1; p.twfine = nullptr; p.twpq = fs.twPQ;
-  dim3 grid(16, n_win);
-  k_cols128<<<grid, 128, 0, c.stream>>>(p);
+  const int T = fs.N1 / 16;                         // 8, 4 or 2: columns per CTA = 128 / T
+  dim3 grid(256 / (128 / T), n_win);
+  if (T == 8)      k_cols16T<8><<<grid, 128, 0, c.stream>>>(p);
+  else if (T == 4) k_cols16T<4><<<grid, 128, 0, c.stream>>>(p);
+  else if (T == 2) k_cols16T<2><<<grid, 128, 0, c.stream>>>(p);
+  else return cudaErrorInvalidValue;
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }
@@ -250,7 +263,8 @@ struct Rows256K {
 
 #define LDR 273
 
-// N1 = rows per window: 256 (N = 65536, SPEC F.4) or 128 (N = 32768, SPEC F.5); output bin k = k1 + N1 (ka + 16 kb)
+// N1 = rows per window: 256 (N = 65536, SPEC F.4) or 128 / 64 / 32 (N = 32768 / 16384 / 8192, SPEC F.5); output bin
+// k = k1 + N1 (ka + 16 kb)
 template <int MODE, int N1 = 256>
 __global__ void __launch_bounds__(512, 2) k_rows256(const Rows256K p)
 {
@@ -317,16 +331,19 @@ cudaError_t sdb_launch_rows256(const SdbLaunchCtx &c, const SdbFourStep &fs, con
     cudaFuncSetAttribute(k_rows256<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(k_rows256<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(k_rows256<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<0, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(k_rows256<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   }
-  if (fs.N1 == 128) {
-    dim3 grid(4, a.n_windows);
-    if (mode == 0) k_rows256<0, 128><<<grid, 512, smem, c.stream>>>(p);
-    else           k_rows256<1, 128><<<grid, 512, smem, c.stream>>>(p);
-  } else {
-    dim3 grid(8, a.n_windows);
-    if (mode == 0) k_rows256<0, 256><<<grid, 512, smem, c.stream>>>(p);
-    else           k_rows256<1, 256><<<grid, 512, smem, c.stream>>>(p);
+  dim3 grid(fs.N1 / 32, a.n_windows);               // 32 rows of the scratch per CTA
+#define ROWS_CASE(N1_) case N1_: if (mode == 0) k_rows256<0, N1_><<<grid, 512, smem, c.stream>>>(p); \
+                                 else           k_rows256<1, N1_><<<grid, 512, smem, c.stream>>>(p); break
+  switch (fs.N1) {
+    ROWS_CASE(256); ROWS_CASE(128); ROWS_CASE(64); ROWS_CASE(32);
+    default: return cudaErrorInvalidValue;
   }
+#undef ROWS_CASE
   if (c.launch_counter) ++*c.launch_counter;
   return cudaGetLastError();
 }
