@@ -229,3 +229,23 @@ def test_reference_shaped_worker_over_the_shim_is_bit_identical(oracle, interlac
                 sent = True
     assert k == got
     t.close()
+
+
+def test_c_abi_presets_equal_the_oracle_presets(oracle):
+    """sdb_tv_params_pal / _ntsc (host-only entry points of the C-ABI) fill the same block as the oracle's presets and
+    as the shim's su_tv_processor_params_* (modulo the shim's wider integer fields)."""
+    import sigdigger_b200 as sdb
+    L, T = sdb.load_library(), tv_lib()
+    for name in ("pal", "ntsc"):
+        for fs in (8e6, 13.5e6):
+            a, b = sdb.TvParams(), OL.TvParams()
+            getattr(L, "sdb_tv_params_" + name)(C.byref(a), fs)
+            getattr(T, "sdo_tv_params_" + name)(C.byref(b), fs)
+            assert bytes(a) == bytes(b)
+    su = C.CDLL(sdb.LIB_PATH.replace("libsigdigger_b200.so", "libsigutils.so"))
+    s = ShimTvParams()
+    su.su_tv_processor_params_pal.argtypes = [C.c_void_p, C.c_float]
+    su.su_tv_processor_params_pal(C.byref(s), 8e6)
+    b = OL.TvParams()
+    T.sdo_tv_params_pal(C.byref(b), 8e6)
+    assert all(getattr(s, n) == getattr(b, n) for n, _ in OL.TvParams._fields_)
