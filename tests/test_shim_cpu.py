@@ -81,3 +81,16 @@ def test_config_bag_round_trip():
     assert L.suscan_config_get_value(C.c_void_p(dup), b"clock.running")
     assert not L.suscan_config_get_value(C.c_void_p(dup), b"audio.volume")       # not a psk key
     L.suscan_config_destroy(C.c_void_p(cfg)); L.suscan_config_destroy(C.c_void_p(dup))
+
+
+def test_umbrella_header_compiles_as_c_and_cxx(tmp_path):
+    """<suscan.h> (Suscan/Library.cpp:24, Default/GenericInspector/InspectorUI.cpp:43) brings in the whole suscan-named
+    surface, as C and as C++"""
+    src = tmp_path / "umbrella.c"
+    src.write_text('#include <suscan.h>\n#include <sigutils/tvproc.h>\n#include <sigutils/softtune.h>\n'
+                   'int main(void) { struct sigutils_channel c = sigutils_channel_INITIALIZER; (void) c; '
+                   'return suscan_sigutils_init(0) ? 0 : 1; }\n')
+    inc = os.path.join(SB.ROOT, "include")
+    for cmd in (["gcc", "-std=gnu11", "-Wall", "-Werror"], ["g++", "-std=c++17", "-Wall", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
