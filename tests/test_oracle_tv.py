@@ -249,3 +249,47 @@ def test_c_abi_presets_equal_the_oracle_presets(oracle):
     b = OL.TvParams()
     T.sdo_tv_params_pal(C.byref(b), 8e6)
     assert all(getattr(s, n) == getattr(b, n) for n, _ in OL.TvParams._fields_)
+
+
+def test_free_running_raster_reverse_and_comb(oracle):
+    """SPEC TV.2 / TV.6 without the sync separator: the raster free-runs at line_len, `reverse` shows x instead of
+    1 - x (the sub-pixel weights of a pixel sum to one), and the comb filter removes a component that alternates from
+    line to line (what it is there for: the chroma sub-carrier of a composite signal)."""
+    lines = 20
+    p = toy_params(lines, False, 4)
+    p.enable_sync, p.enable_agc, p.line_len = 0, 0, 64.0                # integer line length: pixels = samples
+    n = 64 * lines * 3
+    rng = np.random.default_rng(7)
+    x = rng.uniform(0.1, 0.9, n).astype(np.float32)
+    t = OracleTv(p)
+    assert t.feed(x) == 3                                               # exactly one frame per 64 * 20 samples
+    f0 = t.frame(0)
+    assert np.array_equal(f0.ravel(), (np.float32(1.0) - x[:64 * lines]))    # d = 0: pixel n = 1 - x[n]
+    t.close()
+    p.reverse = 1
+    t = OracleTv(p)
+    t.feed(x)
+    assert np.array_equal(t.frame(0).ravel(), x[:64 * lines])
+    t.close()
+    # fractional line length: every pixel is the (1 - d, d) blend of two consecutive samples
+    p.reverse, p.line_len = 0, 64.5
+    t = OracleTv(p)
+    t.feed(x)
+    row1 = t.frame(0)[1]                # 65 samples went into the first line; sample 65 lands at x = 0.5 of the second
+    want = 1.0 - (0.5 * x[65:65 + 63].astype(np.float64) + 0.5 * x[66:66 + 63])      # pixel k = (v[64 + k] + v[65 + k]) / 2
+    assert np.max(np.abs(row1[1:64] - want)) < 1e-6
+    t.close()
+    # comb: luma repeats line after line, "chroma" flips sign every line -> (x + previous line) / 2 keeps the luma
+    p.line_len, p.enable_comb, p.comb_reverse = 64.0, 1, 0
+    luma = np.tile(rng.uniform(0.2, 0.6, 64), lines * 2)
+    chroma = 0.2 * np.tile(np.concatenate([np.ones(64), -np.ones(64)]), lines)
+    t = OracleTv(p)
+    t.feed((luma + chroma).astype(np.float32))
+    fr = t.frame(1)                                                     # past the first (unfilled delay line) frame
+    assert np.max(np.abs((1.0 - fr[3]) - luma[:64])) < 1e-6
+    p.comb_reverse = 1                                                  # the other output of the comb: the chroma
+    t2 = OracleTv(p)
+    t2.feed((luma + chroma).astype(np.float32))
+    assert np.max(np.abs(np.abs(1.0 - t2.frame(1)[3]) - 0.2)) < 1e-6
+    t.close()
+    t2.close()
